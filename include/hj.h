@@ -1,0 +1,308 @@
+/*
+ * hj.h — C ABI of the B200-native (sm_100a) execution backend for hephaestus-jit.
+ *
+ * This is the drop-in boundary: exactly the entry points a Rust
+ * `CudaDevice: BackendDevice` / `CudaBuffer: BackendBuffer` (the `todo!()` stubs at
+ * hephaestus-jit/src/backend/cuda/mod.rs:16-73 and the `todo!()` arms at
+ * hephaestus-jit/src/backend/mod.rs:104,112,118) would bind through `extern "C"`.
+ * Plain pointers and sizes only; no torch / C++ types cross this line.
+ * INTEGRATION.md shows the Rust-side binding.
+ *
+ * Conventions
+ *   - every function returns hj_status (0 = ok); the message of the last failure on the
+ *     calling thread is available through hj_last_error().
+ *   - hj_device / hj_buffer / hj_kernel / hj_graph are intrusively ref-counted handles
+ *     (the reference clones Arc<Buffer> freely: backend/vulkan/mod.rs:461-465).
+ *   - all work is enqueued on the device's stream; calls that return data to the host
+ *     (hj_buffer_to_host, hj_device_sync) block until it is visible, every other call is
+ *     stream-ordered and asynchronous.  The reference blocks on a fence after every
+ *     execute_graph (vulkan_core/device.rs:297-334); stream order gives the same
+ *     observable behaviour to `to_host`.
+ *   - there is NO CPU fallback: without a CUDA device every compute entry point fails
+ *     with HJ_ERR_NO_DEVICE.
+ */
+#ifndef HJ_H
+#define HJ_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef int32_t hj_status;
+enum {
+    HJ_OK = 0,
+    HJ_ERR_INVALID = 1,      /* bad argument (null handle, n == 0, size mismatch, ...)        */
+    HJ_ERR_UNSUPPORTED = 2,  /* (op, type) pair the reference marks todo!() (reduce.rs:84-166) */
+    HJ_ERR_CUDA = 3,         /* a CUDA runtime / driver call failed                            */
+    HJ_ERR_NVRTC = 4,        /* runtime compilation of a fused kernel failed                   */
+    HJ_ERR_NCCL = 5,         /* NCCL failure or libnccl not loadable                           */
+    HJ_ERR_NO_DEVICE = 6,    /* no CUDA device / driver present                                */
+    HJ_ERR_OOM = 7
+};
+
+/* Scalar element types; numbering follows the declaration order of `VarType`
+ * (hephaestus-jit/src/vartype.rs:89-104). */
+typedef enum {
+    HJ_VOID = 0, HJ_BOOL = 1, HJ_I8 = 2, HJ_U8 = 3, HJ_I16 = 4, HJ_U16 = 5, HJ_I32 = 6,
+    HJ_U32 = 7, HJ_I64 = 8, HJ_U64 = 9, HJ_F16 = 10, HJ_F32 = 11, HJ_F64 = 12,
+    /* composite kinds, only used inside hj_type_desc */
+    HJ_VEC = 13, HJ_ARRAY = 14, HJ_MAT = 15, HJ_STRUCT = 16
+} hj_type_kind;
+
+/* Reduction operators; numbering follows `ReduceOp` (hephaestus-jit/src/op.rs:90-99). */
+typedef enum {
+    HJ_REDUCE_MAX = 0, HJ_REDUCE_MIN = 1, HJ_REDUCE_SUM = 2, HJ_REDUCE_PROD = 3,
+    HJ_REDUCE_OR = 4, HJ_REDUCE_AND = 5, HJ_REDUCE_XOR = 6
+} hj_reduce_op;
+
+typedef struct hj_device hj_device;
+typedef struct hj_buffer hj_buffer;
+typedef struct hj_kernel hj_kernel;
+
+const char* hj_last_error(void);
+/* Library/ABI version, bumped on every incompatible change. */
+uint32_t hj_abi_version(void);
+/* Number of visible CUDA devices (0 without a driver; never fails). */
+int32_t hj_device_count(void);
+
+/* ---- device --------------------------------------------------------------------------
+ * replaces CudaDevice::create (backend/cuda/mod.rs:16-19); devices are process-global
+ * singletons per ordinal like VulkanDevice::create (backend/vulkan/mod.rs:94-113). */
+hj_status hj_device_create(int32_t ordinal, hj_device** out);
+hj_status hj_device_retain(hj_device* dev);
+hj_status hj_device_release(hj_device* dev);
+hj_status hj_device_sync(hj_device* dev);
+/* The cudaStream_t all work of this device is enqueued on. */
+hj_status hj_device_stream(hj_device* dev, void** out_stream);
+/* Enqueue on a caller-owned stream instead (e.g. torch's current stream); NULL restores
+ * the device's own stream. */
+hj_status hj_device_set_stream(hj_device* dev, void* stream);
+hj_status hj_device_info(hj_device* dev, int32_t* sm_count, int32_t* cc_major, int32_t* cc_minor,
+                         uint64_t* total_mem, uint64_t* l2_bytes);
+/* Pool statistics (the reference's ResourcePool, vulkan_core/pool.rs:52-66). */
+hj_status hj_device_pool_stats(hj_device* dev, uint64_t* bytes_live, uint64_t* bytes_cached,
+                               uint64_t* n_alloc, uint64_t* n_reuse);
+hj_status hj_device_pool_trim(hj_device* dev);
+/* Number of kernel launches this library has enqueued on `dev` since creation. */
+hj_status hj_device_launch_count(hj_device* dev, uint64_t* out);
+
+/* ---- buffers -------------------------------------------------------------------------
+ * replaces BackendDevice::create_buffer / create_buffer_from_slice
+ * (backend/mod.rs:30-31, backend/vulkan/mod.rs:129-148,427-452) and
+ * BackendBuffer::to_host (backend/mod.rs:39, backend/vulkan/mod.rs:478-509).
+ * Contents of a fresh buffer are unspecified (recycled pool memory, pool.rs:36-41). */
+hj_status hj_buffer_create(hj_device* dev, size_t bytes, hj_buffer** out);
+hj_status hj_buffer_create_from_slice(hj_device* dev, const void* data, size_t bytes,
+                                      hj_buffer** out);
+/* Non-owning view over device memory someone else allocated (e.g. a torch tensor). */
+hj_status hj_buffer_wrap(hj_device* dev, void* device_ptr, size_t bytes, hj_buffer** out);
+hj_status hj_buffer_retain(hj_buffer* buf);
+hj_status hj_buffer_release(hj_buffer* buf);
+hj_status hj_buffer_to_host(hj_buffer* buf, size_t offset_bytes, size_t nbytes, void* dst);
+/* Stream-ordered host->device copy into an existing buffer (no allocation). */
+hj_status hj_buffer_upload(hj_buffer* buf, size_t offset_bytes, const void* src, size_t nbytes);
+hj_status hj_buffer_fill_zero(hj_buffer* buf);
+hj_status hj_buffer_device_ptr(hj_buffer* buf, void** out);
+hj_status hj_buffer_size(hj_buffer* buf, size_t* out_bytes);
+hj_status hj_buffer_device(hj_buffer* buf, hj_device** out); /* borrowed, not retained */
+/* Pinned host staging memory for the end-to-end path. */
+hj_status hj_host_alloc(size_t bytes, void** out);
+hj_status hj_host_free(void* ptr);
+
+/* ---- device ops (hand-written sm_100a kernels) ---------------------------------------
+ * Direct entry points for the three DeviceOp passes execute_graph dispatches to
+ * (backend/vulkan/mod.rs:259-299).  `n` is the element count of `src`. */
+
+/* dst[0] = fold(op, src[0..n)); replaces builtin::reduce::reduce (builtin/reduce.rs:22-314).
+ * Integer results are exact (wrapping); f32/f64 sums are reordered (tolerance in DESIGN.md). */
+hj_status hj_reduce(hj_device* dev, hj_reduce_op op, hj_type_kind ty, size_t n,
+                    hj_buffer* src, hj_buffer* dst);
+/* dst[i] = sum(src[0..=i]) (inclusive) or sum(src[0..i)) (exclusive); replaces
+ * builtin::prefix_sum::prefix_sum_large (builtin/prefix_sum.rs:31-162).
+ * `seed` (may be NULL) is a 1-element device buffer added to every output: the cross-GPU
+ * offset of a sharded scan. */
+hj_status hj_prefix_sum(hj_device* dev, hj_type_kind ty, size_t n, int32_t inclusive,
+                        hj_buffer* src, hj_buffer* dst, hj_buffer* seed);
+/* index_out[0..count) = ascending positions of non-zero mask bytes, out_count[0] = count;
+ * replaces builtin::compress::compress_large (builtin/compress.rs:157-283).
+ * Elements of index_out at and beyond `count` are left untouched, exactly like the
+ * reference (they stay zero from the scheduler's zero-fill pass, trace.rs:1600-1601).
+ * `size_buf` (may be NULL) holds a device-resident u32 element count <= n (DynSize).
+ * `index_base` is added to every emitted index (shard offset, 0 on a single GPU). */
+hj_status hj_compress(hj_device* dev, size_t n, hj_buffer* size_buf, hj_buffer* out_count,
+                      hj_buffer* src_mask, hj_buffer* index_out, uint32_t index_base);
+/* dst[idx[i]] = op(dst[idx[i]], value) for i in 0..n  — the ScatterReduce kernel op
+ * (codegen/glsl/mod.rs:400-446) specialised for the histogram shape: `src` is either a
+ * buffer of n values or NULL (then `literal` is the u64 bit pattern of the value).
+ * Supported: op Sum/Min/Max/Or/And/Xor, ty U32/I32/F32(sum)/U64(sum). */
+hj_status hj_scatter_reduce(hj_device* dev, hj_reduce_op op, hj_type_kind ty, size_t n,
+                            hj_buffer* idx, hj_buffer* src, uint64_t literal,
+                            hj_buffer* dst, size_t n_dst);
+/* dst[i] = src[idx[i]] for i in 0..n (Gather kernel op, codegen/glsl/mod.rs:523-579),
+ * elem_bytes in {1,2,4,8,16}. */
+hj_status hj_gather(hj_device* dev, size_t elem_bytes, size_t n, hj_buffer* src,
+                    hj_buffer* idx, hj_buffer* dst);
+
+/* ---- fused-kernel IR (NVRTC path) ----------------------------------------------------
+ * Flat mirror of `IR` / `ir::Var` (hephaestus-jit/src/ir.rs:12-46) and of the interned
+ * `VarType` tree (vartype.rs:89-122). */
+
+/* One node of the type table.  Scalars: kind only.  Vec/Array: elem + num.
+ * Mat: elem + cols + rows.  Struct: `num` field types at struct_fields[first_field..]. */
+typedef struct {
+    uint32_t kind;        /* hj_type_kind */
+    uint32_t elem;        /* index into types[] (Vec/Array/Mat) */
+    uint32_t num;         /* Vec/Array length, Struct field count */
+    uint32_t cols, rows;  /* Mat */
+    uint32_t first_field; /* Struct: offset into struct_fields[] */
+} hj_type_desc;
+
+/* KernelOp tags (hephaestus-jit/src/op.rs:49-88), `arg` carries the payload. */
+typedef enum {
+    HJ_OP_NOP = 0, HJ_OP_SCATTER = 1,
+    HJ_OP_SCATTER_REDUCE = 2,  /* arg = hj_reduce_op */
+    HJ_OP_SCATTER_ATOMIC = 3,  /* arg = hj_reduce_op */
+    HJ_OP_ATOMIC_INC = 4, HJ_OP_GATHER = 5, HJ_OP_INDEX = 6, HJ_OP_LITERAL = 7,
+    HJ_OP_EXTRACT = 8,         /* arg = element */
+    HJ_OP_DYN_EXTRACT = 9, HJ_OP_CONSTRUCT = 10, HJ_OP_SELECT = 11,
+    HJ_OP_LOOP_START = 12, HJ_OP_LOOP_END = 13, HJ_OP_IF_START = 14, HJ_OP_IF_END = 15,
+    HJ_OP_TEX_LOOKUP = 16, HJ_OP_TRACE_RAY = 17, /* out of scope: rejected */
+    HJ_OP_BOP = 18,            /* arg = hj_bop */
+    HJ_OP_UOP = 19,            /* arg = hj_uop */
+    HJ_OP_FMA = 20, HJ_OP_BUFFER_REF = 21,
+    HJ_OP_TEXTURE_REF = 22, HJ_OP_ACCEL_REF = 23 /* out of scope: rejected */
+} hj_kernel_op;
+
+/* Bop / Uop numbering follows op.rs:2-31 / op.rs:33-46. */
+typedef enum {
+    HJ_BOP_ADD = 0, HJ_BOP_SUB, HJ_BOP_MUL, HJ_BOP_DIV, HJ_BOP_MODULUS, HJ_BOP_MIN, HJ_BOP_MAX,
+    HJ_BOP_INNER, HJ_BOP_AND, HJ_BOP_OR, HJ_BOP_XOR, HJ_BOP_SHL, HJ_BOP_SHR,
+    HJ_BOP_EQ, HJ_BOP_NEQ, HJ_BOP_LT, HJ_BOP_LE, HJ_BOP_GT, HJ_BOP_GE
+} hj_bop;
+typedef enum {
+    HJ_UOP_CAST = 0, HJ_UOP_BITCAST, HJ_UOP_NEG, HJ_UOP_SQRT, HJ_UOP_ABS, HJ_UOP_SIN,
+    HJ_UOP_COS, HJ_UOP_EXP2, HJ_UOP_LOG2
+} hj_uop;
+
+typedef struct {
+    uint32_t ty;        /* index into types[] */
+    uint32_t op;        /* hj_kernel_op */
+    uint32_t arg;       /* op payload */
+    uint32_t dep_start; /* deps[dep_start..dep_end) */
+    uint32_t dep_end;
+    uint32_t _pad;
+    uint64_t data;      /* literal bits / buffer slot (ir.rs:16) */
+} hj_ir_var;
+
+typedef struct {
+    const hj_ir_var* vars;
+    uint32_t n_vars;
+    const uint32_t* deps;
+    uint32_t n_deps;
+    const hj_type_desc* types;
+    uint32_t n_types;
+    const uint32_t* struct_fields;
+    uint32_t n_struct_fields;
+    uint32_t n_buffers;
+} hj_ir;
+
+/* Content hash of an IR (the kernel-cache key; plays the role of Prehashed<IR>,
+ * prehashed.rs:9-26).  Stable across processes. */
+uint64_t hj_ir_hash(const hj_ir* ir);
+/* Lower an IR to CUDA C++ (what the NVRTC stage compiles).  Returns a malloc'ed,
+ * NUL-terminated string the caller frees with hj_free_string. Works without a GPU. */
+hj_status hj_ir_codegen(const hj_ir* ir, char** out_source);
+void hj_free_string(char* s);
+/* Compile (or fetch from the per-device cache keyed by IR hash) the fused kernel for
+ * `ir`; replaces VulkanDevice::compile_ir + Pipeline::create
+ * (backend/vulkan/mod.rs:83-91, vulkan_core/pipeline.rs:30-46). */
+hj_status hj_kernel_get(hj_device* dev, const hj_ir* ir, hj_kernel** out);
+hj_status hj_kernel_release(hj_kernel* k);
+/* Compile `ir` to an sm_100a cubin without a device (build check / cache warm-up).
+ * The cubin is malloc'ed; free with hj_free_string((char*)cubin). */
+hj_status hj_ir_compile_cubin(const hj_ir* ir, void** out_cubin, size_t* out_size);
+/* Launch over `size` elements (or the device-resident u32 in `size_buf` if non-NULL,
+ * capped by `size`), buffers in IR slot order; replaces the Kernel arm of execute_graph
+ * (backend/vulkan/mod.rs:194-257).  `index_base` offsets KernelOp::Index (sharding). */
+hj_status hj_kernel_launch(hj_device* dev, hj_kernel* k, size_t size, hj_buffer* size_buf,
+                           hj_buffer* const* buffers, uint32_t n_buffers, uint32_t index_base);
+/* cache statistics: compiled (misses) / hits, and on-disk cubin cache hits */
+hj_status hj_device_kernel_cache_stats(hj_device* dev, uint64_t* n_compiled, uint64_t* n_hits,
+                                       uint64_t* n_disk_hits);
+
+/* ---- execute_graph -------------------------------------------------------------------
+ * replaces BackendDevice::execute_graph (backend/mod.rs:33, backend/vulkan/mod.rs:151-383).
+ * The pass list is what Graph::passes() exposes (graph.rs:409-425). */
+typedef enum {
+    HJ_PASS_KERNEL = 0, HJ_PASS_REDUCE = 1, HJ_PASS_PREFIX_SUM = 2, HJ_PASS_COMPRESS = 3
+} hj_pass_kind;
+
+typedef struct {
+    uint32_t kind;            /* hj_pass_kind */
+    uint32_t arg;             /* reduce: hj_reduce_op; prefix sum: inclusive flag */
+    const uint32_t* resources; /* ResourceId list in the reference's order (see hj.h top of
+                                  section): kernel = IR slot order; reduce/scan = [dst, src];
+                                  compress = [index_out, out_count, src] */
+    uint32_t n_resources;
+    int32_t size_buffer;      /* ResourceId of the DynSize buffer, or -1 */
+    const hj_ir* ir;          /* kernel passes */
+    uint64_t size;            /* kernel passes: static element count */
+} hj_pass;
+
+typedef struct {
+    uint64_t size; /* elements */
+    uint32_t ty;   /* hj_type_kind of the element (scalars) or HJ_STRUCT etc. */
+    uint32_t elem_bytes;
+} hj_buffer_desc;
+
+/* Per-pass timing, mirror of PassReport/ExecReport (backend/report.rs:2-19). */
+typedef struct {
+    char name[64];
+    double start_us;
+    double duration_us;
+} hj_pass_report;
+typedef struct {
+    double cpu_duration_us;
+    uint32_t n_passes;
+    hj_pass_report* passes; /* caller-provided array of >= n_passes entries, or NULL */
+    uint32_t passes_capacity;
+} hj_report;
+
+hj_status hj_execute_graph(hj_device* dev, const hj_pass* passes, uint32_t n_passes,
+                           hj_buffer* const* env, const hj_buffer_desc* descs,
+                           uint32_t n_resources, hj_report* report /* may be NULL */);
+
+/* ---- sharded (multi-GPU) ops ---------------------------------------------------------
+ * One process per GPU; `hj_comm` wraps an NCCL communicator created from a unique id the
+ * host distributes (torch.distributed store / broadcast).  The reference has no multi-GPU
+ * code; these combine per-GPU partials exactly as BASELINE.json names. */
+typedef struct hj_comm hj_comm;
+#define HJ_UNIQUE_ID_BYTES 128
+hj_status hj_comm_unique_id(uint8_t out_id[HJ_UNIQUE_ID_BYTES]);
+hj_status hj_comm_create(hj_device* dev, const uint8_t id[HJ_UNIQUE_ID_BYTES], int32_t rank,
+                         int32_t world, hj_comm** out);
+hj_status hj_comm_destroy(hj_comm* comm);
+/* local reduce of this rank's shard, then all-reduce of the partials: dst[0] on every rank
+ * holds the global result. */
+hj_status hj_sharded_reduce(hj_comm* comm, hj_reduce_op op, hj_type_kind ty, size_t n_local,
+                            hj_buffer* src, hj_buffer* dst);
+/* shard totals -> all-gather -> exclusive offset -> seeded local scan. */
+hj_status hj_sharded_prefix_sum(hj_comm* comm, hj_type_kind ty, size_t n_local,
+                                int32_t inclusive, hj_buffer* src, hj_buffer* dst);
+/* local compress with global indices (index_base = global start of the shard); all-gather
+ * of the counts: counts_out[world] (u32, device) and out_count[0] = global count. */
+hj_status hj_sharded_compress(hj_comm* comm, size_t n_local, uint32_t index_base,
+                              hj_buffer* src_mask, hj_buffer* index_out, hj_buffer* out_count,
+                              hj_buffer* counts_out);
+/* privatised local histogram, then all-reduce (sum) of the n_dst bins. */
+hj_status hj_sharded_scatter_reduce(hj_comm* comm, hj_reduce_op op, hj_type_kind ty,
+                                    size_t n_local, hj_buffer* idx, hj_buffer* src,
+                                    uint64_t literal, hj_buffer* dst, size_t n_dst);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HJ_H */
