@@ -1,0 +1,190 @@
+"""hephaestus-jit_b200 — B200-native (sm_100a) execution backend for hephaestus-jit.
+
+Host-side mirror of the reference's backend interface
+(hephaestus-jit/src/backend/mod.rs:26-155: ``Device`` / ``Buffer``) over the C ABI in
+include/hj.h.  The directory name contains a hyphen, so import it with
+``importlib.import_module("hephaestus-jit_b200")`` (tests/ and bench.py do).
+
+Nothing here computes on the CPU: every operation is a call into libhj_b200.so, which
+enqueues hand-written or NVRTC-compiled sm_100a kernels.  Without the shared library the
+import fails; without a CUDA device ``Device.cuda`` raises ``HjError(ERR_NO_DEVICE)``.
+"""
+from __future__ import annotations
+
+import ctypes
+
+import numpy as np
+
+from . import _lib
+from ._lib import HjError, check, lib
+
+__all__ = ["Device", "Buffer", "HjError", "device_count", "VOID", "BOOL", "I8", "U8", "I16", "U16",
+           "I32", "U32", "I64", "U64", "F16", "F32", "F64", "MAX", "MIN", "SUM", "PROD", "OR", "AND",
+           "XOR", "dtype_of", "type_of_dtype"]
+
+# hj_type_kind — order of VarType (vartype.rs:89-104)
+VOID, BOOL, I8, U8, I16, U16, I32, U32, I64, U64, F16, F32, F64 = range(13)
+VEC, ARRAY, MAT, STRUCT = 13, 14, 15, 16
+# hj_reduce_op — order of ReduceOp (op.rs:90-99)
+MAX, MIN, SUM, PROD, OR, AND, XOR = range(7)
+
+_NP = {BOOL: np.bool_, I8: np.int8, U8: np.uint8, I16: np.int16, U16: np.uint16, I32: np.int32,
+       U32: np.uint32, I64: np.int64, U64: np.uint64, F16: np.float16, F32: np.float32,
+       F64: np.float64}
+_FROM_NP = {np.dtype(v): k for k, v in _NP.items()}
+TYPE_SIZE = {VOID: 0, BOOL: 1, I8: 1, U8: 1, I16: 2, U16: 2, I32: 4, U32: 4, I64: 8, U64: 8, F16: 2,
+             F32: 4, F64: 8}
+
+
+def dtype_of(ty: int) -> np.dtype:
+    return np.dtype(_NP[ty])
+
+
+def type_of_dtype(dt) -> int:
+    return _FROM_NP[np.dtype(dt)]
+
+
+def device_count() -> int:
+    return int(lib.hj_device_count())
+
+
+class Buffer:
+    """Mirror of ``backend::Buffer`` (backend/mod.rs:131-155): a ref-counted device allocation."""
+
+    __slots__ = ("_h", "device", "__weakref__")
+
+    def __init__(self, handle: int, device: "Device"):
+        self._h = ctypes.c_void_p(handle)
+        self.device = device
+
+    def __del__(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h:
+            lib.hj_buffer_release(h)
+
+    @property
+    def handle(self) -> ctypes.c_void_p:
+        return self._h
+
+    @property
+    def size(self) -> int:
+        out = ctypes.c_size_t()
+        check(lib.hj_buffer_size(self._h, ctypes.byref(out)))
+        return out.value
+
+    @property
+    def ptr(self) -> int:
+        out = ctypes.c_void_p()
+        check(lib.hj_buffer_device_ptr(self._h, ctypes.byref(out)))
+        return out.value or 0
+
+    def to_host(self, dtype, start: int = 0, end: int | None = None) -> np.ndarray:
+        """``BackendBuffer::to_host::<T>(range)`` (backend/mod.rs:39): element range -> host."""
+        dt = np.dtype(dtype)
+        if end is None:
+            end = self.size // dt.itemsize
+        n = max(0, end - start)
+        out = np.empty(n, dtype=dt)
+        check(lib.hj_buffer_to_host(self._h, start * dt.itemsize, n * dt.itemsize,
+                                    out.ctypes.data_as(ctypes.c_void_p)))
+        return out
+
+    def upload(self, data: np.ndarray, offset_bytes: int = 0) -> None:
+        data = np.ascontiguousarray(data)
+        check(lib.hj_buffer_upload(self._h, offset_bytes, data.ctypes.data_as(ctypes.c_void_p),
+                                   data.nbytes))
+
+    def fill_zero(self) -> None:
+        check(lib.hj_buffer_fill_zero(self._h))
+
+
+class Device:
+    """Mirror of ``backend::Device`` (backend/mod.rs:66-126), CUDA arm."""
+
+    def __init__(self, handle: int, ordinal: int):
+        self._h = ctypes.c_void_p(handle)
+        self.ordinal = ordinal
+
+    @staticmethod
+    def cuda(ordinal: int = 0) -> "Device":
+        """``Device::cuda(id)`` (backend/mod.rs:73-75)."""
+        out = ctypes.c_void_p()
+        check(lib.hj_device_create(ordinal, ctypes.byref(out)))
+        return Device(out.value, ordinal)
+
+    @property
+    def handle(self) -> ctypes.c_void_p:
+        return self._h
+
+    # -- buffers ------------------------------------------------------------------------
+    def create_buffer(self, size: int) -> Buffer:
+        out = ctypes.c_void_p()
+        check(lib.hj_buffer_create(self._h, size, ctypes.byref(out)))
+        return Buffer(out.value, self)
+
+    def create_buffer_from_slice(self, data) -> Buffer:
+        a = np.ascontiguousarray(data)
+        out = ctypes.c_void_p()
+        check(lib.hj_buffer_create_from_slice(self._h, a.ctypes.data_as(ctypes.c_void_p), a.nbytes,
+                                              ctypes.byref(out)))
+        return Buffer(out.value, self)
+
+    def wrap(self, device_ptr: int, nbytes: int) -> Buffer:
+        out = ctypes.c_void_p()
+        check(lib.hj_buffer_wrap(self._h, ctypes.c_void_p(device_ptr), nbytes, ctypes.byref(out)))
+        return Buffer(out.value, self)
+
+    # -- control ------------------------------------------------------------------------
+    def sync(self) -> None:
+        check(lib.hj_device_sync(self._h))
+
+    @property
+    def stream(self) -> int:
+        out = ctypes.c_void_p()
+        check(lib.hj_device_stream(self._h, ctypes.byref(out)))
+        return out.value or 0
+
+    def set_stream(self, stream: int | None) -> None:
+        check(lib.hj_device_set_stream(self._h, ctypes.c_void_p(stream or 0)))
+
+    def info(self) -> dict:
+        sm, ma, mi = ctypes.c_int32(), ctypes.c_int32(), ctypes.c_int32()
+        mem, l2 = ctypes.c_uint64(), ctypes.c_uint64()
+        check(lib.hj_device_info(self._h, ctypes.byref(sm), ctypes.byref(ma), ctypes.byref(mi),
+                                 ctypes.byref(mem), ctypes.byref(l2)))
+        return {"sm_count": sm.value, "cc": (ma.value, mi.value), "total_mem": mem.value,
+                "l2_bytes": l2.value}
+
+    def pool_stats(self) -> dict:
+        v = [ctypes.c_uint64() for _ in range(4)]
+        check(lib.hj_device_pool_stats(self._h, *[ctypes.byref(x) for x in v]))
+        return dict(zip(("bytes_live", "bytes_cached", "n_alloc", "n_free"), (x.value for x in v)))
+
+    def launch_count(self) -> int:
+        out = ctypes.c_uint64()
+        check(lib.hj_device_launch_count(self._h, ctypes.byref(out)))
+        return out.value
+
+    # -- device ops (direct entry points; execute_graph dispatches to the same kernels) ----
+    def reduce(self, op: int, ty: int, n: int, src: Buffer, dst: Buffer) -> None:
+        check(lib.hj_reduce(self._h, op, ty, n, src.handle, dst.handle))
+
+    def prefix_sum(self, ty: int, n: int, inclusive: bool, src: Buffer, dst: Buffer,
+                   seed: Buffer | None = None) -> None:
+        check(lib.hj_prefix_sum(self._h, ty, n, int(inclusive), src.handle, dst.handle,
+                                seed.handle if seed else None))
+
+    def compress(self, n: int, out_count: Buffer, src_mask: Buffer, index_out: Buffer,
+                 size_buf: Buffer | None = None, index_base: int = 0) -> None:
+        check(lib.hj_compress(self._h, n, size_buf.handle if size_buf else None, out_count.handle,
+                              src_mask.handle, index_out.handle, index_base))
+
+    def scatter_reduce(self, op: int, ty: int, n: int, idx: Buffer, src: Buffer | None, literal,
+                       dst: Buffer, n_dst: int) -> None:
+        lit = int(np.array([literal], dtype=_NP[ty]).view(
+            {1: np.uint8, 2: np.uint16, 4: np.uint32, 8: np.uint64}[TYPE_SIZE[ty]])[0])
+        check(lib.hj_scatter_reduce(self._h, op, ty, n, idx.handle, src.handle if src else None, lit,
+                                    dst.handle, n_dst))
+
+    def gather(self, elem_bytes: int, n: int, src: Buffer, idx: Buffer, dst: Buffer) -> None:
+        check(lib.hj_gather(self._h, elem_bytes, n, src.handle, idx.handle, dst.handle))

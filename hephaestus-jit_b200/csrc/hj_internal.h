@@ -1,0 +1,126 @@
+// hj_internal.h — shared internals of libhj_b200.so (not part of the C ABI).
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/hj.h"
+
+namespace hj {
+
+// ---- error plumbing ---------------------------------------------------------------------
+void set_error(const char* fmt, ...);
+hj_status fail(hj_status code, const char* fmt, ...);
+
+#define HJ_CUDA(expr)                                                                     \
+    do {                                                                                  \
+        cudaError_t _e = (expr);                                                          \
+        if (_e != cudaSuccess) {                                                          \
+            cudaGetLastError();                                                           \
+            return ::hj::fail(_e == cudaErrorMemoryAllocation ? HJ_ERR_OOM : HJ_ERR_CUDA, \
+                              "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e),     \
+                              __FILE__, __LINE__);                                        \
+        }                                                                                 \
+    } while (0)
+
+#define HJ_TRY(expr)                        \
+    do {                                    \
+        hj_status _s = (expr);              \
+        if (_s != HJ_OK) return _s;         \
+    } while (0)
+
+#define HJ_REQUIRE(cond, ...)                                  \
+    do {                                                       \
+        if (!(cond)) return ::hj::fail(HJ_ERR_INVALID, __VA_ARGS__); \
+    } while (0)
+
+size_t type_size(hj_type_kind ty);
+const char* type_name(hj_type_kind ty);
+const char* reduce_op_name(hj_reduce_op op);
+
+struct KernelCache;  // jit.cpp
+
+// Persistent per-device scratch of the decoupled-look-back kernels (scan, compress).
+// Status words carry an epoch so the buffer never has to be cleared between launches.
+struct LookbackScratch {
+    void* base = nullptr;   // layout: lookback.cuh (ticket | status words | aggregates | inclusives)
+    size_t bytes = 0;
+    size_t capacity_tiles = 0;
+    uint32_t epoch = 0;     // last epoch handed out; valid epochs are 1 .. 2^30-1
+};
+
+}  // namespace hj
+
+struct hj_device {
+    std::atomic<int> rc{1};
+    int ordinal = 0;
+    cudaStream_t own_stream = nullptr;
+    cudaStream_t stream = nullptr;  // the stream work is enqueued on (own or caller's)
+    cudaMemPool_t pool = nullptr;
+    int sm_count = 0, cc_major = 0, cc_minor = 0;
+    size_t total_mem = 0, l2_bytes = 0;
+    int max_smem_optin = 0;
+    std::mutex mu;  // serialises enqueue + scratch use (Device: Send + Sync in the reference)
+    hj::LookbackScratch lookback;
+    void* reduce_scratch = nullptr;  // partials + ticket of the single-pass reduction
+    size_t reduce_scratch_bytes = 0;
+    std::atomic<uint64_t> launches{0};
+    std::atomic<uint64_t> n_alloc{0}, n_free{0};
+    hj::KernelCache* kcache = nullptr;
+};
+
+struct hj_buffer {
+    std::atomic<int> rc{1};
+    hj_device* dev = nullptr;
+    void* ptr = nullptr;
+    size_t bytes = 0;
+    bool owned = true;
+};
+
+namespace hj {
+
+// RAII guard: selects the device and holds its enqueue lock.
+struct DeviceGuard {
+    hj_device* dev;
+    std::unique_lock<std::mutex> lock;
+    explicit DeviceGuard(hj_device* d) : dev(d), lock(d->mu) { cudaSetDevice(d->ordinal); }
+};
+
+// Grow-only scratch helpers (called with the device lock held).
+hj_status ensure_reduce_scratch(hj_device* dev, size_t bytes);
+hj_status ensure_lookback_scratch(hj_device* dev, size_t n_tiles);
+// Next look-back epoch (clears the scratch on wrap-around).
+hj_status next_epoch(hj_device* dev, uint32_t* out);
+
+// ---- kernel launchers (defined in the .cu files; device lock held by the caller) ---------
+hj_status launch_reduce(hj_device* dev, hj_reduce_op op, hj_type_kind ty, size_t n,
+                        const void* src, void* dst);
+hj_status launch_prefix_sum(hj_device* dev, hj_type_kind ty, size_t n, bool inclusive,
+                            const void* src, void* dst, const void* seed);
+hj_status launch_compress(hj_device* dev, size_t n, const uint32_t* size_buf, uint32_t* out_count,
+                          const uint8_t* mask, uint32_t* index_out, uint32_t index_base);
+hj_status launch_scatter_reduce(hj_device* dev, hj_reduce_op op, hj_type_kind ty, size_t n,
+                                const uint32_t* idx, const void* src, uint64_t literal, void* dst,
+                                size_t n_dst);
+hj_status launch_gather(hj_device* dev, size_t elem_bytes, size_t n, const void* src,
+                        const uint32_t* idx, void* dst);
+hj_status launch_fill(hj_device* dev, void* dst, size_t n, size_t elem_bytes, uint64_t pattern);
+
+inline hj_status check_launch(hj_device* dev, const char* what) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(HJ_ERR_CUDA, "launch of %s failed: %s", what, cudaGetErrorString(e));
+    dev->launches.fetch_add(1, std::memory_order_relaxed);
+    return HJ_OK;
+}
+
+}  // namespace hj

@@ -84,7 +84,7 @@ hj_status hj_device_info(hj_device* dev, int32_t* sm_count, int32_t* cc_major, i
                          uint64_t* total_mem, uint64_t* l2_bytes);
 /* Pool statistics (the reference's ResourcePool, vulkan_core/pool.rs:52-66). */
 hj_status hj_device_pool_stats(hj_device* dev, uint64_t* bytes_live, uint64_t* bytes_cached,
-                               uint64_t* n_alloc, uint64_t* n_reuse);
+                               uint64_t* n_alloc, uint64_t* n_free);
 hj_status hj_device_pool_trim(hj_device* dev);
 /* Number of kernel launches this library has enqueued on `dev` since creation. */
 hj_status hj_device_launch_count(hj_device* dev, uint64_t* out);

@@ -1,0 +1,337 @@
+"""GPU parity tests: the hand-written sm_100a kernels, called through the C ABI, against the CPU
+oracle on the same seeded inputs.  Integer / index / byte results must be bit-exact; float
+reductions and scans must be within the stated relative tolerance of the f64 answer."""
+import importlib
+import json
+import os
+
+import numpy as np
+import pytest
+
+import oracle
+
+pytestmark = pytest.mark.gpu
+
+hj = importlib.import_module("hephaestus-jit_b200")
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+with open(os.path.join(HERE, "golden", "reference_kats.json")) as f:
+    KATS = json.load(f)
+
+TY = {"Bool": hj.BOOL, "I8": hj.I8, "U8": hj.U8, "I16": hj.I16, "U16": hj.U16, "I32": hj.I32,
+      "U32": hj.U32, "I64": hj.I64, "U64": hj.U64, "F32": hj.F32, "F64": hj.F64}
+OP = {"max": hj.MAX, "min": hj.MIN, "sum": hj.SUM, "prod": hj.PROD, "or": hj.OR, "and": hj.AND,
+      "xor": hj.XOR}
+F32_SUM_RTOL = 1e-5  # BASELINE.json north_star: "1e-5 for f32 sums, accounting for reordering"
+
+
+@pytest.fixture(scope="module")
+def dev():
+    return hj.Device.cuda(0)
+
+
+def gpu_reduce(dev, op, ty, x):
+    src = dev.create_buffer_from_slice(x)
+    dst = dev.create_buffer(hj.TYPE_SIZE[ty])
+    dev.reduce(op, ty, x.size, src, dst)
+    return dst.to_host(oracle.NP_DTYPE[ty])[0]
+
+
+def rand_array(rng, ty, n, small=False):
+    dt = oracle.NP_DTYPE[ty]
+    if ty in (hj.F32, hj.F64):
+        return rng.random(n).astype(dt)
+    if ty == hj.BOOL:
+        return rng.integers(0, 2, size=n).astype(np.uint8)
+    info = np.iinfo(dt)
+    if small:
+        return rng.integers(0, 4, size=n).astype(dt)
+    return rng.integers(info.min, int(info.max) + 1, size=n,
+                        dtype=np.int64 if info.min < 0 else np.uint64).astype(dt)
+
+
+# ---- reduce ------------------------------------------------------------------------------
+
+@pytest.mark.parametrize("case", KATS["reduce"], ids=lambda c: f"{c['op']}-{c['ty']}")
+def test_reduce_reference_kats(dev, case):
+    ty = TY[case["ty"]]
+    lo, hi = case["range"]
+    x = np.arange(lo, hi).astype(oracle.NP_DTYPE[ty])
+    assert gpu_reduce(dev, OP[case["op"]], ty, x) == case["expect"]
+
+
+@pytest.mark.parametrize("case", KATS["reduce_random"], ids=lambda c: f"{c['op']}-{c['ty']}")
+def test_reduce_reference_random_cases(dev, case):
+    ty = TY[case["ty"]]
+    rng = np.random.Generator(np.random.PCG64(0))
+    x = rng.integers(case["lo"], case["hi"], size=case["n"]).astype(oracle.NP_DTYPE[ty])
+    assert gpu_reduce(dev, OP[case["op"]], ty, x) == oracle.reduce(OP[case["op"]], ty, x)[0]
+
+
+INT_TYPES = [hj.I8, hj.U8, hj.I16, hj.U16, hj.I32, hj.U32, hj.I64, hj.U64]
+
+
+@pytest.mark.parametrize("ty", INT_TYPES + [hj.BOOL])
+@pytest.mark.parametrize("n", [1, 2, 31, 33, 1000, 4097, 65536 + 3, (1 << 20) + 17])
+def test_reduce_ints_bit_exact_all_ops(dev, ty, n):
+    rng = np.random.Generator(np.random.PCG64(n * 31 + ty))
+    x = rand_array(rng, ty, n)
+    ops = [hj.AND, hj.OR, hj.XOR] if ty == hj.BOOL else [hj.MAX, hj.MIN, hj.SUM, hj.PROD]
+    if ty in (hj.U8, hj.U16, hj.U32, hj.U64):
+        ops += [hj.AND, hj.OR, hj.XOR]
+    for op in ops:
+        if op == hj.PROD:  # keep products non-trivial: odd values never collapse to 0
+            xx = (x | 1).astype(x.dtype)
+        elif op == hj.AND and ty != hj.BOOL:
+            xx = (x | np.array(0x55, dtype=x.dtype)).astype(x.dtype)
+        else:
+            xx = x
+        want = oracle.reduce(op, ty, xx)[0]
+        got = gpu_reduce(dev, op, ty, xx)
+        assert got == want, (oracle.OP_NAME[op], oracle.TYPE_NAME[ty], n)
+
+
+@pytest.mark.parametrize("ty,rtol", [(hj.F32, F32_SUM_RTOL), (hj.F64, 1e-12)])
+@pytest.mark.parametrize("n", [1, 33, 1000, (1 << 20) + 17, 1 << 24])
+def test_reduce_floats(dev, ty, rtol, n):
+    rng = np.random.Generator(np.random.PCG64(n))
+    x = rng.random(n).astype(oracle.NP_DTYPE[ty])
+    exact = float(np.sum(x.astype(np.float64)))
+    got = float(gpu_reduce(dev, hj.SUM, ty, x))
+    assert abs(got - exact) <= rtol * abs(exact)
+    # the reference's own radix-32 tree answer is also within tolerance of ours
+    tree = float(oracle.reduce(hj.SUM, ty, x)[0])
+    assert abs(got - tree) <= 2 * rtol * abs(exact)
+    assert gpu_reduce(dev, hj.MAX, ty, x) == x.max()
+    assert gpu_reduce(dev, hj.MIN, ty, x) == x.min()
+    xs = (1.0 + (x[: min(n, 4096)] - 0.5) * 1e-3).astype(x.dtype)
+    gp = float(gpu_reduce(dev, hj.PROD, ty, xs))
+    wp = float(np.prod(xs.astype(np.float64)))
+    assert abs(gp - wp) <= 1e-4 * abs(wp)
+
+
+def test_reduce_f32_integer_valued_is_exact(dev):
+    """test.rs:580 — f32 sum over integer-valued data compares with assert_eq."""
+    rng = np.random.Generator(np.random.PCG64(0))
+    x = rng.integers(0, 100, size=1000).astype(np.float32)
+    assert gpu_reduce(dev, hj.SUM, hj.F32, x) == np.float32(x.sum(dtype=np.float64))
+
+
+def test_reduce_unsupported_pairs_error(dev):
+    x = np.zeros(16, np.float16)
+    with pytest.raises(hj.HjError) as e:
+        gpu_reduce(dev, hj.SUM, hj.F16, x)
+    assert e.value.status == 2
+    with pytest.raises(hj.HjError):
+        gpu_reduce(dev, hj.AND, hj.I32, np.zeros(16, np.int32))
+    with pytest.raises(hj.HjError):
+        gpu_reduce(dev, hj.SUM, hj.BOOL, np.zeros(16, np.uint8))
+
+
+def test_reduce_deterministic(dev):
+    rng = np.random.Generator(np.random.PCG64(5))
+    x = rng.random(1 << 22, dtype=np.float32)
+    a = gpu_reduce(dev, hj.SUM, hj.F32, x)
+    for _ in range(3):
+        assert gpu_reduce(dev, hj.SUM, hj.F32, x) == a
+
+
+def test_reduce_unaligned_wrapped_buffer(dev):
+    """A wrapped, non-16-byte-aligned view exercises the scalar head/tail path."""
+    rng = np.random.Generator(np.random.PCG64(6))
+    x = rng.integers(0, 2**32, size=100003, dtype=np.uint64).astype(np.uint32)
+    whole = dev.create_buffer_from_slice(x)
+    view = dev.wrap(whole.ptr + 4, (x.size - 1) * 4)
+    dst = dev.create_buffer(4)
+    dev.reduce(hj.SUM, hj.U32, x.size - 1, view, dst)
+    assert dst.to_host(np.uint32)[0] == oracle.reduce(hj.SUM, hj.U32, x[1:])[0]
+
+
+# ---- prefix sum --------------------------------------------------------------------------
+
+def gpu_scan(dev, ty, x, inclusive, seed=None):
+    src = dev.create_buffer_from_slice(x)
+    dst = dev.create_buffer(x.nbytes)
+    sb = dev.create_buffer_from_slice(np.array([seed], dtype=x.dtype)) if seed is not None else None
+    dev.prefix_sum(ty, x.size, inclusive, src, dst, sb)
+    return dst.to_host(x.dtype)
+
+
+def test_prefix_sum_reference_kat(dev):
+    c = KATS["prefix_sum"]
+    x = np.arange(c["n"], dtype=np.uint64)
+    got = gpu_scan(dev, hj.U64, x, True)
+    assert np.array_equal(got, oracle.prefix_sum(hj.U64, x, True))
+    assert int(got[-1]) == c["expect_last"]
+
+
+@pytest.mark.parametrize("ty", INT_TYPES)
+@pytest.mark.parametrize("n", [1, 3, 4095, 4096, 4097, 8195, 100003, (1 << 20) + 5])
+@pytest.mark.parametrize("inclusive", [True, False])
+def test_prefix_sum_ints_bit_exact(dev, ty, n, inclusive):
+    rng = np.random.Generator(np.random.PCG64(n + ty))
+    x = rand_array(rng, ty, n)
+    got = gpu_scan(dev, ty, x, inclusive)
+    assert np.array_equal(got, oracle.prefix_sum(ty, x, inclusive))
+
+
+def test_prefix_sum_large_u32_and_seed(dev):
+    n = (1 << 24) + 123
+    rng = np.random.Generator(np.random.PCG64(1))
+    x = rng.integers(0, 2**32, size=n, dtype=np.uint64).astype(np.uint32)
+    want = oracle.prefix_sum_u32_mt(x, True)
+    assert np.array_equal(gpu_scan(dev, hj.U32, x, True), want)
+    seeded = gpu_scan(dev, hj.U32, x, False, seed=12345)
+    with np.errstate(over="ignore"):
+        assert np.array_equal(seeded, oracle.prefix_sum_u32_mt(x, False) + np.uint32(12345))
+
+
+def test_prefix_sum_repeated_launches_epoch(dev):
+    """Back-to-back scans of different sizes share the epoch-tagged scratch."""
+    rng = np.random.Generator(np.random.PCG64(2))
+    for n in [5000, 1 << 18, 777, (1 << 20) + 1, 4096, 1 << 18]:
+        x = rng.integers(0, 4, size=n).astype(np.uint32)
+        assert np.array_equal(gpu_scan(dev, hj.U32, x, True), np.cumsum(x, dtype=np.uint32))
+
+
+@pytest.mark.parametrize("ty,rtol", [(hj.F32, 1e-5), (hj.F64, 1e-12)])
+@pytest.mark.parametrize("inclusive", [True, False])
+def test_prefix_sum_floats(dev, ty, rtol, inclusive):
+    n = (1 << 20) + 7
+    rng = np.random.Generator(np.random.PCG64(3))
+    x = rng.random(n).astype(oracle.NP_DTYPE[ty])
+    got = gpu_scan(dev, ty, x, inclusive).astype(np.float64)
+    inc = np.cumsum(x.astype(np.float64))
+    want = inc if inclusive else np.concatenate([[0.0], inc[:-1]])
+    err = np.abs(got - want) / np.maximum(np.abs(want), 1.0)
+    assert err.max() < rtol
+
+
+def test_prefix_sum_ref_compat_bench_invariant(dev, monkeypatch):
+    """benches/vulkan.rs:130-137 under HJ_REF_COMPAT=1 (reference defect D10)."""
+    x = np.ones(1 << 16, dtype=np.uint32)
+    assert int(gpu_scan(dev, hj.U32, x, False)[-1]) == x.size - 1
+    monkeypatch.setenv("HJ_REF_COMPAT", "1")
+    assert int(gpu_scan(dev, hj.U32, x, False)[-1]) == x.size
+
+
+# ---- compress ----------------------------------------------------------------------------
+
+def gpu_compress(dev, mask, index_base=0, size=None, sentinel=0):
+    n = mask.size
+    src = dev.create_buffer_from_slice(mask)
+    idx = dev.create_buffer_from_slice(np.full(n, sentinel, dtype=np.uint32))
+    cnt = dev.create_buffer_from_slice(np.zeros(1, np.uint32))
+    sb = dev.create_buffer_from_slice(np.array([size], np.uint32)) if size is not None else None
+    dev.compress(n, cnt, src, idx, size_buf=sb, index_base=index_base)
+    return int(cnt.to_host(np.uint32)[0]), idx.to_host(np.uint32)
+
+
+def test_compress_reference_kats(dev):
+    n = KATS["compress_all_true"]["n"]
+    count, idx = gpu_compress(dev, np.ones(n, np.uint8))
+    assert count == n and np.array_equal(idx, np.arange(n, dtype=np.uint32))
+    rng = np.random.Generator(np.random.PCG64(0))
+    m = rng.integers(0, 2, size=KATS["compress_small"]["n"]).astype(np.uint8)
+    count, idx = gpu_compress(dev, m)
+    wc, wi = oracle.compress(m)
+    assert count == wc and np.array_equal(idx, wi)
+
+
+@pytest.mark.parametrize("n", [1, 15, 17, 2049, 4111, 8191, 8192, 8193, 100003, (1 << 20) + 9])
+@pytest.mark.parametrize("p", [0.0, 0.01, 0.5, 0.99, 1.0])
+def test_compress_bit_exact(dev, n, p):
+    rng = np.random.Generator(np.random.PCG64(n))
+    mask = (rng.random(n) < p).astype(np.uint8)
+    count, idx = gpu_compress(dev, mask, index_base=5, sentinel=0xDEADBEEF)
+    wc, wi = oracle.compress(mask, index_out=np.full(n, 0xDEADBEEF, np.uint32), index_base=5)
+    assert count == wc
+    assert np.array_equal(idx, wi)  # includes the untouched tail
+
+
+def test_compress_large_and_dynsize(dev):
+    n = (1 << 24) + 77
+    rng = np.random.Generator(np.random.PCG64(4))
+    mask = (rng.random(n) < 0.5).astype(np.uint8)
+    count, idx = gpu_compress(dev, mask)
+    wc, wi = oracle.compress(mask, mt=True)
+    assert count == wc and np.array_equal(idx, wi)
+    # DynSize: only the first `size` elements take part
+    size = 1_000_003
+    count, idx = gpu_compress(dev, mask, size=size)
+    wc, wi = oracle.compress(mask[:size], index_out=np.zeros(n, np.uint32))
+    assert count == wc and np.array_equal(idx, wi)
+
+
+# ---- scatter-reduce / gather ----------------------------------------------------------------
+
+def test_scatter_reduce_reference_kat(dev):
+    c = KATS["scatter_reduce"]
+    dst = dev.create_buffer_from_slice(np.array(c["dst"], np.uint32))
+    idx = dev.create_buffer_from_slice(np.full(c["n"], c["idx"], np.uint32))
+    dev.scatter_reduce(hj.SUM, hj.U32, c["n"], idx, None, c["value"], dst, 3)
+    assert dst.to_host(np.uint32).tolist() == c["expect"]
+
+
+@pytest.mark.parametrize("n_bins", [16, 1 << 12, 1 << 16])
+def test_histogram_bit_exact(dev, n_bins):
+    n = (1 << 22) + 3
+    rng = np.random.Generator(np.random.PCG64(n_bins))
+    keys = rng.integers(0, n_bins, size=n).astype(np.uint32)
+    dst = dev.create_buffer_from_slice(np.zeros(n_bins, np.uint32))
+    idx = dev.create_buffer_from_slice(keys)
+    dev.scatter_reduce(hj.SUM, hj.U32, n, idx, None, 1, dst, n_bins)
+    got = dst.to_host(np.uint32)
+    assert np.array_equal(got, oracle.histogram_u32_mt(keys, n_bins))
+    assert int(got.sum(dtype=np.uint64)) == n
+
+
+@pytest.mark.parametrize("op", [hj.MAX, hj.MIN, hj.OR, hj.AND, hj.XOR, hj.SUM])
+def test_scatter_reduce_values_bit_exact(dev, op):
+    n, n_bins = 200003, 1000
+    rng = np.random.Generator(np.random.PCG64(op))
+    keys = rng.integers(0, n_bins, size=n).astype(np.uint32)
+    vals = rng.integers(0, 2**32, size=n, dtype=np.uint64).astype(np.uint32)
+    init = rng.integers(0, 2**32, size=n_bins, dtype=np.uint64).astype(np.uint32)
+    dst = dev.create_buffer_from_slice(init)
+    dev.scatter_reduce(op, hj.U32, n, dev.create_buffer_from_slice(keys),
+                       dev.create_buffer_from_slice(vals), 0, dst, n_bins)
+    want = oracle.scatter_reduce(op, hj.U32, keys, vals, init.copy())
+    assert np.array_equal(dst.to_host(np.uint32), want)
+
+
+def test_scatter_reduce_f32_sum_tolerance(dev):
+    n, n_bins = 1 << 20, 64
+    rng = np.random.Generator(np.random.PCG64(9))
+    keys = rng.integers(0, n_bins, size=n).astype(np.uint32)
+    vals = rng.random(n, dtype=np.float32)
+    dst = dev.create_buffer_from_slice(np.zeros(n_bins, np.float32))
+    dev.scatter_reduce(hj.SUM, hj.F32, n, dev.create_buffer_from_slice(keys),
+                       dev.create_buffer_from_slice(vals), 0.0, dst, n_bins)
+    want = np.zeros(n_bins, np.float64)
+    np.add.at(want, keys, vals.astype(np.float64))
+    assert np.allclose(dst.to_host(np.float32), want, rtol=1e-4)
+
+
+def test_gather_bit_exact(dev):
+    rng = np.random.Generator(np.random.PCG64(10))
+    for dt in (np.uint8, np.uint16, np.float32, np.float64):
+        src = (rng.random(5000) * 200).astype(dt)
+        idx = rng.integers(0, src.size, size=100001).astype(np.uint32)
+        out = dev.create_buffer(idx.size * src.itemsize)
+        dev.gather(src.itemsize, idx.size, dev.create_buffer_from_slice(src),
+                   dev.create_buffer_from_slice(idx), out)
+        assert np.array_equal(out.to_host(dt), oracle.gather(src, idx))
+
+
+# ---- runtime -------------------------------------------------------------------------------
+
+def test_buffer_roundtrip_and_ranges(dev):
+    x = np.arange(1000, dtype=np.int32)
+    b = dev.create_buffer_from_slice(x)
+    assert np.array_equal(b.to_host(np.int32), x)
+    assert np.array_equal(b.to_host(np.int32, 10, 20), x[10:20])
+    with pytest.raises(hj.HjError):
+        b.to_host(np.int32, 0, 1001)
+    assert dev.info()["sm_count"] > 0
+    assert dev.launch_count() > 0
