@@ -1,0 +1,724 @@
+// codegen.cpp — lowers one fused-kernel IR to CUDA C++ for NVRTC (sm_100a).
+//
+// Semantic spec: the reference's GLSL emitter,
+// hephaestus-jit/src/backend/vulkan/codegen/glsl/mod.rs (prologue :129-133, per-op emission
+// :336-918, casts :919-1035).  Every op below cites the lines it restates.  Deliberate
+// differences: FMA is emitted (D1), AtomicInc elects the lowest ACTIVE lane
+// (D8), float literals are emitted as bit patterns (D9).
+//
+// Two entry points are generated per IR:
+//   hj_kernel_scalar — one thread per element, exactly the reference's mapping;
+//   hj_kernel_vec    — each thread owns UNROLL vectors of VEC consecutive elements; buffers
+//     that are only read (or only written, unconditionally, at top level) through the bare
+//     `Index` variable are staged with 128-bit `ld.global.nc` / `st.global` accesses, all
+//     loads issued before the arithmetic.  This is what makes a fused elementwise chain
+//     HBM-bound on B200 instead of LSU-issue-bound.
+#include <cinttypes>
+#include <cstdio>
+#include <map>
+#include <set>
+#include <sstream>
+
+#include "ir.h"
+
+namespace hj {
+namespace {
+
+const char* kScalarNames[] = {"void", "bool", "i8", "u8", "i16", "u16", "i32", "u32", "i64", "u64", "f16", "f32", "f64"};
+
+size_t scalar_size(uint32_t k) {
+    switch (k) {
+    case HJ_BOOL: case HJ_I8: case HJ_U8: return 1;
+    case HJ_I16: case HJ_U16: case HJ_F16: return 2;
+    case HJ_I32: case HJ_U32: case HJ_F32: return 4;
+    case HJ_I64: case HJ_U64: case HJ_F64: return 8;
+    default: return 0;
+    }
+}
+
+struct Gen {
+    IRView v;
+    std::ostringstream types, body;
+    std::set<std::string> emitted_types;
+    std::string err;
+    bool uses_f16 = false;
+
+    explicit Gen(const hj_ir* ir) : v(ir) {}
+
+    bool fail(const std::string& m) { if (err.empty()) err = m; return false; }
+
+    // ---- types -----------------------------------------------------------------------------
+    std::string tname(uint32_t t) {
+        const hj_type_desc& d = v.type(t);
+        switch (d.kind) {
+        case HJ_VEC: return "vec_" + tname(d.elem) + "_" + std::to_string(d.num);
+        case HJ_ARRAY: return "arr_" + tname(d.elem) + "_" + std::to_string(d.num);
+        case HJ_MAT: return "mat_" + tname(d.elem) + "_" + std::to_string(d.cols) + "x" + std::to_string(d.rows);
+        case HJ_STRUCT: {
+            std::string s = "st_";
+            for (uint32_t k = 0; k < d.num; k++) s += tname(v.field(d, k)) + "_";
+            return s + "end";
+        }
+        default:
+            if (d.kind == HJ_F16) uses_f16 = true;
+            return d.kind <= HJ_F64 ? kScalarNames[d.kind] : "void";
+        }
+    }
+    uint32_t n_components(uint32_t t) {
+        const hj_type_desc& d = v.type(t);
+        if (d.kind == HJ_VEC || d.kind == HJ_ARRAY) return d.num;
+        if (d.kind == HJ_MAT) return d.cols * d.rows;
+        return 0;
+    }
+    bool is_composite_elems(uint32_t t) { uint32_t k = v.type(t).kind; return k == HJ_VEC || k == HJ_ARRAY || k == HJ_MAT; }
+    void declare_type(uint32_t t) {
+        const hj_type_desc& d = v.type(t);
+        if (d.kind < HJ_VEC) { tname(t); return; }
+        std::string name = tname(t);
+        if (emitted_types.count(name)) return;
+        if (d.kind == HJ_STRUCT) {
+            for (uint32_t k = 0; k < d.num; k++) declare_type(v.field(d, k));
+            emitted_types.insert(name);
+            types << "struct " << name << " {";
+            for (uint32_t k = 0; k < d.num; k++) types << " " << tname(v.field(d, k)) << " e" << k << ";";
+            types << " };\n";
+        } else {
+            declare_type(d.elem);
+            emitted_types.insert(name);
+            types << "struct " << name << " { " << tname(d.elem) << " e[" << n_components(t) << "]; };\n";
+        }
+    }
+
+    // ---- scalar expression builders -----------------------------------------------------------
+    static std::string hexlit(uint64_t x) {
+        char b[32];
+        snprintf(b, sizeof(b), "0x%" PRIx64 "ull", x);
+        return b;
+    }
+    // Literal: glsl/mod.rs:583-618 (floats as exact bit patterns, D9)
+    bool literal_expr(uint32_t kind, uint64_t data, std::string* out) {
+        switch (kind) {
+        case HJ_BOOL: *out = data ? "true" : "false"; return true;
+        case HJ_I8: case HJ_U8: case HJ_I16: case HJ_U16: case HJ_I32: case HJ_U32: case HJ_I64: case HJ_U64:
+            *out = std::string("(") + kScalarNames[kind] + ")" + hexlit(data);
+            return true;
+        case HJ_F16: *out = "__ushort_as_half((unsigned short)" + hexlit(data & 0xffff) + ")"; return true;
+        case HJ_F32: *out = "__uint_as_float((u32)" + hexlit(data & 0xffffffffull) + ")"; return true;
+        case HJ_F64: *out = "__longlong_as_double((long long)" + hexlit(data) + ")"; return true;
+        default: return fail("Literal of a non-scalar type (todo!() in the reference, glsl/mod.rs:616)");
+        }
+    }
+    // Cast between scalars: glsl/mod.rs:926-957 (GLSL constructors)
+    std::string cast_expr(uint32_t dk, uint32_t sk, const std::string& x) {
+        if (dk == sk) return x;
+        if (dk == HJ_BOOL) {
+            if (sk == HJ_F16) return "(__half2float(" + x + ") != 0.0f)";
+            return "(" + x + " != 0)";
+        }
+        if (sk == HJ_BOOL) {
+            if (dk == HJ_F16) return "__float2half(" + x + " ? 1.0f : 0.0f)";
+            return std::string("(") + kScalarNames[dk] + ")(" + x + " ? 1 : 0)";
+        }
+        if (dk == HJ_F16) return "__float2half((float)(" + x + "))";
+        if (sk == HJ_F16) return std::string("(") + kScalarNames[dk] + ")__half2float(" + x + ")";
+        return std::string("(") + kScalarNames[dk] + ")(" + x + ")";
+    }
+    // BitCast: glsl/mod.rs:844-900
+    bool bitcast_expr(uint32_t dk, uint32_t sk, const std::string& x, std::string* out) {
+        if (dk == sk) { *out = x; return true; }
+        if (is_int_kind(dk) && is_int_kind(sk)) { *out = cast_expr(dk, sk, x); return true; }  // :880-897
+        if (scalar_size(dk) != scalar_size(sk) || dk == HJ_BOOL || sk == HJ_BOOL)
+            return fail("BitCast between types of different size");
+        *out = std::string("hj_bitcast<") + kScalarNames[dk] + ", " + kScalarNames[sk] + ">(" + x + ")";
+        return true;
+    }
+    // Bop on scalars of kind `k` (operand type; result kind `rk`): glsl/mod.rs:786-836
+    bool bop_expr(uint32_t op, uint32_t k, const std::string& a, const std::string& b, std::string* out) {
+        const std::string T = kScalarNames[k];
+        const bool fp = is_float_kind(k), h = k == HJ_F16;
+        auto arith = [&](const char* o) { return "(" + T + ")(" + a + " " + o + " " + b + ")"; };
+        switch (op) {
+        case HJ_BOP_ADD: *out = arith("+"); return true;
+        case HJ_BOP_SUB: *out = arith("-"); return true;
+        case HJ_BOP_MUL: case HJ_BOP_INNER: *out = arith("*"); return true;
+        case HJ_BOP_DIV:
+            if (k == HJ_BOOL) return fail("Div on bool");
+            *out = arith("/"); return true;
+        case HJ_BOP_MODULUS:
+            if (k == HJ_BOOL) return fail("Modulus on bool");
+            if (h) *out = "__float2half(fmodf(__half2float(" + a + "), __half2float(" + b + ")))";
+            else if (k == HJ_F32) *out = "fmodf(" + a + ", " + b + ")";
+            else if (k == HJ_F64) *out = "fmod(" + a + ", " + b + ")";
+            else *out = arith("%");
+            return true;
+        case HJ_BOP_MIN: case HJ_BOP_MAX: {
+            const bool mn = op == HJ_BOP_MIN;
+            if (h) *out = std::string(mn ? "__hmin(" : "__hmax(") + a + ", " + b + ")";
+            else if (k == HJ_F32) *out = std::string(mn ? "fminf(" : "fmaxf(") + a + ", " + b + ")";
+            else if (k == HJ_F64) *out = std::string(mn ? "fmin(" : "fmax(") + a + ", " + b + ")";
+            else if (mn) *out = "(" + b + " < " + a + " ? " + b + " : " + a + ")";
+            else *out = "(" + a + " < " + b + " ? " + b + " : " + a + ")";
+            return true;
+        }
+        case HJ_BOP_AND: case HJ_BOP_OR: case HJ_BOP_XOR: {
+            if (fp) return fail("bitwise op on a float type");
+            if (k == HJ_BOOL) {  // glsl/mod.rs:815-826: &&, ||, !=
+                const char* o = op == HJ_BOP_AND ? "&&" : op == HJ_BOP_OR ? "||" : "!=";
+                *out = "(" + a + " " + o + " " + b + ")";
+            } else {
+                *out = arith(op == HJ_BOP_AND ? "&" : op == HJ_BOP_OR ? "|" : "^");
+            }
+            return true;
+        }
+        case HJ_BOP_SHL: case HJ_BOP_SHR:
+            if (!is_int_kind(k)) return fail("shift on a non-integer type");
+            *out = arith(op == HJ_BOP_SHL ? "<<" : ">>");
+            return true;
+        case HJ_BOP_EQ: *out = "(" + a + " == " + b + ")"; return true;
+        case HJ_BOP_NEQ: *out = "(" + a + " != " + b + ")"; return true;
+        case HJ_BOP_LT: *out = "(" + a + " < " + b + ")"; return true;
+        case HJ_BOP_LE: *out = "(" + a + " <= " + b + ")"; return true;
+        case HJ_BOP_GT: *out = "(" + a + " > " + b + ")"; return true;
+        case HJ_BOP_GE: *out = "(" + a + " >= " + b + ")"; return true;
+        default: return fail("unknown Bop");
+        }
+    }
+    // Uop (other than Cast/BitCast) on a scalar of kind k: glsl/mod.rs:901-910
+    bool uop_expr(uint32_t op, uint32_t k, const std::string& x, std::string* out) {
+        const std::string T = kScalarNames[k];
+        const bool h = k == HJ_F16;
+        auto fn = [&](const char* f32, const char* f64, const char* f16) -> bool {
+            if (k == HJ_F32) { *out = std::string(f32) + "(" + x + ")"; return true; }
+            if (k == HJ_F64) { *out = std::string(f64) + "(" + x + ")"; return true; }
+            if (h) { *out = std::string(f16) + "(" + x + ")"; return true; }
+            return fail("transcendental op on a non-float type");
+        };
+        switch (op) {
+        case HJ_UOP_NEG:
+            if (k == HJ_BOOL) *out = "(!" + x + ")";  // glsl/mod.rs:901-904
+            else if (h) *out = "__hneg(" + x + ")";
+            else *out = "(" + T + ")(-" + x + ")";
+            return true;
+        case HJ_UOP_SQRT: return fn("sqrtf", "sqrt", "hsqrt");
+        case HJ_UOP_ABS:
+            if (k == HJ_F32) *out = "fabsf(" + x + ")";
+            else if (k == HJ_F64) *out = "fabs(" + x + ")";
+            else if (h) *out = "__habs(" + x + ")";
+            else if (is_signed_kind(k)) *out = "(" + T + ")(" + x + " < 0 ? -" + x + " : " + x + ")";
+            else *out = x;
+            return true;
+        case HJ_UOP_SIN: return fn("sinf", "sin", "hsin");
+        case HJ_UOP_COS: return fn("cosf", "cos", "hcos");
+        case HJ_UOP_EXP2: return fn("exp2f", "exp2", "hexp2");
+        case HJ_UOP_LOG2: return fn("log2f", "log2", "hlog2");
+        default: return fail("unknown Uop");
+        }
+    }
+
+    // ---- memory-access analysis ---------------------------------------------------------------
+    struct Slot {
+        uint32_t elem_kind = HJ_VOID;  // scalar kind when every access uses one scalar type, else VOID
+        bool read = false, written = false, atomic = false;
+        bool read_only_index = true;   // every Gather uses the bare Index var, unconditionally or not
+        bool write_only_index_top = true;  // every Scatter: bare Index, no cond, nesting depth 0
+        bool mixed_types = false;
+        bool stage_load = false, stage_store = false;
+    };
+    std::vector<Slot> slots;
+
+    bool is_index_var(uint32_t id) { return v.var(id).op == HJ_OP_INDEX; }
+
+    void note_type(Slot& s, uint32_t t) {
+        uint32_t k = v.type(t).kind;
+        uint32_t kk = is_scalar_kind(k) ? k : (uint32_t)HJ_STRUCT;
+        if (s.elem_kind == HJ_VOID) s.elem_kind = kk;
+        else if (s.elem_kind != kk) s.mixed_types = true;
+    }
+
+    bool analyse() {
+        slots.assign(v.ir->n_buffers, Slot());
+        int depth = 0;
+        for (uint32_t i = 0; i < v.n_vars(); i++) {
+            const hj_ir_var& var = v.var(i);
+            switch (var.op) {
+            case HJ_OP_LOOP_START: case HJ_OP_IF_START: depth++; break;
+            case HJ_OP_LOOP_END: case HJ_OP_IF_END: depth--; break;
+            case HJ_OP_GATHER: {
+                uint32_t buf = v.dep(i, 0);
+                if (v.var(buf).op != HJ_OP_BUFFER_REF) return fail("Gather source is not a BufferRef");
+                Slot& s = slots[v.var(buf).data];
+                s.read = true;
+                note_type(s, var.ty);
+                if (!is_index_var(v.dep(i, 1))) s.read_only_index = false;
+                break;
+            }
+            case HJ_OP_SCATTER: case HJ_OP_SCATTER_REDUCE: case HJ_OP_SCATTER_ATOMIC: case HJ_OP_ATOMIC_INC: {
+                uint32_t buf = v.dep(i, 0);
+                if (v.var(buf).op != HJ_OP_BUFFER_REF) return fail("scatter target is not a BufferRef");
+                Slot& s = slots[v.var(buf).data];
+                s.written = true;
+                if (var.op != HJ_OP_SCATTER) { s.atomic = true; s.write_only_index_top = false; break; }
+                note_type(s, v.var_type(v.dep(i, 1)));
+                if (!is_index_var(v.dep(i, 2)) || v.n_deps(i) > 3 || depth != 0) s.write_only_index_top = false;
+                break;
+            }
+            default: break;
+            }
+        }
+        for (Slot& s : slots) {
+            bool scalar = is_scalar_kind(s.elem_kind) && !s.mixed_types;
+            s.stage_load = scalar && s.read && !s.written && s.read_only_index;
+            s.stage_store = scalar && s.written && !s.read && !s.atomic && s.write_only_index_top;
+        }
+        return true;
+    }
+
+    // ---- body emission ------------------------------------------------------------------------
+    std::string reg(uint32_t id) { return "r" + std::to_string(id); }
+
+    // address expression of a Gather/Scatter index: the bare Index var addresses LOCAL memory
+    // (shard-local element), any computed value is used as is.
+    std::string addr_of(uint32_t idx_var) { return is_index_var(idx_var) ? std::string("index") : reg(idx_var); }
+
+    bool emit_componentwise(std::ostream& o, uint32_t id, uint32_t t, const std::string& expr_k) {
+        o << "    for (int k = 0; k < " << n_components(t) << "; k++) " << reg(id) << ".e[k] = " << expr_k << ";\n";
+        return true;
+    }
+
+    // staged: element (u,k) of the vector path, gathers/scatters of staged slots go through
+    // the in_/out_ register arrays.
+    bool emit_body(std::ostream& o, bool staged) {
+        // declarations first: GLSL-style block scoping would hide loop-carried values
+        for (uint32_t i = 0; i < v.n_vars(); i++) {
+            const hj_ir_var& var = v.var(i);
+            uint32_t k = v.type(var.ty).kind;
+            if (k == HJ_VOID || var.op == HJ_OP_BUFFER_REF) continue;
+            o << "    " << tname(var.ty) << " " << reg(i) << ";\n";
+        }
+        for (uint32_t i = 0; i < v.n_vars(); i++) {
+            const hj_ir_var& var = v.var(i);
+            const uint32_t ty = var.ty;
+            const uint32_t kind = v.type(ty).kind;
+            const std::string T = tname(ty), r = reg(i);
+            auto d = [&](uint32_t k) { return v.dep(i, k); };
+            auto rd = [&](uint32_t k) { return reg(v.dep(i, k)); };
+            switch (var.op) {
+            case HJ_OP_NOP:  // glsl/mod.rs:356-363
+                o << "    " << r << " = " << rd(0) << ";\n";
+                break;
+            case HJ_OP_BUFFER_REF: break;  // glsl/mod.rs:231-250: no statement
+            case HJ_OP_INDEX:  // glsl/mod.rs:580-582; global index on sharded launches
+                o << "    " << r << " = gindex;\n";
+                break;
+            case HJ_OP_LITERAL: {
+                std::string e;
+                if (!literal_expr(kind, var.data, &e)) return false;
+                o << "    " << r << " = " << e << ";\n";
+                break;
+            }
+            case HJ_OP_GATHER: {  // glsl/mod.rs:523-579
+                uint32_t slot = (uint32_t)v.var(d(0)).data;
+                bool has_cond = v.n_deps(i) > 2;
+                std::string load;
+                if (staged && slots[slot].stage_load) {
+                    load = kind == HJ_BOOL ? "(in_" + std::to_string(slot) + "[u].e[k] != 0)"
+                                           : "in_" + std::to_string(slot) + "[u].e[k]";
+                } else {
+                    std::string a = addr_of(d(1));
+                    bool ro = !slots[slot].written && is_scalar_kind(kind) && kind != HJ_F16;
+                    if (kind == HJ_BOOL) load = std::string(ro ? "(__ldg((const u8*)b" : "(((const u8*)b") + std::to_string(slot) + (ro ? " + " + a + ")" : ")[" + a + "]") + " != 0)";
+                    else if (ro) load = "__ldg((const " + T + "*)b" + std::to_string(slot) + " + " + a + ")";
+                    else load = "((const " + T + "*)b" + std::to_string(slot) + ")[" + a + "]";
+                }
+                if (has_cond) {
+                    // inactive lanes yield zero for zeroable types (glsl/mod.rs:534-557,1037-1055)
+                    o << "    hj_zero(" << r << ");\n";
+                    o << "    if (" << rd(2) << ") " << r << " = " << load << ";\n";
+                } else {
+                    o << "    " << r << " = " << load << ";\n";
+                }
+                break;
+            }
+            case HJ_OP_SCATTER: {  // glsl/mod.rs:364-399
+                uint32_t slot = (uint32_t)v.var(d(0)).data;
+                uint32_t src = d(1);
+                uint32_t sk = v.type(v.var_type(src)).kind;
+                std::string ST = tname(v.var_type(src));
+                bool has_cond = v.n_deps(i) > 3;
+                if (staged && slots[slot].stage_store) {
+                    o << "    out_" << slot << "[u].e[k] = " << (sk == HJ_BOOL ? "(u8)(" + reg(src) + " ? 1 : 0)" : reg(src)) << ";\n";
+                    break;
+                }
+                std::string a = addr_of(d(2));
+                std::string st = sk == HJ_BOOL
+                                     ? "((u8*)b" + std::to_string(slot) + ")[" + a + "] = (u8)(" + reg(src) + " ? 1 : 0);"
+                                     : "((" + ST + "*)b" + std::to_string(slot) + ")[" + a + "] = " + reg(src) + ";";
+                if (has_cond) o << "    if (" << rd(3) << ") { " << st << " }\n";
+                else o << "    " << st << "\n";
+                break;
+            }
+            case HJ_OP_SCATTER_REDUCE: case HJ_OP_SCATTER_ATOMIC: {  // glsl/mod.rs:400-492
+                uint32_t slot = (uint32_t)v.var(d(0)).data;
+                uint32_t src = d(1);
+                uint32_t sk = v.type(v.var_type(src)).kind;
+                bool has_cond = v.n_deps(i) > 3;
+                const char* fn = nullptr;
+                switch (var.arg) {
+                case HJ_REDUCE_MAX: fn = "hj_atomic_max"; break;
+                case HJ_REDUCE_MIN: fn = "hj_atomic_min"; break;
+                case HJ_REDUCE_SUM: fn = "hj_atomic_add"; break;
+                case HJ_REDUCE_OR: fn = "hj_atomic_or"; break;
+                case HJ_REDUCE_AND: fn = "hj_atomic_and"; break;
+                case HJ_REDUCE_XOR: fn = "hj_atomic_xor"; break;
+                default: return fail("ScatterReduce(Prod) is todo!() in the reference (glsl/mod.rs:422,472)");
+                }
+                bool ok = sk == HJ_I32 || sk == HJ_U32 || sk == HJ_I64 || sk == HJ_U64 ||
+                          ((sk == HJ_F32 || sk == HJ_F64) && (var.arg == HJ_REDUCE_SUM || var.arg == HJ_REDUCE_MIN || var.arg == HJ_REDUCE_MAX));
+                if (!ok) return fail("atomic scatter on an unsupported element type");
+                std::string ST = tname(v.var_type(src));
+                std::string call = std::string(fn) + "((" + ST + "*)b" + std::to_string(slot) + " + " + addr_of(d(2)) + ", " + reg(src) + ")";
+                if (var.op == HJ_OP_SCATTER_ATOMIC) {
+                    o << "    hj_zero(" << r << ");\n";
+                    if (has_cond) o << "    if (" << rd(3) << ") " << r << " = " << call << ";\n";
+                    else o << "    " << r << " = " << call << ";\n";
+                } else {
+                    if (has_cond) o << "    if (" << rd(3) << ") { " << call << "; }\n";
+                    else o << "    " << call << ";\n";
+                }
+                break;
+            }
+            case HJ_OP_ATOMIC_INC: {  // glsl/mod.rs:493-522, leader = lowest ACTIVE lane (D8)
+                uint32_t slot = (uint32_t)v.var(d(0)).data;
+                if (kind != HJ_U32 && kind != HJ_I32) return fail("AtomicInc on a non 32-bit integer buffer");
+                o << "    " << r << " = (" << T << ")hj_atomic_inc((u32*)b" << slot << " + " << addr_of(d(1)) << ", " << rd(2) << ");\n";
+                break;
+            }
+            case HJ_OP_EXTRACT: {  // glsl/mod.rs:619-640
+                uint32_t sk = v.type(v.var_type(d(0))).kind;
+                if (sk == HJ_STRUCT) o << "    " << r << " = " << rd(0) << ".e" << var.arg << ";\n";
+                else if (sk == HJ_VEC || sk == HJ_ARRAY || sk == HJ_MAT) o << "    " << r << " = " << rd(0) << ".e[" << var.arg << "];\n";
+                else return fail("Extract from a scalar");
+                break;
+            }
+            case HJ_OP_DYN_EXTRACT:  // glsl/mod.rs:641-650
+                if (v.type(v.var_type(d(0))).kind != HJ_ARRAY) return fail("DynExtract from a non-array");
+                o << "    " << r << " = " << rd(0) << ".e[" << rd(1) << "];\n";
+                break;
+            case HJ_OP_CONSTRUCT: {  // glsl/mod.rs:651-687
+                uint32_t nd = v.n_deps(i);
+                if (kind == HJ_STRUCT) {
+                    if (nd != v.type(ty).num) return fail("Construct: field count mismatch");
+                    for (uint32_t k = 0; k < nd; k++) o << "    " << r << ".e" << k << " = " << rd(k) << ";\n";
+                } else if (kind == HJ_VEC || kind == HJ_ARRAY) {
+                    if (nd != v.type(ty).num) return fail("Construct: element count mismatch");
+                    for (uint32_t k = 0; k < nd; k++) o << "    " << r << ".e[" << k << "] = " << rd(k) << ";\n";
+                } else if (kind == HJ_MAT) {  // column vectors, column-major storage
+                    uint32_t rows = v.type(ty).rows;
+                    if (nd != v.type(ty).cols) return fail("Construct: column count mismatch");
+                    for (uint32_t c = 0; c < nd; c++)
+                        for (uint32_t q = 0; q < rows; q++)
+                            o << "    " << r << ".e[" << c * rows + q << "] = " << rd(c) << ".e[" << q << "];\n";
+                } else return fail("Construct of a scalar type");
+                break;
+            }
+            case HJ_OP_SELECT:  // glsl/mod.rs:688-694
+                o << "    " << r << " = " << rd(0) << " ? " << rd(1) << " : " << rd(2) << ";\n";
+                break;
+            case HJ_OP_LOOP_START:  // glsl/mod.rs:695-700
+                o << "    " << r << " = " << rd(0) << ";\n    while (" << r << ".e0) {\n";
+                break;
+            case HJ_OP_IF_START:  // glsl/mod.rs:710-715
+                o << "    " << r << " = " << rd(0) << ";\n    if (" << r << ".e0) {\n";
+                break;
+            case HJ_OP_LOOP_END: case HJ_OP_IF_END:  // glsl/mod.rs:701-709,716-724
+                o << "    " << rd(0) << " = " << rd(1) << ";\n    }\n    " << r << " = " << rd(0) << ";\n";
+                break;
+            case HJ_OP_BOP: {
+                uint32_t at = v.var_type(d(0));
+                uint32_t ak = v.type(at).kind;
+                std::string e;
+                if (is_scalar_kind(ak)) {
+                    if (!bop_expr(var.arg, ak, rd(0), rd(1), &e)) return false;
+                    o << "    " << r << " = " << e << ";\n";
+                } else if (is_composite_elems(at)) {
+                    uint32_t ek = v.type(v.type(at).elem).kind;
+                    if (!is_scalar_kind(ek)) return fail("Bop on nested composite types");
+                    if (var.arg == HJ_BOP_INNER && ak == HJ_VEC && is_scalar_kind(kind)) {  // dot, glsl/mod.rs:805-813
+                        o << "    " << r << " = (" << T << ")0;\n    for (int k = 0; k < " << n_components(at) << "; k++) " << r
+                          << " = (" << T << ")(" << r << " + " << rd(0) << ".e[k] * " << rd(1) << ".e[k]);\n";
+                    } else if (var.arg == HJ_BOP_EQ || var.arg == HJ_BOP_NEQ) {  // GLSL ==/!= on aggregates -> bool
+                        o << "    " << r << " = true;\n    for (int k = 0; k < " << n_components(at) << "; k++) " << r << " = " << r
+                          << " && (" << rd(0) << ".e[k] == " << rd(1) << ".e[k]);\n";
+                        if (var.arg == HJ_BOP_NEQ) o << "    " << r << " = !" << r << ";\n";
+                    } else {
+                        if (!bop_expr(var.arg, ek, rd(0) + ".e[k]", rd(1) + ".e[k]", &e)) return false;
+                        emit_componentwise(o, i, at, e);
+                    }
+                } else return fail("Bop on a struct type");
+                break;
+            }
+            case HJ_OP_UOP: {
+                uint32_t st = v.var_type(d(0));
+                uint32_t sk = v.type(st).kind;
+                std::string e;
+                if (var.arg == HJ_UOP_CAST) {
+                    if (!emit_cast(o, r, ty, rd(0), st)) return false;
+                } else if (var.arg == HJ_UOP_BITCAST) {
+                    if (!is_scalar_kind(kind) || !is_scalar_kind(sk)) return fail("BitCast on composite types");
+                    if (!bitcast_expr(kind, sk, rd(0), &e)) return false;
+                    o << "    " << r << " = " << e << ";\n";
+                } else if (is_scalar_kind(sk)) {
+                    if (!uop_expr(var.arg, sk, rd(0), &e)) return false;
+                    o << "    " << r << " = " << e << ";\n";
+                } else if (is_composite_elems(st)) {
+                    uint32_t ek = v.type(v.type(st).elem).kind;
+                    if (!uop_expr(var.arg, ek, rd(0) + ".e[k]", &e)) return false;
+                    emit_componentwise(o, i, st, e);
+                } else return fail("Uop on a struct type");
+                break;
+            }
+            case HJ_OP_FMA: {  // the reference emits nothing (glsl/mod.rs:913, defect D1)
+                std::string a = rd(0), b = rd(1), c = rd(2);
+                auto one = [&](uint32_t k, const std::string& x, const std::string& y, const std::string& z) -> std::string {
+                    if (k == HJ_F32) return "fmaf(" + x + ", " + y + ", " + z + ")";
+                    if (k == HJ_F64) return "fma(" + x + ", " + y + ", " + z + ")";
+                    if (k == HJ_F16) return "__hfma(" + x + ", " + y + ", " + z + ")";
+                    return std::string("(") + kScalarNames[k] + ")(" + x + " * " + y + " + " + z + ")";
+                };
+                if (is_scalar_kind(kind) && kind != HJ_BOOL) o << "    " << r << " = " << one(kind, a, b, c) << ";\n";
+                else if (is_composite_elems(ty)) emit_componentwise(o, i, ty, one(v.type(v.type(ty).elem).kind, a + ".e[k]", b + ".e[k]", c + ".e[k]"));
+                else return fail("FMA on an unsupported type");
+                break;
+            }
+            case HJ_OP_TEX_LOOKUP: case HJ_OP_TRACE_RAY: case HJ_OP_TEXTURE_REF: case HJ_OP_ACCEL_REF:
+                return fail("texture / ray-tracing ops are out of scope for the B200 backend");
+            default: return fail("unknown KernelOp " + std::to_string(var.op));
+            }
+        }
+        return true;
+    }
+
+    // Cast incl. Vec<->Array and Struct->Struct (glsl/mod.rs:919-1035)
+    bool emit_cast(std::ostream& o, const std::string& dst, uint32_t dt, const std::string& src, uint32_t st) {
+        const hj_type_desc& D = v.type(dt);
+        const hj_type_desc& S = v.type(st);
+        if (is_scalar_kind(D.kind) && is_scalar_kind(S.kind)) {
+            o << "    " << dst << " = " << cast_expr(D.kind, S.kind, src) << ";\n";
+            return true;
+        }
+        if ((D.kind == HJ_VEC || D.kind == HJ_ARRAY) && (S.kind == HJ_VEC || S.kind == HJ_ARRAY)) {
+            if (D.num != S.num) return fail("Cast between aggregates of different length");
+            uint32_t dk = v.type(D.elem).kind, sk = v.type(S.elem).kind;
+            if (!is_scalar_kind(dk) || !is_scalar_kind(sk)) return fail("Cast of nested aggregates");
+            o << "    for (int k = 0; k < " << D.num << "; k++) " << dst << ".e[k] = " << cast_expr(dk, sk, src + ".e[k]") << ";\n";
+            return true;
+        }
+        if (D.kind == HJ_STRUCT && S.kind == HJ_STRUCT) {
+            if (D.num != S.num) return fail("Cast between structs of different arity");
+            for (uint32_t k = 0; k < D.num; k++)
+                if (!emit_cast(o, dst + ".e" + std::to_string(k), v.field(D, k), src + ".e" + std::to_string(k), v.field(S, k))) return false;
+            return true;
+        }
+        return fail("Cast between these types is todo!() in the reference (glsl/mod.rs:1017)");
+    }
+};
+
+const char* kPrelude = R"PRELUDE(
+typedef signed char i8; typedef unsigned char u8; typedef short i16; typedef unsigned short u16;
+typedef int i32; typedef unsigned int u32; typedef long long i64; typedef unsigned long long u64;
+typedef float f32; typedef double f64;
+#ifdef HJ_USES_F16
+#include <cuda_fp16.h>
+typedef __half f16;
+#endif
+template <typename D, typename S> __device__ __forceinline__ D hj_bitcast(S s) {
+    static_assert(sizeof(D) == sizeof(S), "bitcast size"); D d; memcpy(&d, &s, sizeof(D)); return d;
+}
+template <typename T> __device__ __forceinline__ void hj_zero(T& x) { memset(&x, 0, sizeof(T)); }
+// atomics: meaning of GLSL atomicAdd/Min/Max/And/Or/Xor on buffer elements (glsl/mod.rs:400-492)
+__device__ __forceinline__ u32 hj_atomic_add(u32* p, u32 v) { return atomicAdd(p, v); }
+__device__ __forceinline__ i32 hj_atomic_add(i32* p, i32 v) { return atomicAdd(p, v); }
+__device__ __forceinline__ u64 hj_atomic_add(u64* p, u64 v) { return atomicAdd(p, v); }
+__device__ __forceinline__ i64 hj_atomic_add(i64* p, i64 v) { return (i64)atomicAdd((u64*)p, (u64)v); }
+__device__ __forceinline__ f32 hj_atomic_add(f32* p, f32 v) { return atomicAdd(p, v); }
+__device__ __forceinline__ f64 hj_atomic_add(f64* p, f64 v) { return atomicAdd(p, v); }
+#define HJ_INT_ATOMIC(name, fn) \
+__device__ __forceinline__ u32 name(u32* p, u32 v) { return fn(p, v); } \
+__device__ __forceinline__ i32 name(i32* p, i32 v) { return fn(p, v); } \
+__device__ __forceinline__ u64 name(u64* p, u64 v) { return fn(p, v); } \
+__device__ __forceinline__ i64 name(i64* p, i64 v) { return fn(p, v); }
+HJ_INT_ATOMIC(hj_atomic_max, atomicMax)
+HJ_INT_ATOMIC(hj_atomic_min, atomicMin)
+__device__ __forceinline__ u32 hj_atomic_or(u32* p, u32 v) { return atomicOr(p, v); }
+__device__ __forceinline__ i32 hj_atomic_or(i32* p, i32 v) { return atomicOr(p, v); }
+__device__ __forceinline__ u64 hj_atomic_or(u64* p, u64 v) { return atomicOr(p, v); }
+__device__ __forceinline__ i64 hj_atomic_or(i64* p, i64 v) { return (i64)atomicOr((u64*)p, (u64)v); }
+__device__ __forceinline__ u32 hj_atomic_and(u32* p, u32 v) { return atomicAnd(p, v); }
+__device__ __forceinline__ i32 hj_atomic_and(i32* p, i32 v) { return atomicAnd(p, v); }
+__device__ __forceinline__ u64 hj_atomic_and(u64* p, u64 v) { return atomicAnd(p, v); }
+__device__ __forceinline__ i64 hj_atomic_and(i64* p, i64 v) { return (i64)atomicAnd((u64*)p, (u64)v); }
+__device__ __forceinline__ u32 hj_atomic_xor(u32* p, u32 v) { return atomicXor(p, v); }
+__device__ __forceinline__ i32 hj_atomic_xor(i32* p, i32 v) { return atomicXor(p, v); }
+__device__ __forceinline__ u64 hj_atomic_xor(u64* p, u64 v) { return atomicXor(p, v); }
+__device__ __forceinline__ i64 hj_atomic_xor(i64* p, i64 v) { return (i64)atomicXor((u64*)p, (u64)v); }
+// float min/max through compare-and-swap (not in the reference's extension set; provided so a
+// trace that uses them fails neither at compile nor at run time)
+__device__ __forceinline__ f32 hj_atomic_max(f32* p, f32 v) {
+    u32 old = *(u32*)p, assumed;
+    do { assumed = old; if (__uint_as_float(assumed) >= v) break; old = atomicCAS((u32*)p, assumed, __float_as_uint(v)); } while (old != assumed);
+    return __uint_as_float(old);
+}
+__device__ __forceinline__ f32 hj_atomic_min(f32* p, f32 v) {
+    u32 old = *(u32*)p, assumed;
+    do { assumed = old; if (__uint_as_float(assumed) <= v) break; old = atomicCAS((u32*)p, assumed, __float_as_uint(v)); } while (old != assumed);
+    return __uint_as_float(old);
+}
+__device__ __forceinline__ f64 hj_atomic_max(f64* p, f64 v) {
+    u64 old = *(u64*)p, assumed;
+    do { assumed = old; if (__longlong_as_double((long long)assumed) >= v) break; old = atomicCAS((u64*)p, assumed, (u64)__double_as_longlong(v)); } while (old != assumed);
+    return __longlong_as_double((long long)old);
+}
+__device__ __forceinline__ f64 hj_atomic_min(f64* p, f64 v) {
+    u64 old = *(u64*)p, assumed;
+    do { assumed = old; if (__longlong_as_double((long long)assumed) <= v) break; old = atomicCAS((u64*)p, assumed, (u64)__double_as_longlong(v)); } while (old != assumed);
+    return __longlong_as_double((long long)old);
+}
+// warp-aggregated counter increment (glsl/mod.rs:493-522); the leader is the lowest ACTIVE
+// lane, not lane 0 (reference defect D8).  Lanes with cond == false get an unspecified value.
+__device__ __forceinline__ u32 hj_atomic_inc(u32* p, bool cond) {
+    unsigned active = __activemask();
+    unsigned m = __ballot_sync(active, cond);
+    int leader = __ffs(active) - 1;
+    unsigned lane = threadIdx.x & 31u;
+    u32 base = 0;
+    if ((int)lane == leader && m) base = atomicAdd(p, (u32)__popc(m));
+    base = __shfl_sync(active, base, leader);
+    return base + (u32)__popc(m & ((1u << lane) - 1u));
+}
+template <int BYTES> struct hj_raw;
+template <> struct hj_raw<1> { typedef u8 type; };
+template <> struct hj_raw<2> { typedef u16 type; };
+template <> struct hj_raw<4> { typedef u32 type; };
+template <> struct hj_raw<8> { typedef uint2 type; };
+template <> struct hj_raw<16> { typedef uint4 type; };
+// one aligned vector of N elements of T, moved with a single 1/2/4/8/16-byte access
+template <typename T, int N> struct __align__(sizeof(T) * N) hj_vec { T e[N]; };
+__device__ __forceinline__ uint4 hj_ldg_raw(const uint4* p) {
+    uint4 r; asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p)); return r;
+}
+__device__ __forceinline__ uint2 hj_ldg_raw(const uint2* p) {
+    uint2 r; asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0,%1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p)); return r;
+}
+__device__ __forceinline__ u32 hj_ldg_raw(const u32* p) { return __ldg(p); }
+__device__ __forceinline__ u16 hj_ldg_raw(const u16* p) { return __ldg(p); }
+__device__ __forceinline__ u8 hj_ldg_raw(const u8* p) { return __ldg(p); }
+template <typename T, int N> __device__ __forceinline__ hj_vec<T, N> hj_load_vec(const void* base, u32 first) {
+    typedef typename hj_raw<sizeof(T) * N>::type R;
+    R raw = hj_ldg_raw((const R*)((const T*)base + first));
+    hj_vec<T, N> v; memcpy(&v, &raw, sizeof(R)); return v;
+}
+template <typename T, int N> __device__ __forceinline__ void hj_store_vec(void* base, u32 first, const hj_vec<T, N>& v) {
+    typedef typename hj_raw<sizeof(T) * N>::type R;
+    R raw; memcpy(&raw, &v, sizeof(R));
+    *(R*)((T*)base + first) = raw;
+}
+)PRELUDE";
+
+}  // namespace
+
+bool codegen_cuda(const hj_ir* ir, CodegenResult* out, std::string* err) {
+    std::string verr = validate_ir(ir);
+    if (!verr.empty()) { *err = verr; return false; }
+    Gen g(ir);
+    for (uint32_t i = 0; i < ir->n_vars; i++) g.declare_type(ir->vars[i].ty);
+    if (!g.analyse()) { *err = g.err; return false; }
+
+    // vector geometry: 16 bytes per access for the widest staged element type
+    size_t widest = 0;
+    bool any_staged = false;
+    for (auto& s : g.slots)
+        if (s.stage_load || s.stage_store) { any_staged = true; widest = std::max(widest, scalar_size(s.elem_kind)); }
+    uint32_t vec = widest == 8 ? 2 : 4;
+    uint32_t unroll = 2;
+    if (const char* e = getenv("HJ_JIT_UNROLL")) { int u = atoi(e); if (u >= 1 && u <= 8) unroll = (uint32_t)u; }
+    const uint32_t threads = 256;
+
+    std::ostringstream scalar_body, staged_body;
+    if (!g.emit_body(scalar_body, false)) { *err = g.err; return false; }
+    if (any_staged && !g.emit_body(staged_body, true)) { *err = g.err; return false; }
+
+    std::ostringstream s;
+    if (g.uses_f16) s << "#define HJ_USES_F16 1\n";
+    s << kPrelude << "\n" << g.types.str() << "\n";
+    std::string params = "const u32* __restrict__ size_ptr, u32 size_static, u32 index_base";
+    std::string args = "";
+    for (uint32_t b = 0; b < ir->n_buffers; b++) {
+        params += ", void* __restrict__ b" + std::to_string(b);
+        args += ", b" + std::to_string(b);
+    }
+    // __restrict__ on buffers that alias (the same buffer bound to two slots) would be wrong;
+    // the launcher checks for duplicates and the IR never binds one resource twice
+    // (compiler.rs:187-189 dedups through an IndexSet).
+    s << "__device__ __forceinline__ void hj_element(u32 index, u32 gindex";
+    for (uint32_t b = 0; b < ir->n_buffers; b++) s << ", void* __restrict__ b" << b;
+    s << ") {\n" << scalar_body.str() << "}\n\n";
+
+    s << "#define HJ_SIZE() u32 size = size_static; if (size_ptr) { u32 dyn = *size_ptr; size = dyn < size ? dyn : size; }\n\n";
+    // one invocation per element; `if (index >= size) return;` (glsl/mod.rs:129-133)
+    s << "extern \"C\" __global__ void __launch_bounds__(" << threads << ") hj_kernel_scalar(" << params << ") {\n"
+      << "    HJ_SIZE();\n"
+      << "    u32 index = blockIdx.x * " << threads << "u + threadIdx.x;\n"
+      << "    if (index >= size) return;\n"
+      << "    hj_element(index, index_base + index" << args << ");\n}\n\n";
+
+    if (any_staged) {
+        const uint32_t tile = threads * vec * unroll;
+        s << "extern \"C\" __global__ void __launch_bounds__(" << threads << ") hj_kernel_vec(" << params << ") {\n"
+          << "    HJ_SIZE();\n"
+          << "    const u32 tile = blockIdx.x * " << tile << "u;\n"
+          << "    if (tile >= size) return;\n"
+          << "    if (size - tile >= " << tile << "u) {\n";
+        for (uint32_t b = 0; b < ir->n_buffers; b++) {
+            const auto& sl = g.slots[b];
+            const char* et = sl.elem_kind == HJ_BOOL ? "u8" : kScalarNames[sl.elem_kind];
+            if (sl.stage_load) s << "        hj_vec<" << et << ", " << vec << "> in_" << b << "[" << unroll << "];\n";
+            if (sl.stage_store) s << "        hj_vec<" << et << ", " << vec << "> out_" << b << "[" << unroll << "];\n";
+        }
+        s << "        _Pragma(\"unroll\") for (int u = 0; u < " << unroll << "; u++) {\n"
+          << "            const u32 first = tile + (u * " << threads << "u + threadIdx.x) * " << vec << "u;\n";
+        for (uint32_t b = 0; b < ir->n_buffers; b++) {
+            const auto& sl = g.slots[b];
+            const char* et = sl.elem_kind == HJ_BOOL ? "u8" : kScalarNames[sl.elem_kind];
+            if (sl.stage_load) s << "            in_" << b << "[u] = hj_load_vec<" << et << ", " << vec << ">(b" << b << ", first);\n";
+        }
+        s << "        }\n"
+          << "        _Pragma(\"unroll\") for (int u = 0; u < " << unroll << "; u++) {\n"
+          << "            _Pragma(\"unroll\") for (int k = 0; k < " << vec << "; k++) {\n"
+          << "                const u32 index = tile + (u * " << threads << "u + threadIdx.x) * " << vec << "u + k;\n"
+          << "                const u32 gindex = index_base + index;\n"
+          << staged_body.str()
+          << "            }\n        }\n"
+          << "        _Pragma(\"unroll\") for (int u = 0; u < " << unroll << "; u++) {\n"
+          << "            const u32 first = tile + (u * " << threads << "u + threadIdx.x) * " << vec << "u;\n";
+        for (uint32_t b = 0; b < ir->n_buffers; b++) {
+            const auto& sl = g.slots[b];
+            const char* et = sl.elem_kind == HJ_BOOL ? "u8" : kScalarNames[sl.elem_kind];
+            if (sl.stage_store) s << "            hj_store_vec<" << et << ", " << vec << ">(b" << b << ", first, out_" << b << "[u]);\n";
+        }
+        s << "        }\n"
+          << "    } else {\n"
+          << "        for (u32 e = threadIdx.x; e < " << tile << "u; e += " << threads << "u) {\n"
+          << "            u32 index = tile + e;\n"
+          << "            if (index < size) hj_element(index, index_base + index" << args << ");\n"
+          << "        }\n    }\n}\n";
+    }
+    out->source = s.str();
+    out->has_vec_entry = any_staged;
+    out->vec = vec;
+    out->unroll = unroll;
+    out->threads = threads;
+    out->uses_f16 = g.uses_f16;
+    return true;
+}
+
+}  // namespace hj

@@ -1,0 +1,56 @@
+// ir.h — C++ view over the flat hj_ir (mirror of hephaestus-jit/src/ir.rs:12-46) plus the
+// VarType layout rules (hephaestus-jit/src/vartype.rs:125-189).
+#pragma once
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include "../../include/hj.h"
+
+namespace hj {
+
+struct IRView {
+    const hj_ir* ir;
+    explicit IRView(const hj_ir* p) : ir(p) {}
+    uint32_t n_vars() const { return ir->n_vars; }
+    const hj_ir_var& var(uint32_t i) const { return ir->vars[i]; }
+    uint32_t n_deps(uint32_t i) const { return ir->vars[i].dep_end - ir->vars[i].dep_start; }
+    uint32_t dep(uint32_t i, uint32_t k) const { return ir->deps[ir->vars[i].dep_start + k]; }
+    const hj_type_desc& type(uint32_t t) const { return ir->types[t]; }
+    uint32_t field(const hj_type_desc& t, uint32_t k) const { return ir->struct_fields[t.first_field + k]; }
+    uint32_t var_type(uint32_t i) const { return ir->vars[i].ty; }
+    hj_type_kind kind(uint32_t t) const { return (hj_type_kind)ir->types[t].kind; }
+};
+
+// Structural validation (indices in range, dep counts per op, no out-of-scope ops).
+// Returns an empty string when the IR is well formed, else a description of the problem.
+std::string validate_ir(const hj_ir* ir);
+
+// vartype.rs:125-189
+size_t type_size(const IRView& v, uint32_t t);
+size_t type_align(const IRView& v, uint32_t t);
+size_t struct_offset(const IRView& v, uint32_t t, uint32_t elem);
+
+inline bool is_scalar_kind(uint32_t k) { return k >= HJ_BOOL && k <= HJ_F64; }
+inline bool is_float_kind(uint32_t k) { return k == HJ_F16 || k == HJ_F32 || k == HJ_F64; }
+inline bool is_int_kind(uint32_t k) { return k >= HJ_I8 && k <= HJ_U64; }
+inline bool is_signed_kind(uint32_t k) { return k == HJ_I8 || k == HJ_I16 || k == HJ_I32 || k == HJ_I64; }
+
+// Debug text of an IR in the format of `impl Debug for IR` (ir.rs:47-90), used by the
+// snapshot-parity tests.
+std::string ir_debug_string(const hj_ir* ir);
+
+struct CodegenResult {
+    std::string source;
+    bool has_vec_entry = false;  // "hj_kernel_vec" present (all stores are Index-addressed)
+    uint32_t vec = 1;            // elements per vector access
+    uint32_t unroll = 1;         // vectors per thread
+    uint32_t threads = 256;
+    bool uses_f16 = false;
+};
+// Lower `ir` to CUDA C++; on failure returns false and sets `err`.
+bool codegen_cuda(const hj_ir* ir, CodegenResult* out, std::string* err);
+
+uint64_t hash_bytes(const void* data, size_t n, uint64_t seed = 0xcbf29ce484222325ull);
+
+}  // namespace hj

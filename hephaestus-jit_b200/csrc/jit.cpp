@@ -1,0 +1,248 @@
+// jit.cpp — NVRTC compilation of fused-kernel IR to sm_100a cubins, kernel caches, launch.
+//
+// Plays the role of VulkanDevice::compile_ir + Pipeline::create
+// (hephaestus-jit/src/backend/vulkan/mod.rs:83-91, vulkan_core/pipeline.rs:30-46: an
+// in-memory pipeline cache keyed by the hash of the definition) and of the Kernel arm of
+// execute_graph (vulkan/mod.rs:194-257).  Additions: an on-disk cubin cache (the reference
+// recompiles every process start) and a vectorised entry point (codegen.cpp).
+#include <nvrtc.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
+#include <cstdlib>
+#include <fstream>
+
+#include "hj_internal.h"
+#include "ir.h"
+
+struct hj_kernel {
+    std::atomic<int> rc{1};
+    uint64_t hash = 0;
+    cudaLibrary_t lib = nullptr;
+    cudaKernel_t scalar = nullptr;
+    cudaKernel_t vec = nullptr;
+    uint32_t vec_width = 1, unroll = 1, threads = 256, n_buffers = 0;
+};
+
+namespace hj {
+
+struct KernelCache {
+    std::mutex mu;
+    std::unordered_map<uint64_t, hj_kernel*> kernels;
+    uint64_t n_compiled = 0, n_hits = 0, n_disk_hits = 0;
+};
+
+namespace {
+
+std::string cache_dir() {
+    if (const char* d = getenv("HJ_CACHE_DIR")) return *d ? std::string(d) : std::string();
+    const char* home = getenv("HOME");
+    return std::string(home && *home ? home : "/tmp") + "/.cache/hj_b200";
+}
+
+void mkdirs(const std::string& p) {
+    std::string cur;
+    for (size_t i = 0; i < p.size(); i++) {
+        cur += p[i];
+        if (p[i] == '/' || i + 1 == p.size()) mkdir(cur.c_str(), 0755);
+    }
+}
+
+const char* kArch = "sm_100a";
+
+hj_status nvrtc_compile(const CodegenResult& cg, std::vector<char>* cubin) {
+    nvrtcProgram prog;
+    nvrtcResult r = nvrtcCreateProgram(&prog, cg.source.c_str(), "hj_fused.cu", 0, nullptr, nullptr);
+    if (r != NVRTC_SUCCESS) return fail(HJ_ERR_NVRTC, "nvrtcCreateProgram: %s", nvrtcGetErrorString(r));
+    std::vector<const char*> opts = {"--gpu-architecture=sm_100a", "-std=c++17", "-default-device", "-lineinfo"};
+    if (cg.uses_f16) opts.push_back("--include-path=/usr/local/cuda/include");
+    if (getenv("HJ_FAST_MATH")) opts.push_back("--use_fast_math");
+    r = nvrtcCompileProgram(prog, (int)opts.size(), opts.data());
+    if (r != NVRTC_SUCCESS) {
+        size_t n = 0;
+        nvrtcGetProgramLogSize(prog, &n);
+        std::string log(n, '\0');
+        if (n) nvrtcGetProgramLog(prog, &log[0]);
+        nvrtcDestroyProgram(&prog);
+        if (getenv("HJ_LOG")) fprintf(stderr, "[hj] NVRTC source:\n%s\n", cg.source.c_str());
+        return fail(HJ_ERR_NVRTC, "NVRTC compilation failed: %s\n%.700s", nvrtcGetErrorString(r), log.c_str());
+    }
+    size_t sz = 0;
+    r = nvrtcGetCUBINSize(prog, &sz);
+    if (r != NVRTC_SUCCESS || sz == 0) {
+        nvrtcDestroyProgram(&prog);
+        return fail(HJ_ERR_NVRTC, "nvrtcGetCUBINSize: %s", nvrtcGetErrorString(r));
+    }
+    cubin->resize(sz);
+    r = nvrtcGetCUBIN(prog, cubin->data());
+    nvrtcDestroyProgram(&prog);
+    if (r != NVRTC_SUCCESS) return fail(HJ_ERR_NVRTC, "nvrtcGetCUBIN: %s", nvrtcGetErrorString(r));
+    return HJ_OK;
+}
+
+// cubin for `ir`: on-disk cache keyed by (source hash, arch, NVRTC version), else NVRTC.
+hj_status get_cubin(const hj_ir* ir, CodegenResult* cg, std::vector<char>* cubin, bool* from_disk) {
+    std::string err;
+    if (!codegen_cuda(ir, cg, &err)) return fail(HJ_ERR_INVALID, "IR rejected: %s", err.c_str());
+    *from_disk = false;
+    int maj = 0, min = 0;
+    nvrtcVersion(&maj, &min);
+    uint64_t key = hash_bytes(cg->source.data(), cg->source.size());
+    key = hash_bytes(kArch, strlen(kArch), key);
+    int ver[3] = {maj, min, getenv("HJ_FAST_MATH") ? 1 : 0};
+    key = hash_bytes(ver, sizeof(ver), key);
+    std::string dir = cache_dir();
+    char name[64];
+    snprintf(name, sizeof(name), "/%016llx.cubin", (unsigned long long)key);
+    if (!dir.empty()) {
+        std::ifstream f(dir + name, std::ios::binary);
+        if (f) {
+            cubin->assign(std::istreambuf_iterator<char>(f), std::istreambuf_iterator<char>());
+            if (cubin->size() > 64) { *from_disk = true; return HJ_OK; }
+        }
+    }
+    HJ_TRY(nvrtc_compile(*cg, cubin));
+    if (!dir.empty()) {
+        mkdirs(dir);
+        std::string tmp = dir + name + "." + std::to_string((long)getpid()) + ".tmp";
+        std::ofstream f(tmp, std::ios::binary);
+        if (f) {
+            f.write(cubin->data(), (std::streamsize)cubin->size());
+            f.close();
+            rename(tmp.c_str(), (dir + name).c_str());  // atomic publish
+        }
+    }
+    return HJ_OK;
+}
+
+}  // namespace
+}  // namespace hj
+
+using namespace hj;
+
+extern "C" {
+
+hj_status hj_ir_codegen(const hj_ir* ir, char** out_source) {
+    HJ_REQUIRE(ir && out_source, "null argument");
+    CodegenResult cg;
+    std::string err;
+    if (!codegen_cuda(ir, &cg, &err)) return fail(HJ_ERR_INVALID, "IR rejected: %s", err.c_str());
+    char* s = (char*)malloc(cg.source.size() + 1);
+    if (!s) return fail(HJ_ERR_OOM, "out of host memory");
+    memcpy(s, cg.source.c_str(), cg.source.size() + 1);
+    *out_source = s;
+    return HJ_OK;
+}
+
+void hj_free_string(char* s) { free(s); }
+
+hj_status hj_ir_compile_cubin(const hj_ir* ir, void** out_cubin, size_t* out_size) {
+    HJ_REQUIRE(ir && out_cubin && out_size, "null argument");
+    CodegenResult cg;
+    std::vector<char> cubin;
+    bool disk = false;
+    HJ_TRY(get_cubin(ir, &cg, &cubin, &disk));
+    void* p = malloc(cubin.size());
+    if (!p) return fail(HJ_ERR_OOM, "out of host memory");
+    memcpy(p, cubin.data(), cubin.size());
+    *out_cubin = p;
+    *out_size = cubin.size();
+    return HJ_OK;
+}
+
+hj_status hj_kernel_get(hj_device* dev, const hj_ir* ir, hj_kernel** out) {
+    HJ_REQUIRE(dev && ir && out, "null argument");
+    uint64_t h = hj_ir_hash(ir);
+    {
+        std::lock_guard<std::mutex> g(dev->mu);
+        if (!dev->kcache) dev->kcache = new KernelCache();
+    }
+    KernelCache* kc = dev->kcache;
+    std::lock_guard<std::mutex> g(kc->mu);
+    auto it = kc->kernels.find(h);
+    if (it != kc->kernels.end()) {
+        kc->n_hits++;
+        it->second->rc.fetch_add(1);
+        *out = it->second;
+        return HJ_OK;
+    }
+    CodegenResult cg;
+    std::vector<char> cubin;
+    bool disk = false;
+    HJ_TRY(get_cubin(ir, &cg, &cubin, &disk));
+    cudaSetDevice(dev->ordinal);
+    auto k = new hj_kernel();
+    k->hash = h;
+    cudaError_t e = cudaLibraryLoadData(&k->lib, cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0);
+    if (e == cudaSuccess) e = cudaLibraryGetKernel(&k->scalar, k->lib, "hj_kernel_scalar");
+    if (e == cudaSuccess && cg.has_vec_entry) e = cudaLibraryGetKernel(&k->vec, k->lib, "hj_kernel_vec");
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        if (k->lib) cudaLibraryUnload(k->lib);
+        delete k;
+        return fail(HJ_ERR_CUDA, "loading the compiled kernel failed: %s", cudaGetErrorString(e));
+    }
+    k->vec_width = cg.vec;
+    k->unroll = cg.unroll;
+    k->threads = cg.threads;
+    k->n_buffers = ir->n_buffers;
+    if (disk) kc->n_disk_hits++;
+    else kc->n_compiled++;
+    k->rc.store(2);  // cache + caller
+    kc->kernels[h] = k;
+    *out = k;
+    return HJ_OK;
+}
+
+hj_status hj_kernel_release(hj_kernel* k) {
+    HJ_REQUIRE(k, "null kernel");
+    k->rc.fetch_sub(1);  // the per-device cache keeps compiled kernels for the process lifetime
+    return HJ_OK;
+}
+
+hj_status hj_device_kernel_cache_stats(hj_device* dev, uint64_t* n_compiled, uint64_t* n_hits,
+                                       uint64_t* n_disk_hits) {
+    HJ_REQUIRE(dev, "null device");
+    KernelCache* kc = dev->kcache;
+    if (n_compiled) *n_compiled = kc ? kc->n_compiled : 0;
+    if (n_hits) *n_hits = kc ? kc->n_hits : 0;
+    if (n_disk_hits) *n_disk_hits = kc ? kc->n_disk_hits : 0;
+    return HJ_OK;
+}
+
+hj_status hj_kernel_launch(hj_device* dev, hj_kernel* k, size_t size, hj_buffer* size_buf,
+                           hj_buffer* const* buffers, uint32_t n_buffers, uint32_t index_base) {
+    HJ_REQUIRE(dev && k, "null argument");
+    HJ_REQUIRE(n_buffers == k->n_buffers, "kernel expects %u buffers, got %u", k->n_buffers, n_buffers);
+    HJ_REQUIRE(size <= 0xffffffffull, "kernel size does not fit the u32 index type (trace.rs:552-562)");
+    if (size == 0) return HJ_OK;
+    std::vector<void*> ptrs(n_buffers);
+    bool aligned = true;
+    for (uint32_t i = 0; i < n_buffers; i++) {
+        HJ_REQUIRE(buffers && buffers[i], "buffer %u is null", i);
+        ptrs[i] = buffers[i]->ptr;
+        if ((uintptr_t)ptrs[i] & 15u) aligned = false;
+    }
+    const uint32_t* size_ptr = size_buf ? (const uint32_t*)size_buf->ptr : nullptr;
+    uint32_t size_static = (uint32_t)size;
+    std::vector<void*> args;
+    args.push_back((void*)&size_ptr);
+    args.push_back((void*)&size_static);
+    args.push_back((void*)&index_base);
+    for (uint32_t i = 0; i < n_buffers; i++) args.push_back((void*)&ptrs[i]);
+
+    DeviceGuard g(dev);
+    const bool use_vec = k->vec && aligned && !getenv("HJ_JIT_SCALAR");
+    const size_t per_block = use_vec ? (size_t)k->threads * k->vec_width * k->unroll : k->threads;
+    const unsigned grid = (unsigned)((size + per_block - 1) / per_block);
+    cudaError_t e = cudaLaunchKernel((const void*)(use_vec ? k->vec : k->scalar), dim3(grid), dim3(k->threads),
+                                     args.data(), 0, dev->stream);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return fail(HJ_ERR_CUDA, "launch of fused kernel failed: %s", cudaGetErrorString(e));
+    }
+    dev->launches.fetch_add(1, std::memory_order_relaxed);
+    return HJ_OK;
+}
+
+}  // extern "C"

@@ -77,34 +77,79 @@ __device__ __forceinline__ uint32_t tile_read(const LookbackView& lb, uint32_t t
 }
 
 // Executed by one full warp of tile `tile` (> 0): returns (in every lane) the sum of the
-// aggregates of all predecessor tiles.  Lane l inspects tile - 1 - l - 32*k in round k.
-template <typename P>
+// aggregates of all predecessor tiles.
+//
+// Window width matters on B200: with ~900 tiles in flight the tiles of a wave are
+// contemporaries, so a tile has to walk back over every in-flight predecessor until it meets
+// one whose inclusive prefix is published, and the "inclusive frontier" advances by one
+// window per L2 round trip.  With the classic 32-wide window (one status word per lane, as in
+// the reference, prefix_sum_large.glsl:281-309) that caps the whole kernel at
+// 32 tiles x tile bytes / round trip (measured: 2.8 TB/s for 32 KiB of traffic per tile).
+// Here every lane inspects M consecutive predecessors per round (M independent loads in
+// flight), i.e. a 32*M-wide window; lane l covers tiles win - l*M - m, m = 0..M-1.
+template <typename P, int M = 4>
 __device__ __forceinline__ P tile_lookback(const LookbackView& lb, uint32_t tile) {
     const int lane = lane_id();
     P prefix = (P)0;
-    long long idx = (long long)tile - 1 - lane;
-    while (true) {
-        P v = (P)0;
-        uint32_t state = TILE_INCLUSIVE;  // virtual tiles before tile 0: inclusive, value 0
-        if (idx >= 0) {
-            do {
-                state = tile_read<P>(lb, (uint32_t)idx, &v);
-            } while (state == TILE_INVALID);
+    long long win = (long long)tile - 1;  // nearest tile of the current window
+    // Tiles publish roughly in ticket order, so first wait (ONE polled word per tile, with
+    // back-off) until the nearest predecessor has published anything; only then read windows.
+    // Polling whole windows from ~600 resident tiles at once floods the L2 slices that hold
+    // the frontier's status lines and delays the very stores everybody is waiting for.
+    if (lane == 0) {
+        P dummy;
+        unsigned ns = 32;
+        while (tile_read<P>(lb, tile - 1, &dummy) == TILE_INVALID) {
+            __nanosleep(ns);
+            if (ns < 256) ns *= 2;
         }
-        // every lane has a valid predecessor now
-        unsigned incl_mask = __ballot_sync(0xffffffffu, state == TILE_INCLUSIVE);
-        if (incl_mask) {
-            int first = __ffs(incl_mask) - 1;  // nearest predecessor whose full prefix is known
-            P c = lane <= first ? v : (P)0;
+    }
+    __syncwarp();
+    while (true) {
+        P v[M];
+        uint32_t st[M];
 #pragma unroll
-            for (int m = 16; m > 0; m >>= 1) c = (P)(c + shfl_xor(c, m));
+        for (int m = 0; m < M; m++) {
+            long long idx = win - (long long)lane * M - m;
+            v[m] = (P)0;
+            st[m] = TILE_INCLUSIVE;  // virtual tiles before tile 0: inclusive, value 0
+            if (idx >= 0) st[m] = tile_read<P>(lb, (uint32_t)idx, &v[m]);
+        }
+        // fold this lane's tiles nearest -> farthest: stop at the first inclusive (done) or the
+        // first not-yet-published one (blocked)
+        P sum = (P)0;
+        int kind = 0;  // 0: all aggregates, 1: reached an inclusive prefix, 2: blocked
+#pragma unroll
+        for (int m = 0; m < M; m++) {
+            if (kind == 0) {
+                if (st[m] == TILE_INVALID) kind = 2;
+                else {
+                    sum = (P)(sum + v[m]);
+                    if (st[m] == TILE_INCLUSIVE) kind = 1;
+                }
+            }
+        }
+        const unsigned incl_mask = __ballot_sync(0xffffffffu, kind == 1);
+        const unsigned blocked_mask = __ballot_sync(0xffffffffu, kind == 2);
+        const int first_incl = incl_mask ? __ffs(incl_mask) - 1 : 32;
+        const int first_blocked = blocked_mask ? __ffs(blocked_mask) - 1 : 32;
+        if (first_incl < first_blocked) {  // everything up to the nearest inclusive is known
+            P c = lane <= first_incl ? sum : (P)0;
+#pragma unroll
+            for (int s = 16; s > 0; s >>= 1) c = (P)(c + shfl_xor(c, s));
             return (P)(prefix + c);
         }
-        P c = v;
+        if (first_blocked == 32) {  // a full window of aggregates: accumulate, step back
+            P c = sum;
 #pragma unroll
-        for (int m = 16; m > 0; m >>= 1) c = (P)(c + shfl_xor(c, m));
-        prefix = (P)(prefix + c);
-        idx -= 32;
+            for (int s = 16; s > 0; s >>= 1) c = (P)(c + shfl_xor(c, s));
+            prefix = (P)(prefix + c);
+            win -= 32 * M;
+        }
+        else {
+            // a needed predecessor has not published yet -> poll the same window again, later
+            __nanosleep(128);
+        }
     }
 }
 

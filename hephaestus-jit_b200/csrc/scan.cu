@@ -1,42 +1,83 @@
-// scan.cu — single-pass inclusive/exclusive prefix sum (decoupled look-back) for sm_100a.
+// scan.cu — single-launch inclusive/exclusive prefix sum for sm_100a:
+// decoupled look-back between 64 KiB super-tiles, two sweeps per super-tile through L2.
 //
 // Replaces builtin::prefix_sum::prefix_sum_large
 // (hephaestus-jit/src/backend/vulkan/builtin/prefix_sum.rs:31-162 +
-// kernels/prefix_sum_large.glsl + prefix_sum_large_init.glsl).  Differences by design:
-//   * tile = 256 threads x NLOADS 128-bit vectors (16 KiB for 4/8-byte types, 8x the
-//     reference's 2048-item partition) so that enough bytes are in flight per SM for HBM3e;
-//   * vectors are consumed in the order they are loaded (vector-striped layout), so there is
-//     no shared-memory transpose: per-vector sums are scanned with warp shuffles, the
-//     NLOADS x 8 warp totals by one warp;
-//   * no separate init dispatch (epoch-tagged status words, lookback.cuh);
-//   * the tail is masked in the kernel; nothing is read or written beyond n (reference D7);
-//   * true exclusive and inclusive variants (reference D10), correct for f32/u64/f64 (D3);
-//   * `seed` adds a device-resident offset to every output — the cross-GPU carry of the
-//     sharded scan — at no extra pass.
-// Algorithmic bytes: 2 * sizeof(T) per element (read once, write once); HBM-bound.
+// kernels/prefix_sum_large.glsl + prefix_sum_large_init.glsl).
+//
+// Why not the textbook register-resident single sweep (which the reference uses with
+// 2048-item partitions)?  Measured on B200 (profiles/r01_scan_design.md): with ~600 tiles
+// resident, a tile waits ~7 us for its predecessors' aggregates (three dependent L2 round
+// trips at loaded-fabric latency) while holding its 32 KiB of data in registers; resident
+// bytes / lifetime then caps the kernel at 48 % of the HBM roofline no matter the tile size
+// or the look-back window.  Here the wait holds almost nothing:
+//   sweep 1  each warp streams its contiguous 8 KiB segment of the super-tile (16 coalesced
+//            512-byte rows, all loads in flight, L2 evict_last) and only SUMS it;
+//            warp totals -> block aggregate -> publish -> look-back (lookback.cuh);
+//   sweep 2  each warp re-reads its rows — they are still in the 126 MB L2 (resident
+//            super-tiles total < 64 MB) — scans each row with shuffles and a running carry,
+//            adds the tile prefix and streams the result out (evict_first).
+// DRAM traffic stays at the algorithmic 2 * sizeof(T) bytes per element; the second read is
+// L2 traffic.  Other differences from the reference: no separate init dispatch (epoch-tagged
+// status words), tail masked in the kernel (D7), true exclusive and inclusive variants (D10),
+// correct carries for f32/u64/f64 (D3), and `seed`: a device-resident offset added to every
+// output (the cross-GPU carry of the sharded scan) at no extra pass.
 #include <type_traits>
 
 #include "hj_internal.h"
 #include "lookback.cuh"
 
 namespace hj {
+unsigned long long* g_scan_trace = nullptr;  // set through hj_debug_scan_trace()
 namespace {
 
 constexpr int SCAN_THREADS = 256;
 constexpr int SCAN_WARPS = SCAN_THREADS / 32;
+constexpr int SCAN_ROWS = 16;   // 512-byte rows per warp  -> 8 KiB per warp, 64 KiB per CTA
+constexpr int SCAN_BATCH = 4;   // rows loaded together in sweep 2
+// A CTA waiting for its prefix holds no data, only thread slots: run at full occupancy
+// (8 x 256 threads, <= 32 registers) so that enough CTAs are always streaming.
+constexpr int SCAN_CTAS_PER_SM = 8;
 
-template <typename T, typename P, int NLOADS, bool INCLUSIVE>
-__global__ void __launch_bounds__(SCAN_THREADS)
+// L2 eviction policies (createpolicy + .L2::cache_hint; the bare .L2::evict_* qualifiers are
+// only accepted on 256-bit accesses on sm_100a).
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ uint4 ld_hint_v4(const void* p, uint64_t pol) {
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.u32 {%0,%1,%2,%3}, [%4], %5;"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+                 : "l"(p), "l"(pol));
+    return r;
+}
+__device__ __forceinline__ void st_hint_v4(void* p, uint4 v, uint64_t pol) {
+    asm volatile("st.global.L1::no_allocate.L2::cache_hint.v4.u32 [%0], {%1,%2,%3,%4}, %5;" ::"l"(p),
+                 "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "l"(pol)
+                 : "memory");
+}
+
+template <typename T, typename P, bool INCLUSIVE>
+__global__ void __launch_bounds__(SCAN_THREADS, SCAN_CTAS_PER_SM)
 scan_kernel(const T* __restrict__ src, T* __restrict__ dst, size_t n, const T* __restrict__ seed,
-            LookbackView lb, int vec_ok) {
+            LookbackView lb, int vec_ok, unsigned long long* __restrict__ trace) {
     constexpr int VEC = 16 / sizeof(T);
-    constexpr int TILE = SCAN_THREADS * NLOADS * VEC;
-    static_assert(NLOADS * SCAN_WARPS <= 32, "warp totals must fit one warp");
+    constexpr int ROW = 32 * VEC;              // elements per coalesced warp row
+    constexpr int SEG = SCAN_ROWS * ROW;       // elements per warp
+    constexpr int TILE = SCAN_WARPS * SEG;     // elements per CTA
     __shared__ uint32_t s_tile;
-    __shared__ P s_warp[NLOADS * SCAN_WARPS];
-    __shared__ P s_prefix;
+    __shared__ P s_warp[SCAN_WARPS];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    unsigned long long t_start = 0, t_summed = 0, t_prefix = 0;
+    if (trace && tid == 0) t_start = globaltimer_ns();
     if (tid == 0) {
         uint32_t t = atomicAdd(lb.ticket, 1u);
         if (t == gridDim.x - 1) *lb.ticket = 0;  // last ticket: re-arm for the next launch
@@ -46,52 +87,43 @@ scan_kernel(const T* __restrict__ src, T* __restrict__ dst, size_t n, const T* _
     const uint32_t tile = s_tile;
     const size_t base = (size_t)tile * TILE;
     const bool full = vec_ok && base + TILE <= n;
+    const size_t lane_base = base + (size_t)warp * SEG + lane * VEC;  // this lane's vector in row 0
 
-    // ---- load: vector (i, tid) sits at element offset (i*THREADS + tid)*VEC of the tile
-    P x[NLOADS][VEC];
+    const uint64_t keep = l2_policy_evict_last();    // sweep-1 lines are re-read in sweep 2
+    const uint64_t drop = l2_policy_evict_first();   // sweep-2 reads and the output are final
+
+    // ---- sweep 1: total of this warp's segment
+    P total = (P)0;
     if (full) {
-        uint4 raw[NLOADS];
-        const uint4* vsrc = reinterpret_cast<const uint4*>(src + base);
+        const uint4* vsrc = reinterpret_cast<const uint4*>(src + lane_base);
+        uint4 raw[SCAN_ROWS];
 #pragma unroll
-        for (int i = 0; i < NLOADS; i++) raw[i] = ld_stream_v4(vsrc + i * SCAN_THREADS + tid);
+        for (int r = 0; r < SCAN_ROWS; r++) raw[r] = ld_hint_v4(vsrc + r * 32, keep);
 #pragma unroll
-        for (int i = 0; i < NLOADS; i++) {
-            const T* e = reinterpret_cast<const T*>(&raw[i]);
+        for (int r = 0; r < SCAN_ROWS; r++) {
+            const T* e = reinterpret_cast<const T*>(&raw[r]);
 #pragma unroll
-            for (int j = 0; j < VEC; j++) x[i][j] = (P)e[j];
+            for (int j = 0; j < VEC; j++) total = (P)(total + (P)e[j]);
         }
     } else {
-#pragma unroll
-        for (int i = 0; i < NLOADS; i++)
-#pragma unroll
+        for (int r = 0; r < SCAN_ROWS; r++)
             for (int j = 0; j < VEC; j++) {
-                size_t e = base + (size_t)(i * SCAN_THREADS + tid) * VEC + j;
-                x[i][j] = e < n ? (P)src[e] : (P)0;
+                size_t e = lane_base + (size_t)r * ROW + j;
+                if (e < n) total = (P)(total + (P)src[e]);
             }
     }
-
-    // ---- per-vector sums, warp scans, warp totals
-    P excl_in_warp[NLOADS];
 #pragma unroll
-    for (int i = 0; i < NLOADS; i++) {
-        P s = x[i][0];
-#pragma unroll
-        for (int j = 1; j < VEC; j++) s = (P)(s + x[i][j]);
-        P inc = warp_inclusive_sum(s);
-        if (lane == 31) s_warp[i * SCAN_WARPS + warp] = inc;
-        P up = shfl_up(inc, 1);
-        excl_in_warp[i] = lane == 0 ? (P)0 : up;
-    }
+    for (int m = 16; m > 0; m >>= 1) total = (P)(total + shfl_xor(total, m));
+    if (lane == 0) s_warp[warp] = total;
     __syncthreads();
+    if (trace && tid == 0) t_summed = globaltimer_ns();
 
-    // ---- warp 0: scan the NLOADS*WARPS totals, then resolve the tile prefix by look-back
+    // ---- warp 0: scan the warp totals, resolve the tile prefix by look-back
     if (warp == 0) {
-        constexpr int NT = NLOADS * SCAN_WARPS;
-        P v = lane < NT ? s_warp[lane] : (P)0;
+        P v = lane < SCAN_WARPS ? s_warp[lane] : (P)0;
         P inc = warp_inclusive_sum(v);
         P aggregate = shfl_idx(inc, 31);
         P up = shfl_up(inc, 1);
-        if (lane < NT) s_warp[lane] = lane == 0 ? (P)0 : up;
         P exclusive;
         if (tile == 0) {
             exclusive = seed ? (P)seed[0] : (P)0;
@@ -101,38 +133,79 @@ scan_kernel(const T* __restrict__ src, T* __restrict__ dst, size_t n, const T* _
             exclusive = tile_lookback<P>(lb, tile);
             if (lane == 0) tile_publish<P>(lb, tile, TILE_INCLUSIVE, (P)(exclusive + aggregate));
         }
-        if (lane == 0) s_prefix = exclusive;
+        // offset of each warp's segment = tile prefix + totals of the warps before it
+        if (lane < SCAN_WARPS) s_warp[lane] = (P)(exclusive + (lane == 0 ? (P)0 : up));
     }
     __syncthreads();
-    const P tile_prefix = s_prefix;
+    if (trace && tid == 0) t_prefix = globaltimer_ns();
 
-    // ---- finish: running sum inside each vector, store
+    // ---- sweep 2: re-read (L2), scan rows with a running carry, store
+    P carry = s_warp[warp];
+    if (full) {
+        const uint4* vsrc = reinterpret_cast<const uint4*>(src + lane_base);
+        uint4* vdst = reinterpret_cast<uint4*>(dst + lane_base);
+#pragma unroll 1
+        for (int r0 = 0; r0 < SCAN_ROWS; r0 += SCAN_BATCH) {
+            uint4 raw[SCAN_BATCH];
 #pragma unroll
-    for (int i = 0; i < NLOADS; i++) {
-        P run = (P)(tile_prefix + (P)(s_warp[i * SCAN_WARPS + warp] + excl_in_warp[i]));
-        T out[VEC];
+            for (int b = 0; b < SCAN_BATCH; b++) raw[b] = ld_hint_v4(vsrc + (r0 + b) * 32, drop);
 #pragma unroll
-        for (int j = 0; j < VEC; j++) {
-            if (INCLUSIVE) { run = (P)(run + x[i][j]); out[j] = (T)run; }
-            else { out[j] = (T)run; run = (P)(run + x[i][j]); }
+            for (int b = 0; b < SCAN_BATCH; b++) {
+                const T* e = reinterpret_cast<const T*>(&raw[b]);
+                P x[VEC];
+                P s = (P)0;
+#pragma unroll
+                for (int j = 0; j < VEC; j++) { x[j] = (P)e[j]; s = (P)(s + x[j]); }
+                P inc = warp_inclusive_sum(s);
+                P up = shfl_up(inc, 1);
+                P run = (P)(carry + (lane == 0 ? (P)0 : up));
+                carry = (P)(carry + shfl_idx(inc, 31));
+                T out[VEC];
+#pragma unroll
+                for (int j = 0; j < VEC; j++) {
+                    if (INCLUSIVE) { run = (P)(run + x[j]); out[j] = (T)run; }
+                    else { out[j] = (T)run; run = (P)(run + x[j]); }
+                }
+                st_hint_v4(vdst + (r0 + b) * 32, *reinterpret_cast<const uint4*>(out), drop);
+            }
         }
-        if (full) {
-            st_stream_v4(reinterpret_cast<uint4*>(dst + base) + i * SCAN_THREADS + tid,
-                         *reinterpret_cast<const uint4*>(out));
-        } else {
-#pragma unroll
+    } else {
+        for (int r = 0; r < SCAN_ROWS; r++) {
+            P x[VEC];
+            P s = (P)0;
             for (int j = 0; j < VEC; j++) {
-                size_t e = base + (size_t)(i * SCAN_THREADS + tid) * VEC + j;
-                if (e < n) dst[e] = out[j];
+                size_t e = lane_base + (size_t)r * ROW + j;
+                x[j] = e < n ? (P)src[e] : (P)0;
+                s = (P)(s + x[j]);
+            }
+            P inc = warp_inclusive_sum(s);
+            P up = shfl_up(inc, 1);
+            P run = (P)(carry + (lane == 0 ? (P)0 : up));
+            carry = (P)(carry + shfl_idx(inc, 31));
+            for (int j = 0; j < VEC; j++) {
+                size_t e = lane_base + (size_t)r * ROW + j;
+                T o;
+                if (INCLUSIVE) { run = (P)(run + x[j]); o = (T)run; }
+                else { o = (T)run; run = (P)(run + x[j]); }
+                if (e < n) dst[e] = o;
             }
         }
     }
+    if (trace && tid == 0) {  // development aid: per-tile timeline (tools/scan_timeline.py)
+        unsigned smid;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        trace[tile * 5 + 0] = t_start;
+        trace[tile * 5 + 1] = t_summed;
+        trace[tile * 5 + 2] = t_prefix;
+        trace[tile * 5 + 3] = globaltimer_ns();
+        trace[tile * 5 + 4] = smid;
+    }
 }
 
-template <typename T, typename P, int NLOADS>
+template <typename T, typename P>
 hj_status run(hj_device* dev, size_t n, bool inclusive, const void* src, void* dst, const void* seed) {
     constexpr int VEC = 16 / sizeof(T);
-    constexpr size_t TILE = (size_t)SCAN_THREADS * NLOADS * VEC;
+    constexpr size_t TILE = (size_t)SCAN_WARPS * SCAN_ROWS * 32 * VEC;
     size_t n_tiles = (n + TILE - 1) / TILE;
     HJ_REQUIRE(n_tiles < (1ull << 31), "prefix_sum: too many tiles");
     HJ_TRY(ensure_lookback_scratch(dev, n_tiles));
@@ -141,11 +214,11 @@ hj_status run(hj_device* dev, size_t n, bool inclusive, const void* src, void* d
     LookbackView lb = lookback_view(dev->lookback.base, dev->lookback.capacity_tiles, epoch);
     int vec_ok = (((uintptr_t)src | (uintptr_t)dst) & 15u) == 0;
     if (inclusive)
-        scan_kernel<T, P, NLOADS, true><<<(unsigned)n_tiles, SCAN_THREADS, 0, dev->stream>>>(
-            (const T*)src, (T*)dst, n, (const T*)seed, lb, vec_ok);
+        scan_kernel<T, P, true><<<(unsigned)n_tiles, SCAN_THREADS, 0, dev->stream>>>(
+            (const T*)src, (T*)dst, n, (const T*)seed, lb, vec_ok, g_scan_trace);
     else
-        scan_kernel<T, P, NLOADS, false><<<(unsigned)n_tiles, SCAN_THREADS, 0, dev->stream>>>(
-            (const T*)src, (T*)dst, n, (const T*)seed, lb, vec_ok);
+        scan_kernel<T, P, false><<<(unsigned)n_tiles, SCAN_THREADS, 0, dev->stream>>>(
+            (const T*)src, (T*)dst, n, (const T*)seed, lb, vec_ok, g_scan_trace);
     return check_launch(dev, "scan_kernel");
 }
 
@@ -155,15 +228,19 @@ hj_status launch_prefix_sum(hj_device* dev, hj_type_kind ty, size_t n, bool incl
                             void* dst, const void* seed) {
     // Integer sums wrap, so signed types run on the unsigned kernel of the same width.
     switch (ty) {
-    case HJ_I8: case HJ_U8: return run<uint8_t, uint32_t, 1>(dev, n, inclusive, src, dst, seed);
-    case HJ_I16: case HJ_U16: return run<uint16_t, uint32_t, 2>(dev, n, inclusive, src, dst, seed);
-    case HJ_I32: case HJ_U32: return run<uint32_t, uint32_t, 4>(dev, n, inclusive, src, dst, seed);
-    case HJ_I64: case HJ_U64: return run<uint64_t, uint64_t, 4>(dev, n, inclusive, src, dst, seed);
-    case HJ_F32: return run<float, float, 4>(dev, n, inclusive, src, dst, seed);
-    case HJ_F64: return run<double, double, 4>(dev, n, inclusive, src, dst, seed);
+    case HJ_I8: case HJ_U8: return run<uint8_t, uint32_t>(dev, n, inclusive, src, dst, seed);
+    case HJ_I16: case HJ_U16: return run<uint16_t, uint32_t>(dev, n, inclusive, src, dst, seed);
+    case HJ_I32: case HJ_U32: return run<uint32_t, uint32_t>(dev, n, inclusive, src, dst, seed);
+    case HJ_I64: case HJ_U64: return run<uint64_t, uint64_t>(dev, n, inclusive, src, dst, seed);
+    case HJ_F32: return run<float, float>(dev, n, inclusive, src, dst, seed);
+    case HJ_F64: return run<double, double>(dev, n, inclusive, src, dst, seed);
     default:
         return fail(HJ_ERR_UNSUPPORTED, "prefix_sum: unsupported element type %s", type_name(ty));
     }
 }
 
 }  // namespace hj
+
+// Development aid (not part of include/hj.h): record {start, summed, prefix known, end, smid}
+// per tile of subsequent scans into a device buffer of 5 * n_tiles u64 (NULL disables).
+extern "C" void hj_debug_scan_trace(void* device_ptr) { hj::g_scan_trace = (unsigned long long*)device_ptr; }

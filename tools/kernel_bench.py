@@ -48,7 +48,11 @@ def main():
     n = 1 << args.log2n
     torch.cuda.set_device(0)
     dev = hj.Device.cuda(0)
-    dev.set_stream(torch.cuda.current_stream().cuda_stream)
+    # a non-default torch stream: events recorded by torch and kernels enqueued by the library
+    # must share ONE stream (the legacy default stream handle is 0, which hj treats as "own")
+    side = torch.cuda.Stream()
+    torch.cuda.set_stream(side)
+    dev.set_stream(side.cuda_stream)
     pk = peak()
     rows = []
 
