@@ -188,3 +188,77 @@ class Device:
 
     def gather(self, elem_bytes: int, n: int, src: Buffer, idx: Buffer, dst: Buffer) -> None:
         check(lib.hj_gather(self._h, elem_bytes, n, src.handle, idx.handle, dst.handle))
+
+    # -- fused kernels (NVRTC path) -------------------------------------------------------
+    def kernel(self, ir) -> "Kernel":
+        """Compile (or fetch from the cache keyed by IR hash) the fused kernel for ``ir``
+        (an ``_lib.Ir`` or an ``ir.IRBuilder``)."""
+        keep = None
+        if hasattr(ir, "build"):
+            keep, ir = ir, ir.build()
+        out = ctypes.c_void_p()
+        check(lib.hj_kernel_get(self._h, ctypes.byref(ir), ctypes.byref(out)))
+        return Kernel(out.value, keep)
+
+    def launch(self, kernel: "Kernel", size: int, buffers, size_buf: Buffer | None = None,
+               index_base: int = 0) -> None:
+        arr = (ctypes.c_void_p * max(len(buffers), 1))(*[b.handle for b in buffers])
+        check(lib.hj_kernel_launch(self._h, kernel.handle, size, size_buf.handle if size_buf else None,
+                                   arr, len(buffers), index_base))
+
+    def kernel_cache_stats(self) -> dict:
+        v = [ctypes.c_uint64() for _ in range(3)]
+        check(lib.hj_device_kernel_cache_stats(self._h, *[ctypes.byref(x) for x in v]))
+        return dict(zip(("compiled", "hits", "disk_hits"), (x.value for x in v)))
+
+    def execute_graph(self, passes, env, descs, timed: bool = False):
+        """``BackendDevice::execute_graph`` (backend/mod.rs:33).
+
+        passes: list of dicts {kind, arg, resources, size_buffer, ir (IRBuilder|None), size};
+        env: list of Buffer (or None); descs: list of (size_elems, ty, elem_bytes).
+        Returns the list of (name, start_us, duration_us) when ``timed``."""
+        n = len(passes)
+        c_passes = (_lib.Pass * max(n, 1))()
+        keep = []
+        for i, p in enumerate(passes):
+            res = (ctypes.c_uint32 * max(len(p["resources"]), 1))(*p["resources"])
+            ir_ptr = None
+            if p.get("ir") is not None:
+                ir = p["ir"].build() if hasattr(p["ir"], "build") else p["ir"]
+                keep.append(ir)
+                ir_ptr = ctypes.pointer(ir)
+            keep.append(res)
+            c_passes[i] = _lib.Pass(p["kind"], p.get("arg", 0), res, len(p["resources"]),
+                                    p.get("size_buffer", -1) if p.get("size_buffer") is not None else -1,
+                                    ir_ptr, p.get("size", 0))
+        c_env = (ctypes.c_void_p * max(len(env), 1))(*[(b.handle if b is not None else None) for b in env])
+        c_desc = (_lib.BufferDesc * max(len(descs), 1))(*[_lib.BufferDesc(*d) for d in descs])
+        report = _lib.Report()
+        reps = (_lib.PassReport * max(n, 1))()
+        if timed:
+            report.passes = reps
+            report.passes_capacity = n
+        check(lib.hj_execute_graph(self._h, c_passes, n, c_env, c_desc, len(env), ctypes.byref(report)))
+        if timed:
+            return [(reps[i].name.decode(), reps[i].start_us, reps[i].duration_us) for i in range(n)]
+        return None
+
+
+PASS_KERNEL, PASS_REDUCE, PASS_PREFIX_SUM, PASS_COMPRESS = range(4)
+
+
+class Kernel:
+    """A compiled fused kernel (NVRTC -> sm_100a cubin), owned by the per-device cache."""
+
+    def __init__(self, handle: int, keep=None):
+        self._h = ctypes.c_void_p(handle)
+        self._keep = keep
+
+    @property
+    def handle(self) -> ctypes.c_void_p:
+        return self._h
+
+    def __del__(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h:
+            lib.hj_kernel_release(h)

@@ -1,0 +1,122 @@
+// graph_exec.cpp — hj_execute_graph: the pass interpreter behind BackendDevice::execute_graph.
+//
+// Restates VulkanDevice::execute_graph (hephaestus-jit/src/backend/vulkan/mod.rs:151-383) for
+// the CUDA backend: walks Graph::passes() in order; a Kernel pass fetches the NVRTC-compiled
+// kernel for its IR from the per-device cache and launches it over the pass size (or the
+// device-resident DynSize count); a DeviceOp pass dispatches to the hand-written kernel with
+// the resource order the reference uses (Reduce / PrefixSum: [dst, src], mod.rs:259-280;
+// Compress: [index_out, out_count, src], mod.rs:281-299).  Stream order replaces the
+// reference's render-graph barriers (vulkan_core/graph.rs:362-570): every pass is enqueued on
+// the device stream, so a pass sees all writes of the passes before it.
+//
+// Timing: when the caller asks for a report, each pass is bracketed by CUDA events and the
+// call blocks until they are resolved — the reference always blocks on a fence and reads GPU
+// timestamps (vulkan_core/device.rs:297-334, profiler.rs:56-131).  Without a report the call
+// is asynchronous.
+#include <chrono>
+
+#include "hj_internal.h"
+#include "ir.h"
+
+using namespace hj;
+
+extern "C" hj_status hj_execute_graph(hj_device* dev, const hj_pass* passes, uint32_t n_passes,
+                                      hj_buffer* const* env, const hj_buffer_desc* descs,
+                                      uint32_t n_resources, hj_report* report) {
+    HJ_REQUIRE(dev && (passes || n_passes == 0), "hj_execute_graph: null argument");
+    HJ_REQUIRE((env && descs) || n_resources == 0, "hj_execute_graph: null environment");
+    auto cpu_start = std::chrono::steady_clock::now();
+    const bool timed = report && report->passes && report->passes_capacity >= n_passes;
+    std::vector<cudaEvent_t> ev;
+    if (timed) {
+        cudaSetDevice(dev->ordinal);
+        ev.resize((size_t)n_passes + 1);
+        for (auto& e : ev) HJ_CUDA(cudaEventCreate(&e));
+        HJ_CUDA(cudaEventRecord(ev[0], dev->stream));
+    }
+    auto res = [&](const hj_pass& p, uint32_t k, hj_buffer** out, const hj_buffer_desc** desc) -> hj_status {
+        HJ_REQUIRE(k < p.n_resources, "pass references resource slot %u but has %u", k, p.n_resources);
+        uint32_t id = p.resources[k];
+        HJ_REQUIRE(id < n_resources, "ResourceId %u out of range (%u resources)", id, n_resources);
+        HJ_REQUIRE(env[id], "resource %u has been left empty (graph.rs: UninitializedResourve)", id);
+        *out = env[id];
+        if (desc) *desc = &descs[id];
+        return HJ_OK;
+    };
+
+    for (uint32_t i = 0; i < n_passes; i++) {
+        const hj_pass& p = passes[i];
+        char name[64];
+        hj_buffer* size_buf = nullptr;
+        if (p.size_buffer >= 0) {
+            HJ_REQUIRE((uint32_t)p.size_buffer < n_resources && env[p.size_buffer], "size buffer resource missing");
+            size_buf = env[p.size_buffer];
+        }
+        switch (p.kind) {
+        case HJ_PASS_KERNEL: {
+            HJ_REQUIRE(p.ir, "kernel pass %u without IR", i);
+            snprintf(name, sizeof(name), "JIT Kernel %u [%llu]", i, (unsigned long long)p.size);
+            hj_kernel* k = nullptr;
+            HJ_TRY(hj_kernel_get(dev, p.ir, &k));
+            std::vector<hj_buffer*> bufs(p.n_resources);
+            for (uint32_t b = 0; b < p.n_resources; b++) HJ_TRY(res(p, b, &bufs[b], nullptr));
+            hj_status s = hj_kernel_launch(dev, k, p.size, size_buf, bufs.data(), p.n_resources, 0);
+            hj_kernel_release(k);
+            HJ_TRY(s);
+            break;
+        }
+        case HJ_PASS_REDUCE: {
+            snprintf(name, sizeof(name), "Reduce");
+            hj_buffer *dst, *src;
+            const hj_buffer_desc *ddst, *dsrc;
+            HJ_TRY(res(p, 0, &dst, &ddst));
+            HJ_TRY(res(p, 1, &src, &dsrc));
+            HJ_TRY(hj_reduce(dev, (hj_reduce_op)p.arg, (hj_type_kind)ddst->ty, dsrc->size, src, dst));
+            break;
+        }
+        case HJ_PASS_PREFIX_SUM: {
+            snprintf(name, sizeof(name), "Prefix Sum Large");
+            hj_buffer *dst, *src;
+            const hj_buffer_desc *ddst, *dsrc;
+            HJ_TRY(res(p, 0, &dst, &ddst));
+            HJ_TRY(res(p, 1, &src, &dsrc));
+            HJ_TRY(hj_prefix_sum(dev, (hj_type_kind)ddst->ty, dsrc->size, (int32_t)p.arg, src, dst, nullptr));
+            break;
+        }
+        case HJ_PASS_COMPRESS: {
+            snprintf(name, sizeof(name), "Compress Large");
+            hj_buffer *index_out, *out_count, *src;
+            const hj_buffer_desc* dsrc;
+            HJ_TRY(res(p, 0, &index_out, nullptr));
+            HJ_TRY(res(p, 1, &out_count, nullptr));
+            HJ_TRY(res(p, 2, &src, &dsrc));
+            HJ_TRY(hj_compress(dev, dsrc->size, size_buf, out_count, src, index_out, 0));
+            break;
+        }
+        default:
+            return fail(HJ_ERR_UNSUPPORTED, "pass %u: device op %u is out of scope for the B200 backend "
+                        "(MatMul / FusedMlp / textures / acceleration structures)", i, p.kind);
+        }
+        if (timed) {
+            HJ_CUDA(cudaEventRecord(ev[i + 1], dev->stream));
+            snprintf(report->passes[i].name, sizeof(report->passes[i].name), "%s", name);
+        }
+    }
+    if (timed) {
+        HJ_CUDA(cudaEventSynchronize(ev[n_passes]));
+        for (uint32_t i = 0; i < n_passes; i++) {
+            float start_ms = 0.f, dur_ms = 0.f;
+            cudaEventElapsedTime(&start_ms, ev[0], ev[i]);
+            cudaEventElapsedTime(&dur_ms, ev[i], ev[i + 1]);
+            report->passes[i].start_us = start_ms * 1e3;
+            report->passes[i].duration_us = dur_ms * 1e3;
+        }
+        for (auto& e : ev) cudaEventDestroy(e);
+    }
+    if (report) {
+        report->n_passes = n_passes;
+        report->cpu_duration_us =
+            std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - cpu_start).count();
+    }
+    return HJ_OK;
+}
