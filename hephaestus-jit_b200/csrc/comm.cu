@@ -1,0 +1,301 @@
+// comm.cu — multi-GPU layer: one process per GPU, per-GPU partials combined over NCCL
+// (NVLink 5 / NVSwitch).
+//
+// The reference has no multi-GPU code at all; this layer is what
+// BASELINE.json's north star adds on top of the backend: arrays are partitioned into
+// contiguous shards, each rank runs the single-GPU kernel on its shard, and only
+//   * one scalar per rank      (reduce: partials;  scan / compress: shard totals / counts), or
+//   * one histogram per rank   (scatter-reduce),
+// crosses the fabric.  The payloads are tiny, so the exchange is an all-gather of `world`
+// scalars followed by a fold IN RANK ORDER on every rank: deterministic for floats, and it
+// covers the operators / types NCCL has no reduction for (and / or / xor, 16-bit integers).
+// The scan and compress kernels take the cross-GPU carry as a device-resident seed / index
+// base, so no second pass over the data is needed to apply it (scan.cu, compress.cu).
+//
+// NCCL is loaded with dlopen at first use (libnccl.so.2: the copy torch already mapped when
+// running under torchrun, else the system one), so libhj_b200.so itself has no NCCL dependency.
+#include <dlfcn.h>
+#include <nccl.h>
+
+#include "common.cuh"
+#include "hj_internal.h"
+
+struct hj_comm {
+    hj_device* dev = nullptr;
+    ncclComm_t comm = nullptr;
+    int rank = 0, world = 1;
+    void* scratch = nullptr;  // [0,64): local scalar | [64, 64+8*world): gathered | then: seed / sum
+};
+
+namespace hj {
+namespace {
+
+struct NcclApi {
+    void* handle = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    const char* (*GetErrorString)(ncclResult_t) = nullptr;
+    std::string error;
+};
+
+NcclApi& nccl() {
+    static NcclApi api;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        const char* names[] = {"libnccl.so.2", "libnccl.so"};
+        for (const char* n : names) {
+            api.handle = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+            if (api.handle) break;
+        }
+        if (!api.handle) { api.error = std::string("cannot load libnccl: ") + dlerror(); return; }
+#define HJ_SYM(field, sym)                                                      \
+    api.field = reinterpret_cast<decltype(api.field)>(dlsym(api.handle, sym));  \
+    if (!api.field) { api.error = std::string("libnccl lacks ") + sym; return; }
+        HJ_SYM(GetUniqueId, "ncclGetUniqueId")
+        HJ_SYM(CommInitRank, "ncclCommInitRank")
+        HJ_SYM(CommDestroy, "ncclCommDestroy")
+        HJ_SYM(AllGather, "ncclAllGather")
+        HJ_SYM(AllReduce, "ncclAllReduce")
+        HJ_SYM(GetErrorString, "ncclGetErrorString")
+#undef HJ_SYM
+    });
+    return api;
+}
+
+#define HJ_NCCL(expr)                                                                        \
+    do {                                                                                     \
+        ncclResult_t _r = (expr);                                                            \
+        if (_r != ncclSuccess)                                                               \
+            return fail(HJ_ERR_NCCL, "%s failed: %s", #expr, nccl().GetErrorString(_r));     \
+    } while (0)
+
+hj_status need_nccl() {
+    NcclApi& a = nccl();
+    if (!a.error.empty()) return fail(HJ_ERR_NCCL, "%s", a.error.c_str());
+    return HJ_OK;
+}
+
+// seed[0] = sum of gathered[0 .. rank)  (exclusive scan of the per-rank totals at `rank`);
+// total[0] = sum of gathered[0 .. world)
+template <typename T>
+__global__ void offsets_kernel(const T* gathered, int rank, int world, T* seed, T* total) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        T s = (T)0, pre = (T)0;
+        for (int q = 0; q < world; q++) {
+            if (q == rank) pre = s;
+            s = (T)(s + gathered[q]);
+        }
+        if (seed) seed[0] = pre;
+        if (total) total[0] = s;
+    }
+}
+
+// dst[i] = fold over ranks (in rank order) of all[q * n + i]
+template <typename T, int OP>
+__global__ void fold_ranks_kernel(const T* all, size_t n, int world, T* dst) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    T v = all[i];
+    for (int q = 1; q < world; q++) {
+        T o = all[(size_t)q * n + i];
+        if (OP == HJ_REDUCE_OR) v |= o;
+        else if (OP == HJ_REDUCE_AND) v &= o;
+        else v ^= o;
+    }
+    dst[i] = v;
+}
+
+bool nccl_type(hj_type_kind ty, ncclDataType_t* out) {
+    switch (ty) {
+    case HJ_I8: *out = ncclInt8; return true;
+    case HJ_U8: case HJ_BOOL: *out = ncclUint8; return true;
+    case HJ_I32: *out = ncclInt32; return true;
+    case HJ_U32: *out = ncclUint32; return true;
+    case HJ_I64: *out = ncclInt64; return true;
+    case HJ_U64: *out = ncclUint64; return true;
+    case HJ_F32: *out = ncclFloat32; return true;
+    case HJ_F64: *out = ncclFloat64; return true;
+    default: return false;
+    }
+}
+
+char* local_slot(hj_comm* c) { return reinterpret_cast<char*>(c->scratch); }
+char* gathered_slot(hj_comm* c) { return reinterpret_cast<char*>(c->scratch) + 64; }
+char* extra_slot(hj_comm* c) { return reinterpret_cast<char*>(c->scratch) + 64 + 8 * (size_t)c->world; }
+
+// all-gather one element of `es` bytes per rank: local_slot -> gathered_slot
+hj_status gather_scalars(hj_comm* c, size_t es) {
+    HJ_NCCL(nccl().AllGather(local_slot(c), gathered_slot(c), es, ncclUint8, c->comm, c->dev->stream));
+    return HJ_OK;
+}
+
+}  // namespace
+}  // namespace hj
+
+using namespace hj;
+
+extern "C" {
+
+hj_status hj_comm_unique_id(uint8_t out_id[HJ_UNIQUE_ID_BYTES]) {
+    HJ_REQUIRE(out_id, "null argument");
+    HJ_TRY(need_nccl());
+    static_assert(sizeof(ncclUniqueId) == HJ_UNIQUE_ID_BYTES, "ncclUniqueId size");
+    ncclUniqueId id;
+    HJ_NCCL(nccl().GetUniqueId(&id));
+    memcpy(out_id, &id, sizeof(id));
+    return HJ_OK;
+}
+
+hj_status hj_comm_create(hj_device* dev, const uint8_t id[HJ_UNIQUE_ID_BYTES], int32_t rank, int32_t world,
+                         hj_comm** out) {
+    HJ_REQUIRE(dev && id && out, "null argument");
+    HJ_REQUIRE(world >= 1 && rank >= 0 && rank < world, "bad rank %d / world %d", rank, world);
+    HJ_TRY(need_nccl());
+    DeviceGuard g(dev);
+    auto c = new hj_comm();
+    c->dev = dev;
+    c->rank = rank;
+    c->world = world;
+    ncclUniqueId uid;
+    memcpy(&uid, id, sizeof(uid));
+    ncclResult_t r = nccl().CommInitRank(&c->comm, world, uid, rank);
+    if (r != ncclSuccess) {
+        delete c;
+        return fail(HJ_ERR_NCCL, "ncclCommInitRank failed: %s", nccl().GetErrorString(r));
+    }
+    cudaError_t e = cudaMalloc(&c->scratch, 64 + 8 * (size_t)world + 64);
+    if (e != cudaSuccess) {
+        nccl().CommDestroy(c->comm);
+        delete c;
+        return fail(HJ_ERR_CUDA, "cudaMalloc failed: %s", cudaGetErrorString(e));
+    }
+    cudaMemsetAsync(c->scratch, 0, 64 + 8 * (size_t)world + 64, dev->stream);
+    dev->rc.fetch_add(1);
+    *out = c;
+    return HJ_OK;
+}
+
+hj_status hj_comm_destroy(hj_comm* c) {
+    HJ_REQUIRE(c, "null comm");
+    {
+        DeviceGuard g(c->dev);
+        cudaStreamSynchronize(c->dev->stream);
+        if (c->comm) nccl().CommDestroy(c->comm);
+        if (c->scratch) cudaFree(c->scratch);
+    }
+    c->dev->rc.fetch_sub(1);
+    delete c;
+    return HJ_OK;
+}
+
+hj_status hj_sharded_reduce(hj_comm* c, hj_reduce_op op, hj_type_kind ty, size_t n_local, hj_buffer* src,
+                            hj_buffer* dst) {
+    HJ_REQUIRE(c && src && dst, "hj_sharded_reduce: null argument");
+    size_t es = type_size(ty);
+    HJ_REQUIRE(es && n_local >= 1 && n_local * es <= src->bytes && es <= dst->bytes, "hj_sharded_reduce: bad sizes");
+    DeviceGuard g(c->dev);
+    // local partial -> all-gather -> fold in rank order with the same reduction kernel
+    HJ_TRY(launch_reduce(c->dev, op, ty, n_local, src->ptr, local_slot(c)));
+    if (c->world == 1) {
+        HJ_CUDA(cudaMemcpyAsync(dst->ptr, local_slot(c), es, cudaMemcpyDeviceToDevice, c->dev->stream));
+        return HJ_OK;
+    }
+    HJ_TRY(gather_scalars(c, es));
+    return launch_reduce(c->dev, op, ty, (size_t)c->world, gathered_slot(c), dst->ptr);
+}
+
+hj_status hj_sharded_prefix_sum(hj_comm* c, hj_type_kind ty, size_t n_local, int32_t inclusive, hj_buffer* src,
+                                hj_buffer* dst) {
+    HJ_REQUIRE(c && src && dst, "hj_sharded_prefix_sum: null argument");
+    size_t es = type_size(ty);
+    HJ_REQUIRE(es && n_local >= 1 && n_local * es <= src->bytes && n_local * es <= dst->bytes,
+               "hj_sharded_prefix_sum: bad sizes");
+    DeviceGuard g(c->dev);
+    if (c->world == 1) return launch_prefix_sum(c->dev, ty, n_local, inclusive != 0, src->ptr, dst->ptr, nullptr);
+    // shard total (a read-only pass, sizeof(T) bytes/element) -> all-gather -> exclusive offset
+    // of this rank -> scan seeded with the offset.  12 bytes/element in total for 4-byte types.
+    HJ_TRY(launch_reduce(c->dev, HJ_REDUCE_SUM, ty, n_local, src->ptr, local_slot(c)));
+    HJ_TRY(gather_scalars(c, es));
+    void* seed = extra_slot(c);
+    switch (es) {
+    case 1: offsets_kernel<uint8_t><<<1, 32, 0, c->dev->stream>>>((const uint8_t*)gathered_slot(c), c->rank, c->world, (uint8_t*)seed, nullptr); break;
+    case 2: offsets_kernel<uint16_t><<<1, 32, 0, c->dev->stream>>>((const uint16_t*)gathered_slot(c), c->rank, c->world, (uint16_t*)seed, nullptr); break;
+    case 4:
+        if (ty == HJ_F32) offsets_kernel<float><<<1, 32, 0, c->dev->stream>>>((const float*)gathered_slot(c), c->rank, c->world, (float*)seed, nullptr);
+        else offsets_kernel<uint32_t><<<1, 32, 0, c->dev->stream>>>((const uint32_t*)gathered_slot(c), c->rank, c->world, (uint32_t*)seed, nullptr);
+        break;
+    default:
+        if (ty == HJ_F64) offsets_kernel<double><<<1, 32, 0, c->dev->stream>>>((const double*)gathered_slot(c), c->rank, c->world, (double*)seed, nullptr);
+        else offsets_kernel<unsigned long long><<<1, 32, 0, c->dev->stream>>>((const unsigned long long*)gathered_slot(c), c->rank, c->world, (unsigned long long*)seed, nullptr);
+        break;
+    }
+    HJ_TRY(check_launch(c->dev, "offsets_kernel"));
+    return launch_prefix_sum(c->dev, ty, n_local, inclusive != 0, src->ptr, dst->ptr, seed);
+}
+
+hj_status hj_sharded_compress(hj_comm* c, size_t n_local, uint32_t index_base, hj_buffer* src_mask,
+                              hj_buffer* index_out, hj_buffer* out_count, hj_buffer* counts_out) {
+    HJ_REQUIRE(c && src_mask && index_out && out_count, "hj_sharded_compress: null argument");
+    HJ_REQUIRE(n_local >= 1 && n_local <= src_mask->bytes && n_local * 4 <= index_out->bytes && out_count->bytes >= 4,
+               "hj_sharded_compress: bad sizes");
+    HJ_REQUIRE(!counts_out || counts_out->bytes >= 4 * (size_t)c->world, "hj_sharded_compress: counts_out too small");
+    DeviceGuard g(c->dev);
+    // local compaction with GLOBAL indices; the per-rank segment stays on its GPU
+    HJ_TRY(launch_compress(c->dev, n_local, nullptr, (uint32_t*)local_slot(c), (const uint8_t*)src_mask->ptr,
+                           (uint32_t*)index_out->ptr, index_base));
+    if (c->world > 1) HJ_TRY(gather_scalars(c, 4));
+    else HJ_CUDA(cudaMemcpyAsync(gathered_slot(c), local_slot(c), 4, cudaMemcpyDeviceToDevice, c->dev->stream));
+    offsets_kernel<uint32_t><<<1, 32, 0, c->dev->stream>>>((const uint32_t*)gathered_slot(c), c->rank, c->world, nullptr,
+                                                          (uint32_t*)out_count->ptr);
+    HJ_TRY(check_launch(c->dev, "offsets_kernel"));
+    if (counts_out)
+        HJ_CUDA(cudaMemcpyAsync(counts_out->ptr, gathered_slot(c), 4 * (size_t)c->world, cudaMemcpyDeviceToDevice,
+                                c->dev->stream));
+    return HJ_OK;
+}
+
+hj_status hj_sharded_scatter_reduce(hj_comm* c, hj_reduce_op op, hj_type_kind ty, size_t n_local, hj_buffer* idx,
+                                    hj_buffer* src, uint64_t literal, hj_buffer* dst, size_t n_dst) {
+    HJ_REQUIRE(c && idx && dst, "hj_sharded_scatter_reduce: null argument");
+    size_t es = type_size(ty);
+    HJ_REQUIRE(es && n_local * 4 <= idx->bytes && n_dst * es <= dst->bytes && (!src || n_local * es <= src->bytes),
+               "hj_sharded_scatter_reduce: bad sizes");
+    DeviceGuard g(c->dev);
+    // privatised per GPU: every rank reduces its keys into its own copy of dst (which the
+    // caller initialised with the operator's identity), then the copies are combined
+    HJ_TRY(launch_scatter_reduce(c->dev, op, ty, n_local, (const uint32_t*)idx->ptr, src ? src->ptr : nullptr, literal,
+                                 dst->ptr, n_dst));
+    if (c->world == 1) return HJ_OK;
+    ncclDataType_t dt;
+    HJ_REQUIRE(nccl_type(ty, &dt), "hj_sharded_scatter_reduce: no NCCL type for %s", type_name(ty));
+    if (op == HJ_REDUCE_SUM || op == HJ_REDUCE_MAX || op == HJ_REDUCE_MIN) {
+        ncclRedOp_t rop = op == HJ_REDUCE_SUM ? ncclSum : op == HJ_REDUCE_MAX ? ncclMax : ncclMin;
+        HJ_NCCL(nccl().AllReduce(dst->ptr, dst->ptr, n_dst, dt, rop, c->comm, c->dev->stream));
+        return HJ_OK;
+    }
+    // and / or / xor: all-gather the copies and fold in rank order
+    HJ_REQUIRE(es == 4 || es == 8, "hj_sharded_scatter_reduce: bitwise ops need a 4- or 8-byte type");
+    void* all = nullptr;
+    HJ_CUDA(cudaMallocAsync(&all, n_dst * es * (size_t)c->world, c->dev->stream));
+    HJ_NCCL(nccl().AllGather(dst->ptr, all, n_dst * es, ncclUint8, c->comm, c->dev->stream));
+    unsigned grid = (unsigned)((n_dst + 255) / 256);
+#define HJ_FOLD(T, OP) fold_ranks_kernel<T, OP><<<grid, 256, 0, c->dev->stream>>>((const T*)all, n_dst, c->world, (T*)dst->ptr)
+    if (es == 4) {
+        if (op == HJ_REDUCE_OR) HJ_FOLD(uint32_t, HJ_REDUCE_OR);
+        else if (op == HJ_REDUCE_AND) HJ_FOLD(uint32_t, HJ_REDUCE_AND);
+        else HJ_FOLD(uint32_t, HJ_REDUCE_XOR);
+    } else {
+        if (op == HJ_REDUCE_OR) HJ_FOLD(unsigned long long, HJ_REDUCE_OR);
+        else if (op == HJ_REDUCE_AND) HJ_FOLD(unsigned long long, HJ_REDUCE_AND);
+        else HJ_FOLD(unsigned long long, HJ_REDUCE_XOR);
+    }
+#undef HJ_FOLD
+    hj_status s = check_launch(c->dev, "fold_ranks_kernel");
+    cudaFreeAsync(all, c->dev->stream);
+    return s;
+}
+
+}  // extern "C"

@@ -1,0 +1,123 @@
+"""Multi-GPU layer (host side): contiguous sharding of 1-D arrays over the ranks of one node and
+the NCCL-backed combine ops of include/hj.h (``hj_sharded_*``).
+
+One process per GPU.  The reference has no multi-GPU code; the partitioning
+follows BASELINE.json: reductions all-reduce their partials, scans and compaction apply the
+exclusive scan of the per-GPU totals as an offset, histograms are privatised per GPU.
+
+``exchange_*`` are the host-visible statement of the exchange protocol (what crosses the fabric
+and how it is folded); they run on any torch.distributed backend and are what the world-size-2
+gloo tests exercise on CPU.  On GPUs the same protocol runs inside libhj_b200.so on the device
+stream (csrc/comm.cu) — nothing is copied to the host.
+"""
+from __future__ import annotations
+
+import ctypes
+
+import numpy as np
+
+from . import Buffer, Device, TYPE_SIZE, _NP
+from ._lib import HJ_UNIQUE_ID_BYTES, check, lib
+
+
+def shard_bounds(n: int, world: int, rank: int) -> tuple[int, int]:
+    """Contiguous block of rank ``rank``: sizes differ by at most one, order preserved."""
+    base, rem = divmod(n, world)
+    start = rank * base + min(rank, rem)
+    return start, start + base + (1 if rank < rem else 0)
+
+
+def exclusive_offsets(totals):
+    """offset[r] = fold(totals[0..r)) — the carry each rank seeds its scan / compaction with."""
+    out, acc = [], type(totals[0])(0) if len(totals) else 0
+    for t in totals:
+        out.append(acc)
+        acc = acc + t
+    return out
+
+
+class Comm:
+    """An NCCL communicator bound to one Device (``hj_comm``)."""
+
+    def __init__(self, dev: Device, unique_id: bytes, rank: int, world: int):
+        assert len(unique_id) == HJ_UNIQUE_ID_BYTES
+        self.dev, self.rank, self.world = dev, rank, world
+        out = ctypes.c_void_p()
+        buf = (ctypes.c_uint8 * HJ_UNIQUE_ID_BYTES).from_buffer_copy(unique_id)
+        check(lib.hj_comm_create(dev.handle, buf, rank, world, ctypes.byref(out)))
+        self._h = out
+
+    @staticmethod
+    def unique_id() -> bytes:
+        buf = (ctypes.c_uint8 * HJ_UNIQUE_ID_BYTES)()
+        check(lib.hj_comm_unique_id(buf))
+        return bytes(buf)
+
+    @staticmethod
+    def from_torch(dev: Device) -> "Comm":
+        """Create the communicator of the current torch.distributed job (id broadcast from rank 0)."""
+        import torch.distributed as dist
+        rank, world = dist.get_rank(), dist.get_world_size()
+        box = [Comm.unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(box, src=0)
+        return Comm(dev, box[0], rank, world)
+
+    def destroy(self):
+        h, self._h = self._h, None
+        if h:
+            check(lib.hj_comm_destroy(h))
+
+    # ---- sharded ops (device-side exchange) ---------------------------------------------------
+    def reduce(self, op: int, ty: int, n_local: int, src: Buffer, dst: Buffer) -> None:
+        check(lib.hj_sharded_reduce(self._h, op, ty, n_local, src.handle, dst.handle))
+
+    def prefix_sum(self, ty: int, n_local: int, inclusive: bool, src: Buffer, dst: Buffer) -> None:
+        check(lib.hj_sharded_prefix_sum(self._h, ty, n_local, int(inclusive), src.handle, dst.handle))
+
+    def compress(self, n_local: int, index_base: int, src_mask: Buffer, index_out: Buffer, out_count: Buffer,
+                 counts_out: Buffer | None = None) -> None:
+        check(lib.hj_sharded_compress(self._h, n_local, index_base, src_mask.handle, index_out.handle,
+                                      out_count.handle, counts_out.handle if counts_out else None))
+
+    def scatter_reduce(self, op: int, ty: int, n_local: int, idx: Buffer, src: Buffer | None, literal,
+                       dst: Buffer, n_dst: int) -> None:
+        lit = int(np.array([literal], dtype=_NP[ty]).view(
+            {1: np.uint8, 2: np.uint16, 4: np.uint32, 8: np.uint64}[TYPE_SIZE[ty]])[0])
+        check(lib.hj_sharded_scatter_reduce(self._h, op, ty, n_local, idx.handle,
+                                            src.handle if src else None, lit, dst.handle, n_dst))
+
+
+# ---- the exchange protocol on host tensors (any backend; used by the gloo tests) ---------------
+
+def _all_gather_scalar(value: np.generic):
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size()
+    raw = np.frombuffer(np.asarray(value).tobytes().ljust(8, b"\0"), dtype=np.uint8).copy()
+    mine = torch.from_numpy(raw)
+    outs = [torch.empty_like(mine) for _ in range(world)]
+    dist.all_gather(outs, mine)
+    n = np.asarray(value).dtype.itemsize
+    return [np.frombuffer(o.numpy().tobytes()[:n], dtype=np.asarray(value).dtype)[0] for o in outs]
+
+
+def exchange_reduce(partial: np.generic, fold):
+    """All-gather the per-rank partials, fold them in rank order on every rank."""
+    parts = _all_gather_scalar(partial)
+    acc = parts[0]
+    for p in parts[1:]:
+        acc = fold(acc, p)
+    return acc
+
+
+def exchange_scan_offset(local_total: np.generic):
+    """All-gather the shard totals; this rank's scan is seeded with the exclusive prefix."""
+    import torch.distributed as dist
+    with np.errstate(over="ignore"):
+        return exclusive_offsets(_all_gather_scalar(local_total))[dist.get_rank()]
+
+
+def exchange_counts(local_count: int):
+    """All-gather the per-rank compaction counts: (counts, exclusive offsets, global count)."""
+    counts = [int(c) for c in _all_gather_scalar(np.uint32(local_count))]
+    return counts, exclusive_offsets(counts), sum(counts)

@@ -1,0 +1,84 @@
+"""Host logic of the multi-GPU layer on CPU: shard partitioning, and the exchange protocol
+(partials -> all-gather -> rank-order fold; totals -> exclusive offsets; counts -> global offsets)
+run over torch.distributed `gloo` with world_size 2 and 3, the local work done by the oracle."""
+import importlib
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sharded = importlib.import_module("hephaestus-jit_b200.sharded")
+
+
+def test_shard_bounds_cover_and_balance():
+    for n in (0, 1, 7, 8, 1000, (1 << 30) + 5):
+        for world in (1, 2, 3, 4, 8):
+            spans = [sharded.shard_bounds(n, world, r) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+            sizes = [e - s for s, e in spans]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def test_exclusive_offsets():
+    assert sharded.exclusive_offsets([3, 0, 5, 2]) == [0, 3, 3, 8]
+    off = sharded.exclusive_offsets([np.uint32(0xFFFFFFFF), np.uint32(2), np.uint32(1)])
+    with np.errstate(over="ignore"):
+        assert [int(x) for x in off] == [0, 0xFFFFFFFF, 1]  # wraps like the device arithmetic
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, n):
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    import torch.distributed as dist
+
+    import oracle
+    sh = importlib.import_module("hephaestus-jit_b200.sharded")
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        rng = np.random.Generator(np.random.PCG64(42))  # every rank generates the whole array
+        u = rng.integers(0, 2**32, size=n, dtype=np.uint64).astype(np.uint32)
+        f = rng.random(n, dtype=np.float32)
+        mask = (rng.random(n) < 0.3).astype(np.uint8)
+        s, e = sh.shard_bounds(n, world, rank)
+
+        # reduce: local partial (oracle) -> exchange -> equals the single-array reduction
+        with np.errstate(over="ignore"):
+            tot = sh.exchange_reduce(oracle.reduce(oracle.SUM, oracle.U32, u[s:e])[0], lambda a, b: a + b)
+        assert tot == oracle.reduce(oracle.SUM, oracle.U32, u)[0]
+        mx = sh.exchange_reduce(oracle.reduce(oracle.MAX, oracle.F32, f[s:e])[0], max)
+        assert mx == f.max()
+        x = sh.exchange_reduce(oracle.reduce(oracle.XOR, oracle.U32, u[s:e])[0], lambda a, b: a ^ b)
+        assert x == np.bitwise_xor.reduce(u)
+        fs = sh.exchange_reduce(oracle.reduce(oracle.SUM, oracle.F32, f[s:e])[0], lambda a, b: np.float32(a + b))
+        assert abs(float(fs) - float(f.astype(np.float64).sum())) <= 1e-5 * n
+
+        # scan: shard total -> exclusive offset -> seeded local scan == slice of the global scan
+        with np.errstate(over="ignore"):
+            off = sh.exchange_scan_offset(oracle.reduce(oracle.SUM, oracle.U32, u[s:e])[0])
+            local = oracle.prefix_sum(oracle.U32, u[s:e], True) + np.uint32(off)
+        assert np.array_equal(local, oracle.prefix_sum(oracle.U32, u, True)[s:e])
+
+        # compress: local compaction with global indices; counts -> offsets; concatenation == global
+        cnt, idx = oracle.compress(mask[s:e], index_base=s)
+        counts, offsets, total = sh.exchange_counts(cnt)
+        gcnt, gidx = oracle.compress(mask)
+        assert total == gcnt and counts[rank] == cnt
+        assert np.array_equal(idx[:cnt], gidx[offsets[rank]: offsets[rank] + cnt])
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_exchange_protocol_gloo(world):
+    mp.spawn(_worker, args=(world, _free_port(), 100003), nprocs=world, join=True)
