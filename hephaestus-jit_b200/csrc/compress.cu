@@ -18,8 +18,11 @@
 //   * the tail (and a device-resident DynSize count) is masked in the kernel (reference D4);
 //   * `index_base` is added to every index: the shard's global offset on multi-GPU runs.
 // Algorithmic bytes: n (mask) + 4 * count (indices); HBM-bound.
+#include <cstdlib>
+
 #include "hj_internal.h"
 #include "lookback.cuh"
+#include "ring.cuh"
 
 namespace hj {
 namespace {
@@ -137,11 +140,175 @@ compress_kernel(const uint8_t* __restrict__ mask, size_t n, const uint32_t* __re
     }
 }
 
+// ---- ring pipeline variant (ring.cuh): the default for 16-byte aligned masks ------------------
+// Tile = 28 KiB of mask bytes, 28 consumer warps with a 1 KiB slice (two 512-element rows) each.
+// Phase 1 turns every 16-byte vector into a 16-bit lane mask (bit tricks, no per-byte work),
+// counts it, and parks the mask in the first two bytes of the vector it came from.  Phase 2
+// reads the masks back, ranks both rows with ONE packed warp scan, and stages the selected
+// positions of a row as u16 offsets in the slice's own bytes (dead by then) before a
+// coalesced store of base + offset.  The kernel is instruction-issue bound, not HBM bound, at
+// low selectivity, hence the 28 warps and the lean inner loops.
+constexpr int CR_TILE = 28672, CR_STAGES = 7, CR_WARPS = 28, CR_AHEAD = 3, CR_PWARPS = 1;
+constexpr int CR_SLICE = CR_TILE / CR_WARPS;  // 1024 mask bytes per warp = 2 rows
+static_assert(CR_SLICE == 1024, "emit() is written for two rows per warp");
+
+// 16 mask bytes -> 16-bit lane mask (bit i = byte i is non-zero).
+// Fast path: `bool` buffers only ever hold 0 or 1 (codegen stores bool as u8 0/1,
+// codegen/glsl/mod.rs:256-270), so bit 0 of each byte IS the flag and one multiply-gather per
+// word collects the four flags (all 16 partial products land on distinct bits).  Any other
+// byte value takes the exact "non-zero" path.
+__device__ __forceinline__ uint32_t gather_lo(uint32_t w) { return (w * 0x10204080u) >> 28; }  // bits 0,8,16,24
+__device__ __forceinline__ uint32_t nonzero_lo(uint32_t w) {
+    return ((((w & 0x7f7f7f7fu) + 0x7f7f7f7fu) | w) & 0x80808080u) >> 7;
+}
+__device__ __forceinline__ uint32_t lane_mask16(uint4 v) {
+    if (((v.x | v.y | v.z | v.w) & 0xfefefefeu) != 0u) {
+        v.x = nonzero_lo(v.x); v.y = nonzero_lo(v.y); v.z = nonzero_lo(v.z); v.w = nonzero_lo(v.w);
+    }
+    return gather_lo(v.x) | (gather_lo(v.y) << 4) | (gather_lo(v.z) << 8) | (gather_lo(v.w) << 12);
+}
+
+template <int CFG>
+struct CompressOp {
+    using P = uint32_t;
+    static constexpr bool DENSE = (CFG & 2) != 0, VEC = (CFG & 4) != 0;
+    struct Args {
+        uint32_t* index_out;
+        uint32_t* out_count;
+        uint32_t index_base;
+    };
+    static __device__ __forceinline__ P total(const char* slice, int lane) {
+        char* mine = const_cast<char*>(slice) + lane * 16;
+        const uint32_t b0 = lane_mask16(lds_v4(mine));
+        const uint32_t b1 = lane_mask16(lds_v4(mine + 512));
+        *reinterpret_cast<uint16_t*>(mine) = (uint16_t)b0;
+        *reinterpret_cast<uint16_t*>(mine + 512) = (uint16_t)b1;
+        return __reduce_add_sync(0xffffffffu, __popc(b0) + __popc(b1));
+    }
+    // One 512-element row: lane `lane` owns bits `b` (elements lane*16 ..), its first selected
+    // element has rank `k` in the row.  Selected positions are staged as u16 row offsets, then
+    // written as base + offset with 128-bit stores once the output address is 16-byte aligned.
+    static __device__ __forceinline__ void emit_row(uint16_t* stage, uint32_t b, uint32_t k, uint32_t row_total,
+                                                    uint32_t base, uint32_t* out, int lane) {
+        const uint32_t mine = lane * 16;
+        if (row_total <= 64) {
+            // sparse row: most lanes hold 0 or 1 selected elements, so the k-th stores of all
+            // lanes are nearly contiguous already — write straight to HBM, no staging
+            while (b) {
+                const int j = __ffs(b) - 1;
+                b &= b - 1;
+                out[k++] = base + mine + j;
+            }
+            return;
+        }
+        if (DENSE) {
+            // dense row: 16 predicated steps, no divergence, no bit scans
+            uint16_t* p = stage + k;
+#pragma unroll
+            for (int j = 0; j < 16; j++) {
+                if (b & (1u << j)) *p++ = (uint16_t)(mine + j);
+            }
+        } else {
+            while (b) {
+                const int j = __ffs(b) - 1;
+                b &= b - 1;
+                stage[k++] = (uint16_t)(mine + j);
+            }
+        }
+        __syncwarp();
+        if (!VEC) {
+            for (uint32_t q = lane; q < row_total; q += 32) out[q] = base + stage[q];
+            __syncwarp();
+            return;
+        }
+        // head: scalar stores until `out` is 16-byte aligned; body: 4 indices per store; tail
+        const uint32_t head = min(row_total, (uint32_t)((16u - ((uint32_t)(uintptr_t)out & 15u)) & 15u) >> 2);
+        if ((uint32_t)lane < head) out[lane] = base + stage[lane];
+        const uint32_t body = (row_total - head) >> 2;  // full groups of four
+        for (uint32_t g = lane; g < body; g += 32) {
+            const uint16_t* q = stage + head + 4 * g;
+            uint4 v;
+            v.x = base + q[0]; v.y = base + q[1]; v.z = base + q[2]; v.w = base + q[3];
+            *reinterpret_cast<uint4*>(out + head + 4 * g) = v;
+        }
+        const uint32_t done = head + 4 * body;
+        if (done + lane < row_total) out[done + lane] = base + stage[done + lane];
+        __syncwarp();
+    }
+    static __device__ __forceinline__ void emit(const char* slice, size_t byte_off, uint32_t, P carry, int lane,
+                                                int, const Args& a) {
+        const uint32_t b0 = *reinterpret_cast<const uint16_t*>(slice + lane * 16);
+        const uint32_t b1 = *reinterpret_cast<const uint16_t*>(slice + 512 + lane * 16);
+        __syncwarp();  // every lane holds its masks: the slice may now be reused as the stage
+        // one scan for both rows: counts packed as (row1 << 16) | row0, each at most 512
+        const uint32_t c = __popc(b0) | (__popc(b1) << 16);
+        const uint32_t inc = warp_inclusive_sum(c);
+        const uint32_t tot = __shfl_sync(0xffffffffu, inc, 31);
+        if (tot == 0) {  // nothing selected in this slice
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // phase 1 parked the masks here
+            return;
+        }
+        const uint32_t ex = inc - c;
+        const uint32_t t0 = tot & 0xffffu, t1 = tot >> 16;
+        uint16_t* stage = reinterpret_cast<uint16_t*>(const_cast<char*>(slice));
+        const uint32_t base = a.index_base + (uint32_t)byte_off;
+        if (t0) emit_row(stage, b0, ex & 0xffffu, t0, base, a.index_out + carry, lane);
+        if (t1) emit_row(stage, b1, ex >> 16, t1, base + 512, a.index_out + carry + t0, lane);
+        // the stage was written through the generic proxy and is next written by TMA
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    // compress_large.glsl:214-216: the last partition publishes the count
+    static __device__ __forceinline__ void finish(P total, const Args& a) { a.out_count[0] = total; }
+};
+
+template <int CFG>
+__global__ void __launch_bounds__((CR_WARPS + 2 + CR_PWARPS) * 32, 1)
+compress_ring_kernel(const uint8_t* __restrict__ mask, size_t n, const uint32_t* __restrict__ size_buf,
+                     uint32_t* __restrict__ out_count, uint32_t* __restrict__ index_out, uint32_t index_base,
+                     LookbackView lb, uint32_t G) {
+    extern __shared__ __align__(128) char smem[];
+    size_t n_eff = n;
+    if (size_buf) {  // DynSize: device-resident element count (graph.rs:503-508)
+        const size_t dyn = size_buf[0];
+        n_eff = dyn < n ? dyn : n;
+    }
+    const uint32_t n_tiles = (uint32_t)((n_eff + CR_TILE - 1) / CR_TILE);
+    if (n_tiles == 0 && blockIdx.x == 0 && threadIdx.x == 0) out_count[0] = 0;
+    typename CompressOp<CFG>::Args args{index_out, out_count, index_base};
+    ring_pipeline<CompressOp<CFG>, CR_TILE, CR_STAGES, CR_WARPS, CR_AHEAD, CR_PWARPS>(reinterpret_cast<const char*>(mask), n_eff,
+                                                                      n_tiles, 0u, lb, G, args, smem);
+}
+
 }  // namespace
 
 hj_status launch_compress(hj_device* dev, size_t n, const uint32_t* size_buf, uint32_t* out_count,
                           const uint8_t* mask, uint32_t* index_out, uint32_t index_base) {
     HJ_REQUIRE(n <= 0xffffffffull, "compress: n does not fit the u32 index type");
+    static const int cfg = getenv("HJ_COMPRESS_CFG") ? atoi(getenv("HJ_COMPRESS_CFG")) : 3;  // 0: look-back kernel
+    if (cfg != 0 && ((uintptr_t)mask & 15u) == 0 && n >= (64u << 10)) {
+        const size_t tiles = (n + CR_TILE - 1) / CR_TILE;
+        HJ_TRY(ensure_lookback_scratch(dev, tiles));
+        uint32_t ep;
+        HJ_TRY(next_epoch(dev, &ep));
+        LookbackView view = lookback_view(dev->lookback.base, dev->lookback.capacity_tiles, ep);
+        const size_t smem = ring_smem_bytes<uint32_t, CR_TILE, CR_STAGES, CR_WARPS>();
+        const unsigned grid = (unsigned)(tiles < (size_t)dev->sm_count ? tiles : (size_t)dev->sm_count);
+        auto launch = [&](auto kernel) -> hj_status {
+            HJ_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            kernel<<<grid, (CR_WARPS + 2 + CR_PWARPS) * 32, smem, dev->stream>>>(mask, n, size_buf, out_count, index_out,
+                                                                                index_base, view, (grid + 31u) & ~31u);
+            return HJ_OK;
+        };
+        // measured on B200 (profiles/r01_compress_ring_sweep.txt): predicated dense staging with
+        // scalar coalesced copy-out (3) beats the bit-scan loop (1) and 128-bit copy-out (5, 7)
+        switch (cfg) {
+        case 1: HJ_TRY(launch(compress_ring_kernel<1>)); break;
+        case 5: HJ_TRY(launch(compress_ring_kernel<5>)); break;
+        case 7: HJ_TRY(launch(compress_ring_kernel<7>)); break;
+        default: HJ_TRY(launch(compress_ring_kernel<3>)); break;
+        }
+        return check_launch(dev, "compress_ring_kernel");
+    }
     size_t n_tiles = (n + CMP_TILE - 1) / CMP_TILE;
     HJ_TRY(ensure_lookback_scratch(dev, n_tiles));
     uint32_t epoch;

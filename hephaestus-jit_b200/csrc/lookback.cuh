@@ -7,8 +7,8 @@
 // dispatch before every scan (prefix_sum_large_init.glsl).  Here:
 //   * 4-byte prefixes use the same packed 64-bit word (one relaxed 64-bit store/load is
 //     atomic), the value is BIT-cast, not value-converted;
-//   * 8-byte prefixes use a flag array plus separate aggregate / inclusive arrays with
-//     release/acquire ordering, so nothing is truncated;
+//   * 8-byte prefixes use two such words (low half + flag, high half + flag) that a reader
+//     only accepts when both flags agree, so nothing is truncated and nothing needs ordering;
 //   * the flag carries a 30-bit launch epoch, so the scratch is never cleared between
 //     launches: a word written by an earlier launch simply reads as "not ready";
 //   * tiles take their index from an atomic ticket (like the reference,
@@ -49,10 +49,12 @@ __device__ __forceinline__ void tile_publish(const LookbackView& lb, uint32_t ti
         uint32_t bits = *reinterpret_cast<uint32_t*>(&value);
         st_relaxed_u64(lb.words + tile, ((unsigned long long)bits << 32) | flag);
     } else {
+        // two self-describing words: (low half, flag) and (high half, flag).  A reader accepts
+        // the pair only when both flags agree, so no store ordering is needed and both halves
+        // travel in one round trip.
         unsigned long long bits = *reinterpret_cast<unsigned long long*>(&value);
-        unsigned long long* slot = (state == TILE_AGGREGATE ? lb.agg : lb.incl) + tile;
-        st_relaxed_u64(slot, bits);
-        st_release_u32(reinterpret_cast<unsigned*>(lb.words + tile), flag);
+        st_relaxed_u64(lb.words + tile, (bits << 32) | flag);
+        st_relaxed_u64(lb.agg + tile, (bits & 0xffffffff00000000ull) | flag);
     }
 }
 
@@ -67,12 +69,13 @@ __device__ __forceinline__ uint32_t tile_read(const LookbackView& lb, uint32_t t
         *value = *reinterpret_cast<P*>(&bits);
         return flag & 3u;
     } else {
-        uint32_t flag = ld_acquire_u32(reinterpret_cast<const unsigned*>(lb.words + tile));
-        if ((flag >> 2) != lb.epoch) return TILE_INVALID;
-        uint32_t state = flag & 3u;
-        unsigned long long bits = ld_relaxed_u64((state == TILE_AGGREGATE ? lb.agg : lb.incl) + tile);
+        unsigned long long w0 = ld_relaxed_u64(lb.words + tile);
+        unsigned long long w1 = ld_relaxed_u64(lb.agg + tile);
+        uint32_t flag = (uint32_t)w0;
+        if ((flag >> 2) != lb.epoch || (uint32_t)w1 != flag) return TILE_INVALID;  // absent or torn
+        unsigned long long bits = (w0 >> 32) | (w1 & 0xffffffff00000000ull);
         *value = *reinterpret_cast<P*>(&bits);
-        return state;
+        return flag & 3u;
     }
 }
 

@@ -1,0 +1,278 @@
+// ring.cuh — persistent "reduce-ahead" tile pipeline shared by the scan and compress kernels.
+//
+// The reference's scan/compress (kernels/prefix_sum_large.glsl:165-359,
+// compress_large.glsl:76-229) are one-workgroup-per-2048-items decoupled look-back kernels: a
+// partition loads its items, publishes its aggregate, then spins walking back over its
+// predecessors' status words while it HOLDS its items in registers.  On B200 that wait (several
+// loaded-fabric L2 round trips) sits on the critical path of every tile (profiles/r01_*: 48 % of
+// the HBM roofline register-resident, 70 % with an L2-resident second sweep that re-fetches 40 %
+// of the input from DRAM).  This skeleton takes the wait off the critical path instead:
+//
+//   * one persistent CTA per SM; tiles are handed out by an atomic ticket (so a tile only ever
+//     depends on tiles whose CTA is already running — no co-residency assumption);
+//   * a producer lane streams each tile into a shared-memory ring with ONE TMA bulk copy
+//     (cp.async.bulk + mbarrier complete_tx): no registers, no LSU queue slots are held by data
+//     in flight, and the number of bytes in flight per SM is bounded by the ring;
+//   * consumer warps run two phases per tile, software-pipelined AHEAD tiles apart:
+//       phase 1 (tile i+AHEAD): reduce the tile from shared memory, publish the tile aggregate;
+//       phase 2 (tile i)      : re-read the tile from shared memory, apply the exclusive prefix,
+//                                write the result to HBM;
+//   * a prefix warp (or PWARPS of them, taking tiles in turn) turns published aggregates into tile prefixes.  Because aggregates are
+//     published AHEAD tiles (several microseconds) before they are needed, it never has to
+//     wait in steady state, and no "inclusive" status is ever published: tiles are grouped in
+//     rounds of G consecutive tickets, prefix(t) = (sum of all complete rounds before t's
+//     round) + (sum of the aggregates of the tiles before t in its round); each CTA keeps the
+//     running sum of complete rounds in a register.
+//
+// HBM traffic is exactly the algorithmic bytes (every input byte is fetched once, by TMA; every
+// output byte written once); the status-word polling is L2-resident and ~2 % of the traffic.
+#pragma once
+#include "lookback.cuh"
+
+namespace hj {
+
+constexpr uint32_t RING_END = 0xffffffffu;  // s_tile value: no more tiles
+
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ uint4 lds_v4(const void* p) {
+    uint4 r;
+    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+                 : "r"(smem_u32(p)));
+    return r;
+}
+
+// Sums of the published aggregates of tiles [a, mid) and [mid, b) in ONE sweep — executed by one
+// full warp, results in every lane.  Up to 32*M status words are fetched per round trip; words
+// not yet published are re-polled (with back-off) until they are.
+template <typename P, int M>
+__device__ __forceinline__ void ring_sum_ranges(const LookbackView& lb, uint32_t a, uint32_t mid, uint32_t b,
+                                                P* sum_lo, P* sum_hi) {
+    const int lane = lane_id();
+    P lo = (P)0, hi = (P)0;
+    for (uint32_t base = a; base < b; base += 32 * M) {
+        P v[M];
+        uint32_t st[M];
+#pragma unroll
+        for (int m = 0; m < M; m++) {
+            const uint32_t u = base + m * 32 + lane;
+            v[m] = (P)0;
+            st[m] = TILE_AGGREGATE;
+            if (u < b) st[m] = tile_read<P>(lb, u, &v[m]);
+        }
+        // anything not yet published: re-poll all of them together (independent loads), backing off
+        unsigned ns = 32;
+        while (true) {
+            bool pending = false;
+#pragma unroll
+            for (int m = 0; m < M; m++) pending |= (st[m] == TILE_INVALID);
+            if (!__any_sync(0xffffffffu, pending)) break;
+            __nanosleep(ns);
+            if (ns < 256) ns *= 2;
+#pragma unroll
+            for (int m = 0; m < M; m++)
+                if (st[m] == TILE_INVALID) st[m] = tile_read<P>(lb, base + m * 32 + lane, &v[m]);
+        }
+#pragma unroll
+        for (int m = 0; m < M; m++) {
+            const uint32_t u = base + m * 32 + lane;
+            if (u < mid) lo = (P)(lo + v[m]);
+            else hi = (P)(hi + v[m]);
+        }
+    }
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) {
+        lo = (P)(lo + shfl_xor(lo, s));
+        hi = (P)(hi + shfl_xor(hi, s));
+    }
+    *sum_lo = lo;
+    *sum_hi = hi;
+}
+
+// Shared-memory control block of the ring (placed after the data stages).
+template <typename P, int STAGES, int CWARPS>
+struct RingCtl {
+    uint64_t full[STAGES];    // producer -> everyone: tile landed (tx-count barrier)
+    uint64_t empty[STAGES];   // consumers -> producer: stage may be overwritten
+    uint64_t agg[STAGES];     // consumers -> prefix warp: warp totals written
+    uint64_t pub[STAGES];     // publisher warp -> prefix warp: aggregate published, woff written
+    uint64_t pref[STAGES];    // prefix warp -> consumers: tile prefix written
+    uint32_t tile[STAGES];    // ticket of the tile in each stage, RING_END after the last one
+    P wsum[STAGES][CWARPS];   // per-warp totals of the tile (phase 1)
+    P woff[STAGES][CWARPS];   // offset of each warp's slice inside the tile (publisher warp)
+    P tagg[STAGES];           // tile aggregate
+    P tpre[STAGES];           // exclusive prefix of the tile (prefix warp)
+};
+
+// The kernel body.  `Op` supplies the element-level work:
+//   using P                              prefix type (u32 / u64 / float / double)
+//   static P    total(slice, lane)       phase 1: this warp's total of its SLICE bytes
+//   static void emit(slice, byte_off, valid_bytes, carry, lane, warp, args, scratch)
+//                                         phase 2: write the outputs of the slice that starts
+//                                         `byte_off` bytes into the input
+//   static void finish(total, args)      called once by the CTA that owns the last tile
+// TILE bytes per stage, STAGES stages, CWARPS consumer warps, phase 1 runs AHEAD tiles ahead.
+template <class Op, int TILE, int STAGES, int CWARPS, int AHEAD, int PWARPS = 1>
+__device__ __forceinline__ void ring_pipeline(const char* __restrict__ src, size_t n_bytes, uint32_t n_tiles,
+                                              typename Op::P seed, LookbackView lb, uint32_t G,
+                                              const typename Op::Args& args, char* smem) {
+    using P = typename Op::P;
+    using Ctl = RingCtl<P, STAGES, CWARPS>;
+    static_assert(AHEAD >= 1 && AHEAD < STAGES, "phase 1 must stay inside the ring");
+    constexpr int SLICE = TILE / CWARPS;  // bytes of a tile owned by one consumer warp
+    static_assert(SLICE % 512 == 0, "a warp slice is a whole number of 512-byte rows");
+    char* stages = smem;
+    Ctl* ctl = reinterpret_cast<Ctl*>(smem + (size_t)STAGES * TILE);
+    const int warp = warp_id(), lane = lane_id();
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; s++) {
+            mbar_init(&ctl->full[s], 1);
+            mbar_init(&ctl->empty[s], CWARPS);
+            mbar_init(&ctl->agg[s], CWARPS);
+            mbar_init(&ctl->pub[s], 1);
+            mbar_init(&ctl->pref[s], 1);
+        }
+    }
+    __syncthreads();
+
+    if (warp == 0) {
+        // ---------------- producer: ticket -> TMA bulk copy of the tile into the next stage
+        for (uint32_t it = 0;; it++) {
+            const int s = it % STAGES;
+            const uint32_t use = it / STAGES;
+            // draw the ticket first: the atomic's round trip overlaps the wait for the stage
+            uint32_t t = 0;
+            if (lane == 0) {
+                t = atomicAdd(lb.ticket, 1u);
+                // n_tiles real tickets + one terminating ticket per CTA are drawn per launch
+                if (t == n_tiles + gridDim.x - 1) *lb.ticket = 0;
+            }
+            if (use > 0) mbar_wait(&ctl->empty[s], (use - 1) & 1);
+            t = __shfl_sync(0xffffffffu, t, 0);
+            if (t >= n_tiles) {
+                if (lane == 0) {
+                    ctl->tile[s] = RING_END;
+                    mbar_arrive(&ctl->full[s]);
+                }
+                break;
+            }
+            char* dst = stages + (size_t)s * TILE;
+            const size_t off = (size_t)t * TILE;
+            const size_t left = n_bytes - off;
+            const uint32_t bytes = left < (size_t)TILE ? (uint32_t)left : (uint32_t)TILE;
+            const uint32_t bulk = bytes & ~15u;
+            if (bytes < (uint32_t)TILE) {
+                // ragged last tile: the tail of the stage reads as zero (identity of the sum)
+                for (uint32_t b = bulk + lane * 4; b < (uint32_t)TILE; b += 128)
+                    *reinterpret_cast<uint32_t*>(dst + b) = 0u;
+                __syncwarp();
+                for (uint32_t b = bulk + lane; b < bytes; b += 32) dst[b] = src[off + b];
+                __syncwarp();
+            }
+            if (lane == 0) {
+                ctl->tile[s] = t;
+                if (bulk) {
+                    mbar_expect_tx(&ctl->full[s], bulk);
+                    tma_load_1d(dst, src + off, bulk, &ctl->full[s]);
+                } else {
+                    mbar_arrive(&ctl->full[s]);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ---------------- publisher warp: warp totals -> tile aggregate, published at once.
+        // It never waits on another CTA, so aggregates appear AHEAD tiles before they are needed.
+        for (uint32_t it = 0;; it++) {
+            const int s = it % STAGES;
+            const uint32_t par = (it / STAGES) & 1;
+            mbar_wait(&ctl->full[s], par);
+            const uint32_t t = ctl->tile[s];
+            if (t == RING_END) break;
+            mbar_wait(&ctl->agg[s], par);
+            P w = lane < CWARPS ? ctl->wsum[s][lane] : (P)0;
+            P inc = warp_inclusive_sum(w);
+            const P aggregate = shfl_idx(inc, 31);
+            if (lane == 0) {
+                tile_publish<P>(lb, t, TILE_AGGREGATE, aggregate);
+                ctl->tagg[s] = aggregate;
+            }
+            if (lane < CWARPS) ctl->woff[s][lane] = (P)(inc - w);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&ctl->pub[s]);
+        }
+    } else if (warp < 2 + PWARPS) {
+        // ---------------- prefix warps: published aggregates -> exclusive prefix of the tile.
+        // One sweep costs an L2 round trip (~1 us loaded); when a tile's HBM time is shorter
+        // than that (compress: 1 byte per element), PWARPS warps take the tiles in turn.
+        P rounds_total = seed;     // sum of all complete rounds before `next_round`
+        uint32_t next_round = 0;
+        for (uint32_t it = 0;; it++) {
+            const int s = it % STAGES;
+            const uint32_t par = (it / STAGES) & 1;
+            mbar_wait(&ctl->full[s], par);
+            const uint32_t t = ctl->tile[s];
+            if (t == RING_END) break;
+            if (PWARPS > 1 && (int)(it % PWARPS) != warp - 2) continue;
+            // [next_round*G, k*G): rounds completed since this CTA's previous tile; [k*G, t): the
+            // tiles before t in its own round — contiguous, so one sweep (one L2 round trip for
+            // up to 256 status words) serves both
+            const uint32_t k = t / G;
+            P full_rounds, partial;
+            ring_sum_ranges<P, (PWARPS > 1 ? 16 : 8)>(lb, next_round * G, k * G, t, &full_rounds, &partial);
+            rounds_total = (P)(rounds_total + full_rounds);
+            next_round = k;
+            const P exclusive = (P)(rounds_total + partial);
+            mbar_wait(&ctl->pub[s], par);
+            if (lane == 0) {
+                ctl->tpre[s] = exclusive;
+                if (t == n_tiles - 1) Op::finish((P)(exclusive + ctl->tagg[s]), args);
+                mbar_arrive(&ctl->pref[s]);
+            }
+        }
+    } else {
+        // ---------------- consumers: phase 1 of tile it, phase 2 of tile it - AHEAD
+        const int cw = warp - 2 - PWARPS;
+        uint32_t n_iter = 0xffffffffu;  // number of real tiles of this CTA, known at RING_END
+        // (stage, parity) of phase 1 and phase 2 advance incrementally: no division by STAGES
+        int s1 = 0, s2 = 0;
+        uint32_t par1 = 0, par2 = 0;
+        for (uint32_t it = 0;; it++) {
+            if (n_iter == 0xffffffffu) {
+                mbar_wait(&ctl->full[s1], par1);
+                if (ctl->tile[s1] == RING_END) {
+                    n_iter = it;
+                } else {
+                    const P total = Op::total(stages + (size_t)s1 * TILE + (size_t)cw * SLICE, lane);
+                    if (lane == 0) {
+                        ctl->wsum[s1][cw] = total;
+                        mbar_arrive(&ctl->agg[s1]);
+                    }
+                }
+                if (++s1 == STAGES) { s1 = 0; par1 ^= 1; }
+            }
+            if (it >= (uint32_t)AHEAD) {
+                if (it - AHEAD >= n_iter) break;
+                mbar_wait(&ctl->pref[s2], par2);
+                const uint32_t t = ctl->tile[s2];
+                const size_t byte_off = (size_t)t * TILE + (size_t)cw * SLICE;
+                const size_t valid = byte_off < n_bytes ? n_bytes - byte_off : 0;
+                Op::emit(stages + (size_t)s2 * TILE + (size_t)cw * SLICE, byte_off,
+                         valid < (size_t)SLICE ? (uint32_t)valid : (uint32_t)SLICE,
+                         (P)(ctl->tpre[s2] + ctl->woff[s2][cw]), lane, cw, args);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&ctl->empty[s2]);
+                if (++s2 == STAGES) { s2 = 0; par2 ^= 1; }
+            }
+        }
+    }
+}
+
+template <typename P, int TILE, int STAGES, int CWARPS>
+constexpr size_t ring_smem_bytes() {
+    return (size_t)STAGES * TILE + sizeof(RingCtl<P, STAGES, CWARPS>);
+}
+
+}  // namespace hj

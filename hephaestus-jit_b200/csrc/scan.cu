@@ -22,10 +22,13 @@
 // status words), tail masked in the kernel (D7), true exclusive and inclusive variants (D10),
 // correct carries for f32/u64/f64 (D3), and `seed`: a device-resident offset added to every
 // output (the cross-GPU carry of the sharded scan) at no extra pass.
+#include <algorithm>
+#include <cstdlib>
 #include <type_traits>
 
 #include "hj_internal.h"
 #include "lookback.cuh"
+#include "ring.cuh"
 
 namespace hj {
 unsigned long long* g_scan_trace = nullptr;  // set through hj_debug_scan_trace()
@@ -202,8 +205,109 @@ scan_kernel(const T* __restrict__ src, T* __restrict__ dst, size_t n, const T* _
     }
 }
 
+// ---- ring pipeline variant (ring.cuh): the default for 16-byte aligned buffers -----------------
+template <typename T, typename P_, bool INCLUSIVE, int SLICE>
+struct ScanOp {
+    using P = P_;
+    static constexpr int VEC = 16 / sizeof(T);
+    static constexpr int ROWS = SLICE / 512;
+    struct Args {
+        T* dst;
+    };
+    // phase 1: total of this warp's slice (the stage tail of a ragged tile is zero-filled)
+    static __device__ __forceinline__ P total(const char* slice, int lane) {
+        P acc = (P)0;
+#pragma unroll
+        for (int r = 0; r < ROWS; r++) {
+            const uint4 raw = lds_v4(slice + r * 512 + lane * 16);
+            const T* e = reinterpret_cast<const T*>(&raw);
+#pragma unroll
+            for (int j = 0; j < VEC; j++) acc = (P)(acc + (P)e[j]);
+        }
+#pragma unroll
+        for (int m = 16; m > 0; m >>= 1) acc = (P)(acc + shfl_xor(acc, m));
+        return acc;
+    }
+    // phase 2: scan the slice row by row with a running carry and stream the result out
+    static __device__ __forceinline__ void emit(const char* slice, size_t byte_off, uint32_t valid, P carry,
+                                                int lane, int, const Args& a) {
+        char* out_base = reinterpret_cast<char*>(a.dst) + byte_off;
+#pragma unroll
+        for (int r = 0; r < ROWS; r++) {
+            const uint32_t o = r * 512 + lane * 16;
+            if ((uint32_t)(r * 512) >= valid) break;  // warp-uniform: nothing left in this slice
+            const uint4 raw = lds_v4(slice + o);
+            const T* e = reinterpret_cast<const T*>(&raw);
+            P x[VEC];
+            P s = (P)0;
+#pragma unroll
+            for (int j = 0; j < VEC; j++) { x[j] = (P)e[j]; s = (P)(s + x[j]); }
+            const P inc = warp_inclusive_sum(s);
+            P run = (P)(carry + (P)(inc - s));
+            carry = (P)(carry + shfl_idx(inc, 31));
+            T out[VEC];
+#pragma unroll
+            for (int j = 0; j < VEC; j++) {
+                if (INCLUSIVE) { run = (P)(run + x[j]); out[j] = (T)run; }
+                else { out[j] = (T)run; run = (P)(run + x[j]); }
+            }
+            if (o + 16 <= valid) {
+                st_stream_v4(out_base + o, *reinterpret_cast<const uint4*>(out));
+            } else {
+#pragma unroll
+                for (int j = 0; j < VEC; j++)
+                    if (o + j * sizeof(T) < valid) reinterpret_cast<T*>(out_base + o)[j] = out[j];
+            }
+        }
+    }
+    static __device__ __forceinline__ void finish(P, const Args&) {}
+};
+
+template <typename T, typename P, bool INCLUSIVE, int TILE, int STAGES, int CWARPS, int AHEAD>
+__global__ void __launch_bounds__((CWARPS + 3) * 32, 1)
+scan_ring_kernel(const T* __restrict__ src, T* __restrict__ dst, size_t n, const T* __restrict__ seed,
+                 LookbackView lb, uint32_t n_tiles, uint32_t G) {
+    extern __shared__ __align__(128) char smem[];
+    using Op = ScanOp<T, P, INCLUSIVE, TILE / CWARPS>;
+    typename Op::Args args{dst};
+    ring_pipeline<Op, TILE, STAGES, CWARPS, AHEAD>(reinterpret_cast<const char*>(src), n * sizeof(T), n_tiles,
+                                                   seed ? (P)seed[0] : (P)0, lb, G, args, smem);
+}
+
+template <typename T, typename P, int TILE, int STAGES, int CWARPS, int AHEAD>
+hj_status run_ring(hj_device* dev, size_t n, bool inclusive, const void* src, void* dst, const void* seed) {
+    const size_t n_tiles = (n * sizeof(T) + TILE - 1) / TILE;
+    HJ_REQUIRE(n_tiles < (1ull << 31), "prefix_sum: too many tiles");
+    HJ_TRY(ensure_lookback_scratch(dev, n_tiles));
+    uint32_t epoch;
+    HJ_TRY(next_epoch(dev, &epoch));
+    LookbackView lb = lookback_view(dev->lookback.base, dev->lookback.capacity_tiles, epoch);
+    const size_t smem = ring_smem_bytes<P, TILE, STAGES, CWARPS>();
+    const unsigned grid = (unsigned)std::min<size_t>(n_tiles, (size_t)dev->sm_count);
+    const uint32_t G = (grid + 31u) & ~31u;  // tiles per round: about one per CTA
+    auto launch = [&](auto kernel) -> hj_status {
+        HJ_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kernel<<<grid, (CWARPS + 3) * 32, smem, dev->stream>>>((const T*)src, (T*)dst, n, (const T*)seed, lb,
+                                                              (uint32_t)n_tiles, G);
+        return check_launch(dev, "scan_ring_kernel");
+    };
+    return inclusive ? launch(scan_ring_kernel<T, P, true, TILE, STAGES, CWARPS, AHEAD>)
+                     : launch(scan_ring_kernel<T, P, false, TILE, STAGES, CWARPS, AHEAD>);
+}
+
 template <typename T, typename P>
 hj_status run(hj_device* dev, size_t n, bool inclusive, const void* src, void* dst, const void* seed) {
+    // 16-byte aligned buffers (every buffer this library allocates) take the ring pipeline;
+    // anything else, and tiny inputs, the look-back kernel below.
+    const bool aligned = (((uintptr_t)src | (uintptr_t)dst) & 15u) == 0;
+    static const int cfg = getenv("HJ_SCAN_CFG") ? atoi(getenv("HJ_SCAN_CFG")) : 1;  // 0: look-back kernel
+    if (aligned && cfg != 0 && n * sizeof(T) >= (64u << 10)) {
+        // measured on B200 (profiles/r01_scan_ring_sweep.txt): 32 KiB x 6 stages, phase 1 three
+        // tiles ahead for <= 4-byte prefixes; 8-byte prefixes (twice the shuffle work per byte,
+        // two status words per tile) do better with fewer, larger tiles
+        if (sizeof(P) == 8) return run_ring<T, P, 49152, 4, 16, 2>(dev, n, inclusive, src, dst, seed);
+        return run_ring<T, P, 32768, 6, 16, 3>(dev, n, inclusive, src, dst, seed);
+    }
     constexpr int VEC = 16 / sizeof(T);
     constexpr size_t TILE = (size_t)SCAN_WARPS * SCAN_ROWS * 32 * VEC;
     size_t n_tiles = (n + TILE - 1) / TILE;
