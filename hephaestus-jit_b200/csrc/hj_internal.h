@@ -74,6 +74,8 @@ struct hj_device {
     hj::LookbackScratch lookback;
     void* reduce_scratch = nullptr;  // partials + ticket of the single-pass reduction
     size_t reduce_scratch_bytes = 0;
+    void* hist_scratch = nullptr;    // per-CTA-group private histograms of the privatised scatter-reduce
+    size_t hist_scratch_bytes = 0;
     std::atomic<uint64_t> launches{0};
     std::atomic<uint64_t> n_alloc{0}, n_free{0};
     hj::KernelCache* kcache = nullptr;
@@ -98,6 +100,7 @@ struct DeviceGuard {
 
 // Grow-only scratch helpers (called with the device lock held).
 hj_status ensure_reduce_scratch(hj_device* dev, size_t bytes);
+hj_status ensure_hist_scratch(hj_device* dev, size_t bytes);
 hj_status ensure_lookback_scratch(hj_device* dev, size_t n_tiles);
 // Next look-back epoch (clears the scratch on wrap-around).
 hj_status next_epoch(hj_device* dev, uint32_t* out);

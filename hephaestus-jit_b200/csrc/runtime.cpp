@@ -63,6 +63,16 @@ hj_status ensure_reduce_scratch(hj_device* dev, size_t bytes) {
     return HJ_OK;
 }
 
+hj_status ensure_hist_scratch(hj_device* dev, size_t bytes) {
+    if (dev->hist_scratch_bytes >= bytes) return HJ_OK;
+    if (dev->hist_scratch) HJ_CUDA(cudaFree(dev->hist_scratch));  // implicit sync: safe
+    dev->hist_scratch = nullptr;
+    dev->hist_scratch_bytes = 0;
+    HJ_CUDA(cudaMalloc(&dev->hist_scratch, bytes));
+    dev->hist_scratch_bytes = bytes;
+    return HJ_OK;
+}
+
 hj_status ensure_lookback_scratch(hj_device* dev, size_t n_tiles) {
     LookbackScratch& lb = dev->lookback;
     if (lb.capacity_tiles >= n_tiles) return HJ_OK;

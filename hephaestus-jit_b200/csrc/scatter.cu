@@ -12,10 +12,14 @@
 //   * otherwise             : keys are streamed with 128-bit loads and applied with
 //     fire-and-forget `red.global` (L2 atomics; 2^16 bins x 4 B = 256 KiB stay L2-resident).
 // Algorithmic bytes: 4 per key (+ sizeof(T) per value if a value buffer is given).
+#include <algorithm>
 #include <type_traits>
+
+#include <cstdlib>
 
 #include "common.cuh"
 #include "hj_internal.h"
+#include "ring.cuh"
 
 namespace hj {
 namespace {
@@ -107,6 +111,148 @@ histogram_smem(const uint32_t* __restrict__ idx, uint32_t literal, uint32_t* __r
     }
 }
 
+// ---- privatised histogram with a TMA key ring (u32/i32 sum of a literal) ------------------------
+// One persistent CTA per SM; keys stream through a shared-memory ring filled by TMA bulk copies
+// (as in ring.cuh, minus the prefix logic: consumers wait for a stage, apply it, hand it back)
+// and are applied to bins in shared memory with shared-memory atomics.  How the bins fit:
+//   * PACKED16 (literal 1, <= 2^16 bins): two 16-bit counters per 32-bit word, so 2^16 bins are
+//     128 KiB and every SM holds ALL bins.  A counter that crosses 0x8000 is "cashed": the thread
+//     whose add crossed it (unique: the returned old value was 0x7fff) subtracts 0x8000 again and
+//     adds 0x8000 to the bin in HBM.  The counter can neither carry into its neighbour nor wrap:
+//     that would take 32768 further adds to one bin between the crossing add and its subtract,
+//     and a CTA has at most 28 warps x 32 lanes x 4 adds in flight.
+//   * windows (any literal, <= 8 x 32768 bins): the bin range is split into `parts` windows of
+//     <= 32768 u32 bins; groups of `parts` CTAs walk the SAME key tiles, each applying only the
+//     keys of its own window (the partners' copies of a tile come out of L2, so HBM still
+//     delivers every key once, but every SM ingests `parts` times its share).
+// Every CTA (group) ends with a private histogram; they are stored side by side in a scratch
+// buffer with plain coalesced stores and a small fold kernel adds them into dst (one global
+// atomic per bin and CTA would cost as much as the histogram itself).
+// Rejected after measurement (profiles/r01_histogram.txt): a 2-CTA cluster applying the
+// partner's keys over DSMEM — remote shared-memory atomics ran at ~0.3 per clock per SM.
+constexpr int HR_TILE = 14336, HR_STAGES = 6, HR_WARPS = 28;  // one 512-byte row per warp and tile
+constexpr uint32_t HR_MAX_BINS = 32768;
+
+struct HistCtl {
+    uint64_t full[HR_STAGES];
+    uint64_t empty[HR_STAGES];
+};
+
+template <bool PACKED16>
+__global__ void __launch_bounds__((HR_WARPS + 1) * 32, 1)
+hist_ring_kernel(const uint32_t* __restrict__ keys, size_t n, uint32_t literal, void* __restrict__ out,
+                 uint32_t* __restrict__ dst, uint32_t n_dst, uint32_t bins_per_part, uint32_t parts) {
+    extern __shared__ __align__(128) char smem[];
+    char* stages = smem;
+    HistCtl* ctl = reinterpret_cast<HistCtl*>(smem + (size_t)HR_STAGES * HR_TILE);
+    uint32_t* bins = reinterpret_cast<uint32_t*>(smem + (size_t)HR_STAGES * HR_TILE + sizeof(HistCtl));
+    const int warp = warp_id(), lane = lane_id();
+    const uint32_t part = blockIdx.x % parts, group = blockIdx.x / parts, n_groups = gridDim.x / parts;
+    const uint32_t lo = part * bins_per_part;
+    const uint32_t nb = min(bins_per_part, n_dst - lo);
+    const uint32_t n_words = PACKED16 ? (bins_per_part + 1) / 2 : bins_per_part;
+    const size_t n_bytes = n * 4;
+    const uint32_t n_tiles = (uint32_t)((n_bytes + HR_TILE - 1) / HR_TILE);
+
+    for (uint32_t b = threadIdx.x; b < n_words; b += blockDim.x) bins[b] = 0;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < HR_STAGES; s++) {
+            mbar_init(&ctl->full[s], 1);
+            mbar_init(&ctl->empty[s], HR_WARPS);
+        }
+    }
+    __syncthreads();
+
+    if (warp == 0) {
+        int s = 0;
+        uint32_t use = 0;
+        for (uint32_t t = group; t < n_tiles; t += n_groups) {
+            if (use > 0) mbar_wait(&ctl->empty[s], (use - 1) & 1);
+            char* stage = stages + (size_t)s * HR_TILE;
+            const size_t off = (size_t)t * HR_TILE;
+            const size_t left = n_bytes - off;
+            const uint32_t bytes = left < (size_t)HR_TILE ? (uint32_t)left : (uint32_t)HR_TILE;
+            const uint32_t bulk = bytes & ~15u;
+            if (bytes < (uint32_t)HR_TILE) {
+                // ragged last tile: pad with a key no window accepts
+                for (uint32_t b = bulk + lane * 4; b < (uint32_t)HR_TILE; b += 128)
+                    *reinterpret_cast<uint32_t*>(stage + b) = b < bytes ? keys[(off + b) / 4] : 0xffffffffu;
+                __syncwarp();
+            }
+            if (lane == 0) {
+                if (bulk) {
+                    mbar_expect_tx(&ctl->full[s], bulk);
+                    tma_load_1d(stage, reinterpret_cast<const char*>(keys) + off, bulk, &ctl->full[s]);
+                } else {
+                    mbar_arrive(&ctl->full[s]);
+                }
+            }
+            if (++s == HR_STAGES) { s = 0; use++; }
+        }
+    } else {
+        const int cw = warp - 1;
+        int s = 0;
+        uint32_t par = 0;
+        for (uint32_t t = group; t < n_tiles; t += n_groups) {
+            mbar_wait(&ctl->full[s], par);
+            const uint4 k = lds_v4(stages + (size_t)s * HR_TILE + cw * 512 + lane * 16);
+            const uint32_t kk[4] = {k.x, k.y, k.z, k.w};
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                const uint32_t a = kk[i] - lo;
+                if (a < nb) {
+                    if (PACKED16) {
+                        const uint32_t sh = (a & 1u) * 16u;
+                        const uint32_t old = atomicAdd(bins + (a >> 1), 1u << sh);
+                        if (((old >> sh) & 0xffffu) == 0x7fffu) {  // this add crossed 0x8000: cash it
+                            atomicSub(bins + (a >> 1), 0x8000u << sh);
+                            atomicAdd(dst + lo + a, 0x8000u);
+                        }
+                    } else {
+                        atomicAdd(bins + a, literal);
+                    }
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&ctl->empty[s]);
+            if (++s == HR_STAGES) { s = 0; par ^= 1; }
+        }
+    }
+    __syncthreads();
+    // private histogram of this group: coalesced plain stores, folded by hist_fold_kernel
+    if (PACKED16) {
+        uint32_t* mine = reinterpret_cast<uint32_t*>(out) + (size_t)group * ((n_dst + 1) / 2);
+        for (uint32_t b = threadIdx.x; b < (nb + 1) / 2; b += blockDim.x) mine[b] = bins[b];
+    } else {
+        uint32_t* mine = reinterpret_cast<uint32_t*>(out) + (size_t)group * n_dst + lo;
+        for (uint32_t b = threadIdx.x; b < nb; b += blockDim.x) mine[b] = bins[b];
+    }
+}
+
+// dst[b] += sum over groups of their private counter (u32, or u16 pairs packed in u32 words)
+template <bool PACKED16>
+__global__ void __launch_bounds__(256)
+hist_fold_kernel(const uint32_t* __restrict__ scratch, uint32_t n_groups, uint32_t* __restrict__ dst, uint32_t n_dst) {
+    const uint32_t i = blockIdx.x * 256 + threadIdx.x;
+    if (PACKED16) {
+        const uint32_t n_words = (n_dst + 1) / 2;
+        if (i >= n_words) return;
+        uint32_t even = 0, odd = 0;
+        for (uint32_t g = 0; g < n_groups; g++) {
+            const uint32_t w = scratch[(size_t)g * n_words + i];
+            even += w & 0xffffu;
+            odd += w >> 16;
+        }
+        if (even) dst[2 * i] += even;
+        if (odd && 2 * i + 1 < n_dst) dst[2 * i + 1] += odd;
+    } else {
+        if (i >= n_dst) return;
+        uint32_t acc = 0;
+        for (uint32_t g = 0; g < n_groups; g++) acc += scratch[(size_t)g * n_dst + i];
+        if (acc) dst[i] += acc;
+    }
+}
+
 template <typename T>
 __global__ void __launch_bounds__(256)
 gather_kernel(const T* __restrict__ src, const uint32_t* __restrict__ idx, T* __restrict__ dst, size_t n) {
@@ -157,20 +303,55 @@ hj_status launch_scatter_reduce(hj_device* dev, hj_reduce_op op, hj_type_kind ty
     hj_status s = HJ_ERR_UNSUPPORTED;
     if (op == HJ_REDUCE_PROD)  // todo!() in the reference (glsl/mod.rs:422)
         return fail(HJ_ERR_UNSUPPORTED, "scatter_reduce(Prod) is not implemented by the reference");
-    // privatised shared-memory histogram for small bin counts
-    if (op == HJ_REDUCE_SUM && (ty == HJ_U32 || ty == HJ_I32) && !src && n_dst * 4 <= 64 * 1024 &&
-        n >= (1u << 16)) {
-        int vec_ok = ((uintptr_t)idx & 15u) == 0;
-        size_t want = (n / 4 + SR_THREADS * 8 - 1) / (SR_THREADS * 8);
-        size_t cap = (size_t)dev->sm_count * 2;
-        int grid = (int)(want < 1 ? 1 : (want > cap ? cap : want));
-        size_t smem = n_dst * 4;
-        if (smem > 48 * 1024)
-            HJ_CUDA(cudaFuncSetAttribute(histogram_smem, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)smem));
-        histogram_smem<<<grid, SR_THREADS, smem, dev->stream>>>(idx, (uint32_t)literal, (uint32_t*)dst, n,
-                                                               (uint32_t)n_dst, vec_ok);
-        return check_launch(dev, "histogram_smem");
+    // privatised shared-memory histogram (u32/i32 sum of a literal)
+    static const int hist_cfg = getenv("HJ_HIST_CFG") ? atoi(getenv("HJ_HIST_CFG")) : 1;  // 0: global atomics
+    if (op == HJ_REDUCE_SUM && (ty == HJ_U32 || ty == HJ_I32) && !src && n >= (1u << 16) && hist_cfg != 0) {
+        const uint32_t parts = (uint32_t)((n_dst + HR_MAX_BINS - 1) / HR_MAX_BINS);
+        if (((uintptr_t)idx & 15u) == 0 && parts <= 8 && n >= (1u << 20)) {
+            const size_t ring = (size_t)HR_STAGES * HR_TILE + sizeof(HistCtl);
+            const bool packed16 = parts > 1 && n_dst <= 65536 && (uint32_t)literal == 1u && hist_cfg != 2;
+            if (packed16) {
+                // every SM holds all bins as 16-bit counters and walks only its own key tiles
+                const uint32_t n_groups = (uint32_t)dev->sm_count;
+                const uint32_t n_words = (uint32_t)((n_dst + 1) / 2);
+                HJ_TRY(ensure_hist_scratch(dev, (size_t)n_groups * n_words * 4));
+                const size_t smem = ring + (size_t)n_words * 4;
+                auto kern = hist_ring_kernel<true>;
+                HJ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                kern<<<n_groups, (HR_WARPS + 1) * 32, smem, dev->stream>>>(
+                    idx, n, 1u, dev->hist_scratch, (uint32_t*)dst, (uint32_t)n_dst, (uint32_t)n_dst, 1u);
+                HJ_TRY(check_launch(dev, "hist_ring_kernel"));
+                hist_fold_kernel<true><<<(n_words + 255) / 256, 256, 0, dev->stream>>>(
+                    (const uint32_t*)dev->hist_scratch, n_groups, (uint32_t*)dst, (uint32_t)n_dst);
+                return check_launch(dev, "hist_fold_kernel");
+            }
+            // u32 bins in windows: groups of `parts` CTAs share the key tiles
+            const uint32_t bins_per_part = (uint32_t)((n_dst + parts - 1) / parts);
+            const uint32_t n_groups = std::max(1u, (uint32_t)dev->sm_count / parts);
+            HJ_TRY(ensure_hist_scratch(dev, (size_t)n_groups * n_dst * 4));
+            const size_t smem = ring + (size_t)bins_per_part * 4;
+            auto kern = hist_ring_kernel<false>;
+            HJ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            kern<<<n_groups * parts, (HR_WARPS + 1) * 32, smem, dev->stream>>>(
+                idx, n, (uint32_t)literal, dev->hist_scratch, (uint32_t*)dst, (uint32_t)n_dst, bins_per_part, parts);
+            HJ_TRY(check_launch(dev, "hist_ring_kernel"));
+            hist_fold_kernel<false><<<(unsigned)((n_dst + 255) / 256), 256, 0, dev->stream>>>(
+                (const uint32_t*)dev->hist_scratch, n_groups, (uint32_t*)dst, (uint32_t)n_dst);
+            return check_launch(dev, "hist_fold_kernel");
+        }
+        if (n_dst * 4 <= 64 * 1024) {
+            int vec_ok = ((uintptr_t)idx & 15u) == 0;
+            size_t want = (n / 4 + SR_THREADS * 8 - 1) / (SR_THREADS * 8);
+            size_t cap = (size_t)dev->sm_count * 2;
+            int grid = (int)(want < 1 ? 1 : (want > cap ? cap : want));
+            size_t smem = n_dst * 4;
+            if (smem > 48 * 1024)
+                HJ_CUDA(cudaFuncSetAttribute(histogram_smem, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)smem));
+            histogram_smem<<<grid, SR_THREADS, smem, dev->stream>>>(idx, (uint32_t)literal, (uint32_t*)dst, n,
+                                                                   (uint32_t)n_dst, vec_ok);
+            return check_launch(dev, "histogram_smem");
+        }
     }
     switch (ty) {
     case HJ_U32: s = run_sr_int<uint32_t>(dev, op, n, idx, src, literal, dst, n_dst); break;

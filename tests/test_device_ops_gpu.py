@@ -286,6 +286,31 @@ def test_histogram_bit_exact(dev, n_bins):
     assert int(got.sum(dtype=np.uint64)) == n
 
 
+@pytest.mark.parametrize("n_bins,literal,dist", [
+    (1 << 16, 1, "hot"),       # packed 16-bit counters: hot bins cross 0x8000 and are cashed into HBM
+    (1 << 16, 3, "uniform"),   # literal != 1: u32 bins in two windows
+    (100_000, 1, "uniform"),   # more than 2^16 bins: four windows, ragged last window
+    (40_000, 1, "oob"),        # keys >= n_dst are ignored
+    (1 << 15, 1, "uniform"),   # one window holding every bin
+])
+def test_histogram_ring_paths_bit_exact(dev, n_bins, literal, dist):
+    n = (1 << 22) + 12345
+    rng = np.random.Generator(np.random.PCG64(n_bins + literal))
+    if dist == "hot":
+        keys = np.where(rng.random(n) < 0.6, rng.integers(0, 4, size=n), rng.integers(0, n_bins, size=n)).astype(np.uint32)
+    elif dist == "oob":
+        keys = rng.integers(0, 2 * n_bins, size=n).astype(np.uint32)
+        keys[::1001] = 0xFFFFFFFF
+    else:
+        keys = rng.integers(0, n_bins, size=n).astype(np.uint32)
+    init = rng.integers(0, 1000, size=n_bins).astype(np.uint32)
+    dst = dev.create_buffer_from_slice(init)
+    dev.scatter_reduce(hj.SUM, hj.U32, n, dev.create_buffer_from_slice(keys), None, literal, dst, n_bins)
+    inside = keys[keys < n_bins]
+    want = init + (oracle.histogram_u32_mt(inside, n_bins) * np.uint32(literal))
+    assert np.array_equal(dst.to_host(np.uint32), want)
+
+
 @pytest.mark.parametrize("op", [hj.MAX, hj.MIN, hj.OR, hj.AND, hj.XOR, hj.SUM])
 def test_scatter_reduce_values_bit_exact(dev, op):
     n, n_bins = 200003, 1000
