@@ -63,6 +63,12 @@ class PassReport(ctypes.Structure):
                 ("duration_us", ctypes.c_double)]
 
 
+class GraphReport(ctypes.Structure):
+    _fields_ = [("aliasing_rate", ctypes.c_float), ("aliasing_duration_us", ctypes.c_double),
+                ("backend_cpu_us", ctypes.c_double), ("n_passes", ctypes.c_uint32),
+                ("passes", ctypes.POINTER(PassReport)), ("passes_capacity", ctypes.c_uint32)]
+
+
 class Report(ctypes.Structure):
     _fields_ = [("cpu_duration_us", ctypes.c_double), ("n_passes", ctypes.c_uint32),
                 ("passes", ctypes.POINTER(PassReport)), ("passes_capacity", ctypes.c_uint32)]
@@ -90,6 +96,7 @@ lib = _load()
 _vp, _sz, _i32, _u32, _u64 = (ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int32, ctypes.c_uint32,
                               ctypes.c_uint64)
 _pvp = ctypes.POINTER(ctypes.c_void_p)
+_pu64, _pu32, _pi32 = ctypes.POINTER(ctypes.c_uint64), ctypes.POINTER(ctypes.c_uint32), ctypes.POINTER(ctypes.c_int32)
 
 _SIGS = {
     "hj_last_error": (ctypes.c_char_p, []),
@@ -141,6 +148,69 @@ _SIGS = {
     "hj_sharded_prefix_sum": (_i32, [_vp, _i32, _sz, _i32, _vp, _vp]),
     "hj_sharded_compress": (_i32, [_vp, _sz, _u32, _vp, _vp, _vp, _vp]),
     "hj_sharded_scatter_reduce": (_i32, [_vp, _i32, _i32, _sz, _vp, _vp, _u64, _vp, _sz]),
+    # ---- trace / schedule / graph
+    "hj_tr_type_scalar": (_u32, [_u32]),
+    "hj_tr_type_vector": (_u32, [_u32, _u32]),
+    "hj_tr_type_array": (_u32, [_u32, _u32]),
+    "hj_tr_type_matrix": (_u32, [_u32, _u32, _u32]),
+    "hj_tr_type_struct": (_u32, [ctypes.POINTER(_u32), _u32]),
+    "hj_tr_type_size": (_sz, [_u32]),
+    "hj_tr_type_alignment": (_sz, [_u32]),
+    "hj_tr_type_offset": (_sz, [_u32, _u32]),
+    "hj_tr_type_kind": (_u32, [_u32]),
+    "hj_tr_var_retain": (_i32, [_u64]),
+    "hj_tr_var_release": (_i32, [_u64]),
+    "hj_tr_var_info": (_i32, [_u64, _pu32, _pi32, _pu64, _pi32, _pu64, _pi32]),
+    "hj_tr_var_hash": (_u64, [_u64]),
+    "hj_tr_is_empty": (_i32, []),
+    "hj_tr_n_live": (_u64, []),
+    "hj_tr_var_buffer": (_i32, [_u64, _pvp]),
+    "hj_tr_index": (_i32, [_pu64]),
+    "hj_tr_sized_index": (_i32, [_u64, _pu64]),
+    "hj_tr_dynamic_index": (_i32, [_u64, _u64, _pu64]),
+    "hj_tr_literal": (_i32, [_u32, _u64, _pu64]),
+    "hj_tr_sized_literal": (_i32, [_u32, _u64, _u64, _pu64]),
+    "hj_tr_array": (_i32, [_vp, _u32, _vp, _u64, _pu64]),
+    "hj_tr_from_buffer": (_i32, [_vp, _u32, _u64, _pu64]),
+    "hj_tr_bop": (_i32, [_u32, _u64, _u64, _pu64]),
+    "hj_tr_uop": (_i32, [_u32, _u64, _pu64]),
+    "hj_tr_cast": (_i32, [_u64, _u32, _pu64]),
+    "hj_tr_bitcast": (_i32, [_u64, _u32, _pu64]),
+    "hj_tr_fma": (_i32, [_u64, _u64, _u64, _pu64]),
+    "hj_tr_select": (_i32, [_u64, _u64, _u64, _pu64]),
+    "hj_tr_extract": (_i32, [_u64, _u32, _pu64]),
+    "hj_tr_extract_dyn": (_i32, [_u64, _u64, _pu64]),
+    "hj_tr_composite": (_i32, [_pu64, _u32, _pu64]),
+    "hj_tr_vec": (_i32, [_pu64, _u32, _pu64]),
+    "hj_tr_arr": (_i32, [_pu64, _u32, _pu64]),
+    "hj_tr_gather": (_i32, [_u64, _u64, _u64, _pu64]),
+    "hj_tr_scatter": (_i32, [_u64, _u64, _u64, _u64]),
+    "hj_tr_scatter_reduce": (_i32, [_u64, _u64, _u64, _u64, _u32]),
+    "hj_tr_scatter_atomic": (_i32, [_u64, _u64, _u64, _u64, _u32, _pu64]),
+    "hj_tr_atomic_inc": (_i32, [_u64, _u64, _u64, _pu64]),
+    "hj_tr_prefix_sum": (_i32, [_u64, _i32, _pu64]),
+    "hj_tr_reduce": (_i32, [_u64, _u32, _pu64]),
+    "hj_tr_compress": (_i32, [_u64, _pu64, _pu64]),
+    "hj_tr_compress_dyn": (_i32, [_u64, _pu64]),
+    "hj_tr_scope_start": (_i32, [_i32, _pu64, _u32, _pu64, _pu64]),
+    "hj_tr_scope_end": (_i32, [_u64, _pu64, _u32, _pu64]),
+    "hj_tr_schedule": (_i32, [_u64]),
+    "hj_tr_schedule_eval": (_i32, []),
+    "hj_tr_reset_schedule": (_i32, []),
+    "hj_tr_var_size": (_i32, [_u64, _pu64]),
+    "hj_tr_to_host": (_i32, [_u64, _u64, _u64, _vp]),
+    "hj_tr_compile": (_i32, [_pvp]),
+    "hj_tr_compile_fn": (_i32, [_pu64, _u32, _pu64, _u32, _pvp]),
+    "hj_graph_retain": (_i32, [_vp]),
+    "hj_graph_release": (_i32, [_vp]),
+    "hj_graph_n_passes": (_u32, [_vp]),
+    "hj_graph_n_outputs": (_u32, [_vp]),
+    "hj_graph_debug_string": (_i32, [_vp, _pvp]),
+    "hj_graph_launch": (_i32, [_vp, _vp, _pu64, _u32, _pu64, ctypes.POINTER(GraphReport)]),
+    "hj_fcache_get": (_i32, [_u64, _pvp]),
+    "hj_fcache_put": (_i32, [_u64, _vp]),
+    "hj_fcache_clear": (_i32, []),
+    "hj_fcache_size": (_u64, []),
 }
 
 for _name, (_res, _args) in _SIGS.items():

