@@ -124,7 +124,7 @@ def run_reference(args):
     if rank != 0:
         return 0
     import oracle
-    oracle.set_threads(0)
+    oracle.set_threads(os.cpu_count() or 1)  # torchrun exports OMP_NUM_THREADS=1: ask for every core
     cores = oracle.get_threads()
     n = 1 << 24  # bounded sample of the 2^28-element workload per step
     rng = np.random.Generator(np.random.PCG64(0))
@@ -157,7 +157,7 @@ def run_reference(args):
 
 def cpu_baseline():
     import oracle
-    oracle.set_threads(0)
+    oracle.set_threads(os.cpu_count() or 1)
     cores = oracle.get_threads()
     n = 1 << 24
     rng = np.random.Generator(np.random.PCG64(0))
@@ -230,6 +230,62 @@ def run_suite(torch, hj, dev, peak, world, rank, comm):
                                                                       "bound": "L2 atomic throughput, not HBM"})
     if world > 1:
         out["_note"] = f"per-GPU share (1/{world}) of each array, local kernels only; collectives reported under 'sharded'"
+    return out
+
+
+def run_sharded(torch, dist, hj, dev, peak, world, rank):
+    """The sharded ops of BASELINE.json (C3 / C4 / C5) INCLUDING their NCCL exchange: 2^30 (2^28 for
+    the histogram) elements split contiguously over the ranks, timed with CUDA events on the launch
+    stream, max over ranks.  GB/s = GLOBAL algorithmic bytes / time; the scan moves 12 B/elem when
+    sharded (shard totals first) but is credited with 8."""
+    sharded = importlib.import_module("hephaestus-jit_b200.sharded")
+    comm = sharded.Comm.from_torch(dev)
+    out = {}
+    g = torch.Generator(device="cuda").manual_seed(4321 + rank)
+    wrap = lambda t: dev.wrap(t.data_ptr(), t.numel() * t.element_size())
+    n30, n28 = (1 << 30) // world, (1 << 28) // world
+
+    def timed(fn, iters=10):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        dist.barrier()
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(iters)]
+        for a, b in ev:
+            a.record()
+            fn()
+            b.record()
+        torch.cuda.synchronize()
+        ms = sorted(a.elapsed_time(b) for a, b in ev)[iters // 2]
+        t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def entry(nbytes_global, ms):
+        gbs = nbytes_global / ms / 1e6
+        return {"GB/s": round(gbs, 1), "frac_of_measured_peak_x_gpus": round(gbs / (peak * world), 4), "ms": round(ms, 4)}
+
+    xf = torch.rand(n30, device="cuda", generator=g, dtype=torch.float32)
+    xu = torch.randint(0, 4, (n30,), device="cuda", generator=g, dtype=torch.int32)
+    o1 = torch.zeros(16, device="cuda", dtype=torch.float32)
+    on = torch.empty(n30, device="cuda", dtype=torch.int32)
+    bf, bu, bo1, bon = wrap(xf), wrap(xu), wrap(o1), wrap(on)
+    out["C3 sharded reduce sum f32 2^30 + all-gather"] = entry(4 * n30 * world, timed(lambda: comm.reduce(hj.SUM, hj.F32, n30, bf, bo1)))
+    out["C3 sharded reduce max u32 2^30 + all-gather"] = entry(4 * n30 * world, timed(lambda: comm.reduce(hj.MAX, hj.U32, n30, bu, bo1)))
+    out["C4 sharded inclusive scan u32 2^30 (totals pass + all-gather + seeded scan)"] = entry(
+        8 * n30 * world, timed(lambda: comm.prefix_sum(hj.U32, n30, True, bu, bon)))
+    mask = (torch.rand(n30, device="cuda", generator=g) < 0.5).to(torch.uint8)
+    cnt = torch.zeros(1, device="cuda", dtype=torch.int32)
+    counts = torch.zeros(world, device="cuda", dtype=torch.int32)
+    bm, bc, bcs = wrap(mask), wrap(cnt), wrap(counts)
+    ms = timed(lambda: comm.compress(n30, (rank * n30) & 0xFFFFFFFF, bm, bon, bc, bcs))
+    out["C4 sharded compress p=0.5 2^30 + all-gather of counts"] = entry(n30 * world + 4 * int(cnt.item()), ms)
+    keys = torch.randint(0, 1 << 16, (n28,), device="cuda", generator=g, dtype=torch.int32)
+    hist = torch.zeros(1 << 16, device="cuda", dtype=torch.int32)
+    bk, bh = wrap(keys), wrap(hist)
+    out["C5 sharded histogram 2^28 keys -> 2^16 bins + all-reduce"] = entry(
+        4 * n28 * world, timed(lambda: comm.scatter_reduce(hj.SUM, hj.U32, n28, bk, None, 1, bh, 1 << 16)))
+    comm.destroy()
     return out
 
 
@@ -323,46 +379,73 @@ def run_own(args):
         want = oracle.c2_chain(x[:m].cpu().numpy())
         check = bool(np.allclose(got, want, rtol=4e-7, atol=1e-7))
 
-    # ---- end-to-end through the C ABI with host buffers (pinned), rank-local
+    # ---- end-to-end through the C ABI with HOST buffers (pinned), rank-local.  Two public paths:
+    #  (a) pipelined: hj_kernel_map_host streams chunks through upload / kernel / download streams
+    #      (the headline e2e: every input byte crosses PCIe in, every output byte out, per step);
+    #  (b) blocking, the reference's own call sequence: upload -> execute_graph -> to_host.
     import ctypes
     L = importlib.import_module("hephaestus-jit_b200._lib")
     hx, hy = ctypes.c_void_p(), ctypes.c_void_p()
     L.check(L.lib.hj_host_alloc(4 * n, ctypes.byref(hx)))
     L.check(L.lib.hj_host_alloc(4 * n, ctypes.byref(hy)))
     host_x = np.ctypeslib.as_array(ctypes.cast(hx, ctypes.POINTER(ctypes.c_float)), shape=(n,))
+    host_y = np.ctypeslib.as_array(ctypes.cast(hy, ctypes.POINTER(ctypes.c_float)), shape=(n,))
     host_x[:] = np.random.Generator(np.random.PCG64(rank)).random(n, dtype=np.float32) * 8 - 4
-    dx, dy = dev.create_buffer(4 * n), dev.create_buffer(4 * n)
     e2e_steps = max(3, min(args.steps, 10))
 
-    def e2e_step():
+    def e2e_pipelined():
+        dev.map_host(kernel, n, [hx.value, hy.value], 1 << 23)
+
+    dx, dy = dev.create_buffer(4 * n), dev.create_buffer(4 * n)
+
+    def e2e_blocking():
         L.check(L.lib.hj_buffer_upload(dx.handle, 0, hx, 4 * n))            # H2D, pinned source
         dev.execute_graph(passes, [dx, dy], descs)
         L.check(L.lib.hj_buffer_to_host(dy.handle, 0, 4 * n, hy))           # D2H, blocks until visible
 
-    e2e_step()
-    if world > 1:
-        dist.barrier()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        e2e_step()
-    dev.sync()
-    e2e_s = (time.perf_counter() - t0) / e2e_steps
-    if world > 1:
-        t = torch.tensor([e2e_s], device="cuda", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_s = float(t.item())
-    e2e = {"value": world * nbytes_step / e2e_s / 1e9, "unit": "GB/s", "h2d_bytes_per_step": 4 * n,
-           "d2h_bytes_per_step": 4 * n, "ms_per_step": e2e_s * 1e3, "steps": e2e_steps,
-           "path": "hj_buffer_upload (pinned) -> hj_execute_graph -> hj_buffer_to_host"}
+    def time_e2e(fn):
+        fn()
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            fn()
+        dev.sync()
+        dt = (time.perf_counter() - t0) / e2e_steps
+        if world > 1:
+            t = torch.tensor([dt], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        return dt
+
+    launches_e2e0 = dev.launch_count()
+    pipe_s = time_e2e(e2e_pipelined)
+    launches_e2e = (dev.launch_count() - launches_e2e0) // (e2e_steps + 1)
+    e2e_ok = None
+    if rank == 0:
+        import oracle
+        m = 1 << 16
+        e2e_ok = bool(np.allclose(host_y[-m:], oracle.c2_chain(host_x[-m:].copy()), rtol=4e-7, atol=1e-7))
+    block_s = time_e2e(e2e_blocking)
+    e2e = {"value": world * nbytes_step / pipe_s / 1e9, "unit": "GB/s", "h2d_bytes_per_step": 4 * n,
+           "d2h_bytes_per_step": 4 * n, "ms_per_step": pipe_s * 1e3, "steps": e2e_steps,
+           "path": "pinned host arrays -> hj_kernel_map_host (8 Mi-element chunks: upload | kernel | download streams)",
+           "kernel_launches_per_step": int(launches_e2e), "oracle_check": e2e_ok,
+           "blocking_path": {"value": world * nbytes_step / block_s / 1e9, "ms_per_step": block_s * 1e3,
+                             "path": "hj_buffer_upload (pinned) -> hj_execute_graph -> hj_buffer_to_host"}}
     L.lib.hj_host_free(hx)
     L.lib.hj_host_free(hy)
     del dx, dy
 
     suite = None
+    shard_suite = None
     if not args.no_suite:
         del x, y
         torch.cuda.empty_cache()
         suite = run_suite(torch, hj, dev, peak, world, rank, None)
+        if world > 1:
+            torch.cuda.empty_cache()
+            shard_suite = run_sharded(torch, dist, hj, dev, peak, world, rank)
 
     if rank == 0:
         achieved = nbytes_step / (kernel_ms * 1e-3) / 1e9
@@ -394,6 +477,8 @@ def run_own(args):
         }
         if suite is not None:
             line["suite"] = suite
+        if shard_suite is not None:
+            line["sharded"] = shard_suite
         print(json.dumps(line))
     if world > 1:
         dist.barrier()

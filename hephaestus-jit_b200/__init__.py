@@ -206,6 +206,14 @@ class Device:
         check(lib.hj_kernel_launch(self._h, kernel.handle, size, size_buf.handle if size_buf else None,
                                    arr, len(buffers), index_base))
 
+    def map_host(self, kernel: "Kernel", n: int, host_arrays, chunk_elems: int = 0) -> None:
+        """Out-of-core elementwise map: ``host_arrays[i]`` (numpy arrays or raw addresses, pinned for
+        full speed) is buffer slot ``i`` of the kernel; upload, kernel and download are pipelined
+        chunk by chunk (hj_kernel_map_host)."""
+        ptrs = [a.ctypes.data if hasattr(a, "ctypes") else int(a) for a in host_arrays]
+        arr = (ctypes.c_void_p * max(len(ptrs), 1))(*ptrs)
+        check(lib.hj_kernel_map_host(self._h, kernel.handle, n, arr, len(ptrs), chunk_elems))
+
     def kernel_cache_stats(self) -> dict:
         v = [ctypes.c_uint64() for _ in range(3)]
         check(lib.hj_device_kernel_cache_stats(self._h, *[ctypes.byref(x) for x in v]))

@@ -138,6 +138,7 @@ _SIGS = {
     "hj_kernel_release": (_i32, [_vp]),
     "hj_ir_compile_cubin": (_i32, [ctypes.POINTER(Ir), _pvp, ctypes.POINTER(_sz)]),
     "hj_kernel_launch": (_i32, [_vp, _vp, _sz, _vp, _pvp, _u32, _u32]),
+    "hj_kernel_map_host": (_i32, [_vp, _vp, _sz, _pvp, _u32, _sz]),
     "hj_device_kernel_cache_stats": (_i32, [_vp] + [ctypes.POINTER(_u64)] * 3),
     "hj_execute_graph": (_i32, [_vp, ctypes.POINTER(Pass), _u32, _pvp, ctypes.POINTER(BufferDesc),
                                 _u32, ctypes.POINTER(Report)]),

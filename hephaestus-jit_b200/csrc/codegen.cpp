@@ -718,6 +718,12 @@ bool codegen_cuda(const hj_ir* ir, CodegenResult* out, std::string* err) {
     out->unroll = unroll;
     out->threads = threads;
     out->uses_f16 = g.uses_f16;
+    out->slot_flags.clear();
+    out->slot_elem_bytes.clear();
+    for (auto& sl : g.slots) {
+        out->slot_flags.push_back((uint8_t)((sl.stage_load ? 1 : 0) | (sl.stage_store ? 2 : 0)));
+        out->slot_elem_bytes.push_back((uint32_t)scalar_size(sl.elem_kind));
+    }
     return true;
 }
 

@@ -20,6 +20,43 @@
 
 using namespace hj;
 
+namespace {
+// A kernel pass whose whole IR is `dst[keys[i]] += literal` (u32 / i32) — what
+// `sized_literal(v, n).scatter_reduce(&hist, &keys, ReduceOp::Sum)` (trace.rs:1210-1233) compiles
+// to — is a histogram: it goes to the privatised shared-memory kernel (scatter.cu) instead of
+// one global atomic per key from the JIT kernel.  Returns false if the IR has any other shape.
+struct HistMatch {
+    uint32_t dst_slot, key_slot, ty;
+    uint64_t literal;
+};
+bool match_histogram(const hj_ir* ir, HistMatch* m) {
+    IRView v(ir);
+    if (ir->n_buffers != 2 || ir->n_vars != 6) return false;
+    int sr = -1;
+    for (uint32_t i = 0; i < ir->n_vars; i++) {
+        const uint32_t op = v.var(i).op;
+        if (op == HJ_OP_SCATTER_REDUCE) {
+            if (sr >= 0) return false;
+            sr = (int)i;
+        } else if (op != HJ_OP_BUFFER_REF && op != HJ_OP_LITERAL && op != HJ_OP_INDEX && op != HJ_OP_GATHER) {
+            return false;
+        }
+    }
+    if (sr < 0 || v.n_deps(sr) != 3 || v.var(sr).arg != HJ_REDUCE_SUM) return false;
+    const uint32_t dst = v.dep(sr, 0), src = v.dep(sr, 1), idx = v.dep(sr, 2);
+    if (v.var(dst).op != HJ_OP_BUFFER_REF || v.var(src).op != HJ_OP_LITERAL || v.var(idx).op != HJ_OP_GATHER) return false;
+    if (v.n_deps(idx) != 2 || v.var(v.dep(idx, 0)).op != HJ_OP_BUFFER_REF || v.var(v.dep(idx, 1)).op != HJ_OP_INDEX) return false;
+    const uint32_t kind = v.kind(v.var_type(src));
+    if ((kind != HJ_U32 && kind != HJ_I32) || v.kind(v.var_type(idx)) != HJ_U32 || v.kind(v.var_type(dst)) != kind) return false;
+    m->dst_slot = (uint32_t)v.var(dst).data;
+    m->key_slot = (uint32_t)v.var(v.dep(idx, 0)).data;
+    if (m->dst_slot == m->key_slot) return false;
+    m->ty = kind;
+    m->literal = v.var(src).data;
+    return true;
+}
+}  // namespace
+
 extern "C" hj_status hj_execute_graph(hj_device* dev, const hj_pass* passes, uint32_t n_passes,
                                       hj_buffer* const* env, const hj_buffer_desc* descs,
                                       uint32_t n_resources, hj_report* report) {
@@ -55,6 +92,17 @@ extern "C" hj_status hj_execute_graph(hj_device* dev, const hj_pass* passes, uin
         switch (p.kind) {
         case HJ_PASS_KERNEL: {
             HJ_REQUIRE(p.ir, "kernel pass %u without IR", i);
+            HistMatch hm;
+            if (!size_buf && p.n_resources == 2 && p.size >= (1u << 20) && match_histogram(p.ir, &hm)) {
+                snprintf(name, sizeof(name), "Histogram %u [%llu]", i, (unsigned long long)p.size);
+                hj_buffer *dst, *keys;
+                const hj_buffer_desc* ddst;
+                HJ_TRY(res(p, hm.dst_slot, &dst, &ddst));
+                HJ_TRY(res(p, hm.key_slot, &keys, nullptr));
+                HJ_TRY(hj_scatter_reduce(dev, HJ_REDUCE_SUM, (hj_type_kind)hm.ty, p.size, keys, nullptr, hm.literal, dst,
+                                         ddst->size));
+                break;
+            }
             snprintf(name, sizeof(name), "JIT Kernel %u [%llu]", i, (unsigned long long)p.size);
             hj_kernel* k = nullptr;
             HJ_TRY(hj_kernel_get(dev, p.ir, &k));

@@ -47,6 +47,10 @@ struct CodegenResult {
     uint32_t unroll = 1;         // vectors per thread
     uint32_t threads = 256;
     bool uses_f16 = false;
+    // per buffer slot: bit 0 = only read through the bare Index (staged loads), bit 1 = only
+    // written through the bare Index at top level (staged stores); 0 = accessed some other way
+    std::vector<uint8_t> slot_flags;
+    std::vector<uint32_t> slot_elem_bytes;
 };
 // Lower `ir` to CUDA C++; on failure returns false and sets `err`.
 bool codegen_cuda(const hj_ir* ir, CodegenResult* out, std::string* err);

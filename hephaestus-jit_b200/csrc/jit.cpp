@@ -9,6 +9,7 @@
 #include <sys/stat.h>
 #include <unistd.h>
 
+#include <algorithm>
 #include <cstdlib>
 #include <fstream>
 
@@ -22,6 +23,8 @@ struct hj_kernel {
     cudaKernel_t scalar = nullptr;
     cudaKernel_t vec = nullptr;
     uint32_t vec_width = 1, unroll = 1, threads = 256, n_buffers = 0;
+    std::vector<uint8_t> slot_flags;        // codegen.cpp: 1 = streamed input, 2 = streamed output
+    std::vector<uint32_t> slot_elem_bytes;
 };
 
 namespace hj {
@@ -186,6 +189,8 @@ hj_status hj_kernel_get(hj_device* dev, const hj_ir* ir, hj_kernel** out) {
     k->unroll = cg.unroll;
     k->threads = cg.threads;
     k->n_buffers = ir->n_buffers;
+    k->slot_flags = cg.slot_flags;
+    k->slot_elem_bytes = cg.slot_elem_bytes;
     if (disk) kc->n_disk_hits++;
     else kc->n_compiled++;
     k->rc.store(2);  // cache + caller
@@ -243,6 +248,106 @@ hj_status hj_kernel_launch(hj_device* dev, hj_kernel* k, size_t size, hj_buffer*
     }
     dev->launches.fetch_add(1, std::memory_order_relaxed);
     return HJ_OK;
+}
+
+// Out-of-core elementwise map: every buffer of the kernel lives in HOST memory (pinned for full
+// speed) and is addressed by the bare Index only.  The array is cut into chunks that flow
+// through three streams — upload, kernel, download — with device-side chunk buffers reused
+// round-robin, so the PCIe link runs in both directions while the kernel works on the chunk in
+// between.  KernelOp::Index keeps its global value (index_base = chunk offset).  This is the
+// pipelined form of `tr::array(..)` -> launch -> `to_vec(..)` (trace.rs:647-663, 1404-1438),
+// which the reference runs as three blocking steps.
+hj_status hj_kernel_map_host(hj_device* dev, hj_kernel* k, size_t n, void* const* host_arrays, uint32_t n_arrays,
+                             size_t chunk_elems) {
+    HJ_REQUIRE(dev && k && host_arrays, "null argument");
+    HJ_REQUIRE(n_arrays == k->n_buffers, "kernel expects %u buffers, got %u", k->n_buffers, n_arrays);
+    HJ_REQUIRE(n <= 0xffffffffull, "size does not fit the u32 index type");
+    HJ_REQUIRE(k->vec, "kernel has no streamed entry point");
+    for (uint32_t i = 0; i < n_arrays; i++) {
+        HJ_REQUIRE(host_arrays[i], "host array %u is null", i);
+        HJ_REQUIRE(k->slot_flags[i] == 1 || k->slot_flags[i] == 2,
+                   "buffer %u is not accessed through the bare Index only: the kernel cannot be streamed", i);
+    }
+    if (n == 0) return HJ_OK;
+    const size_t per_block = (size_t)k->threads * k->vec_width * k->unroll;
+    if (chunk_elems == 0) chunk_elems = (size_t)1 << 24;
+    chunk_elems = (chunk_elems + per_block - 1) / per_block * per_block;
+    constexpr int DEPTH = 3;
+    DeviceGuard g(dev);
+    cudaStream_t s_up, s_k, s_down;
+    HJ_CUDA(cudaStreamCreateWithFlags(&s_up, cudaStreamNonBlocking));
+    HJ_CUDA(cudaStreamCreateWithFlags(&s_k, cudaStreamNonBlocking));
+    HJ_CUDA(cudaStreamCreateWithFlags(&s_down, cudaStreamNonBlocking));
+    cudaEvent_t up_done[DEPTH], k_done[DEPTH], down_done[DEPTH], start;
+    for (int d = 0; d < DEPTH; d++) {
+        HJ_CUDA(cudaEventCreateWithFlags(&up_done[d], cudaEventDisableTiming));
+        HJ_CUDA(cudaEventCreateWithFlags(&k_done[d], cudaEventDisableTiming));
+        HJ_CUDA(cudaEventCreateWithFlags(&down_done[d], cudaEventDisableTiming));
+    }
+    // order after everything already enqueued on the device stream
+    HJ_CUDA(cudaEventCreateWithFlags(&start, cudaEventDisableTiming));
+    HJ_CUDA(cudaEventRecord(start, dev->stream));
+    HJ_CUDA(cudaStreamWaitEvent(s_up, start, 0));
+    HJ_CUDA(cudaStreamWaitEvent(s_k, start, 0));
+    HJ_CUDA(cudaStreamWaitEvent(s_down, start, 0));
+    std::vector<char*> dbuf((size_t)DEPTH * n_arrays, nullptr);
+    hj_status st = HJ_OK;
+    for (size_t i = 0; i < dbuf.size() && st == HJ_OK; i++) {
+        void* p = nullptr;
+        cudaError_t e = cudaMallocAsync(&p, chunk_elems * k->slot_elem_bytes[i % n_arrays], dev->stream);
+        if (e != cudaSuccess) { cudaGetLastError(); st = fail(HJ_ERR_OOM, "chunk buffer allocation failed: %s", cudaGetErrorString(e)); }
+        dbuf[i] = (char*)p;
+    }
+    if (st == HJ_OK) {
+        HJ_CUDA(cudaEventRecord(start, dev->stream));  // allocations are stream-ordered
+        HJ_CUDA(cudaStreamWaitEvent(s_up, start, 0));
+        HJ_CUDA(cudaStreamWaitEvent(s_k, start, 0));
+        HJ_CUDA(cudaStreamWaitEvent(s_down, start, 0));
+    }
+    const size_t n_chunks = (n + chunk_elems - 1) / chunk_elems;
+    for (size_t c = 0; c < n_chunks && st == HJ_OK; c++) {
+        const int d = (int)(c % DEPTH);
+        const size_t first = c * chunk_elems;
+        const size_t count = std::min(chunk_elems, n - first);
+        char** bufs = &dbuf[(size_t)d * n_arrays];
+        // the slot is free once the chunk that used it DEPTH steps ago has been downloaded
+        if (c >= DEPTH) cudaStreamWaitEvent(s_up, down_done[d], 0);
+        for (uint32_t i = 0; i < n_arrays; i++)
+            if (k->slot_flags[i] == 1)
+                cudaMemcpyAsync(bufs[i], (const char*)host_arrays[i] + first * k->slot_elem_bytes[i],
+                                count * k->slot_elem_bytes[i], cudaMemcpyHostToDevice, s_up);
+        cudaEventRecord(up_done[d], s_up);
+        cudaStreamWaitEvent(s_k, up_done[d], 0);
+        if (c >= DEPTH) cudaStreamWaitEvent(s_k, down_done[d], 0);
+        std::vector<void*> ptrs(n_arrays);
+        for (uint32_t i = 0; i < n_arrays; i++) ptrs[i] = bufs[i];
+        const uint32_t* size_ptr = nullptr;
+        uint32_t size_static = (uint32_t)count, index_base = (uint32_t)first;
+        std::vector<void*> args = {(void*)&size_ptr, (void*)&size_static, (void*)&index_base};
+        for (uint32_t i = 0; i < n_arrays; i++) args.push_back((void*)&ptrs[i]);
+        const unsigned grid = (unsigned)((count + per_block - 1) / per_block);
+        cudaError_t e = cudaLaunchKernel((const void*)k->vec, dim3(grid), dim3(k->threads), args.data(), 0, s_k);
+        if (e != cudaSuccess) { cudaGetLastError(); st = fail(HJ_ERR_CUDA, "launch of fused kernel failed: %s", cudaGetErrorString(e)); break; }
+        dev->launches.fetch_add(1, std::memory_order_relaxed);
+        cudaEventRecord(k_done[d], s_k);
+        cudaStreamWaitEvent(s_down, k_done[d], 0);
+        for (uint32_t i = 0; i < n_arrays; i++)
+            if (k->slot_flags[i] == 2)
+                cudaMemcpyAsync((char*)host_arrays[i] + first * k->slot_elem_bytes[i], bufs[i],
+                                count * k->slot_elem_bytes[i], cudaMemcpyDeviceToHost, s_down);
+        cudaEventRecord(down_done[d], s_down);
+    }
+    // results are visible on return, like BackendBuffer::to_host
+    cudaStreamSynchronize(s_up);
+    cudaStreamSynchronize(s_k);
+    cudaError_t fin = cudaStreamSynchronize(s_down);
+    for (char* p : dbuf)
+        if (p) cudaFreeAsync(p, dev->stream);
+    for (int d = 0; d < DEPTH; d++) { cudaEventDestroy(up_done[d]); cudaEventDestroy(k_done[d]); cudaEventDestroy(down_done[d]); }
+    cudaEventDestroy(start);
+    cudaStreamDestroy(s_up); cudaStreamDestroy(s_k); cudaStreamDestroy(s_down);
+    if (st == HJ_OK && fin != cudaSuccess) { cudaGetLastError(); st = fail(HJ_ERR_CUDA, "streamed map failed: %s", cudaGetErrorString(fin)); }
+    return st;
 }
 
 }  // extern "C"

@@ -229,6 +229,13 @@ hj_status hj_ir_compile_cubin(const hj_ir* ir, void** out_cubin, size_t* out_siz
  * (backend/vulkan/mod.rs:194-257).  `index_base` offsets KernelOp::Index (sharding). */
 hj_status hj_kernel_launch(hj_device* dev, hj_kernel* k, size_t size, hj_buffer* size_buf,
                            hj_buffer* const* buffers, uint32_t n_buffers, uint32_t index_base);
+/* Out-of-core elementwise map over HOST arrays (pinned memory for full PCIe speed): array i is
+ * the kernel's buffer slot i and holds `n` elements; every slot must be accessed through the bare
+ * Index only.  Chunks of `chunk_elems` elements (0 = default) are pipelined through upload /
+ * kernel / download streams; results are visible on return.  The pipelined form of
+ * tr::array -> launch -> to_vec (trace.rs:647-663, 1404-1438). */
+hj_status hj_kernel_map_host(hj_device* dev, hj_kernel* k, size_t n, void* const* host_arrays,
+                             uint32_t n_arrays, size_t chunk_elems);
 /* cache statistics: compiled (misses) / hits, and on-disk cubin cache hits */
 hj_status hj_device_kernel_cache_stats(hj_device* dev, uint64_t* n_compiled, uint64_t* n_hits,
                                        uint64_t* n_disk_hits);

@@ -176,3 +176,28 @@ def test_execute_graph_prefix_sum_pass_and_errors(dev):
         dev.execute_graph([{"kind": 7, "resources": [0, 1]}], env, descs)
     with pytest.raises(hj.HjError):  # empty resource slot
         dev.execute_graph([{"kind": hj.PASS_PREFIX_SUM, "arg": 1, "resources": [0, 1]}], [env[0], None], descs)
+
+
+def test_map_host_streams_chunks_with_global_index(dev):
+    """hj_kernel_map_host: host arrays in, host arrays out, chunked through three streams; Index
+    keeps its global value across chunks and the ragged last chunk is masked."""
+    import ctypes
+    irm = importlib.import_module("hephaestus-jit_b200.ir")
+    n = (1 << 20) + 12345
+    rng = np.random.Generator(np.random.PCG64(3))
+    x = (rng.random(n, dtype=np.float32) * 8 - 4).astype(np.float32)
+    y = np.zeros(n, np.float32)
+    k = dev.kernel(irm.c2_chain_ir())
+    dev.map_host(k, n, [x, y], chunk_elems=1 << 17)  # 9 chunks, pageable host memory is allowed
+    assert np.allclose(y, oracle.c2_chain(x), rtol=4e-7, atol=1e-7)
+    # y[i] = x[i] + f32(Index): the index must be global, not chunk-local
+    b = irm.IRBuilder()
+    f32, u32 = b.scalar(irm.F32), b.scalar(irm.U32)
+    src = b.buffer_ref(f32, 0)
+    idx = b.index()
+    val = b.gather(f32, src, idx)
+    s = b.bop(irm.BOP_ADD, f32, val, b.uop(irm.UOP_CAST, f32, idx))
+    b.scatter(b.buffer_ref(f32, 1), s, idx)
+    k2 = dev.kernel(b)
+    dev.map_host(k2, n, [x, y], chunk_elems=1 << 18)
+    assert np.array_equal(y, x + np.arange(n, dtype=np.uint32).astype(np.float32))

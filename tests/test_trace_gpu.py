@@ -300,8 +300,11 @@ def test_histogram_through_trace(device):
     hist = tr.sized_literal(0, nb, U32)
     tr.sized_literal(1, n, U32).scatter_reduce(hist, tr.array(keys, device), hj.SUM)
     hist.schedule()
-    tr.compile().launch(device)
+    rep = tr.compile().launch(device, timed=True)
     assert np.array_equal(hist.to_vec(), oracle.histogram_u32_mt(keys, nb))
+    # execute_graph recognises the `dst[keys[i]] += literal` kernel and runs the privatised
+    # shared-memory histogram instead of one global atomic per key
+    assert rep.passes[-1][0].startswith("Histogram")
 
 
 def test_c2_chain_traced_end_to_end(device):
