@@ -227,7 +227,7 @@ def run_suite(torch, hj, dev, peak, world, rank, comm):
     bk, bh = wrap(keys), wrap(hist)
     ms = timed_events(torch, lambda: dev.scatter_reduce(hj.SUM, hj.U32, n28, bk, None, 1, bh, 1 << 16), iters, 3)
     out["C5 histogram 2^28 keys -> 2^16 bins"] = entry(4 * n28, ms, {"elements_per_s": n28 / ms * 1e3, "bytes_per_elem": 4,
-                                                                      "bound": "L2 atomic throughput, not HBM"})
+                                                                      "bound": "shared-memory atomic throughput, not HBM"})
     if world > 1:
         out["_note"] = f"per-GPU share (1/{world}) of each array, local kernels only; collectives reported under 'sharded'"
     return out

@@ -639,7 +639,12 @@ bool codegen_cuda(const hj_ir* ir, CodegenResult* out, std::string* err) {
     for (auto& s : g.slots)
         if (s.stage_load || s.stage_store) { any_staged = true; widest = std::max(widest, scalar_size(s.elem_kind)); }
     uint32_t vec = widest == 8 ? 2 : 4;
-    uint32_t unroll = 2;
+    // vectors per thread: measured on B200 for the C2 chain (profiles/r01_jit_unroll.txt):
+    // 1 -> 5326, 2 -> 5910, 3 -> 6366, 4 -> 6373, 6 -> 6430, 8 -> 6205 GB/s.  4 keeps the register
+    // budget reasonable; kernels that stage many buffers fall back to 2.
+    size_t n_staged = 0;
+    for (auto& sl : g.slots) n_staged += (sl.stage_load || sl.stage_store) ? 1 : 0;
+    uint32_t unroll = n_staged <= 3 ? 4 : 2;
     if (const char* e = getenv("HJ_JIT_UNROLL")) { int u = atoi(e); if (u >= 1 && u <= 8) unroll = (uint32_t)u; }
     const uint32_t threads = 256;
 

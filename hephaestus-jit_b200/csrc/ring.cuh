@@ -241,7 +241,7 @@ __device__ __forceinline__ void ring_pipeline(const char* __restrict__ src, size
         uint32_t par1 = 0, par2 = 0;
         for (uint32_t it = 0;; it++) {
             if (n_iter == 0xffffffffu) {
-                mbar_wait(&ctl->full[s1], par1);
+                mbar_wait_parked(&ctl->full[s1], par1);
                 if (ctl->tile[s1] == RING_END) {
                     n_iter = it;
                 } else {
@@ -255,7 +255,7 @@ __device__ __forceinline__ void ring_pipeline(const char* __restrict__ src, size
             }
             if (it >= (uint32_t)AHEAD) {
                 if (it - AHEAD >= n_iter) break;
-                mbar_wait(&ctl->pref[s2], par2);
+                mbar_wait_parked(&ctl->pref[s2], par2);
                 const uint32_t t = ctl->tile[s2];
                 const size_t byte_off = (size_t)t * TILE + (size_t)cw * SLICE;
                 const size_t valid = byte_off < n_bytes ? n_bytes - byte_off : 0;
