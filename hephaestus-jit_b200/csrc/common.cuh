@@ -134,7 +134,7 @@ __device__ __forceinline__ void mbar_wait_parked(uint64_t* bar, uint32_t parity)
             : "r"(smem_u32(bar)), "r"(parity), "r"(20000u)
             : "memory");
         if (done) break;
-        __nanosleep(100);
+        __nanosleep(400);
     }
 }
 // global -> shared bulk copy; dst/src 16-byte aligned, bytes a multiple of 16

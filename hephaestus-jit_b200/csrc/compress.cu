@@ -148,9 +148,7 @@ compress_kernel(const uint8_t* __restrict__ mask, size_t n, const uint32_t* __re
 // positions of a row as u16 offsets in the slice's own bytes (dead by then) before a
 // coalesced store of base + offset.  The kernel is instruction-issue bound, not HBM bound, at
 // low selectivity, hence the 28 warps and the lean inner loops.
-constexpr int CR_TILE = 28672, CR_STAGES = 7, CR_WARPS = 28, CR_AHEAD = 3, CR_PWARPS = 1;
-constexpr int CR_SLICE = CR_TILE / CR_WARPS;  // 1024 mask bytes per warp = 2 rows
-static_assert(CR_SLICE == 1024, "emit() is written for two rows per warp");
+constexpr int CR_WARPS = 28;
 
 // 16 mask bytes -> 16-bit lane mask (bit i = byte i is non-zero).
 // Fast path: `bool` buffers only ever hold 0 or 1 (codegen stores bool as u8 0/1,
@@ -168,22 +166,41 @@ __device__ __forceinline__ uint32_t lane_mask16(uint4 v) {
     return gather_lo(v.x) | (gather_lo(v.y) << 4) | (gather_lo(v.z) << 8) | (gather_lo(v.w) << 12);
 }
 
-template <int CFG>
+template <int CFG, int SLICE, int TILE, int TSLOTS>
 struct CompressOp {
     using P = uint32_t;
+    static constexpr int ROWS = SLICE / 512;  // 512-element rows per warp slice, ranked in pairs
+    static_assert(ROWS % 2 == 0, "rows are ranked in pairs");
     static constexpr bool DENSE = (CFG & 2) != 0, VEC = (CFG & 4) != 0;
+    static constexpr bool NO_PHASE2 = (CFG & 32) != 0, NO_PHASE1 = (CFG & 128) != 0;  // ablation experiments only
+    static constexpr bool SKIP_PREFIX = (CFG & 256) != 0;
     struct Args {
         uint32_t* index_out;
         uint32_t* out_count;
         uint32_t index_base;
     };
-    static __device__ __forceinline__ P total(const char* slice, int lane) {
-        char* mine = const_cast<char*>(slice) + lane * 16;
-        const uint32_t b0 = lane_mask16(lds_v4(mine));
-        const uint32_t b1 = lane_mask16(lds_v4(mine + 512));
-        *reinterpret_cast<uint16_t*>(mine) = (uint16_t)b0;
-        *reinterpret_cast<uint16_t*>(mine + 512) = (uint16_t)b1;
-        return __reduce_add_sync(0xffffffffu, __popc(b0) + __popc(b1));
+    // aux layout (shared memory behind the ring): TSLOTS mask planes of TILE/8 bytes (one u16 per
+    // 16 mask bytes), then one 1 KiB index stage per consumer warp.  Phase 1 leaves only the masks
+    // behind, so the 28 KiB data stage goes straight back to the producer (EARLY release).
+    static constexpr int MASK_PLANE = TILE / 8;
+    static __device__ __forceinline__ uint16_t* masks_of(char* aux, int slot, int cw) {
+        return reinterpret_cast<uint16_t*>(aux + slot * MASK_PLANE + cw * (SLICE / 8));
+    }
+    static __device__ __forceinline__ uint16_t* stage_of(char* aux, int cw) {
+        return reinterpret_cast<uint16_t*>(aux + TSLOTS * MASK_PLANE + cw * 1024);
+    }
+    static __device__ __forceinline__ P total(const char* slice, char* aux, int slot, int cw, int lane) {
+        if (NO_PHASE1) return 0;
+        const char* mine = slice + lane * 16;
+        uint16_t* m = masks_of(aux, slot, cw);
+        uint32_t cnt = 0;
+#pragma unroll
+        for (int r = 0; r < ROWS; r++) {
+            const uint32_t b = lane_mask16(lds_v4(mine + r * 512));
+            m[r * 32 + lane] = (uint16_t)b;
+            cnt += __popc(b);
+        }
+        return __reduce_add_sync(0xffffffffu, cnt);
     }
     // One 512-element row: lane `lane` owns bits `b` (elements lane*16 ..), its first selected
     // element has rank `k` in the row.  Selected positions are staged as u16 row offsets, then
@@ -235,34 +252,35 @@ struct CompressOp {
         if (done + lane < row_total) out[done + lane] = base + stage[done + lane];
         __syncwarp();
     }
-    static __device__ __forceinline__ void emit(const char* slice, size_t byte_off, uint32_t, P carry, int lane,
-                                                int, const Args& a) {
-        const uint32_t b0 = *reinterpret_cast<const uint16_t*>(slice + lane * 16);
-        const uint32_t b1 = *reinterpret_cast<const uint16_t*>(slice + 512 + lane * 16);
-        __syncwarp();  // every lane holds its masks: the slice may now be reused as the stage
-        // one scan for both rows: counts packed as (row1 << 16) | row0, each at most 512
-        const uint32_t c = __popc(b0) | (__popc(b1) << 16);
-        const uint32_t inc = warp_inclusive_sum(c);
-        const uint32_t tot = __shfl_sync(0xffffffffu, inc, 31);
-        if (tot == 0) {  // nothing selected in this slice
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // phase 1 parked the masks here
-            return;
-        }
-        const uint32_t ex = inc - c;
-        const uint32_t t0 = tot & 0xffffu, t1 = tot >> 16;
-        uint16_t* stage = reinterpret_cast<uint16_t*>(const_cast<char*>(slice));
+    static __device__ __forceinline__ void emit(const char*, char* aux, int slot, size_t byte_off, uint32_t, P carry,
+                                                int lane, int cw, const Args& a) {
+        if (NO_PHASE2) return;
+        uint32_t bits[ROWS];
+#pragma unroll
+        const uint16_t* m = masks_of(aux, slot, cw);
+#pragma unroll
+        for (int r = 0; r < ROWS; r++) bits[r] = m[r * 32 + lane];
+        uint16_t* stage = stage_of(aux, cw);
         const uint32_t base = a.index_base + (uint32_t)byte_off;
-        if (t0) emit_row(stage, b0, ex & 0xffffu, t0, base, a.index_out + carry, lane);
-        if (t1) emit_row(stage, b1, ex >> 16, t1, base + 512, a.index_out + carry + t0, lane);
-        // the stage was written through the generic proxy and is next written by TMA
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+#pragma unroll
+        for (int r = 0; r < ROWS; r += 2) {
+            // one scan per pair of rows: counts packed as (odd row << 16) | even row, each <= 512
+            const uint32_t c = __popc(bits[r]) | (__popc(bits[r + 1]) << 16);
+            const uint32_t inc = warp_inclusive_sum(c);
+            const uint32_t tot = __shfl_sync(0xffffffffu, inc, 31);
+            const uint32_t ex = inc - c;
+            const uint32_t t0 = tot & 0xffffu, t1 = tot >> 16;
+            if (t0) emit_row(stage, bits[r], ex & 0xffffu, t0, base + r * 512, a.index_out + carry, lane);
+            if (t1) emit_row(stage, bits[r + 1], ex >> 16, t1, base + (r + 1) * 512, a.index_out + carry + t0, lane);
+            carry += t0 + t1;
+        }
     }
     // compress_large.glsl:214-216: the last partition publishes the count
     static __device__ __forceinline__ void finish(P total, const Args& a) { a.out_count[0] = total; }
 };
 
-template <int CFG>
-__global__ void __launch_bounds__((CR_WARPS + 2 + CR_PWARPS) * 32, 1)
+template <int CFG, int CR_TILE, int CR_STAGES, int CR_TSLOTS, int CR_AHEAD>
+__global__ void __launch_bounds__((CR_WARPS + 3) * 32, 1)
 compress_ring_kernel(const uint8_t* __restrict__ mask, size_t n, const uint32_t* __restrict__ size_buf,
                      uint32_t* __restrict__ out_count, uint32_t* __restrict__ index_out, uint32_t index_base,
                      LookbackView lb, uint32_t G) {
@@ -274,8 +292,9 @@ compress_ring_kernel(const uint8_t* __restrict__ mask, size_t n, const uint32_t*
     }
     const uint32_t n_tiles = (uint32_t)((n_eff + CR_TILE - 1) / CR_TILE);
     if (n_tiles == 0 && blockIdx.x == 0 && threadIdx.x == 0) out_count[0] = 0;
-    typename CompressOp<CFG>::Args args{index_out, out_count, index_base};
-    ring_pipeline<CompressOp<CFG>, CR_TILE, CR_STAGES, CR_WARPS, CR_AHEAD, CR_PWARPS>(reinterpret_cast<const char*>(mask), n_eff,
+    using Op = CompressOp<CFG, CR_TILE / CR_WARPS, CR_TILE, CR_TSLOTS>;
+    typename Op::Args args{index_out, out_count, index_base};
+    ring_pipeline<Op, CR_TILE, CR_STAGES, CR_WARPS, CR_AHEAD, CR_TSLOTS, true>(reinterpret_cast<const char*>(mask), n_eff,
                                                                       n_tiles, 0u, lb, G, args, smem);
 }
 
@@ -284,28 +303,34 @@ compress_ring_kernel(const uint8_t* __restrict__ mask, size_t n, const uint32_t*
 hj_status launch_compress(hj_device* dev, size_t n, const uint32_t* size_buf, uint32_t* out_count,
                           const uint8_t* mask, uint32_t* index_out, uint32_t index_base) {
     HJ_REQUIRE(n <= 0xffffffffull, "compress: n does not fit the u32 index type");
-    static const int cfg = getenv("HJ_COMPRESS_CFG") ? atoi(getenv("HJ_COMPRESS_CFG")) : 3;  // 0: look-back kernel
+    static const int cfg = getenv("HJ_COMPRESS_CFG") ? atoi(getenv("HJ_COMPRESS_CFG")) : 67;  // 0: look-back kernel
     if (cfg != 0 && ((uintptr_t)mask & 15u) == 0 && n >= (64u << 10)) {
-        const size_t tiles = (n + CR_TILE - 1) / CR_TILE;
+        // tile geometry: 28 KiB tiles, 5 data stages (all but one in flight), 8 tile slots with
+        // phase 1 six tiles ahead of phase 2; or 56 KiB tiles x 3 stages, 4 slots, three ahead
+        const bool big = (cfg & 64) != 0;
+        const size_t tile_bytes = big ? 57344 : 28672;
+        const size_t tiles = (n + tile_bytes - 1) / tile_bytes;
         HJ_TRY(ensure_lookback_scratch(dev, tiles));
         uint32_t ep;
         HJ_TRY(next_epoch(dev, &ep));
         LookbackView view = lookback_view(dev->lookback.base, dev->lookback.capacity_tiles, ep);
-        const size_t smem = ring_smem_bytes<uint32_t, CR_TILE, CR_STAGES, CR_WARPS>();
         const unsigned grid = (unsigned)(tiles < (size_t)dev->sm_count ? tiles : (size_t)dev->sm_count);
-        auto launch = [&](auto kernel) -> hj_status {
+        auto launch = [&](auto kernel, size_t smem) -> hj_status {
             HJ_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            kernel<<<grid, (CR_WARPS + 2 + CR_PWARPS) * 32, smem, dev->stream>>>(mask, n, size_buf, out_count, index_out,
+            kernel<<<grid, (CR_WARPS + 3) * 32, smem, dev->stream>>>(mask, n, size_buf, out_count, index_out,
                                                                                 index_base, view, (grid + 31u) & ~31u);
             return HJ_OK;
         };
-        // measured on B200 (profiles/r01_compress_ring_sweep.txt): predicated dense staging with
-        // scalar coalesced copy-out (3) beats the bit-scan loop (1) and 128-bit copy-out (5, 7)
+        const size_t smem_small = ring_smem_bytes<uint32_t, 28672, 5, CR_WARPS, 8>(8 * (28672 / 8) + CR_WARPS * 1024);
+        const size_t smem_big = ring_smem_bytes<uint32_t, 57344, 3, CR_WARPS, 4>(4 * (57344 / 8) + CR_WARPS * 1024);
         switch (cfg) {
-        case 1: HJ_TRY(launch(compress_ring_kernel<1>)); break;
-        case 5: HJ_TRY(launch(compress_ring_kernel<5>)); break;
-        case 7: HJ_TRY(launch(compress_ring_kernel<7>)); break;
-        default: HJ_TRY(launch(compress_ring_kernel<3>)); break;
+        case 1: HJ_TRY(launch(compress_ring_kernel<1, 28672, 5, 8, 6>, smem_small)); break;
+        case 35: HJ_TRY(launch(compress_ring_kernel<35, 28672, 5, 8, 6>, smem_small)); break;
+        case 163: HJ_TRY(launch(compress_ring_kernel<163, 28672, 5, 8, 6>, smem_small)); break;
+        case 419: HJ_TRY(launch(compress_ring_kernel<419, 28672, 5, 8, 6>, smem_small)); break;
+        case 64 + 35: HJ_TRY(launch(compress_ring_kernel<35, 57344, 3, 4, 3>, smem_big)); break;
+        case 3: HJ_TRY(launch(compress_ring_kernel<3, 28672, 5, 8, 6>, smem_small)); break;
+        default: HJ_TRY(launch(compress_ring_kernel<3, 57344, 3, 4, 3>, smem_big)); break;
         }
         return check_launch(dev, "compress_ring_kernel");
     }

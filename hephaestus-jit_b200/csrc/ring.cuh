@@ -17,7 +17,7 @@
 //       phase 1 (tile i+AHEAD): reduce the tile from shared memory, publish the tile aggregate;
 //       phase 2 (tile i)      : re-read the tile from shared memory, apply the exclusive prefix,
 //                                write the result to HBM;
-//   * a prefix warp (or PWARPS of them, taking tiles in turn) turns published aggregates into tile prefixes.  Because aggregates are
+//   * a prefix warp turns published aggregates into tile prefixes.  Because aggregates are
 //     published AHEAD tiles (several microseconds) before they are needed, it never has to
 //     wait in steady state, and no "inclusive" status is ever published: tiles are grouped in
 //     rounds of G consecutive tickets, prefix(t) = (sum of all complete rounds before t's
@@ -91,74 +91,98 @@ __device__ __forceinline__ void ring_sum_ranges(const LookbackView& lb, uint32_t
     *sum_hi = hi;
 }
 
-// Shared-memory control block of the ring (placed after the data stages).
-template <typename P, int STAGES, int CWARPS>
+// Shared-memory control block of the ring (placed after the data stages).  Two rings: the DATA
+// stages the TMA fills (full / empty), and the TILE slots that carry a tile's bookkeeping from
+// phase 1 to phase 2 (agg / pub / pref and the per-warp sums and offsets).  With EARLY release
+// (phase 2 does not need the tile's bytes any more, e.g. compress keeps only bit masks) a data
+// stage goes back to the producer right after phase 1, so every stage but one is in flight and
+// the number of tile slots — not the number of stages — bounds how far phase 1 runs ahead.
+template <typename P, int STAGES, int TSLOTS, int CWARPS>
 struct RingCtl {
-    uint64_t full[STAGES];    // producer -> everyone: tile landed (tx-count barrier)
+    uint64_t full[STAGES];    // producer -> consumers: tile landed (tx-count barrier)
     uint64_t empty[STAGES];   // consumers -> producer: stage may be overwritten
-    uint64_t agg[STAGES];     // consumers -> prefix warp: warp totals written
-    uint64_t pub[STAGES];     // publisher warp -> prefix warp: aggregate published, woff written
-    uint64_t pref[STAGES];    // prefix warp -> consumers: tile prefix written
-    uint32_t tile[STAGES];    // ticket of the tile in each stage, RING_END after the last one
-    P wsum[STAGES][CWARPS];   // per-warp totals of the tile (phase 1)
-    P woff[STAGES][CWARPS];   // offset of each warp's slice inside the tile (publisher warp)
-    P tagg[STAGES];           // tile aggregate
-    P tpre[STAGES];           // exclusive prefix of the tile (prefix warp)
+    uint64_t agg[TSLOTS];     // consumers -> publisher warp: warp totals written
+    uint64_t pub[TSLOTS];     // publisher warp -> prefix warp: aggregate published, woff written
+    uint64_t pref[TSLOTS];    // prefix warp -> consumers: tile prefix written
+    uint32_t stile[STAGES];   // ticket of the tile in each data stage, RING_END after the last one
+    uint32_t ttile[TSLOTS][CWARPS];  // ticket of the tile in each tile slot, one private copy per consumer warp
+                                     // (a fast warp may re-enter a slot while a slow one still reads its own)
+    P wsum[TSLOTS][CWARPS];   // per-warp totals of the tile (phase 1)
+    P woff[TSLOTS][CWARPS];   // offset of each warp's slice inside the tile (publisher warp)
+    P tagg[TSLOTS];           // tile aggregate
+    P tpre[TSLOTS];           // exclusive prefix of the tile (prefix warp)
 };
 
 // The kernel body.  `Op` supplies the element-level work:
-//   using P                              prefix type (u32 / u64 / float / double)
-//   static P    total(slice, lane)       phase 1: this warp's total of its SLICE bytes
-//   static void emit(slice, byte_off, valid_bytes, carry, lane, warp, args, scratch)
-//                                         phase 2: write the outputs of the slice that starts
-//                                         `byte_off` bytes into the input
-//   static void finish(total, args)      called once by the CTA that owns the last tile
-// TILE bytes per stage, STAGES stages, CWARPS consumer warps, phase 1 runs AHEAD tiles ahead.
-template <class Op, int TILE, int STAGES, int CWARPS, int AHEAD, int PWARPS = 1>
+//   using P                                   prefix type (u32 / u64 / float / double)
+//   static P    total(slice, aux, slot, cw, lane)
+//                                              phase 1: this warp's total of its SLICE bytes; may park
+//                                              per-tile data in `aux` (shared memory after the ring)
+//   static void emit(slice, aux, slot, byte_off, valid_bytes, carry, lane, cw, args)
+//                                              phase 2: write the outputs of the slice that starts
+//                                              `byte_off` bytes into the input (slice is only valid
+//                                              without EARLY release)
+//   static void finish(total, args)           called once by the CTA that owns the last tile
+// TILE bytes per stage, STAGES data stages, TSLOTS tile slots, CWARPS consumer warps; phase 1 runs
+// AHEAD tiles ahead of phase 2.
+template <class Op, int TILE, int STAGES, int CWARPS, int AHEAD, int TSLOTS = STAGES, bool EARLY = false>
 __device__ __forceinline__ void ring_pipeline(const char* __restrict__ src, size_t n_bytes, uint32_t n_tiles,
                                               typename Op::P seed, LookbackView lb, uint32_t G,
                                               const typename Op::Args& args, char* smem) {
     using P = typename Op::P;
-    using Ctl = RingCtl<P, STAGES, CWARPS>;
-    static_assert(AHEAD >= 1 && AHEAD < STAGES, "phase 1 must stay inside the ring");
+    using Ctl = RingCtl<P, STAGES, TSLOTS, CWARPS>;
+    static_assert(AHEAD >= 1 && AHEAD < TSLOTS, "a tile slot must outlive the AHEAD tiles between its two phases");
+    static_assert(EARLY || AHEAD < STAGES, "without early release the data must stay in the ring until phase 2");
     constexpr int SLICE = TILE / CWARPS;  // bytes of a tile owned by one consumer warp
     static_assert(SLICE % 512 == 0, "a warp slice is a whole number of 512-byte rows");
     char* stages = smem;
     Ctl* ctl = reinterpret_cast<Ctl*>(smem + (size_t)STAGES * TILE);
+    char* aux = smem + (size_t)STAGES * TILE + ((sizeof(Ctl) + 127) & ~(size_t)127);
     const int warp = warp_id(), lane = lane_id();
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; s++) {
             mbar_init(&ctl->full[s], 1);
             mbar_init(&ctl->empty[s], CWARPS);
-            mbar_init(&ctl->agg[s], CWARPS);
-            mbar_init(&ctl->pub[s], 1);
-            mbar_init(&ctl->pref[s], 1);
+        }
+        for (int q = 0; q < TSLOTS; q++) {
+            mbar_init(&ctl->agg[q], CWARPS);
+            mbar_init(&ctl->pub[q], 1);
+            mbar_init(&ctl->pref[q], 1);
         }
     }
     __syncthreads();
 
     if (warp == 0) {
-        // ---------------- producer: ticket -> TMA bulk copy of the tile into the next stage
+        // ---------------- producer: ticket -> TMA bulk copy of the tile into the next stage.
+        // The ticket atomic is an L2 round trip (~0.5 us loaded); drawn one at a time it caps the
+        // CTA at one tile per round trip (measured: 0.66 us fixed cost per tile).  TICKETS draws
+        // are therefore kept in flight: the value consumed now was requested TICKETS tiles ago.
+        constexpr int TICKETS = 1;
+        const uint32_t last_draw = n_tiles + gridDim.x * TICKETS - 1;  // every CTA draws its tiles + TICKETS
+        uint32_t tq[TICKETS];
+#pragma unroll
+        for (int i = 0; i < TICKETS; i++) tq[i] = lane == 0 ? atomicAdd(lb.ticket, 1u) : 0u;
         for (uint32_t it = 0;; it++) {
             const int s = it % STAGES;
             const uint32_t use = it / STAGES;
-            // draw the ticket first: the atomic's round trip overlaps the wait for the stage
-            uint32_t t = 0;
-            if (lane == 0) {
-                t = atomicAdd(lb.ticket, 1u);
-                // n_tiles real tickets + one terminating ticket per CTA are drawn per launch
-                if (t == n_tiles + gridDim.x - 1) *lb.ticket = 0;
-            }
+            uint32_t t = tq[0];
+#pragma unroll
+            for (int i = 0; i + 1 < TICKETS; i++) tq[i] = tq[i + 1];
+            if (lane == 0 && t == last_draw) *lb.ticket = 0;  // the very last draw re-arms the counter
             if (use > 0) mbar_wait(&ctl->empty[s], (use - 1) & 1);
             t = __shfl_sync(0xffffffffu, t, 0);
             if (t >= n_tiles) {
                 if (lane == 0) {
-                    ctl->tile[s] = RING_END;
+#pragma unroll
+                    for (int i = 0; i + 1 < TICKETS; i++)
+                        if (tq[i] == last_draw) *lb.ticket = 0;
+                    ctl->stile[s] = RING_END;
                     mbar_arrive(&ctl->full[s]);
                 }
                 break;
             }
+            tq[TICKETS - 1] = lane == 0 ? atomicAdd(lb.ticket, 1u) : 0u;
             char* dst = stages + (size_t)s * TILE;
             const size_t off = (size_t)t * TILE;
             const size_t left = n_bytes - off;
@@ -173,7 +197,7 @@ __device__ __forceinline__ void ring_pipeline(const char* __restrict__ src, size
                 __syncwarp();
             }
             if (lane == 0) {
-                ctl->tile[s] = t;
+                ctl->stile[s] = t;
                 if (bulk) {
                     mbar_expect_tx(&ctl->full[s], bulk);
                     tma_load_1d(dst, src + off, bulk, &ctl->full[s]);
@@ -185,94 +209,122 @@ __device__ __forceinline__ void ring_pipeline(const char* __restrict__ src, size
     } else if (warp == 1) {
         // ---------------- publisher warp: warp totals -> tile aggregate, published at once.
         // It never waits on another CTA, so aggregates appear AHEAD tiles before they are needed.
-        for (uint32_t it = 0;; it++) {
-            const int s = it % STAGES;
-            const uint32_t par = (it / STAGES) & 1;
-            mbar_wait(&ctl->full[s], par);
-            const uint32_t t = ctl->tile[s];
-            if (t == RING_END) break;
-            mbar_wait(&ctl->agg[s], par);
-            P w = lane < CWARPS ? ctl->wsum[s][lane] : (P)0;
+        int q = 0;
+        uint32_t par = 0;
+        for (;;) {
+            mbar_wait(&ctl->agg[q], par);
+            const uint32_t t = ctl->ttile[q][0];
+            if (t == RING_END) {
+                if (lane == 0) mbar_arrive(&ctl->pub[q]);
+                break;
+            }
+            P w = lane < CWARPS ? ctl->wsum[q][lane] : (P)0;
             P inc = warp_inclusive_sum(w);
             const P aggregate = shfl_idx(inc, 31);
             if (lane == 0) {
                 tile_publish<P>(lb, t, TILE_AGGREGATE, aggregate);
-                ctl->tagg[s] = aggregate;
+                ctl->tagg[q] = aggregate;
             }
-            if (lane < CWARPS) ctl->woff[s][lane] = (P)(inc - w);
+            if (lane < CWARPS) ctl->woff[q][lane] = (P)(inc - w);
             __syncwarp();
-            if (lane == 0) mbar_arrive(&ctl->pub[s]);
+            if (lane == 0) mbar_arrive(&ctl->pub[q]);
+            if (++q == TSLOTS) { q = 0; par ^= 1; }
         }
-    } else if (warp < 2 + PWARPS) {
-        // ---------------- prefix warps: published aggregates -> exclusive prefix of the tile.
-        // One sweep costs an L2 round trip (~1 us loaded); when a tile's HBM time is shorter
-        // than that (compress: 1 byte per element), PWARPS warps take the tiles in turn.
-        P rounds_total = seed;     // sum of all complete rounds before `next_round`
+    } else if (warp == 2) {
+        // ---------------- prefix warp: published aggregates -> exclusive prefix of the tile.
+        // Tiles are grouped in rounds of G consecutive tickets: prefix(t) = (sum of all complete
+        // rounds before t's round, kept in a register) + (aggregates of the tiles before t in its
+        // round).  [next_round*G, k*G) — rounds completed since this CTA's previous tile — and
+        // [k*G, t) are contiguous, so one sweep (one L2 round trip for up to 256 status words)
+        // serves both.  Variants measured and dropped (profiles/r01_ring_sweeps.txt): summing only
+        // the tickets between this CTA's consecutive tiles (f32 scan 10 % slower), two sweeps in
+        // flight (every prefix arrives a tile period later: scan 12 % slower).
+        P rounds_total = seed;
         uint32_t next_round = 0;
-        for (uint32_t it = 0;; it++) {
-            const int s = it % STAGES;
-            const uint32_t par = (it / STAGES) & 1;
-            mbar_wait(&ctl->full[s], par);
-            const uint32_t t = ctl->tile[s];
+        int q = 0, sd = 0;     // tile slot; data stage of the tile (only tracked without EARLY release)
+        uint32_t par = 0, spar = 0;
+        for (;;) {
+            // Without EARLY release the data stage still names its tile when the prefix warp gets
+            // to it, so the sweep can start as soon as the tile has landed and overlap phase 1 and
+            // the publisher; with EARLY release the ticket is only safe to read after `pub`.
+            uint32_t t;
+            if (!EARLY) {
+                mbar_wait(&ctl->full[sd], spar);
+                t = ctl->stile[sd];
+                if (++sd == STAGES) { sd = 0; spar ^= 1; }
+            } else {
+                mbar_wait(&ctl->pub[q], par);
+                t = ctl->ttile[q][0];
+            }
             if (t == RING_END) break;
-            if (PWARPS > 1 && (int)(it % PWARPS) != warp - 2) continue;
-            // [next_round*G, k*G): rounds completed since this CTA's previous tile; [k*G, t): the
-            // tiles before t in its own round — contiguous, so one sweep (one L2 round trip for
-            // up to 256 status words) serves both
             const uint32_t k = t / G;
-            P full_rounds, partial;
-            ring_sum_ranges<P, (PWARPS > 1 ? 16 : 8)>(lb, next_round * G, k * G, t, &full_rounds, &partial);
+            P full_rounds = (P)0, partial = (P)0;
+            if (!Op::SKIP_PREFIX)  // (ablation hook: measure the pipeline without the status-word sweep)
+                ring_sum_ranges<P, 8>(lb, next_round * G, k * G, t, &full_rounds, &partial);
             rounds_total = (P)(rounds_total + full_rounds);
             next_round = k;
             const P exclusive = (P)(rounds_total + partial);
-            mbar_wait(&ctl->pub[s], par);
+            if (!EARLY) mbar_wait(&ctl->pub[q], par);
             if (lane == 0) {
-                ctl->tpre[s] = exclusive;
-                if (t == n_tiles - 1) Op::finish((P)(exclusive + ctl->tagg[s]), args);
-                mbar_arrive(&ctl->pref[s]);
+                ctl->tpre[q] = exclusive;
+                if (t == n_tiles - 1) Op::finish((P)(exclusive + ctl->tagg[q]), args);
+                mbar_arrive(&ctl->pref[q]);
             }
+            if (++q == TSLOTS) { q = 0; par ^= 1; }
         }
     } else {
         // ---------------- consumers: phase 1 of tile it, phase 2 of tile it - AHEAD
-        const int cw = warp - 2 - PWARPS;
+        const int cw = warp - 3;
         uint32_t n_iter = 0xffffffffu;  // number of real tiles of this CTA, known at RING_END
-        // (stage, parity) of phase 1 and phase 2 advance incrementally: no division by STAGES
-        int s1 = 0, s2 = 0;
-        uint32_t par1 = 0, par2 = 0;
+        // (stage / slot, parity) advance incrementally: no division by STAGES
+        int s1 = 0, s2 = 0, q1 = 0, q2 = 0;
+        uint32_t spar1 = 0, qpar2 = 0;
         for (uint32_t it = 0;; it++) {
             if (n_iter == 0xffffffffu) {
-                mbar_wait_parked(&ctl->full[s1], par1);
-                if (ctl->tile[s1] == RING_END) {
+                mbar_wait(&ctl->full[s1], spar1);
+                const uint32_t t = ctl->stile[s1];
+                P total = (P)0;
+                if (t == RING_END) {
                     n_iter = it;
                 } else {
-                    const P total = Op::total(stages + (size_t)s1 * TILE + (size_t)cw * SLICE, lane);
-                    if (lane == 0) {
-                        ctl->wsum[s1][cw] = total;
-                        mbar_arrive(&ctl->agg[s1]);
+                    total = Op::total(stages + (size_t)s1 * TILE + (size_t)cw * SLICE, aux, q1, cw, lane);
+                    if (EARLY) {
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&ctl->empty[s1]);
                     }
                 }
-                if (++s1 == STAGES) { s1 = 0; par1 ^= 1; }
+                // every warp arrives (also at RING_END, so the control warps wake up and stop)
+                if (lane == 0) {
+                    ctl->ttile[q1][cw] = t;
+                    ctl->wsum[q1][cw] = total;
+                    mbar_arrive(&ctl->agg[q1]);
+                }
+                if (++s1 == STAGES) { s1 = 0; spar1 ^= 1; }
+                if (++q1 == TSLOTS) q1 = 0;
             }
             if (it >= (uint32_t)AHEAD) {
                 if (it - AHEAD >= n_iter) break;
-                mbar_wait_parked(&ctl->pref[s2], par2);
-                const uint32_t t = ctl->tile[s2];
+                mbar_wait(&ctl->pref[q2], qpar2);
+                const uint32_t t = ctl->ttile[q2][cw];
                 const size_t byte_off = (size_t)t * TILE + (size_t)cw * SLICE;
                 const size_t valid = byte_off < n_bytes ? n_bytes - byte_off : 0;
-                Op::emit(stages + (size_t)s2 * TILE + (size_t)cw * SLICE, byte_off,
+                Op::emit(stages + (size_t)s2 * TILE + (size_t)cw * SLICE, aux, q2, byte_off,
                          valid < (size_t)SLICE ? (uint32_t)valid : (uint32_t)SLICE,
-                         (P)(ctl->tpre[s2] + ctl->woff[s2][cw]), lane, cw, args);
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&ctl->empty[s2]);
-                if (++s2 == STAGES) { s2 = 0; par2 ^= 1; }
+                         (P)(ctl->tpre[q2] + ctl->woff[q2][cw]), lane, cw, args);
+                if (!EARLY) {
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&ctl->empty[s2]);
+                }
+                if (++s2 == STAGES) s2 = 0;
+                if (++q2 == TSLOTS) { q2 = 0; qpar2 ^= 1; }
             }
         }
     }
 }
 
-template <typename P, int TILE, int STAGES, int CWARPS>
-constexpr size_t ring_smem_bytes() {
-    return (size_t)STAGES * TILE + sizeof(RingCtl<P, STAGES, CWARPS>);
+template <typename P, int TILE, int STAGES, int CWARPS, int TSLOTS = STAGES>
+constexpr size_t ring_smem_bytes(size_t aux_bytes = 0) {
+    return (size_t)STAGES * TILE + ((sizeof(RingCtl<P, STAGES, TSLOTS, CWARPS>) + 127) & ~(size_t)127) + aux_bytes;
 }
 
 }  // namespace hj

@@ -209,13 +209,14 @@ scan_kernel(const T* __restrict__ src, T* __restrict__ dst, size_t n, const T* _
 template <typename T, typename P_, bool INCLUSIVE, int SLICE>
 struct ScanOp {
     using P = P_;
+    static constexpr bool SKIP_PREFIX = false;
     static constexpr int VEC = 16 / sizeof(T);
     static constexpr int ROWS = SLICE / 512;
     struct Args {
         T* dst;
     };
     // phase 1: total of this warp's slice (the stage tail of a ragged tile is zero-filled)
-    static __device__ __forceinline__ P total(const char* slice, int lane) {
+    static __device__ __forceinline__ P total(const char* slice, char*, int, int, int lane) {
         P acc = (P)0;
 #pragma unroll
         for (int r = 0; r < ROWS; r++) {
@@ -229,7 +230,7 @@ struct ScanOp {
         return acc;
     }
     // phase 2: scan the slice row by row with a running carry and stream the result out
-    static __device__ __forceinline__ void emit(const char* slice, size_t byte_off, uint32_t valid, P carry,
+    static __device__ __forceinline__ void emit(const char* slice, char*, int, size_t byte_off, uint32_t valid, P carry,
                                                 int lane, int, const Args& a) {
         char* out_base = reinterpret_cast<char*>(a.dst) + byte_off;
 #pragma unroll
