@@ -125,7 +125,7 @@ struct RingCtl {
 //   static void finish(total, args)           called once by the CTA that owns the last tile
 // TILE bytes per stage, STAGES data stages, TSLOTS tile slots, CWARPS consumer warps; phase 1 runs
 // AHEAD tiles ahead of phase 2.
-template <class Op, int TILE, int STAGES, int CWARPS, int AHEAD, int TSLOTS = STAGES, bool EARLY = false>
+template <class Op, int TILE, int STAGES, int CWARPS, int AHEAD, int TSLOTS = STAGES, bool EARLY = false, int SWEEP_M = 8>
 __device__ __forceinline__ void ring_pipeline(const char* __restrict__ src, size_t n_bytes, uint32_t n_tiles,
                                               typename Op::P seed, LookbackView lb, uint32_t G,
                                               const typename Op::Args& args, char* smem) {
@@ -260,7 +260,7 @@ __device__ __forceinline__ void ring_pipeline(const char* __restrict__ src, size
             const uint32_t k = t / G;
             P full_rounds = (P)0, partial = (P)0;
             if (!Op::SKIP_PREFIX)  // (ablation hook: measure the pipeline without the status-word sweep)
-                ring_sum_ranges<P, 8>(lb, next_round * G, k * G, t, &full_rounds, &partial);
+                ring_sum_ranges<P, SWEEP_M>(lb, next_round * G, k * G, t, &full_rounds, &partial);
             rounds_total = (P)(rounds_total + full_rounds);
             next_round = k;
             const P exclusive = (P)(rounds_total + partial);

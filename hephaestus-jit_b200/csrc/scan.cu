@@ -271,7 +271,7 @@ scan_ring_kernel(const T* __restrict__ src, T* __restrict__ dst, size_t n, const
     extern __shared__ __align__(128) char smem[];
     using Op = ScanOp<T, P, INCLUSIVE, TILE / CWARPS>;
     typename Op::Args args{dst};
-    ring_pipeline<Op, TILE, STAGES, CWARPS, AHEAD>(reinterpret_cast<const char*>(src), n * sizeof(T), n_tiles,
+    ring_pipeline<Op, TILE, STAGES, CWARPS, AHEAD, STAGES, false, 10>(reinterpret_cast<const char*>(src), n * sizeof(T), n_tiles,
                                                    seed ? (P)seed[0] : (P)0, lb, G, args, smem);
 }
 
