@@ -229,27 +229,34 @@ hist_ring_kernel(const uint32_t* __restrict__ keys, size_t n, uint32_t literal, 
     }
 }
 
-// dst[b] += sum over groups of their private counter (u32, or u16 pairs packed in u32 words)
+// dst[b] += sum over groups of their private counter (u32, or u16 pairs packed in u32 words).
+// The groups are split over gridDim.y so that enough loads are in flight to stream the scratch
+// (148 x 128 KiB) at HBM speed; each slice adds its partial sum with one global atomic per bin.
+constexpr int HF_SLICES = 8;
 template <bool PACKED16>
 __global__ void __launch_bounds__(256)
 hist_fold_kernel(const uint32_t* __restrict__ scratch, uint32_t n_groups, uint32_t* __restrict__ dst, uint32_t n_dst) {
     const uint32_t i = blockIdx.x * 256 + threadIdx.x;
+    const uint32_t per = (n_groups + gridDim.y - 1) / gridDim.y;
+    const uint32_t g0 = blockIdx.y * per, g1 = min(n_groups, g0 + per);
     if (PACKED16) {
         const uint32_t n_words = (n_dst + 1) / 2;
         if (i >= n_words) return;
         uint32_t even = 0, odd = 0;
-        for (uint32_t g = 0; g < n_groups; g++) {
-            const uint32_t w = scratch[(size_t)g * n_words + i];
+#pragma unroll 4
+        for (uint32_t g = g0; g < g1; g++) {
+            const uint32_t w = __ldg(scratch + (size_t)g * n_words + i);
             even += w & 0xffffu;
             odd += w >> 16;
         }
-        if (even) dst[2 * i] += even;
-        if (odd && 2 * i + 1 < n_dst) dst[2 * i + 1] += odd;
+        if (even) atomicAdd(dst + 2 * i, even);
+        if (odd && 2 * i + 1 < n_dst) atomicAdd(dst + 2 * i + 1, odd);
     } else {
         if (i >= n_dst) return;
         uint32_t acc = 0;
-        for (uint32_t g = 0; g < n_groups; g++) acc += scratch[(size_t)g * n_dst + i];
-        if (acc) dst[i] += acc;
+#pragma unroll 4
+        for (uint32_t g = g0; g < g1; g++) acc += __ldg(scratch + (size_t)g * n_dst + i);
+        if (acc) atomicAdd(dst + i, acc);
     }
 }
 
@@ -321,7 +328,7 @@ hj_status launch_scatter_reduce(hj_device* dev, hj_reduce_op op, hj_type_kind ty
                 kern<<<n_groups, (HR_WARPS + 1) * 32, smem, dev->stream>>>(
                     idx, n, 1u, dev->hist_scratch, (uint32_t*)dst, (uint32_t)n_dst, (uint32_t)n_dst, 1u);
                 HJ_TRY(check_launch(dev, "hist_ring_kernel"));
-                hist_fold_kernel<true><<<(n_words + 255) / 256, 256, 0, dev->stream>>>(
+                hist_fold_kernel<true><<<dim3((n_words + 255) / 256, HF_SLICES), 256, 0, dev->stream>>>(
                     (const uint32_t*)dev->hist_scratch, n_groups, (uint32_t*)dst, (uint32_t)n_dst);
                 return check_launch(dev, "hist_fold_kernel");
             }
@@ -335,7 +342,7 @@ hj_status launch_scatter_reduce(hj_device* dev, hj_reduce_op op, hj_type_kind ty
             kern<<<n_groups * parts, (HR_WARPS + 1) * 32, smem, dev->stream>>>(
                 idx, n, (uint32_t)literal, dev->hist_scratch, (uint32_t*)dst, (uint32_t)n_dst, bins_per_part, parts);
             HJ_TRY(check_launch(dev, "hist_ring_kernel"));
-            hist_fold_kernel<false><<<(unsigned)((n_dst + 255) / 256), 256, 0, dev->stream>>>(
+            hist_fold_kernel<false><<<dim3((unsigned)((n_dst + 255) / 256), HF_SLICES), 256, 0, dev->stream>>>(
                 (const uint32_t*)dev->hist_scratch, n_groups, (uint32_t*)dst, (uint32_t)n_dst);
             return check_launch(dev, "hist_fold_kernel");
         }
