@@ -15,16 +15,27 @@
 // NCCL is loaded with dlopen at first use (libnccl.so.2: the copy torch already mapped when
 // running under torchrun, else the system one), so libhj_b200.so itself has no NCCL dependency.
 #include <dlfcn.h>
+
+#include <cstdlib>
+#include <vector>
 #include <nccl.h>
 
 #include "common.cuh"
 #include "hj_internal.h"
+
+constexpr int HJ_MAX_PEERS = 16;
 
 struct hj_comm {
     hj_device* dev = nullptr;
     ncclComm_t comm = nullptr;
     int rank = 0, world = 1;
     void* scratch = nullptr;  // [0,64): local scalar | [64, 64+8*world): gathered | then: seed / sum
+    // peer-memory exchange (NVLink / NVSwitch): every rank's mailbox is mapped into every process
+    // through CUDA IPC, so `world` scalars are all-gathered by direct remote stores + local polling
+    void* mailbox = nullptr;              // own: 2 parities x world slots x 16 bytes
+    void* peer_mailbox[HJ_MAX_PEERS] = {};  // [rank] = own mailbox, others IPC-mapped
+    bool p2p = false;
+    uint32_t xepoch = 0;
 };
 
 namespace hj {
@@ -126,10 +137,103 @@ char* local_slot(hj_comm* c) { return reinterpret_cast<char*>(c->scratch); }
 char* gathered_slot(hj_comm* c) { return reinterpret_cast<char*>(c->scratch) + 64; }
 char* extra_slot(hj_comm* c) { return reinterpret_cast<char*>(c->scratch) + 64 + 8 * (size_t)c->world; }
 
+// ---- all-gather of one scalar per rank over peer memory ------------------------------------------
+// Payloads on this path are one scalar per GPU, so the exchange is pure latency: an NCCL
+// all-gather costs ~30-40 us per call on 8 GPUs (measured, profiles/r01_sharded.txt), more than the
+// whole local reduction of a 2^27-element shard.  Instead every rank STORES its value straight
+// into the mailbox of every peer (one 16-byte slot per source rank, mapped with CUDA IPC, the
+// stores travel over NVLink / NVSwitch) and then polls its OWN mailbox until all `world` slots
+// carry the current epoch.  A slot is two self-describing words, (low half | epoch) and
+// (high half | epoch), so no ordering between the two stores is needed.  Two mailbox parities
+// alternate: a rank can only be one exchange ahead of a peer (it needs the peer's value of the
+// current exchange to finish it), so the slot it overwrites next is never one still being read.
+struct PeerView {
+    unsigned long long* box[HJ_MAX_PEERS];
+    int rank, world;
+};
+__device__ __forceinline__ void st_sys_u64(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_sys_u64(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__global__ void __launch_bounds__(32)
+peer_allgather_kernel(PeerView pv, uint32_t epoch, const void* __restrict__ local, int es, void* __restrict__ gathered) {
+    const int lane = threadIdx.x;
+    if (lane >= pv.world) return;
+    unsigned long long bits = 0;
+    memcpy(&bits, local, es);  // es in {1, 2, 4, 8}
+    const size_t parity_off = (size_t)(epoch & 1u) * pv.world * 2;
+    unsigned long long* remote = pv.box[lane] + parity_off + (size_t)pv.rank * 2;
+    st_sys_u64(remote, (bits << 32) | epoch);
+    st_sys_u64(remote + 1, (bits & 0xffffffff00000000ull) | epoch);
+    const unsigned long long* mine = pv.box[pv.rank] + parity_off + (size_t)lane * 2;
+    unsigned long long w0, w1;
+    unsigned ns = 20;
+    while (true) {
+        w0 = ld_sys_u64(mine);
+        w1 = ld_sys_u64(mine + 1);
+        if ((uint32_t)w0 == epoch && (uint32_t)w1 == epoch) break;
+        __nanosleep(ns);
+        if (ns < 1000) ns *= 2;
+    }
+    const unsigned long long v = (w0 >> 32) | (w1 & 0xffffffff00000000ull);
+    memcpy(reinterpret_cast<char*>(gathered) + (size_t)lane * es, &v, es);
+}
+
 // all-gather one element of `es` bytes per rank: local_slot -> gathered_slot
 hj_status gather_scalars(hj_comm* c, size_t es) {
+    if (c->p2p) {
+        PeerView pv;
+        for (int i = 0; i < c->world; i++) pv.box[i] = reinterpret_cast<unsigned long long*>(c->peer_mailbox[i]);
+        pv.rank = c->rank;
+        pv.world = c->world;
+        if (++c->xepoch == 0) c->xepoch = 1;  // 0 is what a cleared mailbox holds
+        peer_allgather_kernel<<<1, 32, 0, c->dev->stream>>>(pv, c->xepoch, local_slot(c), (int)es, gathered_slot(c));
+        return check_launch(c->dev, "peer_allgather_kernel");
+    }
     HJ_NCCL(nccl().AllGather(local_slot(c), gathered_slot(c), es, ncclUint8, c->comm, c->dev->stream));
     return HJ_OK;
+}
+
+// Map every rank's mailbox into this process (CUDA IPC handles all-gathered once over NCCL).
+// Any failure leaves c->p2p false and the NCCL path in use.
+void setup_peer_mailboxes(hj_comm* c) {
+    if (c->world < 2 || c->world > HJ_MAX_PEERS || getenv("HJ_NO_P2P")) return;
+    const size_t box_bytes = 2 * (size_t)HJ_MAX_PEERS * 16;
+    if (cudaMalloc(&c->mailbox, box_bytes) != cudaSuccess) { cudaGetLastError(); c->mailbox = nullptr; return; }
+    cudaMemsetAsync(c->mailbox, 0, box_bytes, c->dev->stream);  // ordered before the handle exchange below
+    cudaIpcMemHandle_t mine;
+    if (cudaIpcGetMemHandle(&mine, c->mailbox) != cudaSuccess) { cudaGetLastError(); return; }
+    void* d_handles = nullptr;
+    const size_t hs = sizeof(cudaIpcMemHandle_t);
+    if (cudaMalloc(&d_handles, hs * (c->world + 1)) != cudaSuccess) { cudaGetLastError(); return; }
+    char* send = reinterpret_cast<char*>(d_handles) + hs * c->world;
+    cudaMemcpyAsync(send, &mine, hs, cudaMemcpyHostToDevice, c->dev->stream);
+    bool ok = nccl().AllGather(send, d_handles, hs, ncclUint8, c->comm, c->dev->stream) == ncclSuccess;
+    std::vector<cudaIpcMemHandle_t> all(c->world);
+    ok = ok && cudaMemcpyAsync(all.data(), d_handles, hs * c->world, cudaMemcpyDeviceToHost, c->dev->stream) == cudaSuccess;
+    ok = ok && cudaStreamSynchronize(c->dev->stream) == cudaSuccess;
+    cudaFree(d_handles);
+    for (int r = 0; ok && r < c->world; r++) {
+        if (r == c->rank) { c->peer_mailbox[r] = c->mailbox; continue; }
+        if (cudaIpcOpenMemHandle(&c->peer_mailbox[r], all[r], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+            cudaGetLastError();
+            ok = false;
+        }
+    }
+    // every rank must agree, or some would wait on mailboxes nobody writes: all-reduce the verdict
+    int* d_ok = nullptr;
+    if (cudaMalloc(&d_ok, sizeof(int)) != cudaSuccess) { cudaGetLastError(); return; }
+    int h_ok = ok ? 1 : 0;
+    cudaMemcpyAsync(d_ok, &h_ok, sizeof(int), cudaMemcpyHostToDevice, c->dev->stream);
+    bool agreed = nccl().AllReduce(d_ok, d_ok, 1, ncclInt32, ncclMin, c->comm, c->dev->stream) == ncclSuccess;
+    cudaMemcpyAsync(&h_ok, d_ok, sizeof(int), cudaMemcpyDeviceToHost, c->dev->stream);
+    cudaStreamSynchronize(c->dev->stream);
+    cudaFree(d_ok);
+    c->p2p = agreed && h_ok == 1;
 }
 
 }  // namespace
@@ -173,6 +277,7 @@ hj_status hj_comm_create(hj_device* dev, const uint8_t id[HJ_UNIQUE_ID_BYTES], i
         return fail(HJ_ERR_CUDA, "cudaMalloc failed: %s", cudaGetErrorString(e));
     }
     cudaMemsetAsync(c->scratch, 0, 64 + 8 * (size_t)world + 64, dev->stream);
+    setup_peer_mailboxes(c);
     dev->rc.fetch_add(1);
     *out = c;
     return HJ_OK;
@@ -183,7 +288,10 @@ hj_status hj_comm_destroy(hj_comm* c) {
     {
         DeviceGuard g(c->dev);
         cudaStreamSynchronize(c->dev->stream);
+        for (int r = 0; r < c->world && r < HJ_MAX_PEERS; r++)
+            if (r != c->rank && c->peer_mailbox[r]) cudaIpcCloseMemHandle(c->peer_mailbox[r]);
         if (c->comm) nccl().CommDestroy(c->comm);
+        if (c->mailbox) cudaFree(c->mailbox);
         if (c->scratch) cudaFree(c->scratch);
     }
     c->dev->rc.fetch_sub(1);
