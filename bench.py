@@ -228,6 +228,50 @@ def run_suite(torch, hj, dev, peak, world, rank, comm):
     ms = timed_events(torch, lambda: dev.scatter_reduce(hj.SUM, hj.U32, n28, bk, None, 1, bh, 1 << 16), iters, 3)
     out["C5 histogram 2^28 keys -> 2^16 bins"] = entry(4 * n28, ms, {"elements_per_s": n28 / ms * 1e3, "bytes_per_elem": 4,
                                                                       "bound": "shared-memory atomic throughput, not HBM"})
+    # C5b: gather (12 B/elem nominal: u32 index + f32 value + f32 out) and the traced Monte-Carlo loop
+    del keys, hist
+    idx = torch.randint(0, 1 << 20, (n28,), device="cuda", generator=g, dtype=torch.int32)
+    outf = torch.empty(n28, device="cuda", dtype=torch.float32)
+    bi, bof = wrap(idx), wrap(outf)
+    for log_t in (20, 28):
+        table = torch.rand(1 << log_t, device="cuda", generator=g, dtype=torch.float32)
+        if log_t == 28:
+            idx = torch.randint(0, 1 << 28, (n28,), device="cuda", generator=g, dtype=torch.int32)
+            bi = wrap(idx)
+        bt = wrap(table)
+        ms = timed_events(torch, lambda: dev.gather(4, n28, bt, bi, bof), iters, 3)
+        out[f"C5 gather f32 2^28 indices, table 2^{log_t}"] = entry(12 * n28, ms, {
+            "elements_per_s": n28 / ms * 1e3, "bytes_per_elem": 12,
+            "bound": "L2-resident table: HBM streams of idx/out" if log_t == 20 else "DRAM sectors: 32 B fetched per 4 B used"})
+        del table
+    del idx, outf
+    if world == 1:
+        tr = importlib.import_module("hephaestus-jit_b200.tr")
+        n_l, k_it, log_t = 1 << 24, 16, 20
+        table = tr.from_buffer(wrap(torch.rand(1 << log_t, device="cuda", generator=g, dtype=torch.float32)), hj.F32, 1 << log_t)
+
+        def mc_graph():
+            s0 = tr.sized_index(n_l).mul(tr.literal(2654435761, hj.U32)).add(tr.literal(12345, hj.U32))
+            acc0, it0, c0 = tr.sized_literal(0.0, n_l, hj.F32), tr.sized_literal(0, n_l, hj.U32), tr.literal(True)
+
+            def body(c, vs):
+                s_, acc, it = vs
+                s_ = s_.mul(tr.literal(1664525, hj.U32)).add(tr.literal(1013904223, hj.U32))
+                acc = acc.add(table.gather(s_.shr(tr.literal(32 - log_t, hj.U32))))
+                it = it.add(tr.literal(1, hj.U32))
+                return c.and_(it.lt(tr.literal(k_it, hj.U32))), [s_, acc, it]
+
+            c1, (s1, acc1, it1) = tr.loop_record(c0, [s0, acc0, it0], body)
+            total = acc1.reduce_sum()
+            total.schedule()
+            return tr.compile(), total
+
+        graph, total = mc_graph()
+        ms = timed_events(torch, lambda: graph.launch(dev), 5, 2)
+        out["C5 traced Monte-Carlo loop: 2^24 lanes x 16 gathers (table 2^20) + reduce_sum"] = {
+            "ms": round(ms, 4), "lanes_per_s": n_l / ms * 1e3, "gathers_per_s": n_l * k_it / ms * 1e3,
+            "passes": graph.n_passes(), "sum": float(total.item())}
+        del graph, total, table
     if world > 1:
         out["_note"] = f"per-GPU share (1/{world}) of each array, local kernels only; collectives reported under 'sharded'"
     return out

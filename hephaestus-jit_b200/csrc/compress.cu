@@ -181,13 +181,13 @@ struct CompressOp {
     };
     // aux layout (shared memory behind the ring): TSLOTS mask planes of TILE/8 bytes (one u16 per
     // 16 mask bytes), then one 1 KiB index stage per consumer warp.  Phase 1 leaves only the masks
-    // behind, so the 28 KiB data stage goes straight back to the producer (EARLY release).
+    // behind, so the data stage goes straight back to the producer (EARLY release).
+    static __device__ __forceinline__ uint16_t* stage_of(char* aux, int cw) {
+        return reinterpret_cast<uint16_t*>(aux + TSLOTS * MASK_PLANE + cw * 1024);
+    }
     static constexpr int MASK_PLANE = TILE / 8;
     static __device__ __forceinline__ uint16_t* masks_of(char* aux, int slot, int cw) {
         return reinterpret_cast<uint16_t*>(aux + slot * MASK_PLANE + cw * (SLICE / 8));
-    }
-    static __device__ __forceinline__ uint16_t* stage_of(char* aux, int cw) {
-        return reinterpret_cast<uint16_t*>(aux + TSLOTS * MASK_PLANE + cw * 1024);
     }
     static __device__ __forceinline__ P total(const char* slice, char* aux, int slot, int cw, int lane) {
         if (NO_PHASE1) return 0;
@@ -205,61 +205,70 @@ struct CompressOp {
     // One 512-element row: lane `lane` owns bits `b` (elements lane*16 ..), its first selected
     // element has rank `k` in the row.  Selected positions are staged as u16 row offsets, then
     // written as base + offset with 128-bit stores once the output address is 16-byte aligned.
-    static __device__ __forceinline__ void emit_row(uint16_t* stage, uint32_t b, uint32_t k, uint32_t row_total,
-                                                    uint32_t base, uint32_t* out, int lane) {
-        const uint32_t mine = lane * 16;
-        if (row_total <= 64) {
-            // sparse row: most lanes hold 0 or 1 selected elements, so the k-th stores of all
-            // lanes are nearly contiguous already — write straight to HBM, no staging
+    // One 512-element row whose 32 lane masks sit in shared memory as 16 consecutive 32-bit words:
+    // word j holds elements 32j .. 32j+31 in order (lane L owns elements 16L .. 16L+15, so two
+    // adjacent u16 lane masks ARE one such word).
+    //   sparse row (<= 64 selected): every lane walks its own bits and stores straight to HBM —
+    //     most lanes hold 0 or 1 selected elements, so the k-th stores are nearly contiguous;
+    //   medium row (< 416 selected): compacted through a per-warp u16 stage, see below;
+    //   dense row: 16 steps, one word each.  All lanes read the same word (a broadcast, no bank
+    //     conflicts), lane l owns element 32j + l, its rank inside the word is popc(word & lt_mask)
+    //     and the word's offset in the row comes from one 16-lane scan of the word popcounts.  The
+    //     selected lanes of a step store one CONTIGUOUS run of indices: no staging buffer, no
+    //     divergence, no copy-out pass.  Its cost does not depend on the density, so it only wins
+    //     when most lanes store (measured at 2^28: p = 0.99 297 -> 250 us, but p = 0.5 164 -> 224 us).
+    static __device__ __forceinline__ void emit_row(const uint32_t* words, uint16_t* stage, uint32_t b, uint32_t k,
+                                                    uint32_t row_total, uint32_t base, uint32_t* out, int lane) {
+        if (row_total <= 64 || !DENSE) {
+            const uint32_t mine = base + lane * 16;
             while (b) {
                 const int j = __ffs(b) - 1;
                 b &= b - 1;
-                out[k++] = base + mine + j;
+                out[k++] = mine + j;
             }
             return;
         }
-        if (DENSE) {
-            // dense row: 16 predicated steps, no divergence, no bit scans
+        if (row_total < 416) {
+            // medium density: the word path below would issue 16 half-empty stores per row.
+            // Compact the row through a u16 stage instead (16 predicated steps, no divergence,
+            // no bit scans), then copy out with full 128-byte warp stores.
+            const uint32_t mine = lane * 16;
             uint16_t* p = stage + k;
 #pragma unroll
             for (int j = 0; j < 16; j++) {
                 if (b & (1u << j)) *p++ = (uint16_t)(mine + j);
             }
-        } else {
-            while (b) {
-                const int j = __ffs(b) - 1;
-                b &= b - 1;
-                stage[k++] = (uint16_t)(mine + j);
-            }
-        }
-        __syncwarp();
-        if (!VEC) {
+            __syncwarp();
             for (uint32_t q = lane; q < row_total; q += 32) out[q] = base + stage[q];
             __syncwarp();
             return;
         }
-        // head: scalar stores until `out` is 16-byte aligned; body: 4 indices per store; tail
-        const uint32_t head = min(row_total, (uint32_t)((16u - ((uint32_t)(uintptr_t)out & 15u)) & 15u) >> 2);
-        if ((uint32_t)lane < head) out[lane] = base + stage[lane];
-        const uint32_t body = (row_total - head) >> 2;  // full groups of four
-        for (uint32_t g = lane; g < body; g += 32) {
-            const uint16_t* q = stage + head + 4 * g;
-            uint4 v;
-            v.x = base + q[0]; v.y = base + q[1]; v.z = base + q[2]; v.w = base + q[3];
-            *reinterpret_cast<uint4*>(out + head + 4 * g) = v;
+        const uint32_t wl = lane < 16 ? words[lane] : 0u;
+        const uint32_t pc = __popc(wl);
+        uint32_t inc = pc;
+#pragma unroll
+        for (int d = 1; d < 16; d <<= 1) {
+            const uint32_t o = __shfl_up_sync(0xffffffffu, inc, d);
+            if (lane >= d) inc += o;
         }
-        const uint32_t done = head + 4 * body;
-        if (done + lane < row_total) out[done + lane] = base + stage[done + lane];
-        __syncwarp();
+        const uint32_t ex = inc - pc;  // lanes 0..15: selected elements before word `lane`
+        const uint32_t lt = (1u << lane) - 1u, me = 1u << lane;
+        const uint32_t v0 = base + lane;
+#pragma unroll
+        for (int j = 0; j < 16; j++) {
+            const uint32_t w = words[j];
+            const uint32_t off = __shfl_sync(0xffffffffu, ex, j);
+            if (w & me) out[off + __popc(w & lt)] = v0 + 32 * j;
+        }
     }
     static __device__ __forceinline__ void emit(const char*, char* aux, int slot, size_t byte_off, uint32_t, P carry,
                                                 int lane, int cw, const Args& a) {
         if (NO_PHASE2) return;
         uint32_t bits[ROWS];
-#pragma unroll
         const uint16_t* m = masks_of(aux, slot, cw);
 #pragma unroll
         for (int r = 0; r < ROWS; r++) bits[r] = m[r * 32 + lane];
+        const uint32_t* words = reinterpret_cast<const uint32_t*>(m);  // 16 words per row
         uint16_t* stage = stage_of(aux, cw);
         const uint32_t base = a.index_base + (uint32_t)byte_off;
 #pragma unroll
@@ -270,8 +279,8 @@ struct CompressOp {
             const uint32_t tot = __shfl_sync(0xffffffffu, inc, 31);
             const uint32_t ex = inc - c;
             const uint32_t t0 = tot & 0xffffu, t1 = tot >> 16;
-            if (t0) emit_row(stage, bits[r], ex & 0xffffu, t0, base + r * 512, a.index_out + carry, lane);
-            if (t1) emit_row(stage, bits[r + 1], ex >> 16, t1, base + (r + 1) * 512, a.index_out + carry + t0, lane);
+            if (t0) emit_row(words + r * 16, stage, bits[r], ex & 0xffffu, t0, base + r * 512, a.index_out + carry, lane);
+            if (t1) emit_row(words + (r + 1) * 16, stage, bits[r + 1], ex >> 16, t1, base + (r + 1) * 512, a.index_out + carry + t0, lane);
             carry += t0 + t1;
         }
     }

@@ -267,6 +267,35 @@ gather_kernel(const T* __restrict__ src, const uint32_t* __restrict__ idx, T* __
     for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < n; i += stride) dst[i] = __ldg(src + idx[i]);
 }
 
+// 4-byte elements, 16-byte aligned idx / dst: indices arrive as 128-bit streaming loads, eight
+// independent gathers per thread are in flight, results leave as 128-bit streaming stores.  The
+// table goes through the read-only path (L1 + L2); what bounds the kernel is the L2 sector rate
+// (L2-resident table) or the DRAM sector rate (32 bytes fetched per 4 bytes used).
+__global__ void __launch_bounds__(256)
+gather4_vec_kernel(const uint32_t* __restrict__ src, const uint32_t* __restrict__ idx, uint32_t* __restrict__ dst,
+                   size_t n) {
+    const size_t nvec = n / 4;
+    const uint4* vidx = reinterpret_cast<const uint4*>(idx);
+    uint4* vdst = reinterpret_cast<uint4*>(dst);
+    const size_t stride = (size_t)gridDim.x * 256;
+    size_t v = (size_t)blockIdx.x * 256 + threadIdx.x;
+    for (; v + stride < nvec; v += 2 * stride) {
+        const uint4 a = ld_stream_v4(vidx + v), b = ld_stream_v4(vidx + v + stride);
+        uint4 x, y;
+        x.x = __ldg(src + a.x); x.y = __ldg(src + a.y); x.z = __ldg(src + a.z); x.w = __ldg(src + a.w);
+        y.x = __ldg(src + b.x); y.y = __ldg(src + b.y); y.z = __ldg(src + b.z); y.w = __ldg(src + b.w);
+        st_stream_v4(vdst + v, x);
+        st_stream_v4(vdst + v + stride, y);
+    }
+    for (; v < nvec; v += stride) {
+        const uint4 a = ld_stream_v4(vidx + v);
+        uint4 x;
+        x.x = __ldg(src + a.x); x.y = __ldg(src + a.y); x.z = __ldg(src + a.z); x.w = __ldg(src + a.w);
+        st_stream_v4(vdst + v, x);
+    }
+    for (size_t e = nvec * 4 + (size_t)blockIdx.x * 256 + threadIdx.x; e < n; e += stride) dst[e] = __ldg(src + idx[e]);
+}
+
 template <typename T>
 __global__ void __launch_bounds__(256) fill_kernel(T* __restrict__ dst, size_t n, T v) {
     const size_t stride = (size_t)gridDim.x * 256;
@@ -383,7 +412,12 @@ hj_status launch_gather(hj_device* dev, size_t elem_bytes, size_t n, const void*
     switch (elem_bytes) {
     case 1: gather_kernel<uint8_t><<<grid, 256, 0, dev->stream>>>((const uint8_t*)src, idx, (uint8_t*)dst, n); break;
     case 2: gather_kernel<uint16_t><<<grid, 256, 0, dev->stream>>>((const uint16_t*)src, idx, (uint16_t*)dst, n); break;
-    case 4: gather_kernel<uint32_t><<<grid, 256, 0, dev->stream>>>((const uint32_t*)src, idx, (uint32_t*)dst, n); break;
+    case 4:
+        if ((((uintptr_t)idx | (uintptr_t)dst) & 15u) == 0 && n >= 4096)
+            gather4_vec_kernel<<<std::min<size_t>((n / 8 + 255) / 256, cap), 256, 0, dev->stream>>>((const uint32_t*)src, idx, (uint32_t*)dst, n);
+        else
+            gather_kernel<uint32_t><<<grid, 256, 0, dev->stream>>>((const uint32_t*)src, idx, (uint32_t*)dst, n);
+        break;
     case 8: gather_kernel<uint2><<<grid, 256, 0, dev->stream>>>((const uint2*)src, idx, (uint2*)dst, n); break;
     case 16: gather_kernel<uint4><<<grid, 256, 0, dev->stream>>>((const uint4*)src, idx, (uint4*)dst, n); break;
     default: return fail(HJ_ERR_INVALID, "gather: element size %zu not in {1,2,4,8,16}", elem_bytes);
