@@ -22,8 +22,9 @@
 
 #include "common.cuh"
 #include "hj_internal.h"
+#include "peer.cuh"
 
-constexpr int HJ_MAX_PEERS = 16;
+using hj::HJ_MAX_PEERS;
 
 struct hj_comm {
     hj_device* dev = nullptr;
@@ -147,50 +148,35 @@ char* extra_slot(hj_comm* c) { return reinterpret_cast<char*>(c->scratch) + 64 +
 // (high half | epoch), so no ordering between the two stores is needed.  Two mailbox parities
 // alternate: a rank can only be one exchange ahead of a peer (it needs the peer's value of the
 // current exchange to finish it), so the slot it overwrites next is never one still being read.
-struct PeerView {
-    unsigned long long* box[HJ_MAX_PEERS];
-    int rank, world;
-};
-__device__ __forceinline__ void st_sys_u64(unsigned long long* p, unsigned long long v) {
-    asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
-__device__ __forceinline__ unsigned long long ld_sys_u64(const unsigned long long* p) {
-    unsigned long long v;
-    asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-    return v;
-}
 __global__ void __launch_bounds__(32)
 peer_allgather_kernel(PeerView pv, uint32_t epoch, const void* __restrict__ local, int es, void* __restrict__ gathered) {
     const int lane = threadIdx.x;
     if (lane >= pv.world) return;
     unsigned long long bits = 0;
     memcpy(&bits, local, es);  // es in {1, 2, 4, 8}
-    const size_t parity_off = (size_t)(epoch & 1u) * pv.world * 2;
-    unsigned long long* remote = pv.box[lane] + parity_off + (size_t)pv.rank * 2;
-    st_sys_u64(remote, (bits << 32) | epoch);
-    st_sys_u64(remote + 1, (bits & 0xffffffff00000000ull) | epoch);
-    const unsigned long long* mine = pv.box[pv.rank] + parity_off + (size_t)lane * 2;
-    unsigned long long w0, w1;
-    unsigned ns = 20;
-    while (true) {
-        w0 = ld_sys_u64(mine);
-        w1 = ld_sys_u64(mine + 1);
-        if ((uint32_t)w0 == epoch && (uint32_t)w1 == epoch) break;
-        __nanosleep(ns);
-        if (ns < 1000) ns *= 2;
-    }
-    const unsigned long long v = (w0 >> 32) | (w1 & 0xffffffff00000000ull);
+    const unsigned long long v = peer_exchange(pv, epoch, bits, lane);
     memcpy(reinterpret_cast<char*>(gathered) + (size_t)lane * es, &v, es);
+}
+
+// exchange epochs are 31-bit and never 0 (0 is what a cleared mailbox holds; bit 31 is a mode flag)
+void next_xepoch(hj_comm* c) {
+    c->xepoch = (c->xepoch + 1) & 0x7fffffffu;
+    if (c->xepoch == 0) c->xepoch = 1;
+}
+
+PeerView peer_view(hj_comm* c) {
+    PeerView pv;
+    for (int i = 0; i < HJ_MAX_PEERS; i++) pv.box[i] = reinterpret_cast<unsigned long long*>(c->peer_mailbox[i]);
+    pv.rank = c->rank;
+    pv.world = c->world;
+    return pv;
 }
 
 // all-gather one element of `es` bytes per rank: local_slot -> gathered_slot
 hj_status gather_scalars(hj_comm* c, size_t es) {
     if (c->p2p) {
-        PeerView pv;
-        for (int i = 0; i < c->world; i++) pv.box[i] = reinterpret_cast<unsigned long long*>(c->peer_mailbox[i]);
-        pv.rank = c->rank;
-        pv.world = c->world;
-        if (++c->xepoch == 0) c->xepoch = 1;  // 0 is what a cleared mailbox holds
+        PeerView pv = peer_view(c);
+        next_xepoch(c);
         peer_allgather_kernel<<<1, 32, 0, c->dev->stream>>>(pv, c->xepoch, local_slot(c), (int)es, gathered_slot(c));
         return check_launch(c->dev, "peer_allgather_kernel");
     }
@@ -305,6 +291,13 @@ hj_status hj_sharded_reduce(hj_comm* c, hj_reduce_op op, hj_type_kind ty, size_t
     size_t es = type_size(ty);
     HJ_REQUIRE(es && n_local >= 1 && n_local * es <= src->bytes && es <= dst->bytes, "hj_sharded_reduce: bad sizes");
     DeviceGuard g(c->dev);
+    if (c->p2p && c->world > 1) {
+        // ONE kernel: the CTA that finishes the local reduction sends the partial to every peer's
+        // mailbox over NVLink, collects theirs and folds them in rank order (reduce.cu)
+        PeerView pv = peer_view(c);
+        next_xepoch(c);
+        return launch_reduce(c->dev, op, ty, n_local, src->ptr, dst->ptr, &pv, c->xepoch);
+    }
     // local partial -> all-gather -> fold in rank order with the same reduction kernel
     HJ_TRY(launch_reduce(c->dev, op, ty, n_local, src->ptr, local_slot(c)));
     if (c->world == 1) {
@@ -325,6 +318,13 @@ hj_status hj_sharded_prefix_sum(hj_comm* c, hj_type_kind ty, size_t n_local, int
     if (c->world == 1) return launch_prefix_sum(c->dev, ty, n_local, inclusive != 0, src->ptr, dst->ptr, nullptr);
     // shard total (a read-only pass, sizeof(T) bytes/element) -> all-gather -> exclusive offset
     // of this rank -> scan seeded with the offset.  12 bytes/element in total for 4-byte types.
+    if (c->p2p) {
+        // the totals pass, the exchange over peer memory and the exclusive offset are ONE kernel
+        PeerView pv = peer_view(c);
+        next_xepoch(c);
+        HJ_TRY(launch_reduce(c->dev, HJ_REDUCE_SUM, ty, n_local, src->ptr, extra_slot(c), &pv, c->xepoch | 0x80000000u));
+        return launch_prefix_sum(c->dev, ty, n_local, inclusive != 0, src->ptr, dst->ptr, extra_slot(c));
+    }
     HJ_TRY(launch_reduce(c->dev, HJ_REDUCE_SUM, ty, n_local, src->ptr, local_slot(c)));
     HJ_TRY(gather_scalars(c, es));
     void* seed = extra_slot(c);

@@ -106,8 +106,11 @@ hj_status ensure_lookback_scratch(hj_device* dev, size_t n_tiles);
 hj_status next_epoch(hj_device* dev, uint32_t* out);
 
 // ---- kernel launchers (defined in the .cu files; device lock held by the caller) ---------
+struct PeerView;  // peer.cuh
+// `peers` / `epoch` (optional): fold the result with the partials of the other ranks over peer
+// memory inside the same kernel (sharded reduce, comm.cu)
 hj_status launch_reduce(hj_device* dev, hj_reduce_op op, hj_type_kind ty, size_t n,
-                        const void* src, void* dst);
+                        const void* src, void* dst, const PeerView* peers = nullptr, uint32_t epoch = 0);
 hj_status launch_prefix_sum(hj_device* dev, hj_type_kind ty, size_t n, bool inclusive,
                             const void* src, void* dst, const void* seed);
 hj_status launch_compress(hj_device* dev, size_t n, const uint32_t* size_buf, uint32_t* out_count,
