@@ -166,14 +166,11 @@ __device__ __forceinline__ uint32_t lane_mask16(uint4 v) {
     return gather_lo(v.x) | (gather_lo(v.y) << 4) | (gather_lo(v.z) << 8) | (gather_lo(v.w) << 12);
 }
 
-template <int CFG, int SLICE, int TILE, int TSLOTS>
+template <int SLICE, int TILE, int TSLOTS>
 struct CompressOp {
     using P = uint32_t;
     static constexpr int ROWS = SLICE / 512;  // 512-element rows per warp slice, ranked in pairs
     static_assert(ROWS % 2 == 0, "rows are ranked in pairs");
-    static constexpr bool DENSE = (CFG & 2) != 0, VEC = (CFG & 4) != 0;
-    static constexpr bool NO_PHASE2 = (CFG & 32) != 0, NO_PHASE1 = (CFG & 128) != 0;  // ablation experiments only
-    static constexpr bool SKIP_PREFIX = (CFG & 256) != 0;
     struct Args {
         uint32_t* index_out;
         uint32_t* out_count;
@@ -190,7 +187,6 @@ struct CompressOp {
         return reinterpret_cast<uint16_t*>(aux + slot * MASK_PLANE + cw * (SLICE / 8));
     }
     static __device__ __forceinline__ P total(const char* slice, char* aux, int slot, int cw, int lane) {
-        if (NO_PHASE1) return 0;
         const char* mine = slice + lane * 16;
         uint16_t* m = masks_of(aux, slot, cw);
         uint32_t cnt = 0;
@@ -219,7 +215,7 @@ struct CompressOp {
     //     when most lanes store (measured at 2^28: p = 0.99 297 -> 250 us, but p = 0.5 164 -> 224 us).
     static __device__ __forceinline__ void emit_row(const uint32_t* words, uint16_t* stage, uint32_t b, uint32_t k,
                                                     uint32_t row_total, uint32_t base, uint32_t* out, int lane) {
-        if (row_total <= 64 || !DENSE) {
+        if (row_total <= 64) {
             const uint32_t mine = base + lane * 16;
             while (b) {
                 const int j = __ffs(b) - 1;
@@ -263,7 +259,6 @@ struct CompressOp {
     }
     static __device__ __forceinline__ void emit(const char*, char* aux, int slot, size_t byte_off, uint32_t, P carry,
                                                 int lane, int cw, const Args& a) {
-        if (NO_PHASE2) return;
         uint32_t bits[ROWS];
         const uint16_t* m = masks_of(aux, slot, cw);
 #pragma unroll
@@ -288,7 +283,7 @@ struct CompressOp {
     static __device__ __forceinline__ void finish(P total, const Args& a) { a.out_count[0] = total; }
 };
 
-template <int CFG, int CR_TILE, int CR_STAGES, int CR_TSLOTS, int CR_AHEAD>
+template <int CR_TILE, int CR_STAGES, int CR_TSLOTS, int CR_AHEAD>
 __global__ void __launch_bounds__((CR_WARPS + 3) * 32, 1)
 compress_ring_kernel(const uint8_t* __restrict__ mask, size_t n, const uint32_t* __restrict__ size_buf,
                      uint32_t* __restrict__ out_count, uint32_t* __restrict__ index_out, uint32_t index_base,
@@ -301,7 +296,7 @@ compress_ring_kernel(const uint8_t* __restrict__ mask, size_t n, const uint32_t*
     }
     const uint32_t n_tiles = (uint32_t)((n_eff + CR_TILE - 1) / CR_TILE);
     if (n_tiles == 0 && blockIdx.x == 0 && threadIdx.x == 0) out_count[0] = 0;
-    using Op = CompressOp<CFG, CR_TILE / CR_WARPS, CR_TILE, CR_TSLOTS>;
+    using Op = CompressOp<CR_TILE / CR_WARPS, CR_TILE, CR_TSLOTS>;
     typename Op::Args args{index_out, out_count, index_base};
     ring_pipeline<Op, CR_TILE, CR_STAGES, CR_WARPS, CR_AHEAD, CR_TSLOTS, true>(reinterpret_cast<const char*>(mask), n_eff,
                                                                       n_tiles, 0u, lb, G, args, smem);
@@ -312,11 +307,11 @@ compress_ring_kernel(const uint8_t* __restrict__ mask, size_t n, const uint32_t*
 hj_status launch_compress(hj_device* dev, size_t n, const uint32_t* size_buf, uint32_t* out_count,
                           const uint8_t* mask, uint32_t* index_out, uint32_t index_base) {
     HJ_REQUIRE(n <= 0xffffffffull, "compress: n does not fit the u32 index type");
-    static const int cfg = getenv("HJ_COMPRESS_CFG") ? atoi(getenv("HJ_COMPRESS_CFG")) : 67;  // 0: look-back kernel
+    static const int cfg = getenv("HJ_COMPRESS_CFG") ? atoi(getenv("HJ_COMPRESS_CFG")) : 1;  // 0: look-back kernel, 3: 28 KiB tiles
     if (cfg != 0 && ((uintptr_t)mask & 15u) == 0 && n >= (64u << 10)) {
         // tile geometry: 28 KiB tiles, 5 data stages (all but one in flight), 8 tile slots with
         // phase 1 six tiles ahead of phase 2; or 56 KiB tiles x 3 stages, 4 slots, three ahead
-        const bool big = (cfg & 64) != 0;
+        const bool big = cfg != 3;  // HJ_COMPRESS_CFG=3 selects the 28 KiB geometry
         const size_t tile_bytes = big ? 57344 : 28672;
         const size_t tiles = (n + tile_bytes - 1) / tile_bytes;
         HJ_TRY(ensure_lookback_scratch(dev, tiles));
@@ -332,15 +327,10 @@ hj_status launch_compress(hj_device* dev, size_t n, const uint32_t* size_buf, ui
         };
         const size_t smem_small = ring_smem_bytes<uint32_t, 28672, 5, CR_WARPS, 8>(8 * (28672 / 8) + CR_WARPS * 1024);
         const size_t smem_big = ring_smem_bytes<uint32_t, 57344, 3, CR_WARPS, 4>(4 * (57344 / 8) + CR_WARPS * 1024);
-        switch (cfg) {
-        case 1: HJ_TRY(launch(compress_ring_kernel<1, 28672, 5, 8, 6>, smem_small)); break;
-        case 35: HJ_TRY(launch(compress_ring_kernel<35, 28672, 5, 8, 6>, smem_small)); break;
-        case 163: HJ_TRY(launch(compress_ring_kernel<163, 28672, 5, 8, 6>, smem_small)); break;
-        case 419: HJ_TRY(launch(compress_ring_kernel<419, 28672, 5, 8, 6>, smem_small)); break;
-        case 64 + 35: HJ_TRY(launch(compress_ring_kernel<35, 57344, 3, 4, 3>, smem_big)); break;
-        case 3: HJ_TRY(launch(compress_ring_kernel<3, 28672, 5, 8, 6>, smem_small)); break;
-        default: HJ_TRY(launch(compress_ring_kernel<3, 57344, 3, 4, 3>, smem_big)); break;
-        }
+        // measured on B200 (profiles/r01_ring_sweeps.txt): the 56 KiB geometry wins at low
+        // selectivity (fewer status-word sweeps per byte) and ties elsewhere
+        if (big) HJ_TRY(launch(compress_ring_kernel<57344, 3, 4, 3>, smem_big));
+        else HJ_TRY(launch(compress_ring_kernel<28672, 5, 8, 6>, smem_small));
         return check_launch(dev, "compress_ring_kernel");
     }
     size_t n_tiles = (n + CMP_TILE - 1) / CMP_TILE;

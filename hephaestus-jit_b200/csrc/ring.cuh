@@ -259,8 +259,7 @@ __device__ __forceinline__ void ring_pipeline(const char* __restrict__ src, size
             if (t == RING_END) break;
             const uint32_t k = t / G;
             P full_rounds = (P)0, partial = (P)0;
-            if (!Op::SKIP_PREFIX)  // (ablation hook: measure the pipeline without the status-word sweep)
-                ring_sum_ranges<P, SWEEP_M>(lb, next_round * G, k * G, t, &full_rounds, &partial);
+            ring_sum_ranges<P, SWEEP_M>(lb, next_round * G, k * G, t, &full_rounds, &partial);
             rounds_total = (P)(rounds_total + full_rounds);
             next_round = k;
             const P exclusive = (P)(rounds_total + partial);

@@ -209,7 +209,6 @@ scan_kernel(const T* __restrict__ src, T* __restrict__ dst, size_t n, const T* _
 template <typename T, typename P_, bool INCLUSIVE, int SLICE>
 struct ScanOp {
     using P = P_;
-    static constexpr bool SKIP_PREFIX = false;
     static constexpr int VEC = 16 / sizeof(T);
     static constexpr int ROWS = SLICE / 512;
     struct Args {
