@@ -13,6 +13,10 @@
  * hephaestus-jit/src/backend/vulkan/builtin/).  Pinning: tests/test_oracle_golden.py checks
  * this file against every known-answer vector the reference's own tests hold for the path
  * (hephaestus-jit/src/test.rs:493-1019, transcribed in tests/golden/reference_kats.json).
+ * PARITY UNPINNED where the reference holds no vector: exclusive scans (the
+ * reference's exclusive scan is inclusive), f32 / f64 / u64 scans (D3), reductions
+ * beyond 1000 elements, compress with a non-trivial mask beyond 128 elements, and every float
+ * elementwise op other than cos.  For those this file is the only statement of the contract.
  *
  * Build: see oracle/Makefile  (gcc -O2 -fopenmp -ffp-contract=off, no -march=native so the
  * .so also runs on the GPU box's host CPU; contraction is off so float results do not

@@ -1,0 +1,48 @@
+"""CPU checks of the drop-in boundary: libhj_b200.so loads without a GPU, exports every symbol
+include/hj.h declares, every symbol has a ctypes signature in the host mirror, and the compute entry
+points fail loudly (no CPU fallback) when no CUDA device is present."""
+import ctypes
+import importlib
+
+import numpy as np
+import pytest
+
+hj = importlib.import_module("hephaestus-jit_b200")
+L = importlib.import_module("hephaestus-jit_b200._lib")
+
+
+def test_library_exports_every_declared_symbol():
+    declared = L.declared_symbols()
+    assert len(declared) > 100
+    missing = [s for s in declared if not hasattr(L.lib, s)]
+    assert not missing, f"libhj_b200.so does not export {missing}"
+    unsigned = [s for s in declared if s not in L._SIGS]
+    assert not unsigned, f"no ctypes signature for {unsigned}"
+
+
+def test_abi_version_and_device_count():
+    assert L.lib.hj_abi_version() >= 1
+    assert L.lib.hj_device_count() >= 0
+
+
+def test_no_cpu_fallback_without_a_device():
+    if hj.device_count() > 0:
+        pytest.skip("a GPU is present")
+    with pytest.raises(hj.HjError) as e:
+        hj.Device.cuda(0)
+    assert e.value.status in (L.ERR_NO_DEVICE, L.ERR_CUDA)
+    # null handles are rejected, not dereferenced
+    assert L.lib.hj_reduce(None, 2, 7, 10, None, None) != 0
+    assert L.lib.hj_prefix_sum(None, 7, 10, 1, None, None, None) != 0
+    assert L.lib.hj_execute_graph(None, None, 0, None, None, 0, None) != 0
+    assert L.last_error() != ""
+
+
+def test_ir_codegen_and_cubin_work_without_a_gpu():
+    irm = importlib.import_module("hephaestus-jit_b200.ir")
+    ir = irm.c2_chain_ir().build()
+    src = irm.codegen(ir)
+    assert "hj_kernel_vec" in src and "fmaf" in src and "sinf" in src and "exp2f" in src
+    cubin = irm.compile_cubin(ir)
+    assert cubin[:4] == b"\x7fELF"
+    assert irm.ir_hash(ir) == irm.ir_hash(irm.c2_chain_ir().build())  # stable content hash
