@@ -244,3 +244,34 @@ def test_launch_without_gpu_fails_loudly():
         pytest.skip("a GPU is present")
     with pytest.raises(hj.HjError):
         hj.Device.cuda(0)
+
+
+def test_concurrent_tracing_from_several_threads():
+    """The trace is one process-global table behind a mutex, the schedule is thread-local
+    (trace.rs:71-76): threads tracing at the same time must not see each other's schedules."""
+    import threading
+
+    errors = []
+
+    def worker(seed):
+        try:
+            for rep in range(50):
+                n = 100 + seed * 7 + rep
+                x = tr.sized_index(n).cast(F32)
+                y = x.mul(tr.literal(float(seed + 1), F32)).add(tr.literal(1.0, F32))
+                s = y.reduce_sum()
+                s.schedule()
+                g = tr.compile()
+                text = g.debug_string()
+                assert g.n_passes() == 2, g.n_passes()
+                assert f"size: {n}," in text
+                del x, y, s, g
+        except Exception as e:  # noqa: BLE001
+            errors.append(repr(e))
+
+    threads = [threading.Thread(target=worker, args=(i,)) for i in range(4)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors
