@@ -59,7 +59,7 @@ class Buffer:
 
     def __del__(self):
         h, self._h = getattr(self, "_h", None), None
-        if h:
+        if h and lib is not None:  # module globals are torn down before objects at interpreter exit
             lib.hj_buffer_release(h)
 
     @property
@@ -268,5 +268,5 @@ class Kernel:
 
     def __del__(self):
         h, self._h = getattr(self, "_h", None), None
-        if h:
+        if h and lib is not None:  # module globals are torn down before objects at interpreter exit
             lib.hj_kernel_release(h)

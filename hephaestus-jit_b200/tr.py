@@ -485,7 +485,7 @@ class Graph:
 
     def __del__(self):
         h, self._h = getattr(self, "_h", None), None
-        if h:
+        if h and lib is not None:  # module globals are torn down before objects at interpreter exit
             lib.hj_graph_release(h)
 
     def n_passes(self) -> int:

@@ -1,5 +1,5 @@
 import importlib, os, sys, torch
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, ROOT)
+ROOT = os.environ.get("HJ_ROOT", os.path.dirname(os.path.dirname(os.path.abspath(__file__)))); sys.path.insert(0, ROOT)
 hj = importlib.import_module("hephaestus-jit_b200")
 torch.cuda.set_device(0); dev = hj.Device.cuda(0)
 side = torch.cuda.Stream(); torch.cuda.set_stream(side); dev.set_stream(side.cuda_stream)
