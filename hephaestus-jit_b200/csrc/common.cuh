@@ -3,6 +3,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <type_traits>
+
 namespace hj {
 
 constexpr int WARP = 32;
@@ -85,13 +87,26 @@ __device__ __forceinline__ T shfl_idx(T v, int src) {
 // Inclusive warp scan (sum) with shuffles.
 template <typename T>
 __device__ __forceinline__ T warp_inclusive_sum(T v) {
-    const int lane = lane_id();
+    if constexpr (sizeof(T) == 4 && std::is_integral<T>::value) {
+        // shfl.up hands back "source lane was in range" as a predicate: two instructions per
+        // step instead of shuffle + lane compare + select
+        uint32_t u = (uint32_t)v;
 #pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        T o = shfl_up(v, d);
-        if (lane >= d) v = (T)(v + o);
+        for (int d = 1; d < 32; d <<= 1) {
+            asm("{\n.reg .u32 t;\n.reg .pred p;\nshfl.sync.up.b32 t|p, %0, %1, 0, 0xffffffff;\n@p add.u32 %0, %0, t;\n}"
+                : "+r"(u)
+                : "r"(d));
+        }
+        return (T)u;
+    } else {
+        const int lane = lane_id();
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            T o = shfl_up(v, d);
+            if (lane >= d) v = (T)(v + o);
+        }
+        return v;
     }
-    return v;
 }
 
 

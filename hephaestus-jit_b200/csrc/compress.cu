@@ -152,10 +152,9 @@ constexpr int CR_WARPS = 28;
 
 // 16 mask bytes -> 16-bit lane mask (bit i = byte i is non-zero).
 // Fast path: `bool` buffers only ever hold 0 or 1 (codegen stores bool as u8 0/1,
-// codegen/glsl/mod.rs:256-270), so bit 0 of each byte IS the flag and one multiply-gather per
-// word collects the four flags (all 16 partial products land on distinct bits).  Any other
-// byte value takes the exact "non-zero" path.
-__device__ __forceinline__ uint32_t gather_lo(uint32_t w) { return (w * 0x10204080u) >> 28; }  // bits 0,8,16,24
+// codegen/glsl/mod.rs:256-270), so the four-way byte dot product with (1, 2, 4, 8) IS the 4-bit
+// mask of a word (IDP.4A, 5 instructions per 16 bytes instead of 13 with multiply-gathers).
+// Any other byte value is first normalised to 0/1 (exact "non-zero" test).
 __device__ __forceinline__ uint32_t nonzero_lo(uint32_t w) {
     return ((((w & 0x7f7f7f7fu) + 0x7f7f7f7fu) | w) & 0x80808080u) >> 7;
 }
@@ -163,8 +162,12 @@ __device__ __forceinline__ uint32_t lane_mask16(uint4 v) {
     if (((v.x | v.y | v.z | v.w) & 0xfefefefeu) != 0u) {
         v.x = nonzero_lo(v.x); v.y = nonzero_lo(v.y); v.z = nonzero_lo(v.z); v.w = nonzero_lo(v.w);
     }
-    return gather_lo(v.x) | (gather_lo(v.y) << 4) | (gather_lo(v.z) << 8) | (gather_lo(v.w) << 12);
+    const uint32_t lo = __dp4a(v.y, 0x80402010u, __dp4a(v.x, 0x08040201u, 0u));
+    const uint32_t hi = __dp4a(v.w, 0x80402010u, __dp4a(v.z, 0x08040201u, 0u));
+    return lo + (hi << 8);
 }
+
+unsigned long long* g_compress_trace = nullptr;  // set through hj_debug_compress_trace()
 
 template <int SLICE, int TILE, int TSLOTS>
 struct CompressOp {
@@ -258,9 +261,37 @@ struct CompressOp {
         }
     }
     static __device__ __forceinline__ void emit(const char*, char* aux, int slot, size_t byte_off, uint32_t, P carry,
-                                                int lane, int cw, const Args& a) {
-        uint32_t bits[ROWS];
+                                                P slice_total, int lane, int cw, const Args& a) {
         const uint16_t* m = masks_of(aux, slot, cw);
+        if (slice_total <= 64u * ROWS) {
+            // Sparse slice (p <~ 0.12; the total is the one phase 1 counted).  The mask plane of
+            // the slice IS its bitmap in element order (ROWS * 16 words), so a lane may just as
+            // well own WPL consecutive words: ONE warp scan ranks the whole slice and every lane
+            // walks its own bits straight to HBM — no per-row scans, no staging.  At p = 0.01 this
+            // is 31 M instead of 49 M warp instructions for 2^28 elements.
+            if (slice_total == 0) return;
+            constexpr int WPL = ROWS / 2;
+            uint32_t w[WPL];
+            uint32_t c = 0;
+#pragma unroll
+            for (int i = 0; i < WPL; i++) {
+                w[i] = reinterpret_cast<const uint32_t*>(m)[lane * WPL + i];
+                c += __popc(w[i]);
+            }
+            uint32_t* out = a.index_out + carry + (warp_inclusive_sum(c) - c);
+            const uint32_t e = a.index_base + (uint32_t)byte_off + lane * (32 * WPL);
+#pragma unroll
+            for (int i = 0; i < WPL; i++) {
+                uint32_t b = w[i];
+                while (b) {
+                    const int j = __ffs(b) - 1;
+                    b &= b - 1;
+                    *out++ = e + 32 * i + j;
+                }
+            }
+            return;
+        }
+        uint32_t bits[ROWS];
 #pragma unroll
         for (int r = 0; r < ROWS; r++) bits[r] = m[r * 32 + lane];
         const uint32_t* words = reinterpret_cast<const uint32_t*>(m);  // 16 words per row
@@ -283,11 +314,11 @@ struct CompressOp {
     static __device__ __forceinline__ void finish(P total, const Args& a) { a.out_count[0] = total; }
 };
 
-template <int CR_TILE, int CR_STAGES, int CR_TSLOTS, int CR_AHEAD>
+template <int CR_TILE, int CR_STAGES, int CR_TSLOTS, int CR_AHEAD, bool TRACE = false>
 __global__ void __launch_bounds__((CR_WARPS + 3) * 32, 1)
 compress_ring_kernel(const uint8_t* __restrict__ mask, size_t n, const uint32_t* __restrict__ size_buf,
                      uint32_t* __restrict__ out_count, uint32_t* __restrict__ index_out, uint32_t index_base,
-                     LookbackView lb, uint32_t G) {
+                     LookbackView lb, uint32_t G, unsigned long long* trace) {
     extern __shared__ __align__(128) char smem[];
     size_t n_eff = n;
     if (size_buf) {  // DynSize: device-resident element count (graph.rs:503-508)
@@ -298,8 +329,8 @@ compress_ring_kernel(const uint8_t* __restrict__ mask, size_t n, const uint32_t*
     if (n_tiles == 0 && blockIdx.x == 0 && threadIdx.x == 0) out_count[0] = 0;
     using Op = CompressOp<CR_TILE / CR_WARPS, CR_TILE, CR_TSLOTS>;
     typename Op::Args args{index_out, out_count, index_base};
-    ring_pipeline<Op, CR_TILE, CR_STAGES, CR_WARPS, CR_AHEAD, CR_TSLOTS, true>(reinterpret_cast<const char*>(mask), n_eff,
-                                                                      n_tiles, 0u, lb, G, args, smem);
+    ring_pipeline<Op, CR_TILE, CR_STAGES, CR_WARPS, CR_AHEAD, CR_TSLOTS, true, 8, TRACE>(
+        reinterpret_cast<const char*>(mask), n_eff, n_tiles, 0u, lb, G, args, smem, trace);
 }
 
 }  // namespace
@@ -322,14 +353,16 @@ hj_status launch_compress(hj_device* dev, size_t n, const uint32_t* size_buf, ui
         auto launch = [&](auto kernel, size_t smem) -> hj_status {
             HJ_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             kernel<<<grid, (CR_WARPS + 3) * 32, smem, dev->stream>>>(mask, n, size_buf, out_count, index_out,
-                                                                                index_base, view, (grid + 31u) & ~31u);
+                                                                                index_base, view, (grid + 31u) & ~31u,
+                                                                                g_compress_trace);
             return HJ_OK;
         };
         const size_t smem_small = ring_smem_bytes<uint32_t, 28672, 5, CR_WARPS, 8>(8 * (28672 / 8) + CR_WARPS * 1024);
         const size_t smem_big = ring_smem_bytes<uint32_t, 57344, 3, CR_WARPS, 4>(4 * (57344 / 8) + CR_WARPS * 1024);
         // measured on B200 (profiles/r01_ring_sweeps.txt): the 56 KiB geometry wins at low
         // selectivity (fewer status-word sweeps per byte) and ties elsewhere
-        if (big) HJ_TRY(launch(compress_ring_kernel<57344, 3, 4, 3>, smem_big));
+        if (g_compress_trace) HJ_TRY(launch(compress_ring_kernel<57344, 3, 4, 3, true>, smem_big));  // tools/ring_timeline.py
+        else if (big) HJ_TRY(launch(compress_ring_kernel<57344, 3, 4, 3>, smem_big));
         else HJ_TRY(launch(compress_ring_kernel<28672, 5, 8, 6>, smem_small));
         return check_launch(dev, "compress_ring_kernel");
     }
@@ -345,3 +378,5 @@ hj_status launch_compress(hj_device* dev, size_t n, const uint32_t* size_buf, ui
 }
 
 }  // namespace hj
+
+extern "C" void hj_debug_compress_trace(void* device_ptr) { hj::g_compress_trace = (unsigned long long*)device_ptr; }

@@ -118,17 +118,20 @@ struct RingCtl {
 //   static P    total(slice, aux, slot, cw, lane)
 //                                              phase 1: this warp's total of its SLICE bytes; may park
 //                                              per-tile data in `aux` (shared memory after the ring)
-//   static void emit(slice, aux, slot, byte_off, valid_bytes, carry, lane, cw, args)
+//   static void emit(slice, aux, slot, byte_off, valid_bytes, carry, slice_total, lane, cw, args)
 //                                              phase 2: write the outputs of the slice that starts
 //                                              `byte_off` bytes into the input (slice is only valid
 //                                              without EARLY release)
 //   static void finish(total, args)           called once by the CTA that owns the last tile
 // TILE bytes per stage, STAGES data stages, TSLOTS tile slots, CWARPS consumer warps; phase 1 runs
 // AHEAD tiles ahead of phase 2.
-template <class Op, int TILE, int STAGES, int CWARPS, int AHEAD, int TSLOTS = STAGES, bool EARLY = false, int SWEEP_M = 8>
+// TRACE (development aid, tools/ring_timeline.py): globaltimer stamps per tile in `trace` (10 words per tile).
+template <class Op, int TILE, int STAGES, int CWARPS, int AHEAD, int TSLOTS = STAGES, bool EARLY = false, int SWEEP_M = 8,
+          bool TRACE = false>
 __device__ __forceinline__ void ring_pipeline(const char* __restrict__ src, size_t n_bytes, uint32_t n_tiles,
                                               typename Op::P seed, LookbackView lb, uint32_t G,
-                                              const typename Op::Args& args, char* smem) {
+                                              const typename Op::Args& args, char* smem,
+                                              unsigned long long* trace = nullptr) {
     using P = typename Op::P;
     using Ctl = RingCtl<P, STAGES, TSLOTS, CWARPS>;
     static_assert(AHEAD >= 1 && AHEAD < TSLOTS, "a tile slot must outlive the AHEAD tiles between its two phases");
@@ -139,6 +142,13 @@ __device__ __forceinline__ void ring_pipeline(const char* __restrict__ src, size
     Ctl* ctl = reinterpret_cast<Ctl*>(smem + (size_t)STAGES * TILE);
     char* aux = smem + (size_t)STAGES * TILE + ((sizeof(Ctl) + 127) & ~(size_t)127);
     const int warp = warp_id(), lane = lane_id();
+    // stamp k of tile t: 0 drawn, 1 phase 1 starts, 2 phase 1 done, 3 aggregate published,
+    // 4 sweep starts, 5 prefix handed over, 6 phase 2 starts, 7 phase 2 done (consumer warp 0), 8 CTA
+    auto stamp = [&](uint32_t t, int k) {
+        if constexpr (TRACE) {
+            if (trace && t != RING_END) trace[(size_t)t * 10 + k] = k == 8 ? (unsigned long long)blockIdx.x : globaltimer_ns();
+        }
+    };
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; s++) {
@@ -197,6 +207,8 @@ __device__ __forceinline__ void ring_pipeline(const char* __restrict__ src, size
                 __syncwarp();
             }
             if (lane == 0) {
+                stamp(t, 0);
+                stamp(t, 8);
                 ctl->stile[s] = t;
                 if (bulk) {
                     mbar_expect_tx(&ctl->full[s], bulk);
@@ -224,6 +236,7 @@ __device__ __forceinline__ void ring_pipeline(const char* __restrict__ src, size
             if (lane == 0) {
                 tile_publish<P>(lb, t, TILE_AGGREGATE, aggregate);
                 ctl->tagg[q] = aggregate;
+                stamp(t, 3);
             }
             if (lane < CWARPS) ctl->woff[q][lane] = (P)(inc - w);
             __syncwarp();
@@ -258,6 +271,7 @@ __device__ __forceinline__ void ring_pipeline(const char* __restrict__ src, size
             }
             if (t == RING_END) break;
             const uint32_t k = t / G;
+            if (lane == 0) stamp(t, 4);
             P full_rounds = (P)0, partial = (P)0;
             ring_sum_ranges<P, SWEEP_M>(lb, next_round * G, k * G, t, &full_rounds, &partial);
             rounds_total = (P)(rounds_total + full_rounds);
@@ -267,6 +281,7 @@ __device__ __forceinline__ void ring_pipeline(const char* __restrict__ src, size
             if (lane == 0) {
                 ctl->tpre[q] = exclusive;
                 if (t == n_tiles - 1) Op::finish((P)(exclusive + ctl->tagg[q]), args);
+                stamp(t, 5);
                 mbar_arrive(&ctl->pref[q]);
             }
             if (++q == TSLOTS) { q = 0; par ^= 1; }
@@ -286,6 +301,7 @@ __device__ __forceinline__ void ring_pipeline(const char* __restrict__ src, size
                 if (t == RING_END) {
                     n_iter = it;
                 } else {
+                    if (cw == 0 && lane == 0) stamp(t, 1);
                     total = Op::total(stages + (size_t)s1 * TILE + (size_t)cw * SLICE, aux, q1, cw, lane);
                     if (EARLY) {
                         __syncwarp();
@@ -294,6 +310,7 @@ __device__ __forceinline__ void ring_pipeline(const char* __restrict__ src, size
                 }
                 // every warp arrives (also at RING_END, so the control warps wake up and stop)
                 if (lane == 0) {
+                    if (cw == 0) stamp(t, 2);
                     ctl->ttile[q1][cw] = t;
                     ctl->wsum[q1][cw] = total;
                     mbar_arrive(&ctl->agg[q1]);
@@ -305,11 +322,16 @@ __device__ __forceinline__ void ring_pipeline(const char* __restrict__ src, size
                 if (it - AHEAD >= n_iter) break;
                 mbar_wait(&ctl->pref[q2], qpar2);
                 const uint32_t t = ctl->ttile[q2][cw];
+                if (cw == 0 && lane == 0) stamp(t, 6);
                 const size_t byte_off = (size_t)t * TILE + (size_t)cw * SLICE;
                 const size_t valid = byte_off < n_bytes ? n_bytes - byte_off : 0;
                 Op::emit(stages + (size_t)s2 * TILE + (size_t)cw * SLICE, aux, q2, byte_off,
                          valid < (size_t)SLICE ? (uint32_t)valid : (uint32_t)SLICE,
-                         (P)(ctl->tpre[q2] + ctl->woff[q2][cw]), lane, cw, args);
+                         (P)(ctl->tpre[q2] + ctl->woff[q2][cw]), ctl->wsum[q2][cw], lane, cw, args);
+                if (TRACE && cw == 0) {
+                    __syncwarp();
+                    if (lane == 0) stamp(t, 7);
+                }
                 if (!EARLY) {
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&ctl->empty[s2]);

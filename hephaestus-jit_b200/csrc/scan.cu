@@ -230,7 +230,7 @@ struct ScanOp {
     }
     // phase 2: scan the slice row by row with a running carry and stream the result out
     static __device__ __forceinline__ void emit(const char* slice, char*, int, size_t byte_off, uint32_t valid, P carry,
-                                                int lane, int, const Args& a) {
+                                                P, int lane, int, const Args& a) {
         char* out_base = reinterpret_cast<char*>(a.dst) + byte_off;
 #pragma unroll
         for (int r = 0; r < ROWS; r++) {

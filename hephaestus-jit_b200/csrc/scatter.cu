@@ -116,11 +116,10 @@ histogram_smem(const uint32_t* __restrict__ idx, uint32_t literal, uint32_t* __r
 // (as in ring.cuh, minus the prefix logic: consumers wait for a stage, apply it, hand it back)
 // and are applied to bins in shared memory with shared-memory atomics.  How the bins fit:
 //   * PACKED16 (literal 1, <= 2^16 bins): two 16-bit counters per 32-bit word, so 2^16 bins are
-//     128 KiB and every SM holds ALL bins.  A counter that crosses 0x8000 is "cashed": the thread
-//     whose add crossed it (unique: the returned old value was 0x7fff) subtracts 0x8000 again and
-//     adds 0x8000 to the bin in HBM.  The counter can neither carry into its neighbour nor wrap:
-//     that would take 32768 further adds to one bin between the crossing add and its subtract,
-//     and a CTA has at most 28 warps x 32 lanes x 4 adds in flight.
+//     128 KiB and every SM holds ALL bins.  Adds do not use the atomic's return value (ATOMS
+//     without a return trip sustains 5.3 lanes/clk/SM, with one 4.0 — profiles/r01_histogram.txt),
+//     so nobody sees a counter fill up; instead the consumer warps sweep all counters every
+//     HR_SWEEP tiles and move their high bits to the bins in HBM (see HR_SWEEP below).
 //   * windows (any literal, <= 8 x 32768 bins): the bin range is split into `parts` windows of
 //     <= 32768 u32 bins; groups of `parts` CTAs walk the SAME key tiles, each applying only the
 //     keys of its own window (the partners' copies of a tile come out of L2, so HBM still
@@ -138,6 +137,12 @@ struct HistCtl {
     uint64_t empty[HR_STAGES];
 };
 
+// PACKED16: every HR_SWEEP tiles the consumer warps sweep the counters between two barriers and move
+// the top three bits of each to the bin in HBM.  After a sweep a counter is < 0x2000, a CTA applies
+// at most HR_SWEEP * HR_TILE / 4 = 57344 keys between two sweeps, 0x1fff + 57344 = 0xffff: no
+// counter can wrap or carry whatever the key distribution.
+constexpr int HR_SWEEP = 16;
+static_assert(0x1fff + HR_SWEEP * (HR_TILE / 4) <= 0xffff, "a 16-bit counter must survive one sweep period");
 template <bool PACKED16>
 __global__ void __launch_bounds__((HR_WARPS + 1) * 32, 1)
 hist_ring_kernel(const uint32_t* __restrict__ keys, size_t n, uint32_t literal, void* __restrict__ out,
@@ -154,7 +159,7 @@ hist_ring_kernel(const uint32_t* __restrict__ keys, size_t n, uint32_t literal, 
     const size_t n_bytes = n * 4;
     const uint32_t n_tiles = (uint32_t)((n_bytes + HR_TILE - 1) / HR_TILE);
 
-    for (uint32_t b = threadIdx.x; b < n_words; b += blockDim.x) bins[b] = 0;
+    for (uint32_t b = threadIdx.x; b < ((n_words + 3u) & ~3u); b += blockDim.x) bins[b] = 0;
     if (threadIdx.x == 0) {
         for (int s = 0; s < HR_STAGES; s++) {
             mbar_init(&ctl->full[s], 1);
@@ -192,7 +197,7 @@ hist_ring_kernel(const uint32_t* __restrict__ keys, size_t n, uint32_t literal, 
     } else {
         const int cw = warp;
         int s = 0;
-        uint32_t par = 0;
+        uint32_t par = 0, since_sweep = 0;
         for (uint32_t t = group; t < n_tiles; t += n_groups) {
             mbar_wait(&ctl->full[s], par);
             const uint4 k = lds_v4(stages + (size_t)s * HR_TILE + cw * 512 + lane * 16);
@@ -202,12 +207,7 @@ hist_ring_kernel(const uint32_t* __restrict__ keys, size_t n, uint32_t literal, 
                 const uint32_t a = kk[i] - lo;
                 if (a < nb) {
                     if (PACKED16) {
-                        const uint32_t sh = (a & 1u) * 16u;
-                        const uint32_t old = atomicAdd(bins + (a >> 1), 1u << sh);
-                        if (((old >> sh) & 0xffffu) == 0x7fffu) {  // this add crossed 0x8000: cash it
-                            atomicSub(bins + (a >> 1), 0x8000u << sh);
-                            atomicAdd(dst + lo + a, 0x8000u);
-                        }
+                        atomicAdd(bins + (a >> 1), 1u << ((a & 1u) * 16u));  // result unused: ATOMS without a return trip
                     } else {
                         atomicAdd(bins + a, literal);
                     }
@@ -216,6 +216,29 @@ hist_ring_kernel(const uint32_t* __restrict__ keys, size_t n, uint32_t literal, 
             __syncwarp();
             if (lane == 0) mbar_arrive(&ctl->empty[s]);
             if (++s == HR_STAGES) { s = 0; par ^= 1; }
+            if (PACKED16 && ++since_sweep == HR_SWEEP) {
+                // every consumer warp has applied the same HR_SWEEP tiles: sweep between two
+                // barriers of the consumer warps (the producer keeps streaming keys meanwhile)
+                since_sweep = 0;
+                asm volatile("bar.sync 1, %0;" ::"n"(HR_WARPS * 32) : "memory");
+                for (uint32_t w = threadIdx.x * 4; w < n_words; w += HR_WARPS * 32 * 4) {
+                    uint4 v = *reinterpret_cast<uint4*>(bins + w);
+                    if ((v.x | v.y | v.z | v.w) & 0xe000e000u) {
+                        const uint32_t vv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                        for (int i = 0; i < 4; i++) {
+                            const uint32_t c = vv[i] & 0xe000e000u;
+                            if (c) {
+                                bins[w + i] = vv[i] - c;
+                                const uint32_t b0 = 2 * (w + i);
+                                if (c & 0xffffu) atomicAdd(dst + lo + b0, c & 0xffffu);
+                                if (c >> 16) atomicAdd(dst + lo + b0 + 1, c >> 16);
+                            }
+                        }
+                    }
+                }
+                asm volatile("bar.sync 1, %0;" ::"n"(HR_WARPS * 32) : "memory");
+            }
         }
     }
     __syncthreads();
@@ -351,7 +374,7 @@ hj_status launch_scatter_reduce(hj_device* dev, hj_reduce_op op, hj_type_kind ty
                 const uint32_t n_groups = (uint32_t)dev->sm_count;
                 const uint32_t n_words = (uint32_t)((n_dst + 1) / 2);
                 HJ_TRY(ensure_hist_scratch(dev, (size_t)n_groups * n_words * 4));
-                const size_t smem = ring + (size_t)n_words * 4;
+                const size_t smem = ring + (((size_t)n_words + 3) & ~(size_t)3) * 4;
                 auto kern = hist_ring_kernel<true>;
                 HJ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
                 kern<<<n_groups, (HR_WARPS + 1) * 32, smem, dev->stream>>>(

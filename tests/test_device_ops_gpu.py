@@ -249,6 +249,24 @@ def test_compress_bit_exact(dev, n, p):
     assert np.array_equal(idx, wi)  # includes the untouched tail
 
 
+def test_compress_mixed_density(dev):
+    # density changes every 1000 elements so sparse, medium and dense rows (and slices) meet in one
+    # launch of the ring kernel
+    n = (1 << 22) + 1234
+    rng = np.random.Generator(np.random.PCG64(11))
+    dens = rng.choice([0.0, 0.002, 0.02, 0.1, 0.13, 0.3, 0.8, 0.82, 0.97, 1.0], size=n // 1000 + 1)
+    mask = (rng.random(n) < np.repeat(dens, 1000)[:n]).astype(np.uint8)
+    count, idx = gpu_compress(dev, mask, index_base=3, sentinel=0xDEADBEEF)
+    wc, wi = oracle.compress(mask, index_out=np.full(n, 0xDEADBEEF, np.uint32), index_base=3, mt=True)
+    assert count == wc and np.array_equal(idx, wi)
+    # Outside the reference's contract (its rank is the running sum of the mask BYTES, so it only
+    # defines 0/1 masks, compress_large.glsl:126-132): this backend selects every non-zero byte.
+    vals = rng.choice(np.array([1, 1, 1, 2, 128, 255], np.uint8), size=n)
+    wide = np.where(mask != 0, vals, 0).astype(np.uint8)
+    count2, idx2 = gpu_compress(dev, wide, index_base=3, sentinel=0xDEADBEEF)
+    assert count2 == wc and np.array_equal(idx2, wi)
+
+
 def test_compress_large_and_dynsize(dev):
     n = (1 << 24) + 77
     rng = np.random.Generator(np.random.PCG64(4))
@@ -308,6 +326,21 @@ def test_histogram_ring_paths_bit_exact(dev, n_bins, literal, dist):
     dev.scatter_reduce(hj.SUM, hj.U32, n, dev.create_buffer_from_slice(keys), None, literal, dst, n_bins)
     inside = keys[keys < n_bins]
     want = init + (oracle.histogram_u32_mt(inside, n_bins) * np.uint32(literal))
+    assert np.array_equal(dst.to_host(np.uint32), want)
+
+
+def test_histogram_single_bin_worst_case(dev):
+    # every key hits one bin (and its 16-bit neighbour in the same word): each CTA pushes 2^25 / 148
+    # adds through ONE packed counter, several sweep periods' worth — no counter may wrap or carry
+    n, n_bins = 1 << 25, 1 << 16
+    keys = np.full(n, 40001, np.uint32)
+    keys[1::3] = 40000
+    init = np.arange(n_bins, dtype=np.uint32)
+    dst = dev.create_buffer_from_slice(init)
+    dev.scatter_reduce(hj.SUM, hj.U32, n, dev.create_buffer_from_slice(keys), None, 1, dst, n_bins)
+    want = init.copy()
+    want[40000] += np.uint32(np.count_nonzero(keys == 40000))
+    want[40001] += np.uint32(np.count_nonzero(keys == 40001))
     assert np.array_equal(dst.to_host(np.uint32), want)
 
 
