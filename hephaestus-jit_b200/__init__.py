@@ -219,12 +219,21 @@ class Device:
         check(lib.hj_device_kernel_cache_stats(self._h, *[ctypes.byref(x) for x in v]))
         return dict(zip(("compiled", "hits", "disk_hits"), (x.value for x in v)))
 
-    def execute_graph(self, passes, env, descs, timed: bool = False):
+    def graph_cache_stats(self):
+        """(captured, replayed, plain) counters of ``hj_execute_graph_cached``."""
+        c, r, p = _lib._u64(), _lib._u64(), _lib._u64()
+        check(lib.hj_graph_cache_stats(self._h, ctypes.byref(c), ctypes.byref(r), ctypes.byref(p)))
+        return c.value, r.value, p.value
+
+    def execute_graph(self, passes, env, descs, timed: bool = False, graph_key: int = 0):
         """``BackendDevice::execute_graph`` (backend/mod.rs:33).
 
         passes: list of dicts {kind, arg, resources, size_buffer, ir (IRBuilder|None), size};
         env: list of Buffer (or None); descs: list of (size_elems, ty, elem_bytes).
-        Returns the list of (name, start_us, duration_us) when ``timed``."""
+        Returns the list of (name, start_us, duration_us) when ``timed``.  A non-zero
+        ``graph_key`` names a pass list that is launched repeatedly: from the second launch with
+        the same buffers on it is replayed as one captured CUDA graph (returns 0 / 1 / 2 =
+        executed / captured / replayed)."""
         n = len(passes)
         c_passes = (_lib.Pass * max(n, 1))()
         keep = []
@@ -246,6 +255,10 @@ class Device:
         if timed:
             report.passes = reps
             report.passes_capacity = n
+        if graph_key and not timed:
+            how = ctypes.c_uint32()
+            check(lib.hj_execute_graph_cached(self._h, graph_key, c_passes, n, c_env, c_desc, len(env), ctypes.byref(how)))
+            return how.value
         check(lib.hj_execute_graph(self._h, c_passes, n, c_env, c_desc, len(env), ctypes.byref(report)))
         if timed:
             return [(reps[i].name.decode(), reps[i].start_us, reps[i].duration_us) for i in range(n)]

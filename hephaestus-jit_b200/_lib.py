@@ -142,6 +142,10 @@ _SIGS = {
     "hj_device_kernel_cache_stats": (_i32, [_vp] + [ctypes.POINTER(_u64)] * 3),
     "hj_execute_graph": (_i32, [_vp, ctypes.POINTER(Pass), _u32, _pvp, ctypes.POINTER(BufferDesc),
                                 _u32, ctypes.POINTER(Report)]),
+    "hj_execute_graph_cached": (_i32, [_vp, _u64, ctypes.POINTER(Pass), _u32, _pvp, ctypes.POINTER(BufferDesc),
+                                       _u32, ctypes.POINTER(_u32)]),
+    "hj_graph_cache_drop": (_i32, [_vp, _u64]),
+    "hj_graph_cache_stats": (_i32, [_vp] + [ctypes.POINTER(_u64)] * 3),
     "hj_comm_unique_id": (_i32, [_vp]),
     "hj_comm_create": (_i32, [_vp, _vp, _i32, _i32, _pvp]),
     "hj_comm_destroy": (_i32, [_vp]),

@@ -60,18 +60,24 @@ __global__ void __launch_bounds__(CMP_THREADS, CMP_CTAS_PER_SM)
 compress_kernel(const uint8_t* __restrict__ mask, size_t n, const uint32_t* __restrict__ size_buf,
                 uint32_t* __restrict__ out_count, uint32_t* __restrict__ index_out,
                 uint32_t index_base, LookbackView lb, int vec_ok) {
-    __shared__ uint32_t s_tile;
+    __shared__ uint32_t s_tile, s_epoch;
     __shared__ uint32_t s_warp[CMP_WARPS];
     __shared__ uint32_t s_stage[CMP_WARPS][CMP_ROW];  // 16 KiB: one row of indices per warp
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) {
+        const uint32_t e = epoch_begin(lb);
         uint32_t t = atomicAdd(lb.ticket, 1u);
-        if (t == gridDim.x - 1) *lb.ticket = 0;
+        if (t == gridDim.x - 1) {
+            *lb.ticket = 0;
+            epoch_advance(lb, e);
+        }
         s_tile = t;
+        s_epoch = e;
     }
     __syncthreads();
     const uint32_t tile = s_tile;
+    lb.epoch = s_epoch;
     const size_t base = (size_t)tile * CMP_TILE;
     size_t n_eff = n;
     if (size_buf) {  // DynSize: device-resident element count (graph.rs:503-508)
@@ -346,9 +352,8 @@ hj_status launch_compress(hj_device* dev, size_t n, const uint32_t* size_buf, ui
         const size_t tile_bytes = big ? 57344 : 28672;
         const size_t tiles = (n + tile_bytes - 1) / tile_bytes;
         HJ_TRY(ensure_lookback_scratch(dev, tiles));
-        uint32_t ep;
-        HJ_TRY(next_epoch(dev, &ep));
-        LookbackView view = lookback_view(dev->lookback.base, dev->lookback.capacity_tiles, ep);
+        HJ_TRY(count_epoch(dev));
+        LookbackView view = lookback_view(dev->lookback.base, dev->lookback.capacity_tiles, 0);
         const unsigned grid = (unsigned)(tiles < (size_t)dev->sm_count ? tiles : (size_t)dev->sm_count);
         auto launch = [&](auto kernel, size_t smem) -> hj_status {
             HJ_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -368,9 +373,8 @@ hj_status launch_compress(hj_device* dev, size_t n, const uint32_t* size_buf, ui
     }
     size_t n_tiles = (n + CMP_TILE - 1) / CMP_TILE;
     HJ_TRY(ensure_lookback_scratch(dev, n_tiles));
-    uint32_t epoch;
-    HJ_TRY(next_epoch(dev, &epoch));
-    LookbackView lb = lookback_view(dev->lookback.base, dev->lookback.capacity_tiles, epoch);
+    HJ_TRY(count_epoch(dev));
+    LookbackView lb = lookback_view(dev->lookback.base, dev->lookback.capacity_tiles, 0);
     int vec_ok = ((uintptr_t)mask & 15u) == 0;
     compress_kernel<<<(unsigned)n_tiles, CMP_THREADS, 0, dev->stream>>>(mask, n, size_buf, out_count,
                                                                        index_out, index_base, lb, vec_ok);

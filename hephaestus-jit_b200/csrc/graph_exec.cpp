@@ -20,6 +20,24 @@
 
 using namespace hj;
 
+namespace hj {
+// Captured CUDA graphs of hj_execute_graph_cached.  An instance belongs to one pass list (key) AND
+// one set of buffer addresses: kernel nodes hold raw pointers.  `generation` is the scratch
+// generation at capture (a reallocated scratch invalidates every instance).
+struct GraphInstance {
+    std::vector<void*> ptrs;
+    cudaGraphExec_t exec = nullptr;
+    uint64_t generation = 0, last_use = 0;
+    uint32_t n_epochs = 0;     // look-back epochs one replay consumes (host-side wrap accounting)
+    uint64_t n_launches = 0;   // kernel launches one replay stands for
+    bool uncapturable = false;
+};
+struct GraphCache {
+    std::unordered_map<uint64_t, std::vector<GraphInstance>> by_key;
+    uint64_t captured = 0, replayed = 0, plain = 0, clock = 0;
+};
+}  // namespace hj
+
 namespace {
 // A kernel pass whose whole IR is `dst[keys[i]] += literal` (u32 / i32) — what
 // `sized_literal(v, n).scatter_reduce(&hist, &keys, ReduceOp::Sum)` (trace.rs:1210-1233) compiles
@@ -166,5 +184,129 @@ extern "C" hj_status hj_execute_graph(hj_device* dev, const hj_pass* passes, uin
         report->cpu_duration_us =
             std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - cpu_start).count();
     }
+    return HJ_OK;
+}
+
+namespace {
+constexpr size_t MAX_INSTANCES_PER_KEY = 8;
+
+void destroy_instance(GraphInstance& g) {
+    if (g.exec) cudaGraphExecDestroy(g.exec);
+    g.exec = nullptr;
+}
+}  // namespace
+
+extern "C" hj_status hj_execute_graph_cached(hj_device* dev, uint64_t graph_key, const hj_pass* passes,
+                                             uint32_t n_passes, hj_buffer* const* env, const hj_buffer_desc* descs,
+                                             uint32_t n_resources, uint32_t* how) {
+    HJ_REQUIRE(dev && (passes || n_passes == 0), "hj_execute_graph_cached: null argument");
+    HJ_REQUIRE((env && descs) || n_resources == 0, "hj_execute_graph_cached: null environment");
+    static const bool disabled = getenv("HJ_NO_CUDA_GRAPHS") != nullptr;
+    if (how) *how = 0;
+    DeviceGuard g(dev);  // held across the whole capture: nobody else may enqueue on the capturing stream
+    if (!dev->gcache) dev->gcache = new GraphCache();
+    GraphCache& gc = *dev->gcache;
+    if (disabled || n_passes == 0) {
+        gc.plain++;
+        return hj_execute_graph(dev, passes, n_passes, env, descs, n_resources, nullptr);
+    }
+    std::vector<void*> sig(n_resources);
+    for (uint32_t i = 0; i < n_resources; i++) sig[i] = env[i] ? env[i]->ptr : nullptr;
+    std::vector<GraphInstance>& insts = gc.by_key[graph_key];
+    GraphInstance* inst = nullptr;
+    for (GraphInstance& c : insts)
+        if (c.ptrs == sig) inst = &c;
+
+    if (!inst) {
+        // first sight of these addresses: execute normally (compiles kernels, sizes every scratch)
+        if (insts.size() >= MAX_INSTANCES_PER_KEY) {
+            size_t oldest = 0;
+            for (size_t i = 1; i < insts.size(); i++)
+                if (insts[i].last_use < insts[oldest].last_use) oldest = i;
+            destroy_instance(insts[oldest]);
+            insts.erase(insts.begin() + (long)oldest);
+        }
+        GraphInstance fresh;
+        fresh.ptrs = std::move(sig);
+        fresh.last_use = ++gc.clock;
+        insts.push_back(std::move(fresh));
+        gc.plain++;
+        return hj_execute_graph(dev, passes, n_passes, env, descs, n_resources, nullptr);
+    }
+    inst->last_use = ++gc.clock;
+    if (inst->exec && inst->generation != dev->lookback.generation) destroy_instance(*inst);  // stale scratch pointers
+    if (inst->exec) {
+        HJ_TRY(count_epoch(dev, inst->n_epochs));
+        HJ_CUDA(cudaGraphLaunch(inst->exec, dev->stream));
+        dev->launches.fetch_add(inst->n_launches, std::memory_order_relaxed);
+        gc.replayed++;
+        if (how) *how = 2;
+        return HJ_OK;
+    }
+    if (inst->uncapturable) {
+        gc.plain++;
+        return hj_execute_graph(dev, passes, n_passes, env, descs, n_resources, nullptr);
+    }
+    // second launch with these addresses: capture the pass list
+    const uint32_t epochs0 = dev->lookback.epoch;
+    const uint64_t launches0 = dev->launches.load(std::memory_order_relaxed);
+    const uint64_t gen0 = dev->lookback.generation;
+    cudaGraph_t graph = nullptr;
+    cudaError_t e = cudaStreamBeginCapture(dev->stream, cudaStreamCaptureModeThreadLocal);
+    hj_status st = HJ_ERR_CUDA;
+    if (e == cudaSuccess) {
+        st = hj_execute_graph(dev, passes, n_passes, env, descs, n_resources, nullptr);
+        e = cudaStreamEndCapture(dev->stream, &graph);
+    }
+    const uint32_t n_epochs = dev->lookback.epoch - epochs0;
+    const bool ok = e == cudaSuccess && st == HJ_OK && graph && gen0 == dev->lookback.generation &&
+                    dev->lookback.epoch >= epochs0;
+    if (ok) e = cudaGraphInstantiate(&inst->exec, graph, 0);
+    if (graph) cudaGraphDestroy(graph);
+    if (!ok || e != cudaSuccess) {
+        // nothing ran (the work was only recorded): fall back to the pass-by-pass path for good
+        cudaGetLastError();
+        inst->exec = nullptr;
+        inst->uncapturable = true;
+        dev->lookback.epoch = epochs0;
+        dev->launches.store(launches0, std::memory_order_relaxed);
+        gc.plain++;
+        return hj_execute_graph(dev, passes, n_passes, env, descs, n_resources, nullptr);
+    }
+    inst->generation = gen0;
+    inst->n_epochs = n_epochs;
+    inst->n_launches = dev->launches.load(std::memory_order_relaxed) - launches0;
+    HJ_CUDA(cudaGraphLaunch(inst->exec, dev->stream));
+    gc.captured++;
+    if (how) *how = 1;
+    return HJ_OK;
+}
+
+extern "C" hj_status hj_graph_cache_drop(hj_device* dev, uint64_t graph_key) {
+    HJ_REQUIRE(dev, "null device");
+    DeviceGuard g(dev);
+    if (!dev->gcache) return HJ_OK;
+    auto& map = dev->gcache->by_key;
+    if (graph_key == 0) {
+        for (auto& kv : map)
+            for (GraphInstance& c : kv.second) destroy_instance(c);
+        map.clear();
+        return HJ_OK;
+    }
+    auto it = map.find(graph_key);
+    if (it != map.end()) {
+        for (GraphInstance& c : it->second) destroy_instance(c);
+        map.erase(it);
+    }
+    return HJ_OK;
+}
+
+extern "C" hj_status hj_graph_cache_stats(hj_device* dev, uint64_t* captured, uint64_t* replayed, uint64_t* plain) {
+    HJ_REQUIRE(dev, "null device");
+    DeviceGuard g(dev);
+    const GraphCache* gc = dev->gcache;
+    if (captured) *captured = gc ? gc->captured : 0;
+    if (replayed) *replayed = gc ? gc->replayed : 0;
+    if (plain) *plain = gc ? gc->plain : 0;
     return HJ_OK;
 }

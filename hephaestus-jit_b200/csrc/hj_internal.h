@@ -49,6 +49,7 @@ const char* type_name(hj_type_kind ty);
 const char* reduce_op_name(hj_reduce_op op);
 
 struct KernelCache;  // jit.cpp
+struct GraphCache;   // graph_exec.cpp
 
 // Persistent per-device scratch of the decoupled-look-back kernels (scan, compress).
 // Status words carry an epoch so the buffer never has to be cleared between launches.
@@ -56,7 +57,8 @@ struct LookbackScratch {
     void* base = nullptr;   // layout: lookback.cuh (ticket | status words | aggregates | inclusives)
     size_t bytes = 0;
     size_t capacity_tiles = 0;
-    uint32_t epoch = 0;     // last epoch handed out; valid epochs are 1 .. 2^30-1
+    uint32_t epoch = 0;     // epochs consumed by the launches enqueued since the scratch was last cleared
+    uint64_t generation = 0;  // bumped whenever any per-device scratch is reallocated (captured graphs hold raw pointers)
 };
 
 }  // namespace hj
@@ -70,7 +72,8 @@ struct hj_device {
     int sm_count = 0, cc_major = 0, cc_minor = 0;
     size_t total_mem = 0, l2_bytes = 0;
     int max_smem_optin = 0;
-    std::mutex mu;  // serialises enqueue + scratch use (Device: Send + Sync in the reference)
+    std::recursive_mutex mu;  // serialises enqueue + scratch use (Device: Send + Sync in the reference);
+                              // recursive: a graph capture holds it across the passes it enqueues
     hj::LookbackScratch lookback;
     void* reduce_scratch = nullptr;  // partials + ticket of the single-pass reduction
     size_t reduce_scratch_bytes = 0;
@@ -79,6 +82,7 @@ struct hj_device {
     std::atomic<uint64_t> launches{0};
     std::atomic<uint64_t> n_alloc{0}, n_free{0};
     hj::KernelCache* kcache = nullptr;
+    hj::GraphCache* gcache = nullptr;  // captured CUDA graphs of hj_execute_graph_cached
 };
 
 struct hj_buffer {
@@ -94,7 +98,7 @@ namespace hj {
 // RAII guard: selects the device and holds its enqueue lock.
 struct DeviceGuard {
     hj_device* dev;
-    std::unique_lock<std::mutex> lock;
+    std::unique_lock<std::recursive_mutex> lock;
     explicit DeviceGuard(hj_device* d) : dev(d), lock(d->mu) { cudaSetDevice(d->ordinal); }
 };
 
@@ -102,8 +106,9 @@ struct DeviceGuard {
 hj_status ensure_reduce_scratch(hj_device* dev, size_t bytes);
 hj_status ensure_hist_scratch(hj_device* dev, size_t bytes);
 hj_status ensure_lookback_scratch(hj_device* dev, size_t n_tiles);
-// Next look-back epoch (clears the scratch on wrap-around).
-hj_status next_epoch(hj_device* dev, uint32_t* out);
+// Accounts for `n` launches of epoch-consuming kernels (clears the scratch before the device-side
+// epoch could wrap).
+hj_status count_epoch(hj_device* dev, uint32_t n = 1);
 
 // ---- kernel launchers (defined in the .cu files; device lock held by the caller) ---------
 struct PeerView;  // peer.cuh

@@ -157,7 +157,7 @@ hj_status hj_kernel_get(hj_device* dev, const hj_ir* ir, hj_kernel** out) {
     HJ_REQUIRE(dev && ir && out, "null argument");
     uint64_t h = hj_ir_hash(ir);
     {
-        std::lock_guard<std::mutex> g(dev->mu);
+        std::lock_guard<std::recursive_mutex> g(dev->mu);
         if (!dev->kcache) dev->kcache = new KernelCache();
     }
     KernelCache* kc = dev->kcache;

@@ -10,7 +10,11 @@
 //   * 8-byte prefixes use two such words (low half + flag, high half + flag) that a reader
 //     only accepts when both flags agree, so nothing is truncated and nothing needs ordering;
 //   * the flag carries a 30-bit launch epoch, so the scratch is never cleared between
-//     launches: a word written by an earlier launch simply reads as "not ready";
+//     launches: a word written by an earlier launch simply reads as "not ready".  The epoch
+//     lives in the scratch itself (next to the ticket): every CTA reads it before its first
+//     ticket draw and the CTA that makes the launch's last draw advances it.  No launch
+//     parameter changes from one launch to the next, so the kernels can be replayed from a
+//     captured CUDA graph (graph_exec.cpp);
 //   * tiles take their index from an atomic ticket (like the reference,
 //     prefix_sum_large.glsl:177-186), so a tile only ever waits on tiles that already run.
 #pragma once
@@ -20,10 +24,10 @@ namespace hj {
 
 enum : uint32_t { TILE_INVALID = 0, TILE_AGGREGATE = 1, TILE_INCLUSIVE = 2 };
 
-// Scratch layout (bytes): [0,64) ticket counter | words: max_tiles * 8 | agg: max_tiles * 8 |
-// incl: max_tiles * 8.  4-byte prefixes only touch `words`.
+// Scratch layout (bytes): [0,4) ticket counter | [4,8) epoch of the previous launch | words:
+// max_tiles * 8 | agg: max_tiles * 8 | incl: max_tiles * 8.  4-byte prefixes only touch `words`.
 struct LookbackView {
-    unsigned* ticket;
+    unsigned* ticket;  // ticket[1] = epoch counter
     unsigned long long* words;
     unsigned long long* agg;
     unsigned long long* incl;
@@ -40,6 +44,14 @@ static inline LookbackView lookback_view(void* base, size_t n_tiles, uint32_t ep
     v.epoch = epoch;
     return v;
 }
+constexpr uint32_t EPOCH_MASK = 0x3fffffffu;
+// Epoch of this launch; to be read by ONE thread per CTA BEFORE the CTA's first ticket draw (acquire:
+// the draw cannot move ahead of it), so it is read before the launch's last draw, whose CTA calls
+// epoch_advance.
+__device__ __forceinline__ uint32_t epoch_begin(const LookbackView& lb) {
+    return (ld_acquire_u32(lb.ticket + 1) + 1u) & EPOCH_MASK;
+}
+__device__ __forceinline__ void epoch_advance(const LookbackView& lb, uint32_t epoch) { lb.ticket[1] = epoch; }
 
 template <typename P>
 __device__ __forceinline__ void tile_publish(const LookbackView& lb, uint32_t tile, uint32_t state,

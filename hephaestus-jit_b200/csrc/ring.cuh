@@ -111,6 +111,7 @@ struct RingCtl {
     P woff[TSLOTS][CWARPS];   // offset of each warp's slice inside the tile (publisher warp)
     P tagg[TSLOTS];           // tile aggregate
     P tpre[TSLOTS];           // exclusive prefix of the tile (prefix warp)
+    uint32_t epoch;           // this launch's status-word epoch (lookback.cuh: epoch_begin)
 };
 
 // The kernel body.  `Op` supplies the element-level work:
@@ -160,8 +161,10 @@ __device__ __forceinline__ void ring_pipeline(const char* __restrict__ src, size
             mbar_init(&ctl->pub[q], 1);
             mbar_init(&ctl->pref[q], 1);
         }
+        ctl->epoch = epoch_begin(lb);
     }
     __syncthreads();
+    lb.epoch = ctl->epoch;
 
     if (warp == 0) {
         // ---------------- producer: ticket -> TMA bulk copy of the tile into the next stage.
@@ -179,14 +182,20 @@ __device__ __forceinline__ void ring_pipeline(const char* __restrict__ src, size
             uint32_t t = tq[0];
 #pragma unroll
             for (int i = 0; i + 1 < TICKETS; i++) tq[i] = tq[i + 1];
-            if (lane == 0 && t == last_draw) *lb.ticket = 0;  // the very last draw re-arms the counter
+            if (lane == 0 && t == last_draw) {  // the very last draw re-arms the counter, advances the epoch
+                *lb.ticket = 0;
+                epoch_advance(lb, lb.epoch);
+            }
             if (use > 0) mbar_wait(&ctl->empty[s], (use - 1) & 1);
             t = __shfl_sync(0xffffffffu, t, 0);
             if (t >= n_tiles) {
                 if (lane == 0) {
 #pragma unroll
                     for (int i = 0; i + 1 < TICKETS; i++)
-                        if (tq[i] == last_draw) *lb.ticket = 0;
+                        if (tq[i] == last_draw) {
+                            *lb.ticket = 0;
+                            epoch_advance(lb, lb.epoch);
+                        }
                     ctl->stile[s] = RING_END;
                     mbar_arrive(&ctl->full[s]);
                 }

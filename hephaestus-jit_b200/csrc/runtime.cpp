@@ -57,6 +57,7 @@ hj_status ensure_reduce_scratch(hj_device* dev, size_t bytes) {
     if (dev->reduce_scratch_bytes >= bytes) return HJ_OK;
     if (dev->reduce_scratch) HJ_CUDA(cudaFree(dev->reduce_scratch));  // implicit sync: safe
     dev->reduce_scratch = nullptr;
+    dev->lookback.generation++;
     HJ_CUDA(cudaMalloc(&dev->reduce_scratch, bytes));
     HJ_CUDA(cudaMemsetAsync(dev->reduce_scratch, 0, bytes, dev->stream));
     dev->reduce_scratch_bytes = bytes;
@@ -68,6 +69,7 @@ hj_status ensure_hist_scratch(hj_device* dev, size_t bytes) {
     if (dev->hist_scratch) HJ_CUDA(cudaFree(dev->hist_scratch));  // implicit sync: safe
     dev->hist_scratch = nullptr;
     dev->hist_scratch_bytes = 0;
+    dev->lookback.generation++;
     HJ_CUDA(cudaMalloc(&dev->hist_scratch, bytes));
     dev->hist_scratch_bytes = bytes;
     return HJ_OK;
@@ -82,6 +84,8 @@ hj_status ensure_lookback_scratch(hj_device* dev, size_t n_tiles) {
     lb.base = nullptr;
     lb.capacity_tiles = 0;
     size_t bytes = 64 + cap * 24;
+    lb.generation++;
+    lb.epoch = 0;
     HJ_CUDA(cudaMalloc(&lb.base, bytes));
     HJ_CUDA(cudaMemsetAsync(lb.base, 0, bytes, dev->stream));
     lb.capacity_tiles = cap;
@@ -90,13 +94,16 @@ hj_status ensure_lookback_scratch(hj_device* dev, size_t n_tiles) {
     return HJ_OK;
 }
 
-hj_status next_epoch(hj_device* dev, uint32_t* out) {
+// The epoch itself lives on the device (lookback.cuh); the host only counts how many epochs the
+// launches it has enqueued (graph replays included) will consume, and clears the scratch — epoch
+// counter included — before the 30-bit epoch could wrap onto a stale status word.
+hj_status count_epoch(hj_device* dev, uint32_t n) {
     LookbackScratch& lb = dev->lookback;
-    if (lb.epoch >= (1u << 30) - 1) {  // wrap: clear once, restart
+    if (lb.base && (uint64_t)lb.epoch + n >= (1u << 30) - 1) {
         HJ_CUDA(cudaMemsetAsync(lb.base, 0, lb.bytes, dev->stream));
         lb.epoch = 0;
     }
-    *out = ++lb.epoch;
+    lb.epoch += n;
     return HJ_OK;
 }
 

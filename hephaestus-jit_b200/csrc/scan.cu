@@ -75,19 +75,25 @@ scan_kernel(const T* __restrict__ src, T* __restrict__ dst, size_t n, const T* _
     constexpr int ROW = 32 * VEC;              // elements per coalesced warp row
     constexpr int SEG = SCAN_ROWS * ROW;       // elements per warp
     constexpr int TILE = SCAN_WARPS * SEG;     // elements per CTA
-    __shared__ uint32_t s_tile;
+    __shared__ uint32_t s_tile, s_epoch;
     __shared__ P s_warp[SCAN_WARPS];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     unsigned long long t_start = 0, t_summed = 0, t_prefix = 0;
     if (trace && tid == 0) t_start = globaltimer_ns();
     if (tid == 0) {
+        const uint32_t e = epoch_begin(lb);
         uint32_t t = atomicAdd(lb.ticket, 1u);
-        if (t == gridDim.x - 1) *lb.ticket = 0;  // last ticket: re-arm for the next launch
+        if (t == gridDim.x - 1) {  // last ticket: re-arm for the next launch
+            *lb.ticket = 0;
+            epoch_advance(lb, e);
+        }
         s_tile = t;
+        s_epoch = e;
     }
     __syncthreads();
     const uint32_t tile = s_tile;
+    lb.epoch = s_epoch;
     const size_t base = (size_t)tile * TILE;
     const bool full = vec_ok && base + TILE <= n;
     const size_t lane_base = base + (size_t)warp * SEG + lane * VEC;  // this lane's vector in row 0
@@ -279,9 +285,8 @@ hj_status run_ring(hj_device* dev, size_t n, bool inclusive, const void* src, vo
     const size_t n_tiles = (n * sizeof(T) + TILE - 1) / TILE;
     HJ_REQUIRE(n_tiles < (1ull << 31), "prefix_sum: too many tiles");
     HJ_TRY(ensure_lookback_scratch(dev, n_tiles));
-    uint32_t epoch;
-    HJ_TRY(next_epoch(dev, &epoch));
-    LookbackView lb = lookback_view(dev->lookback.base, dev->lookback.capacity_tiles, epoch);
+    HJ_TRY(count_epoch(dev));
+    LookbackView lb = lookback_view(dev->lookback.base, dev->lookback.capacity_tiles, 0);
     const size_t smem = ring_smem_bytes<P, TILE, STAGES, CWARPS>();
     const unsigned grid = (unsigned)std::min<size_t>(n_tiles, (size_t)dev->sm_count);
     const uint32_t G = (grid + 31u) & ~31u;  // tiles per round: about one per CTA
@@ -313,9 +318,8 @@ hj_status run(hj_device* dev, size_t n, bool inclusive, const void* src, void* d
     size_t n_tiles = (n + TILE - 1) / TILE;
     HJ_REQUIRE(n_tiles < (1ull << 31), "prefix_sum: too many tiles");
     HJ_TRY(ensure_lookback_scratch(dev, n_tiles));
-    uint32_t epoch;
-    HJ_TRY(next_epoch(dev, &epoch));
-    LookbackView lb = lookback_view(dev->lookback.base, dev->lookback.capacity_tiles, epoch);
+    HJ_TRY(count_epoch(dev));
+    LookbackView lb = lookback_view(dev->lookback.base, dev->lookback.capacity_tiles, 0);
     int vec_ok = (((uintptr_t)src | (uintptr_t)dst) & 15u) == 0;
     if (inclusive)
         scan_kernel<T, P, true><<<(unsigned)n_tiles, SCAN_THREADS, 0, dev->stream>>>(

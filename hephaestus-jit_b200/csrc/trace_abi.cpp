@@ -213,7 +213,7 @@ hj_status hj_graph_launch(hj_graph* g, hj_device* dev, const uint64_t* inputs, u
             br.passes = report->passes;
             br.passes_capacity = report->passes_capacity;
         }
-        launch_graph(*g->g, dev, vec_of(inputs, n_in), &outs, &lr, report ? &br : nullptr);
+        launch_graph(*g->g, dev, vec_of(inputs, n_in), &outs, &lr, timed ? &br : nullptr);  // per-pass timings need the pass-by-pass path
         if (outputs_out)
             for (size_t i = 0; i < outs.size(); i++) outputs_out[i] = outs[i];
         else
@@ -222,7 +222,7 @@ hj_status hj_graph_launch(hj_graph* g, hj_device* dev, const uint64_t* inputs, u
             report->aliasing_rate = lr.aliasing_rate;
             report->aliasing_duration_us = lr.aliasing_duration_us;
             report->n_passes = lr.n_passes;
-            report->backend_cpu_us = br.cpu_duration_us;
+            report->backend_cpu_us = lr.backend_cpu_us;
         }
     });
 }

@@ -142,6 +142,8 @@ struct GraphResource {  // graph.rs:44-51
     VarId id = NO_VAR;  // Captured: owns a reference; Internal: weak
 };
 struct Graph {
+    uint64_t uid = 0;                        // key of its captured CUDA graphs (hj_execute_graph_cached)
+    mutable hj_device* launched_on = nullptr;  // device holding captured instances of this graph
     std::vector<Pass> passes;
     std::vector<BufferDesc> resource_descs;
     std::vector<GraphResource> resources;

@@ -282,6 +282,26 @@ hj_status hj_execute_graph(hj_device* dev, const hj_pass* passes, uint32_t n_pas
                            hj_buffer* const* env, const hj_buffer_desc* descs,
                            uint32_t n_resources, hj_report* report /* may be NULL */);
 
+/* The same call for a pass list the caller launches again and again — what FCache::call does
+ * with a recorded function's Graph (hephaestus-jit/src/record.rs:120-210, graph.rs:192-400; the
+ * reference re-records and re-submits a Vulkan command buffer on every launch,
+ * backend/vulkan/mod.rs:151-383).  `graph_key` names the pass list (the caller guarantees that one
+ * key always comes with the same passes and descs).  The first launch of a (key, buffer
+ * addresses) pair executes normally, the second captures the whole pass list into ONE CUDA graph,
+ * every later one replays it with a single cudaGraphLaunch.  Launches whose buffers sit at other
+ * addresses than any captured instance take the normal path.  `how`, if not NULL, receives
+ * 0 = executed pass by pass, 1 = captured and launched, 2 = replayed. */
+hj_status hj_execute_graph_cached(hj_device* dev, uint64_t graph_key, const hj_pass* passes,
+                                  uint32_t n_passes, hj_buffer* const* env,
+                                  const hj_buffer_desc* descs, uint32_t n_resources,
+                                  uint32_t* how /* may be NULL */);
+/* Drops the captured instances of one key (0: of every key), e.g. when the caller frees a Graph. */
+hj_status hj_graph_cache_drop(hj_device* dev, uint64_t graph_key);
+/* Counters since device creation: graphs captured, graph replays, uncaptured launches through
+ * hj_execute_graph_cached. */
+hj_status hj_graph_cache_stats(hj_device* dev, uint64_t* captured, uint64_t* replayed,
+                               uint64_t* plain);
+
 /* ---- sharded (multi-GPU) ops ---------------------------------------------------------
  * One process per GPU; `hj_comm` wraps an NCCL communicator created from a unique id the
  * host distributes (torch.distributed store / broadcast).  The reference has no multi-GPU

@@ -33,5 +33,7 @@ for name, build in (("3 chained kernels (aliasing1)", build_chain), ("kernel + r
     t1 = time.perf_counter()
     dev.sync()
     t2 = time.perf_counter()
-    print(f"{name}: {g.n_passes()} passes, {(t1-t0)/n*1e6:.1f} us per launch_with call (host), {(t2-t0)/n*1e6:.1f} us incl. GPU drain")
+    mode = "pass by pass (HJ_NO_CUDA_GRAPHS)" if os.environ.get("HJ_NO_CUDA_GRAPHS") else "captured CUDA graph replay"
+    print(f"{name} [{mode}]: {g.n_passes()} passes, {(t1-t0)/n*1e6:.1f} us per launch_with call (host), "
+          f"{(t2-t0)/n*1e6:.1f} us incl. GPU drain; graph cache (captured, replayed, plain) = {dev.graph_cache_stats()}")
     del g, keep
