@@ -159,7 +159,8 @@ hist_ring_kernel(const uint32_t* __restrict__ keys, size_t n, uint32_t literal, 
     const size_t n_bytes = n * 4;
     const uint32_t n_tiles = (uint32_t)((n_bytes + HR_TILE - 1) / HR_TILE);
 
-    for (uint32_t b = threadIdx.x; b < ((n_words + 3u) & ~3u); b += blockDim.x) bins[b] = 0;
+    // PACKED16: also the padding the 128-bit sweep reads and the 32 dummy words
+    for (uint32_t b = threadIdx.x; b < (PACKED16 ? ((n_words + 3u) & ~3u) + 32u : n_words); b += blockDim.x) bins[b] = 0;
     if (threadIdx.x == 0) {
         for (int s = 0; s < HR_STAGES; s++) {
             mbar_init(&ctl->full[s], 1);
@@ -196,21 +197,33 @@ hist_ring_kernel(const uint32_t* __restrict__ keys, size_t n, uint32_t literal, 
         }
     } else {
         const int cw = warp;
+        const uint32_t bins_s = smem_u32(bins);
         int s = 0;
         uint32_t par = 0, since_sweep = 0;
         for (uint32_t t = group; t < n_tiles; t += n_groups) {
             mbar_wait(&ctl->full[s], par);
             const uint4 k = lds_v4(stages + (size_t)s * HR_TILE + cw * 512 + lane * 16);
             const uint32_t kk[4] = {k.x, k.y, k.z, k.w};
+            if (PACKED16) {
+                // PACKED16 runs with one window (lo == 0).  No branch per key: keys outside the bins
+                // (and the padding of a ragged tile) go to a dummy counter — one word per lane, so
+                // they do not serialise — behind the real ones, which is never flushed or stored.
+                const uint32_t dummy = ((nb + 1u) & ~1u) + 2u * lane;
 #pragma unroll
-            for (int i = 0; i < 4; i++) {
-                const uint32_t a = kk[i] - lo;
-                if (a < nb) {
-                    if (PACKED16) {
-                        atomicAdd(bins + (a >> 1), 1u << ((a & 1u) * 16u));  // result unused: ATOMS without a return trip
-                    } else {
-                        atomicAdd(bins + a, literal);
-                    }
+                for (int i = 0; i < 4; i++) {
+                    // keys in [nb, dummy) are dummy counters too (of lower lanes, or the unused upper
+                    // half of the last word when nb is odd): one VIMNMX instead of compare + select
+                    const uint32_t a = min(kk[i], dummy);
+                    uint32_t addr, val;
+                    asm("mad.lo.u32 %0, %1, 2, %2;" : "=r"(addr) : "r"(a & ~1u), "r"(bins_s));  // word address
+                    asm("mad.lo.u32 %0, %1, 0xffff, 1;" : "=r"(val) : "r"(a & 1u));           // 1 or 0x10000
+                    asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(addr), "r"(val) : "memory");
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    const uint32_t a = kk[i] - lo;
+                    if (a < nb) atomicAdd(bins + a, literal);
                 }
             }
             __syncwarp();
@@ -228,11 +241,11 @@ hist_ring_kernel(const uint32_t* __restrict__ keys, size_t n, uint32_t literal, 
 #pragma unroll
                         for (int i = 0; i < 4; i++) {
                             const uint32_t c = vv[i] & 0xe000e000u;
-                            if (c) {
+                            if (c && w + i < n_words) {  // (the dummy words behind the bins are never flushed)
                                 bins[w + i] = vv[i] - c;
                                 const uint32_t b0 = 2 * (w + i);
                                 if (c & 0xffffu) atomicAdd(dst + lo + b0, c & 0xffffu);
-                                if (c >> 16) atomicAdd(dst + lo + b0 + 1, c >> 16);
+                                if ((c >> 16) && b0 + 1 < nb) atomicAdd(dst + lo + b0 + 1, c >> 16);
                             }
                         }
                     }
@@ -374,7 +387,7 @@ hj_status launch_scatter_reduce(hj_device* dev, hj_reduce_op op, hj_type_kind ty
                 const uint32_t n_groups = (uint32_t)dev->sm_count;
                 const uint32_t n_words = (uint32_t)((n_dst + 1) / 2);
                 HJ_TRY(ensure_hist_scratch(dev, (size_t)n_groups * n_words * 4));
-                const size_t smem = ring + (((size_t)n_words + 3) & ~(size_t)3) * 4;
+                const size_t smem = ring + ((((size_t)n_words + 3) & ~(size_t)3) + 32) * 4;  // + 32 dummy words
                 auto kern = hist_ring_kernel<true>;
                 HJ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
                 kern<<<n_groups, (HR_WARPS + 1) * 32, smem, dev->stream>>>(
