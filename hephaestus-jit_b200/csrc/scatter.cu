@@ -138,11 +138,12 @@ struct HistCtl {
 };
 
 // PACKED16: every HR_SWEEP tiles the consumer warps sweep the counters between two barriers and move
-// the top three bits of each to the bin in HBM.  After a sweep a counter is < 0x2000, a CTA applies
-// at most HR_SWEEP * HR_TILE / 4 = 57344 keys between two sweeps, 0x1fff + 57344 = 0xffff: no
+// the top six bits of each to the bin in HBM.  After a sweep a counter is < 0x400, a CTA applies
+// at most HR_SWEEP * HR_TILE / 4 = 64512 keys between two sweeps, 0x3ff + 64512 = 0xffff: no
 // counter can wrap or carry whatever the key distribution.
-constexpr int HR_SWEEP = 16;
-static_assert(0x1fff + HR_SWEEP * (HR_TILE / 4) <= 0xffff, "a 16-bit counter must survive one sweep period");
+constexpr int HR_SWEEP = 18;
+constexpr uint32_t HR_HIGH = 0xfc00fc00u;
+static_assert((~HR_HIGH & 0xffffu) + HR_SWEEP * (HR_TILE / 4) <= 0xffff, "a 16-bit counter must survive one sweep period");
 template <bool PACKED16>
 __global__ void __launch_bounds__((HR_WARPS + 1) * 32, 1)
 hist_ring_kernel(const uint32_t* __restrict__ keys, size_t n, uint32_t literal, void* __restrict__ out,
@@ -160,7 +161,7 @@ hist_ring_kernel(const uint32_t* __restrict__ keys, size_t n, uint32_t literal, 
     const uint32_t n_tiles = (uint32_t)((n_bytes + HR_TILE - 1) / HR_TILE);
 
     // PACKED16: also the padding the 128-bit sweep reads and the 32 dummy words
-    for (uint32_t b = threadIdx.x; b < (PACKED16 ? ((n_words + 3u) & ~3u) + 32u : n_words); b += blockDim.x) bins[b] = 0;
+    for (uint32_t b = threadIdx.x; b < (PACKED16 ? ((n_words + 3u) & ~3u) : n_words) + 32u; b += blockDim.x) bins[b] = 0;
     if (threadIdx.x == 0) {
         for (int s = 0; s < HR_STAGES; s++) {
             mbar_init(&ctl->full[s], 1);
@@ -220,10 +221,13 @@ hist_ring_kernel(const uint32_t* __restrict__ keys, size_t n, uint32_t literal, 
                     asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(addr), "r"(val) : "memory");
                 }
             } else {
+                // same trick with u32 bins: keys outside this window (below lo they wrap to huge
+                // values) land on the lane's dummy word behind the window
+                const uint32_t dummy = nb + lane;
 #pragma unroll
                 for (int i = 0; i < 4; i++) {
-                    const uint32_t a = kk[i] - lo;
-                    if (a < nb) atomicAdd(bins + a, literal);
+                    const uint32_t a = min(kk[i] - lo, dummy);
+                    asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(bins_s + 4u * a), "r"(literal) : "memory");
                 }
             }
             __syncwarp();
@@ -236,11 +240,11 @@ hist_ring_kernel(const uint32_t* __restrict__ keys, size_t n, uint32_t literal, 
                 asm volatile("bar.sync 1, %0;" ::"n"(HR_WARPS * 32) : "memory");
                 for (uint32_t w = threadIdx.x * 4; w < n_words; w += HR_WARPS * 32 * 4) {
                     uint4 v = *reinterpret_cast<uint4*>(bins + w);
-                    if ((v.x | v.y | v.z | v.w) & 0xe000e000u) {
+                    if ((v.x | v.y | v.z | v.w) & HR_HIGH) {
                         const uint32_t vv[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
                         for (int i = 0; i < 4; i++) {
-                            const uint32_t c = vv[i] & 0xe000e000u;
+                            const uint32_t c = vv[i] & HR_HIGH;
                             if (c && w + i < n_words) {  // (the dummy words behind the bins are never flushed)
                                 bins[w + i] = vv[i] - c;
                                 const uint32_t b0 = 2 * (w + i);
@@ -401,7 +405,7 @@ hj_status launch_scatter_reduce(hj_device* dev, hj_reduce_op op, hj_type_kind ty
             const uint32_t bins_per_part = (uint32_t)((n_dst + parts - 1) / parts);
             const uint32_t n_groups = std::max(1u, (uint32_t)dev->sm_count / parts);
             HJ_TRY(ensure_hist_scratch(dev, (size_t)n_groups * n_dst * 4));
-            const size_t smem = ring + (size_t)bins_per_part * 4;
+            const size_t smem = ring + ((size_t)bins_per_part + 32) * 4;  // + 32 dummy words
             auto kern = hist_ring_kernel<false>;
             HJ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             kern<<<n_groups * parts, (HR_WARPS + 1) * 32, smem, dev->stream>>>(
