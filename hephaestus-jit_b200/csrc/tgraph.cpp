@@ -377,6 +377,8 @@ void launch_graph(const Graph& g, hj_device* dev, const std::vector<VarId>& inpu
             internal[i] = res[i] == nullptr;
             n_internal += internal[i];
         }
+        std::vector<bool> is_output(nres, false);
+        for (uint32_t rid : g.outputs) is_output[rid] = true;
         std::map<std::pair<size_t, TypeId>, std::vector<hj_buffer*>> cache;  // key: pow2-rounded desc
         for (size_t p = 0; p < g.passes.size(); p++) {
             for (uint32_t rid : g.passes[p].resources) {
@@ -394,7 +396,11 @@ void launch_graph(const Graph& g, hj_device* dev, const std::vector<VarId>& inpu
                         res[rid] = create_buffer(dev, rounded);
                     }
                 }
-                if (life[rid].second == p && res[rid]) {
+                // (graph.rs:283-290 re-inserts every dead internal buffer; an OUTPUT of a recorded
+                // function is such a resource once the variables of the first trace are gone, and a
+                // later pass would overwrite it before launch_with hands it back — outputs stay out
+                // of the cache here)
+                if (life[rid].second == p && res[rid] && !is_output[rid]) {
                     hj_buffer_retain(res[rid]);
                     cache[key].push_back(res[rid]);
                 }

@@ -199,6 +199,26 @@ hj_status hj_graph_debug_string(hj_graph* g, char** out) {
         memcpy(*out, s.c_str(), s.size() + 1);
     });
 }
+// Wire format of a compiled graph (tgraph_io.cpp).  *bytes_out is malloc'ed: free with hj_free_string.
+hj_status hj_graph_serialize(hj_graph* g, void** bytes_out, size_t* n_out) {
+    HJ_REQUIRE(g && bytes_out && n_out, "hj_graph_serialize: null argument");
+    return guarded([&] {
+        const std::vector<uint8_t> v = serialize_graph(*g->g);
+        void* p = malloc(v.size());
+        if (!p) throw TraceError("hj_graph_serialize: out of host memory");
+        memcpy(p, v.data(), v.size());
+        *bytes_out = p;
+        *n_out = v.size();
+    });
+}
+hj_status hj_graph_deserialize(hj_device* dev, const void* bytes, size_t n, hj_graph** out) {
+    HJ_REQUIRE(bytes && out, "hj_graph_deserialize: null argument");
+    return guarded([&] {
+        Graph* g = deserialize_graph(dev, bytes, n);
+        *out = new hj_graph();
+        (*out)->g.reset(g);
+    });
+}
 // Graph::launch_with (graph.rs:192-400).  outputs_out receives hj_graph_n_outputs new references.
 hj_status hj_graph_launch(hj_graph* g, hj_device* dev, const uint64_t* inputs, uint32_t n_in, uint64_t* outputs_out,
                           hj_graph_report* report) {

@@ -163,6 +163,9 @@ Graph* compile_graph(ThreadState& ts, const std::vector<VarId>& inputs, const st
 void launch_graph(const Graph& g, hj_device* dev, const std::vector<VarId>& inputs, std::vector<VarId>* outputs,
                   LaunchReport* report, hj_report* backend_report);
 std::string graph_debug_string(const Graph& g);
+// wire format of a compiled graph (tgraph_io.cpp); captured buffers travel with their contents
+std::vector<uint8_t> serialize_graph(const Graph& g);
+Graph* deserialize_graph(hj_device* dev, const void* bytes, size_t n_bytes);
 
 }  // namespace tr
 }  // namespace hj

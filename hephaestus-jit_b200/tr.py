@@ -498,6 +498,22 @@ class Graph:
         lib.hj_free_string(out)
         return s
 
+    def serialize(self) -> bytes:
+        """Wire format of the graph (passes + kernel IR + resources + captured buffer contents);
+        the reference keeps graphs in memory only (graph.rs:145-151)."""
+        out, n = ctypes.c_void_p(), ctypes.c_size_t()
+        check(lib.hj_graph_serialize(self._h, ctypes.byref(out), ctypes.byref(n)))
+        data = ctypes.string_at(out, n.value)
+        lib.hj_free_string(out)
+        return data
+
+    @staticmethod
+    def deserialize(data: bytes, device: "Device | None" = None) -> "Graph":
+        """Rebuild a graph in this process; `device` is needed when it captured buffers."""
+        out = ctypes.c_void_p()
+        check(lib.hj_graph_deserialize(device.handle if device is not None else None, data, len(data), ctypes.byref(out)))
+        return Graph(out.value)
+
     def launch(self, device: Device, timed: bool = False) -> Report:
         return self.launch_with(device, [], timed)[0]
 

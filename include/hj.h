@@ -422,6 +422,13 @@ hj_status hj_graph_retain(hj_graph* g);
 hj_status hj_graph_release(hj_graph* g);
 uint32_t hj_graph_n_passes(hj_graph* g);
 uint32_t hj_graph_n_outputs(hj_graph* g);
+/* Wire format of a compiled graph: passes with their kernel IR, resource table, inputs/outputs and
+ * the contents of captured buffers (the reference keeps graphs in memory only, graph.rs:145-151;
+ * together with the on-disk cubin cache a recorded function starts in a fresh process without
+ * tracing or compiling).  *bytes_out is malloc'ed — free with hj_free_string((char*)bytes).
+ * `dev` of hj_graph_deserialize may be NULL for graphs that capture no buffers. */
+hj_status hj_graph_serialize(hj_graph* g, void** bytes_out, size_t* n_out);
+hj_status hj_graph_deserialize(hj_device* dev, const void* bytes, size_t n, hj_graph** out);
 /* `{:#?}` of the Graph, byte-identical to the reference's insta snapshots; free with hj_free_string */
 hj_status hj_graph_debug_string(hj_graph* g, char** out);
 /* Graph::launch / launch_with (graph.rs:180-400); outputs_out (may be NULL) receives

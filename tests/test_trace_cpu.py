@@ -275,3 +275,51 @@ def test_concurrent_tracing_from_several_threads():
     for t in threads:
         t.join()
     assert not errors, errors
+
+
+# ---- wire format of a compiled graph (csrc/tgraph_io.cpp) --------------------------------
+def _graphs_for_io():
+    x = tr.sized_index(1 << 10).cast(F32)
+    t = x.fma(tr.literal(1.5, F32), tr.literal(0.25, F32))
+    t.sin().select(x.gt(tr.literal(0.0, F32)), t.exp2()).schedule()
+    yield tr.compile()
+    s = tr.sized_index(1000).cast(F32).mul(tr.literal(2.0, F32)).reduce_sum()
+    s.add(tr.literal(1.0, F32)).schedule()
+    yield tr.compile()
+    m = tr.sized_index(64).lt(tr.literal(10, U32))
+    count, idx = m.compress()
+    tr.sized_index(64).prefix_sum(True).schedule()
+    yield tr.compile()
+    del count, idx
+    dyn = tr.sized_index(128).lt(tr.literal(64, U32)).compress_dyn()
+    dyn.add(tr.literal(1, U32)).schedule()
+    yield tr.compile()
+    # composite types travel through the type table
+    v = tr.vec([tr.sized_literal(1.0, 16, F32), tr.literal(2.0, F32), tr.literal(3.0, F32)])
+    v.schedule()
+    yield tr.compile()
+
+
+def test_graph_serialize_round_trip():
+    for g in _graphs_for_io():
+        blob = g.serialize()
+        assert blob[:8] == b"HJGRAPH1"
+        h = tr.Graph.deserialize(blob)
+        assert h.n_passes() == g.n_passes()
+        assert h.debug_string() == g.debug_string()
+        assert h.serialize() == blob  # canonical: a second trip is byte-identical
+        del h, g
+        gc.collect()
+
+
+def test_graph_deserialize_rejects_damaged_input():
+    tr.sized_index(256).add(tr.literal(3, U32)).schedule()
+    blob = tr.compile().serialize()
+    with pytest.raises(hj.HjError, match="not a serialised graph"):
+        tr.Graph.deserialize(b"nonsense" + blob[8:])
+    with pytest.raises(hj.HjError, match="checksum"):
+        tr.Graph.deserialize(blob[:40] + bytes([blob[40] ^ 1]) + blob[41:])
+    with pytest.raises(hj.HjError):
+        tr.Graph.deserialize(blob[: len(blob) // 2])
+    with pytest.raises(hj.HjError):
+        tr.Graph.deserialize(b"")

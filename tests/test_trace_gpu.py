@@ -546,3 +546,115 @@ def test_wavefront_example(device):  # test.rs:1020-1062 (prints only in the ref
         alive = alive & (want > np.float32(0.1))
     assert np.array_equal(a2.to_vec(), want)
     assert np.array_equal(mask2.to_vec(np.bool_), alive)
+
+
+# ---- wire format of a compiled graph (csrc/tgraph_io.cpp) --------------------------------
+def _traced_pipeline(x, table):
+    """kernel -> reduce -> kernel -> scan -> compress_dyn-sized kernel, with a captured table."""
+    y = x.mul(tr.literal(3, U32)).add(table.gather(x.and_(tr.literal(255, U32))))
+    total = y.reduce_sum()
+    z = y.add(total.gather(tr.literal(0, U32)))  # element 0 for every lane
+    scan = z.prefix_sum(True)
+    idx = y.and_(tr.literal(1, U32)).eq(tr.literal(1, U32)).compress_dyn()
+    picked = y.gather(idx)
+    return [z, scan, picked]
+
+
+def _pipeline_expected(xs, tab):
+    y = (xs * np.uint32(3) + tab[xs & 255]).astype(np.uint32)
+    z = (y + y.sum(dtype=np.uint32)).astype(np.uint32)
+    return z, np.cumsum(z, dtype=np.uint32), y[(y & 1) == 1]
+
+
+def test_graph_serialize_launch_matches(device, tmp_path):
+    rng = np.random.Generator(np.random.PCG64(5))
+    n = 100_003
+    xs = rng.integers(0, 1 << 20, size=n).astype(np.uint32)
+    tab = rng.integers(0, 1 << 16, size=256).astype(np.uint32)
+    x, table = tr.array(xs, device), tr.array(tab, device)
+    outs = _traced_pipeline(x, table)
+    graph = tr.compile_fn([x], outs)
+    n_picked = int(((xs * np.uint32(3) + tab[xs & 255]).astype(np.uint32) & 1).sum())
+    del outs
+    blob = graph.serialize()
+    assert len(blob) > 256 * 4  # the captured table travels with the graph
+    loaded = tr.Graph.deserialize(blob, device)
+    assert loaded.n_passes() == graph.n_passes() and loaded.debug_string() == graph.debug_string()
+    # other inputs than the ones it was traced with, several launches (the second and third replay
+    # one captured CUDA graph)
+    for seed in (6, 7, 8):
+        xs2 = np.random.Generator(np.random.PCG64(seed)).integers(0, 1 << 20, size=n).astype(np.uint32)
+        x2 = tr.array(xs2, device)
+        want = _pipeline_expected(xs2, tab)
+        for g in (graph, loaded):
+            _, (z, scan, picked) = g.launch_with(device, [x2])
+            assert np.array_equal(z.to_vec(np.uint32), want[0])
+            assert np.array_equal(scan.to_vec(np.uint32), want[1])
+            assert np.array_equal(picked.to_vec(np.uint32)[: len(want[2])], want[2])
+            del z, scan, picked
+        del x2
+    assert n_picked > 0
+    del graph, loaded, x, table
+
+
+def test_graph_serialize_fresh_process(device, tmp_path):
+    """A second process launches the graph from the file alone: no tracing, no scheduling; its
+    kernels come out of the on-disk cubin cache the first process filled."""
+    import subprocess
+    import sys
+
+    rng = np.random.Generator(np.random.PCG64(9))
+    n = 65_537
+    xs = rng.integers(0, 1 << 20, size=n).astype(np.uint32)
+    tab = rng.integers(0, 1 << 16, size=256).astype(np.uint32)
+    x, table = tr.array(xs, device), tr.array(tab, device)
+    outs = _traced_pipeline(x, table)
+    graph = tr.compile_fn([x], outs)
+    del outs
+    graph.launch_with(device, [x])  # compiles the kernels -> cubins land in the disk cache
+    path = tmp_path / "pipeline.hjgraph"
+    path.write_bytes(graph.serialize())
+    np.save(tmp_path / "x.npy", xs)
+    del graph, x, table
+    script = f"""
+import importlib, sys, numpy as np
+sys.path.insert(0, {os.path.dirname(HERE)!r})
+hj = importlib.import_module("hephaestus-jit_b200"); tr = importlib.import_module("hephaestus-jit_b200.tr")
+dev = hj.Device.cuda(0)
+g = tr.Graph.deserialize(open({str(path)!r}, "rb").read(), dev)
+x = tr.array(np.load({str(tmp_path / "x.npy")!r}), dev)
+_, (z, scan, picked) = g.launch_with(dev, [x])
+np.save({str(tmp_path / "z.npy")!r}, z.to_vec(np.uint32)); np.save({str(tmp_path / "scan.npy")!r}, scan.to_vec(np.uint32))
+np.save({str(tmp_path / "picked.npy")!r}, picked.to_vec(np.uint32))
+print("STATS", dev.kernel_cache_stats())
+"""
+    out = subprocess.run([sys.executable, "-c", script], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    assert "STATS" in out.stdout
+    want = _pipeline_expected(xs, tab)
+    assert np.array_equal(np.load(tmp_path / "z.npy"), want[0])
+    assert np.array_equal(np.load(tmp_path / "scan.npy"), want[1])
+    assert np.array_equal(np.load(tmp_path / "picked.npy")[: len(want[2])], want[2])
+
+
+def test_record_outputs_survive_later_passes(device):
+    """An output produced by an early pass must not be handed to a later pass as a temporary when
+    the recorded graph is re-launched (the reference's lifetime aliasing, graph.rs:237-296, re-inserts
+    every dead internal buffer; outputs are kept out of that cache here)."""
+    def fn(a):
+        early = a.add(tr.literal(1, U32))
+        early.schedule()
+        s = a.prefix_sum(True)             # device op: closes the group
+        t1 = s.mul(tr.literal(2, U32))     # same-size temporaries of later passes
+        s2 = t1.prefix_sum(True)
+        late = s2.add(tr.literal(5, U32))
+        return [early, late]
+
+    f = rec.record(fn)
+    for seed in range(4):
+        xs = np.random.Generator(np.random.PCG64(seed)).integers(0, 100, size=4096).astype(np.uint32)
+        (early, late), _ = f(device, tr.array(xs, device))
+        want_late = np.cumsum(np.cumsum(xs, dtype=np.uint32) * np.uint32(2), dtype=np.uint32) + np.uint32(5)
+        assert np.array_equal(early.to_vec(np.uint32), xs + 1), f"call {seed}: early output overwritten"
+        assert np.array_equal(late.to_vec(np.uint32), want_late)
+        del early, late
