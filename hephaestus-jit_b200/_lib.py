@@ -153,6 +153,7 @@ _SIGS = {
     "hj_sharded_prefix_sum": (_i32, [_vp, _i32, _sz, _i32, _vp, _vp]),
     "hj_sharded_compress": (_i32, [_vp, _sz, _u32, _vp, _vp, _vp, _vp]),
     "hj_sharded_scatter_reduce": (_i32, [_vp, _i32, _i32, _sz, _vp, _vp, _u64, _vp, _sz]),
+    "hj_sharded_rebalance": (_i32, [_vp, _sz, _vp, _vp, _vp, _vp, ctypes.POINTER(_u64)]),
     # ---- trace / schedule / graph
     "hj_tr_type_scalar": (_u32, [_u32]),
     "hj_tr_type_vector": (_u32, [_u32, _u32]),

@@ -49,6 +49,10 @@ struct NcclApi {
     ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
     ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
     const char* (*GetErrorString)(ncclResult_t) = nullptr;
     std::string error;
 };
@@ -71,6 +75,10 @@ NcclApi& nccl() {
         HJ_SYM(CommDestroy, "ncclCommDestroy")
         HJ_SYM(AllGather, "ncclAllGather")
         HJ_SYM(AllReduce, "ncclAllReduce")
+        HJ_SYM(Send, "ncclSend")
+        HJ_SYM(Recv, "ncclRecv")
+        HJ_SYM(GroupStart, "ncclGroupStart")
+        HJ_SYM(GroupEnd, "ncclGroupEnd")
         HJ_SYM(GetErrorString, "ncclGetErrorString")
 #undef HJ_SYM
     });
@@ -404,6 +412,68 @@ hj_status hj_sharded_scatter_reduce(hj_comm* c, hj_reduce_op op, hj_type_kind ty
     hj_status s = check_launch(c->dev, "fold_ranks_kernel");
     cudaFreeAsync(all, c->dev->stream);
     return s;
+}
+
+// Re-partition a sharded, compacted sequence evenly (the step after compress_dyn in a
+// multi-GPU wavefront loop).  Rank q holds counts[q] elements; the global sequence is their
+// concatenation in rank order.  Afterwards rank r holds the contiguous block
+// [r*T/W + min(r, T%W), ...) of it (sizes differ by at most one, order preserved) in `dst`.
+// The counts are read back to the host once (W x 4 bytes): the caller sizes its next launches
+// from *new_count_host anyway; the payload moves GPU to GPU over NVLink as grouped ncclSend /
+// ncclRecv of exactly the overlapping slices — every element crosses the fabric at most once
+// and elements that stay on their rank are one device-to-device copy.
+hj_status hj_sharded_rebalance(hj_comm* c, size_t elem_bytes, hj_buffer* src, hj_buffer* counts, hj_buffer* dst,
+                               hj_buffer* out_count, uint64_t* new_count_host) {
+    HJ_REQUIRE(c && src && counts && dst, "hj_sharded_rebalance: null argument");
+    HJ_REQUIRE(elem_bytes >= 1 && elem_bytes <= 64, "hj_sharded_rebalance: bad element size");
+    HJ_REQUIRE(counts->bytes >= 4 * (size_t)c->world, "hj_sharded_rebalance: counts too small");
+    HJ_REQUIRE(!out_count || out_count->bytes >= 4, "hj_sharded_rebalance: out_count too small");
+    DeviceGuard g(c->dev);
+    const int W = c->world, me = c->rank;
+    std::vector<uint32_t> cnt(W);
+    HJ_CUDA(cudaMemcpyAsync(cnt.data(), counts->ptr, 4 * (size_t)W, cudaMemcpyDeviceToHost, c->dev->stream));
+    HJ_CUDA(cudaStreamSynchronize(c->dev->stream));
+    std::vector<uint64_t> src0(W + 1, 0), dst0(W + 1, 0);  // source / target block boundaries
+    for (int q = 0; q < W; q++) src0[q + 1] = src0[q] + cnt[q];
+    const uint64_t T = src0[W], base = T / W, rem = T % W;
+    for (int q = 0; q <= W; q++) dst0[q] = (uint64_t)q * base + ((uint64_t)q < rem ? (uint64_t)q : rem);
+    const uint64_t mine = dst0[me + 1] - dst0[me];
+    HJ_REQUIRE((uint64_t)cnt[me] * elem_bytes <= src->bytes, "hj_sharded_rebalance: counts[rank] exceeds src");
+    HJ_REQUIRE(mine * elem_bytes <= dst->bytes, "hj_sharded_rebalance: dst holds %zu bytes, the balanced block needs %llu",
+               dst->bytes, (unsigned long long)(mine * elem_bytes));
+    if (W > 1) HJ_TRY(need_nccl());
+    auto overlap = [](uint64_t a0, uint64_t a1, uint64_t b0, uint64_t b1, uint64_t* lo, uint64_t* hi) {
+        *lo = a0 > b0 ? a0 : b0;
+        *hi = a1 < b1 ? a1 : b1;
+        return *lo < *hi;
+    };
+    uint64_t lo, hi;
+    if (overlap(src0[me], src0[me + 1], dst0[me], dst0[me + 1], &lo, &hi))  // what stays here
+        HJ_CUDA(cudaMemcpyAsync((char*)dst->ptr + (lo - dst0[me]) * elem_bytes, (const char*)src->ptr + (lo - src0[me]) * elem_bytes,
+                                (hi - lo) * elem_bytes, cudaMemcpyDeviceToDevice, c->dev->stream));
+    if (W > 1) {
+        HJ_NCCL(nccl().GroupStart());
+        ncclResult_t r = ncclSuccess;
+        for (int q = 0; q < W && r == ncclSuccess; q++) {
+            if (q == me) continue;
+            if (overlap(src0[me], src0[me + 1], dst0[q], dst0[q + 1], &lo, &hi))  // my elements in q's block
+                r = nccl().Send((const char*)src->ptr + (lo - src0[me]) * elem_bytes, (hi - lo) * elem_bytes, ncclUint8, q, c->comm,
+                                c->dev->stream);
+            if (r == ncclSuccess && overlap(src0[q], src0[q + 1], dst0[me], dst0[me + 1], &lo, &hi))  // q's elements in mine
+                r = nccl().Recv((char*)dst->ptr + (lo - dst0[me]) * elem_bytes, (hi - lo) * elem_bytes, ncclUint8, q, c->comm,
+                                c->dev->stream);
+        }
+        const ncclResult_t e = nccl().GroupEnd();
+        HJ_NCCL(r);
+        HJ_NCCL(e);
+    }
+    if (out_count) {
+        const uint32_t m32 = (uint32_t)mine;
+        HJ_CUDA(cudaMemcpyAsync(out_count->ptr, &m32, 4, cudaMemcpyHostToDevice, c->dev->stream));
+        HJ_CUDA(cudaStreamSynchronize(c->dev->stream));  // m32 lives on this stack frame
+    }
+    if (new_count_host) *new_count_host = mine;
+    return HJ_OK;
 }
 
 }  // extern "C"

@@ -86,6 +86,34 @@ class Comm:
         check(lib.hj_sharded_scatter_reduce(self._h, op, ty, n_local, idx.handle,
                                             src.handle if src else None, lit, dst.handle, n_dst))
 
+    def rebalance(self, elem_bytes: int, src: Buffer, counts: Buffer, dst: Buffer,
+                  out_count: Buffer | None = None) -> int:
+        """Even re-partition of a sharded compacted sequence (order preserved); returns this
+        rank's new element count."""
+        n = ctypes.c_uint64()
+        check(lib.hj_sharded_rebalance(self._h, elem_bytes, src.handle, counts.handle, dst.handle,
+                                       out_count.handle if out_count else None, ctypes.byref(n)))
+        return n.value
+
+
+def rebalance_plan(counts, rank: int):
+    """What rank ``rank`` sends and receives when the concatenation of per-rank segments of lengths
+    ``counts`` is re-partitioned into ``shard_bounds`` blocks: two lists of
+    ``(peer, offset in my segment / my block, length)``; ``peer == rank`` is the local copy."""
+    world = len(counts)
+    src0 = [0] + list(np.cumsum(np.asarray(counts, dtype=np.int64)))
+    total = int(src0[-1])
+    dst = [shard_bounds(total, world, q) for q in range(world)]
+    sends, recvs = [], []
+    for q in range(world):
+        lo, hi = max(src0[rank], dst[q][0]), min(src0[rank + 1], dst[q][1])
+        if lo < hi:
+            sends.append((q, int(lo - src0[rank]), int(hi - lo)))
+        lo, hi = max(src0[q], dst[rank][0]), min(src0[q + 1], dst[rank][1])
+        if lo < hi:
+            recvs.append((q, int(lo - dst[rank][0]), int(hi - lo)))
+    return sends, recvs
+
 
 # ---- the exchange protocol on host tensors (any backend; used by the gloo tests) ---------------
 
@@ -121,3 +149,36 @@ def exchange_counts(local_count: int):
     """All-gather the per-rank compaction counts: (counts, exclusive offsets, global count)."""
     counts = [int(c) for c in _all_gather_scalar(np.uint32(local_count))]
     return counts, exclusive_offsets(counts), sum(counts)
+
+
+def exchange_rebalance(local: np.ndarray) -> np.ndarray:
+    """Host statement of ``hj_sharded_rebalance``: all-gather the counts, then point-to-point
+    transfers of exactly the overlapping slices."""
+    import torch
+    import torch.distributed as dist
+    rank = dist.get_rank()
+    counts, _, total = exchange_counts(len(local))
+    lo, hi = shard_bounds(total, len(counts), rank)
+    out = np.empty(hi - lo, dtype=local.dtype)
+    sends, recvs = rebalance_plan(counts, rank)
+    ops, keep = [], []
+    for peer, off, n in recvs:
+        if peer == rank:
+            continue
+        t = torch.empty(n * local.dtype.itemsize, dtype=torch.uint8)
+        keep.append((t, off, n))
+        ops.append(dist.P2POp(dist.irecv, t, peer))
+    for peer, off, n in sends:
+        if peer == rank:
+            src_off = off
+            dst_off = next(o for p, o, _ in recvs if p == rank)
+            out[dst_off:dst_off + n] = local[src_off:src_off + n]
+            continue
+        t = torch.from_numpy(np.frombuffer(local[off:off + n].tobytes(), dtype=np.uint8).copy())
+        ops.append(dist.P2POp(dist.isend, t, peer))
+    if ops:
+        for w in dist.batch_isend_irecv(ops):
+            w.wait()
+    for t, off, n in keep:
+        out[off:off + n] = np.frombuffer(t.numpy().tobytes(), dtype=local.dtype)
+    return out

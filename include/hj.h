@@ -328,6 +328,13 @@ hj_status hj_sharded_compress(hj_comm* comm, size_t n_local, uint32_t index_base
 hj_status hj_sharded_scatter_reduce(hj_comm* comm, hj_reduce_op op, hj_type_kind ty,
                                     size_t n_local, hj_buffer* idx, hj_buffer* src,
                                     uint64_t literal, hj_buffer* dst, size_t n_dst);
+/* Re-partition a sharded compacted sequence evenly over the ranks, order preserved: rank q holds
+ * counts[q] elements of `elem_bytes` in `src` (counts: u32[world] on the device, as written by
+ * hj_sharded_compress); afterwards `dst` holds this rank's block of the concatenated sequence,
+ * out_count[0] (device u32, may be NULL) and *new_count_host (may be NULL) its length.  Block
+ * boundaries are q*T/W + min(q, T%W).  Slices move GPU to GPU (grouped ncclSend/ncclRecv). */
+hj_status hj_sharded_rebalance(hj_comm* comm, size_t elem_bytes, hj_buffer* src, hj_buffer* counts,
+                               hj_buffer* dst, hj_buffer* out_count, uint64_t* new_count_host);
 
 /* ---- trace / schedule / graph (host side) ------------------------------------------------
  * C++ restatement of the layers ABOVE the backend traits, so that programs written against

@@ -31,6 +31,30 @@ def test_exclusive_offsets():
         assert [int(x) for x in off] == [0, 0xFFFFFFFF, 1]  # wraps like the device arithmetic
 
 
+def test_rebalance_plan_moves_every_element_once():
+    rng = np.random.Generator(np.random.PCG64(3))
+    for world in (1, 2, 3, 4, 8):
+        for counts in ([0] * world, [5] * world, [100] + [0] * (world - 1), [0] * (world - 1) + [17],
+                       list(rng.integers(0, 1000, size=world))):
+            total = int(sum(counts))
+            sent = 0
+            inbox = {r: [] for r in range(world)}
+            for r in range(world):
+                sends, recvs = sharded.rebalance_plan(counts, r)
+                # my sends tile my segment, my receives tile my block, both in order
+                assert [o for _, o, _ in sends] == list(np.cumsum([0] + [n for _, _, n in sends[:-1]])) if sends else True
+                assert sum(n for _, _, n in sends) == counts[r]
+                lo, hi = sharded.shard_bounds(total, world, r)
+                assert sum(n for _, _, n in recvs) == hi - lo
+                sent += sum(n for _, _, n in sends)
+                for peer, _, n in sends:
+                    inbox[peer].append((r, n))
+            assert sent == total
+            for r in range(world):  # what the peers send to r is what r expects to receive
+                _, recvs = sharded.rebalance_plan(counts, r)
+                assert inbox[r] == [(p, n) for p, _, n in recvs]
+
+
 def _free_port():
     with socket.socket() as s:
         s.bind(("127.0.0.1", 0))
@@ -75,6 +99,14 @@ def _worker(rank, world, port, n):
         gcnt, gidx = oracle.compress(mask)
         assert total == gcnt and counts[rank] == cnt
         assert np.array_equal(idx[:cnt], gidx[offsets[rank]: offsets[rank] + cnt])
+
+        # rebalance: a skewed compaction (most survivors on the first ranks) re-partitioned evenly
+        skew = (rng.random(n) < np.linspace(0.9, 0.02, n)).astype(np.uint8)
+        cnt, idx = oracle.compress(skew[s:e], index_base=s)
+        gcnt, gidx = oracle.compress(skew)
+        mine = sh.exchange_rebalance(idx[:cnt])
+        lo, hi = sh.shard_bounds(gcnt, world, rank)
+        assert np.array_equal(mine, gidx[lo:hi])
     finally:
         dist.destroy_process_group()
 

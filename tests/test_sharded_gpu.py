@@ -62,11 +62,24 @@ def _worker(rank, world, uid, n):
         want = np.zeros(1 << 10, np.uint32)
         np.bitwise_or.at(want, keys & 1023, u)
         assert np.array_equal(ored.to_host(np.uint32), want)
+        # rebalance: a skewed compaction re-partitioned evenly, order preserved
+        skew = (rng.random(n) < np.linspace(0.9, 0.02, n)).astype(np.uint8)
+        idx = dev.create_buffer_from_slice(np.zeros(nl, np.uint32))
+        comm.compress(nl, s, dev.create_buffer_from_slice(skew[s:e]), idx, cnt, counts)
+        gcnt, gidx = oracle.compress(skew)
+        lo, hi = sh.shard_bounds(gcnt, world, rank)
+        bal, new_cnt = dev.create_buffer(4 * max(hi - lo, 1)), dev.create_buffer(4)
+        got = comm.rebalance(4, idx, counts, bal, new_cnt)
+        assert got == hi - lo and int(new_cnt.to_host(np.uint32)[0]) == hi - lo
+        assert np.array_equal(bal.to_host(np.uint32)[: hi - lo], gidx[lo:hi])
+        small = dev.create_buffer(4)
+        with pytest.raises(hjw.HjError, match="balanced block"):
+            comm.rebalance(4, idx, counts, small, None)
     finally:
         comm.destroy()
 
 
-@pytest.mark.parametrize("world", [2, 4, 8])
+@pytest.mark.parametrize("world", [1, 2, 4, 8])
 def test_sharded_ops_match_oracle(world):
     if hj.device_count() < world:
         pytest.skip(f"needs {world} GPUs")
