@@ -473,7 +473,7 @@ def run_own(args):
     block_s = time_e2e(e2e_blocking)
     e2e = {"value": world * nbytes_step / pipe_s / 1e9, "unit": "GB/s", "h2d_bytes_per_step": 4 * n,
            "d2h_bytes_per_step": 4 * n, "ms_per_step": pipe_s * 1e3, "steps": e2e_steps,
-           "path": "pinned host arrays -> hj_kernel_map_host (8 Mi-element chunks: upload | kernel | download streams)",
+           "path": "pinned host arrays -> hj_kernel_map_host (8 Mi-element chunks, ramped at both ends: upload | kernel | download streams)",
            "kernel_launches_per_step": int(launches_e2e), "oracle_check": e2e_ok,
            "blocking_path": {"value": world * nbytes_step / block_s / 1e9, "ms_per_step": block_s * 1e3,
                              "path": "hj_buffer_upload (pinned) -> hj_execute_graph -> hj_buffer_to_host"}}

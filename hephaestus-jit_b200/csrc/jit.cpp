@@ -304,11 +304,33 @@ hj_status hj_kernel_map_host(hj_device* dev, hj_kernel* k, size_t n, void* const
         HJ_CUDA(cudaStreamWaitEvent(s_k, start, 0));
         HJ_CUDA(cudaStreamWaitEvent(s_down, start, 0));
     }
-    const size_t n_chunks = (n + chunk_elems - 1) / chunk_elems;
+    // Chunk schedule: the pipeline's fill (first upload) and drain (last download) cannot overlap
+    // with traffic in the other direction, so the first and last chunks are small (1/8, 1/4, 1/2 of
+    // a full chunk on the way in, mirrored on the way out) and only the middle runs at full size.
+    std::vector<std::pair<size_t, size_t>> chunks;  // (first element, count)
+    {
+        static const bool ramp = !getenv("HJ_MAP_NO_RAMP");
+        size_t left = n;
+        auto take = [&](size_t c) {
+            c = std::min(c, left);
+            if (c) {
+                chunks.emplace_back(n - left, c);
+                left -= c;
+            }
+        };
+        if (ramp && n >= 4 * chunk_elems) {
+            const size_t tail_total = chunk_elems / 2 + chunk_elems / 4 + chunk_elems / 8;
+            for (size_t div = 8; div >= 2; div /= 2) take(chunk_elems / div);
+            while (left > tail_total) take(std::min(chunk_elems, left - tail_total));
+            for (size_t div = 2; div <= 8; div *= 2) take(chunk_elems / div);
+        }
+        while (left) take(chunk_elems);
+    }
+    const size_t n_chunks = chunks.size();
     for (size_t c = 0; c < n_chunks && st == HJ_OK; c++) {
         const int d = (int)(c % DEPTH);
-        const size_t first = c * chunk_elems;
-        const size_t count = std::min(chunk_elems, n - first);
+        const size_t first = chunks[c].first;
+        const size_t count = chunks[c].second;
         char** bufs = &dbuf[(size_t)d * n_arrays];
         // the slot is free once the chunk that used it DEPTH steps ago has been downloaded
         if (c >= DEPTH) cudaStreamWaitEvent(s_up, down_done[d], 0);
