@@ -141,8 +141,12 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": gbs, "unit": "GB/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "C2 fused elementwise chain fma->sin/exp2->select over f32, CPU sample 2^24 elements/step",
-                   "note": "reference (nightly Rust + Vulkan/lavapipe) is not buildable in this image; oracle port timed instead"},
+        "config": {
+            # the own arm's config (same workload, same metric and unit); what one CPU step covers is in `sample`
+            "workload": "C2: fused elementwise chain fma -> sin/exp2 -> select over 2^28 f32 per GPU, one NVRTC kernel",
+            "elements_per_gpu": 1 << 28, "bytes_per_element": BYTES_PER_ELEM,
+            "sample": "each step = 2^24 of the 2^28 elements on the host cores",
+            "note": "reference (nightly Rust + Vulkan/lavapipe) is not buildable in this image; oracle port timed instead"},
         "cpu_baseline": {"value": gbs, "unit": "GB/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": gbs, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -342,6 +346,8 @@ def run_own(args):
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        # NCCL's own banner (NCCL_DEBUG=VERSION/INFO) goes to stdout by default: keep stdout for the JSON line
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     torch.cuda.set_device(local_rank)
 
