@@ -310,6 +310,9 @@ def test_histogram_bit_exact(dev, n_bins):
     (100_000, 1, "uniform"),   # more than 2^16 bins: four windows, ragged last window
     (40_000, 1, "oob"),        # keys >= n_dst are ignored
     (1 << 15, 1, "uniform"),   # one window holding every bin
+    (40_001, 1, "oob"),        # odd bin count, packed counters: the unused upper half of the last word takes key == n_dst
+    (50_001, 1, "edge"),       # every key is n_dst - 1 or n_dst: the last real counter and its out-of-range neighbour
+    (99_999, 5, "oob"),        # odd windows, literal != 1, half the keys out of range (dummy words behind each window)
 ])
 def test_histogram_ring_paths_bit_exact(dev, n_bins, literal, dist):
     n = (1 << 22) + 12345
@@ -319,6 +322,8 @@ def test_histogram_ring_paths_bit_exact(dev, n_bins, literal, dist):
     elif dist == "oob":
         keys = rng.integers(0, 2 * n_bins, size=n).astype(np.uint32)
         keys[::1001] = 0xFFFFFFFF
+    elif dist == "edge":
+        keys = np.where(rng.random(n) < 0.5, n_bins - 1, n_bins).astype(np.uint32)
     else:
         keys = rng.integers(0, n_bins, size=n).astype(np.uint32)
     init = rng.integers(0, 1000, size=n_bins).astype(np.uint32)
