@@ -28,6 +28,29 @@ __device__ __forceinline__ unsigned long long ld_sys_u64(const unsigned long lon
     return v;
 }
 
+// The two halves of an exchange, for callers that split them over different threads (a thread that
+// only polls has no remote store outstanding when it fences afterwards).
+__device__ __forceinline__ void peer_send(const PeerView& pv, uint32_t epoch, unsigned long long bits, int peer) {
+    const size_t parity_off = (size_t)(epoch & 1u) * pv.world * 2;
+    unsigned long long* remote = pv.box[peer] + parity_off + (size_t)pv.rank * 2;
+    st_sys_u64(remote, (bits << 32) | epoch);
+    st_sys_u64(remote + 1, (bits & 0xffffffff00000000ull) | epoch);
+}
+__device__ __forceinline__ unsigned long long peer_wait(const PeerView& pv, uint32_t epoch, int peer) {
+    const size_t parity_off = (size_t)(epoch & 1u) * pv.world * 2;
+    const unsigned long long* mine = pv.box[pv.rank] + parity_off + (size_t)peer * 2;
+    unsigned long long w0, w1;
+    unsigned ns = 20;
+    while (true) {
+        w0 = ld_sys_u64(mine);
+        w1 = ld_sys_u64(mine + 1);
+        if ((uint32_t)w0 == epoch && (uint32_t)w1 == epoch) break;
+        __nanosleep(ns);
+        if (ns < 1000) ns *= 2;
+    }
+    return (w0 >> 32) | (w1 & 0xffffffff00000000ull);
+}
+
 // Executed by threads 0 .. world-1 of one CTA: thread `peer` sends `bits` (this rank's value) to
 // rank `peer` and returns the value rank `peer` sent here.
 __device__ __forceinline__ unsigned long long peer_exchange(const PeerView& pv, uint32_t epoch, unsigned long long bits,

@@ -62,6 +62,22 @@ def _worker(rank, world, uid, n):
         want = np.zeros(1 << 10, np.uint32)
         np.bitwise_or.at(want, keys & 1023, u)
         assert np.array_equal(ored.to_host(np.uint32), want)
+        # array exchange over peer memory with other types / operators, and repeated calls (box parities)
+        for rep in range(3):
+            fv = rng.random(n, dtype=np.float32)
+            facc = dev.create_buffer_from_slice(np.zeros(4096, np.float32))
+            comm.scatter_reduce(hjw.SUM, hjw.F32, nl, dev.create_buffer_from_slice(keys[s:e] & 4095),
+                                dev.create_buffer_from_slice(fv[s:e]), 0.0, facc, 4096)
+            wantf = np.zeros(4096, np.float64)
+            np.add.at(wantf, keys & 4095, fv.astype(np.float64))
+            assert np.allclose(facc.to_host(np.float32), wantf, rtol=1e-4)
+            iv = rng.integers(-2**31, 2**31, size=n, dtype=np.int64).astype(np.int32)
+            imin = dev.create_buffer_from_slice(np.full(2048, 2**31 - 1, np.int32))
+            comm.scatter_reduce(hjw.MIN, hjw.I32, nl, dev.create_buffer_from_slice(keys[s:e] & 2047),
+                                dev.create_buffer_from_slice(iv[s:e]), 0, imin, 2048)
+            wanti = np.full(2048, 2**31 - 1, np.int32)
+            np.minimum.at(wanti, keys & 2047, iv)
+            assert np.array_equal(imin.to_host(np.int32), wanti)
         # rebalance: a skewed compaction re-partitioned evenly, order preserved
         skew = (rng.random(n) < np.linspace(0.9, 0.02, n)).astype(np.uint8)
         idx = dev.create_buffer_from_slice(np.zeros(nl, np.uint32))
