@@ -12,7 +12,7 @@
 //! source a maintainer drops into the reference tree.  Every call it makes is exercised here through
 //! the ctypes mirror (hephaestus-jit_b200/__init__.py) and the C++ restatement of `launch_with`
 //! (csrc/tgraph.cpp), which flattens passes exactly as `execute_graph` below does.
-mod ffi;
+mod ffi; // = bindings/rust/backend_cuda_ffi.rs, installed as backend/cuda/ffi.rs
 
 use std::collections::HashMap;
 use std::ffi::CStr;
