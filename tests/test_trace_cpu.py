@@ -323,3 +323,15 @@ def test_graph_deserialize_rejects_damaged_input():
         tr.Graph.deserialize(blob[: len(blob) // 2])
     with pytest.raises(hj.HjError):
         tr.Graph.deserialize(b"")
+
+
+def test_graph_wire_format_is_stable():
+    """A blob written by an earlier build (tests/golden/graph_wire_v1.hjgraph: C2 chain -> reduce_sum,
+    plus a compress_dyn-sized kernel) still loads and means the same graph."""
+    with open(os.path.join(HERE, "golden", "graph_wire_v1.hjgraph"), "rb") as f:
+        blob = f.read()
+    with open(os.path.join(HERE, "golden", "graph_wire_v1.debug.txt")) as f:
+        want = f.read()
+    g = tr.Graph.deserialize(blob)
+    assert g.debug_string() == want
+    assert g.serialize() == blob
