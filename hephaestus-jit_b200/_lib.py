@@ -188,6 +188,7 @@ _SIGS = {
     "hj_tr_extract_dyn": (_i32, [_u64, _u64, _pu64]),
     "hj_tr_composite": (_i32, [_pu64, _u32, _pu64]),
     "hj_tr_vec": (_i32, [_pu64, _u32, _pu64]),
+    "hj_tr_mat": (_i32, [_pu64, _u32, _pu64]),
     "hj_tr_arr": (_i32, [_pu64, _u32, _pu64]),
     "hj_tr_gather": (_i32, [_u64, _u64, _u64, _pu64]),
     "hj_tr_scatter": (_i32, [_u64, _u64, _u64, _u64]),

@@ -446,6 +446,15 @@ struct Gen {
                     if (var.arg == HJ_BOP_INNER && ak == HJ_VEC && is_scalar_kind(kind)) {  // dot, glsl/mod.rs:805-813
                         o << "    " << r << " = (" << T << ")0;\n    for (int k = 0; k < " << n_components(at) << "; k++) " << r
                           << " = (" << T << ")(" << r << " + " << rd(0) << ".e[k] * " << rd(1) << ".e[k]);\n";
+                    } else if (var.arg == HJ_BOP_MUL && ak == HJ_MAT && v.type(at).cols == v.type(at).rows) {
+                        // GLSL `*` on matrices is the linear-algebra product (glsl/mod.rs emits `a * b`),
+                        // column-major: (A*B)[c][q] = sum_k A[k][q] * B[c][k]; operands share one type
+                        // (trace.rs asserts it), so the matrices are square
+                        const uint32_t nn = v.type(at).rows;
+                        o << "    for (int c = 0; c < " << nn << "; c++) for (int q = 0; q < " << nn << "; q++) {\n        "
+                          << tname(v.type(at).elem) << " acc = 0;\n        for (int k = 0; k < " << nn << "; k++) acc += " << rd(0)
+                          << ".e[k * " << nn << " + q] * " << rd(1) << ".e[c * " << nn << " + k];\n        " << r << ".e[c * " << nn
+                          << " + q] = acc;\n    }\n";
                     } else if (var.arg == HJ_BOP_EQ || var.arg == HJ_BOP_NEQ) {  // GLSL ==/!= on aggregates -> bool
                         o << "    " << r << " = true;\n    for (int k = 0; k < " << n_components(at) << "; k++) " << r << " = " << r
                           << " && (" << rd(0) << ".e[k] == " << rd(1) << ".e[k]);\n";

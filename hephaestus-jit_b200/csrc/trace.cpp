@@ -397,6 +397,12 @@ VarId composite(const std::vector<VarId>& refs) {  // trace.rs:675-693
 }
 VarId vec(const std::vector<VarId>& refs) { return construct(type_vector(type_of(refs.at(0)), (uint32_t)refs.size()), refs); }
 VarId arr(const std::vector<VarId>& refs) { return construct(type_array(type_of(refs.at(0)), (uint32_t)refs.size()), refs); }
+// tr::mat (trace.rs:734-756): columns are vectors of `rows` elements, storage is column-major
+VarId mat(const std::vector<VarId>& columns) {
+    const TypeNode col = type_node(type_of(columns.at(0)));
+    if (col.kind != HJ_VEC) throw TraceError("mat: the columns must be vectors");
+    return construct(type_matrix(col.elem, (uint32_t)columns.size(), col.num), columns);
+}
 
 // ---- references, gather, scatter (trace.rs:1084-1334, 1354-1375) -----------------------------------
 static VarId get_ref(VarId a, bool mutable_) {

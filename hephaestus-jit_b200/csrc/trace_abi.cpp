@@ -113,6 +113,7 @@ hj_status hj_tr_extract_dyn(uint64_t a, uint64_t elem, uint64_t* out) { OUT(extr
 hj_status hj_tr_composite(const uint64_t* refs, uint32_t n, uint64_t* out) { OUT(composite(vec_of(refs, n))); }
 hj_status hj_tr_vec(const uint64_t* refs, uint32_t n, uint64_t* out) { OUT(vec(vec_of(refs, n))); }
 hj_status hj_tr_arr(const uint64_t* refs, uint32_t n, uint64_t* out) { OUT(arr(vec_of(refs, n))); }
+hj_status hj_tr_mat(const uint64_t* columns, uint32_t n, uint64_t* out) { OUT(mat(vec_of(columns, n))); }
 hj_status hj_tr_gather(uint64_t src, uint64_t idx, uint64_t active, uint64_t* out) { OUT(gather_if(src, idx, active)); }
 hj_status hj_tr_scatter(uint64_t src, uint64_t dst, uint64_t idx, uint64_t active) {
     return guarded([&] { scatter_like(HJ_OP_SCATTER, 0, src, dst, idx, active); });

@@ -102,6 +102,7 @@ VarId extract_dyn(VarId a, VarId elem);
 VarId composite(const std::vector<VarId>& refs);
 VarId vec(const std::vector<VarId>& refs);
 VarId arr(const std::vector<VarId>& refs);
+VarId mat(const std::vector<VarId>& columns);
 VarId gather_if(VarId self, VarId idx, VarId active);
 VarId scatter_like(uint32_t kop, uint32_t rop, VarId self, VarId dst, VarId idx, VarId active);
 VarId atomic_inc(VarId self, VarId idx, VarId active);

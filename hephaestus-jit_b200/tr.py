@@ -399,6 +399,13 @@ def vec(refs) -> VarRef:
     return VarRef(out.value)
 
 
+def mat(columns) -> VarRef:
+    """``tr::mat`` (trace.rs:734-756): a matrix from its column vectors."""
+    out = _u64()
+    check(lib.hj_tr_mat(_handles(columns), len(columns), ctypes.byref(out)))
+    return VarRef(out.value)
+
+
 def arr(refs) -> VarRef:
     out = _u64()
     check(lib.hj_tr_arr(_handles(refs), len(refs), ctypes.byref(out)))

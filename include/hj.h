@@ -388,6 +388,7 @@ hj_status hj_tr_extract(uint64_t a, uint32_t elem, uint64_t* out);              
 hj_status hj_tr_extract_dyn(uint64_t a, uint64_t elem, uint64_t* out);            /* :1460-1477 */
 hj_status hj_tr_composite(const uint64_t* refs, uint32_t n, uint64_t* out);       /* :675-693 */
 hj_status hj_tr_vec(const uint64_t* refs, uint32_t n, uint64_t* out);             /* :717-737 */
+hj_status hj_tr_mat(const uint64_t* columns, uint32_t n, uint64_t* out);         /* :734-756 */
 hj_status hj_tr_arr(const uint64_t* refs, uint32_t n, uint64_t* out);             /* :694-712 */
 hj_status hj_tr_gather(uint64_t src, uint64_t idx, uint64_t active, uint64_t* out); /* gather_if :1125-1164 */
 hj_status hj_tr_scatter(uint64_t src, uint64_t dst, uint64_t idx, uint64_t active); /* :1167-1209 */

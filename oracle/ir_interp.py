@@ -199,11 +199,11 @@ class Interp:
             v = buf.reshape(-1)[safe]
             v = (v != 0) if k == BOOL else v.astype(NP[k])
             return np.where(mask, v, np.zeros(1, dtype=v.dtype))
-        if k in (VEC, ARRAY):
-            num = self.types[t][2]
+        if k in (VEC, ARRAY, MAT):  # matrices are stored column by column, packed
+            num = self.types[t][2] if k != MAT else self.types[t][3] * self.types[t][4]
             b2 = buf.reshape(-1, num)
             return [np.where(mask, b2[safe, c], 0).astype(b2.dtype) for c in range(num)]
-        raise NotImplementedError("gather of struct / matrix types")
+        raise NotImplementedError("gather of struct types")
 
     def store(self, buf, t, idx, val, mask):
         k = self.kind(t)
@@ -213,14 +213,14 @@ class Interp:
             v = self._bcast(val, mask.shape[0])
             flat[idx[sel].astype(np.int64)] = v[sel].astype(flat.dtype)
             return
-        if k in (VEC, ARRAY):
-            num = self.types[t][2]
+        if k in (VEC, ARRAY, MAT):
+            num = self.types[t][2] if k != MAT else self.types[t][3] * self.types[t][4]
             b2 = buf.reshape(-1, num)
             for c in range(num):
                 v = self._bcast(val[c], mask.shape[0])
                 b2[idx[sel].astype(np.int64), c] = v[sel].astype(b2.dtype)
             return
-        raise NotImplementedError("scatter of struct / matrix types")
+        raise NotImplementedError("scatter of struct types")
 
     # ---- execution -------------------------------------------------------------------------
     def run(self, size, buffers, size_buf=None, index_base=0):
@@ -373,6 +373,17 @@ class Interp:
                 for x, y in zip(a, b):
                     acc = (acc + (x * y).astype(NP[k])).astype(NP[k])
                 return acc
+            if arg == BOP_MUL and ak == MAT and self.types[at][3] == self.types[at][4]:
+                # GLSL `*` on matrices (glsl/mod.rs emits `a * b`): column-major linear-algebra product
+                nn = self.types[at][4]
+                out = []
+                for c in range(nn):
+                    for q in range(nn):
+                        acc = np.zeros(n, dtype=NP[ek])
+                        for kk in range(nn):
+                            acc = (acc + (self._bcast(a[kk * nn + q], n) * self._bcast(b[c * nn + kk], n)).astype(NP[ek])).astype(NP[ek])
+                        out.append(acc)
+                return out
             if arg in (BOP_EQ, BOP_NEQ):
                 eq = np.ones(n, dtype=bool)
                 for x, y in zip(a, b):

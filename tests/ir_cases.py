@@ -582,6 +582,33 @@ def vector_ops(n=1025):
                 exact=False, rtol=1e-6, atol=1e-6)
 
 
+def matrix_product(n=257):
+    """test.rs matrix_times_matrix: `m0.mul(&m1)` on matrices is GLSL's linear-algebra product
+    (column-major).  Lane 0..: A = [[1,2],[3,4]] + index, B = [[5,6],[7,8]]; lane 0 is the reference's
+    program, whose product [[19,22],[43,50]] is stored column by column."""
+    b = irm.IRBuilder()
+    f32 = b.scalar(I.F32)
+    v2, m2 = b.vec(f32, 2), b.mat(f32, 2, 2)
+    idx = b.index()
+    fi = b.uop(I.UOP_CAST, f32, idx)
+    lit = lambda x: b.bop(I.BOP_ADD, f32, b.literal(I.F32, x), fi)
+    a0 = b.push(I.OP_CONSTRUCT, v2, [lit(1.0), lit(3.0)])
+    a1 = b.push(I.OP_CONSTRUCT, v2, [lit(2.0), lit(4.0)])
+    ma = b.push(I.OP_CONSTRUCT, m2, [a0, a1])
+    b0 = b.push(I.OP_CONSTRUCT, v2, [b.literal(I.F32, 5.0), b.literal(I.F32, 7.0)])
+    b1 = b.push(I.OP_CONSTRUCT, v2, [b.literal(I.F32, 6.0), b.literal(I.F32, 8.0)])
+    mb = b.push(I.OP_CONSTRUCT, m2, [b0, b1])
+    prod = b.bop(I.BOP_MUL, m2, ma, mb)
+    r0 = b.buffer_ref(m2)
+    b.scatter(r0, prod, idx)
+    i = np.arange(n, dtype=np.float32)
+    A = np.stack([np.stack([1 + i, 2 + i], -1), np.stack([3 + i, 4 + i], -1)], -2)  # (n, row, col)
+    B = np.array([[5, 6], [7, 8]], np.float32)
+    want = np.einsum("nij,jk->nik", A, B).transpose(0, 2, 1).reshape(n, 4).astype(np.float32)  # column-major
+    assert want[0].tolist() == [19.0, 43.0, 22.0, 50.0]
+    return Case("matrix_product", b, n, [np.zeros((n, 4), np.float32)], expect={0: want})
+
+
 SYNTHETIC_CASES = (
     [lambda k=k: binary_ops(k) for k in INT_KINDS + FLOAT_KINDS]
     + [bool_ops]
@@ -592,7 +619,7 @@ SYNTHETIC_CASES = (
     + [lambda: scatter_reduce_ops(I.I32, I.R_MIN), lambda: scatter_reduce_ops(I.U64, I.R_SUM),
        lambda: scatter_reduce_ops(I.I64, I.R_MAX), lambda: scatter_reduce_ops(I.F32, I.R_SUM),
        lambda: scatter_reduce_ops(I.F32, I.R_MAX), lambda: scatter_reduce_ops(I.U32, I.R_SUM, cond=True)]
-    + [dyn_size, index_base, c2_chain, mixed_width, in_place_update, vector_ops]
+    + [dyn_size, index_base, c2_chain, mixed_width, in_place_update, vector_ops, matrix_product]
 )
 
 ALL_CASES = REFERENCE_CASES + SYNTHETIC_CASES
