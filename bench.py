@@ -341,13 +341,17 @@ def run_own(args):
     import torch
     import torch.distributed as dist
 
+    # stdout carries exactly ONE line, the JSON: anything native libraries print on fd 1 meanwhile
+    # (NCCL's version banner, for one) is sent to stderr instead
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
+
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        # NCCL's own banner (NCCL_DEBUG=VERSION/INFO) goes to stdout by default: keep stdout for the JSON line
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     torch.cuda.set_device(local_rank)
 
@@ -529,7 +533,8 @@ def run_own(args):
             line["suite"] = suite
         if shard_suite is not None:
             line["sharded"] = shard_suite
-        print(json.dumps(line))
+        sys.stdout.flush()
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
