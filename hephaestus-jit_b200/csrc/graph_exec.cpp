@@ -73,6 +73,55 @@ bool match_histogram(const hj_ir* ir, HistMatch* m) {
     m->literal = v.var(src).data;
     return true;
 }
+
+// The scheduler zero-fills the whole index buffer in the kernel pass in front of every Compress
+// (`index = sized_literal(0, n)`, trace.rs:1600-1601; usually fused with the kernel that computes
+// the mask): 4 bytes written per element, as much as a compaction at p = 0.5 moves in total, only
+// to be overwritten below `count`.  When that pass holds `index[i] = 0` as a plain top-level
+// Scatter of a zero literal at the bare Index and nothing else touches the buffer, the store is
+// taken out of the kernel (or the pass is skipped when nothing else is left in it) and the
+// Compress pass zeroes index[count..n) itself: same bytes in the buffer afterwards, 4 * count
+// bytes of HBM writes less and often one launch less.
+struct PrefillMatch {
+    uint32_t scatter_var, literal_ty;
+    bool only_side_effect;  // the kernel does nothing else: skip the pass
+};
+bool match_index_prefill(const hj_ir* ir, uint32_t slot, PrefillMatch* m) {
+    IRView v(ir);
+    int found = -1, depth = 0;
+    uint32_t other_effects = 0;
+    for (uint32_t i = 0; i < ir->n_vars; i++) {
+        const hj_ir_var& var = v.var(i);
+        if (var.op == HJ_OP_LOOP_START || var.op == HJ_OP_IF_START) depth++;
+        if (var.op == HJ_OP_LOOP_END || var.op == HJ_OP_IF_END) depth--;
+        const bool effect = var.op == HJ_OP_SCATTER || var.op == HJ_OP_SCATTER_REDUCE || var.op == HJ_OP_SCATTER_ATOMIC ||
+                            var.op == HJ_OP_ATOMIC_INC;
+        bool is_prefill = false;
+        if (var.op == HJ_OP_SCATTER && depth == 0 && v.n_deps(i) == 3 && found < 0) {
+            const hj_ir_var &dst = v.var(v.dep(i, 0)), &src = v.var(v.dep(i, 1)), &idx = v.var(v.dep(i, 2));
+            is_prefill = dst.op == HJ_OP_BUFFER_REF && dst.data == slot && src.op == HJ_OP_LITERAL && src.data == 0 &&
+                         v.kind(src.ty) == HJ_U32 && idx.op == HJ_OP_INDEX;
+        }
+        if (is_prefill) {
+            found = (int)i;
+            m->literal_ty = v.var(v.dep(i, 1)).ty;
+        } else if (effect) {
+            other_effects++;
+        }
+    }
+    if (found < 0) return false;
+    for (uint32_t i = 0; i < ir->n_vars; i++) {  // nothing else may read or write the buffer, or name the store
+        if ((int)i == found) continue;
+        for (uint32_t k = 0; k < v.n_deps(i); k++) {
+            const uint32_t d = v.dep(i, k);
+            if ((int)d == found) return false;
+            if (v.var(d).op == HJ_OP_BUFFER_REF && v.var(d).data == slot) return false;
+        }
+    }
+    m->scatter_var = (uint32_t)found;
+    m->only_side_effect = other_effects == 0;
+    return true;
+}
 }  // namespace
 
 extern "C" hj_status hj_execute_graph(hj_device* dev, const hj_pass* passes, uint32_t n_passes,
@@ -99,6 +148,7 @@ extern "C" hj_status hj_execute_graph(hj_device* dev, const hj_pass* passes, uin
         return HJ_OK;
     };
 
+    int64_t zero_tail_for = -1;  // index of the Compress pass that has to zero index[count..n) itself
     for (uint32_t i = 0; i < n_passes; i++) {
         const hj_pass& p = passes[i];
         char name[64];
@@ -121,9 +171,43 @@ extern "C" hj_status hj_execute_graph(hj_device* dev, const hj_pass* passes, uin
                                          ddst->size));
                 break;
             }
+            // zero-fill of the index buffer of the Compress pass that follows (see match_index_prefill)
+            const hj_ir* ir = p.ir;
+            hj_ir ir_without_fill;
+            std::vector<hj_ir_var> vars_without_fill;
+            PrefillMatch pm;
+            static const bool no_elision = getenv("HJ_NO_PREFILL_ELISION") != nullptr;
+            if (!no_elision && !size_buf && i + 1 < n_passes && passes[i + 1].kind == HJ_PASS_COMPRESS &&
+                passes[i + 1].n_resources >= 3) {
+                const hj_pass& c = passes[i + 1];
+                const uint32_t index_res = c.resources[0], mask_res = c.resources[2];
+                uint32_t slot = p.n_resources;
+                for (uint32_t b = 0; b < p.n_resources; b++)
+                    if (p.resources[b] == index_res) slot = slot == p.n_resources ? b : p.n_resources + 1;
+                if (slot < p.n_resources && index_res < n_resources && mask_res < n_resources && env[index_res] &&
+                    ((uintptr_t)env[index_res]->ptr & 15u) == 0 && descs[index_res].size == p.size &&
+                    descs[mask_res].size == p.size && match_index_prefill(p.ir, slot, &pm)) {
+                    zero_tail_for = (int64_t)i + 1;
+                    if (pm.only_side_effect) {
+                        snprintf(name, sizeof(name), "JIT Kernel %u [%llu] (index zero-fill left to Compress)", i,
+                                 (unsigned long long)p.size);
+                        break;
+                    }
+                    vars_without_fill.assign(p.ir->vars, p.ir->vars + p.ir->n_vars);
+                    hj_ir_var& dead = vars_without_fill[pm.scatter_var];  // becomes an unused `u32 r = 0`
+                    dead.ty = pm.literal_ty;
+                    dead.op = HJ_OP_LITERAL;
+                    dead.arg = 0;
+                    dead.dep_start = dead.dep_end = 0;
+                    dead.data = 0;
+                    ir_without_fill = *p.ir;
+                    ir_without_fill.vars = vars_without_fill.data();
+                    ir = &ir_without_fill;
+                }
+            }
             snprintf(name, sizeof(name), "JIT Kernel %u [%llu]", i, (unsigned long long)p.size);
             hj_kernel* k = nullptr;
-            HJ_TRY(hj_kernel_get(dev, p.ir, &k));
+            HJ_TRY(hj_kernel_get(dev, ir, &k));
             std::vector<hj_buffer*> bufs(p.n_resources);
             for (uint32_t b = 0; b < p.n_resources; b++) HJ_TRY(res(p, b, &bufs[b], nullptr));
             hj_status s = hj_kernel_launch(dev, k, p.size, size_buf, bufs.data(), p.n_resources, 0);
@@ -157,6 +241,10 @@ extern "C" hj_status hj_execute_graph(hj_device* dev, const hj_pass* passes, uin
             HJ_TRY(res(p, 1, &out_count, nullptr));
             HJ_TRY(res(p, 2, &src, &dsrc));
             HJ_TRY(hj_compress(dev, dsrc->size, size_buf, out_count, src, index_out, 0));
+            if (zero_tail_for == (int64_t)i) {  // the pass in front left the zero-fill to us
+                DeviceGuard g(dev);
+                HJ_TRY(launch_compress_zero_tail(dev, (uint32_t*)index_out->ptr, (const uint32_t*)out_count->ptr, dsrc->size));
+            }
             break;
         }
         default:

@@ -118,6 +118,7 @@ hj_status launch_reduce(hj_device* dev, hj_reduce_op op, hj_type_kind ty, size_t
                         const void* src, void* dst, const PeerView* peers = nullptr, uint32_t epoch = 0);
 hj_status launch_prefix_sum(hj_device* dev, hj_type_kind ty, size_t n, bool inclusive,
                             const void* src, void* dst, const void* seed);
+hj_status launch_compress_zero_tail(hj_device* dev, uint32_t* index_out, const uint32_t* count, size_t n);
 hj_status launch_compress(hj_device* dev, size_t n, const uint32_t* size_buf, uint32_t* out_count,
                           const uint8_t* mask, uint32_t* index_out, uint32_t index_base);
 hj_status launch_scatter_reduce(hj_device* dev, hj_reduce_op op, hj_type_kind ty, size_t n,

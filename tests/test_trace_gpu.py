@@ -768,3 +768,31 @@ def test_array_dyn_extract_vec3_layout_cast(device):  # test.rs:1278-1355
     tr.compile().launch(device)
     assert lst(arr2, np.int32) == [1, 2, 3, 1, 2, 3]
     assert lst(vec, np.float32) == [1.0, 2.0, 3.0, 1.0, 2.0, 3.0]
+
+
+# ---- execute_graph leaves the index zero-fill in front of a Compress to the Compress pass ----------------
+@pytest.mark.parametrize("n", [1, 5, 1000, 65_536, 1_000_003])
+@pytest.mark.parametrize("mask_evaluated", [False, True])
+def test_compress_index_prefill_elision(device, n, mask_evaluated):
+    """`index = sized_literal(0, n)` (trace.rs:1600-1601) is scheduled into the kernel in front of the
+    Compress pass; the backend drops that store and zeroes index[count..n) after the compaction.
+    The buffer must come out exactly as with the reference's order of work — also when the pool
+    hands back a dirty allocation."""
+    rng = np.random.Generator(np.random.PCG64(n))
+    for p in (0.0, 0.3, 1.0):
+        junk = [device.create_buffer_from_slice(np.full(n, 0xDEADBEEF, np.uint32)) for _ in range(3)]
+        del junk  # back to the pool with its contents
+        vals = rng.random(n, dtype=np.float32)
+        x = tr.array(vals, device)
+        mask = x.lt(tr.literal(p, F32))
+        if mask_evaluated:      # the kernel in front of Compress then holds NOTHING but the zero-fill
+            mask.schedule()
+            tr.compile().launch(device)
+        count, index = mask.compress()
+        g = tr.compile()
+        for _ in range(3):      # the third launch replays a captured CUDA graph
+            g.launch(device)
+            cnt, want = oracle.compress((vals < np.float32(p)).astype(np.uint8))
+            assert int(count.to_vec(np.uint32)[0]) == cnt
+            assert np.array_equal(index.to_vec(np.uint32), want)   # indices, then zeros up to n
+        del count, index, mask, x, g
