@@ -177,6 +177,26 @@ extern "C" hj_status hj_execute_graph(hj_device* dev, const hj_pass* passes, uin
             std::vector<hj_ir_var> vars_without_fill;
             PrefillMatch pm;
             static const bool no_elision = getenv("HJ_NO_PREFILL_ELISION") != nullptr;
+            // `count = sized_literal(0, 1)` (trace.rs:1599) gets a one-element kernel of its own; the
+            // Compress pass always writes out_count[0], so a pass that does nothing else is dropped
+            if (!no_elision && !size_buf && p.size == 1 && p.n_resources == 1) {
+                bool dropped = false;
+                for (uint32_t j = i + 1; j < n_passes && j <= i + 2 && !dropped; j++) {
+                    const hj_pass& c = passes[j];
+                    if (c.kind == HJ_PASS_COMPRESS && c.n_resources >= 3 && c.resources[1] == p.resources[0] &&
+                        c.resources[0] != p.resources[0] && c.resources[2] != p.resources[0]) {
+                        dropped = match_index_prefill(p.ir, 0, &pm) && pm.only_side_effect;
+                        break;
+                    }
+                    bool touches = c.size_buffer >= 0 && (uint32_t)c.size_buffer == p.resources[0];
+                    for (uint32_t b = 0; b < c.n_resources; b++) touches = touches || c.resources[b] == p.resources[0];
+                    if (touches) break;
+                }
+                if (dropped) {
+                    snprintf(name, sizeof(name), "JIT Kernel %u [1] (count zero-fill left to Compress)", i);
+                    break;
+                }
+            }
             if (!no_elision && !size_buf && i + 1 < n_passes && passes[i + 1].kind == HJ_PASS_COMPRESS &&
                 passes[i + 1].n_resources >= 3) {
                 const hj_pass& c = passes[i + 1];
