@@ -796,3 +796,43 @@ def test_compress_index_prefill_elision(device, n, mask_evaluated):
             assert int(count.to_vec(np.uint32)[0]) == cnt
             assert np.array_equal(index.to_vec(np.uint32), want)   # indices, then zeros up to n
         del count, index, mask, x, g
+
+
+def test_record_persistent_cache_fresh_process(device, tmp_path):
+    """record(f, cache_dir=...): a second process that records a function under the same name launches
+    the stored graph — its Python body is never called (it raises), nothing is traced or compiled."""
+    import subprocess
+    import sys
+
+    rng = np.random.Generator(np.random.PCG64(11))
+    n = 50_001
+    xs = rng.integers(0, 1 << 20, size=n).astype(np.uint32)
+    tab = rng.integers(0, 1 << 16, size=256).astype(np.uint32)
+    table = tr.array(tab, device)
+    f = rec.record(lambda x: _traced_pipeline(x, table), cache_dir=str(tmp_path), name="pipeline_v1")
+    (z, scan, picked), _ = f(device, tr.array(xs, device))
+    want = _pipeline_expected(xs, tab)
+    assert np.array_equal(z.to_vec(np.uint32), want[0]) and np.array_equal(scan.to_vec(np.uint32), want[1])
+    assert len(list(tmp_path.glob("*.hjgraph"))) == 1
+    del z, scan, picked, table, f
+    xs2 = rng.integers(0, 1 << 20, size=n).astype(np.uint32)
+    np.save(tmp_path / "x.npy", xs2)
+    script = f"""
+import importlib, sys, numpy as np
+sys.path.insert(0, {os.path.dirname(HERE)!r})
+hj = importlib.import_module("hephaestus-jit_b200"); tr = importlib.import_module("hephaestus-jit_b200.tr")
+rec = importlib.import_module("hephaestus-jit_b200.record")
+dev = hj.Device.cuda(0)
+def body(x):
+    raise AssertionError("the function was traced again")
+f = rec.record(body, cache_dir={str(tmp_path)!r}, name="pipeline_v1")
+(z, scan, picked), _ = f(dev, tr.array(np.load({str(tmp_path / "x.npy")!r}), dev))
+np.save({str(tmp_path / "z.npy")!r}, z.to_vec(np.uint32)); np.save({str(tmp_path / "scan.npy")!r}, scan.to_vec(np.uint32))
+np.save({str(tmp_path / "picked.npy")!r}, picked.to_vec(np.uint32))
+"""
+    out = subprocess.run([sys.executable, "-c", script], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    want = _pipeline_expected(xs2, tab)
+    assert np.array_equal(np.load(tmp_path / "z.npy"), want[0])
+    assert np.array_equal(np.load(tmp_path / "scan.npy"), want[1])
+    assert np.array_equal(np.load(tmp_path / "picked.npy")[: len(want[2])], want[2])
