@@ -144,10 +144,15 @@ struct HistCtl {
 constexpr int HR_SWEEP = 18;
 constexpr uint32_t HR_HIGH = 0xfc00fc00u;
 static_assert((~HR_HIGH & 0xffffu) + HR_SWEEP * (HR_TILE / 4) <= 0xffff, "a 16-bit counter must survive one sweep period");
+// `rs` (u32 bins, one window): log2 of the number of COPIES of every bin.  Copy c of bin b is word
+// (b << rs) + c and lane l adds to copy l & (2^rs - 1): with 32 copies (<= 1023 bins) a lane only
+// ever touches bank l, so a warp's adds never collide — not in a bank, and not on an address either,
+// which is what serialises a skewed histogram (all 32 lanes on one hot bin).  Fewer copies for more
+// bins (16 up to 2047, ... 2 up to 16383) still thin the collisions out.
 template <bool PACKED16>
 __global__ void __launch_bounds__((HR_WARPS + 1) * 32, 1)
 hist_ring_kernel(const uint32_t* __restrict__ keys, size_t n, uint32_t literal, void* __restrict__ out,
-                 uint32_t* __restrict__ dst, uint32_t n_dst, uint32_t bins_per_part, uint32_t parts) {
+                 uint32_t* __restrict__ dst, uint32_t n_dst, uint32_t bins_per_part, uint32_t parts, uint32_t rs) {
     extern __shared__ __align__(128) char smem[];
     char* stages = smem;
     HistCtl* ctl = reinterpret_cast<HistCtl*>(smem + (size_t)HR_STAGES * HR_TILE);
@@ -156,7 +161,7 @@ hist_ring_kernel(const uint32_t* __restrict__ keys, size_t n, uint32_t literal, 
     const uint32_t part = blockIdx.x % parts, group = blockIdx.x / parts, n_groups = gridDim.x / parts;
     const uint32_t lo = part * bins_per_part;
     const uint32_t nb = min(bins_per_part, n_dst - lo);
-    const uint32_t n_words = PACKED16 ? (bins_per_part + 1) / 2 : bins_per_part;
+    const uint32_t n_words = PACKED16 ? (bins_per_part + 1) / 2 : (rs ? (bins_per_part + 1) << rs : bins_per_part);
     const size_t n_bytes = n * 4;
     const uint32_t n_tiles = (uint32_t)((n_bytes + HR_TILE - 1) / HR_TILE);
 
@@ -223,11 +228,20 @@ hist_ring_kernel(const uint32_t* __restrict__ keys, size_t n, uint32_t literal, 
             } else {
                 // same trick with u32 bins: keys outside this window (below lo they wrap to huge
                 // values) land on the lane's dummy word behind the window
-                const uint32_t dummy = nb + lane;
+                if (rs) {  // replicated bins; row `nb` is the dummy row
+                    const uint32_t mine_s = bins_s + 4u * (lane & ((1u << rs) - 1u)), sh = rs + 2u;
 #pragma unroll
-                for (int i = 0; i < 4; i++) {
-                    const uint32_t a = min(kk[i] - lo, dummy);
-                    asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(bins_s + 4u * a), "r"(literal) : "memory");
+                    for (int i = 0; i < 4; i++) {
+                        const uint32_t a = min(kk[i] - lo, nb);
+                        asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(mine_s + (a << sh)), "r"(literal) : "memory");
+                    }
+                } else {
+                    const uint32_t dummy = nb + lane;
+#pragma unroll
+                    for (int i = 0; i < 4; i++) {
+                        const uint32_t a = min(kk[i] - lo, dummy);
+                        asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(bins_s + 4u * a), "r"(literal) : "memory");
+                    }
                 }
             }
             __syncwarp();
@@ -265,7 +279,16 @@ hist_ring_kernel(const uint32_t* __restrict__ keys, size_t n, uint32_t literal, 
         for (uint32_t b = threadIdx.x; b < (nb + 1) / 2; b += blockDim.x) mine[b] = bins[b];
     } else {
         uint32_t* mine = reinterpret_cast<uint32_t*>(out) + (size_t)group * n_dst + lo;
-        for (uint32_t b = threadIdx.x; b < nb; b += blockDim.x) mine[b] = bins[b];
+        if (rs) {  // sum the copies; thread b starts at copy b so that a warp's reads spread over the banks
+            const uint32_t copies = 1u << rs;
+            for (uint32_t b = threadIdx.x; b < nb; b += blockDim.x) {
+                uint32_t acc = 0;
+                for (uint32_t c = 0; c < copies; c++) acc += bins[(b << rs) + ((c + b) & (copies - 1u))];
+                mine[b] = acc;
+            }
+        } else {
+            for (uint32_t b = threadIdx.x; b < nb; b += blockDim.x) mine[b] = bins[b];
+        }
     }
 }
 
@@ -395,7 +418,7 @@ hj_status launch_scatter_reduce(hj_device* dev, hj_reduce_op op, hj_type_kind ty
                 auto kern = hist_ring_kernel<true>;
                 HJ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
                 kern<<<n_groups, (HR_WARPS + 1) * 32, smem, dev->stream>>>(
-                    idx, n, 1u, dev->hist_scratch, (uint32_t*)dst, (uint32_t)n_dst, (uint32_t)n_dst, 1u);
+                    idx, n, 1u, dev->hist_scratch, (uint32_t*)dst, (uint32_t)n_dst, (uint32_t)n_dst, 1u, 0u);
                 HJ_TRY(check_launch(dev, "hist_ring_kernel"));
                 hist_fold_kernel<true><<<dim3((n_words + 255) / 256, HF_SLICES), 256, 0, dev->stream>>>(
                     (const uint32_t*)dev->hist_scratch, n_groups, (uint32_t*)dst, (uint32_t)n_dst);
@@ -405,11 +428,16 @@ hj_status launch_scatter_reduce(hj_device* dev, hj_reduce_op op, hj_type_kind ty
             const uint32_t bins_per_part = (uint32_t)((n_dst + parts - 1) / parts);
             const uint32_t n_groups = std::max(1u, (uint32_t)dev->sm_count / parts);
             HJ_TRY(ensure_hist_scratch(dev, (size_t)n_groups * n_dst * 4));
-            const size_t smem = ring + ((size_t)bins_per_part + 32) * 4;  // + 32 dummy words
+            // one window with room to spare: several copies of every bin (see hist_ring_kernel)
+            uint32_t rs = 0;
+            static const bool no_repl = getenv("HJ_HIST_NO_REPL") != nullptr;
+            if (parts == 1 && !no_repl)
+                while (rs < 5 && ((size_t)(bins_per_part + 1) << (rs + 1)) <= HR_MAX_BINS + 1024) rs++;  // 1024 bins x 32 copies + the dummy row
+            const size_t smem = ring + (rs ? ((size_t)(bins_per_part + 1) << rs) + 32 : (size_t)bins_per_part + 32) * 4;  // + dummy words
             auto kern = hist_ring_kernel<false>;
             HJ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             kern<<<n_groups * parts, (HR_WARPS + 1) * 32, smem, dev->stream>>>(
-                idx, n, (uint32_t)literal, dev->hist_scratch, (uint32_t*)dst, (uint32_t)n_dst, bins_per_part, parts);
+                idx, n, (uint32_t)literal, dev->hist_scratch, (uint32_t*)dst, (uint32_t)n_dst, bins_per_part, parts, rs);
             HJ_TRY(check_launch(dev, "hist_ring_kernel"));
             hist_fold_kernel<false><<<dim3((unsigned)((n_dst + 255) / 256), HF_SLICES), 256, 0, dev->stream>>>(
                 (const uint32_t*)dev->hist_scratch, n_groups, (uint32_t*)dst, (uint32_t)n_dst);

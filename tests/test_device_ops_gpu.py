@@ -313,6 +313,10 @@ def test_histogram_bit_exact(dev, n_bins):
     (40_001, 1, "oob"),        # odd bin count, packed counters: the unused upper half of the last word takes key == n_dst
     (50_001, 1, "edge"),       # every key is n_dst - 1 or n_dst: the last real counter and its out-of-range neighbour
     (99_999, 5, "oob"),        # odd windows, literal != 1, half the keys out of range (dummy words behind each window)
+    (1000, 1, "oob"),          # 32 copies of every bin (one per lane), dummy row for the keys out of range
+    (1024, 3, "hot"),          # 32 copies, 1024 bins + dummy row exactly fill the window
+    (3000, 1, "edge"),         # 8 copies
+    (16_383, 2, "uniform"),    # 2 copies
 ])
 def test_histogram_ring_paths_bit_exact(dev, n_bins, literal, dist):
     n = (1 << 22) + 12345

@@ -19,10 +19,13 @@ def timeit(fn, iters=10):
     torch.cuda.synchronize()
     return sorted(a.elapsed_time(b) for a, b in ev)[iters // 2]
 for n, nb, dist in ((1 << 28, 1 << 16, "uniform"), ((1 << 28) - 777, 1 << 16, "uniform"), (1 << 28, 1 << 16, "zipf"), (1 << 28, 1 << 10, "uniform"),
-                    (1 << 28, 100000, "uniform"), ((1 << 20) + 3, 1 << 16, "uniform"), (1 << 26, 1 << 18, "uniform"), (1 << 26, 40000, "oob")):
+                    (1 << 28, 100000, "uniform"), ((1 << 20) + 3, 1 << 16, "uniform"), (1 << 26, 1 << 18, "uniform"), (1 << 26, 40000, "oob"),
+                    (1 << 28, 1 << 10, "one"), (1 << 28, 256, "uniform"), (1 << 28, 4000, "uniform"), (1 << 28, 1 << 10, "zipf")):
     if dist == "zipf":
         u = torch.rand(n, device="cuda", generator=g)
         keys = ((nb ** u - 1).clamp(0, nb - 1)).to(torch.int32)  # heavy head, log-uniform
+    elif dist == "one":
+        keys = torch.full((n,), 7, device="cuda", dtype=torch.int32)
     elif dist == "oob":
         keys = torch.randint(0, 2 * nb, (n,), device="cuda", generator=g, dtype=torch.int32)
     else:
