@@ -175,7 +175,14 @@ __device__ __forceinline__ uint32_t lane_mask16(uint4 v) {
 
 unsigned long long* g_compress_trace = nullptr;  // set through hj_debug_compress_trace()
 
-template <int SLICE, int TILE, int TSLOTS>
+// ZT ("zero tail"): the kernel also leaves index_out[count .. n) zeroed, so the scheduler's zero-fill
+// of the whole index buffer in front of the Compress pass can go (graph_exec.cpp).  Nobody has to
+// know `count` for that: the slice that ends at element e, with r selected elements up to e, proves
+// that every position >= r + (n - e) lies in the tail (all n - e remaining elements could still be
+// selected, no more).  These bounds telescope — slice s owns [B(s), B(s-1)), exactly as many
+// positions as it has UNselected elements — so every slice writes 4 bytes per element in total,
+// indices below `count` and zeros above, the ranges are disjoint and end at `count`.
+template <int SLICE, int TILE, int TSLOTS, bool ZT = false>
 struct CompressOp {
     using P = uint32_t;
     static constexpr int ROWS = SLICE / 512;  // 512-element rows per warp slice, ranked in pairs
@@ -184,6 +191,7 @@ struct CompressOp {
         uint32_t* index_out;
         uint32_t* out_count;
         uint32_t index_base;
+        size_t n;  // ZT: number of mask elements = length of index_out
     };
     // aux layout (shared memory behind the ring): TSLOTS mask planes of TILE/8 bytes (one u16 per
     // 16 mask bytes), then one 1 KiB index stage per consumer warp.  Phase 1 leaves only the masks
@@ -266,8 +274,20 @@ struct CompressOp {
             if (w & me) out[off + __popc(w & lt)] = v0 + 32 * j;
         }
     }
-    static __device__ __forceinline__ void emit(const char*, char* aux, int slot, size_t byte_off, uint32_t, P carry,
+    static __device__ __forceinline__ void emit(const char*, char* aux, int slot, size_t byte_off, uint32_t valid, P carry,
                                                 P slice_total, int lane, int cw, const Args& a) {
+        if (ZT && valid > slice_total) {  // this slice's share of the zero tail (index_out is 16-byte aligned)
+            const uint32_t nz = valid - slice_total;
+            const size_t first = (size_t)carry + slice_total + (a.n - (byte_off + valid));
+            uint32_t* z = a.index_out + first;
+            const uint32_t head = min(nz, (uint32_t)((4u - (first & 3u)) & 3u));
+            if ((uint32_t)lane < head) z[lane] = 0;
+            const uint32_t n_vec = (nz - head) / 4;
+            uint4* zv = reinterpret_cast<uint4*>(z + head);
+            for (uint32_t v = lane; v < n_vec; v += 32) st_stream_v4(zv + v, make_uint4(0, 0, 0, 0));
+            const uint32_t done = head + 4 * n_vec;
+            if ((uint32_t)lane < nz - done) z[done + lane] = 0;
+        }
         const uint16_t* m = masks_of(aux, slot, cw);
         if (slice_total <= 64u * ROWS) {
             // Sparse slice (p <~ 0.12; the total is the one phase 1 counted).  The mask plane of
@@ -320,7 +340,7 @@ struct CompressOp {
     static __device__ __forceinline__ void finish(P total, const Args& a) { a.out_count[0] = total; }
 };
 
-template <int CR_TILE, int CR_STAGES, int CR_TSLOTS, int CR_AHEAD, bool TRACE = false>
+template <int CR_TILE, int CR_STAGES, int CR_TSLOTS, int CR_AHEAD, bool TRACE = false, bool ZT = false>
 __global__ void __launch_bounds__((CR_WARPS + 3) * 32, 1)
 compress_ring_kernel(const uint8_t* __restrict__ mask, size_t n, const uint32_t* __restrict__ size_buf,
                      uint32_t* __restrict__ out_count, uint32_t* __restrict__ index_out, uint32_t index_base,
@@ -333,8 +353,8 @@ compress_ring_kernel(const uint8_t* __restrict__ mask, size_t n, const uint32_t*
     }
     const uint32_t n_tiles = (uint32_t)((n_eff + CR_TILE - 1) / CR_TILE);
     if (n_tiles == 0 && blockIdx.x == 0 && threadIdx.x == 0) out_count[0] = 0;
-    using Op = CompressOp<CR_TILE / CR_WARPS, CR_TILE, CR_TSLOTS>;
-    typename Op::Args args{index_out, out_count, index_base};
+    using Op = CompressOp<CR_TILE / CR_WARPS, CR_TILE, CR_TSLOTS, ZT>;
+    typename Op::Args args{index_out, out_count, index_base, n_eff};
     ring_pipeline<Op, CR_TILE, CR_STAGES, CR_WARPS, CR_AHEAD, CR_TSLOTS, true, 8, TRACE>(
         reinterpret_cast<const char*>(mask), n_eff, n_tiles, 0u, lb, G, args, smem, trace);
 }
@@ -378,8 +398,17 @@ hj_status launch_compress_zero_tail(hj_device* dev, uint32_t* index_out, const u
 }
 
 hj_status launch_compress(hj_device* dev, size_t n, const uint32_t* size_buf, uint32_t* out_count,
-                          const uint8_t* mask, uint32_t* index_out, uint32_t index_base) {
+                          const uint8_t* mask, uint32_t* index_out, uint32_t index_base, bool zero_tail) {
     HJ_REQUIRE(n <= 0xffffffffull, "compress: n does not fit the u32 index type");
+    if (zero_tail) {  // only the ring kernel on a statically sized, aligned buffer zeroes the tail itself
+        static const int c = getenv("HJ_COMPRESS_CFG") ? atoi(getenv("HJ_COMPRESS_CFG")) : 1;
+        const bool in_kernel = c == 1 && !size_buf && !g_compress_trace && ((uintptr_t)mask & 15u) == 0 &&
+                               ((uintptr_t)index_out & 15u) == 0 && n >= (64u << 10) && !getenv("HJ_ZERO_TAIL_KERNEL");
+        if (!in_kernel) {
+            HJ_TRY(launch_compress(dev, n, size_buf, out_count, mask, index_out, index_base, false));
+            return launch_compress_zero_tail(dev, index_out, out_count, n);
+        }
+    }
     static const int cfg = getenv("HJ_COMPRESS_CFG") ? atoi(getenv("HJ_COMPRESS_CFG")) : 1;  // 0: look-back kernel, 3: 28 KiB tiles
     if (cfg != 0 && ((uintptr_t)mask & 15u) == 0 && n >= (64u << 10)) {
         // tile geometry: 28 KiB tiles, 5 data stages (all but one in flight), 8 tile slots with
@@ -403,6 +432,7 @@ hj_status launch_compress(hj_device* dev, size_t n, const uint32_t* size_buf, ui
         // measured on B200 (profiles/r01_ring_sweeps.txt): the 56 KiB geometry wins at low
         // selectivity (fewer status-word sweeps per byte) and ties elsewhere
         if (g_compress_trace) HJ_TRY(launch(compress_ring_kernel<57344, 3, 4, 3, true>, smem_big));  // tools/ring_timeline.py
+        else if (big && zero_tail) HJ_TRY(launch(compress_ring_kernel<57344, 3, 4, 3, false, true>, smem_big));
         else if (big) HJ_TRY(launch(compress_ring_kernel<57344, 3, 4, 3>, smem_big));
         else HJ_TRY(launch(compress_ring_kernel<28672, 5, 8, 6>, smem_small));
         return check_launch(dev, "compress_ring_kernel");

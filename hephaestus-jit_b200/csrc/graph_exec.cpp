@@ -260,10 +260,16 @@ extern "C" hj_status hj_execute_graph(hj_device* dev, const hj_pass* passes, uin
             HJ_TRY(res(p, 0, &index_out, nullptr));
             HJ_TRY(res(p, 1, &out_count, nullptr));
             HJ_TRY(res(p, 2, &src, &dsrc));
-            HJ_TRY(hj_compress(dev, dsrc->size, size_buf, out_count, src, index_out, 0));
             if (zero_tail_for == (int64_t)i) {  // the pass in front left the zero-fill to us
+                const size_t n = dsrc->size;
+                HJ_REQUIRE(n >= 1 && n <= src->bytes && n * 4 <= index_out->bytes && out_count->bytes >= 4 &&
+                               (!size_buf || size_buf->bytes >= 4),
+                           "compress pass %u: buffer sizes do not match %zu elements", i, n);
                 DeviceGuard g(dev);
-                HJ_TRY(launch_compress_zero_tail(dev, (uint32_t*)index_out->ptr, (const uint32_t*)out_count->ptr, dsrc->size));
+                HJ_TRY(launch_compress(dev, n, size_buf ? (const uint32_t*)size_buf->ptr : nullptr, (uint32_t*)out_count->ptr,
+                                       (const uint8_t*)src->ptr, (uint32_t*)index_out->ptr, 0, true));
+            } else {
+                HJ_TRY(hj_compress(dev, dsrc->size, size_buf, out_count, src, index_out, 0));
             }
             break;
         }

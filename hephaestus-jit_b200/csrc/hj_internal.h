@@ -119,8 +119,10 @@ hj_status launch_reduce(hj_device* dev, hj_reduce_op op, hj_type_kind ty, size_t
 hj_status launch_prefix_sum(hj_device* dev, hj_type_kind ty, size_t n, bool inclusive,
                             const void* src, void* dst, const void* seed);
 hj_status launch_compress_zero_tail(hj_device* dev, uint32_t* index_out, const uint32_t* count, size_t n);
+// zero_tail: also leave index_out[count .. n) zeroed (in the ring kernel where it can, else by
+// launch_compress_zero_tail afterwards)
 hj_status launch_compress(hj_device* dev, size_t n, const uint32_t* size_buf, uint32_t* out_count,
-                          const uint8_t* mask, uint32_t* index_out, uint32_t index_base);
+                          const uint8_t* mask, uint32_t* index_out, uint32_t index_base, bool zero_tail = false);
 hj_status launch_scatter_reduce(hj_device* dev, hj_reduce_op op, hj_type_kind ty, size_t n,
                                 const uint32_t* idx, const void* src, uint64_t literal, void* dst,
                                 size_t n_dst);
