@@ -280,6 +280,23 @@ def run_suite(torch, hj, dev, peak, world, rank, comm):
             "ms": round(ms, 4), "lanes_per_s": n_l / ms * 1e3, "gathers_per_s": n_l * k_it / ms * 1e3,
             "passes": graph.n_passes(), "sum": float(total.item())}
         del graph, total, table
+        # C4 through the trace layer: `mask.compress()` as a user of the reference writes it — the
+        # scheduler's zero-fill of the index buffer + the Compress pass (the backend
+        # leaves the zero-fill to the compaction).  5 B/elem = 1 (mask) + 4 (every index word is written once)
+        try:
+            n_c = 1 << 28
+            mask_t = (torch.rand(n_c, device="cuda", generator=g) < 0.5).to(torch.uint8)
+            mvar = tr.from_buffer(wrap(mask_t), hj.BOOL, n_c)
+            count, index = mvar.compress()
+            cgraph = tr.compile()
+            ms = timed_events(torch, lambda: cgraph.launch(dev), 5, 3)
+            c = int(count.to_vec(np.uint32)[0])
+            ok = c == int(mask_t.sum().item()) and bool((index.to_vec(np.uint32, c, min(c + 4096, n_c)) == 0).all())
+            out["C4 traced mask.compress() p=0.5 2^28 (zero-fill + Compress passes)"] = entry(5 * n_c, ms, {
+                "elements_per_s": n_c / ms * 1e3, "bytes_per_elem": 5, "passes": cgraph.n_passes(), "count_and_tail_ok": ok})
+            del count, index, cgraph, mvar, mask_t
+        except Exception as exc:  # an extra line of the suite must never take the bench down
+            out["C4 traced mask.compress() p=0.5 2^28 (zero-fill + Compress passes)"] = {"error": str(exc)[:200]}
     if world > 1:
         out["_note"] = f"per-GPU share (1/{world}) of each array, local kernels only; collectives reported under 'sharded'"
     return out
