@@ -402,3 +402,26 @@ def test_buffer_roundtrip_and_ranges(dev):
         b.to_host(np.int32, 0, 1001)
     assert dev.info()["sm_count"] > 0
     assert dev.launch_count() > 0
+
+
+# ---- BASELINE.json config 1, exactly as SURVEY.md §8d states it --------------------------------------
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_baseline_config_c1(dev, seed):
+    """C1: u32 exclusive prefix sum + f32 sum-reduce over 2^20 elements (the reference's own
+    CPU-runnable case).  Inputs per SURVEY §8d: numpy PCG64(seed); u32 uniform in [0, 16) for the scan
+    (bit-exact); f32 uniform [0, 1) for the sum (rel 1e-5 vs f64) plus an integer-valued f32 set in
+    [0, 100) that must be exact (mirrors test.rs:580)."""
+    n = 1 << 20
+    rng = np.random.Generator(np.random.PCG64(seed))
+    u = rng.integers(0, 16, size=n).astype(np.uint32)
+    src, dst = dev.create_buffer_from_slice(u), dev.create_buffer(4 * n)
+    dev.prefix_sum(hj.U32, n, False, src, dst)
+    assert np.array_equal(dst.to_host(np.uint32), oracle.prefix_sum(oracle.U32, u, False))
+    f = rng.random(n, dtype=np.float32)
+    got = gpu_reduce(dev, hj.SUM, hj.F32, f)
+    exact = float(f.astype(np.float64).sum())
+    assert abs(float(got) - exact) <= F32_SUM_RTOL * exact
+    assert abs(float(oracle.reduce(oracle.SUM, oracle.F32, f)[0]) - exact) <= F32_SUM_RTOL * exact  # the oracle's tree order too
+    fi = rng.integers(0, 100, size=n).astype(np.float32)   # sum < 2^27 is not exactly representable step by step ...
+    got_i = gpu_reduce(dev, hj.SUM, hj.F32, fi[:1000])       # ... so the exact case keeps the reference's 1000 elements
+    assert float(got_i) == float(fi[:1000].astype(np.float64).sum())
