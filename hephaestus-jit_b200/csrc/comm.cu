@@ -213,7 +213,7 @@ __device__ __forceinline__ uint4 ld_sys_v4(const uint4* p) {
 
 template <typename T, int OP>
 __global__ void __launch_bounds__(256)
-array_allreduce_kernel(int rank, int world, uint32_t epoch, ArrayBoxes ab, uint4* __restrict__ dst, uint32_t n_vec, int dbg) {
+array_allreduce_kernel(int rank, int world, uint32_t epoch, ArrayBoxes ab, uint4* __restrict__ dst, uint32_t n_vec) {
     static_assert(sizeof(T) == 4, "4-byte elements");
     const uint32_t i = blockIdx.x * 256 + threadIdx.x;
     if (i >= n_vec) return;
@@ -223,7 +223,7 @@ array_allreduce_kernel(int rank, int world, uint32_t epoch, ArrayBoxes ab, uint4
 #pragma unroll
     for (int q = 0; q < HJ_MAX_PEERS; q++)
         if (q < world && q != rank) {
-            uint4* to = ((dbg & 1) ? ab.box[rank] + (size_t)q * slot_vecs : ab.box[q] + (size_t)rank * slot_vecs) + 2 * (size_t)i;
+            uint4* to = ab.box[q] + (size_t)rank * slot_vecs + 2 * (size_t)i;
             st_sys_v4(to, w0);
             st_sys_v4(to + 1, w1);
         }
@@ -281,9 +281,8 @@ hj_status peer_array_allreduce(hj_comm* c, hj_reduce_op op, void* dst, size_t n)
     ArrayBoxes ab;
     for (int r = 0; r < HJ_MAX_PEERS; r++)
         ab.box[r] = r < c->world ? (uint4*)(reinterpret_cast<char*>(c->peer_arraybox[r]) + parity_off) : nullptr;
-    static const int dbg = getenv("HJ_PEER_ARRAY_DBG") ? atoi(getenv("HJ_PEER_ARRAY_DBG")) : 0;  // 1: loop back (timing only)
 #define HJ_COMBINE(OP) \
-    array_allreduce_kernel<T, OP><<<grid, 256, 0, c->dev->stream>>>(c->rank, c->world, c->xepoch, ab, (uint4*)dst, n_vec, dbg)
+    array_allreduce_kernel<T, OP><<<grid, 256, 0, c->dev->stream>>>(c->rank, c->world, c->xepoch, ab, (uint4*)dst, n_vec)
     switch (op) {
     case HJ_REDUCE_SUM: HJ_COMBINE(HJ_REDUCE_SUM); break;
     case HJ_REDUCE_MAX: HJ_COMBINE(HJ_REDUCE_MAX); break;
