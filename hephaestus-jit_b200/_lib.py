@@ -208,6 +208,7 @@ _SIGS = {
     "hj_tr_to_host": (_i32, [_u64, _u64, _u64, _vp]),
     "hj_tr_compile": (_i32, [_pvp]),
     "hj_tr_compile_fn": (_i32, [_pu64, _u32, _pu64, _u32, _pvp]),
+    "hj_ir_index_zero_fill": (_i32, [ctypes.POINTER(Ir), _u32, ctypes.POINTER(_u32), ctypes.POINTER(_i32)]),
     "hj_graph_retain": (_i32, [_vp]),
     "hj_graph_release": (_i32, [_vp]),
     "hj_graph_n_passes": (_u32, [_vp]),

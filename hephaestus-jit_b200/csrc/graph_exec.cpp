@@ -124,6 +124,18 @@ bool match_index_prefill(const hj_ir* ir, uint32_t slot, PrefillMatch* m) {
 }
 }  // namespace
 
+// What execute_graph decides for a kernel pass in front of a Compress pass, exposed so that the
+// decision can be tested without a GPU: 1 if buffer slot `slot` of `ir` is only ever written by a
+// top-level, unconditional `Scatter(BufferRef(slot), Literal 0u32, Index)`.
+extern "C" int32_t hj_ir_index_zero_fill(const hj_ir* ir, uint32_t slot, uint32_t* scatter_var, int32_t* nothing_else) {
+    if (!ir || !validate_ir(ir).empty()) return 0;
+    PrefillMatch m;
+    if (!match_index_prefill(ir, slot, &m)) return 0;
+    if (scatter_var) *scatter_var = m.scatter_var;
+    if (nothing_else) *nothing_else = m.only_side_effect ? 1 : 0;
+    return 1;
+}
+
 extern "C" hj_status hj_execute_graph(hj_device* dev, const hj_pass* passes, uint32_t n_passes,
                                       hj_buffer* const* env, const hj_buffer_desc* descs,
                                       uint32_t n_resources, hj_report* report) {

@@ -282,6 +282,13 @@ hj_status hj_execute_graph(hj_device* dev, const hj_pass* passes, uint32_t n_pas
                            hj_buffer* const* env, const hj_buffer_desc* descs,
                            uint32_t n_resources, hj_report* report /* may be NULL */);
 
+/* The zero-fill of a Compress pass's index buffer (`index = sized_literal(0, n)`, trace.rs:1600-1601)
+ * is left to the compaction when the kernel pass in front holds it as a plain store: returns 1 if
+ * buffer slot `slot` of `ir` is only ever written by a top-level, unconditional
+ * Scatter(BufferRef(slot), Literal 0u32, Index) and never read; *scatter_var = that variable,
+ * *nothing_else = 1 if the kernel has no other side effect (the pass is then skipped).  Host-only. */
+int32_t hj_ir_index_zero_fill(const hj_ir* ir, uint32_t slot, uint32_t* scatter_var, int32_t* nothing_else);
+
 /* The same call for a pass list the caller launches again and again — what FCache::call does
  * with a recorded function's Graph (hephaestus-jit/src/record.rs:120-210, graph.rs:192-400; the
  * reference re-records and re-submits a Vulkan command buffer on every launch,

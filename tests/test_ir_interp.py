@@ -9,6 +9,7 @@ import pytest
 
 import ir_cases
 from oracle import ir_interp
+from oracle import ir_interp as I  # op / type constants
 
 irm = importlib.import_module("hephaestus-jit_b200.ir")
 
@@ -120,3 +121,51 @@ def test_malformed_ir_is_rejected():
     b.scatter_reduce(3, r, b.literal(irm.U32, 1), b.index())
     with pytest.raises(hj.HjError):
         irm.codegen(b.build())
+
+
+# ---- execute_graph's decision to leave the index zero-fill of a Compress pass to the compaction ------------
+def _zero_fill_match(builder, slot):
+    import ctypes
+    L = importlib.import_module("hephaestus-jit_b200._lib")
+    var, only = ctypes.c_uint32(0xFFFFFFFF), ctypes.c_int32(-1)
+    assert "hj_kernel" in irm.codegen(builder.build())  # a well-formed kernel: a rejection below is the matcher's
+    hit = L.lib.hj_ir_index_zero_fill(ctypes.byref(builder.build()), slot, ctypes.byref(var), ctypes.byref(only))
+    return (hit, var.value, only.value)
+
+
+def test_index_zero_fill_matcher():
+    """The store may only be dropped when dropping it cannot be observed: a plain, unconditional,
+    top-level `index[i] = 0u32` at the bare Index into a buffer nothing else in the kernel touches."""
+    def fill_kernel(lit=0, kind=I.U32, with_mask=False, cond=False, idx_expr=False, read_back=False, in_loop=False):
+        b = irm.IRBuilder()
+        zero = b.literal(kind, lit)
+        ref = b.buffer_ref(b.scalar(kind))
+        idx = b.index()
+        where = b.bop(I.BOP_ADD, b.scalar(I.U32), idx, b.literal(I.U32, 1)) if idx_expr else idx
+        c = b.bop(I.BOP_LT, b.scalar(I.BOOL), idx, b.literal(I.U32, 5)) if cond else None
+        if in_loop:
+            state = b.push(I.OP_CONSTRUCT, b.struct([b.scalar(I.BOOL)]), [b.literal(I.BOOL, 0)])
+            start = b.push(I.OP_LOOP_START, b.struct([b.scalar(I.BOOL)]), [state])
+        sc = b.scatter(ref, zero, where, c)
+        if in_loop:
+            b.push(I.OP_LOOP_END, b.struct([b.scalar(I.BOOL)]), [start, state])
+        if with_mask:  # the usual shape: the mask of the compaction is computed by the same kernel
+            m = b.bop(I.BOP_LT, b.scalar(I.BOOL), idx, b.literal(I.U32, 10))
+            b.scatter(b.buffer_ref(b.scalar(I.BOOL)), m, idx)
+        if read_back:
+            v = b.gather(b.scalar(kind), ref, idx)
+            b.scatter(b.buffer_ref(b.scalar(kind)), v, idx)
+        return b, sc
+
+    b, sc = fill_kernel()
+    assert _zero_fill_match(b, 0) == (1, sc, 1)                    # nothing else in the kernel: skip the pass
+    b, sc = fill_kernel(with_mask=True)
+    assert _zero_fill_match(b, 0) == (1, sc, 0)                    # the mask store stays, the fill goes
+    assert _zero_fill_match(b, 1)[0] == 0                          # the mask buffer is not a zero fill
+    assert _zero_fill_match(fill_kernel(lit=7)[0], 0)[0] == 0      # not zero
+    assert _zero_fill_match(fill_kernel(kind=I.F32)[0], 0)[0] == 0  # not the u32 index type
+    assert _zero_fill_match(fill_kernel(cond=True)[0], 0)[0] == 0  # conditional store
+    assert _zero_fill_match(fill_kernel(idx_expr=True)[0], 0)[0] == 0  # not at the bare Index
+    assert _zero_fill_match(fill_kernel(read_back=True)[0], 0)[0] == 0  # the kernel reads the buffer too
+    assert _zero_fill_match(fill_kernel(in_loop=True)[0], 0)[0] == 0    # inside a recorded loop
+    assert _zero_fill_match(fill_kernel()[0], 3)[0] == 0           # no such slot
