@@ -17,6 +17,11 @@
 //   pass       : resources[], i32 size_buffer, u32 is_kernel, u64 size, device op {code, arg},
 //                and for kernel passes the IR arrays verbatim (hj_ir_var, deps, hj_type_desc,
 //                struct_fields, n_buffers — the IR carries its own type table)
+// The checksum detects corruption; structure is validated on load (ids in range, well-formed IR) so
+// that a damaged file ends in an error, never in a crash of the parser
+// (tests: test_graph_deserialize_survives_mutations_behind_a_valid_checksum).  It is a cache format for
+// files the process wrote itself, not a sandbox: like any traced program, a graph can address its
+// buffers out of range if its indices say so.
 // Internal resources that were bound to LIVE variables when the graph was compiled (scheduled
 // variables the caller still held) have no variable on the loading side: they become plain
 // temporaries, and results leave through `outputs` (which is how record() returns them).

@@ -335,3 +335,36 @@ def test_graph_wire_format_is_stable():
     g = tr.Graph.deserialize(blob)
     assert g.debug_string() == want
     assert g.serialize() == blob
+
+
+def test_graph_deserialize_survives_mutations_behind_a_valid_checksum():
+    """Corruption the checksum cannot see (here: the checksum is recomputed after every mutation) must
+    end in an error or in a well-formed graph, never in a crash of the parser."""
+    import random
+    import struct
+
+    def fnv(data):
+        h = 0xCBF29CE484222325
+        for b in data:
+            h = ((h ^ b) * 0x100000001B3) & 0xFFFFFFFFFFFFFFFF
+        return h
+
+    with open(os.path.join(HERE, "golden", "graph_wire_v1.hjgraph"), "rb") as f:
+        blob = f.read()
+    body = blob[:-8]
+    assert fnv(body) == struct.unpack("<Q", blob[-8:])[0]
+    rnd = random.Random(1234)
+    accepted = rejected = 0
+    for _ in range(400):
+        m = bytearray(body)
+        for _ in range(rnd.choice((1, 1, 2, 4))):
+            m[rnd.randrange(12, len(m))] = rnd.choice((0, 1, 0xFF, 0x7F, 0x80, rnd.randrange(256)))
+        try:
+            g = tr.Graph.deserialize(bytes(m) + struct.pack("<Q", fnv(m)))
+            g.debug_string()
+            g.serialize()
+            accepted += 1
+            del g
+        except hj.HjError:
+            rejected += 1
+    assert accepted + rejected == 400 and rejected > 0
