@@ -169,3 +169,38 @@ def test_index_zero_fill_matcher():
     assert _zero_fill_match(fill_kernel(read_back=True)[0], 0)[0] == 0  # the kernel reads the buffer too
     assert _zero_fill_match(fill_kernel(in_loop=True)[0], 0)[0] == 0    # inside a recorded loop
     assert _zero_fill_match(fill_kernel()[0], 3)[0] == 0           # no such slot
+
+
+def test_codegen_rejects_or_lowers_mutated_ir_without_crashing():
+    """hj_ir_codegen is the boundary a foreign host hands IR to: a damaged IR (wild type ids, deps,
+    op tags, slot counts) must be refused by validate_ir or lowered, never crash the library."""
+    import random
+    hj = importlib.import_module("hephaestus-jit_b200")
+    rnd = random.Random(99)
+    cases = [c() for c in ir_cases.ALL_CASES]
+    lowered = rejected = 0
+    for _ in range(400):
+        b = copy.deepcopy(rnd.choice(cases).builder)
+        b._keep = None
+        for _ in range(rnd.choice((1, 1, 2, 3))):
+            what = rnd.randrange(4)
+            if what == 0:
+                i = rnd.randrange(len(b.vars))
+                v = list(b.vars[i])
+                v[rnd.randrange(6)] = rnd.choice((0, 1, 2, 3, 5, 7, 20, 23, 24, 0xFFFFFFFF, rnd.randrange(64)))
+                b.vars[i] = tuple(v)
+            elif what == 1 and b.deps:
+                b.deps[rnd.randrange(len(b.deps))] = rnd.choice((0, len(b.vars) - 1, len(b.vars), 0xFFFFFFFF, rnd.randrange(64)))
+            elif what == 2:
+                i = rnd.randrange(len(b.types))
+                t = list(b.types[i])
+                t[rnd.randrange(6)] = rnd.choice((0, 1, 3, 13, 14, 15, 16, 17, 255, 0xFFFFFFFF))
+                b.types[i] = tuple(t)
+            else:
+                b.n_buffers = rnd.choice((0, 1, 2, 100))
+        try:
+            irm.codegen(b.build())
+            lowered += 1
+        except hj.HjError:
+            rejected += 1
+    assert lowered + rejected == 400 and rejected > 50
