@@ -212,10 +212,14 @@ Graph* compile_graph(ThreadState& ts, const std::vector<VarId>& inputs, const st
     std::unique_ptr<Graph> graph(new Graph());
     static std::atomic<uint64_t> next_uid{1};
     graph->uid = next_uid.fetch_add(1);
-    {
+    // The reference panics on the errors below (the process is gone); here they are reported to the
+    // caller, so nothing may be left behind: the builder's temporary references and the schedule
+    // (which graph::compile consumes either way, trace.rs:528-536) are released on every path.
+    try {
         std::lock_guard<std::mutex> lock(g_trace_mu);
         Trace& trace = g_trace;
         GraphBuilder gb(trace);
+        try {
         auto need = [&](VarId id) {
             int r = gb.try_push_resource(id);
             if (r < 0) throw TraceError("Resource does not match variable type! (graph::Error::ResourceMissmatch)");
@@ -296,6 +300,14 @@ Graph* compile_graph(ThreadState& ts, const std::vector<VarId>& inputs, const st
             graph->resources.push_back(r);
         }
         graph->resource_descs = gb.descs;
+        } catch (...) {
+            for (size_t i = graph->resources.size(); i < gb.keys.size(); i++)
+                if (trace.get(gb.keys[i])) trace.dec_rc(gb.keys[i]);
+            throw;
+        }
+    } catch (...) {
+        ts.clear();
+        throw;
     }
     ts.clear();  // the schedule's references are dropped with the ThreadState (trace.rs:528-536)
     return graph.release();

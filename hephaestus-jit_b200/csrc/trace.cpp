@@ -428,6 +428,12 @@ static bool reindex(VarId self, VarId new_idx, VarId* out) {
         *out = ref_clone(self);
         return true;
     }
+    // The reference re-creates a device op (reduce / scan / compress) met on the way with the extent
+    // of the new index (trace.rs:1110-1118) and then panics in the compiler (`todo!()`,
+    // compiler.rs:131) — `x.reduce_sum().gather(0)` over a pure index expression cannot be traced
+    // there.  A device op is not an elementwise expression: it is evaluated and gathered from, like
+    // any other buffer.
+    if (snapshot.op.kind == OpKind::DeviceOp) return false;
     std::vector<VarId> deps;
     for (VarId d : snapshot.deps) {
         VarId nd;

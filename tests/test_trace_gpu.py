@@ -836,3 +836,18 @@ np.save({str(tmp_path / "picked.npy")!r}, picked.to_vec(np.uint32))
     assert np.array_equal(np.load(tmp_path / "z.npy"), want[0])
     assert np.array_equal(np.load(tmp_path / "scan.npy"), want[1])
     assert np.array_equal(np.load(tmp_path / "picked.npy")[: len(want[2])], want[2])
+
+
+def test_gather_from_a_device_op(device):
+    """The reduction result broadcast back over the array (`x + x.reduce_sum().gather(0)`) when x is a pure
+    index expression; the reference cannot trace this (it re-creates the device op while re-indexing and
+    panics in its compiler, trace.rs:1110-1118, compiler.rs:131)."""
+    n = 1000
+    a = tr.sized_index(n)
+    y = a.add(a.reduce_sum().gather(tr.literal(0, U32)))
+    s = a.prefix_sum(True).gather(tr.sized_index(10).mul(tr.literal(7, U32)))
+    y.schedule()
+    s.schedule()
+    tr.compile().launch(device)
+    assert np.array_equal(y.to_vec(np.uint32), np.arange(n, dtype=np.uint32) + np.uint32(n * (n - 1) // 2))
+    assert np.array_equal(s.to_vec(np.uint32), np.cumsum(np.arange(n, dtype=np.uint32), dtype=np.uint32)[::7][:10])
