@@ -214,6 +214,7 @@ _SIGS = {
     "hj_graph_n_passes": (_u32, [_vp]),
     "hj_graph_n_outputs": (_u32, [_vp]),
     "hj_graph_debug_string": (_i32, [_vp, _pvp]),
+    "hj_graph_pass_ir": (_i32, [_vp, _u32, ctypes.POINTER(ctypes.POINTER(Ir))]),
     "hj_graph_serialize": (_i32, [_vp, _pvp, ctypes.POINTER(_sz)]),
     "hj_graph_deserialize": (_i32, [_vp, ctypes.c_char_p, _sz, _pvp]),
     "hj_graph_launch": (_i32, [_vp, _vp, _pu64, _u32, _pu64, ctypes.POINTER(GraphReport)]),

@@ -111,8 +111,10 @@ struct Compiler {
 
     // compiler.rs:135-186
     uint32_t collect_data(VarId id) {
-        auto it = visited.find(id);
-        if (it != visited.end()) return it->second;
+        // The reference looks `id` up in `visited` first (compiler.rs:137-139) — the map of VALUES.  A
+        // variable that one kernel uses both as a value and through a reference (`b < b` next to
+        // `b.gather(i)`), value first, then yields Gather(value, i): GLSL that does not compile.  The
+        // BufferRef itself is de-duplicated by the trivial-variable CSE of push_var.
         const Var& var = trace.var(id);
         Op r = resulting_op(var.op);
         if (r.kind != OpKind::Buffer) throw TraceError("reference to a variable that does not evaluate to a buffer");

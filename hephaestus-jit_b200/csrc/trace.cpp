@@ -424,10 +424,17 @@ static bool reindex(VarId self, VarId new_idx, VarId* out) {
         snapshot.ty = v.ty;
         snapshot.deps = v.deps;
     }
-    if (snapshot.op.kind == OpKind::KernelOp && snapshot.op.code == HJ_OP_BUFFER_REF) {  // is_ref()
+    if (snapshot.op.kind == OpKind::KernelOp && snapshot.op.code == HJ_OP_BUFFER_REF) {  // is_ref() (trace.rs:951-953)
         *out = ref_clone(self);
         return true;
     }
+    // A reference made by get_ref (Op::Ref) is not is_ref() in the reference, which therefore re-indexes
+    // the variable BEHIND it: that fails for evaluated variables (-> the caller evaluates and gathers, the
+    // only outcome that works there), but for a scheduled, not yet launched pure expression it
+    // "succeeds" and leaves a reference to a variable nobody scheduled — a kernel that cannot be
+    // compiled (found by random-program fuzzing: `b = a.gather(i); b.gather(j)` with a = index + 1).
+    // Stopping at the reference gives the working outcome in both cases.
+    if (snapshot.op.kind == OpKind::Ref) return false;
     // The reference re-creates a device op (reduce / scan / compress) met on the way with the extent
     // of the new index (trace.rs:1110-1118) and then panics in the compiler (`todo!()`,
     // compiler.rs:131) — `x.reduce_sum().gather(0)` over a pure index expression cannot be traced

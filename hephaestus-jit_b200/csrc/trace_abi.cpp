@@ -15,6 +15,8 @@ using namespace hj::tr;
 struct hj_graph {
     std::unique_ptr<Graph> g;
     std::atomic<int> rc{1};
+    std::vector<hj_ir> ir_views;  // hj_graph_pass_ir: views into the passes' owned IR, built on first use
+    std::mutex views_mu;
 };
 
 namespace {
@@ -200,6 +202,22 @@ hj_status hj_graph_debug_string(hj_graph* g, char** out) {
         memcpy(*out, s.c_str(), s.size() + 1);
     });
 }
+// The flat IR of kernel pass `pass` (what hj_execute_graph hands to the NVRTC stage), valid while the
+// graph is alive; *out = NULL for device-op passes.  Lets a host inspect / pre-compile the kernels of a
+// graph (hj_ir_codegen, hj_ir_compile_cubin) without launching it.
+hj_status hj_graph_pass_ir(hj_graph* g, uint32_t pass, const hj_ir** out) {
+    HJ_REQUIRE(g && out, "hj_graph_pass_ir: null argument");
+    HJ_REQUIRE(pass < g->g->passes.size(), "hj_graph_pass_ir: pass %u out of range (%zu passes)", pass, g->g->passes.size());
+    std::lock_guard<std::mutex> lock(g->views_mu);
+    if (g->ir_views.empty()) {
+        g->ir_views.resize(g->g->passes.size());
+        for (size_t i = 0; i < g->g->passes.size(); i++)
+            if (g->g->passes[i].is_kernel) g->ir_views[i] = g->g->passes[i].ir.view();
+    }
+    *out = g->g->passes[pass].is_kernel ? &g->ir_views[pass] : nullptr;
+    return HJ_OK;
+}
+
 // Wire format of a compiled graph (tgraph_io.cpp).  *bytes_out is malloc'ed: free with hj_free_string.
 hj_status hj_graph_serialize(hj_graph* g, void** bytes_out, size_t* n_out) {
     HJ_REQUIRE(g && bytes_out && n_out, "hj_graph_serialize: null argument");

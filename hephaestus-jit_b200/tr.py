@@ -505,6 +505,13 @@ class Graph:
         lib.hj_free_string(out)
         return s
 
+    def pass_ir(self, index: int):
+        """The flat IR (``_lib.Ir``) of kernel pass ``index``, or None for a device-op pass; valid while
+        this Graph is alive (``ir.codegen`` / ``ir.compile_cubin`` accept it)."""
+        out = ctypes.POINTER(_lib.Ir)()
+        check(lib.hj_graph_pass_ir(self._h, index, ctypes.byref(out)))
+        return out.contents if out else None
+
     def serialize(self) -> bytes:
         """Wire format of the graph (passes + kernel IR + resources + captured buffer contents);
         the reference keeps graphs in memory only (graph.rs:145-151)."""

@@ -437,6 +437,9 @@ hj_status hj_graph_retain(hj_graph* g);
 hj_status hj_graph_release(hj_graph* g);
 uint32_t hj_graph_n_passes(hj_graph* g);
 uint32_t hj_graph_n_outputs(hj_graph* g);
+/* The flat IR of kernel pass `pass` (valid while the graph is alive; *out = NULL for device-op
+ * passes): inspect or pre-compile a graph's kernels with hj_ir_codegen / hj_ir_compile_cubin. */
+hj_status hj_graph_pass_ir(hj_graph* g, uint32_t pass, const hj_ir** out);
 /* Wire format of a compiled graph: passes with their kernel IR, resource table, inputs/outputs and
  * the contents of captured buffers (the reference keeps graphs in memory only, graph.rs:145-151;
  * together with the on-disk cubin cache a recorded function starts in a fresh process without

@@ -440,3 +440,50 @@ def test_gather_from_a_device_op_evaluates_it():
     graph = tr.compile()
     text = graph.debug_string()
     assert graph.n_passes() == 3 and "ReduceOp(" in text and "Gather(" in text
+
+
+def _lower_every_kernel(graph):
+    irm = import_module("hephaestus-jit_b200.ir")
+    n = 0
+    for i in range(graph.n_passes()):
+        ir = graph.pass_ir(i)
+        if ir is not None:
+            assert "hj_kernel" in irm.codegen(ir)
+            n += 1
+    return n
+
+
+def test_value_and_reference_of_one_variable_in_one_kernel():
+    """`b < b` next to `b.gather(i)`: the reference's compiler resolves the reference through its map of
+    VALUES (compiler.rs:137-139) and emits Gather(value, i), which does not compile; here the reference
+    stays a BufferRef whatever was collected first."""
+    n = 64
+    y = tr.sized_literal(5, n, U32).add(tr.sized_index(n))
+    y.schedule()
+    s = y.prefix_sum(True)
+    b = y.gather(s.and_(tr.literal(0, U32)))
+    d = b.gather(y.and_(tr.literal(0, U32)))
+    c = y.select(b.lt(b), d)
+    c.schedule()
+    g = tr.compile()
+    assert _lower_every_kernel(g) == g.n_passes() - 1   # every pass but the PrefixSum is a kernel that lowers
+    text = g.debug_string()
+    last = text[text.rindex("Kernel {"):]
+    gathers = [ln for ln in last.splitlines() if "= Gather(" in ln]
+    refs = {ln.split(":")[0].strip() for ln in last.splitlines() if "= BufferRef(" in ln}
+    assert gathers and all(ln.split("Gather(")[1].split(",")[0].strip() in refs for ln in gathers)
+
+
+def test_gather_of_a_gather_of_a_scheduled_expression():
+    """`b = a.gather(i); c = b.gather(j)` with `a` scheduled but not launched: re-indexing must stop at the
+    reference to `a` (the reference re-indexes the variable behind it and leaves a kernel reading a buffer
+    nobody writes).  `a` is evaluated once, then gathered from."""
+    n = 64
+    a = tr.sized_index(n).add(tr.literal(1, U32))
+    b = a.gather(tr.literal(n - 1, U32).sub(tr.sized_index(n)))
+    c = b.gather(tr.sized_index(n).shr(tr.literal(1, U32)))
+    c.schedule()
+    g = tr.compile()
+    assert _lower_every_kernel(g) == g.n_passes()
+    text = g.debug_string()
+    assert text.count("Bop(Add)") == 1   # `a` is computed by exactly one kernel, never re-traced at another index

@@ -851,3 +851,19 @@ def test_gather_from_a_device_op(device):
     tr.compile().launch(device)
     assert np.array_equal(y.to_vec(np.uint32), np.arange(n, dtype=np.uint32) + np.uint32(n * (n - 1) // 2))
     assert np.array_equal(s.to_vec(np.uint32), np.cumsum(np.arange(n, dtype=np.uint32), dtype=np.uint32)[::7][:10])
+
+
+def test_gather_chains_over_scheduled_expressions(device):
+    """Gather of a gather over a pure index expression, and a variable used both as a value and through a
+    reference in one kernel (two places where the restated host layer leaves the reference)."""
+    n = 64
+    a = tr.sized_index(n).add(tr.literal(1, U32))                     # a[k] = k + 1
+    b = a.gather(tr.literal(n - 1, U32).sub(tr.sized_index(n)))         # b[k] = a[n-1-k] = n - k
+    c = b.gather(tr.sized_index(n).shr(tr.literal(1, U32)))             # c[k] = b[k/2]   = n - k/2
+    e = b.select(b.lt(c), c)                                            # min(b, c)       = n - k
+    c.schedule()
+    e.schedule()
+    tr.compile().launch(device)
+    k = np.arange(n, dtype=np.uint32)
+    assert np.array_equal(c.to_vec(np.uint32), n - k // 2)
+    assert np.array_equal(e.to_vec(np.uint32), np.minimum(n - k, n - k // 2))
