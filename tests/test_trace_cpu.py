@@ -7,6 +7,7 @@ import gc
 import importlib
 import os
 
+import numpy as np
 import pytest
 
 hj = importlib.import_module("hephaestus-jit_b200")
@@ -487,3 +488,85 @@ def test_gather_of_a_gather_of_a_scheduled_expression():
     assert _lower_every_kernel(g) == g.n_passes()
     text = g.debug_string()
     assert text.count("Bop(Add)") == 1   # `a` is computed by exactly one kernel, never re-traced at another index
+
+
+# ---- whole graphs executed on the CPU (oracle/graph_exec.py) against the numpy statement of the program ----
+def _random_program(rnd, n):
+    """Builds a random traced program and, side by side, its values in numpy.  Returns (outputs, expected):
+    lists of VarRefs and of (array, valid_count or None)."""
+    k_ = np.arange(n, dtype=np.uint32)
+    pool = [(tr.sized_index(n), k_.copy()), (tr.sized_literal(7, n, U32), np.full(n, 7, np.uint32))]
+    bools = [(tr.sized_index(n).lt(tr.literal(n // 2 + 1, U32)), k_ < n // 2 + 1)]
+    terminal = []
+    with np.errstate(over="ignore"):
+        for _ in range(rnd.randrange(4, 18)):
+            op = rnd.randrange(11)
+            (va, a), (vb, b) = rnd.choice(pool), rnd.choice(pool)
+            if op == 0:
+                pool.append((va.add(vb), a + b))
+            elif op == 1:
+                c = rnd.randrange(1, 9)
+                pool.append((va.mul(tr.literal(c, U32)), a * np.uint32(c)))
+            elif op == 2:
+                c = rnd.randrange(0, 5)
+                pool.append((va.shr(tr.literal(c, U32)), a >> np.uint32(c)))
+            elif op == 3:
+                bools.append((va.lt(vb), a < b))
+            elif op == 4:
+                vm, m = rnd.choice(bools)
+                pool.append((va.select(vm, vb), np.where(m, a, b)))
+            elif op == 5:  # gather at an in-range index expression
+                idx_v, idx = vb.and_(tr.literal(n - 1 if n & (n - 1) == 0 else 0, U32)), b & np.uint32(n - 1 if n & (n - 1) == 0 else 0)
+                pool.append((va.gather(idx_v), a[idx]))
+            elif op == 6:
+                inc = rnd.random() < 0.5
+                cs = np.cumsum(a, dtype=np.uint32)
+                pool.append((va.prefix_sum(inc), cs if inc else cs - a))
+            elif op == 7:  # reduction broadcast back
+                pool.append((vb.add(va.reduce_sum().gather(tr.literal(0, U32))), b + a.sum(dtype=np.uint32)))
+            elif op == 8:  # compress: indices, then zeros
+                vm, m = rnd.choice(bools)
+                cnt, idx = vm.compress()
+                want = np.zeros(n, np.uint32)
+                sel = np.nonzero(m)[0].astype(np.uint32)
+                want[: sel.size] = sel
+                pool.append((idx, want))
+                terminal.append((cnt, (np.array([sel.size], np.uint32), None)))
+            elif op == 9:  # compress_dyn: only the first `count` entries are defined
+                vm, m = rnd.choice(bools)
+                sel = np.nonzero(m)[0].astype(np.uint32)
+                terminal.append((vm.compress_dyn().add(tr.literal(3, U32)), (sel + np.uint32(3), sel.size)))
+            elif op == 10:  # scatter through a permutation into a fresh buffer
+                dst = tr.sized_literal(0, n, U32)
+                va.scatter(dst, tr.literal(n - 1, U32).sub(tr.sized_index(n)))
+                pool.append((dst, a[::-1].copy()))
+    outs = [pool[-1], rnd.choice(pool)] + [(v, (w, None)) if not isinstance(w, tuple) else (v, w) for v, w in terminal]
+    outputs = [v for v, _ in outs]
+    expected = [w if isinstance(w, tuple) else (w, None) for _, w in outs]
+    return outputs, expected
+
+
+def test_random_programs_execute_like_numpy():
+    """Trace -> schedule -> graph -> wire format -> CPU pass interpreter (kernel passes: IR interpreter,
+    device ops: the C restatement of the reference's builtins) must give what numpy gives for the same
+    program.  No GPU involved: this checks the host layers and the IR semantics end to end."""
+    import random
+    from oracle import graph_exec
+    rnd = random.Random(2026)
+    gc.collect()
+    base = tr.n_live()
+    checked = 0
+    for it in range(80):
+        n = rnd.choice((1, 8, 64, 1000))
+        outputs, expected = _random_program(rnd, n)
+        g = tr.compile_fn([], outputs)
+        got = graph_exec.execute(g.serialize())
+        for o, (want, valid) in zip(got, expected):
+            m = want.size if valid is None else valid
+            assert np.array_equal(o[:m].astype(np.uint32), want[:m]), (it, n, g.debug_string()[-2500:])
+            checked += 1
+        del g, outputs, expected, got
+        hj.lib.hj_tr_reset_schedule()
+        gc.collect()
+        assert tr.n_live() == base
+    assert checked >= 160
