@@ -500,7 +500,7 @@ def _random_program(rnd, n):
     terminal = []
     with np.errstate(over="ignore"):
         for _ in range(rnd.randrange(4, 18)):
-            op = rnd.randrange(11)
+            op = rnd.randrange(15)
             (va, a), (vb, b) = rnd.choice(pool), rnd.choice(pool)
             if op == 0:
                 pool.append((va.add(vb), a + b))
@@ -540,6 +540,33 @@ def _random_program(rnd, n):
                 dst = tr.sized_literal(0, n, U32)
                 va.scatter(dst, tr.literal(n - 1, U32).sub(tr.sized_index(n)))
                 pool.append((dst, a[::-1].copy()))
+            elif op == 11:  # recorded loop: x = 3x + 1, `reps` times (loop_record!, record.rs:56-73)
+                reps = rnd.randrange(1, 5)
+
+                def body(c, vs, reps=reps):
+                    x, it = vs
+                    it = it.add(tr.literal(1, U32))
+                    return it.lt(tr.literal(reps, U32)), [x.mul(tr.literal(3, U32)).add(tr.literal(1, U32)), it]
+
+                _, (x1, _it) = tr.loop_record(tr.literal(True), [va, tr.sized_literal(0, n, U32)], body)
+                w = a.copy()
+                for _ in range(reps):
+                    w = w * np.uint32(3) + np.uint32(1)
+                pool.append((x1, w))
+            elif op == 12:  # recorded if: x + 7 where the condition holds (if_record!, record.rs:74-91)
+                vm, m = rnd.choice(bools)
+                _, (x1,) = tr.if_record(vm, [va], lambda c, vs: (c, [vs[0].add(tr.literal(7, U32))]))
+                pool.append((x1, np.where(m, a + np.uint32(7), a)))
+            elif op == 13:  # scatter-reduce (sum) into 16 bins, read back per lane
+                dst = tr.sized_literal(0, 16, U32)
+                va.scatter_reduce(dst, vb.and_(tr.literal(15, U32)), hj.SUM)
+                bins = np.zeros(16, np.uint32)
+                np.add.at(bins, b & np.uint32(15), a)
+                pool.append((dst.gather(tr.sized_index(n).and_(tr.literal(15, U32))), bins[k_ & np.uint32(15)]))
+            elif op == 14:  # through f32 and back, exact for small integers
+                small_v, small = va.and_(tr.literal(1023, U32)), a & np.uint32(1023)
+                pool.append((small_v.cast(F32).fma(tr.literal(2.0, F32), tr.literal(1.0, F32)).cast(U32),
+                             small * np.uint32(2) + np.uint32(1)))
     outs = [pool[-1], rnd.choice(pool)] + [(v, (w, None)) if not isinstance(w, tuple) else (v, w) for v, w in terminal]
     outputs = [v for v, _ in outs]
     expected = [w if isinstance(w, tuple) else (w, None) for _, w in outs]
