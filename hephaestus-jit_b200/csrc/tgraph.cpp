@@ -122,36 +122,65 @@ struct Compiler {
         return push_var(HJ_OP_BUFFER_REF, 0, var.ty, slot, {});
     }
 
-    // compiler.rs:66-134
-    uint32_t collect(VarId id) {
-        auto it = visited.find(id);
-        if (it != visited.end()) return it->second;
+    // compiler.rs:66-134.  The reference recurses over the dependencies; a chain of a few hundred
+    // thousand dependent operations (its own `compile` bench traces 10 000) would overflow the stack,
+    // so the same post-order walk — dependencies left to right, then the variable itself, which is
+    // what fixes the numbering of the IR — runs on an explicit stack here.
+    bool collect_leaf(VarId id, uint32_t* out) {  // everything that needs no walk of its own
         const Var& var = trace.var(id);
-        uint32_t out;
         switch (var.op.kind) {
-        case OpKind::Ref: out = collect_data(var.deps.at(0)); break;
+        case OpKind::Ref: *out = collect_data(var.deps.at(0)); return true;
         case OpKind::Buffer: {
             uint32_t data = collect_data(id);
             uint32_t idx = push_var(HJ_OP_INDEX, 0, type_scalar(HJ_U32), 0, {});
-            out = push_var(HJ_OP_GATHER, 0, var.ty, 0, {data, idx});
-            break;
+            *out = push_var(HJ_OP_GATHER, 0, var.ty, 0, {data, idx});
+            return true;
         }
         case OpKind::KernelOp:
-            if (var.op.code == HJ_OP_LITERAL) {
-                out = push_var(HJ_OP_LITERAL, 0, var.ty, var.data.lit, {});
-            } else {
-                std::vector<VarId> tdeps = var.deps;  // collect() may grow the trace-independent state only
-                std::vector<uint32_t> deps;
-                for (VarId d : tdeps) deps.push_back(collect(d));
-                const Var& v2 = trace.var(id);
-                out = push_var(v2.op.code, v2.op.arg, v2.ty, 0, deps);
-            }
-            break;
+            if (var.op.code != HJ_OP_LITERAL) return false;
+            *out = push_var(HJ_OP_LITERAL, 0, var.ty, var.data.lit, {});
+            return true;
         default:
             throw TraceError("a kernel depends on an unevaluated device op (todo!() in the reference, compiler.rs:131)");
         }
-        visited[id] = out;
-        return out;
+    }
+    uint32_t collect(VarId root) {
+        auto hit = visited.find(root);
+        if (hit != visited.end()) return hit->second;
+        uint32_t out;
+        if (collect_leaf(root, &out)) {
+            visited[root] = out;
+            return out;
+        }
+        struct Frame {
+            VarId id;
+            std::vector<VarId> tdeps;
+            std::vector<uint32_t> deps;
+        };
+        std::vector<Frame> stack;
+        stack.push_back({root, trace.var(root).deps, {}});
+        while (true) {
+            Frame& f = stack.back();
+            if (f.deps.size() < f.tdeps.size()) {
+                const VarId d = f.tdeps[f.deps.size()];
+                auto it = visited.find(d);
+                if (it != visited.end()) {
+                    f.deps.push_back(it->second);
+                } else if (collect_leaf(d, &out)) {
+                    visited[d] = out;
+                    stack.back().deps.push_back(out);
+                } else {
+                    stack.push_back({d, trace.var(d).deps, {}});  // invalidates f
+                }
+                continue;
+            }
+            const Var& v = trace.var(f.id);
+            out = push_var(v.op.code, v.op.arg, v.ty, 0, f.deps);
+            visited[f.id] = out;
+            stack.pop_back();
+            if (stack.empty()) return out;
+            stack.back().deps.push_back(out);
+        }
     }
 
     // compiler.rs:20-65

@@ -162,18 +162,21 @@ VarId Trace::new_var_id(Var v) {  // trace.rs:104-111
     return ((VarId)s.gen << 32) | idx;
 }
 void Trace::inc_rc(VarId id) { var(id).rc++; }
-void Trace::dec_rc(VarId id) {  // trace.rs:147-160
-    Var& v = var(id);
-    if (--v.rc == 0) {
-        std::vector<VarId> deps = v.deps;
-        if (v.extent.dynamic) deps.push_back(v.extent.size_var);
+void Trace::dec_rc(VarId first) {  // trace.rs:147-160; a work list instead of the reference's recursion:
+    std::vector<VarId> work{first};  // dropping the end of a 300 000-operation chain must not overflow the stack
+    while (!work.empty()) {
+        const VarId id = work.back();
+        work.pop_back();
+        Var& v = var(id);
+        if (--v.rc != 0) continue;
+        work.insert(work.end(), v.deps.begin(), v.deps.end());
+        if (v.extent.dynamic) work.push_back(v.extent.size_var);
         if (v.data.kind == Resource::Buffer && v.data.buf) hj_buffer_release(v.data.buf);
-        uint32_t idx = (uint32_t)id;
+        const uint32_t idx = (uint32_t)id;
         slots[idx].live = false;
         slots[idx].var = Var();
         free_list.push_back(idx);
         n_live--;
-        for (VarId d : deps) dec_rc(d);
     }
 }
 void Trace::advance(VarId id) {  // trace.rs:129-140

@@ -597,3 +597,19 @@ def test_random_programs_execute_like_numpy():
         gc.collect()
         assert tr.n_live() == base
     assert checked >= 160
+
+
+def test_deep_dependency_chain_does_not_overflow_the_stack():
+    """200 000 chained adds (20 x the reference's `compile` bench, benches/compile.rs:6-27): IR lowering
+    and reference counting walk the chain with explicit work lists instead of recursion."""
+    n = 200_000
+    x = tr.sized_literal(1, 2, I32)
+    one = tr.literal(1, I32)
+    for _ in range(n):
+        x = x.add(one)
+    x.schedule()
+    g = tr.compile()
+    assert g.n_passes() == 1
+    ir = g.pass_ir(0)
+    assert ir.n_vars >= n
+    del x, g, ir, one   # dropping the last reference releases the whole chain
