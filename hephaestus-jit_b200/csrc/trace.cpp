@@ -417,7 +417,9 @@ static VarId get_ref(VarId a, bool mutable_) {
 static void mark_dirty(VarId id) { Lock l; g_trace.var(id).dirty = true; }
 
 // VarRef::reindex (trace.rs:1084-1121): re-trace a pure expression of Index at a new index
-static bool reindex(VarId self, VarId new_idx, VarId* out) {
+static bool reindex(VarId self, VarId new_idx, VarId* out, int depth = 0) {
+    // an expression too deep to re-trace recursively is evaluated and gathered from instead
+    if (depth > 4096) return false;
     Var snapshot;
     {
         Lock l;
@@ -447,7 +449,7 @@ static bool reindex(VarId self, VarId new_idx, VarId* out) {
     std::vector<VarId> deps;
     for (VarId d : snapshot.deps) {
         VarId nd;
-        if (!reindex(d, new_idx, &nd)) {
+        if (!reindex(d, new_idx, &nd, depth + 1)) {
             for (VarId x : deps) ref_drop(x);
             return false;
         }
