@@ -503,7 +503,19 @@ def _random_program(rnd, n):
             op = rnd.randrange(15)
             (va, a), (vb, b) = rnd.choice(pool), rnd.choice(pool)
             if op == 0:
-                pool.append((va.add(vb), a + b))
+                which = rnd.randrange(6)
+                if which == 0:
+                    pool.append((va.add(vb), a + b))
+                elif which == 1:
+                    pool.append((va.sub(vb), a - b))          # wraps like the device arithmetic
+                elif which == 2:
+                    pool.append((va.min(vb), np.minimum(a, b)))
+                elif which == 3:
+                    pool.append((va.max(vb), np.maximum(a, b)))
+                elif which == 4:
+                    pool.append((va.or_(vb), a | b))
+                else:
+                    pool.append((va.xor(vb), a ^ b))
             elif op == 1:
                 c = rnd.randrange(1, 9)
                 pool.append((va.mul(tr.literal(c, U32)), a * np.uint32(c)))
