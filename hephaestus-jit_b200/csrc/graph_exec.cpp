@@ -175,8 +175,8 @@ extern "C" hj_status hj_execute_graph(hj_device* dev, const hj_pass* passes, uin
             HistMatch hm;
             if (!size_buf && p.n_resources == 2 && p.size >= (1u << 20) && match_histogram(p.ir, &hm)) {
                 snprintf(name, sizeof(name), "Histogram %u [%llu]", i, (unsigned long long)p.size);
-                hj_buffer *dst, *keys;
-                const hj_buffer_desc* ddst;
+                hj_buffer *dst = nullptr, *keys = nullptr;
+                const hj_buffer_desc* ddst = nullptr;
                 HJ_TRY(res(p, hm.dst_slot, &dst, &ddst));
                 HJ_TRY(res(p, hm.key_slot, &keys, nullptr));
                 HJ_TRY(hj_scatter_reduce(dev, HJ_REDUCE_SUM, (hj_type_kind)hm.ty, p.size, keys, nullptr, hm.literal, dst,
@@ -249,8 +249,8 @@ extern "C" hj_status hj_execute_graph(hj_device* dev, const hj_pass* passes, uin
         }
         case HJ_PASS_REDUCE: {
             snprintf(name, sizeof(name), "Reduce");
-            hj_buffer *dst, *src;
-            const hj_buffer_desc *ddst, *dsrc;
+            hj_buffer *dst = nullptr, *src = nullptr;
+            const hj_buffer_desc *ddst = nullptr, *dsrc = nullptr;
             HJ_TRY(res(p, 0, &dst, &ddst));
             HJ_TRY(res(p, 1, &src, &dsrc));
             HJ_TRY(hj_reduce(dev, (hj_reduce_op)p.arg, (hj_type_kind)ddst->ty, dsrc->size, src, dst));
@@ -258,8 +258,8 @@ extern "C" hj_status hj_execute_graph(hj_device* dev, const hj_pass* passes, uin
         }
         case HJ_PASS_PREFIX_SUM: {
             snprintf(name, sizeof(name), "Prefix Sum Large");
-            hj_buffer *dst, *src;
-            const hj_buffer_desc *ddst, *dsrc;
+            hj_buffer *dst = nullptr, *src = nullptr;
+            const hj_buffer_desc *ddst = nullptr, *dsrc = nullptr;
             HJ_TRY(res(p, 0, &dst, &ddst));
             HJ_TRY(res(p, 1, &src, &dsrc));
             HJ_TRY(hj_prefix_sum(dev, (hj_type_kind)ddst->ty, dsrc->size, (int32_t)p.arg, src, dst, nullptr));
@@ -267,8 +267,8 @@ extern "C" hj_status hj_execute_graph(hj_device* dev, const hj_pass* passes, uin
         }
         case HJ_PASS_COMPRESS: {
             snprintf(name, sizeof(name), "Compress Large");
-            hj_buffer *index_out, *out_count, *src;
-            const hj_buffer_desc* dsrc;
+            hj_buffer *index_out = nullptr, *out_count = nullptr, *src = nullptr;
+            const hj_buffer_desc* dsrc = nullptr;
             HJ_TRY(res(p, 0, &index_out, nullptr));
             HJ_TRY(res(p, 1, &out_count, nullptr));
             HJ_TRY(res(p, 2, &src, &dsrc));
