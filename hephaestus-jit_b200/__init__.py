@@ -234,22 +234,7 @@ class Device:
         ``graph_key`` names a pass list that is launched repeatedly: from the second launch with
         the same buffers on it is replayed as one captured CUDA graph (returns 0 / 1 / 2 =
         executed / captured / replayed)."""
-        n = len(passes)
-        c_passes = (_lib.Pass * max(n, 1))()
-        keep = []
-        for i, p in enumerate(passes):
-            res = (ctypes.c_uint32 * max(len(p["resources"]), 1))(*p["resources"])
-            ir_ptr = None
-            if p.get("ir") is not None:
-                ir = p["ir"].build() if hasattr(p["ir"], "build") else p["ir"]
-                keep.append(ir)
-                ir_ptr = ctypes.pointer(ir)
-            keep.append(res)
-            c_passes[i] = _lib.Pass(p["kind"], p.get("arg", 0), res, len(p["resources"]),
-                                    p.get("size_buffer", -1) if p.get("size_buffer") is not None else -1,
-                                    ir_ptr, p.get("size", 0))
-        c_env = (ctypes.c_void_p * max(len(env), 1))(*[(b.handle if b is not None else None) for b in env])
-        c_desc = (_lib.BufferDesc * max(len(descs), 1))(*[_lib.BufferDesc(*d) for d in descs])
+        c_passes, n, c_env, c_desc, _keep = marshal_graph(passes, env, descs)
         report = _lib.Report()
         reps = (_lib.PassReport * max(n, 1))()
         if timed:
@@ -266,6 +251,28 @@ class Device:
 
 
 PASS_KERNEL, PASS_REDUCE, PASS_PREFIX_SUM, PASS_COMPRESS = range(4)
+
+
+def marshal_graph(passes, env, descs):
+    """C views of a pass list / environment (see ``Device.execute_graph``); the last element of the
+    returned tuple keeps the ctypes arrays alive."""
+    n = len(passes)
+    c_passes = (_lib.Pass * max(n, 1))()
+    keep = []
+    for i, p in enumerate(passes):
+        res = (ctypes.c_uint32 * max(len(p["resources"]), 1))(*p["resources"])
+        ir_ptr = None
+        if p.get("ir") is not None:
+            ir = p["ir"].build() if hasattr(p["ir"], "build") else p["ir"]
+            keep.append(ir)
+            ir_ptr = ctypes.pointer(ir)
+        keep.append(res)
+        c_passes[i] = _lib.Pass(p["kind"], p.get("arg", 0), res, len(p["resources"]),
+                                p.get("size_buffer", -1) if p.get("size_buffer") is not None else -1,
+                                ir_ptr, p.get("size", 0))
+    c_env = (ctypes.c_void_p * max(len(env), 1))(*[(b.handle if b is not None else None) for b in env])
+    c_desc = (_lib.BufferDesc * max(len(descs), 1))(*[_lib.BufferDesc(*d) for d in descs])
+    return c_passes, n, c_env, c_desc, keep
 
 
 class Kernel:

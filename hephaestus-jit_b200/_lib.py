@@ -69,6 +69,14 @@ class GraphReport(ctypes.Structure):
                 ("passes", ctypes.POINTER(PassReport)), ("passes_capacity", ctypes.c_uint32)]
 
 
+class ShardDesc(ctypes.Structure):
+    _fields_ = [("placement", ctypes.c_uint32), ("deferred", ctypes.c_uint32), ("seed", ctypes.c_void_p)]
+
+
+HJ_IPC_HANDLE_BYTES = 64
+RES_REPLICATED, RES_SHARDED, RES_AUTO = 0, 1, 2
+
+
 class Report(ctypes.Structure):
     _fields_ = [("cpu_duration_us", ctypes.c_double), ("n_passes", ctypes.c_uint32),
                 ("passes", ctypes.POINTER(PassReport)), ("passes_capacity", ctypes.c_uint32)]
@@ -149,6 +157,21 @@ _SIGS = {
     "hj_comm_unique_id": (_i32, [_vp]),
     "hj_comm_create": (_i32, [_vp, _vp, _i32, _i32, _pvp]),
     "hj_comm_destroy": (_i32, [_vp]),
+    "hj_comm_create_local": (_i32, [_vp, _i32, _i32, _pvp, _vp]),
+    "hj_comm_connect": (_i32, [_vp, _vp]),
+    "hj_comm_info": (_i32, [_vp, _pi32, _pi32, _pi32, _pi32]),
+    "hj_comm_device": (_i32, [_vp, _pvp]),
+    "hj_sharded_prefix_sum_deferred": (_i32, [_vp, _i32, _sz, _i32, _vp, _vp, _vp]),
+    "hj_apply_seed": (_i32, [_vp, _i32, _sz, _vp, _vp]),
+    "hj_shard_bounds": (None, [_u64, _i32, _i32, _pu64, _pu64]),
+    "hj_shard_plan": (_i32, [ctypes.POINTER(Pass), _u32, ctypes.POINTER(BufferDesc), _u32, ctypes.POINTER(ShardDesc)]),
+    "hj_execute_graph_sharded": (_i32, [_vp, ctypes.POINTER(Pass), _u32, _pvp, ctypes.POINTER(BufferDesc), _u32,
+                                        ctypes.POINTER(ShardDesc), ctypes.POINTER(Report)]),
+    "hj_tr_array_sharded": (_i32, [_vp, _u32, _vp, _u64, _pu64]),
+    "hj_tr_from_buffer_sharded": (_i32, [_vp, _vp, _u32, _u64, _pu64]),
+    "hj_tr_var_shard": (_i32, [_u64, _pi32, _pu64, _pu64, _pi32]),
+    "hj_tr_materialise": (_i32, [_u64]),
+    "hj_graph_launch_sharded": (_i32, [_vp, _vp, _vp, _pu64, _u32, _pu64, ctypes.POINTER(GraphReport)]),
     "hj_sharded_reduce": (_i32, [_vp, _i32, _i32, _sz, _vp, _vp]),
     "hj_sharded_prefix_sum": (_i32, [_vp, _i32, _sz, _i32, _vp, _vp]),
     "hj_sharded_compress": (_i32, [_vp, _sz, _u32, _vp, _vp, _vp, _vp]),

@@ -13,6 +13,7 @@
 //     `Index` variable are staged with 128-bit `ld.global.nc` / `st.global` accesses, all
 //     loads issued before the arithmetic.  This is what makes a fused elementwise chain
 //     HBM-bound on B200 instead of LSU-issue-bound.
+#include <algorithm>
 #include <cinttypes>
 #include <cstdio>
 #include <map>
@@ -71,6 +72,16 @@ struct Gen {
         return 0;
     }
     bool is_composite_elems(uint32_t t) { uint32_t k = v.type(t).kind; return k == HJ_VEC || k == HJ_ARRAY || k == HJ_MAT; }
+    static size_t align_up(size_t x, size_t a) { return a ? (x + a - 1) / a * a : x; }
+    // alignment the C++ compiler gives the emitted type (composites are plain arrays of their element)
+    size_t natural_align(uint32_t t) {
+        const hj_type_desc& d = v.type(t);
+        if (d.kind < HJ_VEC) return std::max<size_t>(scalar_size(d.kind), 1);
+        if (d.kind != HJ_STRUCT) return natural_align(d.elem);
+        size_t a = 1;
+        for (uint32_t k = 0; k < d.num; k++) a = std::max(a, natural_align(v.field(d, k)));
+        return a;
+    }
     void declare_type(uint32_t t) {
         const hj_type_desc& d = v.type(t);
         if (d.kind < HJ_VEC) { tname(t); return; }
@@ -79,9 +90,33 @@ struct Gen {
         if (d.kind == HJ_STRUCT) {
             for (uint32_t k = 0; k < d.num; k++) declare_type(v.field(d, k));
             emitted_types.insert(name);
+            // The kernel must agree with the HOST layout (vartype.rs:125-189; buffer sizes, strides and
+            // type_offset are computed from it): a Mat is aligned to elem_size * rows there but only to
+            // its element here, so fields are padded explicitly to the host offsets and the result is
+            // pinned with static_asserts — a layout this scheme cannot express fails to compile
+            // instead of corrupting memory.
             types << "struct " << name << " {";
-            for (uint32_t k = 0; k < d.num; k++) types << " " << tname(v.field(d, k)) << " e" << k << ";";
+            size_t end = 0;  // where the C++ compiler stands after the members emitted so far
+            for (uint32_t k = 0; k < d.num; k++) {
+                const uint32_t ft = v.field(d, k);
+                const size_t want = struct_offset(v, t, k);
+                size_t at = align_up(end, natural_align(ft));
+                if (want > at) {
+                    types << " char pad" << k << "[" << (want - end) << "];";  // char: placed exactly at `end`
+                    at = align_up(want, natural_align(ft));
+                }
+                if (at != want) { fail("struct layout of the host (vartype.rs:156-168) cannot be expressed for " + name); return; }
+                types << " " << tname(ft) << " e" << k << ";";
+                end = want + type_size(v, ft);
+            }
+            const size_t host_size = type_size(v, t);
+            if (host_size > align_up(end, natural_align(t))) {
+                types << " char tail[" << (host_size - end) << "];";
+                end = host_size;
+            }
+            if (align_up(end, natural_align(t)) != host_size) { fail("struct size of the host (vartype.rs:125-155) cannot be expressed for " + name); return; }
             types << " };\n";
+            types << "static_assert(sizeof(" << name << ") == " << host_size << ", \"struct layout differs from the host's (vartype.rs:125-155)\");\n";
         } else {
             declare_type(d.elem);
             emitted_types.insert(name);
@@ -640,6 +675,7 @@ bool codegen_cuda(const hj_ir* ir, CodegenResult* out, std::string* err) {
     if (!verr.empty()) { *err = verr; return false; }
     Gen g(ir);
     for (uint32_t i = 0; i < ir->n_vars; i++) g.declare_type(ir->vars[i].ty);
+    if (!g.err.empty()) { *err = g.err; return false; }
     if (!g.analyse()) { *err = g.err; return false; }
 
     // vector geometry: 16 bytes per access for the widest staged element type
@@ -670,9 +706,10 @@ bool codegen_cuda(const hj_ir* ir, CodegenResult* out, std::string* err) {
         params += ", void* __restrict__ b" + std::to_string(b);
         args += ", b" + std::to_string(b);
     }
-    // __restrict__ on buffers that alias (the same buffer bound to two slots) would be wrong;
-    // the launcher checks for duplicates and the IR never binds one resource twice
-    // (compiler.rs:187-189 dedups through an IndexSet).
+    // __restrict__ on buffers that alias (the same buffer bound to two slots) is only sound when no
+    // thread can see another thread's store: hj_kernel_launch (jit.cpp) rejects every overlap except
+    // read-only pairs and the Index-in / Index-out reuse of Graph::launch_with (ir.h: slots_may_share);
+    // the IR itself never binds one resource twice (compiler.rs:187-189 dedups through an IndexSet).
     s << "__device__ __forceinline__ void hj_element(u32 index, u32 gindex";
     for (uint32_t b = 0; b < ir->n_buffers; b++) s << ", void* __restrict__ b" << b;
     s << ") {\n" << scalar_body.str() << "}\n\n";

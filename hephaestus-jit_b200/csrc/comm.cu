@@ -40,6 +40,7 @@ struct hj_comm {
     // peers PUSH (element, epoch) words into slot [their rank] over NVLink, the owner polls locally
     void* peer_arraybox[HJ_MAX_PEERS] = {};
     bool p2p = false;
+    bool connected = true;    // false between hj_comm_create_local and hj_comm_connect
     uint32_t xepoch = 0;
 };
 
@@ -146,6 +147,12 @@ bool nccl_type(hj_type_kind ty, ncclDataType_t* out) {
     }
 }
 
+hj_status need_comm_nccl(hj_comm* c, const char* what) {
+    if (!c->comm)
+        return fail(HJ_ERR_NCCL, "%s needs NCCL, but this communicator was created without it (hj_comm_create_local)", what);
+    return need_nccl();
+}
+
 char* local_slot(hj_comm* c) { return reinterpret_cast<char*>(c->scratch); }
 char* gathered_slot(hj_comm* c) { return reinterpret_cast<char*>(c->scratch) + 64; }
 char* extra_slot(hj_comm* c) { return reinterpret_cast<char*>(c->scratch) + 64 + 8 * (size_t)c->world; }
@@ -202,15 +209,6 @@ __device__ __forceinline__ T fold2(T a, T b) {
     return a;
 }
 
-__device__ __forceinline__ void st_sys_v4(uint4* p, uint4 v) {
-    asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
-}
-__device__ __forceinline__ uint4 ld_sys_v4(const uint4* p) {
-    uint4 v;
-    asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
-    return v;
-}
-
 template <typename T, int OP>
 __global__ void __launch_bounds__(256)
 array_allreduce_kernel(int rank, int world, uint32_t epoch, ArrayBoxes ab, uint4* __restrict__ dst, uint32_t n_vec) {
@@ -220,6 +218,10 @@ array_allreduce_kernel(int rank, int world, uint32_t epoch, ArrayBoxes ab, uint4
     const uint4 mine = dst[i];
     const size_t slot_vecs = HJ_ARRAYSLOT_BYTES / 16;
     const uint4 w0 = make_uint4(mine.x, epoch, mine.y, epoch), w1 = make_uint4(mine.z, epoch, mine.w, epoch);
+    const uint4* own = ab.box[0];  // ab.box[rank] without indexing the parameter struct dynamically
+#pragma unroll
+    for (int q = 1; q < HJ_MAX_PEERS; q++)
+        if (q == rank) own = ab.box[q];
 #pragma unroll
     for (int q = 0; q < HJ_MAX_PEERS; q++)
         if (q < world && q != rank) {
@@ -234,7 +236,7 @@ array_allreduce_kernel(int rank, int world, uint32_t epoch, ArrayBoxes ab, uint4
         if (q < world) {  // rank order: the same association, hence the same bits, on every rank
             uint4 src = mine;
             if (q != rank) {
-                const uint4* from = ab.box[rank] + (size_t)q * slot_vecs + 2 * (size_t)i;
+                const uint4* from = own + (size_t)q * slot_vecs + 2 * (size_t)i;
                 uint4 a, b;
                 unsigned ns = 20;
                 while (true) {
@@ -271,18 +273,30 @@ PeerView peer_view(hj_comm* c) {
     return pv;
 }
 
-// dst (n elements of a 4-byte type) = fold over ranks of their dst, through the peer inboxes
-template <typename T>
-hj_status peer_array_allreduce(hj_comm* c, hj_reduce_op op, void* dst, size_t n) {
-    const uint32_t n_vec = (uint32_t)(n / 4);
+ArrayPeerView array_view(hj_comm* c) {  // consumes one exchange epoch
+    ArrayPeerView ax;
     next_xepoch(c);
     const size_t parity_off = (size_t)(c->xepoch & 1u) * (size_t)c->world * HJ_ARRAYSLOT_BYTES;
+    for (int r = 0; r < HJ_MAX_PEERS; r++)
+        ax.box[r] = r < c->world ? (uint4*)(reinterpret_cast<char*>(c->peer_arraybox[r]) + parity_off) : nullptr;
+    ax.rank = c->rank;
+    ax.world = c->world;
+    ax.epoch = c->xepoch;
+    ax.slot_vecs = (uint32_t)(HJ_ARRAYSLOT_BYTES / 16);
+    return ax;
+}
+
+// dst (n elements of a 4-byte type) = fold over ranks of their dst, through the peer inboxes
+// `view`: an epoch the caller has already drawn (array_view), else a new one is drawn here
+template <typename T>
+hj_status peer_array_allreduce(hj_comm* c, hj_reduce_op op, void* dst, size_t n, const ArrayPeerView* view) {
+    const uint32_t n_vec = (uint32_t)(n / 4);
+    const ArrayPeerView ax = view ? *view : array_view(c);
     const unsigned grid = (n_vec + 255) / 256;
     ArrayBoxes ab;
-    for (int r = 0; r < HJ_MAX_PEERS; r++)
-        ab.box[r] = r < c->world ? (uint4*)(reinterpret_cast<char*>(c->peer_arraybox[r]) + parity_off) : nullptr;
+    for (int r = 0; r < HJ_MAX_PEERS; r++) ab.box[r] = ax.box[r];
 #define HJ_COMBINE(OP) \
-    array_allreduce_kernel<T, OP><<<grid, 256, 0, c->dev->stream>>>(c->rank, c->world, c->xepoch, ab, (uint4*)dst, n_vec)
+    array_allreduce_kernel<T, OP><<<grid, 256, 0, c->dev->stream>>>(c->rank, c->world, ax.epoch, ab, (uint4*)dst, n_vec)
     switch (op) {
     case HJ_REDUCE_SUM: HJ_COMBINE(HJ_REDUCE_SUM); break;
     case HJ_REDUCE_MAX: HJ_COMBINE(HJ_REDUCE_MAX); break;
@@ -303,38 +317,95 @@ hj_status gather_scalars(hj_comm* c, size_t es) {
         peer_allgather_kernel<<<1, 32, 0, c->dev->stream>>>(pv, c->xepoch, local_slot(c), (int)es, gathered_slot(c));
         return check_launch(c->dev, "peer_allgather_kernel");
     }
+    HJ_TRY(need_comm_nccl(c, "the all-gather fallback"));
     HJ_NCCL(nccl().AllGather(local_slot(c), gathered_slot(c), es, ncclUint8, c->comm, c->dev->stream));
     return HJ_OK;
 }
 
-// Map every rank's mailbox into this process (CUDA IPC handles all-gathered once over NCCL).
-// Any failure leaves c->p2p false and the NCCL path in use.
+// dst[i] += seed[0]: materialises a scan result that was left with a deferred seed
+template <typename T>
+__global__ void __launch_bounds__(256) apply_seed_kernel(T* __restrict__ dst, size_t n, const T* __restrict__ seed) {
+    constexpr int VEC = 16 / sizeof(T);
+    const T s = seed[0];
+    const size_t nvec = n / VEC, stride = (size_t)gridDim.x * 256;
+    uint4* v = reinterpret_cast<uint4*>(dst);
+    for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < nvec; i += stride) {
+        uint4 raw = v[i];
+        T* e = reinterpret_cast<T*>(&raw);
+#pragma unroll
+        for (int j = 0; j < VEC; j++) e[j] = (T)(e[j] + s);
+        v[i] = raw;
+    }
+    for (size_t i = nvec * VEC + (size_t)blockIdx.x * 256 + threadIdx.x; i < n; i += stride) dst[i] = (T)(dst[i] + s);
+}
+template <typename T>
+__global__ void __launch_bounds__(256) apply_seed_scalar_kernel(T* __restrict__ dst, size_t n, const T* __restrict__ seed) {
+    const T s = seed[0];
+    const size_t stride = (size_t)gridDim.x * 256;
+    for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < n; i += stride) dst[i] = (T)(dst[i] + s);
+}
+template <typename T>
+hj_status run_apply_seed(hj_device* dev, size_t n, void* dst, const void* seed) {
+    const size_t want = (n * sizeof(T) / 16 + 255) / 256, cap = (size_t)dev->sm_count * 16;
+    const unsigned grid = (unsigned)(want < 1 ? 1 : (want > cap ? cap : want));
+    if (((uintptr_t)dst & 15u) == 0) apply_seed_kernel<T><<<grid, 256, 0, dev->stream>>>((T*)dst, n, (const T*)seed);
+    else apply_seed_scalar_kernel<T><<<grid, 256, 0, dev->stream>>>((T*)dst, n, (const T*)seed);
+    return check_launch(dev, "apply_seed_kernel");
+}
+
+// Peer mailboxes.  Every rank allocates one IPC-exportable block (scalar mailbox slots, then the
+// array inbox), hands its cudaIpcMemHandle_t to every other rank — over NCCL (hj_comm_create) or
+// through the host (hj_comm_create_local + hj_comm_connect: any transport, NCCL not needed) —
+// and maps theirs.  Any failure leaves c->p2p false and the NCCL path in use.
+size_t mailbox_bytes(int world) { return HJ_ARRAYBOX_OFFSET + 2 * (size_t)world * HJ_ARRAYSLOT_BYTES; }
+
+bool alloc_mailbox(hj_comm* c, cudaIpcMemHandle_t* mine) {
+    static_assert(2 * (size_t)HJ_MAX_PEERS * 16 <= HJ_ARRAYBOX_OFFSET, "mailbox slots overlap the array box");
+    static_assert(sizeof(cudaIpcMemHandle_t) == HJ_IPC_HANDLE_BYTES, "cudaIpcMemHandle_t size");
+    const size_t box_bytes = mailbox_bytes(c->world);
+    if (cudaMalloc(&c->mailbox, box_bytes) != cudaSuccess) { cudaGetLastError(); c->mailbox = nullptr; return false; }
+    // epoch 0 = empty; completed before anybody can learn the handle
+    if (cudaMemsetAsync(c->mailbox, 0, box_bytes, c->dev->stream) != cudaSuccess ||
+        cudaStreamSynchronize(c->dev->stream) != cudaSuccess) { cudaGetLastError(); return false; }
+    if (cudaIpcGetMemHandle(mine, c->mailbox) != cudaSuccess) { cudaGetLastError(); return false; }
+    return true;
+}
+
+bool open_mailboxes(hj_comm* c, const cudaIpcMemHandle_t* all) {
+    bool ok = true;
+    for (int r = 0; ok && r < c->world; r++) {
+        if (r == c->rank) { c->peer_mailbox[r] = c->mailbox; continue; }
+        if (cudaIpcOpenMemHandle(&c->peer_mailbox[r], all[r], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+            cudaGetLastError();
+            c->peer_mailbox[r] = nullptr;
+            ok = false;
+        }
+    }
+    return ok;
+}
+
+void finish_mailboxes(hj_comm* c, bool agreed) {
+    c->p2p = agreed;
+    for (int r = 0; c->p2p && r < c->world; r++)
+        c->peer_arraybox[r] = reinterpret_cast<char*>(c->peer_mailbox[r]) + HJ_ARRAYBOX_OFFSET;
+}
+
 void setup_peer_mailboxes(hj_comm* c) {
     if (c->world < 2 || c->world > HJ_MAX_PEERS || getenv("HJ_NO_P2P")) return;
-    // mailbox slots, then the array inbox: 2 parities x world slots of (element, epoch) pairs
-    const size_t box_bytes = HJ_ARRAYBOX_OFFSET + 2 * (size_t)c->world * HJ_ARRAYSLOT_BYTES;
-    static_assert(2 * (size_t)HJ_MAX_PEERS * 16 <= HJ_ARRAYBOX_OFFSET, "mailbox slots overlap the array box");
-    if (cudaMalloc(&c->mailbox, box_bytes) != cudaSuccess) { cudaGetLastError(); c->mailbox = nullptr; return; }
-    cudaMemsetAsync(c->mailbox, 0, box_bytes, c->dev->stream);  // epoch 0 = empty; ordered before the handle exchange below
     cudaIpcMemHandle_t mine;
-    if (cudaIpcGetMemHandle(&mine, c->mailbox) != cudaSuccess) { cudaGetLastError(); return; }
+    bool ok = alloc_mailbox(c, &mine);
+    // from here on every rank takes part in both collectives, whatever happened locally
     void* d_handles = nullptr;
     const size_t hs = sizeof(cudaIpcMemHandle_t);
     if (cudaMalloc(&d_handles, hs * (c->world + 1)) != cudaSuccess) { cudaGetLastError(); return; }
     char* send = reinterpret_cast<char*>(d_handles) + hs * c->world;
     cudaMemcpyAsync(send, &mine, hs, cudaMemcpyHostToDevice, c->dev->stream);
-    bool ok = nccl().AllGather(send, d_handles, hs, ncclUint8, c->comm, c->dev->stream) == ncclSuccess;
+    ok = nccl().AllGather(send, d_handles, hs, ncclUint8, c->comm, c->dev->stream) == ncclSuccess && ok;
     std::vector<cudaIpcMemHandle_t> all(c->world);
-    ok = ok && cudaMemcpyAsync(all.data(), d_handles, hs * c->world, cudaMemcpyDeviceToHost, c->dev->stream) == cudaSuccess;
-    ok = ok && cudaStreamSynchronize(c->dev->stream) == cudaSuccess;
+    ok = cudaMemcpyAsync(all.data(), d_handles, hs * c->world, cudaMemcpyDeviceToHost, c->dev->stream) == cudaSuccess && ok;
+    ok = cudaStreamSynchronize(c->dev->stream) == cudaSuccess && ok;
     cudaFree(d_handles);
-    for (int r = 0; ok && r < c->world; r++) {
-        if (r == c->rank) { c->peer_mailbox[r] = c->mailbox; continue; }
-        if (cudaIpcOpenMemHandle(&c->peer_mailbox[r], all[r], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
-            cudaGetLastError();
-            ok = false;
-        }
-    }
+    ok = ok && open_mailboxes(c, all.data());
     // every rank must agree, or some would wait on mailboxes nobody writes: all-reduce the verdict
     int* d_ok = nullptr;
     if (cudaMalloc(&d_ok, sizeof(int)) != cudaSuccess) { cudaGetLastError(); return; }
@@ -344,12 +415,88 @@ void setup_peer_mailboxes(hj_comm* c) {
     cudaMemcpyAsync(&h_ok, d_ok, sizeof(int), cudaMemcpyDeviceToHost, c->dev->stream);
     cudaStreamSynchronize(c->dev->stream);
     cudaFree(d_ok);
-    c->p2p = agreed && h_ok == 1;
-    for (int r = 0; c->p2p && r < c->world; r++)
-        c->peer_arraybox[r] = reinterpret_cast<char*>(c->peer_mailbox[r]) + HJ_ARRAYBOX_OFFSET;
+    finish_mailboxes(c, agreed && h_ok == 1);
 }
 
 }  // namespace
+}  // namespace hj
+
+namespace hj {
+namespace {
+// Local compaction with GLOBAL indices (index_base = global start of the shard); out_count[0] = global
+// count, counts[q] = count of rank q (counts_out, else the communicator's scratch).  With peer memory the
+// exchange of the counts runs inside the compaction kernel (compress.cu: CompressOp::finish).
+hj_status sharded_compress(hj_comm* c, size_t n_local, uint32_t index_base, const uint8_t* mask, uint32_t* index_out,
+                           uint32_t* out_count, uint32_t* counts_out, bool zero_tail) {
+    uint32_t* counts = counts_out ? counts_out : (uint32_t*)gathered_slot(c);
+    if (c->world == 1) {
+        HJ_TRY(launch_compress(c->dev, n_local, nullptr, out_count, mask, index_out, index_base, zero_tail));
+        HJ_CUDA(cudaMemcpyAsync(counts, out_count, 4, cudaMemcpyDeviceToDevice, c->dev->stream));
+        return HJ_OK;
+    }
+    if (c->p2p && compress_can_fuse_exchange(n_local, mask)) {
+        PeerView pv = peer_view(c);
+        next_xepoch(c);
+        const bool zt_in_kernel = zero_tail && ((uintptr_t)index_out & 15u) == 0 && !getenv("HJ_ZERO_TAIL_KERNEL");
+        HJ_TRY(launch_compress(c->dev, n_local, nullptr, out_count, mask, index_out, index_base, zt_in_kernel, counts, &pv,
+                               c->xepoch));
+        if (zero_tail && !zt_in_kernel) return launch_compress_zero_tail(c->dev, index_out, counts + c->rank, n_local);
+        return HJ_OK;
+    }
+    // small / misaligned shards, or no peer memory: compaction, then the exchange as its own step
+    HJ_TRY(launch_compress(c->dev, n_local, nullptr, (uint32_t*)local_slot(c), mask, index_out, index_base, zero_tail));
+    HJ_TRY(gather_scalars(c, 4));
+    offsets_kernel<uint32_t><<<1, 32, 0, c->dev->stream>>>((const uint32_t*)gathered_slot(c), c->rank, c->world, nullptr,
+                                                          out_count);
+    HJ_TRY(check_launch(c->dev, "offsets_kernel"));
+    if (counts_out)
+        HJ_CUDA(cudaMemcpyAsync(counts_out, gathered_slot(c), 4 * (size_t)c->world, cudaMemcpyDeviceToDevice, c->dev->stream));
+    return HJ_OK;
+}
+}  // namespace
+
+namespace {
+// seed[0] = sum of the shard totals of the ranks before this one, without a fused kernel: totals
+// pass (+ exchange in its last CTA over peer memory, else all-gather + offsets kernel)
+hj_status exclusive_offset_of_totals(hj_comm* c, hj_type_kind ty, size_t n_local, const void* src, void* seed) {
+    const size_t es = type_size(ty);
+    if (c->p2p) {
+        PeerView pv = peer_view(c);
+        next_xepoch(c);
+        return launch_reduce(c->dev, HJ_REDUCE_SUM, ty, n_local, src, seed, &pv, c->xepoch | 0x80000000u);
+    }
+    HJ_TRY(launch_reduce(c->dev, HJ_REDUCE_SUM, ty, n_local, src, local_slot(c)));
+    HJ_TRY(gather_scalars(c, es));
+    switch (es) {
+    case 1: offsets_kernel<uint8_t><<<1, 32, 0, c->dev->stream>>>((const uint8_t*)gathered_slot(c), c->rank, c->world, (uint8_t*)seed, nullptr); break;
+    case 2: offsets_kernel<uint16_t><<<1, 32, 0, c->dev->stream>>>((const uint16_t*)gathered_slot(c), c->rank, c->world, (uint16_t*)seed, nullptr); break;
+    case 4:
+        if (ty == HJ_F32) offsets_kernel<float><<<1, 32, 0, c->dev->stream>>>((const float*)gathered_slot(c), c->rank, c->world, (float*)seed, nullptr);
+        else offsets_kernel<uint32_t><<<1, 32, 0, c->dev->stream>>>((const uint32_t*)gathered_slot(c), c->rank, c->world, (uint32_t*)seed, nullptr);
+        break;
+    default:
+        if (ty == HJ_F64) offsets_kernel<double><<<1, 32, 0, c->dev->stream>>>((const double*)gathered_slot(c), c->rank, c->world, (double*)seed, nullptr);
+        else offsets_kernel<unsigned long long><<<1, 32, 0, c->dev->stream>>>((const unsigned long long*)gathered_slot(c), c->rank, c->world, (unsigned long long*)seed, nullptr);
+        break;
+    }
+    return check_launch(c->dev, "offsets_kernel");
+}
+}  // namespace
+
+}  // namespace hj
+
+namespace hj {
+hj_status sharded_compress_pass(hj_comm* c, size_t n_local, uint32_t index_base, hj_buffer* mask, hj_buffer* index_out,
+                                hj_buffer* out_count, bool zero_tail) {
+    HJ_REQUIRE(c->connected, "communicator is not connected yet (hj_comm_connect)");
+    DeviceGuard g(c->dev);
+    return sharded_compress(c, n_local, index_base, (const uint8_t*)mask->ptr, (uint32_t*)index_out->ptr,
+                            (uint32_t*)out_count->ptr, nullptr, zero_tail);
+}
+}  // namespace hj
+
+namespace hj {
+hj_device* comm_device(hj_comm* c) { return c->dev; }
 }  // namespace hj
 
 using namespace hj;
@@ -396,6 +543,65 @@ hj_status hj_comm_create(hj_device* dev, const uint8_t id[HJ_UNIQUE_ID_BYTES], i
     return HJ_OK;
 }
 
+hj_status hj_comm_create_local(hj_device* dev, int32_t rank, int32_t world, hj_comm** out,
+                               uint8_t handle_out[HJ_IPC_HANDLE_BYTES]) {
+    HJ_REQUIRE(dev && out && handle_out, "null argument");
+    HJ_REQUIRE(world >= 1 && world <= HJ_MAX_PEERS && rank >= 0 && rank < world, "bad rank %d / world %d (at most %d ranks)",
+               rank, world, HJ_MAX_PEERS);
+    DeviceGuard g(dev);
+    auto c = new hj_comm();
+    c->dev = dev;
+    c->rank = rank;
+    c->world = world;
+    c->connected = world == 1;
+    cudaError_t e = cudaMalloc(&c->scratch, 64 + 8 * (size_t)world + 64 + 64);
+    if (e != cudaSuccess) {
+        delete c;
+        return fail(HJ_ERR_CUDA, "cudaMalloc failed: %s", cudaGetErrorString(e));
+    }
+    cudaMemsetAsync(c->scratch, 0, 64 + 8 * (size_t)world + 64 + 64, dev->stream);
+    cudaIpcMemHandle_t mine;
+    memset(&mine, 0, sizeof(mine));
+    if (world > 1 && !alloc_mailbox(c, &mine)) {
+        if (c->mailbox) cudaFree(c->mailbox);
+        cudaFree(c->scratch);
+        delete c;
+        return fail(HJ_ERR_CUDA, "cannot allocate / export the peer mailbox (CUDA IPC)");
+    }
+    memcpy(handle_out, &mine, sizeof(mine));
+    dev->rc.fetch_add(1);
+    *out = c;
+    return HJ_OK;
+}
+
+hj_status hj_comm_connect(hj_comm* c, const uint8_t* handles) {
+    HJ_REQUIRE(c && (handles || c->world == 1), "null argument");
+    HJ_REQUIRE(!c->comm, "hj_comm_connect: this communicator was bootstrapped over NCCL");
+    if (c->connected) return HJ_OK;
+    DeviceGuard g(c->dev);
+    std::vector<cudaIpcMemHandle_t> all(c->world);
+    memcpy(all.data(), handles, sizeof(cudaIpcMemHandle_t) * (size_t)c->world);
+    if (!open_mailboxes(c, all.data())) return fail(HJ_ERR_CUDA, "cudaIpcOpenMemHandle failed for a peer mailbox");
+    finish_mailboxes(c, true);
+    c->connected = true;
+    return HJ_OK;
+}
+
+hj_status hj_comm_info(hj_comm* c, int32_t* rank, int32_t* world, int32_t* peer_memory, int32_t* has_nccl) {
+    HJ_REQUIRE(c, "null comm");
+    if (rank) *rank = c->rank;
+    if (world) *world = c->world;
+    if (peer_memory) *peer_memory = c->p2p ? 1 : 0;
+    if (has_nccl) *has_nccl = c->comm ? 1 : 0;
+    return HJ_OK;
+}
+
+hj_status hj_comm_device(hj_comm* c, hj_device** out) {
+    HJ_REQUIRE(c && out, "null argument");
+    *out = c->dev;
+    return HJ_OK;
+}
+
 hj_status hj_comm_destroy(hj_comm* c) {
     HJ_REQUIRE(c, "null comm");
     {
@@ -412,9 +618,12 @@ hj_status hj_comm_destroy(hj_comm* c) {
     return HJ_OK;
 }
 
+#define HJ_COMM_READY(c) HJ_REQUIRE((c)->connected, "communicator is not connected yet (hj_comm_connect)")
+
 hj_status hj_sharded_reduce(hj_comm* c, hj_reduce_op op, hj_type_kind ty, size_t n_local, hj_buffer* src,
                             hj_buffer* dst) {
     HJ_REQUIRE(c && src && dst, "hj_sharded_reduce: null argument");
+    HJ_COMM_READY(c);
     size_t es = type_size(ty);
     HJ_REQUIRE(es && n_local >= 1 && n_local * es <= src->bytes && es <= dst->bytes, "hj_sharded_reduce: bad sizes");
     DeviceGuard g(c->dev);
@@ -438,80 +647,111 @@ hj_status hj_sharded_reduce(hj_comm* c, hj_reduce_op op, hj_type_kind ty, size_t
 hj_status hj_sharded_prefix_sum(hj_comm* c, hj_type_kind ty, size_t n_local, int32_t inclusive, hj_buffer* src,
                                 hj_buffer* dst) {
     HJ_REQUIRE(c && src && dst, "hj_sharded_prefix_sum: null argument");
+    HJ_COMM_READY(c);
     size_t es = type_size(ty);
     HJ_REQUIRE(es && n_local >= 1 && n_local * es <= src->bytes && n_local * es <= dst->bytes,
                "hj_sharded_prefix_sum: bad sizes");
     DeviceGuard g(c->dev);
     if (c->world == 1) return launch_prefix_sum(c->dev, ty, n_local, inclusive != 0, src->ptr, dst->ptr, nullptr);
-    // shard total (a read-only pass, sizeof(T) bytes/element) -> all-gather -> exclusive offset
-    // of this rank -> scan seeded with the offset.  12 bytes/element in total for 4-byte types.
-    if (c->p2p) {
-        // the totals pass, the exchange over peer memory and the exclusive offset are ONE kernel
+    // MATERIALISED result: shard total (a read-only pass, sizeof(T) bytes/element, the exchange fused
+    // into its last CTA) -> scan seeded with this rank's exclusive offset.  12 bytes/element for 4-byte
+    // types; hj_sharded_prefix_sum_deferred is the 8-byte form.
+    HJ_TRY(exclusive_offset_of_totals(c, ty, n_local, src->ptr, extra_slot(c)));
+    return launch_prefix_sum(c->dev, ty, n_local, inclusive != 0, src->ptr, dst->ptr, extra_slot(c));
+}
+
+hj_status hj_sharded_prefix_sum_deferred(hj_comm* c, hj_type_kind ty, size_t n_local, int32_t inclusive, hj_buffer* src,
+                                         hj_buffer* dst, hj_buffer* seed_out) {
+    HJ_REQUIRE(c && src && dst && seed_out, "hj_sharded_prefix_sum_deferred: null argument");
+    HJ_COMM_READY(c);
+    size_t es = type_size(ty);
+    HJ_REQUIRE(es && n_local >= 1 && n_local * es <= src->bytes && n_local * es <= dst->bytes && seed_out->bytes >= es,
+               "hj_sharded_prefix_sum_deferred: bad sizes");
+    DeviceGuard g(c->dev);
+    if (c->world == 1) {
+        HJ_CUDA(cudaMemsetAsync(seed_out->ptr, 0, es, c->dev->stream));
+        return launch_prefix_sum(c->dev, ty, n_local, inclusive != 0, src->ptr, dst->ptr, nullptr);
+    }
+    if (c->p2p && prefix_sum_can_fuse_exchange(ty, n_local, src->ptr, dst->ptr)) {
+        // ONE kernel, 2 * sizeof(T) bytes/element: the local scan; the CTA that owns the last tile sends
+        // the shard total to every peer's mailbox and leaves the sum of the lower ranks' totals in seed_out
         PeerView pv = peer_view(c);
         next_xepoch(c);
-        HJ_TRY(launch_reduce(c->dev, HJ_REDUCE_SUM, ty, n_local, src->ptr, extra_slot(c), &pv, c->xepoch | 0x80000000u));
-        return launch_prefix_sum(c->dev, ty, n_local, inclusive != 0, src->ptr, dst->ptr, extra_slot(c));
+        return launch_prefix_sum(c->dev, ty, n_local, inclusive != 0, src->ptr, dst->ptr, nullptr, seed_out->ptr, &pv,
+                                 c->xepoch);
     }
-    HJ_TRY(launch_reduce(c->dev, HJ_REDUCE_SUM, ty, n_local, src->ptr, local_slot(c)));
-    HJ_TRY(gather_scalars(c, es));
-    void* seed = extra_slot(c);
-    switch (es) {
-    case 1: offsets_kernel<uint8_t><<<1, 32, 0, c->dev->stream>>>((const uint8_t*)gathered_slot(c), c->rank, c->world, (uint8_t*)seed, nullptr); break;
-    case 2: offsets_kernel<uint16_t><<<1, 32, 0, c->dev->stream>>>((const uint16_t*)gathered_slot(c), c->rank, c->world, (uint16_t*)seed, nullptr); break;
-    case 4:
-        if (ty == HJ_F32) offsets_kernel<float><<<1, 32, 0, c->dev->stream>>>((const float*)gathered_slot(c), c->rank, c->world, (float*)seed, nullptr);
-        else offsets_kernel<uint32_t><<<1, 32, 0, c->dev->stream>>>((const uint32_t*)gathered_slot(c), c->rank, c->world, (uint32_t*)seed, nullptr);
-        break;
-    default:
-        if (ty == HJ_F64) offsets_kernel<double><<<1, 32, 0, c->dev->stream>>>((const double*)gathered_slot(c), c->rank, c->world, (double*)seed, nullptr);
-        else offsets_kernel<unsigned long long><<<1, 32, 0, c->dev->stream>>>((const unsigned long long*)gathered_slot(c), c->rank, c->world, (unsigned long long*)seed, nullptr);
-        break;
+    // small / misaligned shards, or no peer memory: totals pass + exchange, then the unseeded scan
+    HJ_TRY(exclusive_offset_of_totals(c, ty, n_local, src->ptr, seed_out->ptr));
+    return launch_prefix_sum(c->dev, ty, n_local, inclusive != 0, src->ptr, dst->ptr, nullptr);
+}
+
+hj_status hj_apply_seed(hj_device* dev, hj_type_kind ty, size_t n, hj_buffer* buf, hj_buffer* seed) {
+    HJ_REQUIRE(dev && buf && seed, "hj_apply_seed: null argument");
+    const size_t es = type_size(ty);
+    HJ_REQUIRE(es && n * es <= buf->bytes && seed->bytes >= es, "hj_apply_seed: bad sizes");
+    if (n == 0) return HJ_OK;
+    DeviceGuard g(dev);
+    switch (ty) {
+    case HJ_I8: case HJ_U8: return run_apply_seed<uint8_t>(dev, n, buf->ptr, seed->ptr);
+    case HJ_I16: case HJ_U16: return run_apply_seed<uint16_t>(dev, n, buf->ptr, seed->ptr);
+    case HJ_I32: case HJ_U32: return run_apply_seed<uint32_t>(dev, n, buf->ptr, seed->ptr);
+    case HJ_I64: case HJ_U64: return run_apply_seed<unsigned long long>(dev, n, buf->ptr, seed->ptr);
+    case HJ_F32: return run_apply_seed<float>(dev, n, buf->ptr, seed->ptr);
+    case HJ_F64: return run_apply_seed<double>(dev, n, buf->ptr, seed->ptr);
+    default: return fail(HJ_ERR_UNSUPPORTED, "hj_apply_seed: unsupported element type %s", type_name(ty));
     }
-    HJ_TRY(check_launch(c->dev, "offsets_kernel"));
-    return launch_prefix_sum(c->dev, ty, n_local, inclusive != 0, src->ptr, dst->ptr, seed);
 }
 
 hj_status hj_sharded_compress(hj_comm* c, size_t n_local, uint32_t index_base, hj_buffer* src_mask,
                               hj_buffer* index_out, hj_buffer* out_count, hj_buffer* counts_out) {
     HJ_REQUIRE(c && src_mask && index_out && out_count, "hj_sharded_compress: null argument");
+    HJ_COMM_READY(c);
     HJ_REQUIRE(n_local >= 1 && n_local <= src_mask->bytes && n_local * 4 <= index_out->bytes && out_count->bytes >= 4,
                "hj_sharded_compress: bad sizes");
     HJ_REQUIRE(!counts_out || counts_out->bytes >= 4 * (size_t)c->world, "hj_sharded_compress: counts_out too small");
     DeviceGuard g(c->dev);
-    // local compaction with GLOBAL indices; the per-rank segment stays on its GPU
-    HJ_TRY(launch_compress(c->dev, n_local, nullptr, (uint32_t*)local_slot(c), (const uint8_t*)src_mask->ptr,
-                           (uint32_t*)index_out->ptr, index_base));
-    if (c->world > 1) HJ_TRY(gather_scalars(c, 4));
-    else HJ_CUDA(cudaMemcpyAsync(gathered_slot(c), local_slot(c), 4, cudaMemcpyDeviceToDevice, c->dev->stream));
-    offsets_kernel<uint32_t><<<1, 32, 0, c->dev->stream>>>((const uint32_t*)gathered_slot(c), c->rank, c->world, nullptr,
-                                                          (uint32_t*)out_count->ptr);
-    HJ_TRY(check_launch(c->dev, "offsets_kernel"));
-    if (counts_out)
-        HJ_CUDA(cudaMemcpyAsync(counts_out->ptr, gathered_slot(c), 4 * (size_t)c->world, cudaMemcpyDeviceToDevice,
-                                c->dev->stream));
-    return HJ_OK;
+    return sharded_compress(c, n_local, index_base, (const uint8_t*)src_mask->ptr, (uint32_t*)index_out->ptr,
+                            (uint32_t*)out_count->ptr, counts_out ? (uint32_t*)counts_out->ptr : nullptr, false);
 }
 
 hj_status hj_sharded_scatter_reduce(hj_comm* c, hj_reduce_op op, hj_type_kind ty, size_t n_local, hj_buffer* idx,
                                     hj_buffer* src, uint64_t literal, hj_buffer* dst, size_t n_dst) {
     HJ_REQUIRE(c && idx && dst, "hj_sharded_scatter_reduce: null argument");
+    HJ_COMM_READY(c);
     size_t es = type_size(ty);
     HJ_REQUIRE(es && n_local * 4 <= idx->bytes && n_dst * es <= dst->bytes && (!src || n_local * es <= src->bytes),
                "hj_sharded_scatter_reduce: bad sizes");
     DeviceGuard g(c->dev);
     // privatised per GPU: every rank reduces its keys into its own copy of dst (which the
-    // caller initialised with the operator's identity), then the copies are combined
-    HJ_TRY(launch_scatter_reduce(c->dev, op, ty, n_local, (const uint32_t*)idx->ptr, src ? src->ptr : nullptr, literal,
-                                 dst->ptr, n_dst));
-    if (c->world == 1) return HJ_OK;
-    // small 4-byte arrays (the BASELINE histogram: 2^16 u32 bins = 256 KiB): exchange over peer memory
-    const bool float_bits = ty == HJ_F32 && (op == HJ_REDUCE_OR || op == HJ_REDUCE_AND || op == HJ_REDUCE_XOR);
-    if (c->p2p && es == 4 && n_dst % 4 == 0 && n_dst * 4 <= HJ_ARRAYBOX_BYTES && ((uintptr_t)dst->ptr & 15u) == 0 &&
-        !float_bits && !getenv("HJ_NO_PEER_ARRAY")) {
-        if (ty == HJ_F32) return peer_array_allreduce<float>(c, op, dst->ptr, n_dst);
-        if (ty == HJ_I32) return peer_array_allreduce<int32_t>(c, op, dst->ptr, n_dst);
-        if (ty == HJ_U32) return peer_array_allreduce<uint32_t>(c, op, dst->ptr, n_dst);
+    // caller initialised with the operator's identity), then the copies are combined.  The
+    // packed-16 histogram (BASELINE: 2^16 u32 bins) folds its private counters AND runs the
+    // exchange over peer memory in one kernel (scatter.cu: hist_fold_exchange_kernel).
+    bool exchanged = false;
+    const bool small_array = c->p2p && c->world > 1 && es == 4 && n_dst * 4 <= HJ_ARRAYBOX_BYTES && !getenv("HJ_NO_PEER_ARRAY");
+    if (small_array && op == HJ_REDUCE_SUM && (ty == HJ_U32 || ty == HJ_I32) && !src && n_local >= 1) {
+        ArrayPeerView ax = array_view(c);
+        // every rank must consume this epoch whether or not its own launch takes the fused path; the
+        // choice below only depends on (n_dst, literal, alignment, n_local >= 2^20) — ranks whose
+        // shard is too small for the ring kernel run the plain exchange with the SAME epoch
+        HJ_TRY(launch_scatter_reduce(c->dev, op, ty, n_local, (const uint32_t*)idx->ptr, nullptr, literal, dst->ptr, n_dst, &ax,
+                                     &exchanged));
+        if (exchanged) return HJ_OK;
+        if (n_dst % 4 == 0 && ((uintptr_t)dst->ptr & 15u) == 0)
+            return peer_array_allreduce<uint32_t>(c, op, dst->ptr, n_dst, &ax);
+        // cannot happen for library-allocated buffers; fall through to NCCL with the epoch spent
+    } else {
+        HJ_TRY(launch_scatter_reduce(c->dev, op, ty, n_local, (const uint32_t*)idx->ptr, src ? src->ptr : nullptr, literal,
+                                     dst->ptr, n_dst));
     }
+    if (c->world == 1) return HJ_OK;
+    // small 4-byte arrays: exchange over peer memory
+    const bool float_bits = ty == HJ_F32 && (op == HJ_REDUCE_OR || op == HJ_REDUCE_AND || op == HJ_REDUCE_XOR);
+    if (small_array && n_dst % 4 == 0 && ((uintptr_t)dst->ptr & 15u) == 0 && !float_bits) {
+        if (ty == HJ_F32) return peer_array_allreduce<float>(c, op, dst->ptr, n_dst, nullptr);
+        if (ty == HJ_I32) return peer_array_allreduce<int32_t>(c, op, dst->ptr, n_dst, nullptr);
+        if (ty == HJ_U32) return peer_array_allreduce<uint32_t>(c, op, dst->ptr, n_dst, nullptr);
+    }
+    HJ_TRY(need_comm_nccl(c, "hj_sharded_scatter_reduce of an array too large for the peer inbox"));
     ncclDataType_t dt;
     HJ_REQUIRE(nccl_type(ty, &dt), "hj_sharded_scatter_reduce: no NCCL type for %s", type_name(ty));
     if (op == HJ_REDUCE_SUM || op == HJ_REDUCE_MAX || op == HJ_REDUCE_MIN) {
@@ -568,7 +808,7 @@ hj_status hj_sharded_rebalance(hj_comm* c, size_t elem_bytes, hj_buffer* src, hj
     HJ_REQUIRE((uint64_t)cnt[me] * elem_bytes <= src->bytes, "hj_sharded_rebalance: counts[rank] exceeds src");
     HJ_REQUIRE(mine * elem_bytes <= dst->bytes, "hj_sharded_rebalance: dst holds %zu bytes, the balanced block needs %llu",
                dst->bytes, (unsigned long long)(mine * elem_bytes));
-    if (W > 1) HJ_TRY(need_nccl());
+    if (W > 1) HJ_TRY(need_comm_nccl(c, "hj_sharded_rebalance"));
     auto overlap = [](uint64_t a0, uint64_t a1, uint64_t b0, uint64_t b1, uint64_t* lo, uint64_t* hi) {
         *lo = a0 > b0 ? a0 : b0;
         *hi = a1 < b1 ? a1 : b1;

@@ -160,6 +160,13 @@ __device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gmem_src
                  : "memory");
 }
 
+// Programmatic dependent launch (PDL): a kernel launched with
+// cudaLaunchAttributeProgrammaticStreamSerialization may start once every CTA of the kernel in
+// front has called pdl_launch_dependents (or exited); pdl_wait blocks until that kernel has
+// completed and its memory is visible.  Both are no-ops in a launch without the attribute.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 static inline int div_up(size_t a, size_t b) { return (int)((a + b - 1) / b); }
 
 }  // namespace hj

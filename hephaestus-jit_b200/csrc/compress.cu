@@ -4,24 +4,28 @@
 // (hephaestus-jit/src/backend/vulkan/builtin/compress.rs:157-283 +
 // kernels/compress_large.glsl:76-229).  Same contract: index_out[0..count) receives the
 // positions of the set mask bytes in ascending order, out_count[0] the count, entries at and
-// beyond count are not touched.  Differences by design:
-//   * two sweeps per 32 KiB super-tile, like the scan kernel (scan.cu explains why the
-//     register-resident single sweep stalls on B200): sweep 1 only COUNTS the set bytes of
-//     each warp's contiguous 4 KiB segment; block aggregate -> publish -> 128-wide look-back;
-//     sweep 2 re-reads the mask rows (1 byte/element, L2-resident) and emits the indices;
-//   * each 16-byte vector is turned into a 16-bit lane mask with SIMD-in-word compares and
-//     a multiply-gather, counted with popc — no per-byte scan;
-//   * the indices of a 512-element warp row are compacted in a per-warp shared-memory stage
-//     and written with coalesced 128-byte warp stores; sweep 2 needs no block barrier.  The
-//     reference's per-thread scattered stores (compress_large.glsl:224-228) touch one 32-byte
-//     sector per 4-byte index;
-//   * the tail (and a device-resident DynSize count) is masked in the kernel (reference D4);
-//   * `index_base` is added to every index: the shard's global offset on multi-GPU runs.
-// Algorithmic bytes: n (mask) + 4 * count (indices); HBM-bound.
+// beyond count are not touched (unless the caller asks for the zero tail, see ZT below).
+//
+// Two kernels live here:
+//   * compress_ring_kernel — THE DEFAULT for 16-byte aligned masks of >= 64 KiB: the persistent
+//     ring of ring.cuh with 56 KiB tiles x 3 TMA stages, 28 consumer warps and EARLY release.
+//     Phase 1 turns every 16-byte vector into a 16-bit lane mask (IDP.4A: for 0/1 bytes the byte dot
+//     product with (1,2,4,8) IS the mask nibble), counts it and parks the mask in a side plane, so
+//     the data stage returns to the producer at once; phase 2 ranks rows in pairs with one packed
+//     warp scan and picks a store path per density (sparse: direct; medium: u16 stage + 128-byte
+//     warp stores; dense: word-broadcast, contiguous runs).  DESIGN.md 3.3 has the measurements.
+//     On a sharded launch `finish` also exchanges the per-rank counts over peer memory (comm.cu).
+//   * compress_kernel — the fallback for small or misaligned inputs: two sweeps per 32 KiB tile
+//     with decoupled look-back (sweep 1 counts, sweep 2 re-reads the L2-resident rows and emits).
+// Differences from the reference in both: the tail and a device-resident DynSize count are masked
+// in the kernel (D4), `index_base` is added to every index (the shard's global offset), indices
+// leave as coalesced warp stores instead of one 32-byte sector per 4-byte index
+// (compress_large.glsl:224-228).  Algorithmic bytes: n (mask) + 4 * count (indices).
 #include <cstdlib>
 
 #include "hj_internal.h"
 #include "lookback.cuh"
+#include "peer.cuh"
 #include "ring.cuh"
 
 namespace hj {
@@ -192,6 +196,11 @@ struct CompressOp {
         uint32_t* out_count;
         uint32_t index_base;
         size_t n;  // ZT: number of mask elements = length of index_out
+        // sharded compaction (comm.cu): xepoch != 0 makes the CTA that owns the last tile exchange the
+        // per-rank counts over peer memory — out_count[0] = global count, counts_out[q] = count of rank q
+        uint32_t* counts_out;
+        PeerView pv;
+        uint32_t xepoch;
     };
     // aux layout (shared memory behind the ring): TSLOTS mask planes of TILE/8 bytes (one u16 per
     // 16 mask bytes), then one 1 KiB index stage per consumer warp.  Phase 1 leaves only the masks
@@ -337,14 +346,24 @@ struct CompressOp {
         }
     }
     // compress_large.glsl:214-216: the last partition publishes the count
-    static __device__ __forceinline__ void finish(P total, const Args& a) { a.out_count[0] = total; }
+    static __device__ __forceinline__ void finish(P total, const Args& a, int lane) {
+        if (a.xepoch == 0) {
+            if (lane == 0) a.out_count[0] = total;
+            return;
+        }
+        const uint32_t c = (uint32_t)peer_allgather_warp(a.pv, a.xepoch, total, lane);  // lane q: count of rank q
+        if (a.counts_out && lane < a.pv.world) a.counts_out[lane] = c;
+        const uint32_t all = __reduce_add_sync(0xffffffffu, c);
+        if (lane == 0) a.out_count[0] = all;
+    }
 };
 
 template <int CR_TILE, int CR_STAGES, int CR_TSLOTS, int CR_AHEAD, bool TRACE = false, bool ZT = false>
 __global__ void __launch_bounds__((CR_WARPS + 3) * 32, 1)
 compress_ring_kernel(const uint8_t* __restrict__ mask, size_t n, const uint32_t* __restrict__ size_buf,
                      uint32_t* __restrict__ out_count, uint32_t* __restrict__ index_out, uint32_t index_base,
-                     LookbackView lb, uint32_t G, unsigned long long* trace) {
+                     LookbackView lb, uint32_t G, unsigned long long* trace, uint32_t* __restrict__ counts_out,
+                     PeerView pv, uint32_t xepoch) {
     extern __shared__ __align__(128) char smem[];
     size_t n_eff = n;
     if (size_buf) {  // DynSize: device-resident element count (graph.rs:503-508)
@@ -354,7 +373,7 @@ compress_ring_kernel(const uint8_t* __restrict__ mask, size_t n, const uint32_t*
     const uint32_t n_tiles = (uint32_t)((n_eff + CR_TILE - 1) / CR_TILE);
     if (n_tiles == 0 && blockIdx.x == 0 && threadIdx.x == 0) out_count[0] = 0;
     using Op = CompressOp<CR_TILE / CR_WARPS, CR_TILE, CR_TSLOTS, ZT>;
-    typename Op::Args args{index_out, out_count, index_base, n_eff};
+    typename Op::Args args{index_out, out_count, index_base, n_eff, counts_out, pv, xepoch};
     ring_pipeline<Op, CR_TILE, CR_STAGES, CR_WARPS, CR_AHEAD, CR_TSLOTS, true, 8, TRACE>(
         reinterpret_cast<const char*>(mask), n_eff, n_tiles, 0u, lb, G, args, smem, trace);
 }
@@ -397,14 +416,23 @@ hj_status launch_compress_zero_tail(hj_device* dev, uint32_t* index_out, const u
     return check_launch(dev, "compress_zero_tail_kernel");
 }
 
+bool compress_can_fuse_exchange(size_t n, const uint8_t* mask) {
+    static const int cfg = getenv("HJ_COMPRESS_CFG") ? atoi(getenv("HJ_COMPRESS_CFG")) : 1;
+    return cfg != 0 && ((uintptr_t)mask & 15u) == 0 && n >= (64u << 10) && !g_compress_trace;
+}
+
 hj_status launch_compress(hj_device* dev, size_t n, const uint32_t* size_buf, uint32_t* out_count,
-                          const uint8_t* mask, uint32_t* index_out, uint32_t index_base, bool zero_tail) {
+                          const uint8_t* mask, uint32_t* index_out, uint32_t index_base, bool zero_tail,
+                          uint32_t* counts_out, const PeerView* peers, uint32_t xepoch) {
     HJ_REQUIRE(n <= 0xffffffffull, "compress: n does not fit the u32 index type");
+    HJ_REQUIRE(!peers || (compress_can_fuse_exchange(n, mask) && !size_buf),
+               "compress: the fused exchange needs the ring kernel and a static size");
     if (zero_tail) {  // only the ring kernel on a statically sized, aligned buffer zeroes the tail itself
         static const int c = getenv("HJ_COMPRESS_CFG") ? atoi(getenv("HJ_COMPRESS_CFG")) : 1;
         const bool in_kernel = c == 1 && !size_buf && !g_compress_trace && ((uintptr_t)mask & 15u) == 0 &&
                                ((uintptr_t)index_out & 15u) == 0 && n >= (64u << 10) && !getenv("HJ_ZERO_TAIL_KERNEL");
         if (!in_kernel) {
+            HJ_REQUIRE(!peers, "compress: zero tail outside the ring kernel cannot be combined with the fused exchange");
             HJ_TRY(launch_compress(dev, n, size_buf, out_count, mask, index_out, index_base, false));
             return launch_compress_zero_tail(dev, index_out, out_count, n);
         }
@@ -424,7 +452,8 @@ hj_status launch_compress(hj_device* dev, size_t n, const uint32_t* size_buf, ui
             HJ_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             kernel<<<grid, (CR_WARPS + 3) * 32, smem, dev->stream>>>(mask, n, size_buf, out_count, index_out,
                                                                                 index_base, view, (grid + 31u) & ~31u,
-                                                                                g_compress_trace);
+                                                                                g_compress_trace, counts_out,
+                                                                                peers ? *peers : PeerView(), peers ? xepoch : 0u);
             return HJ_OK;
         };
         const size_t smem_small = ring_smem_bytes<uint32_t, 28672, 5, CR_WARPS, 8>(8 * (28672 / 8) + CR_WARPS * 1024);

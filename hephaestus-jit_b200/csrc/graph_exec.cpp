@@ -13,6 +13,7 @@
 // call blocks until they are resolved — the reference always blocks on a fence and reads GPU
 // timestamps (vulkan_core/device.rs:297-334, profiler.rs:56-131).  Without a report the call
 // is asynchronous.
+#include <algorithm>
 #include <chrono>
 
 #include "hj_internal.h"
@@ -136,18 +137,127 @@ extern "C" int32_t hj_ir_index_zero_fill(const hj_ir* ir, uint32_t slot, uint32_
     return 1;
 }
 
-extern "C" hj_status hj_execute_graph(hj_device* dev, const hj_pass* passes, uint32_t n_passes,
-                                      hj_buffer* const* env, const hj_buffer_desc* descs,
-                                      uint32_t n_resources, hj_report* report) {
-    HJ_REQUIRE(dev && (passes || n_passes == 0), "hj_execute_graph: null argument");
-    HJ_REQUIRE((env && descs) || n_resources == 0, "hj_execute_graph: null environment");
+namespace {
+
+// CUDA events of a timed launch; destroyed on every path out of execute_passes
+struct EventList {
+    std::vector<cudaEvent_t> ev;
+    ~EventList() {
+        for (cudaEvent_t e : ev)
+            if (e) cudaEventDestroy(e);
+    }
+    hj_status create(size_t n) {
+        ev.assign(n, nullptr);
+        for (auto& e : ev) HJ_CUDA(cudaEventCreate(&e));
+        return HJ_OK;
+    }
+};
+
+// Sharded execution (hj_execute_graph_sharded): which rank this is and where every resource lives
+struct ShardCtx {
+    hj_comm* comm;
+    hj_shard_desc* shards;
+    int rank, world;
+};
+
+void shard_bounds(uint64_t n, int world, int rank, uint64_t* start, uint64_t* end) {
+    const uint64_t base = n / (uint64_t)world, rem = n % (uint64_t)world;
+    *start = (uint64_t)rank * base + std::min<uint64_t>((uint64_t)rank, rem);
+    *end = *start + base + ((uint64_t)rank < rem ? 1 : 0);
+}
+
+// An owned copy of an IR whose Gathers from the `deferred` slots add the slot's seed (a one-element
+// buffer bound to a NEW slot behind the original ones): Gather(buf, i) becomes
+// Gather(buf, i) + Gather(seed, 0).  This is how the consumers of a sharded scan apply the
+// cross-GPU offset at load instead of the scan paying a second pass over its output.
+struct SeededIR {
+    std::vector<hj_ir_var> vars;
+    std::vector<uint32_t> deps;
+    std::vector<hj_type_desc> types;
+    hj_ir view;
+    std::vector<uint32_t> seed_of_slot;  // extra slot k (n_buffers + k of the original) carries the seed of this original slot
+};
+void build_seeded_ir(const hj_ir* ir, const std::vector<bool>& deferred, SeededIR* out) {
+    IRView v(ir);
+    out->types.assign(ir->types, ir->types + ir->n_types);
+    uint32_t u32_ty = ir->n_types;
+    for (uint32_t t = 0; t < ir->n_types; t++)
+        if (ir->types[t].kind == HJ_U32) { u32_ty = t; break; }
+    if (u32_ty == ir->n_types) {
+        hj_type_desc d = {};
+        d.kind = HJ_U32;
+        out->types.push_back(d);
+    }
+    std::vector<int64_t> extra_slot(ir->n_buffers, -1);
+    std::vector<uint32_t> remap(ir->n_vars);
+    auto push = [&](uint32_t ty, uint32_t op, uint32_t arg, uint64_t data, std::initializer_list<uint32_t> d) {
+        hj_ir_var nv = {};
+        nv.ty = ty;
+        nv.op = op;
+        nv.arg = arg;
+        nv.data = data;
+        nv.dep_start = (uint32_t)out->deps.size();
+        out->deps.insert(out->deps.end(), d.begin(), d.end());
+        nv.dep_end = (uint32_t)out->deps.size();
+        out->vars.push_back(nv);
+        return (uint32_t)out->vars.size() - 1;
+    };
+    for (uint32_t i = 0; i < ir->n_vars; i++) {
+        hj_ir_var nv = v.var(i);
+        const uint32_t d0 = nv.dep_start, d1 = nv.dep_end;
+        nv.dep_start = (uint32_t)out->deps.size();
+        for (uint32_t k = d0; k < d1; k++) out->deps.push_back(remap[ir->deps[k]]);
+        nv.dep_end = (uint32_t)out->deps.size();
+        out->vars.push_back(nv);
+        uint32_t id = (uint32_t)out->vars.size() - 1;
+        if (nv.op == HJ_OP_GATHER && d1 - d0 == 2) {
+            const hj_ir_var& buf = v.var(ir->deps[d0]);
+            if (buf.op == HJ_OP_BUFFER_REF && buf.data < ir->n_buffers && deferred[buf.data]) {
+                if (extra_slot[buf.data] < 0) {
+                    extra_slot[buf.data] = (int64_t)ir->n_buffers + (int64_t)out->seed_of_slot.size();
+                    out->seed_of_slot.push_back((uint32_t)buf.data);
+                }
+                const uint32_t ref = push(buf.ty, HJ_OP_BUFFER_REF, 0, (uint64_t)extra_slot[buf.data], {});
+                const uint32_t zero = push(u32_ty, HJ_OP_LITERAL, 0, 0, {});
+                const uint32_t seed = push(nv.ty, HJ_OP_GATHER, 0, 0, {ref, zero});
+                id = push(nv.ty, HJ_OP_BOP, HJ_BOP_ADD, 0, {id, seed});
+            }
+        }
+        remap[i] = id;
+    }
+    out->view = *ir;
+    out->view.vars = out->vars.data();
+    out->view.n_vars = (uint32_t)out->vars.size();
+    out->view.deps = out->deps.data();
+    out->view.n_deps = (uint32_t)out->deps.size();
+    out->view.types = out->types.data();
+    out->view.n_types = (uint32_t)out->types.size();
+    out->view.n_buffers = ir->n_buffers + (uint32_t)out->seed_of_slot.size();
+}
+
+bool integer_kind(uint32_t k) { return k >= HJ_I8 && k <= HJ_U64; }
+
+// buf[0 .. n_local) += seed: a deferred scan result becomes an ordinary shard
+hj_status materialise(hj_device* dev, const ShardCtx* sc, uint32_t rid, hj_buffer* buf, const hj_buffer_desc& d) {
+    hj_shard_desc& sd = sc->shards[rid];
+    if (!sd.deferred) return HJ_OK;
+    HJ_REQUIRE(sd.seed, "resource %u is marked deferred but carries no seed buffer", rid);
+    uint64_t s0, s1;
+    shard_bounds(d.size, sc->world, sc->rank, &s0, &s1);
+    HJ_TRY(hj_apply_seed(dev, (hj_type_kind)d.ty, (size_t)(s1 - s0), buf, sd.seed));
+    sd.deferred = 0;
+    return HJ_OK;
+}
+
+hj_status execute_passes(hj_device* dev, const ShardCtx* sc, const hj_pass* passes, uint32_t n_passes,
+                         hj_buffer* const* env, const hj_buffer_desc* descs, uint32_t n_resources, hj_report* report) {
     auto cpu_start = std::chrono::steady_clock::now();
     const bool timed = report && report->passes && report->passes_capacity >= n_passes;
-    std::vector<cudaEvent_t> ev;
+    EventList events;
+    std::vector<cudaEvent_t>& ev = events.ev;
     if (timed) {
         cudaSetDevice(dev->ordinal);
-        ev.resize((size_t)n_passes + 1);
-        for (auto& e : ev) HJ_CUDA(cudaEventCreate(&e));
+        HJ_TRY(events.create((size_t)n_passes + 1));
         HJ_CUDA(cudaEventRecord(ev[0], dev->stream));
     }
     auto res = [&](const hj_pass& p, uint32_t k, hj_buffer** out, const hj_buffer_desc** desc) -> hj_status {
@@ -157,6 +267,18 @@ extern "C" hj_status hj_execute_graph(hj_device* dev, const hj_pass* passes, uin
         HJ_REQUIRE(env[id], "resource %u has been left empty (graph.rs: UninitializedResourve)", id);
         *out = env[id];
         if (desc) *desc = &descs[id];
+        return HJ_OK;
+    };
+    auto sharded = [&](uint32_t rid) { return sc && sc->shards[rid].placement == HJ_RES_SHARDED; };
+    // this rank's block of a sharded resource
+    auto local_of = [&](uint32_t rid, uint64_t* start, uint64_t* count) -> hj_status {
+        uint64_t s0, s1;
+        shard_bounds(descs[rid].size, sc->world, sc->rank, &s0, &s1);
+        HJ_REQUIRE(s1 > s0, "resource %u: %llu elements cannot be sharded over %d ranks", rid,
+                   (unsigned long long)descs[rid].size, sc->world);
+        HJ_REQUIRE(descs[rid].size <= 0xffffffffull, "resource %u: global size does not fit the u32 index type", rid);
+        *start = s0;
+        *count = s1 - s0;
         return HJ_OK;
     };
 
@@ -169,18 +291,42 @@ extern "C" hj_status hj_execute_graph(hj_device* dev, const hj_pass* passes, uin
             HJ_REQUIRE((uint32_t)p.size_buffer < n_resources && env[p.size_buffer], "size buffer resource missing");
             size_buf = env[p.size_buffer];
         }
+        for (uint32_t b = 0; b < p.n_resources; b++)
+            HJ_REQUIRE(p.resources && p.resources[b] < n_resources, "pass %u: ResourceId out of range", i);
         switch (p.kind) {
         case HJ_PASS_KERNEL: {
             HJ_REQUIRE(p.ir, "kernel pass %u without IR", i);
+            {   // an FFI caller may hand over anything: the matchers below index vars / deps by id
+                const std::string verr = validate_ir(p.ir);
+                if (!verr.empty()) return fail(HJ_ERR_INVALID, "kernel pass %u: IR rejected: %s", i, verr.c_str());
+                HJ_REQUIRE(p.ir->n_buffers == p.n_resources, "kernel pass %u: IR names %u buffers, the pass binds %u", i,
+                           p.ir->n_buffers, p.n_resources);
+            }
+            bool pass_sharded = false;
+            for (uint32_t b = 0; b < p.n_resources; b++) pass_sharded = pass_sharded || sharded(p.resources[b]);
+            HJ_REQUIRE(!(pass_sharded && size_buf), "kernel pass %u: a DynSize kernel over sharded resources is not supported "
+                       "(re-balance the compacted sequence first: hj_sharded_rebalance)", i);
             HistMatch hm;
-            if (!size_buf && p.n_resources == 2 && p.size >= (1u << 20) && match_histogram(p.ir, &hm)) {
+            if (!size_buf && p.n_resources == 2 && p.size >= (1u << 20) && match_histogram(p.ir, &hm) &&
+                (!pass_sharded || (sharded(p.resources[hm.key_slot]) && !sharded(p.resources[hm.dst_slot])))) {
                 snprintf(name, sizeof(name), "Histogram %u [%llu]", i, (unsigned long long)p.size);
                 hj_buffer *dst = nullptr, *keys = nullptr;
                 const hj_buffer_desc* ddst = nullptr;
                 HJ_TRY(res(p, hm.dst_slot, &dst, &ddst));
                 HJ_TRY(res(p, hm.key_slot, &keys, nullptr));
-                HJ_TRY(hj_scatter_reduce(dev, HJ_REDUCE_SUM, (hj_type_kind)hm.ty, p.size, keys, nullptr, hm.literal, dst,
-                                         ddst->size));
+                if (pass_sharded) {
+                    // privatised per GPU, then combined: the result is the sum over ranks of their copies of
+                    // dst, so only rank 0 keeps what dst held before
+                    uint64_t k0, kn;
+                    HJ_TRY(local_of(p.resources[hm.key_slot], &k0, &kn));
+                    HJ_TRY(materialise(dev, sc, p.resources[hm.key_slot], keys, descs[p.resources[hm.key_slot]]));
+                    if (sc->rank != 0) HJ_CUDA(cudaMemsetAsync(dst->ptr, 0, ddst->size * 4, dev->stream));
+                    HJ_TRY(hj_sharded_scatter_reduce(sc->comm, HJ_REDUCE_SUM, (hj_type_kind)hm.ty, (size_t)kn, keys, nullptr,
+                                                     hm.literal, dst, ddst->size));
+                } else {
+                    HJ_TRY(hj_scatter_reduce(dev, HJ_REDUCE_SUM, (hj_type_kind)hm.ty, p.size, keys, nullptr, hm.literal, dst,
+                                             ddst->size));
+                }
                 break;
             }
             // zero-fill of the index buffer of the Compress pass that follows (see match_index_prefill)
@@ -218,7 +364,8 @@ extern "C" hj_status hj_execute_graph(hj_device* dev, const hj_pass* passes, uin
                     if (p.resources[b] == index_res) slot = slot == p.n_resources ? b : p.n_resources + 1;
                 if (slot < p.n_resources && index_res < n_resources && mask_res < n_resources && env[index_res] &&
                     ((uintptr_t)env[index_res]->ptr & 15u) == 0 && descs[index_res].size == p.size &&
-                    descs[mask_res].size == p.size && match_index_prefill(p.ir, slot, &pm)) {
+                    descs[mask_res].size == p.size && sharded(index_res) == sharded(mask_res) &&
+                    match_index_prefill(p.ir, slot, &pm)) {
                     zero_tail_for = (int64_t)i + 1;
                     if (pm.only_side_effect) {
                         snprintf(name, sizeof(name), "JIT Kernel %u [%llu] (index zero-fill left to Compress)", i,
@@ -238,11 +385,48 @@ extern "C" hj_status hj_execute_graph(hj_device* dev, const hj_pass* passes, uin
                 }
             }
             snprintf(name, sizeof(name), "JIT Kernel %u [%llu]", i, (unsigned long long)p.size);
-            hj_kernel* k = nullptr;
-            HJ_TRY(hj_kernel_get(dev, ir, &k));
             std::vector<hj_buffer*> bufs(p.n_resources);
             for (uint32_t b = 0; b < p.n_resources; b++) HJ_TRY(res(p, b, &bufs[b], nullptr));
-            hj_status s = hj_kernel_launch(dev, k, p.size, size_buf, bufs.data(), p.n_resources, 0);
+            size_t launch_size = p.size;
+            uint32_t index_base = 0;
+            SeededIR seeded;
+            if (pass_sharded) {
+                // every sharded resource is one contiguous block of a global array of p.size elements,
+                // addressed by the bare Index; everything else is a replica and may only be read
+                std::vector<SlotAccess> access;
+                analyse_slot_access(ir, &access);
+                uint64_t s0 = 0, cnt = 0;
+                std::vector<bool> add_seed(p.n_resources, false);
+                bool any_seed = false;
+                for (uint32_t b = 0; b < p.n_resources; b++) {
+                    const uint32_t rid = p.resources[b];
+                    if (!sharded(rid)) {
+                        if (access[b].written)
+                            return fail(HJ_ERR_UNSUPPORTED, "kernel pass %u writes resource %u, a replica, from a kernel over "
+                                        "sharded data: scatters into a sharded-over destination are replicas only (SURVEY 8e)", i, rid);
+                        continue;
+                    }
+                    if (descs[rid].size != p.size || !access[b].index_only)
+                        return fail(HJ_ERR_UNSUPPORTED, "kernel pass %u addresses sharded resource %u through a computed index "
+                                    "or with another extent: only Index-addressed access shards (SURVEY 8e)", i, rid);
+                    HJ_TRY(local_of(rid, &s0, &cnt));
+                    if (sc->shards[rid].deferred) {
+                        if (access[b].written || access[b].cond_gather) HJ_TRY(materialise(dev, sc, rid, bufs[b], descs[rid]));
+                        else add_seed[b] = any_seed = true;
+                    }
+                }
+                launch_size = (size_t)cnt;
+                index_base = (uint32_t)s0;
+                if (any_seed) {
+                    build_seeded_ir(ir, add_seed, &seeded);
+                    ir = &seeded.view;
+                    for (uint32_t slot : seeded.seed_of_slot) bufs.push_back(sc->shards[p.resources[slot]].seed);
+                    for (hj_buffer* sb : bufs) HJ_REQUIRE(sb, "kernel pass %u: a deferred resource carries no seed buffer", i);
+                }
+            }
+            hj_kernel* k = nullptr;
+            HJ_TRY(hj_kernel_get(dev, ir, &k));
+            hj_status s = hj_kernel_launch(dev, k, launch_size, size_buf, bufs.data(), (uint32_t)bufs.size(), index_base);
             hj_kernel_release(k);
             HJ_TRY(s);
             break;
@@ -253,7 +437,14 @@ extern "C" hj_status hj_execute_graph(hj_device* dev, const hj_pass* passes, uin
             const hj_buffer_desc *ddst = nullptr, *dsrc = nullptr;
             HJ_TRY(res(p, 0, &dst, &ddst));
             HJ_TRY(res(p, 1, &src, &dsrc));
-            HJ_TRY(hj_reduce(dev, (hj_reduce_op)p.arg, (hj_type_kind)ddst->ty, dsrc->size, src, dst));
+            if (sharded(p.resources[1])) {
+                uint64_t s0, cnt;
+                HJ_TRY(local_of(p.resources[1], &s0, &cnt));
+                HJ_TRY(materialise(dev, sc, p.resources[1], src, *dsrc));
+                HJ_TRY(hj_sharded_reduce(sc->comm, (hj_reduce_op)p.arg, (hj_type_kind)ddst->ty, (size_t)cnt, src, dst));
+            } else {
+                HJ_TRY(hj_reduce(dev, (hj_reduce_op)p.arg, (hj_type_kind)ddst->ty, dsrc->size, src, dst));
+            }
             break;
         }
         case HJ_PASS_PREFIX_SUM: {
@@ -262,7 +453,26 @@ extern "C" hj_status hj_execute_graph(hj_device* dev, const hj_pass* passes, uin
             const hj_buffer_desc *ddst = nullptr, *dsrc = nullptr;
             HJ_TRY(res(p, 0, &dst, &ddst));
             HJ_TRY(res(p, 1, &src, &dsrc));
-            HJ_TRY(hj_prefix_sum(dev, (hj_type_kind)ddst->ty, dsrc->size, (int32_t)p.arg, src, dst, nullptr));
+            if (sharded(p.resources[1])) {
+                HJ_REQUIRE(sharded(p.resources[0]), "prefix-sum pass %u: the scan of a sharded resource is sharded", i);
+                uint64_t s0, cnt;
+                HJ_TRY(local_of(p.resources[1], &s0, &cnt));
+                HJ_TRY(materialise(dev, sc, p.resources[1], src, *dsrc));
+                hj_shard_desc& sd = sc->shards[p.resources[0]];
+                static const bool no_defer = getenv("HJ_NO_DEFERRED_SEED") != nullptr;
+                if (sd.seed && integer_kind(ddst->ty) && sc->world > 1 && !no_defer) {
+                    // 8 bytes per element: local scan, the rank's offset stays in `seed` for the consumers
+                    HJ_TRY(hj_sharded_prefix_sum_deferred(sc->comm, (hj_type_kind)ddst->ty, (size_t)cnt, (int32_t)p.arg, src, dst,
+                                                          sd.seed));
+                    sd.deferred = 1;
+                    snprintf(name, sizeof(name), "Prefix Sum Large (deferred seed)");
+                } else {
+                    HJ_TRY(hj_sharded_prefix_sum(sc->comm, (hj_type_kind)ddst->ty, (size_t)cnt, (int32_t)p.arg, src, dst));
+                    sd.deferred = 0;
+                }
+            } else {
+                HJ_TRY(hj_prefix_sum(dev, (hj_type_kind)ddst->ty, dsrc->size, (int32_t)p.arg, src, dst, nullptr));
+            }
             break;
         }
         case HJ_PASS_COMPRESS: {
@@ -272,7 +482,17 @@ extern "C" hj_status hj_execute_graph(hj_device* dev, const hj_pass* passes, uin
             HJ_TRY(res(p, 0, &index_out, nullptr));
             HJ_TRY(res(p, 1, &out_count, nullptr));
             HJ_TRY(res(p, 2, &src, &dsrc));
-            if (zero_tail_for == (int64_t)i) {  // the pass in front left the zero-fill to us
+            const bool zt = zero_tail_for == (int64_t)i;  // the pass in front left the zero-fill to us
+            if (sharded(p.resources[2])) {
+                HJ_REQUIRE(sharded(p.resources[0]) && !sharded(p.resources[1]),
+                           "compress pass %u: the index segment of a sharded mask is sharded, the count a replica", i);
+                HJ_REQUIRE(!size_buf, "compress pass %u: DynSize over a sharded mask is not supported", i);
+                uint64_t s0, cnt;
+                HJ_TRY(local_of(p.resources[2], &s0, &cnt));
+                HJ_REQUIRE(cnt <= src->bytes && cnt * 4 <= index_out->bytes && out_count->bytes >= 4,
+                           "compress pass %u: buffer sizes do not match the %llu-element shard", i, (unsigned long long)cnt);
+                HJ_TRY(sharded_compress_pass(sc->comm, (size_t)cnt, (uint32_t)s0, src, index_out, out_count, zt));
+            } else if (zt) {
                 const size_t n = dsrc->size;
                 HJ_REQUIRE(n >= 1 && n <= src->bytes && n * 4 <= index_out->bytes && out_count->bytes >= 4 &&
                                (!size_buf || size_buf->bytes >= 4),
@@ -303,7 +523,6 @@ extern "C" hj_status hj_execute_graph(hj_device* dev, const hj_pass* passes, uin
             report->passes[i].start_us = start_ms * 1e3;
             report->passes[i].duration_us = dur_ms * 1e3;
         }
-        for (auto& e : ev) cudaEventDestroy(e);
     }
     if (report) {
         report->n_passes = n_passes;
@@ -311,6 +530,105 @@ extern "C" hj_status hj_execute_graph(hj_device* dev, const hj_pass* passes, uin
             std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - cpu_start).count();
     }
     return HJ_OK;
+}
+
+}  // namespace
+
+extern "C" hj_status hj_execute_graph(hj_device* dev, const hj_pass* passes, uint32_t n_passes,
+                                      hj_buffer* const* env, const hj_buffer_desc* descs,
+                                      uint32_t n_resources, hj_report* report) {
+    HJ_REQUIRE(dev && (passes || n_passes == 0), "hj_execute_graph: null argument");
+    HJ_REQUIRE((env && descs) || n_resources == 0, "hj_execute_graph: null environment");
+    return execute_passes(dev, nullptr, passes, n_passes, env, descs, n_resources, report);
+}
+
+// ---- sharded execution ---------------------------------------------------------------------------
+extern "C" void hj_shard_bounds(uint64_t n, int32_t world, int32_t rank, uint64_t* start, uint64_t* end) {
+    uint64_t s = 0, e = 0;
+    if (world >= 1 && rank >= 0 && rank < world) shard_bounds(n, world, rank, &s, &e);
+    if (start) *start = s;
+    if (end) *end = e;
+}
+
+// Placement propagation, host only.  Resources the caller has placed keep their placement; every
+// HJ_RES_AUTO resource takes the placement of the first pass that writes it:
+//   kernel over sharded data  -> outputs of the pass extent written at the bare Index are SHARDED,
+//                                 everything else a replica;
+//   Reduce                    -> dst replicated (every rank ends up with the global result);
+//   PrefixSum                 -> dst like src;
+//   Compress                  -> index_out like the mask, out_count replicated (global count).
+extern "C" hj_status hj_shard_plan(const hj_pass* passes, uint32_t n_passes, const hj_buffer_desc* descs, uint32_t n_resources,
+                                   hj_shard_desc* shards) {
+    HJ_REQUIRE((passes || n_passes == 0) && ((descs && shards) || n_resources == 0), "hj_shard_plan: null argument");
+    auto place = [&](uint32_t rid, uint32_t pl) {
+        if (shards[rid].placement == HJ_RES_AUTO) shards[rid].placement = pl;
+    };
+    for (uint32_t i = 0; i < n_passes; i++) {
+        const hj_pass& p = passes[i];
+        for (uint32_t b = 0; b < p.n_resources; b++)
+            HJ_REQUIRE(p.resources && p.resources[b] < n_resources, "pass %u: ResourceId out of range", i);
+        switch (p.kind) {
+        case HJ_PASS_KERNEL: {
+            HJ_REQUIRE(p.ir, "kernel pass %u without IR", i);
+            const std::string verr = validate_ir(p.ir);
+            if (!verr.empty()) return fail(HJ_ERR_INVALID, "kernel pass %u: IR rejected: %s", i, verr.c_str());
+            HJ_REQUIRE(p.ir->n_buffers == p.n_resources, "kernel pass %u: IR names %u buffers, the pass binds %u", i,
+                       p.ir->n_buffers, p.n_resources);
+            bool any = false;
+            for (uint32_t b = 0; b < p.n_resources; b++) any = any || shards[p.resources[b]].placement == HJ_RES_SHARDED;
+            std::vector<SlotAccess> access;
+            analyse_slot_access(p.ir, &access);
+            for (uint32_t b = 0; b < p.n_resources; b++) {
+                const uint32_t rid = p.resources[b];
+                const bool shard_out = any && p.size_buffer < 0 && access[b].written && access[b].index_only && descs[rid].size == p.size;
+                place(rid, shard_out ? HJ_RES_SHARDED : HJ_RES_REPLICATED);
+            }
+            break;
+        }
+        case HJ_PASS_REDUCE:
+            HJ_REQUIRE(p.n_resources >= 2, "reduce pass %u needs [dst, src]", i);
+            place(p.resources[1], HJ_RES_REPLICATED);
+            place(p.resources[0], HJ_RES_REPLICATED);
+            break;
+        case HJ_PASS_PREFIX_SUM:
+            HJ_REQUIRE(p.n_resources >= 2, "prefix-sum pass %u needs [dst, src]", i);
+            place(p.resources[1], HJ_RES_REPLICATED);
+            place(p.resources[0], shards[p.resources[1]].placement);
+            break;
+        case HJ_PASS_COMPRESS:
+            HJ_REQUIRE(p.n_resources >= 3, "compress pass %u needs [index_out, out_count, src]", i);
+            place(p.resources[2], HJ_RES_REPLICATED);
+            place(p.resources[0], shards[p.resources[2]].placement);
+            place(p.resources[1], HJ_RES_REPLICATED);
+            break;
+        default:
+            return fail(HJ_ERR_UNSUPPORTED, "pass %u: device op %u is out of scope for the B200 backend", i, p.kind);
+        }
+    }
+    for (uint32_t r = 0; r < n_resources; r++) place(r, HJ_RES_REPLICATED);  // never touched by a pass
+    return HJ_OK;
+}
+
+extern "C" hj_status hj_execute_graph_sharded(hj_comm* comm, const hj_pass* passes, uint32_t n_passes, hj_buffer* const* env,
+                                              const hj_buffer_desc* descs, uint32_t n_resources, hj_shard_desc* shards,
+                                              hj_report* report) {
+    HJ_REQUIRE(comm && (passes || n_passes == 0), "hj_execute_graph_sharded: null argument");
+    HJ_REQUIRE((env && descs && shards) || n_resources == 0, "hj_execute_graph_sharded: null environment");
+    ShardCtx sc;
+    sc.comm = comm;
+    sc.shards = shards;
+    int32_t rank = 0, world = 1;
+    HJ_TRY(hj_comm_info(comm, &rank, &world, nullptr, nullptr));
+    sc.rank = rank;
+    sc.world = world;
+    for (uint32_t r = 0; r < n_resources; r++)
+        HJ_REQUIRE(shards[r].placement == HJ_RES_REPLICATED || shards[r].placement == HJ_RES_SHARDED,
+                   "resource %u has no placement (run hj_shard_plan first)", r);
+    hj_device* dev = comm_device(comm);
+    // the exchange epochs of the sharded kernels are launch parameters: not replayable from a captured
+    // CUDA graph, so a sharded launch always runs pass by pass, with the device lock held throughout
+    DeviceGuard g(dev);
+    return execute_passes(dev, &sc, passes, n_passes, env, descs, n_resources, report);
 }
 
 namespace {

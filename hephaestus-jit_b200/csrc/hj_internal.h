@@ -116,19 +116,37 @@ struct PeerView;  // peer.cuh
 // memory inside the same kernel (sharded reduce, comm.cu)
 hj_status launch_reduce(hj_device* dev, hj_reduce_op op, hj_type_kind ty, size_t n,
                         const void* src, void* dst, const PeerView* peers = nullptr, uint32_t epoch = 0);
+// `seed_out` / `peers` / `xepoch` (optional, ring kernel only — see prefix_sum_can_fuse_exchange):
+// the kernel also exchanges the shard totals over peer memory and writes this rank's exclusive
+// offset to seed_out[0] (the DEFERRED seed of a sharded scan, comm.cu)
 hj_status launch_prefix_sum(hj_device* dev, hj_type_kind ty, size_t n, bool inclusive,
-                            const void* src, void* dst, const void* seed);
+                            const void* src, void* dst, const void* seed, void* seed_out = nullptr,
+                            const PeerView* peers = nullptr, uint32_t xepoch = 0);
+bool prefix_sum_can_fuse_exchange(hj_type_kind ty, size_t n, const void* src, const void* dst);
 hj_status launch_compress_zero_tail(hj_device* dev, uint32_t* index_out, const uint32_t* count, size_t n);
 // zero_tail: also leave index_out[count .. n) zeroed (in the ring kernel where it can, else by
 // launch_compress_zero_tail afterwards)
+// `counts_out` / `peers` / `xepoch` (optional, ring kernel only — see compress_can_fuse_exchange): the
+// kernel also exchanges the per-rank counts over peer memory; out_count[0] then holds the GLOBAL
+// count and counts_out[q] (may be NULL) the count of rank q
 hj_status launch_compress(hj_device* dev, size_t n, const uint32_t* size_buf, uint32_t* out_count,
-                          const uint8_t* mask, uint32_t* index_out, uint32_t index_base, bool zero_tail = false);
+                          const uint8_t* mask, uint32_t* index_out, uint32_t index_base, bool zero_tail = false,
+                          uint32_t* counts_out = nullptr, const PeerView* peers = nullptr, uint32_t xepoch = 0);
+bool compress_can_fuse_exchange(size_t n, const uint8_t* mask);
+struct ArrayPeerView;  // peer.cuh
+// `ax` (optional): on the packed-16 histogram path the fold kernel also all-reduces the bins over
+// peer memory; *exchanged tells the caller whether that happened (else it combines the copies itself)
 hj_status launch_scatter_reduce(hj_device* dev, hj_reduce_op op, hj_type_kind ty, size_t n,
                                 const uint32_t* idx, const void* src, uint64_t literal, void* dst,
-                                size_t n_dst);
+                                size_t n_dst, const ArrayPeerView* ax = nullptr, bool* exchanged = nullptr);
 hj_status launch_gather(hj_device* dev, size_t elem_bytes, size_t n, const void* src,
                         const uint32_t* idx, void* dst);
 hj_status launch_fill(hj_device* dev, void* dst, size_t n, size_t elem_bytes, uint64_t pattern);
+
+// comm.cu internals used by the sharded pass interpreter (graph_exec.cpp)
+hj_device* comm_device(hj_comm* c);
+hj_status sharded_compress_pass(hj_comm* c, size_t n_local, uint32_t index_base, hj_buffer* mask, hj_buffer* index_out,
+                                hj_buffer* out_count, bool zero_tail);
 
 inline hj_status check_launch(hj_device* dev, const char* what) {
     cudaError_t e = cudaGetLastError();

@@ -17,6 +17,43 @@ uint64_t hash_bytes(const void* data, size_t n, uint64_t h) {
     return h;
 }
 
+void analyse_slot_access(const hj_ir* ir, std::vector<SlotAccess>* out) {
+    IRView v(ir);
+    out->assign(ir->n_buffers, SlotAccess());
+    int depth = 0;
+    for (uint32_t i = 0; i < ir->n_vars; i++) {
+        const hj_ir_var& var = v.var(i);
+        switch (var.op) {
+        case HJ_OP_LOOP_START: case HJ_OP_IF_START: depth++; break;
+        case HJ_OP_LOOP_END: case HJ_OP_IF_END: depth--; break;
+        case HJ_OP_GATHER: {
+            const hj_ir_var& buf = v.var(v.dep(i, 0));
+            if (buf.op != HJ_OP_BUFFER_REF || buf.data >= ir->n_buffers) break;
+            SlotAccess& s = (*out)[buf.data];
+            s.read = true;
+            s.last_read = i;
+            if (v.n_deps(i) > 2) s.cond_gather = true;
+            if (v.var(v.dep(i, 1)).op != HJ_OP_INDEX) s.index_only = false;
+            if (v.var(v.dep(i, 1)).op != HJ_OP_INDEX || depth != 0) s.identity = false;
+            break;
+        }
+        case HJ_OP_SCATTER: case HJ_OP_SCATTER_REDUCE: case HJ_OP_SCATTER_ATOMIC: case HJ_OP_ATOMIC_INC: {
+            const hj_ir_var& buf = v.var(v.dep(i, 0));
+            if (buf.op != HJ_OP_BUFFER_REF || buf.data >= ir->n_buffers) break;
+            SlotAccess& s = (*out)[buf.data];
+            s.written = true;
+            if (s.first_write > (int64_t)i) s.first_write = i;
+            // AtomicInc: deps = [dst, idx, active] — a counter, never a shard
+            if (var.op == HJ_OP_ATOMIC_INC || v.var(v.dep(i, 2)).op != HJ_OP_INDEX) s.index_only = false;
+            if (var.op != HJ_OP_SCATTER) { s.read = true; s.identity = false; break; }  // atomics read-modify-write
+            if (v.var(v.dep(i, 2)).op != HJ_OP_INDEX || depth != 0) s.identity = false;
+            break;
+        }
+        default: break;
+        }
+    }
+}
+
 static bool dep_count_ok(uint32_t op, uint32_t n, const char** want) {
     switch (op) {
     case HJ_OP_NOP: *want = "1"; return n == 1;

@@ -2,6 +2,7 @@
 // VarType layout rules (hephaestus-jit/src/vartype.rs:125-189).
 #pragma once
 #include <cstdint>
+#include <climits>
 #include <string>
 #include <vector>
 
@@ -25,6 +26,29 @@ struct IRView {
 // Structural validation (indices in range, dep counts per op, no out-of-scope ops).
 // Returns an empty string when the IR is well formed, else a description of the problem.
 std::string validate_ir(const hj_ir* ir);
+
+// How one kernel touches each of its buffer slots — what decides whether two slots may be bound to
+// the SAME buffer (Graph::launch_with's lifetime aliasing hands a buffer released in pass p to a
+// resource first used in pass p, graph.rs:237-296; hj_kernel_launch rejects every other duplicate).
+struct SlotAccess {
+    bool read = false, written = false;
+    // every access is a plain Gather / Scatter at the bare Index variable, outside loops and ifs
+    bool identity = true;
+    // every access uses the bare Index variable as its index (loops / ifs / conditions allowed): the
+    // slot can hold one contiguous shard of a global array (graph_exec.cpp, sharded execution)
+    bool index_only = true;
+    bool cond_gather = false;            // some Gather carries a condition (inactive lanes read as 0)
+    int64_t last_read = -1;              // position (var index) of the last Gather
+    int64_t first_write = INT64_MAX;     // position of the first Scatter
+};
+// `ir` must have passed validate_ir.
+void analyse_slot_access(const hj_ir* ir, std::vector<SlotAccess>* out);
+// A slot that is only read and a slot that is only written may share one buffer when each thread
+// reads element `Index` of the first before it writes element `Index` of the second and nothing else:
+// no thread ever sees another thread's store.
+inline bool slots_may_share(const SlotAccess& r, const SlotAccess& w) {
+    return r.identity && w.identity && !r.written && !w.read && r.last_read < w.first_write;
+}
 
 // vartype.rs:125-189
 size_t type_size(const IRView& v, uint32_t t);

@@ -10,8 +10,10 @@
 #include <unistd.h>
 
 #include <algorithm>
+#include <condition_variable>
 #include <cstdlib>
 #include <fstream>
+#include <unordered_set>
 
 #include "hj_internal.h"
 #include "ir.h"
@@ -25,13 +27,20 @@ struct hj_kernel {
     uint32_t vec_width = 1, unroll = 1, threads = 256, n_buffers = 0;
     std::vector<uint8_t> slot_flags;        // codegen.cpp: 1 = streamed input, 2 = streamed output
     std::vector<uint32_t> slot_elem_bytes;
+    std::vector<hj::SlotAccess> slot_access;  // which slots may legally be bound to one buffer
 };
 
 namespace hj {
 
+// The per-device pipeline cache.  A miss compiles OUTSIDE the lock: the hash is parked in
+// `in_flight`, other threads asking for the same IR wait on the condition variable, and every
+// other lookup (hits, misses of other IRs) goes on meanwhile — concurrent execute_graph calls
+// (Device is Send + Sync) never queue behind somebody else's ~300 ms NVRTC run.
 struct KernelCache {
     std::mutex mu;
+    std::condition_variable cv;
     std::unordered_map<uint64_t, hj_kernel*> kernels;
+    std::unordered_set<uint64_t> in_flight;
     uint64_t n_compiled = 0, n_hits = 0, n_disk_hits = 0;
 };
 
@@ -161,40 +170,63 @@ hj_status hj_kernel_get(hj_device* dev, const hj_ir* ir, hj_kernel** out) {
         if (!dev->kcache) dev->kcache = new KernelCache();
     }
     KernelCache* kc = dev->kcache;
-    std::lock_guard<std::mutex> g(kc->mu);
-    auto it = kc->kernels.find(h);
-    if (it != kc->kernels.end()) {
-        kc->n_hits++;
-        it->second->rc.fetch_add(1);
-        *out = it->second;
-        return HJ_OK;
+    {
+        std::unique_lock<std::mutex> g(kc->mu);
+        while (true) {
+            auto it = kc->kernels.find(h);
+            if (it != kc->kernels.end()) {
+                kc->n_hits++;
+                it->second->rc.fetch_add(1);
+                *out = it->second;
+                return HJ_OK;
+            }
+            if (!kc->in_flight.count(h)) break;
+            kc->cv.wait(g);  // another thread is compiling this very IR
+        }
+        kc->in_flight.insert(h);
     }
+    // ---- compile and load without the cache lock
     CodegenResult cg;
     std::vector<char> cubin;
     bool disk = false;
-    HJ_TRY(get_cubin(ir, &cg, &cubin, &disk));
-    cudaSetDevice(dev->ordinal);
-    auto k = new hj_kernel();
-    k->hash = h;
-    cudaError_t e = cudaLibraryLoadData(&k->lib, cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0);
-    if (e == cudaSuccess) e = cudaLibraryGetKernel(&k->scalar, k->lib, "hj_kernel_scalar");
-    if (e == cudaSuccess && cg.has_vec_entry) e = cudaLibraryGetKernel(&k->vec, k->lib, "hj_kernel_vec");
-    if (e != cudaSuccess) {
-        cudaGetLastError();
-        if (k->lib) cudaLibraryUnload(k->lib);
-        delete k;
-        return fail(HJ_ERR_CUDA, "loading the compiled kernel failed: %s", cudaGetErrorString(e));
+    hj_kernel* k = nullptr;
+    hj_status st = get_cubin(ir, &cg, &cubin, &disk);
+    if (st == HJ_OK) {
+        cudaSetDevice(dev->ordinal);
+        k = new hj_kernel();
+        k->hash = h;
+        cudaError_t e = cudaLibraryLoadData(&k->lib, cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0);
+        if (e == cudaSuccess) e = cudaLibraryGetKernel(&k->scalar, k->lib, "hj_kernel_scalar");
+        if (e == cudaSuccess && cg.has_vec_entry) e = cudaLibraryGetKernel(&k->vec, k->lib, "hj_kernel_vec");
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            if (k->lib) cudaLibraryUnload(k->lib);
+            delete k;
+            k = nullptr;
+            st = fail(HJ_ERR_CUDA, "loading the compiled kernel failed: %s", cudaGetErrorString(e));
+        }
     }
-    k->vec_width = cg.vec;
-    k->unroll = cg.unroll;
-    k->threads = cg.threads;
-    k->n_buffers = ir->n_buffers;
-    k->slot_flags = cg.slot_flags;
-    k->slot_elem_bytes = cg.slot_elem_bytes;
-    if (disk) kc->n_disk_hits++;
-    else kc->n_compiled++;
-    k->rc.store(2);  // cache + caller
-    kc->kernels[h] = k;
+    if (k) {
+        k->vec_width = cg.vec;
+        k->unroll = cg.unroll;
+        k->threads = cg.threads;
+        k->n_buffers = ir->n_buffers;
+        k->slot_flags = cg.slot_flags;
+        k->slot_elem_bytes = cg.slot_elem_bytes;
+        analyse_slot_access(ir, &k->slot_access);
+        k->rc.store(2);  // cache + caller
+    }
+    {
+        std::lock_guard<std::mutex> g(kc->mu);
+        kc->in_flight.erase(h);
+        if (k) {
+            if (disk) kc->n_disk_hits++;
+            else kc->n_compiled++;
+            kc->kernels[h] = k;
+        }
+    }
+    kc->cv.notify_all();  // waiters of a failed compile retry it themselves and report their own error
+    if (st != HJ_OK) return st;
     *out = k;
     return HJ_OK;
 }
@@ -228,6 +260,21 @@ hj_status hj_kernel_launch(hj_device* dev, hj_kernel* k, size_t size, hj_buffer*
         ptrs[i] = buffers[i]->ptr;
         if ((uintptr_t)ptrs[i] & 15u) aligned = false;
     }
+    // One buffer under two slots: every slot is declared __restrict__ and read-only slots are loaded
+    // through the non-coherent path, so a duplicate is only legal when no thread can observe another
+    // thread's store — both read-only, or an Index-addressed input whose element is read before the
+    // same element of an Index-addressed output is written (the in-place reuse Graph::launch_with's
+    // lifetime aliasing produces, graph.rs:237-296).
+    for (uint32_t i = 0; i < n_buffers; i++)
+        for (uint32_t j = i + 1; j < n_buffers; j++) {
+            const char *a0 = (const char*)ptrs[i], *b0 = (const char*)ptrs[j];
+            if (a0 + buffers[i]->bytes <= b0 || b0 + buffers[j]->bytes <= a0) continue;
+            const SlotAccess &a = k->slot_access[i], &b = k->slot_access[j];
+            if (!a.written && !b.written) continue;
+            HJ_REQUIRE(slots_may_share(a, b) || slots_may_share(b, a),
+                       "buffer slots %u and %u overlap in memory and the kernel does not access both through the bare Index "
+                       "(read before write): the result would depend on thread order", i, j);
+        }
     const uint32_t* size_ptr = size_buf ? (const uint32_t*)size_buf->ptr : nullptr;
     uint32_t size_static = (uint32_t)size;
     std::vector<void*> args;

@@ -123,7 +123,8 @@ struct RingCtl {
 //                                              phase 2: write the outputs of the slice that starts
 //                                              `byte_off` bytes into the input (slice is only valid
 //                                              without EARLY release)
-//   static void finish(total, args)           called once by the CTA that owns the last tile
+//   static void finish(total, args, lane)     called once, by the prefix warp (all 32 lanes) of the CTA
+//                                              that owns the last tile; `total` includes the seed
 // TILE bytes per stage, STAGES data stages, TSLOTS tile slots, CWARPS consumer warps; phase 1 runs
 // AHEAD tiles ahead of phase 2.
 // TRACE (development aid, tools/ring_timeline.py): globaltimer stamps per tile in `trace` (10 words per tile).
@@ -289,10 +290,12 @@ __device__ __forceinline__ void ring_pipeline(const char* __restrict__ src, size
             if (!EARLY) mbar_wait(&ctl->pub[q], par);
             if (lane == 0) {
                 ctl->tpre[q] = exclusive;
-                if (t == n_tiles - 1) Op::finish((P)(exclusive + ctl->tagg[q]), args);
                 stamp(t, 5);
                 mbar_arrive(&ctl->pref[q]);
             }
+            // the whole warp: a sharded launch runs its cross-GPU exchange here (one lane per peer),
+            // after the last tile's consumers have been released
+            if (t == n_tiles - 1) Op::finish((P)(exclusive + ctl->tagg[q]), args, lane);
             if (++q == TSLOTS) { q = 0; par ^= 1; }
         }
     } else {

@@ -1,33 +1,33 @@
-// scan.cu — single-launch inclusive/exclusive prefix sum for sm_100a:
-// decoupled look-back between 64 KiB super-tiles, two sweeps per super-tile through L2.
+// scan.cu — single-launch inclusive/exclusive prefix sum for sm_100a.
 //
 // Replaces builtin::prefix_sum::prefix_sum_large
 // (hephaestus-jit/src/backend/vulkan/builtin/prefix_sum.rs:31-162 +
 // kernels/prefix_sum_large.glsl + prefix_sum_large_init.glsl).
 //
-// Why not the textbook register-resident single sweep (which the reference uses with
-// 2048-item partitions)?  Measured on B200 (profiles/r01_scan_design.md): with ~600 tiles
-// resident, a tile waits ~7 us for its predecessors' aggregates (three dependent L2 round
-// trips at loaded-fabric latency) while holding its 32 KiB of data in registers; resident
-// bytes / lifetime then caps the kernel at 48 % of the HBM roofline no matter the tile size
-// or the look-back window.  Here the wait holds almost nothing:
-//   sweep 1  each warp streams its contiguous 8 KiB segment of the super-tile (16 coalesced
-//            512-byte rows, all loads in flight, L2 evict_last) and only SUMS it;
-//            warp totals -> block aggregate -> publish -> look-back (lookback.cuh);
-//   sweep 2  each warp re-reads its rows — they are still in the 126 MB L2 (resident
-//            super-tiles total < 64 MB) — scans each row with shuffles and a running carry,
-//            adds the tile prefix and streams the result out (evict_first).
-// DRAM traffic stays at the algorithmic 2 * sizeof(T) bytes per element; the second read is
-// L2 traffic.  Other differences from the reference: no separate init dispatch (epoch-tagged
-// status words), tail masked in the kernel (D7), true exclusive and inclusive variants (D10),
-// correct carries for f32/u64/f64 (D3), and `seed`: a device-resident offset added to every
-// output (the cross-GPU carry of the sharded scan) at no extra pass.
+// Two kernels live here:
+//   * scan_ring_kernel — THE DEFAULT for 16-byte aligned buffers of >= 64 KiB: the persistent
+//     warp-specialised ring of ring.cuh (one CTA per SM, tiles by atomic ticket, a TMA bulk copy per
+//     32 KiB tile into a 6-stage shared-memory ring, phase 1 = reduce tile i+3, phase 2 = scan tile i
+//     from shared memory, round-based prefixes — nobody spins on the critical path).  DRAM traffic
+//     is the algorithmic 2 * sizeof(T) bytes per element; 6.9 TB/s at 2^30 u32.
+//     On a sharded launch its `finish` also runs the cross-GPU exchange of the shard totals over
+//     peer memory and leaves this rank's exclusive offset in `seed_out` (the DEFERRED seed, comm.cu).
+//   * scan_kernel — the fallback for small or misaligned inputs: decoupled look-back between 64 KiB
+//     super-tiles, two sweeps per super-tile through L2 (sweep 1 sums each warp's 8 KiB segment,
+//     look-back resolves the tile prefix, sweep 2 re-reads the rows from L2, scans and stores).
+//     The textbook register-resident single sweep (the reference's design, 2048-item partitions)
+//     stalls at 48 % of the HBM roofline on B200 and this two-sweep variant at 70 %
+//     (profiles/r01_ncu_full_summary.txt) — which is why the ring replaced it as the default.
+// Differences from the reference in both: no separate init dispatch (epoch-tagged status words),
+// tail masked in the kernel (D7), true exclusive and inclusive variants (D10), correct carries for
+// f32/u64/f64 (D3), and `seed`: a device-resident offset added to every output at no extra pass.
 #include <algorithm>
 #include <cstdlib>
 #include <type_traits>
 
 #include "hj_internal.h"
 #include "lookback.cuh"
+#include "peer.cuh"
 #include "ring.cuh"
 
 namespace hj {
@@ -219,6 +219,11 @@ struct ScanOp {
     static constexpr int ROWS = SLICE / 512;
     struct Args {
         T* dst;
+        // sharded scan with a DEFERRED seed (comm.cu): xepoch != 0 makes the CTA that owns the last
+        // tile publish the shard total to every peer and write this rank's exclusive offset
+        T* seed_out;
+        PeerView pv;
+        uint32_t xepoch;
     };
     // phase 1: total of this warp's slice (the stage tail of a ragged tile is zero-filled)
     static __device__ __forceinline__ P total(const char* slice, char*, int, int, int lane) {
@@ -266,22 +271,36 @@ struct ScanOp {
             }
         }
     }
-    static __device__ __forceinline__ void finish(P, const Args&) {}
+    // Sharded scan, one kernel: the shard total (the last tile's inclusive prefix) goes to every
+    // peer's mailbox over NVLink, the totals of the ranks before this one are summed in rank order
+    // and left in seed_out[0] — the offset every consumer of `dst` adds.
+    static __device__ __forceinline__ void finish(P total, const Args& a, int lane) {
+        if (a.xepoch == 0) return;
+        unsigned long long bits = 0;
+        memcpy(&bits, &total, sizeof(P));
+        const unsigned long long got = peer_allgather_warp(a.pv, a.xepoch, bits, lane);
+        P mine;
+        memcpy(&mine, &got, sizeof(P));
+        P before = (P)0;
+        for (int q = 0; q < a.pv.rank; q++) before = (P)(before + shfl_idx(mine, q));
+        if (lane == 0) a.seed_out[0] = (T)before;
+    }
 };
 
 template <typename T, typename P, bool INCLUSIVE, int TILE, int STAGES, int CWARPS, int AHEAD>
 __global__ void __launch_bounds__((CWARPS + 3) * 32, 1)
 scan_ring_kernel(const T* __restrict__ src, T* __restrict__ dst, size_t n, const T* __restrict__ seed,
-                 LookbackView lb, uint32_t n_tiles, uint32_t G) {
+                 LookbackView lb, uint32_t n_tiles, uint32_t G, T* __restrict__ seed_out, PeerView pv, uint32_t xepoch) {
     extern __shared__ __align__(128) char smem[];
     using Op = ScanOp<T, P, INCLUSIVE, TILE / CWARPS>;
-    typename Op::Args args{dst};
+    typename Op::Args args{dst, seed_out, pv, xepoch};
     ring_pipeline<Op, TILE, STAGES, CWARPS, AHEAD, STAGES, false, 10>(reinterpret_cast<const char*>(src), n * sizeof(T), n_tiles,
                                                    seed ? (P)seed[0] : (P)0, lb, G, args, smem);
 }
 
 template <typename T, typename P, int TILE, int STAGES, int CWARPS, int AHEAD>
-hj_status run_ring(hj_device* dev, size_t n, bool inclusive, const void* src, void* dst, const void* seed) {
+hj_status run_ring(hj_device* dev, size_t n, bool inclusive, const void* src, void* dst, const void* seed,
+                   void* seed_out, const PeerView* peers, uint32_t xepoch) {
     const size_t n_tiles = (n * sizeof(T) + TILE - 1) / TILE;
     HJ_REQUIRE(n_tiles < (1ull << 31), "prefix_sum: too many tiles");
     HJ_TRY(ensure_lookback_scratch(dev, n_tiles));
@@ -293,7 +312,8 @@ hj_status run_ring(hj_device* dev, size_t n, bool inclusive, const void* src, vo
     auto launch = [&](auto kernel) -> hj_status {
         HJ_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         kernel<<<grid, (CWARPS + 3) * 32, smem, dev->stream>>>((const T*)src, (T*)dst, n, (const T*)seed, lb,
-                                                              (uint32_t)n_tiles, G);
+                                                              (uint32_t)n_tiles, G, (T*)seed_out,
+                                                              peers ? *peers : PeerView(), peers ? xepoch : 0u);
         return check_launch(dev, "scan_ring_kernel");
     };
     return inclusive ? launch(scan_ring_kernel<T, P, true, TILE, STAGES, CWARPS, AHEAD>)
@@ -301,7 +321,8 @@ hj_status run_ring(hj_device* dev, size_t n, bool inclusive, const void* src, vo
 }
 
 template <typename T, typename P>
-hj_status run(hj_device* dev, size_t n, bool inclusive, const void* src, void* dst, const void* seed) {
+hj_status run(hj_device* dev, size_t n, bool inclusive, const void* src, void* dst, const void* seed,
+              void* seed_out = nullptr, const PeerView* peers = nullptr, uint32_t xepoch = 0) {
     // 16-byte aligned buffers (every buffer this library allocates) take the ring pipeline;
     // anything else, and tiny inputs, the look-back kernel below.
     const bool aligned = (((uintptr_t)src | (uintptr_t)dst) & 15u) == 0;
@@ -310,9 +331,10 @@ hj_status run(hj_device* dev, size_t n, bool inclusive, const void* src, void* d
         // measured on B200 (profiles/r01_scan_ring_sweep.txt): 32 KiB x 6 stages, phase 1 three
         // tiles ahead for <= 4-byte prefixes; 8-byte prefixes (twice the shuffle work per byte,
         // two status words per tile) do better with fewer, larger tiles
-        if (sizeof(P) == 8) return run_ring<T, P, 49152, 4, 16, 2>(dev, n, inclusive, src, dst, seed);
-        return run_ring<T, P, 32768, 6, 16, 3>(dev, n, inclusive, src, dst, seed);
+        if (sizeof(P) == 8) return run_ring<T, P, 49152, 4, 16, 2>(dev, n, inclusive, src, dst, seed, seed_out, peers, xepoch);
+        return run_ring<T, P, 32768, 6, 16, 3>(dev, n, inclusive, src, dst, seed, seed_out, peers, xepoch);
     }
+    if (peers) return fail(HJ_ERR_UNSUPPORTED, "prefix_sum: the fused exchange needs the ring kernel");
     constexpr int VEC = 16 / sizeof(T);
     constexpr size_t TILE = (size_t)SCAN_WARPS * SCAN_ROWS * 32 * VEC;
     size_t n_tiles = (n + TILE - 1) / TILE;
@@ -332,16 +354,22 @@ hj_status run(hj_device* dev, size_t n, bool inclusive, const void* src, void* d
 
 }  // namespace
 
+bool prefix_sum_can_fuse_exchange(hj_type_kind ty, size_t n, const void* src, const void* dst) {
+    const size_t es = type_size(ty);
+    static const int cfg = getenv("HJ_SCAN_CFG") ? atoi(getenv("HJ_SCAN_CFG")) : 1;
+    return (((uintptr_t)src | (uintptr_t)dst) & 15u) == 0 && cfg != 0 && n * es >= (64u << 10);
+}
+
 hj_status launch_prefix_sum(hj_device* dev, hj_type_kind ty, size_t n, bool inclusive, const void* src,
-                            void* dst, const void* seed) {
+                            void* dst, const void* seed, void* seed_out, const PeerView* peers, uint32_t xepoch) {
     // Integer sums wrap, so signed types run on the unsigned kernel of the same width.
     switch (ty) {
-    case HJ_I8: case HJ_U8: return run<uint8_t, uint32_t>(dev, n, inclusive, src, dst, seed);
-    case HJ_I16: case HJ_U16: return run<uint16_t, uint32_t>(dev, n, inclusive, src, dst, seed);
-    case HJ_I32: case HJ_U32: return run<uint32_t, uint32_t>(dev, n, inclusive, src, dst, seed);
-    case HJ_I64: case HJ_U64: return run<uint64_t, uint64_t>(dev, n, inclusive, src, dst, seed);
-    case HJ_F32: return run<float, float>(dev, n, inclusive, src, dst, seed);
-    case HJ_F64: return run<double, double>(dev, n, inclusive, src, dst, seed);
+    case HJ_I8: case HJ_U8: return run<uint8_t, uint32_t>(dev, n, inclusive, src, dst, seed, seed_out, peers, xepoch);
+    case HJ_I16: case HJ_U16: return run<uint16_t, uint32_t>(dev, n, inclusive, src, dst, seed, seed_out, peers, xepoch);
+    case HJ_I32: case HJ_U32: return run<uint32_t, uint32_t>(dev, n, inclusive, src, dst, seed, seed_out, peers, xepoch);
+    case HJ_I64: case HJ_U64: return run<uint64_t, uint64_t>(dev, n, inclusive, src, dst, seed, seed_out, peers, xepoch);
+    case HJ_F32: return run<float, float>(dev, n, inclusive, src, dst, seed, seed_out, peers, xepoch);
+    case HJ_F64: return run<double, double>(dev, n, inclusive, src, dst, seed, seed_out, peers, xepoch);
     default:
         return fail(HJ_ERR_UNSUPPORTED, "prefix_sum: unsupported element type %s", type_name(ty));
     }

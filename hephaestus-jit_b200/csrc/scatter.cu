@@ -19,6 +19,7 @@
 
 #include "common.cuh"
 #include "hj_internal.h"
+#include "peer.cuh"
 #include "ring.cuh"
 
 namespace hj {
@@ -172,6 +173,9 @@ hist_ring_kernel(const uint32_t* __restrict__ keys, size_t n, uint32_t literal, 
             mbar_init(&ctl->full[s], 1);
             mbar_init(&ctl->empty[s], HR_WARPS);
         }
+        // programmatic dependent launch: the fold kernel may be set up while this one runs (it waits
+        // for this grid's completion and memory flush before it reads the private histograms)
+        pdl_launch_dependents();
     }
     __syncthreads();
 
@@ -323,6 +327,49 @@ hist_fold_kernel(const uint32_t* __restrict__ scratch, uint32_t n_groups, uint32
     }
 }
 
+// PACKED16 fold AND, on a sharded launch, the cross-GPU all-reduce of the bins in ONE kernel
+// (launched with programmatic stream serialization behind hist_ring_kernel).  A CTA owns 64 packed
+// words (128 bins) and splits the group list over 4 slices of 64 threads; slice 0 then holds the
+// rank's final counts, adds what dst held, pushes each pair of bins as one self-validating uint4
+// (bin, epoch, bin, epoch) into every peer's inbox over NVLink, polls its own inbox for the peers'
+// pairs and stores the sum over all ranks (peer.cuh: array_pair_allreduce_add) — fold kernel,
+// 8 x 65536 global atomics and the separate exchange kernel of round 1 become one launch.
+constexpr int HFX_WORDS = 64, HFX_SLICES = 4;
+__global__ void __launch_bounds__(HFX_WORDS * HFX_SLICES)
+hist_fold_exchange_kernel(const uint32_t* __restrict__ scratch, uint32_t n_groups, uint32_t* __restrict__ dst, uint32_t n_dst,
+                          ArrayPeerView ax) {
+    __shared__ uint32_t s_even[HFX_SLICES][HFX_WORDS], s_odd[HFX_SLICES][HFX_WORDS];
+    const uint32_t wl = threadIdx.x % HFX_WORDS, slice = threadIdx.x / HFX_WORDS;
+    const uint32_t w = blockIdx.x * HFX_WORDS + wl;
+    const uint32_t n_words = (n_dst + 1) / 2;
+    pdl_wait();  // the private histograms of hist_ring_kernel are complete and visible from here on
+    uint32_t even = 0, odd = 0;
+    if (w < n_words) {
+        const uint32_t per = (n_groups + HFX_SLICES - 1) / HFX_SLICES;
+        const uint32_t g0 = slice * per, g1 = min(n_groups, g0 + per);
+#pragma unroll 8
+        for (uint32_t g = g0; g < g1; g++) {
+            const uint32_t word = __ldg(scratch + (size_t)g * n_words + w);
+            even += word & 0xffffu;
+            odd += word >> 16;
+        }
+    }
+    s_even[slice][wl] = even;
+    s_odd[slice][wl] = odd;
+    __syncthreads();
+    if (slice != 0 || w >= n_words) return;
+#pragma unroll
+    for (int k = 1; k < HFX_SLICES; k++) {
+        even += s_even[k][wl];
+        odd += s_odd[k][wl];
+    }
+    const bool has_odd = 2 * w + 1 < n_dst;
+    uint32_t a = dst[2 * w] + even, b = has_odd ? dst[2 * w + 1] + odd : 0u;
+    if (ax.world > 1) array_pair_allreduce_add(ax, w, a, b, &a, &b);
+    dst[2 * w] = a;
+    if (has_odd) dst[2 * w + 1] = b;
+}
+
 template <typename T>
 __global__ void __launch_bounds__(256)
 gather_kernel(const T* __restrict__ src, const uint32_t* __restrict__ idx, T* __restrict__ dst, size_t n) {
@@ -397,7 +444,8 @@ hj_status run_sr_int(hj_device* dev, hj_reduce_op op, size_t n, const uint32_t* 
 
 hj_status launch_scatter_reduce(hj_device* dev, hj_reduce_op op, hj_type_kind ty, size_t n,
                                 const uint32_t* idx, const void* src, uint64_t literal, void* dst,
-                                size_t n_dst) {
+                                size_t n_dst, const ArrayPeerView* ax, bool* exchanged) {
+    if (exchanged) *exchanged = false;
     if (n == 0) return HJ_OK;
     hj_status s = HJ_ERR_UNSUPPORTED;
     if (op == HJ_REDUCE_PROD)  // todo!() in the reference (glsl/mod.rs:422)
@@ -420,6 +468,27 @@ hj_status launch_scatter_reduce(hj_device* dev, hj_reduce_op op, hj_type_kind ty
                 kern<<<n_groups, (HR_WARPS + 1) * 32, smem, dev->stream>>>(
                     idx, n, 1u, dev->hist_scratch, (uint32_t*)dst, (uint32_t)n_dst, (uint32_t)n_dst, 1u, 0u);
                 HJ_TRY(check_launch(dev, "hist_ring_kernel"));
+                static const bool old_fold = getenv("HJ_HIST_OLD_FOLD") != nullptr;
+                if (!old_fold && ((uintptr_t)dst & 7u) == 0) {
+                    // fold (+ cross-GPU exchange when `ax` is given) in one kernel behind a programmatic
+                    // dependency: its launch overlaps the tail of the ring kernel
+                    const bool with_peers = ax && ax->world > 1 && n_words <= ax->slot_vecs;
+                    ArrayPeerView view = with_peers ? *ax : ArrayPeerView();
+                    if (!with_peers) { view.world = 1; view.rank = 0; }
+                    cudaLaunchConfig_t cfg = {};
+                    cfg.gridDim = dim3((n_words + HFX_WORDS - 1) / HFX_WORDS);
+                    cfg.blockDim = dim3(HFX_WORDS * HFX_SLICES);
+                    cfg.stream = dev->stream;
+                    cudaLaunchAttribute attr[1];
+                    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+                    attr[0].val.programmaticStreamSerializationAllowed = 1;
+                    cfg.attrs = attr;
+                    cfg.numAttrs = 1;
+                    HJ_CUDA(cudaLaunchKernelEx(&cfg, hist_fold_exchange_kernel, (const uint32_t*)dev->hist_scratch, n_groups,
+                                               (uint32_t*)dst, (uint32_t)n_dst, view));
+                    if (exchanged) *exchanged = with_peers;
+                    return check_launch(dev, "hist_fold_exchange_kernel");
+                }
                 hist_fold_kernel<true><<<dim3((n_words + 255) / 256, HF_SLICES), 256, 0, dev->stream>>>(
                     (const uint32_t*)dev->hist_scratch, n_groups, (uint32_t*)dst, (uint32_t)n_dst);
                 return check_launch(dev, "hist_fold_kernel");

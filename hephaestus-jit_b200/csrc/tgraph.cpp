@@ -366,14 +366,72 @@ uint32_t scalar_kind(TypeId t) {
 
 // Graph::launch_with (graph.rs:192-400)
 void launch_graph(const Graph& g, hj_device* dev, const std::vector<VarId>& inputs, std::vector<VarId>* outputs,
-                  LaunchReport* report, hj_report* backend_report) {
+                  LaunchReport* report, hj_report* backend_report, hj_comm* comm) {
     const size_t nres = g.resources.size();
     std::vector<hj_buffer*> res(nres, nullptr);  // each non-null entry owns one reference
+    std::vector<hj_shard_desc> shards(nres);     // sharded launches: placement / deferred seed per resource
+    for (hj_shard_desc& sd : shards) {
+        sd.placement = HJ_RES_AUTO;
+        sd.deferred = 0;
+        sd.seed = nullptr;  // owns one reference when set
+    }
     auto release_all = [&]() {
         for (hj_buffer* b : res)
             if (b) hj_buffer_release(b);
+        for (hj_shard_desc& sd : shards)
+            if (sd.seed) hj_buffer_release(sd.seed);
     };
     try {
+        // what Graph::launch_with hands to BackendDevice::execute_graph (graph.rs:315-323): built first,
+        // a sharded launch plans the placement of every resource from it before buffers are created
+        std::vector<hj_pass> passes(g.passes.size());
+        std::vector<hj_ir> irs(g.passes.size());
+        for (size_t p = 0; p < g.passes.size(); p++) {
+            const Pass& src = g.passes[p];
+            hj_pass& dst = passes[p];
+            memset(&dst, 0, sizeof(dst));
+            dst.resources = src.resources.data();
+            dst.n_resources = (uint32_t)src.resources.size();
+            dst.size_buffer = src.size_buffer;
+            if (src.is_kernel) {
+                irs[p] = src.ir.view();
+                dst.kind = HJ_PASS_KERNEL;
+                dst.ir = &irs[p];
+                dst.size = src.size;
+            } else {
+                switch (src.device_op.code) {
+                case DOP_REDUCE: dst.kind = HJ_PASS_REDUCE; break;
+                case DOP_PREFIX_SUM: dst.kind = HJ_PASS_PREFIX_SUM; break;
+                default: dst.kind = HJ_PASS_COMPRESS; break;
+                }
+                dst.arg = src.device_op.arg;
+            }
+        }
+        std::vector<hj_buffer_desc> descs(nres);
+        for (size_t i = 0; i < nres; i++) {
+            descs[i].size = g.resource_descs[i].size;
+            descs[i].ty = scalar_kind(g.resource_descs[i].ty);
+            descs[i].elem_bytes = (uint32_t)type_size(g.resource_descs[i].ty);
+        }
+        auto bind_var = [&](size_t rid, const Var& var) {  // trace lock held
+            hj_buffer_retain(var.data.buf);
+            if (res[rid]) hj_buffer_release(res[rid]);
+            res[rid] = var.data.buf;
+            if (shards[rid].seed) hj_buffer_release(shards[rid].seed);
+            shards[rid].seed = nullptr;
+            if (var.data.comm) {
+                if (comm && comm != var.data.comm) throw TraceError("variables sharded over different communicators in one launch");
+                comm = var.data.comm;
+                shards[rid].placement = HJ_RES_SHARDED;
+                shards[rid].deferred = var.data.deferred ? 1 : 0;
+                if (var.data.seed) {
+                    hj_buffer_retain(var.data.seed);
+                    shards[rid].seed = var.data.seed;
+                }
+            } else {
+                shards[rid].placement = HJ_RES_REPLICATED;
+            }
+        };
         {
             std::lock_guard<std::mutex> lock(g_trace_mu);
             // inputs by position (graph.rs:205-219)
@@ -385,28 +443,65 @@ void launch_graph(const Graph& g, hj_device* dev, const std::vector<VarId>& inpu
                 have.ty = var.ty;
                 if (!(have == d) || var.data.kind != Resource::Buffer)
                     throw TraceError("Resource does not match variable type! (graph::Error::ResourceMissmatch)");
-                hj_buffer_retain(var.data.buf);
-                if (res[g.inputs[i]]) hj_buffer_release(res[g.inputs[i]]);
-                res[g.inputs[i]] = var.data.buf;
+                bind_var(g.inputs[i], var);
             }
-            // captured and live internal resources (graph.rs:220-235)
+            // captured resources (graph.rs:220-228)
             for (size_t i = 0; i < nres; i++) {
                 if (res[i]) continue;
                 const GraphResource& gr = g.resources[i];
                 if (gr.kind == GraphResource::Captured) {
                     const Var& var = g_trace.var(gr.id);
-                    if (var.data.kind == Resource::Buffer) {
-                        hj_buffer_retain(var.data.buf);
-                        res[i] = var.data.buf;
-                    }
-                } else if (gr.kind == GraphResource::Internal && g_trace.get(gr.id)) {
-                    res[i] = create_buffer(dev, g.resource_descs[i]);
+                    if (var.data.kind == Resource::Buffer) bind_var(i, var);
                 }
             }
         }
+        // ---- sharded launch: where does every resource live, and how large is this rank's part
+        int32_t rank = 0, world = 1;
+        if (comm) {
+            if (hj_comm_info(comm, &rank, &world, nullptr, nullptr) != HJ_OK)
+                throw TraceError(std::string("hj_comm_info failed: ") + hj_last_error());
+            if (hj_shard_plan(passes.data(), (uint32_t)passes.size(), descs.data(), (uint32_t)nres, shards.data()) != HJ_OK)
+                throw TraceError(std::string("hj_shard_plan failed: ") + hj_last_error());
+            // a sharded integer scan result keeps its cross-GPU offset beside it (8 instead of 12 bytes
+            // per element; the consumers add it): give every such destination a seed slot
+            for (const hj_pass& p : passes)
+                if (p.kind == HJ_PASS_PREFIX_SUM && p.n_resources >= 2) {
+                    const uint32_t rid = p.resources[0];
+                    const uint32_t k = descs[rid].ty;
+                    if (shards[rid].placement == HJ_RES_SHARDED && !shards[rid].seed && k >= HJ_I8 && k <= HJ_U64) {
+                        hj_buffer* seed = nullptr;
+                        if (hj_buffer_create(dev, 16, &seed) != HJ_OK)
+                            throw TraceError(std::string("create_buffer failed: ") + hj_last_error());
+                        shards[rid].seed = seed;
+                    }
+                }
+        }
+        auto local_desc = [&](size_t rid, BufferDesc d) {  // what this rank allocates for the resource
+            if (comm && shards[rid].placement == HJ_RES_SHARDED) {
+                uint64_t s0 = 0, s1 = 0;
+                hj_shard_bounds(d.size, world, rank, &s0, &s1);
+                d.size = (size_t)(s1 - s0);
+            }
+            return d;
+        };
+        {
+            std::lock_guard<std::mutex> lock(g_trace_mu);
+            // live internal resources (graph.rs:229-235)
+            for (size_t i = 0; i < nres; i++) {
+                if (res[i]) continue;
+                const GraphResource& gr = g.resources[i];
+                if (gr.kind == GraphResource::Internal && g_trace.get(gr.id))
+                    res[i] = create_buffer(dev, local_desc(i, g.resource_descs[i]));
+            }
+        }
         // lifetime-based aliasing of dead internal resources (graph.rs:237-296).  The reference
-        // hands a buffer released by one resource of a pass to a later resource of the SAME
-        // pass (its own test expects a hit rate of 2/3, test.rs:1638-1670); kept as is.
+        // re-inserts a buffer into its cache the moment the last pass using it comes up, so a later
+        // resource of the SAME pass can pop it (its own test expects a hit rate of 2/3,
+        // test.rs:1638-1670).  That is only sound when no thread of the pass can observe another
+        // thread's store: here a buffer released in pass p is handed to a resource born in pass p
+        // only if p is a kernel that reads the one and writes the other at the bare Index (read
+        // before write, ir.h: slots_may_share) — x = x + 1 in place.  Every other release (gathers
+        // through computed indices, device ops) becomes available from pass p + 1 on.
         auto t0 = std::chrono::steady_clock::now();
         std::vector<std::pair<size_t, size_t>> life(nres, {g.passes.size(), 0});
         for (size_t p = 0; p < g.passes.size(); p++)
@@ -422,21 +517,42 @@ void launch_graph(const Graph& g, hj_device* dev, const std::vector<VarId>& inpu
         }
         std::vector<bool> is_output(nres, false);
         for (uint32_t rid : g.outputs) is_output[rid] = true;
-        std::map<std::pair<size_t, TypeId>, std::vector<hj_buffer*>> cache;  // key: pow2-rounded desc
+        using Key = std::tuple<size_t, TypeId, uint32_t>;  // pow2-rounded desc + placement (a shard is smaller than a replica)
+        std::map<Key, std::vector<hj_buffer*>> cache;
+        struct Released { Key key; hj_buffer* buf; size_t slot; };
+        std::vector<SlotAccess> access;
         for (size_t p = 0; p < g.passes.size(); p++) {
-            for (uint32_t rid : g.passes[p].resources) {
+            const Pass& pass = g.passes[p];
+            std::vector<Released> released;  // by this pass; each entry owns a reference
+            access.clear();
+            for (size_t k = 0; k < pass.resources.size(); k++) {
+                const uint32_t rid = pass.resources[k];
                 if (!internal[rid]) continue;
                 BufferDesc rounded = g.resource_descs[rid];
                 rounded.size = round_pow2(rounded.size);
-                auto key = std::make_pair(rounded.size, rounded.ty);
+                const Key key = std::make_tuple(rounded.size, rounded.ty, comm ? shards[rid].placement : 0u);
                 if (life[rid].first == p && !res[rid]) {
+                    // in-place reuse of a buffer this very pass has just released
+                    if (pass.is_kernel && !released.empty()) {
+                        if (access.empty()) {
+                            hj_ir view = pass.ir.view();
+                            analyse_slot_access(&view, &access);
+                        }
+                        for (size_t q = 0; q < released.size() && !res[rid]; q++)
+                            if (released[q].key == key && k < access.size() && released[q].slot < access.size() &&
+                                slots_may_share(access[released[q].slot], access[k])) {
+                                res[rid] = released[q].buf;
+                                released.erase(released.begin() + (long)q);
+                            }
+                    }
                     auto& bucket = cache[key];
-                    if (!bucket.empty()) {
+                    if (res[rid]) {
+                    } else if (!bucket.empty()) {
                         res[rid] = bucket.back();
                         bucket.pop_back();
                     } else {
                         misses++;
-                        res[rid] = create_buffer(dev, rounded);
+                        res[rid] = create_buffer(dev, local_desc(rid, rounded));
                     }
                 }
                 // (graph.rs:283-290 re-inserts every dead internal buffer; an OUTPUT of a recorded
@@ -445,9 +561,10 @@ void launch_graph(const Graph& g, hj_device* dev, const std::vector<VarId>& inpu
                 // of the cache here)
                 if (life[rid].second == p && res[rid] && !is_output[rid]) {
                     hj_buffer_retain(res[rid]);
-                    cache[key].push_back(res[rid]);
+                    released.push_back({key, res[rid], k});
                 }
             }
+            for (Released& r : released) cache[r.key].push_back(r.buf);
         }
         for (auto& kv : cache)
             for (hj_buffer* b : kv.second) hj_buffer_release(b);
@@ -463,40 +580,15 @@ void launch_graph(const Graph& g, hj_device* dev, const std::vector<VarId>& inpu
 
         // ---- the backend boundary: BackendDevice::execute_graph (graph.rs:315-323)
         if (!g.passes.empty()) {
-            std::vector<hj_pass> passes(g.passes.size());
-            std::vector<hj_ir> irs(g.passes.size());
-            for (size_t p = 0; p < g.passes.size(); p++) {
-                const Pass& src = g.passes[p];
-                hj_pass& dst = passes[p];
-                memset(&dst, 0, sizeof(dst));
-                dst.resources = src.resources.data();
-                dst.n_resources = (uint32_t)src.resources.size();
-                dst.size_buffer = src.size_buffer;
-                if (src.is_kernel) {
-                    irs[p] = src.ir.view();
-                    dst.kind = HJ_PASS_KERNEL;
-                    dst.ir = &irs[p];
-                    dst.size = src.size;
-                } else {
-                    switch (src.device_op.code) {
-                    case DOP_REDUCE: dst.kind = HJ_PASS_REDUCE; break;
-                    case DOP_PREFIX_SUM: dst.kind = HJ_PASS_PREFIX_SUM; break;
-                    default: dst.kind = HJ_PASS_COMPRESS; break;
-                    }
-                    dst.arg = src.device_op.arg;
-                }
-            }
-            std::vector<hj_buffer_desc> descs(nres);
-            for (size_t i = 0; i < nres; i++) {
-                descs[i].size = g.resource_descs[i].size;
-                descs[i].ty = scalar_kind(g.resource_descs[i].ty);
-                descs[i].elem_bytes = (uint32_t)type_size(g.resource_descs[i].ty);
-            }
             // Relaunches of a recorded graph with the same buffers replay ONE captured CUDA graph
-            // instead of enqueueing pass by pass; a launch that wants per-pass timings cannot.
+            // instead of enqueueing pass by pass; a launch that wants per-pass timings cannot, nor
+            // can a sharded one (its exchange epochs are launch parameters).
             hj_status s;
             auto b0 = std::chrono::steady_clock::now();
-            if (backend_report) {
+            if (comm) {
+                s = hj_execute_graph_sharded(comm, passes.data(), (uint32_t)passes.size(), res.data(), descs.data(),
+                                             (uint32_t)nres, shards.data(), backend_report);
+            } else if (backend_report) {
                 s = hj_execute_graph(dev, passes.data(), (uint32_t)passes.size(), res.data(), descs.data(),
                                      (uint32_t)nres, backend_report);
             } else {
@@ -511,6 +603,17 @@ void launch_graph(const Graph& g, hj_device* dev, const std::vector<VarId>& inpu
         }
 
         // ---- write results back (graph.rs:332-393)
+        auto resource_of = [&](size_t rid) {
+            Resource r;
+            r.kind = Resource::Buffer;
+            r.buf = res[rid];
+            if (comm && shards[rid].placement == HJ_RES_SHARDED) {
+                r.comm = comm;
+                r.deferred = shards[rid].deferred != 0;
+                r.seed = r.deferred ? shards[rid].seed : nullptr;
+            }
+            return r;
+        };
         std::lock_guard<std::mutex> lock(g_trace_mu);
         if (outputs) {
             outputs->clear();
@@ -519,26 +622,33 @@ void launch_graph(const Graph& g, hj_device* dev, const std::vector<VarId>& inpu
                 v.op.kind = OpKind::Buffer;
                 v.ty = g.resource_descs[rid].ty;
                 v.extent.n = g.resource_descs[rid].size;
-                v.data.kind = Resource::Buffer;
-                v.data.buf = res[rid];
-                if (res[rid]) hj_buffer_retain(res[rid]);
+                set_resource(v, resource_of(rid));
                 outputs->push_back(g_trace.new_var_id(std::move(v)));
             }
         }
         for (size_t i = 0; i < nres; i++) {
             const GraphResource& gr = g.resources[i];
-            if (gr.kind != GraphResource::Internal || !res[i]) continue;
-            if (Var* var = g_trace.get(gr.id)) {
-                BufferDesc have;
-                have.size = var->extent.n;
-                have.ty = var->ty;
-                if (have == g.resource_descs[i]) {
-                    Resource r;
-                    r.kind = Resource::Buffer;
-                    r.buf = res[i];
-                    set_resource(*var, r);
+            if (!res[i]) continue;
+            if (gr.kind == GraphResource::Internal) {
+                if (Var* var = g_trace.get(gr.id)) {
+                    BufferDesc have;
+                    have.size = var->extent.n;
+                    have.ty = var->ty;
+                    if (have == g.resource_descs[i]) set_resource(*var, resource_of(i));
                 }
+            } else if (comm && shards[i].placement == HJ_RES_SHARDED && gr.kind == GraphResource::Captured) {
+                // a captured deferred scan result a device op of this launch had to materialise
+                if (Var* var = g_trace.get(gr.id))
+                    if (var->data.kind == Resource::Buffer && var->data.buf == res[i] && var->data.deferred && !shards[i].deferred)
+                        set_resource(*var, resource_of(i));
             }
+        }
+        // inputs a pass of this launch materialised in place
+        for (size_t i = 0; comm && i < inputs.size() && i < g.inputs.size(); i++) {
+            const uint32_t rid = g.inputs[i];
+            if (Var* var = g_trace.get(inputs[i]))
+                if (var->data.kind == Resource::Buffer && var->data.buf == res[rid] && var->data.deferred && !shards[rid].deferred)
+                    set_resource(*var, resource_of(rid));
         }
     } catch (...) {
         release_all();

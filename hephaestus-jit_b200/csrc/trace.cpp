@@ -2,6 +2,9 @@
 //
 // Restates hephaestus-jit/src/trace.rs.  Each function cites the lines it follows.  The
 // graph compiler and launcher live in tgraph.cpp.
+#include <type_traits>
+#include <cstring>
+
 #include "trace_internal.h"
 
 #include <algorithm>
@@ -172,6 +175,7 @@ void Trace::dec_rc(VarId first) {  // trace.rs:147-160; a work list instead of t
         work.insert(work.end(), v.deps.begin(), v.deps.end());
         if (v.extent.dynamic) work.push_back(v.extent.size_var);
         if (v.data.kind == Resource::Buffer && v.data.buf) hj_buffer_release(v.data.buf);
+        if (v.data.seed) hj_buffer_release(v.data.seed);
         const uint32_t idx = (uint32_t)id;
         slots[idx].live = false;
         slots[idx].var = Var();
@@ -201,7 +205,9 @@ Op resulting_op(const Op& op) {  // op.rs:167-177, DeviceOp::resulting_op op.rs:
 
 void set_resource(Var& v, const Resource& r) {
     if (r.kind == Resource::Buffer && r.buf) hj_buffer_retain(r.buf);
+    if (r.seed) hj_buffer_retain(r.seed);
     if (v.data.kind == Resource::Buffer && v.data.buf) hj_buffer_release(v.data.buf);
+    if (v.data.seed) hj_buffer_release(v.data.seed);
     v.data = r;
 }
 
@@ -354,6 +360,98 @@ VarId from_buffer(hj_buffer* buf, TypeId ty, size_t n) {
     v.data.kind = Resource::Buffer;
     v.data.buf = buf;
     return new_var(std::move(v), {});
+}
+
+// ---- sharded arrays (no reference counterpart: SURVEY 8e) ------------------------------------------
+namespace {
+void local_block(hj_comm* comm, size_t n_global, uint64_t* start, uint64_t* count) {
+    int32_t rank = 0, world = 1;
+    if (hj_comm_info(comm, &rank, &world, nullptr, nullptr) != HJ_OK) throw TraceError(std::string("hj_comm_info failed: ") + hj_last_error());
+    uint64_t s0 = 0, s1 = 0;
+    hj_shard_bounds(n_global, world, rank, &s0, &s1);
+    *start = s0;
+    *count = s1 - s0;
+}
+hj_device* comm_dev(hj_comm* comm) {
+    hj_device* dev = nullptr;
+    if (hj_comm_device(comm, &dev) != HJ_OK || !dev) throw TraceError(std::string("hj_comm_device failed: ") + hj_last_error());
+    return dev;
+}
+}  // namespace
+VarId array_sharded(hj_comm* comm, TypeId ty, const void* local_data, size_t n_global) {
+    if (!comm) throw TraceError("array_sharded: null communicator");
+    uint64_t s0, cnt;
+    local_block(comm, n_global, &s0, &cnt);
+    if (cnt == 0) throw TraceError("array_sharded: fewer elements than ranks");
+    hj_device* dev = comm_dev(comm);  // the buffer must live where the sharded kernels run
+    hj_buffer* buf = nullptr;
+    if (hj_buffer_create_from_slice(dev, local_data, cnt * type_size(ty), &buf) != HJ_OK)
+        throw TraceError(std::string("create_buffer_from_slice failed: ") + hj_last_error());
+    Extent e; e.n = n_global;
+    Var v = make(OpKind::Buffer, 0, 0, ty, e);
+    v.data.kind = Resource::Buffer;
+    v.data.buf = buf;
+    v.data.comm = comm;
+    return new_var(std::move(v), {});
+}
+VarId from_buffer_sharded(hj_comm* comm, hj_buffer* local_buf, TypeId ty, size_t n_global) {
+    if (!comm || !local_buf) throw TraceError("from_buffer_sharded: null argument");
+    uint64_t s0, cnt;
+    local_block(comm, n_global, &s0, &cnt);
+    size_t bytes = 0;
+    hj_buffer_size(local_buf, &bytes);
+    if (cnt == 0 || bytes < cnt * type_size(ty)) throw TraceError("from_buffer_sharded: the buffer does not hold this rank's block");
+    hj_buffer_retain(local_buf);
+    Extent e; e.n = n_global;
+    Var v = make(OpKind::Buffer, 0, 0, ty, e);
+    v.data.kind = Resource::Buffer;
+    v.data.buf = local_buf;
+    v.data.comm = comm;
+    return new_var(std::move(v), {});
+}
+ShardInfo shard_info(VarId id) {
+    hj_comm* comm = nullptr;
+    ShardInfo si;
+    size_t n = 0;
+    {
+        Lock l;
+        const Var& v = g_trace.var(id);
+        comm = v.data.kind == Resource::Buffer ? v.data.comm : nullptr;
+        si.deferred = v.data.deferred;
+        n = v.extent.n;
+    }
+    if (!comm) return ShardInfo();
+    si.sharded = true;
+    local_block(comm, n, &si.start, &si.count);
+    return si;
+}
+void materialise(VarId id) {
+    hj_buffer *buf = nullptr, *seed = nullptr;
+    hj_comm* comm = nullptr;
+    TypeId ty;
+    size_t n;
+    {
+        Lock l;
+        const Var& v = g_trace.var(id);
+        if (v.data.kind != Resource::Buffer || !v.data.comm || !v.data.deferred) return;
+        buf = v.data.buf; seed = v.data.seed; comm = v.data.comm; ty = v.ty; n = v.extent.n;
+        hj_buffer_retain(buf);
+        hj_buffer_retain(seed);
+    }
+    uint64_t s0, cnt;
+    local_block(comm, n, &s0, &cnt);
+    hj_status s = hj_apply_seed(comm_dev(comm), (hj_type_kind)type_node(ty).kind, cnt, buf, seed);
+    hj_buffer_release(buf);
+    hj_buffer_release(seed);
+    if (s != HJ_OK) throw TraceError(std::string("hj_apply_seed failed: ") + hj_last_error());
+    Lock l;
+    if (Var* v = g_trace.get(id)) {
+        if (v->data.buf == buf) {
+            v->data.deferred = false;
+            if (v->data.seed) hj_buffer_release(v->data.seed);
+            v->data.seed = nullptr;
+        }
+    }
 }
 
 // ---- elementwise ops (trace.rs:968-1082, 1335-1351, 1483-1504) ------------------------------------
@@ -618,19 +716,42 @@ size_t current_size(VarId id) {
     if (hj_buffer_to_host(b, 0, 4, &n) != HJ_OK) throw TraceError(std::string("to_host failed: ") + hj_last_error());
     return (size_t)n;
 }
+// For a sharded variable `start_elem` / `n_elem` address this rank's BLOCK (shard_info); a deferred
+// scan result is completed on the host: the block is downloaded as it is and the rank's offset added.
 void to_host(VarId id, size_t start_elem, size_t n_elem, void* dst) {
-    hj_buffer* b = nullptr;
+    hj_buffer *b = nullptr, *seed = nullptr;
     size_t es;
+    uint32_t kind;
     {
         Lock l;
         const Var& v = g_trace.var(id);
         if (v.data.kind != Resource::Buffer) throw TraceError("to_vec of a variable that has not been evaluated");
         b = v.data.buf;
         es = type_size(v.ty);
+        kind = type_node(v.ty).kind;
+        if (v.data.deferred) seed = v.data.seed;
     }
     if (n_elem == 0) return;
     if (hj_buffer_to_host(b, start_elem * es, n_elem * es, dst) != HJ_OK)
         throw TraceError(std::string("to_host failed: ") + hj_last_error());
+    if (!seed) return;
+    unsigned long long raw = 0;
+    if (hj_buffer_to_host(seed, 0, es, &raw) != HJ_OK) throw TraceError(std::string("to_host failed: ") + hj_last_error());
+    auto add = [&](auto* p) {
+        using T = std::remove_pointer_t<decltype(p)>;
+        T s;
+        memcpy(&s, &raw, sizeof(T));
+        for (size_t i = 0; i < n_elem; i++) p[i] = (T)(p[i] + s);
+    };
+    switch (kind) {
+    case HJ_I8: case HJ_U8: add((uint8_t*)dst); break;
+    case HJ_I16: case HJ_U16: add((uint16_t*)dst); break;
+    case HJ_I32: case HJ_U32: add((uint32_t*)dst); break;
+    case HJ_I64: case HJ_U64: add((uint64_t*)dst); break;
+    case HJ_F32: add((float*)dst); break;
+    case HJ_F64: add((double*)dst); break;
+    default: throw TraceError("to_vec: a deferred seed on a non-scalar variable");
+    }
 }
 
 }  // namespace tr

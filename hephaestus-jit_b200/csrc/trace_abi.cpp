@@ -104,6 +104,24 @@ hj_status hj_tr_literal(uint32_t ty, uint64_t bits, uint64_t* out) { OUT(literal
 hj_status hj_tr_sized_literal(uint32_t ty, uint64_t bits, uint64_t n, uint64_t* out) { OUT(literal(ty, bits, n)); }
 hj_status hj_tr_array(hj_device* dev, uint32_t ty, const void* data, uint64_t n, uint64_t* out) { OUT(array(dev, ty, data, n)); }
 hj_status hj_tr_from_buffer(hj_buffer* buf, uint32_t ty, uint64_t n, uint64_t* out) { OUT(from_buffer(buf, ty, n)); }
+hj_status hj_tr_array_sharded(hj_comm* comm, uint32_t ty, const void* local_data, uint64_t n_global, uint64_t* out) {
+    OUT(array_sharded(comm, ty, local_data, n_global));
+}
+hj_status hj_tr_from_buffer_sharded(hj_comm* comm, hj_buffer* local_buf, uint32_t ty, uint64_t n_global, uint64_t* out) {
+    OUT(from_buffer_sharded(comm, local_buf, ty, n_global));
+}
+hj_status hj_tr_var_shard(uint64_t v, int32_t* sharded, uint64_t* start, uint64_t* count, int32_t* deferred) {
+    return guarded([&] {
+        ShardInfo si = shard_info(v);
+        if (sharded) *sharded = si.sharded;
+        if (start) *start = si.start;
+        if (count) *count = si.count;
+        if (deferred) *deferred = si.deferred;
+    });
+}
+hj_status hj_tr_materialise(uint64_t v) {
+    return guarded([&] { materialise(v); });
+}
 hj_status hj_tr_bop(uint32_t op, uint64_t a, uint64_t b, uint64_t* out) { OUT(bop(op, a, b)); }
 hj_status hj_tr_uop(uint32_t op, uint64_t a, uint64_t* out) { OUT(uop(op, a)); }
 hj_status hj_tr_cast(uint64_t a, uint32_t ty, uint64_t* out) { OUT(cast(a, ty)); }
@@ -239,8 +257,8 @@ hj_status hj_graph_deserialize(hj_device* dev, const void* bytes, size_t n, hj_g
     });
 }
 // Graph::launch_with (graph.rs:192-400).  outputs_out receives hj_graph_n_outputs new references.
-hj_status hj_graph_launch(hj_graph* g, hj_device* dev, const uint64_t* inputs, uint32_t n_in, uint64_t* outputs_out,
-                          hj_graph_report* report) {
+hj_status hj_graph_launch_sharded(hj_graph* g, hj_device* dev, hj_comm* comm, const uint64_t* inputs, uint32_t n_in,
+                                  uint64_t* outputs_out, hj_graph_report* report) {
     HJ_REQUIRE(g && dev, "hj_graph_launch: null argument");
     return guarded([&] {
         std::vector<VarId> outs;
@@ -252,7 +270,7 @@ hj_status hj_graph_launch(hj_graph* g, hj_device* dev, const uint64_t* inputs, u
             br.passes = report->passes;
             br.passes_capacity = report->passes_capacity;
         }
-        launch_graph(*g->g, dev, vec_of(inputs, n_in), &outs, &lr, timed ? &br : nullptr);  // per-pass timings need the pass-by-pass path
+        launch_graph(*g->g, dev, vec_of(inputs, n_in), &outs, &lr, timed ? &br : nullptr, comm);  // per-pass timings need the pass-by-pass path
         if (outputs_out)
             for (size_t i = 0; i < outs.size(); i++) outputs_out[i] = outs[i];
         else
@@ -264,6 +282,10 @@ hj_status hj_graph_launch(hj_graph* g, hj_device* dev, const uint64_t* inputs, u
             report->backend_cpu_us = lr.backend_cpu_us;
         }
     });
+}
+hj_status hj_graph_launch(hj_graph* g, hj_device* dev, const uint64_t* inputs, uint32_t n_in, uint64_t* outputs_out,
+                          hj_graph_report* report) {
+    return hj_graph_launch_sharded(g, dev, nullptr, inputs, n_in, outputs_out, report);
 }
 
 // ---- function cache (record.rs:116-210): key -> compiled graph ------------------------------------------

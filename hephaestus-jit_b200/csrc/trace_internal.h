@@ -22,6 +22,13 @@ struct Resource {
     enum Kind : uint8_t { None, Literal, Buffer } kind = None;
     uint64_t lit = 0;
     hj_buffer* buf = nullptr;  // the Var owns one reference
+    // Sharded arrays (multi-GPU, one process per GPU): `buf` holds this rank's contiguous block of
+    // the variable's global extent (hj_shard_bounds).  `deferred`: the block is a LOCAL scan whose
+    // global value is buf[i] + seed[0] (hj_sharded_prefix_sum_deferred); the Var owns a reference to
+    // `seed`.  The communicator is borrowed: it must outlive the variables sharded over it.
+    hj_comm* comm = nullptr;
+    bool deferred = false;
+    hj_buffer* seed = nullptr;
 };
 
 // trace.rs:301-315
@@ -91,6 +98,12 @@ VarId dynamic_index(size_t capacity, VarId size);
 VarId literal(TypeId ty, uint64_t bits, size_t size);
 VarId array(hj_device* dev, TypeId ty, const void* data, size_t n);
 VarId from_buffer(hj_buffer* buf, TypeId ty, size_t n);
+// this rank's block of an n_global-element array: from host memory / from an existing device buffer
+VarId array_sharded(hj_comm* comm, TypeId ty, const void* local_data, size_t n_global);
+VarId from_buffer_sharded(hj_comm* comm, hj_buffer* local_buf, TypeId ty, size_t n_global);
+struct ShardInfo { bool sharded = false, deferred = false; uint64_t start = 0, count = 0; };
+ShardInfo shard_info(VarId id);
+void materialise(VarId id);  // a deferred scan result becomes an ordinary shard (buf[i] += seed)
 VarId bop(uint32_t op, VarId a, VarId b);
 VarId uop(uint32_t op, VarId a);
 VarId cast(VarId a, TypeId ty);
@@ -161,8 +174,10 @@ struct LaunchReport {  // graph.rs:138-143
 // graph::compile (graph.rs:436-614); consumes `ts`
 Graph* compile_graph(ThreadState& ts, const std::vector<VarId>& inputs, const std::vector<VarId>& outputs);
 // Graph::launch_with (graph.rs:192-400); `outputs` receives new references
+// `comm` != NULL (or any input / captured variable sharded): the graph runs over arrays partitioned
+// across the ranks of the communicator (hj_execute_graph_sharded)
 void launch_graph(const Graph& g, hj_device* dev, const std::vector<VarId>& inputs, std::vector<VarId>* outputs,
-                  LaunchReport* report, hj_report* backend_report);
+                  LaunchReport* report, hj_report* backend_report, hj_comm* comm = nullptr);
 std::string graph_debug_string(const Graph& g);
 // wire format of a compiled graph (tgraph_io.cpp); captured buffers travel with their contents
 std::vector<uint8_t> serialize_graph(const Graph& g);

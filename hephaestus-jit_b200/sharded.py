@@ -16,8 +16,8 @@ import ctypes
 
 import numpy as np
 
-from . import Buffer, Device, TYPE_SIZE, _NP
-from ._lib import HJ_UNIQUE_ID_BYTES, check, lib
+from . import Buffer, Device, TYPE_SIZE, _NP, _lib, marshal_graph
+from ._lib import HJ_IPC_HANDLE_BYTES, HJ_UNIQUE_ID_BYTES, RES_AUTO, RES_REPLICATED, RES_SHARDED, check, lib
 
 
 def shard_bounds(n: int, world: int, rank: int) -> tuple[int, int]:
@@ -62,10 +62,53 @@ class Comm:
         dist.broadcast_object_list(box, src=0)
         return Comm(dev, box[0], rank, world)
 
+    @staticmethod
+    def local(dev: Device, rank: int, world: int, all_gather_bytes) -> "Comm":
+        """The same communicator WITHOUT NCCL (``hj_comm_create_local`` + ``hj_comm_connect``): every rank
+        exports the CUDA-IPC handle of its mailbox, ``all_gather_bytes(handle: bytes) -> list[bytes]``
+        (any host transport: torch.distributed over gloo, a multiprocessing queue, ...) returns the
+        handles of all ranks in rank order.  Ranks may share one GPU."""
+        self = Comm.__new__(Comm)
+        self.dev, self.rank, self.world = dev, rank, world
+        out = ctypes.c_void_p()
+        handle = (ctypes.c_uint8 * HJ_IPC_HANDLE_BYTES)()
+        check(lib.hj_comm_create_local(dev.handle, rank, world, ctypes.byref(out), handle))
+        self._h = out
+        handles = all_gather_bytes(bytes(handle))
+        assert len(handles) == world and all(len(h) == HJ_IPC_HANDLE_BYTES for h in handles)
+        blob = (ctypes.c_uint8 * (HJ_IPC_HANDLE_BYTES * world)).from_buffer_copy(b"".join(handles))
+        check(lib.hj_comm_connect(self._h, blob))
+        return self
+
+    @staticmethod
+    def local_from_torch(dev: Device) -> "Comm":
+        """``Comm.local`` with the handles all-gathered over the current torch.distributed group (any
+        backend; the handles travel as host bytes)."""
+        import torch.distributed as dist
+        rank, world = dist.get_rank(), dist.get_world_size()
+
+        def gather(handle: bytes):
+            box = [None] * world
+            dist.all_gather_object(box, handle)
+            return box
+        return Comm.local(dev, rank, world, gather)
+
+    @property
+    def handle(self):
+        return self._h
+
+    def info(self) -> dict:
+        v = [ctypes.c_int32() for _ in range(4)]
+        check(lib.hj_comm_info(self._h, *[ctypes.byref(x) for x in v]))
+        return dict(zip(("rank", "world", "peer_memory", "nccl"), (x.value for x in v)))
+
     def destroy(self):
         h, self._h = self._h, None
         if h:
             check(lib.hj_comm_destroy(h))
+
+    def bounds(self, n: int) -> tuple[int, int]:
+        return shard_bounds(n, self.world, self.rank)
 
     # ---- sharded ops (device-side exchange) ---------------------------------------------------
     def reduce(self, op: int, ty: int, n_local: int, src: Buffer, dst: Buffer) -> None:
@@ -73,6 +116,34 @@ class Comm:
 
     def prefix_sum(self, ty: int, n_local: int, inclusive: bool, src: Buffer, dst: Buffer) -> None:
         check(lib.hj_sharded_prefix_sum(self._h, ty, n_local, int(inclusive), src.handle, dst.handle))
+
+    def prefix_sum_deferred(self, ty: int, n_local: int, inclusive: bool, src: Buffer, dst: Buffer, seed_out: Buffer) -> None:
+        """Local scan + this rank's exclusive offset in ``seed_out`` (one kernel, 2 x sizeof(T) bytes per
+        element); the global scan is ``dst[i] + seed_out[0]``."""
+        check(lib.hj_sharded_prefix_sum_deferred(self._h, ty, n_local, int(inclusive), src.handle, dst.handle,
+                                                 seed_out.handle))
+
+    def execute_graph(self, passes, env, descs, placement, seeds=None, timed: bool = False):
+        """``hj_execute_graph_sharded``: ``placement[i]`` in {RES_REPLICATED, RES_SHARDED, RES_AUTO} per
+        resource (AUTO ones are planned with ``hj_shard_plan`` first), ``seeds[i]`` an optional
+        one-element Buffer that lets a sharded integer scan into resource i stay deferred.  Returns
+        ``(placement, deferred, report)`` after the call."""
+        c_passes, n, c_env, c_desc, _keep = marshal_graph(passes, env, descs)
+        nres = len(env)
+        sh = (_lib.ShardDesc * max(nres, 1))()
+        for i in range(nres):
+            sh[i].placement = placement[i]
+            sh[i].deferred = 0
+            sh[i].seed = seeds[i].handle if seeds and seeds[i] is not None else None
+        check(lib.hj_shard_plan(c_passes, n, c_desc, nres, sh))
+        report = _lib.Report()
+        reps = (_lib.PassReport * max(n, 1))()
+        if timed:
+            report.passes = reps
+            report.passes_capacity = n
+        check(lib.hj_execute_graph_sharded(self._h, c_passes, n, c_env, c_desc, nres, sh, ctypes.byref(report)))
+        rep = [(reps[i].name.decode(), reps[i].start_us, reps[i].duration_us) for i in range(n)] if timed else None
+        return [sh[i].placement for i in range(nres)], [bool(sh[i].deferred) for i in range(nres)], rep
 
     def compress(self, n_local: int, index_base: int, src_mask: Buffer, index_out: Buffer, out_count: Buffer,
                  counts_out: Buffer | None = None) -> None:
@@ -94,6 +165,16 @@ class Comm:
         check(lib.hj_sharded_rebalance(self._h, elem_bytes, src.handle, counts.handle, dst.handle,
                                        out_count.handle if out_count else None, ctypes.byref(n)))
         return n.value
+
+
+def shard_plan(passes, descs, placement):
+    """Host-only placement propagation (``hj_shard_plan``): returns the placement of every resource."""
+    c_passes, n, _env, c_desc, _keep = marshal_graph(passes, [None] * len(descs), descs)
+    sh = (_lib.ShardDesc * max(len(descs), 1))()
+    for i, p in enumerate(placement):
+        sh[i].placement = p
+    check(lib.hj_shard_plan(c_passes, n, c_desc, len(descs), sh))
+    return [sh[i].placement for i in range(len(descs))]
 
 
 def rebalance_plan(counts, rank: int):

@@ -301,6 +301,9 @@ class VarRef:
         n = _u64()
         check(lib.hj_tr_var_size(self._id, ctypes.byref(n)))
         size = n.value
+        sh = self.shard()
+        if sh is not None:  # a sharded variable reads this rank's block; start / end address the block
+            size = sh[1]
         end = size if end is None else min(end, size)
         start = min(start, end)
         es = lib.hj_tr_type_size(ty)
@@ -317,6 +320,19 @@ class VarRef:
     def item(self, dtype=None):
         assert self.size() == 1
         return self.to_vec(dtype, 0, 1)[0]
+
+    def shard(self):
+        """None for an ordinary variable; ``(start, count, deferred)`` when the variable's buffer is the
+        block ``[start, start + count)`` of its global extent on this rank (``hj_tr_var_shard``).
+        ``deferred``: a scan result kept as (local scan, offset); ``to_vec`` adds the offset."""
+        sharded, deferred, start, count = ctypes.c_int32(), ctypes.c_int32(), _u64(), _u64()
+        check(lib.hj_tr_var_shard(self._id, ctypes.byref(sharded), ctypes.byref(start), ctypes.byref(count),
+                                  ctypes.byref(deferred)))
+        return (start.value, count.value, bool(deferred.value)) if sharded.value else None
+
+    def materialise(self) -> None:
+        """Adds the offset of a deferred scan result on the device (``hj_tr_materialise``)."""
+        check(lib.hj_tr_materialise(self._id))
 
 
 def _into(value, ty_hint: int) -> VarRef:
@@ -374,6 +390,34 @@ def array(data, device: Device, ty: int | None = None) -> VarRef:
         a = a.astype(_NP[ty])
     out = _u64()
     check(lib.hj_tr_array(device.handle, ty, a.ctypes.data_as(ctypes.c_void_p), a.size, ctypes.byref(out)))
+    return VarRef(out.value)
+
+
+def array_sharded(data, comm, ty: int | None = None, is_global: bool = True) -> VarRef:
+    """A variable of ``n`` elements partitioned over the ranks of ``comm`` (``sharded.Comm``): every rank
+    uploads its contiguous block.  ``data`` is the GLOBAL array (each rank slices its block out of it —
+    convenient for tests) or, with ``is_global=False``, ``(local_block, n_global)``."""
+    if is_global:
+        a = np.ascontiguousarray(data)
+        n_global = a.size
+        lo, hi = comm.bounds(n_global)
+        a = np.ascontiguousarray(a[lo:hi])
+    else:
+        a, n_global = np.ascontiguousarray(data[0]), int(data[1])
+        lo, hi = comm.bounds(n_global)
+        assert a.size == hi - lo, "the local block does not match hj_shard_bounds"
+    if ty is None:
+        ty = _FROM_NP[a.dtype]
+    else:
+        a = a.astype(_NP[ty])
+    out = _u64()
+    check(lib.hj_tr_array_sharded(comm.handle, ty, a.ctypes.data_as(ctypes.c_void_p), n_global, ctypes.byref(out)))
+    return VarRef(out.value)
+
+
+def from_buffer_sharded(buf: Buffer, ty: int, n_global: int, comm) -> VarRef:
+    out = _u64()
+    check(lib.hj_tr_from_buffer_sharded(comm.handle, buf.handle, ty, n_global, ctypes.byref(out)))
     return VarRef(out.value)
 
 
@@ -498,6 +542,9 @@ class Graph:
     def n_passes(self) -> int:
         return lib.hj_graph_n_passes(self._h)
 
+    def n_outputs(self) -> int:
+        return lib.hj_graph_n_outputs(self._h)
+
     def debug_string(self) -> str:
         out = ctypes.c_void_p()
         check(lib.hj_graph_debug_string(self._h, ctypes.byref(out)))
@@ -528,11 +575,12 @@ class Graph:
         check(lib.hj_graph_deserialize(device.handle if device is not None else None, data, len(data), ctypes.byref(out)))
         return Graph(out.value)
 
-    def launch(self, device: Device, timed: bool = False) -> Report:
-        return self.launch_with(device, [], timed)[0]
+    def launch(self, device: Device, timed: bool = False, comm=None) -> Report:
+        return self.launch_with(device, [], timed, comm)[0]
 
-    def launch_with(self, device: Device, inputs, timed: bool = False):
-        """``Graph::launch_with(device, inputs)`` -> (Report, outputs)."""
+    def launch_with(self, device: Device, inputs, timed: bool = False, comm=None):
+        """``Graph::launch_with(device, inputs)`` -> (Report, outputs).  ``comm`` (``sharded.Comm``): run over
+        arrays partitioned across its ranks; a graph that meets a sharded variable does so by itself."""
         n_out = lib.hj_graph_n_outputs(self._h)
         outs = (ctypes.c_uint64 * max(n_out, 1))()
         rep = _lib.GraphReport()
@@ -541,7 +589,8 @@ class Graph:
         if timed:
             rep.passes = pr
             rep.passes_capacity = n_p
-        check(lib.hj_graph_launch(self._h, device.handle, _handles(inputs), len(inputs), outs, ctypes.byref(rep)))
+        check(lib.hj_graph_launch_sharded(self._h, device.handle, comm.handle if comm is not None else None,
+                                          _handles(inputs), len(inputs), outs, ctypes.byref(rep)))
         passes = [(pr[i].name.decode(), pr[i].start_us, pr[i].duration_us) for i in range(n_p)] if timed else None
         report = Report(rep.aliasing_rate, rep.aliasing_duration_us, rep.backend_cpu_us, passes)
         return report, [VarRef(outs[i]) for i in range(n_out)]

@@ -318,14 +318,42 @@ typedef struct hj_comm hj_comm;
 hj_status hj_comm_unique_id(uint8_t out_id[HJ_UNIQUE_ID_BYTES]);
 hj_status hj_comm_create(hj_device* dev, const uint8_t id[HJ_UNIQUE_ID_BYTES], int32_t rank,
                          int32_t world, hj_comm** out);
+/* The same communicator WITHOUT NCCL: the scalar / small-array exchanges of the sharded ops only need
+ * every rank's mailbox mapped into every process (CUDA IPC).  hj_comm_create_local allocates this
+ * rank's mailbox and returns its IPC handle; the host all-gathers the `world` handles over any
+ * transport it likes (torch.distributed with gloo, MPI, a pipe) and passes them, in rank order, to
+ * hj_comm_connect.  A communicator built this way supports hj_sharded_reduce / prefix_sum(_deferred) /
+ * compress, hj_sharded_scatter_reduce for 4-byte arrays of <= 65536 elements and
+ * hj_execute_graph_sharded; hj_sharded_rebalance and larger arrays need NCCL and fail with
+ * HJ_ERR_NCCL.  Ranks may share one GPU (useful for testing: the kernels of different processes are
+ * time-sliced, the exchange is the same code). */
+#define HJ_IPC_HANDLE_BYTES 64
+hj_status hj_comm_create_local(hj_device* dev, int32_t rank, int32_t world, hj_comm** out,
+                               uint8_t handle_out[HJ_IPC_HANDLE_BYTES]);
+hj_status hj_comm_connect(hj_comm* comm, const uint8_t* handles /* world x HJ_IPC_HANDLE_BYTES */);
+hj_status hj_comm_info(hj_comm* comm, int32_t* rank, int32_t* world, int32_t* peer_memory, int32_t* has_nccl);
+hj_status hj_comm_device(hj_comm* comm, hj_device** out); /* borrowed, not retained */
 hj_status hj_comm_destroy(hj_comm* comm);
 /* local reduce of this rank's shard, then all-reduce of the partials: dst[0] on every rank
  * holds the global result. */
 hj_status hj_sharded_reduce(hj_comm* comm, hj_reduce_op op, hj_type_kind ty, size_t n_local,
                             hj_buffer* src, hj_buffer* dst);
-/* shard totals -> all-gather -> exclusive offset -> seeded local scan. */
+/* MATERIALISED sharded scan: shard totals (a read-only pass with the exchange fused into its last
+ * CTA) -> exclusive offset -> seeded local scan; dst holds this rank's slice of the global scan.
+ * 3 * sizeof(T) bytes of HBM traffic per element. */
 hj_status hj_sharded_prefix_sum(hj_comm* comm, hj_type_kind ty, size_t n_local,
                                 int32_t inclusive, hj_buffer* src, hj_buffer* dst);
+/* Sharded scan with a DEFERRED seed, 2 * sizeof(T) bytes per element, one kernel: dst receives the
+ * LOCAL scan of the shard and seed_out[0] (device, one element of `ty`) this rank's exclusive offset
+ * (sum of the totals of the ranks before it, exchanged over peer memory by the CTA that owns the
+ * last tile).  The global scan is dst[i] + seed_out[0] — "segment + offset", like the offsets table
+ * of hj_sharded_compress.  Fused kernels of hj_execute_graph_sharded add the seed when they load
+ * the value; hj_apply_seed materialises it. */
+hj_status hj_sharded_prefix_sum_deferred(hj_comm* comm, hj_type_kind ty, size_t n_local,
+                                         int32_t inclusive, hj_buffer* src, hj_buffer* dst,
+                                         hj_buffer* seed_out);
+/* buf[i] += seed[0] for i in 0..n (in place, 2 * sizeof(T) bytes per element). */
+hj_status hj_apply_seed(hj_device* dev, hj_type_kind ty, size_t n, hj_buffer* buf, hj_buffer* seed);
 /* local compress with global indices (index_base = global start of the shard); all-gather
  * of the counts: counts_out[world] (u32, device) and out_count[0] = global count. */
 hj_status hj_sharded_compress(hj_comm* comm, size_t n_local, uint32_t index_base,
@@ -342,6 +370,41 @@ hj_status hj_sharded_scatter_reduce(hj_comm* comm, hj_reduce_op op, hj_type_kind
  * boundaries are q*T/W + min(q, T%W).  Slices move GPU to GPU (grouped ncclSend/ncclRecv). */
 hj_status hj_sharded_rebalance(hj_comm* comm, size_t elem_bytes, hj_buffer* src, hj_buffer* counts,
                                hj_buffer* dst, hj_buffer* out_count, uint64_t* new_count_host);
+
+/* ---- sharded execute_graph ---------------------------------------------------------------
+ * The pass interpreter over arrays partitioned across the ranks of `comm` (one process per GPU):
+ * what BackendDevice::execute_graph (backend/vulkan/mod.rs:151-383) does for one device, pass for
+ * pass, for a Graph whose large arrays are split into contiguous blocks.
+ *   Kernel pass over sharded data  launched over the rank's block with KernelOp::Index = global index
+ *                                  (index_base); replicas may be read (gather tables), not written;
+ *                                  a `dst[keys[i]] += literal` pass is the privatised histogram + the
+ *                                  combine over peer memory (hj_sharded_scatter_reduce);
+ *   Reduce                         hj_sharded_reduce, result replicated;
+ *   PrefixSum                      hj_sharded_prefix_sum_deferred when the destination carries a seed
+ *                                  buffer (integer types): 2 * sizeof(T) bytes/element, the consumers add
+ *                                  the offset; else hj_sharded_prefix_sum;
+ *   Compress                       local compaction with global indices, counts exchanged in the kernel;
+ *                                  index_out stays a per-rank segment, out_count is the global count.
+ * Not sharded (SURVEY 8e "replicas only"): access to a sharded resource through a computed index,
+ * writes to a replica from a sharded kernel, DynSize kernels over sharded data -> HJ_ERR_UNSUPPORTED. */
+typedef enum { HJ_RES_REPLICATED = 0, HJ_RES_SHARDED = 1, HJ_RES_AUTO = 2 } hj_placement;
+typedef struct {
+    uint32_t placement; /* hj_placement.  SHARDED: the buffer holds this rank's block
+                           [start, end) = hj_shard_bounds(descs[i].size, world, rank) of the global array */
+    uint32_t deferred;  /* in / out, SHARDED scan results: 1 = the buffer holds the LOCAL scan; the
+                           global value of element i is buffer[i] + seed[0] */
+    hj_buffer* seed;    /* one element of the resource's type on the device, or NULL (then PrefixSum
+                           results are always materialised) */
+} hj_shard_desc;
+/* Block of rank `rank`: sizes differ by at most one, order preserved. */
+void hj_shard_bounds(uint64_t n, int32_t world, int32_t rank, uint64_t* start, uint64_t* end);
+/* Host only: fills in every HJ_RES_AUTO placement from the passes that write the resource. */
+hj_status hj_shard_plan(const hj_pass* passes, uint32_t n_passes, const hj_buffer_desc* descs,
+                        uint32_t n_resources, hj_shard_desc* shards);
+hj_status hj_execute_graph_sharded(hj_comm* comm, const hj_pass* passes, uint32_t n_passes,
+                                   hj_buffer* const* env, const hj_buffer_desc* descs,
+                                   uint32_t n_resources, hj_shard_desc* shards,
+                                   hj_report* report /* may be NULL */);
 
 /* ---- trace / schedule / graph (host side) ------------------------------------------------
  * C++ restatement of the layers ABOVE the backend traits, so that programs written against
@@ -385,6 +448,18 @@ hj_status hj_tr_literal(uint32_t ty, uint64_t bits, uint64_t* out);             
 hj_status hj_tr_sized_literal(uint32_t ty, uint64_t bits, uint64_t n, uint64_t* out); /* :627-641 */
 hj_status hj_tr_array(hj_device* dev, uint32_t ty, const void* data, uint64_t n, uint64_t* out); /* :647-663 */
 hj_status hj_tr_from_buffer(hj_buffer* buf, uint32_t ty, uint64_t n, uint64_t* out);
+/* Sharded arrays (no reference counterpart; BASELINE north star: "large arrays are partitioned across
+ * the GPUs"): a variable of n_global elements whose buffer holds this rank's contiguous block
+ * (hj_shard_bounds).  Everything traced from it is scheduled exactly like the reference schedules the
+ * unsharded program; Graph launches that meet a sharded variable run through hj_execute_graph_sharded.
+ * The communicator is borrowed and must outlive the variables. */
+hj_status hj_tr_array_sharded(hj_comm* comm, uint32_t ty, const void* local_data, uint64_t n_global, uint64_t* out);
+hj_status hj_tr_from_buffer_sharded(hj_comm* comm, hj_buffer* local_buf, uint32_t ty, uint64_t n_global, uint64_t* out);
+/* *sharded = 1: the variable's buffer is the block [start, start + count) of its global extent;
+ * *deferred = 1: it is a scan result kept as (local scan, offset) — hj_tr_to_host adds the offset,
+ * hj_tr_materialise adds it on the device.  hj_tr_to_host of a sharded variable addresses the BLOCK. */
+hj_status hj_tr_var_shard(uint64_t v, int32_t* sharded, uint64_t* start, uint64_t* count, int32_t* deferred);
+hj_status hj_tr_materialise(uint64_t v);
 hj_status hj_tr_bop(uint32_t op /* hj_bop */, uint64_t a, uint64_t b, uint64_t* out);  /* :968-1046 */
 hj_status hj_tr_uop(uint32_t op /* hj_uop */, uint64_t a, uint64_t* out);              /* :1048-1054 */
 hj_status hj_tr_cast(uint64_t a, uint32_t ty, uint64_t* out);                     /* :1056-1068 */
@@ -453,6 +528,10 @@ hj_status hj_graph_debug_string(hj_graph* g, char** out);
  * hj_graph_n_outputs new references */
 hj_status hj_graph_launch(hj_graph* g, hj_device* dev, const uint64_t* inputs, uint32_t n_in,
                           uint64_t* outputs_out, hj_graph_report* report);
+/* The same over arrays partitioned across the ranks of `comm` (may be NULL: then the communicator
+ * of any sharded input / captured variable is used, and a graph without one runs on `dev` alone). */
+hj_status hj_graph_launch_sharded(hj_graph* g, hj_device* dev, hj_comm* comm, const uint64_t* inputs,
+                                  uint32_t n_in, uint64_t* outputs_out, hj_graph_report* report);
 
 /* function cache of record() (record.rs:116-210): key = hash(function identity, input hashes) */
 hj_status hj_fcache_get(uint64_t key, hj_graph** out); /* *out = NULL on a miss, retained on a hit */

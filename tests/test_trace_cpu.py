@@ -625,3 +625,55 @@ def test_deep_dependency_chain_does_not_overflow_the_stack():
     ir = g.pass_ir(0)
     assert ir.n_vars >= n
     del x, g, ir, one   # dropping the last reference releases the whole chain
+
+
+# ---- record(): what persists on disk (hephaestus-jit_b200/record.py) -----------------------------------------
+def test_record_stable_key_covers_literal_inputs():
+    rec = import_module("hephaestus-jit_b200.record")
+    a, b, c = tr.literal(3, hj.U32), tr.literal(5, hj.U32), tr.literal(3, hj.U32)
+    x = tr.sized_literal(1, 10, hj.U32)
+    lay = ("list", ["v", "v"])
+    ka, kb, kc = (rec._stable_key("f", lay, [x, v]) for v in (a, b, c))
+    assert ka == kc and ka != kb          # the literal's VALUE is part of the key
+    assert rec._stable_key("g", lay, [x, a]) != ka
+    st = tr.composite([tr.sized_literal(1, 4, hj.U32), tr.sized_literal(2, 4, hj.U8)])
+    assert rec._stable_key("f", lay, [x, st]) is None   # composite TypeIds are process-local
+
+
+def test_record_layout_json_round_trip_and_rejects_user_types():
+    rec = import_module("hephaestus-jit_b200.record")
+    lay = ("tuple", ["v", ("list", ["v", "none"]), ("dict", [("a", "v"), (3, ("tuple", []))])])
+    j = rec._layout_to_json(lay)
+    import json
+    assert rec._layout_from_json(json.loads(json.dumps(j))) == lay
+    assert rec._count_vars(lay) == 3
+    assert rec._layout_to_json(("obj", int, None)) is None
+    assert rec._layout_to_json(("list", ["v", ("obj", int, None)])) is None
+    for bad in ({"k": 1}, ["set", []], ["list", "v"], ["dict", [[["x", "k"], "v"]]]):
+        with pytest.raises((ValueError, TypeError)):
+            rec._layout_from_json(bad)
+
+
+def test_record_default_name_fingerprints_closures_and_helpers():
+    rec = import_module("hephaestus-jit_b200.record")
+    import hashlib
+
+    def fp(f):
+        h = hashlib.sha256()
+        ok = rec._code_fingerprint(f, h, set())
+        return ok, h.hexdigest()
+
+    def make(k):
+        def f(x):
+            return x.mul(tr.literal(k, hj.U32))
+        return f
+
+    (ok3, h3), (ok5, h5), (ok3b, h3b) = fp(make(3)), fp(make(5)), fp(make(3))
+    assert ok3 and ok5 and h3 == h3b and h3 != h5    # a plain closure value changes the name
+
+    def make_obj(o):
+        def f(x):
+            return x.mul(o)
+        return f
+
+    assert fp(make_obj(object()))[0] is False        # closes over something opaque: no default persistence

@@ -660,6 +660,80 @@ def test_record_outputs_survive_later_passes(device):
         del early, late
 
 
+def test_record_gather_of_a_temporary_does_not_alias_its_output(device):
+    """`a = x + 1; a.schedule(); b = a.gather(perm)` under record(): `a` dies in the pass that creates
+    `b`.  The reference's lifetime aliasing (graph.rs:283-290) would hand a's buffer to b inside that
+    very pass — threads would read elements other threads are overwriting.  Same-pass reuse is only
+    taken for Index-in / Index-out pairs (tgraph.cpp); this pair must get two buffers."""
+    n = (1 << 20) + 13
+    rng = np.random.Generator(np.random.PCG64(5))
+    perm = rng.permutation(n).astype(np.uint32)
+    pv = tr.array(perm, device)
+
+    def fn(x):
+        a = x.add(tr.literal(1, U32))
+        a.schedule()
+        tr.schedule_eval()
+        return a.gather(pv)
+
+    f = rec.record(fn)
+    for seed in range(3):
+        xs = np.random.Generator(np.random.PCG64(seed)).integers(0, 1 << 30, size=n).astype(np.uint32)
+        b, _ = f(device, tr.array(xs, device))
+        assert np.array_equal(b.to_vec(np.uint32), (xs + 1)[perm]), f"call {seed}"
+        del b
+
+
+def test_kernel_launch_rejects_unsafe_buffer_overlap(device):
+    """hj_kernel_launch: one buffer under a gathered-through-a-computed-index slot and a written slot is
+    refused (every slot is __restrict__ / read through the non-coherent path); the in-place Index-in /
+    Index-out binding is accepted and correct."""
+    irm = importlib.import_module("hephaestus-jit_b200.ir")
+    n = 1 << 16
+    xs = np.arange(n, dtype=np.uint32)
+    # dst[i] = src[i] + 1 in place
+    b = irm.IRBuilder()
+    u32 = b.scalar(hj.U32)
+    src, idx = b.buffer_ref(u32), b.index()
+    v = b.bop(irm.BOP_ADD, u32, b.gather(u32, src, idx), b.literal(hj.U32, 1))
+    b.scatter(b.buffer_ref(u32), v, idx)
+    buf = device.create_buffer_from_slice(xs)
+    device.launch(device.kernel(b), n, [buf, buf])
+    assert np.array_equal(buf.to_host(np.uint32), xs + 1)
+    # dst[i] = src[n-1-i]: a permutation read — overlapping buffers would race
+    b = irm.IRBuilder()
+    u32 = b.scalar(hj.U32)
+    src, idx = b.buffer_ref(u32), b.index()
+    rev = b.bop(irm.BOP_SUB, u32, b.literal(hj.U32, n - 1), idx)
+    b.scatter(b.buffer_ref(u32), b.gather(u32, src, rev), idx)
+    k = device.kernel(b)
+    with pytest.raises(hj.HjError, match="overlap"):
+        device.launch(k, n, [buf, buf])
+    other = device.create_buffer(4 * n)
+    device.launch(k, n, [buf, other])
+    assert np.array_equal(other.to_host(np.uint32), (xs + 1)[::-1])
+
+
+def test_record_persistent_cache_keys_literal_inputs(device, tmp_path):
+    """Unsized literal inputs are constants of the kernel IR: a stored graph for f(x, literal(3)) must
+    not be served to f(x, literal(5)) by a later process (simulated by clearing the function cache)."""
+    L = importlib.import_module("hephaestus-jit_b200._lib")
+    xs = np.arange(1000, dtype=np.uint32)
+
+    def fn(x, k):
+        return x.mul(k)
+
+    for lit in (3, 5, 3):
+        L.check(L.lib.hj_fcache_clear())
+        f = rec.record(fn, cache_dir=str(tmp_path), name="scale_v1")
+        y, _ = f(device, tr.array(xs, device), tr.literal(lit, U32))
+        assert np.array_equal(y.to_vec(np.uint32), xs * np.uint32(lit)), lit
+        del y, f
+    assert len(list(tmp_path.glob("*.hjgraph"))) == 2
+    assert not list(tmp_path.glob("*.layout.tmp")) and all(
+        p.read_text().startswith(("[", '"')) for p in tmp_path.glob("*.layout"))   # JSON, never a pickle
+
+
 # ---- the remaining in-scope reference tests (hephaestus-jit/src/test.rs) --------------------------------
 def test_extract2_and_test_struct(device):  # test.rs:199-235 (print only in the reference; checked here)
     s = tr.composite([tr.sized_literal(2, 2, U32), tr.sized_literal(0xFF, 2, U8)])
