@@ -211,11 +211,21 @@ __device__ __forceinline__ T fold2(T a, T b) {
 
 template <typename T, int OP>
 __global__ void __launch_bounds__(256)
-array_allreduce_kernel(int rank, int world, uint32_t epoch, ArrayBoxes ab, uint4* __restrict__ dst, uint32_t n_vec) {
+array_allreduce_kernel(int rank, int world, uint32_t epoch, ArrayBoxes ab, uint32_t* __restrict__ dst32, uint32_t n) {
     static_assert(sizeof(T) == 4, "4-byte elements");
     const uint32_t i = blockIdx.x * 256 + threadIdx.x;
-    if (i >= n_vec) return;
-    const uint4 mine = dst[i];
+    if (4 * i >= n) return;
+    // a thread owns four elements; the last vector of an array whose length is not a multiple of four
+    // (or whose base is not 16-byte aligned) is moved element by element, the padding travels as zeros
+    const bool whole = 4 * i + 4 <= n && ((uintptr_t)dst32 & 15u) == 0;
+    uint4 mine = make_uint4(0, 0, 0, 0);
+    if (whole) {
+        mine = reinterpret_cast<const uint4*>(dst32)[i];
+    } else {
+        uint32_t e[4] = {0, 0, 0, 0};
+        for (uint32_t k = 0; k < 4 && 4 * i + k < n; k++) e[k] = dst32[4 * i + k];
+        mine = make_uint4(e[0], e[1], e[2], e[3]);
+    }
     const size_t slot_vecs = HJ_ARRAYSLOT_BYTES / 16;
     const uint4 w0 = make_uint4(mine.x, epoch, mine.y, epoch), w1 = make_uint4(mine.z, epoch, mine.w, epoch);
     const uint4* own = ab.box[0];  // ab.box[rank] without indexing the parameter struct dynamically
@@ -256,7 +266,12 @@ array_allreduce_kernel(int rank, int world, uint32_t epoch, ArrayBoxes ab, uint4
         }
     uint4 out;
     memcpy(&out, acc, 16);
-    dst[i] = out;
+    if (whole) {
+        reinterpret_cast<uint4*>(dst32)[i] = out;
+    } else {
+        const uint32_t e[4] = {out.x, out.y, out.z, out.w};
+        for (uint32_t k = 0; k < 4 && 4 * i + k < n; k++) dst32[4 * i + k] = e[k];
+    }
 }
 
 // exchange epochs are 31-bit and never 0 (0 is what a cleared mailbox holds; bit 31 is a mode flag)
@@ -290,13 +305,13 @@ ArrayPeerView array_view(hj_comm* c) {  // consumes one exchange epoch
 // `view`: an epoch the caller has already drawn (array_view), else a new one is drawn here
 template <typename T>
 hj_status peer_array_allreduce(hj_comm* c, hj_reduce_op op, void* dst, size_t n, const ArrayPeerView* view) {
-    const uint32_t n_vec = (uint32_t)(n / 4);
+    const uint32_t n_vec = (uint32_t)((n + 3) / 4);
     const ArrayPeerView ax = view ? *view : array_view(c);
     const unsigned grid = (n_vec + 255) / 256;
     ArrayBoxes ab;
     for (int r = 0; r < HJ_MAX_PEERS; r++) ab.box[r] = ax.box[r];
 #define HJ_COMBINE(OP) \
-    array_allreduce_kernel<T, OP><<<grid, 256, 0, c->dev->stream>>>(c->rank, c->world, ax.epoch, ab, (uint4*)dst, n_vec)
+    array_allreduce_kernel<T, OP><<<grid, 256, 0, c->dev->stream>>>(c->rank, c->world, ax.epoch, ab, (uint32_t*)dst, (uint32_t)n)
     switch (op) {
     case HJ_REDUCE_SUM: HJ_COMBINE(HJ_REDUCE_SUM); break;
     case HJ_REDUCE_MAX: HJ_COMBINE(HJ_REDUCE_MAX); break;
@@ -736,9 +751,7 @@ hj_status hj_sharded_scatter_reduce(hj_comm* c, hj_reduce_op op, hj_type_kind ty
         HJ_TRY(launch_scatter_reduce(c->dev, op, ty, n_local, (const uint32_t*)idx->ptr, nullptr, literal, dst->ptr, n_dst, &ax,
                                      &exchanged));
         if (exchanged) return HJ_OK;
-        if (n_dst % 4 == 0 && ((uintptr_t)dst->ptr & 15u) == 0)
-            return peer_array_allreduce<uint32_t>(c, op, dst->ptr, n_dst, &ax);
-        // cannot happen for library-allocated buffers; fall through to NCCL with the epoch spent
+        return peer_array_allreduce<uint32_t>(c, op, dst->ptr, n_dst, &ax);
     } else {
         HJ_TRY(launch_scatter_reduce(c->dev, op, ty, n_local, (const uint32_t*)idx->ptr, src ? src->ptr : nullptr, literal,
                                      dst->ptr, n_dst));
@@ -746,7 +759,7 @@ hj_status hj_sharded_scatter_reduce(hj_comm* c, hj_reduce_op op, hj_type_kind ty
     if (c->world == 1) return HJ_OK;
     // small 4-byte arrays: exchange over peer memory
     const bool float_bits = ty == HJ_F32 && (op == HJ_REDUCE_OR || op == HJ_REDUCE_AND || op == HJ_REDUCE_XOR);
-    if (small_array && n_dst % 4 == 0 && ((uintptr_t)dst->ptr & 15u) == 0 && !float_bits) {
+    if (small_array && ((uintptr_t)dst->ptr & 3u) == 0 && !float_bits) {
         if (ty == HJ_F32) return peer_array_allreduce<float>(c, op, dst->ptr, n_dst, nullptr);
         if (ty == HJ_I32) return peer_array_allreduce<int32_t>(c, op, dst->ptr, n_dst, nullptr);
         if (ty == HJ_U32) return peer_array_allreduce<uint32_t>(c, op, dst->ptr, n_dst, nullptr);

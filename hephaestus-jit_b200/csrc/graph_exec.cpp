@@ -390,12 +390,18 @@ hj_status execute_passes(hj_device* dev, const ShardCtx* sc, const hj_pass* pass
             size_t launch_size = p.size;
             uint32_t index_base = 0;
             SeededIR seeded;
+            struct Views {  // non-owning views of replicas, released on every path out of this pass
+                std::vector<hj_buffer*> v;
+                ~Views() { for (hj_buffer* b : v) hj_buffer_release(b); }
+                void push_back(hj_buffer* b) { v.push_back(b); }
+            } views;
             if (pass_sharded) {
                 // every sharded resource is one contiguous block of a global array of p.size elements,
                 // addressed by the bare Index; everything else is a replica and may only be read
                 std::vector<SlotAccess> access;
                 analyse_slot_access(ir, &access);
                 uint64_t s0 = 0, cnt = 0;
+                std::vector<uint32_t> replica_views;
                 std::vector<bool> add_seed(p.n_resources, false);
                 bool any_seed = false;
                 for (uint32_t b = 0; b < p.n_resources; b++) {
@@ -404,6 +410,14 @@ hj_status execute_passes(hj_device* dev, const ShardCtx* sc, const hj_pass* pass
                         if (access[b].written)
                             return fail(HJ_ERR_UNSUPPORTED, "kernel pass %u writes resource %u, a replica, from a kernel over "
                                         "sharded data: scatters into a sharded-over destination are replicas only (SURVEY 8e)", i, rid);
+                        // the bare Index addresses the rank's block (codegen.cpp: addr_of), a replica holds the
+                        // WHOLE array: a replica read at Index is bound as the view that starts at the block
+                        if (access[b].any_index) {
+                            if (!access[b].index_only || descs[rid].size != p.size)
+                                return fail(HJ_ERR_UNSUPPORTED, "kernel pass %u reads replica %u both at Index and through computed "
+                                            "indices (or with another extent) from a kernel over sharded data", i, rid);
+                            replica_views.push_back(b);
+                        }
                         continue;
                     }
                     if (descs[rid].size != p.size || !access[b].index_only)
@@ -417,6 +431,14 @@ hj_status execute_passes(hj_device* dev, const ShardCtx* sc, const hj_pass* pass
                 }
                 launch_size = (size_t)cnt;
                 index_base = (uint32_t)s0;
+                for (uint32_t b : replica_views) {
+                    hj_buffer* view = nullptr;
+                    const size_t es = descs[p.resources[b]].elem_bytes;
+                    HJ_REQUIRE((s0 + cnt) * es <= bufs[b]->bytes, "kernel pass %u: replica %u is smaller than the pass extent", i, p.resources[b]);
+                    HJ_TRY(hj_buffer_wrap(dev, (char*)bufs[b]->ptr + s0 * es, (size_t)cnt * es, &view));
+                    views.push_back(view);
+                    bufs[b] = view;
+                }
                 if (any_seed) {
                     build_seeded_ir(ir, add_seed, &seeded);
                     ir = &seeded.view;
@@ -551,18 +573,20 @@ extern "C" void hj_shard_bounds(uint64_t n, int32_t world, int32_t rank, uint64_
 }
 
 // Placement propagation, host only.  Resources the caller has placed keep their placement; every
-// HJ_RES_AUTO resource takes the placement of the first pass that writes it:
-//   kernel over sharded data  -> outputs of the pass extent written at the bare Index are SHARDED,
-//                                 everything else a replica;
-//   Reduce                    -> dst replicated (every rank ends up with the global result);
-//   PrefixSum                 -> dst like src;
-//   Compress                  -> index_out like the mask, out_count replicated (global count).
+// HJ_RES_AUTO resource is placed by the passes that touch it, iterated to a fixed point so that
+// demand also flows backwards (the zero-fill kernel in front of a Compress has no sharded input of
+// its own, but its output is the index segment of a sharded mask):
+//   kernel with a sharded resource -> every undecided resource of the pass extent that is only
+//                                     addressed by the bare Index is SHARDED, the rest replicas;
+//   Reduce                         -> dst replicated (every rank ends up with the global result);
+//   PrefixSum                      -> dst like src (and src like a dst already sharded);
+//   Compress                       -> index_out like the mask (and the mask like an index_out
+//                                     already sharded), out_count replicated (global count).
+// What no sharded pass ever touches stays a replica: the single-GPU program, run by every rank.
 extern "C" hj_status hj_shard_plan(const hj_pass* passes, uint32_t n_passes, const hj_buffer_desc* descs, uint32_t n_resources,
                                    hj_shard_desc* shards) {
     HJ_REQUIRE((passes || n_passes == 0) && ((descs && shards) || n_resources == 0), "hj_shard_plan: null argument");
-    auto place = [&](uint32_t rid, uint32_t pl) {
-        if (shards[rid].placement == HJ_RES_AUTO) shards[rid].placement = pl;
-    };
+    std::vector<std::vector<SlotAccess>> access(n_passes);
     for (uint32_t i = 0; i < n_passes; i++) {
         const hj_pass& p = passes[i];
         for (uint32_t b = 0; b < p.n_resources; b++)
@@ -574,38 +598,56 @@ extern "C" hj_status hj_shard_plan(const hj_pass* passes, uint32_t n_passes, con
             if (!verr.empty()) return fail(HJ_ERR_INVALID, "kernel pass %u: IR rejected: %s", i, verr.c_str());
             HJ_REQUIRE(p.ir->n_buffers == p.n_resources, "kernel pass %u: IR names %u buffers, the pass binds %u", i,
                        p.ir->n_buffers, p.n_resources);
-            bool any = false;
-            for (uint32_t b = 0; b < p.n_resources; b++) any = any || shards[p.resources[b]].placement == HJ_RES_SHARDED;
-            std::vector<SlotAccess> access;
-            analyse_slot_access(p.ir, &access);
-            for (uint32_t b = 0; b < p.n_resources; b++) {
-                const uint32_t rid = p.resources[b];
-                const bool shard_out = any && p.size_buffer < 0 && access[b].written && access[b].index_only && descs[rid].size == p.size;
-                place(rid, shard_out ? HJ_RES_SHARDED : HJ_RES_REPLICATED);
-            }
+            analyse_slot_access(p.ir, &access[i]);
             break;
         }
-        case HJ_PASS_REDUCE:
-            HJ_REQUIRE(p.n_resources >= 2, "reduce pass %u needs [dst, src]", i);
-            place(p.resources[1], HJ_RES_REPLICATED);
-            place(p.resources[0], HJ_RES_REPLICATED);
-            break;
-        case HJ_PASS_PREFIX_SUM:
-            HJ_REQUIRE(p.n_resources >= 2, "prefix-sum pass %u needs [dst, src]", i);
-            place(p.resources[1], HJ_RES_REPLICATED);
-            place(p.resources[0], shards[p.resources[1]].placement);
-            break;
-        case HJ_PASS_COMPRESS:
-            HJ_REQUIRE(p.n_resources >= 3, "compress pass %u needs [index_out, out_count, src]", i);
-            place(p.resources[2], HJ_RES_REPLICATED);
-            place(p.resources[0], shards[p.resources[2]].placement);
-            place(p.resources[1], HJ_RES_REPLICATED);
-            break;
+        case HJ_PASS_REDUCE: HJ_REQUIRE(p.n_resources >= 2, "reduce pass %u needs [dst, src]", i); break;
+        case HJ_PASS_PREFIX_SUM: HJ_REQUIRE(p.n_resources >= 2, "prefix-sum pass %u needs [dst, src]", i); break;
+        case HJ_PASS_COMPRESS: HJ_REQUIRE(p.n_resources >= 3, "compress pass %u needs [index_out, out_count, src]", i); break;
         default:
             return fail(HJ_ERR_UNSUPPORTED, "pass %u: device op %u is out of scope for the B200 backend", i, p.kind);
         }
     }
-    for (uint32_t r = 0; r < n_resources; r++) place(r, HJ_RES_REPLICATED);  // never touched by a pass
+    bool changed = true;
+    auto place = [&](uint32_t rid, uint32_t pl) {
+        if (shards[rid].placement == HJ_RES_AUTO) {
+            shards[rid].placement = pl;
+            changed = true;
+        }
+    };
+    auto is = [&](uint32_t rid, uint32_t pl) { return shards[rid].placement == pl; };
+    for (uint32_t round = 0; changed && round <= n_passes + 1; round++) {
+        changed = false;
+        for (uint32_t i = 0; i < n_passes; i++) {
+            const hj_pass& p = passes[i];
+            switch (p.kind) {
+            case HJ_PASS_KERNEL: {
+                bool any = false;
+                for (uint32_t b = 0; b < p.n_resources; b++) any = any || is(p.resources[b], HJ_RES_SHARDED);
+                if (!any || p.size_buffer >= 0) break;  // undecided for now (or DynSize: never sharded)
+                for (uint32_t b = 0; b < p.n_resources; b++) {
+                    const uint32_t rid = p.resources[b];
+                    const SlotAccess& a = access[i][b];
+                    place(rid, a.index_only && (a.read || a.written) && descs[rid].size == p.size ? HJ_RES_SHARDED : HJ_RES_REPLICATED);
+                }
+                break;
+            }
+            case HJ_PASS_REDUCE: place(p.resources[0], HJ_RES_REPLICATED); break;
+            case HJ_PASS_PREFIX_SUM:
+                if (!is(p.resources[1], HJ_RES_AUTO)) place(p.resources[0], shards[p.resources[1]].placement);
+                else if (is(p.resources[0], HJ_RES_SHARDED)) place(p.resources[1], HJ_RES_SHARDED);
+                break;
+            case HJ_PASS_COMPRESS:
+                place(p.resources[1], HJ_RES_REPLICATED);
+                if (!is(p.resources[2], HJ_RES_AUTO)) place(p.resources[0], shards[p.resources[2]].placement);
+                else if (is(p.resources[0], HJ_RES_SHARDED)) place(p.resources[2], HJ_RES_SHARDED);
+                break;
+            default: break;
+            }
+        }
+    }
+    for (uint32_t r = 0; r < n_resources; r++)
+        if (shards[r].placement == HJ_RES_AUTO) shards[r].placement = HJ_RES_REPLICATED;
     return HJ_OK;
 }
 

@@ -34,6 +34,7 @@ void analyse_slot_access(const hj_ir* ir, std::vector<SlotAccess>* out) {
             s.last_read = i;
             if (v.n_deps(i) > 2) s.cond_gather = true;
             if (v.var(v.dep(i, 1)).op != HJ_OP_INDEX) s.index_only = false;
+            else s.any_index = true;
             if (v.var(v.dep(i, 1)).op != HJ_OP_INDEX || depth != 0) s.identity = false;
             break;
         }
@@ -45,6 +46,7 @@ void analyse_slot_access(const hj_ir* ir, std::vector<SlotAccess>* out) {
             if (s.first_write > (int64_t)i) s.first_write = i;
             // AtomicInc: deps = [dst, idx, active] — a counter, never a shard
             if (var.op == HJ_OP_ATOMIC_INC || v.var(v.dep(i, 2)).op != HJ_OP_INDEX) s.index_only = false;
+            else s.any_index = true;
             if (var.op != HJ_OP_SCATTER) { s.read = true; s.identity = false; break; }  // atomics read-modify-write
             if (v.var(v.dep(i, 2)).op != HJ_OP_INDEX || depth != 0) s.identity = false;
             break;

@@ -37,6 +37,7 @@ struct SlotAccess {
     // every access uses the bare Index variable as its index (loops / ifs / conditions allowed): the
     // slot can hold one contiguous shard of a global array (graph_exec.cpp, sharded execution)
     bool index_only = true;
+    bool any_index = false;              // some access uses the bare Index variable
     bool cond_gather = false;            // some Gather carries a condition (inactive lanes read as 0)
     int64_t last_read = -1;              // position (var index) of the last Gather
     int64_t first_write = INT64_MAX;     // position of the first Scatter

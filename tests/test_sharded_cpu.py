@@ -114,3 +114,68 @@ def _worker(rank, world, port, n):
 @pytest.mark.parametrize("world", [2, 3])
 def test_exchange_protocol_gloo(world):
     mp.spawn(_worker, args=(world, _free_port(), 100003), nprocs=world, join=True)
+
+
+# ---- placement planning of the sharded pass interpreter (hj_shard_plan, host only) ------------------------
+def _c2_like_passes(n, bins=1 << 10):
+    """kernel y = f(x); reduce; scan; compress (with its zero-fill kernel); histogram-shaped kernel."""
+    hj = importlib.import_module("hephaestus-jit_b200")
+    irm = importlib.import_module("hephaestus-jit_b200.ir")
+    # resources: 0 x, 1 y, 2 sum, 3 scan, 4 mask, 5 index, 6 count, 7 keys, 8 hist, 9 table, 10 gathered
+    fill = irm.IRBuilder()
+    u32 = fill.scalar(hj.U32)
+    fill.scatter(fill.buffer_ref(u32), fill.literal(hj.U32, 0), fill.index())
+    hist = irm.IRBuilder()
+    u32 = hist.scalar(hj.U32)
+    dst, keys = hist.buffer_ref(u32), hist.buffer_ref(u32)
+    hist.scatter_reduce(hj.SUM, dst, hist.literal(hj.U32, 1), hist.gather(u32, keys, hist.index()))
+    gat = irm.IRBuilder()   # out[i] = table[x[i]]: a replica read through a computed index
+    u32 = gat.scalar(hj.U32)
+    x, table, idx = gat.buffer_ref(u32), gat.buffer_ref(u32), gat.index()
+    gat.scatter(gat.buffer_ref(u32), gat.gather(u32, table, gat.gather(u32, x, idx)), idx)
+    passes = [
+        {"kind": hj.PASS_KERNEL, "resources": [0, 1], "ir": irm.c2_chain_ir(), "size": n},
+        {"kind": hj.PASS_REDUCE, "arg": hj.SUM, "resources": [2, 1]},
+        {"kind": hj.PASS_PREFIX_SUM, "arg": 1, "resources": [3, 7]},
+        {"kind": hj.PASS_KERNEL, "resources": [5], "ir": fill, "size": n},
+        {"kind": hj.PASS_COMPRESS, "resources": [5, 6, 4]},
+        {"kind": hj.PASS_KERNEL, "resources": [8, 7], "ir": hist, "size": n},
+        {"kind": hj.PASS_KERNEL, "resources": [7, 9, 10], "ir": gat, "size": n},
+    ]
+    descs = [(n, hj.F32, 4), (n, hj.F32, 4), (1, hj.F32, 4), (n, hj.U32, 4), (n, hj.BOOL, 1), (n, hj.U32, 4),
+             (1, hj.U32, 4), (n, hj.U32, 4), (bins, hj.U32, 4), (4096, hj.U32, 4), (n, hj.U32, 4)]
+    return passes, descs
+
+
+def test_shard_plan_propagates_placement():
+    S, R, A = sharded.RES_SHARDED, sharded.RES_REPLICATED, sharded.RES_AUTO
+    passes, descs = _c2_like_passes(1 << 20)
+    #        x  y  sum scan mask index count keys hist table gathered
+    given = [S, A, A,  A,   S,   A,    A,    S,   R,   R,    A]
+    got = sharded.shard_plan(passes, descs, given)
+    assert got == [S, S, R, S, S, S, R, S, R, R, S]
+    # nothing sharded going in: everything is a replica, the single-GPU program
+    assert sharded.shard_plan(passes, descs, [A] * len(descs)) == [R] * len(descs)
+    # (index, resource 5: its zero-fill kernel has no sharded input of its own — the demand flows
+    # backwards from the Compress pass whose mask is sharded)
+
+
+def test_shard_plan_rejects_malformed_pass_lists():
+    hj = importlib.import_module("hephaestus-jit_b200")
+    passes, descs = _c2_like_passes(1 << 12)
+    bad = [dict(passes[0], resources=[0, 99])]
+    with pytest.raises(hj.HjError, match="out of range"):
+        sharded.shard_plan(bad, descs, [sharded.RES_AUTO] * len(descs))
+    with pytest.raises(hj.HjError, match="binds"):
+        sharded.shard_plan([dict(passes[0], resources=[0])], descs, [sharded.RES_AUTO] * len(descs))
+
+
+def test_hj_shard_bounds_matches_the_python_statement():
+    import ctypes
+    L = importlib.import_module("hephaestus-jit_b200._lib")
+    for n in (0, 1, 7, 1000, (1 << 30) + 5):
+        for world in (1, 2, 3, 8):
+            for r in range(world):
+                a, b = ctypes.c_uint64(), ctypes.c_uint64()
+                L.lib.hj_shard_bounds(n, world, r, ctypes.byref(a), ctypes.byref(b))
+                assert (a.value, b.value) == sharded.shard_bounds(n, world, r)

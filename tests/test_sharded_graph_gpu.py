@@ -1,0 +1,281 @@
+"""Sharded execution on the GPU, parity against the oracle on the WHOLE array.
+
+Two layers are covered at world 1, 2 and 3:
+  * the sharded device ops of include/hj.h with their exchange FUSED into the kernel (reduce, scan
+    with a deferred seed, compress with the counts exchange, the packed-16 histogram fold+exchange);
+  * whole traced programs over arrays partitioned with ``tr.array_sharded`` — Graph.launch ->
+    hj_execute_graph_sharded, pass for pass what backend/vulkan/mod.rs:151-383 does on one device.
+
+The communicator is bootstrapped WITHOUT NCCL (hj_comm_create_local / hj_comm_connect: the CUDA-IPC
+handles of the peer mailboxes travel over a torch.distributed gloo group), so the ranks of a world
+may share one GPU: on the one-GPU box the driver tests on, the kernels of the two or three
+processes are time-sliced and the exchange code is exactly the multi-GPU one.  With enough GPUs
+every rank takes its own (tests/test_sharded_gpu.py covers the NCCL bootstrap there).
+"""
+import importlib
+import os
+import socket
+import sys
+import traceback
+
+import numpy as np
+import pytest
+import torch.multiprocessing as mp
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+hj = importlib.import_module("hephaestus-jit_b200")
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _entry(rank, world, port, body, args, errq):
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    os.environ.setdefault("OMP_NUM_THREADS", "2")
+    import torch.distributed as dist
+    comm = None
+    try:
+        dist.init_process_group("gloo", rank=rank, world_size=world)
+        hjw = importlib.import_module("hephaestus-jit_b200")
+        sh = importlib.import_module("hephaestus-jit_b200.sharded")
+        dev = hjw.Device.cuda(rank % max(hjw.device_count(), 1))
+        comm = sh.Comm.local_from_torch(dev)
+        info = comm.info()
+        assert info["world"] == world and info["rank"] == rank and info["nccl"] == 0
+        assert info["peer_memory"] == (1 if world > 1 else 0)
+        globals()[body](rank, world, dev, comm, *args)
+        dev.sync()
+        dist.barrier()
+    except BaseException:  # noqa: BLE001 - reported to the parent, which fails the test
+        errq.put((rank, traceback.format_exc()))
+    finally:
+        try:
+            if comm is not None:
+                comm.destroy()
+            dist.destroy_process_group()
+        except Exception:
+            pass
+
+
+def _run(world, body, *args, timeout=600):
+    ctx = mp.get_context("spawn")
+    errq = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_entry, args=(r, world, port, body, args, errq)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(timeout)
+    hung = [p for p in procs if p.is_alive()]
+    for p in hung:
+        p.kill()
+    errors = []
+    while not errq.empty():
+        errors.append(errq.get())
+    assert not hung, f"{len(hung)} rank(s) did not finish within {timeout} s"
+    assert not errors, "\n".join(f"--- rank {r}\n{tb}" for r, tb in errors)
+    assert all(p.exitcode == 0 for p in procs), [p.exitcode for p in procs]
+
+
+# ---- bodies (run in every rank's process) ------------------------------------------------------------------
+def _device_ops(rank, world, dev, comm, n):
+    import oracle
+    sh = importlib.import_module("hephaestus-jit_b200.sharded")
+    rng = np.random.Generator(np.random.PCG64(7))     # every rank generates the whole array
+    u = rng.integers(0, 2**32, size=n, dtype=np.uint64).astype(np.uint32)
+    f = rng.random(n, dtype=np.float32)
+    s, e = sh.shard_bounds(n, world, rank)
+    nl = e - s
+    out1 = dev.create_buffer(8)
+    for rep in range(3):   # repeated exchanges alternate the mailbox parities
+        for op, ty, arr in ((hj.SUM, hj.U32, u), (hj.MAX, hj.U32, u), (hj.XOR, hj.U32, u), (hj.MIN, hj.F32, f)):
+            comm.reduce(op, ty, nl, dev.create_buffer_from_slice(arr[s:e]), out1)
+            assert out1.to_host(arr.dtype, 0, 1)[0] == oracle.reduce(op, ty, arr)[0], (op, ty)
+    comm.reduce(hj.SUM, hj.F32, nl, dev.create_buffer_from_slice(f[s:e]), out1)
+    exact = float(f.astype(np.float64).sum())
+    assert abs(float(out1.to_host(np.float32, 0, 1)[0]) - exact) <= 1e-5 * exact
+    # scan, materialised (12 B/elem) and with a deferred seed (8 B/elem, the exchange inside the scan kernel)
+    dst, seed = dev.create_buffer(4 * nl), dev.create_buffer(8)
+    src = dev.create_buffer_from_slice(u[s:e])
+    for inclusive in (True, False):
+        want = oracle.prefix_sum(oracle.U32, u, inclusive)[s:e]
+        comm.prefix_sum(hj.U32, nl, inclusive, src, dst)
+        assert np.array_equal(dst.to_host(np.uint32), want)
+        comm.prefix_sum_deferred(hj.U32, nl, inclusive, src, dst, seed)
+        local = dst.to_host(np.uint32)
+        off = seed.to_host(np.uint32, 0, 1)[0]
+        with np.errstate(over="ignore"):
+            assert off == np.uint32(u[:s].astype(np.uint64).sum() & 0xFFFFFFFF)
+            assert np.array_equal(local + off, want)
+        L = importlib.import_module("hephaestus-jit_b200._lib")
+        L.check(L.lib.hj_apply_seed(dev.handle, hj.U32, nl, dst.handle, seed.handle))
+        assert np.array_equal(dst.to_host(np.uint32), want)
+    # u64 / u8 deferred scans: two-word exchange payloads, narrow element types
+    u64 = rng.integers(0, 2**63, size=n, dtype=np.uint64)
+    d64 = dev.create_buffer(8 * nl)
+    comm.prefix_sum_deferred(hj.U64, nl, True, dev.create_buffer_from_slice(u64[s:e]), d64, seed)
+    with np.errstate(over="ignore"):
+        assert np.array_equal(d64.to_host(np.uint64) + seed.to_host(np.uint64, 0, 1)[0], np.cumsum(u64, dtype=np.uint64)[s:e])
+    # compress: per-rank segment with global indices, counts exchanged inside the kernel
+    for p in (0.4, 0.01, 0.97):
+        mask = (rng.random(n) < p).astype(np.uint8)
+        idx = dev.create_buffer_from_slice(np.full(nl, 0xDEADBEEF, np.uint32))
+        cnt, counts = dev.create_buffer(4), dev.create_buffer(4 * world)
+        comm.compress(nl, s, dev.create_buffer_from_slice(mask[s:e]), idx, cnt, counts)
+        gcnt, gidx = oracle.compress(mask)
+        c = counts.to_host(np.uint32)
+        off = int(c[:rank].sum())
+        assert int(cnt.to_host(np.uint32)[0]) == gcnt and int(c.sum()) == gcnt
+        got = idx.to_host(np.uint32)
+        assert np.array_equal(got[: int(c[rank])], gidx[off: off + int(c[rank])])
+        assert (got[int(c[rank]):] == 0xDEADBEEF).all()      # entries beyond the count are not touched
+    # histogram 2^16 bins: packed-16 ring + fold and exchange in one kernel; dst's own contents are kept
+    keys = rng.integers(0, 1 << 16, size=n).astype(np.uint32)
+    start = rng.integers(0, 100, size=1 << 16).astype(np.uint32)
+    for rep in range(2):
+        hist = dev.create_buffer_from_slice(start if rank == 0 else np.zeros(1 << 16, np.uint32))
+        comm.scatter_reduce(hj.SUM, hj.U32, nl, dev.create_buffer_from_slice(keys[s:e]), None, 1, hist, 1 << 16)
+        assert np.array_equal(hist.to_host(np.uint32), oracle.histogram_u32_mt(keys, 1 << 16) + start)
+    # a skewed histogram (every key equal: the sweep path) and an odd bin count
+    same = np.full(n, 12345, np.uint32)
+    hist = dev.create_buffer_from_slice(np.zeros(50001, np.uint32))
+    comm.scatter_reduce(hj.SUM, hj.U32, nl, dev.create_buffer_from_slice(same[s:e]), None, 1, hist, 50001)
+    want = np.zeros(50001, np.uint32)
+    want[12345] = n
+    assert np.array_equal(hist.to_host(np.uint32), want)
+
+
+def _traced_program(rank, world, dev, comm, n):
+    import oracle
+    tr = importlib.import_module("hephaestus-jit_b200.tr")
+    sh = importlib.import_module("hephaestus-jit_b200.sharded")
+    rng = np.random.Generator(np.random.PCG64(21))
+    x = (rng.random(n, dtype=np.float32) * 8 - 4).astype(np.float32)
+    u = rng.integers(0, 1 << 20, size=n).astype(np.uint32)
+    keys = rng.integers(0, 1 << 16, size=n).astype(np.uint32)
+    table = rng.integers(0, 1 << 30, size=4096).astype(np.uint32)
+    s, e = sh.shard_bounds(n, world, rank)
+
+    vx, vu, vk = tr.array_sharded(x, comm), tr.array_sharded(u, comm), tr.array_sharded(keys, comm)
+    vt = tr.array(table, dev)                                   # a replica: the gather table
+    assert vx.shard() == (s, e - s, False) and vt.shard() is None
+    # C2 chain + reduction of its result
+    t = vx.fma(tr.literal(1.5, hj.F32), tr.literal(0.25, hj.F32))
+    y = t.sin().select(vx.gt(tr.literal(0.0, hj.F32)), t.exp2())
+    y.schedule()
+    total = y.abs().reduce_max()
+    total.schedule()
+    # scan with consumers: the fused kernel behind it adds the deferred seed at load; Index is global
+    scan = vu.prefix_sum(True)
+    z = scan.add(tr.sized_index(n)).add(vt.gather(vu.and_(tr.literal(4095, hj.U32))))
+    z.schedule()
+    scan.schedule()
+    scan2 = vk.prefix_sum(False)    # never scheduled itself: lives and dies inside the graph
+    ssum = scan2.reduce_max()       # a device op on a deferred result: materialised first
+    ssum.schedule()
+    # compress of a traced mask, histogram-shaped scatter-reduce
+    mask = vu.and_(tr.literal(3, hj.U32)).eq(tr.literal(1, hj.U32))
+    count, index = mask.compress()
+    hist = tr.sized_literal(0, 1 << 16, hj.U32)
+    tr.sized_literal(1, n, hj.U32).scatter_reduce(hist, vk, hj.SUM)
+    hist.schedule()
+    g = tr.compile()
+    report = g.launch(dev, timed=True)
+    names = [p[0] for p in report.passes]
+    if world > 1:
+        assert any("deferred seed" in nm for nm in names), names
+    assert any(nm.startswith("Histogram") for nm in names) or n < (1 << 20), names
+
+    want_y = oracle.c2_chain(x)
+    assert y.shard() == (s, e - s, False)
+    assert np.allclose(y.to_vec(), want_y[s:e], rtol=4e-7, atol=1e-7)
+    assert float(total.item()) == float(np.abs(want_y).max()) or np.isclose(float(total.item()), float(np.abs(want_y).max()), rtol=4e-7)
+    want_scan = np.cumsum(u, dtype=np.uint32)
+    assert np.array_equal(scan.to_vec(np.uint32), want_scan[s:e])
+    with np.errstate(over="ignore"):
+        want_scan2 = np.cumsum(keys, dtype=np.uint32) - keys
+    assert int(ssum.item()) == int(want_scan2.max())
+    assert scan.shard() == (s, e - s, world > 1)      # still (local scan, offset) on more than one rank
+    with np.errstate(over="ignore"):
+        want_z = want_scan + np.arange(n, dtype=np.uint32) + table[u & 4095]
+    assert np.array_equal(z.to_vec(np.uint32), want_z[s:e])
+    m = ((u & 3) == 1).astype(np.uint8)
+    gcnt, gidx = oracle.compress(m)
+    assert int(count.to_vec(np.uint32)[0]) == gcnt
+    lcnt = int(m[s:e].sum())
+    off = int(m[:s].sum())
+    got = index.to_vec(np.uint32)
+    assert index.shard() == (s, e - s, False) and len(got) == e - s
+    assert np.array_equal(got[:lcnt], gidx[off: off + lcnt]) and (got[lcnt:] == 0).all()   # zero tail like the reference
+    assert np.array_equal(hist.to_vec(np.uint32), oracle.histogram_u32_mt(keys, 1 << 16))
+
+    # a second launch consumes results of the first: a deferred scan result as an input of a later graph
+    w = scan.add(tr.literal(7, hj.U32))
+    w.schedule()
+    tr.compile().launch(dev)
+    assert np.array_equal(w.to_vec(np.uint32), want_scan[s:e] + np.uint32(7))
+    scan.materialise()
+    assert scan.shard() == (s, e - s, False)
+    assert np.array_equal(scan.to_vec(np.uint32), want_scan[s:e])
+
+
+def _unsupported_shapes(rank, world, dev, comm, n):
+    tr = importlib.import_module("hephaestus-jit_b200.tr")
+    u = np.arange(n, dtype=np.uint32)
+    vu = tr.array_sharded(u, comm)
+    perm = tr.array((n - 1 - u).astype(np.uint32), dev)
+    # a sharded array read through a computed index: replicas only
+    bad = vu.gather(perm)
+    bad.schedule()
+    with pytest.raises(hj.HjError, match="computed index|replica"):
+        tr.compile().launch(dev)
+    # a plain scatter into a replica from a kernel over sharded data
+    dst = tr.sized_literal(0, 64, hj.U32)
+    dst.schedule()
+    tr.compile().launch(dev)
+    vu.scatter(dst, vu.and_(tr.literal(63, hj.U32)))
+    with pytest.raises(hj.HjError, match="replica"):
+        tr.compile().launch(dev)
+
+
+@pytest.mark.parametrize("world", [1, 2, 3])
+def test_sharded_device_ops_fused_exchange(world):
+    _run(world, "_device_ops", (1 << 21) + 77)
+
+
+@pytest.mark.parametrize("world", [1, 2, 3])
+def test_traced_program_over_sharded_arrays(world):
+    _run(world, "_traced_program", (1 << 21) + 13)
+
+
+def test_small_shards_take_the_unfused_paths():
+    _run(2, "_device_ops_small", 5003)
+
+
+def _device_ops_small(rank, world, dev, comm, n):
+    import oracle
+    sh = importlib.import_module("hephaestus-jit_b200.sharded")
+    rng = np.random.Generator(np.random.PCG64(3))
+    u = rng.integers(0, 2**32, size=n, dtype=np.uint64).astype(np.uint32)
+    mask = (rng.random(n) < 0.5).astype(np.uint8)
+    s, e = sh.shard_bounds(n, world, rank)
+    nl = e - s
+    dst, seed = dev.create_buffer(4 * nl), dev.create_buffer(8)
+    comm.prefix_sum_deferred(hj.U32, nl, True, dev.create_buffer_from_slice(u[s:e]), dst, seed)
+    with np.errstate(over="ignore"):
+        assert np.array_equal(dst.to_host(np.uint32) + seed.to_host(np.uint32, 0, 1)[0], oracle.prefix_sum(oracle.U32, u, True)[s:e])
+    idx, cnt, counts = dev.create_buffer_from_slice(np.zeros(nl, np.uint32)), dev.create_buffer(4), dev.create_buffer(4 * world)
+    comm.compress(nl, s, dev.create_buffer_from_slice(mask[s:e]), idx, cnt, counts)
+    gcnt, gidx = oracle.compress(mask)
+    c = counts.to_host(np.uint32)
+    assert int(cnt.to_host(np.uint32)[0]) == gcnt
+    assert np.array_equal(idx.to_host(np.uint32)[: int(c[rank])], gidx[int(c[:rank].sum()): int(c[:rank + 1].sum())])
+
+
+def test_shapes_that_do_not_shard_fail_loudly():
+    _run(2, "_unsupported_shapes", 1 << 16)
