@@ -5,30 +5,44 @@
 
 For N > 1 it is launched by torchrun (one rank per GPU); rank 0 prints ONE JSON line.
 
-Workload (BASELINE.json configs[1], "C2"): the fused elementwise chain
-    t = fma(x, 1.5, 0.25);  y = select(x > 0, sin(t), exp2(t))
-over 2^28 f32 per GPU, traced into one kernel, executed through the reference-facing boundary
-(hj_execute_graph: IR -> CUDA C++ -> NVRTC sm_100a cubin, cached by IR hash).  A "step" is one
-pass over the 2^28-element array.  Algorithmic bytes: 8 per element.
+Workload — the hot path BASELINE.json's metric names, "fused map / reduce / scan / compress", as ONE
+pass list handed to the reference-facing boundary (BackendDevice::execute_graph ->
+hj_execute_graph on one GPU, hj_execute_graph_sharded on N), at the sizes of BASELINE configs C2-C4:
 
-  value      GB/s of algorithmic bytes with inputs resident in HBM, K steps timed with CUDA
-             events on the stream the kernels run on, max over ranks (N ranks: weak scaling,
-             every rank owns its own 2^28 elements, Index is global = rank * 2^28 + i).
-  e2e        same metric through the C ABI with HOST buffers: every step uploads the input
-             from pinned host memory (hj_buffer_upload), runs the graph, and reads the full
-             result back (hj_buffer_to_host) inside the timed region.
-  roofline   of the fused kernel against the measured copy bandwidth (MEASURED_PEAKS.json).
-  cpu_baseline  the oracle's C restatement of the same chain on all host cores, bounded sample.
-  suite      the other hot-path kernels of BASELINE.json (C3 reduce, C4 scan + compress,
-             C5 histogram) at their named sizes, each with GB/s and fraction of the peak.
+    pass 0  Kernel     C2: t = fma(x, 1.5, 0.25); y = select(x > 0, sin(t), exp2(t)),  2^28 f32 (NVRTC)
+    pass 1  Reduce     C3: sum of 2^30 f32
+    pass 2  PrefixSum  C4: inclusive scan of 2^30 u32
+    pass 3  Compress   C4: 2^30-byte mask (p = 0.5) -> ascending u32 indices + count
 
-`--impl reference` times the reference's path on the host CPU.  The reference itself (nightly
-Rust + Vulkan on lavapipe) cannot be built or run in this image, so this arm
-runs the oracle port (oracle/hj_oracle.c) with all host threads on a bounded sample per step.
+A "step" is one launch of that list.  The GLOBAL array sizes are fixed: on N GPUs every array is
+split into N contiguous blocks (strong scaling), the kernel pass runs with Index = global index, the
+three device ops run their cross-GPU exchange INSIDE their kernels over peer memory (NVLink): partial
+sums folded in rank order, shard totals -> the scan's deferred seed, per-rank counts -> global count.
+Algorithmic bytes per step: 8 * 2^28 + 4 * 2^30 + 8 * 2^30 + (2^30 + 4 * count).
+
+  value       GB/s of algorithmic bytes, inputs resident in HBM, K steps between two CUDA events on
+              the launch stream, barrier + synchronize on both sides, max over ranks.
+  rooflines   one record per kernel of the step (average pass duration over K further steps, per-pass
+              CUDA events) plus, from the suite, histogram and gather; `roofline` is the record of
+              the kernel that takes the largest share of the step.
+  e2e         the same workload with HOST buffers through the C ABI: every step streams the inputs
+              from pinned host memory and the results back (hj_kernel_map_host, hj_reduce_host,
+              hj_prefix_sum_host, hj_compress_host: upload | kernel | download overlapped).
+  checks      every result of the timed step is verified on every rank (independent torch
+              computations, all-reduced); a wrong result makes the run exit non-zero.
+  cpu_baseline  (N = 1) the oracle's C restatement of the same four ops on all host cores, on a
+              bounded sample.
+  suite       the other kernels BASELINE.json names (reduce variants, compress densities, histogram,
+              gather, traced programs) at their sizes.
+
+`--impl reference` times the reference's path on the host CPU.  The reference itself (nightly Rust +
+Vulkan on lavapipe) cannot be built or run in this image, so this arm runs the oracle
+port (oracle/hj_oracle.c) with all host threads on a bounded sample of the same workload per step.
 """
 from __future__ import annotations
 
 import argparse
+import ctypes
 import importlib
 import json
 import os
@@ -41,9 +55,16 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+COLL_DEVICE = "cuda"  # where the tiny tensors of torch.distributed collectives live (cpu under gloo)
 METRIC = "GB/s & % of HBM roofline for fused map/reduce/scan/compress"
-LOG2N = 28
-BYTES_PER_ELEM = 8  # 1 f32 read + 1 f32 written
+LOG2_MAP, LOG2_OPS = 28, 30
+WORKLOAD = ("C2+C3+C4 as one pass list: fused chain fma -> sin/exp2 -> select over 2^28 f32 (one NVRTC kernel), "
+            "f32 sum over 2^30, inclusive u32 scan over 2^30, compress of a 2^30-byte mask (p=0.5)")
+
+
+def step_bytes(n_map: int, n_ops: int, count: int) -> dict:
+    """Algorithmic bytes of one step per kernel."""
+    return {"map": 8 * n_map, "reduce": 4 * n_ops, "scan": 8 * n_ops, "compress": n_ops + 4 * count}
 
 
 def measured_peak():
@@ -56,7 +77,7 @@ def measured_peak():
 
 
 def ncu_traffic():
-    """DRAM bytes per launch of the fused kernel from the committed ncu capture, or None."""
+    """DRAM bytes per launch from the committed ncu captures of this round (profiles/traffic.json)."""
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
             return json.load(f)
@@ -116,69 +137,106 @@ class ClockSampler(threading.Thread):
 
 
 # --------------------------------------------------------------------------------------------
-# reference arm: the oracle port on the host CPU
+# the CPU legs: the oracle port of the same four ops on the host cores (bounded sample)
 # --------------------------------------------------------------------------------------------
+
+CPU_LOG2_MAP, CPU_LOG2_OPS = 24, 26   # the sample keeps the workload's 1:4 proportion of map to device-op elements
+
+
+class CpuWorkload:
+    """The oracle's restatement of the step on a sample of 2^24 (map) / 2^26 (reduce, scan, compress)
+    elements.  The reduce follows the reference including its staging copy (reduce.rs:219-313)."""
+
+    def __init__(self):
+        import oracle
+        self.o = oracle
+        oracle.set_threads(os.cpu_count() or 1)  # torchrun exports OMP_NUM_THREADS=1: ask for every core
+        self.cores = oracle.get_threads()
+        rng = np.random.Generator(np.random.PCG64(0))
+        nm, no = 1 << CPU_LOG2_MAP, 1 << CPU_LOG2_OPS
+        self.x = (rng.random(nm, dtype=np.float32) * 8 - 4).astype(np.float32)
+        self.f = rng.random(no, dtype=np.float32)
+        self.u = rng.integers(0, 4, size=no).astype(np.uint32)
+        self.mask = (rng.random(no) < 0.5).astype(np.uint8)
+        self.index = np.zeros(no, np.uint32)
+        self.count = int(self.mask.sum())
+        self.bytes = sum(step_bytes(nm, no, self.count).values())
+        self.sample = (f"each step = 2^{CPU_LOG2_MAP} map + 2^{CPU_LOG2_OPS} reduce / scan / compress elements "
+                       f"(the workload's proportions at 1/16 of its size), oracle C port on {self.cores} OpenMP threads")
+
+    def step(self):
+        o = self.o
+        o.c2_chain(self.x, fast=True)
+        o.reduce(o.SUM, o.F32, self.f, faithful_copy=True)
+        o.prefix_sum_u32_mt(self.u, True)
+        o.compress(self.mask, self.index, mt=True)
+
+    def gbs(self, dt_s: float) -> float:
+        return self.bytes / dt_s / 1e9
+
+
+def config_dict(world: int) -> dict:
+    n_map, n_ops = 1 << LOG2_MAP, 1 << LOG2_OPS
+    return {
+        "workload": WORKLOAD,
+        "elements_global": {"map": n_map, "reduce": n_ops, "scan": n_ops, "compress": n_ops},
+        "bytes_per_element": {"map": 8, "reduce": 4, "scan": 8, "compress": "1 + 4p"},
+        "l2_policy": "every array of the step (>= 1 GiB / N per rank) is larger than the 126 MB L2; no flush needed",
+        "boundary": "hj_execute_graph (N=1) / hj_execute_graph_sharded (N>1), one call per step",
+        "parallelism": (f"strong scaling: every array split into {world} contiguous blocks; reduce = partials folded in rank "
+                        "order, scan = shard totals -> deferred seed, compress = per-rank counts -> global count, each "
+                        "exchanged inside the op's own kernel over NVLink peer memory (no NCCL call on the data path)")
+        if world > 1 else "1 GPU",
+    }
+
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    import oracle
-    oracle.set_threads(os.cpu_count() or 1)  # torchrun exports OMP_NUM_THREADS=1: ask for every core
-    cores = oracle.get_threads()
-    n = 1 << 24  # bounded sample of the 2^28-element workload per step
-    rng = np.random.Generator(np.random.PCG64(0))
-    x = (rng.random(n, dtype=np.float32) * 8 - 4).astype(np.float32)
+    w = CpuWorkload()
     for _ in range(max(args.warmup, 1)):
-        oracle.c2_chain(x, fast=True)
+        w.step()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        oracle.c2_chain(x, fast=True)
+        w.step()
     dt = (time.perf_counter() - t0) / args.steps
-    gbs = BYTES_PER_ELEM * n / dt / 1e9
-    sample = f"2^24 of the 2^28 elements per step, oracle C port (libm sinf/exp2f), {cores} OpenMP threads"
+    gbs = w.gbs(dt)
+    cfg = config_dict(args.gpus)  # the own arm's config, key for key; what one CPU step covers is in cpu_baseline.sample
     line = {
         "impl": "reference", "metric": METRIC, "value": gbs, "unit": "GB/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {
-            # the own arm's config (same workload, same metric and unit); what one CPU step covers is in `sample`
-            "workload": "C2: fused elementwise chain fma -> sin/exp2 -> select over 2^28 f32 per GPU, one NVRTC kernel",
-            "elements_per_gpu": 1 << 28, "bytes_per_element": BYTES_PER_ELEM,
-            "sample": "each step = 2^24 of the 2^28 elements on the host cores",
-            "note": "reference (nightly Rust + Vulkan/lavapipe) is not buildable in this image; oracle port timed instead"},
-        "cpu_baseline": {"value": gbs, "unit": "GB/s", "cores": cores, "kind": "port", "sample": sample},
+        "scaling": "strong", "vs_baseline": None, "dtype": "f32/u32/u8", "data": "synthetic",
+        "config": cfg,
+        "cpu_baseline": {"value": gbs, "unit": "GB/s", "cores": w.cores, "kind": "port", "sample": w.sample},
         "e2e": {"value": gbs, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
+        "note": "reference (nightly Rust + Vulkan/lavapipe) is not buildable in this image; oracle port timed instead",
     }
     print(json.dumps(line))
     return 0
 
-
-# --------------------------------------------------------------------------------------------
-# own arm
-# --------------------------------------------------------------------------------------------
 
 def cpu_baseline(check_inputs=None):
     """The one place of the own arm that executes anything under oracle/: times the CPU port on a
     bounded sample and, while it is at it, evaluates `check_inputs` ({name: f32 array}) so that the
     caller can compare the GPU results with them.  Returns (report, {name: oracle output})."""
     import oracle
-    oracle.set_threads(os.cpu_count() or 1)
-    cores = oracle.get_threads()
+    w = CpuWorkload()
     wants = {k: oracle.c2_chain(np.ascontiguousarray(v)) for k, v in (check_inputs or {}).items()}
-    n = 1 << 24
-    rng = np.random.Generator(np.random.PCG64(0))
-    x = (rng.random(n, dtype=np.float32) * 8 - 4).astype(np.float32)
-    oracle.c2_chain(x, fast=True)
+    w.step()
     reps, t0 = 0, time.perf_counter()
-    while time.perf_counter() - t0 < 5.0 or reps < 3:  # bounded: a few seconds of CPU work
-        oracle.c2_chain(x, fast=True)
+    while time.perf_counter() - t0 < 8.0 or reps < 3:  # bounded: a few seconds of CPU work
+        w.step()
         reps += 1
     dt = (time.perf_counter() - t0) / reps
-    return {"value": BYTES_PER_ELEM * n / dt / 1e9, "unit": "GB/s", "cores": cores, "kind": "port",
-            "sample": f"2^24 of the 2^28 elements, {reps} reps, oracle C port with libm sinf/exp2f on {cores} threads"}, wants
+    return {"value": w.gbs(dt), "unit": "GB/s", "cores": w.cores, "kind": "port",
+            "sample": f"{w.sample}; {reps} reps"}, wants
 
+
+# --------------------------------------------------------------------------------------------
+# own arm
+# --------------------------------------------------------------------------------------------
 
 def timed_events(torch, fn, iters, warmup):
     for _ in range(warmup):
@@ -194,7 +252,7 @@ def timed_events(torch, fn, iters, warmup):
     return ts[len(ts) // 2]
 
 
-def run_suite(torch, hj, dev, peak, world, rank, comm):
+def run_suite(torch, hj, dev, peak, world, rank):
     """Per-kernel GB/s at the sizes BASELINE.json names (per-GPU share of the array on N GPUs)."""
     out = {}
     g = torch.Generator(device="cuda").manual_seed(1234 + rank)
@@ -204,7 +262,8 @@ def run_suite(torch, hj, dev, peak, world, rank, comm):
 
     def entry(nbytes, ms, extra=None):
         gbs = nbytes / ms / 1e6
-        e = {"GB/s": round(gbs, 1), "frac_of_measured_peak": round(gbs / peak, 4), "ms": round(ms, 4)}
+        e = {"GB/s": round(gbs, 1), "frac_of_measured_peak": round(gbs / peak, 4), "ms": round(ms, 4),
+             "algorithmic_bytes": int(nbytes)}
         if extra:
             e.update(extra)
         return e
@@ -217,25 +276,28 @@ def run_suite(torch, hj, dev, peak, world, rank, comm):
     for name, op, ty, buf in (("C3 reduce sum f32 2^30", hj.SUM, hj.F32, bf), ("C3 reduce max f32 2^30", hj.MAX, hj.F32, bf),
                               ("C3 reduce sum u32 2^30", hj.SUM, hj.U32, bu), ("C3 reduce min u32 2^30", hj.MIN, hj.U32, bu)):
         ms = timed_events(torch, lambda: dev.reduce(op, ty, n30, buf, bo1), iters, 3)
-        out[name] = entry(4 * n30, ms, {"elements_per_s": n30 / ms * 1e3, "bytes_per_elem": 4})
+        out[name] = entry(4 * n30, ms, {"elements_per_s": n30 / ms * 1e3, "bytes_per_elem": 4, "kernel": "reduce_kernel"})
     ms = timed_events(torch, lambda: dev.prefix_sum(hj.U32, n30, True, bu, bon), iters, 3)
-    out["C4 inclusive scan u32 2^30"] = entry(8 * n30, ms, {"elements_per_s": n30 / ms * 1e3, "bytes_per_elem": 8})
+    out["C4 inclusive scan u32 2^30"] = entry(8 * n30, ms, {"elements_per_s": n30 / ms * 1e3, "bytes_per_elem": 8, "kernel": "scan_ring_kernel"})
     for p in (0.5, 0.01, 0.99):
         mask = (torch.rand(n30, device="cuda", generator=g) < p).to(torch.uint8)
         cnt = torch.zeros(1, device="cuda", dtype=torch.int32)
         bm, bc = wrap(mask), wrap(cnt)
         ms = timed_events(torch, lambda: dev.compress(n30, bc, bm, bon), iters, 3)
         c = int(cnt.item())
-        out[f"C4 compress p={p} 2^30"] = entry(n30 + 4 * c, ms, {"elements_per_s": n30 / ms * 1e3,
+        out[f"C4 compress p={p} 2^30"] = entry(n30 + 4 * c, ms, {"elements_per_s": n30 / ms * 1e3, "kernel": "compress_ring_kernel",
                                                                    "bytes_per_elem": round(1 + 4 * c / n30, 3)})
         del mask
+    del xf, xu, on
     n28 = (1 << 28) // world
     keys = torch.randint(0, 1 << 16, (n28,), device="cuda", generator=g, dtype=torch.int32)
     hist = torch.zeros(1 << 16, device="cuda", dtype=torch.int32)
     bk, bh = wrap(keys), wrap(hist)
     ms = timed_events(torch, lambda: dev.scatter_reduce(hj.SUM, hj.U32, n28, bk, None, 1, bh, 1 << 16), iters, 3)
+    ok = bool((hist.to(torch.int64).sum() == (iters + 3) * n28).item())
     out["C5 histogram 2^28 keys -> 2^16 bins"] = entry(4 * n28, ms, {"elements_per_s": n28 / ms * 1e3, "bytes_per_elem": 4,
-                                                                      "bound": "shared-memory atomic throughput, not HBM"})
+                                                                      "kernel": "hist_ring_kernel + hist_fold_exchange_kernel",
+                                                                      "bound": "shared-memory atomic throughput, not HBM", "sum_ok": ok})
     # C5b: gather (12 B/elem nominal: u32 index + f32 value + f32 out) and the traced Monte-Carlo loop
     del keys, hist
     idx = torch.randint(0, 1 << 20, (n28,), device="cuda", generator=g, dtype=torch.int32)
@@ -248,9 +310,11 @@ def run_suite(torch, hj, dev, peak, world, rank, comm):
             bi = wrap(idx)
         bt = wrap(table)
         ms = timed_events(torch, lambda: dev.gather(4, n28, bt, bi, bof), iters, 3)
+        ok = bool(torch.equal(outf[:4096], table[idx[:4096].long()]))
         out[f"C5 gather f32 2^28 indices, table 2^{log_t}"] = entry(12 * n28, ms, {
-            "elements_per_s": n28 / ms * 1e3, "bytes_per_elem": 12,
-            "bound": "L2-resident table: HBM streams of idx/out" if log_t == 20 else "DRAM sectors: 32 B fetched per 4 B used"})
+            "elements_per_s": n28 / ms * 1e3, "bytes_per_elem": 12, "kernel": "gather4_vec_kernel", "sample_ok": ok,
+            "sector_GB/s": round(40 * n28 / ms / 1e6, 1) if log_t == 28 else None,
+            "bound": "L2-resident table: HBM streams of idx/out" if log_t == 20 else "DRAM sectors: 32 B fetched per 4 B used (+ 8 B of streams)"})
         del table
     del idx, outf
     if world == 1:
@@ -298,17 +362,14 @@ def run_suite(torch, hj, dev, peak, world, rank, comm):
         except Exception as exc:  # an extra line of the suite must never take the bench down
             out["C4 traced mask.compress() p=0.5 2^28 (zero-fill + Compress passes)"] = {"error": str(exc)[:200]}
     if world > 1:
-        out["_note"] = f"per-GPU share (1/{world}) of each array, local kernels only; collectives reported under 'sharded'"
+        out["_note"] = f"per-GPU share (1/{world}) of each array, local kernels only; the exchanges are in the headline step and under 'sharded'"
     return out
 
 
-def run_sharded(torch, dist, hj, dev, peak, world, rank):
-    """The sharded ops of BASELINE.json (C3 / C4 / C5) INCLUDING their NCCL exchange: 2^30 (2^28 for
-    the histogram) elements split contiguously over the ranks, timed with CUDA events on the launch
-    stream, max over ranks.  GB/s = GLOBAL algorithmic bytes / time; the scan moves 12 B/elem when
-    sharded (shard totals first) but is credited with 8."""
-    sharded = importlib.import_module("hephaestus-jit_b200.sharded")
-    comm = sharded.Comm.from_torch(dev)
+def run_sharded_extras(torch, dist, hj, dev, comm, peak, world, rank):
+    """Sharded ops that are not part of the headline step, INCLUDING their exchange, each verified:
+    the C5 histogram (2^28 keys over the ranks, fold + all-reduce of the bins in one kernel), the
+    materialised scan (12 B/elem) next to the deferred one, and a traced program over sharded arrays."""
     out = {}
     g = torch.Generator(device="cuda").manual_seed(4321 + rank)
     wrap = lambda t: dev.wrap(t.data_ptr(), t.numel() * t.element_size())
@@ -326,35 +387,46 @@ def run_sharded(torch, dist, hj, dev, peak, world, rank):
             b.record()
         torch.cuda.synchronize()
         ms = sorted(a.elapsed_time(b) for a, b in ev)[iters // 2]
-        t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+        t = torch.tensor([ms], device=COLL_DEVICE, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    def entry(nbytes_global, ms):
+    def entry(nbytes_global, ms, ok):
         gbs = nbytes_global / ms / 1e6
-        return {"GB/s": round(gbs, 1), "frac_of_measured_peak_x_gpus": round(gbs / (peak * world), 4), "ms": round(ms, 4)}
+        return {"GB/s": round(gbs, 1), "frac_of_measured_peak_x_gpus": round(gbs / (peak * world), 4), "ms": round(ms, 4),
+                "check": bool(ok)}
 
-    xf = torch.rand(n30, device="cuda", generator=g, dtype=torch.float32)
-    xu = torch.randint(0, 4, (n30,), device="cuda", generator=g, dtype=torch.int32)
-    o1 = torch.zeros(16, device="cuda", dtype=torch.float32)
-    on = torch.empty(n30, device="cuda", dtype=torch.int32)
-    bf, bu, bo1, bon = wrap(xf), wrap(xu), wrap(o1), wrap(on)
-    out["C3 sharded reduce sum f32 2^30 + all-gather"] = entry(4 * n30 * world, timed(lambda: comm.reduce(hj.SUM, hj.F32, n30, bf, bo1)))
-    out["C3 sharded reduce max u32 2^30 + all-gather"] = entry(4 * n30 * world, timed(lambda: comm.reduce(hj.MAX, hj.U32, n30, bu, bo1)))
-    out["C4 sharded inclusive scan u32 2^30 (totals pass + all-gather + seeded scan)"] = entry(
-        8 * n30 * world, timed(lambda: comm.prefix_sum(hj.U32, n30, True, bu, bon)))
-    mask = (torch.rand(n30, device="cuda", generator=g) < 0.5).to(torch.uint8)
-    cnt = torch.zeros(1, device="cuda", dtype=torch.int32)
-    counts = torch.zeros(world, device="cuda", dtype=torch.int32)
-    bm, bc, bcs = wrap(mask), wrap(cnt), wrap(counts)
-    ms = timed(lambda: comm.compress(n30, (rank * n30) & 0xFFFFFFFF, bm, bon, bc, bcs))
-    out["C4 sharded compress p=0.5 2^30 + all-gather of counts"] = entry(n30 * world + 4 * int(cnt.item()), ms)
+    def all_true(flag: bool) -> bool:
+        t = torch.tensor([1 if flag else 0], device=COLL_DEVICE, dtype=torch.int32)
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        return bool(t.item())
+
     keys = torch.randint(0, 1 << 16, (n28,), device="cuda", generator=g, dtype=torch.int32)
     hist = torch.zeros(1 << 16, device="cuda", dtype=torch.int32)
     bk, bh = wrap(keys), wrap(hist)
-    out["C5 sharded histogram 2^28 keys -> 2^16 bins + all-reduce"] = entry(
-        4 * n28 * world, timed(lambda: comm.scatter_reduce(hj.SUM, hj.U32, n28, bk, None, 1, bh, 1 << 16)))
-    comm.destroy()
+
+    def hist_step():
+        hist.zero_()
+        comm.scatter_reduce(hj.SUM, hj.U32, n28, bk, None, 1, bh, 1 << 16)
+
+    ms = timed(hist_step)
+    want = torch.bincount(keys.long(), minlength=1 << 16).to(COLL_DEVICE)
+    dist.all_reduce(want)
+    out["C5 sharded histogram 2^28 keys -> 2^16 bins (ring + fold/exchange kernel, incl. 256 KiB memset)"] = entry(
+        4 * n28 * world, ms, all_true(bool(torch.equal(hist.long().to(COLL_DEVICE), want))))
+    del keys, hist, want
+    xu = torch.randint(0, 4, (n30,), device="cuda", generator=g, dtype=torch.int32)
+    on = torch.empty(n30, device="cuda", dtype=torch.int32)
+    bu, bon = wrap(xu), wrap(on)
+    ms = timed(lambda: comm.prefix_sum(hj.U32, n30, True, bu, bon))
+    tot = xu.sum(dtype=torch.int64).reshape(1).to(COLL_DEVICE)
+    tots = [torch.zeros_like(tot) for _ in range(world)]
+    dist.all_gather(tots, tot)
+    upto = int(sum(int(t.item()) for t in tots[: rank + 1]) & 0xFFFFFFFF)
+    ok = (int(on[-1].item()) & 0xFFFFFFFF) == upto
+    out["C4 sharded inclusive scan u32 2^30, MATERIALISED (totals pass + seeded scan: 12 B/elem moved, 8 credited)"] = entry(
+        8 * n30 * world, ms, all_true(ok))
+    del xu, on
     return out
 
 
@@ -371,41 +443,76 @@ def run_own(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    # HJ_BENCH_SHARE_GPU=1 (development aid): all ranks on GPU 0, torch.distributed over gloo and the
+    # NCCL-free communicator — the functional path of an N-rank run on a one-GPU box (timings are
+    # meaningless there: the ranks' kernels are time-sliced)
+    share_gpu = world > 1 and os.environ.get("HJ_BENCH_SHARE_GPU") == "1"
+    if share_gpu:
+        local_rank = 0
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        if share_gpu:
+            dist.init_process_group("gloo")
+        else:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     torch.cuda.set_device(local_rank)
+    global COLL_DEVICE
+    COLL_DEVICE = "cpu" if share_gpu else "cuda"
 
     hj = importlib.import_module("hephaestus-jit_b200")  # raises if libhj_b200.so is missing
     irm = importlib.import_module("hephaestus-jit_b200.ir")
+    L = importlib.import_module("hephaestus-jit_b200._lib")
+    sharded = importlib.import_module("hephaestus-jit_b200.sharded")
     dev = hj.Device.cuda(local_rank)
     stream = torch.cuda.Stream()
     torch.cuda.set_stream(stream)
     dev.set_stream(stream.cuda_stream)  # kernels and torch's timing events share one stream
+    comm = (sharded.Comm.local_from_torch(dev) if share_gpu else sharded.Comm.from_torch(dev)) if world > 1 else None
+    comm_info = comm.info() if comm else None
+
+    def all_true(flag: bool) -> bool:
+        if world == 1:
+            return bool(flag)
+        t = torch.tensor([1 if flag else 0], device=COLL_DEVICE, dtype=torch.int32)
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        return bool(t.item())
 
     peak, peak_src = measured_peak()
-    n = 1 << LOG2N
-    nbytes_step = BYTES_PER_ELEM * n
+    n_map_g, n_ops_g = 1 << LOG2_MAP, 1 << LOG2_OPS
+    m0, m1 = sharded.shard_bounds(n_map_g, world, rank)
+    o0, o1 = sharded.shard_bounds(n_ops_g, world, rank)
+    n_map, n_ops = m1 - m0, o1 - o0
 
-    # synthetic input, resident in HBM: f32 uniform [-4, 4), seeded
+    # synthetic inputs, resident in HBM, seeded: this rank's blocks of the global arrays
     g = torch.Generator(device="cuda").manual_seed(rank)
-    x = torch.rand(n, device="cuda", generator=g, dtype=torch.float32) * 8 - 4
+    x = torch.rand(n_map, device="cuda", generator=g, dtype=torch.float32) * 8 - 4
+    f = torch.rand(n_ops, device="cuda", generator=g, dtype=torch.float32)
+    u = torch.randint(0, 4, (n_ops,), device="cuda", generator=g, dtype=torch.int32)
+    mask = (torch.rand(n_ops, device="cuda", generator=g) < 0.5).to(torch.uint8)
     y = torch.empty_like(x)
-    bx = dev.wrap(x.data_ptr(), 4 * n)
-    by = dev.wrap(y.data_ptr(), 4 * n)
+    s_out = torch.zeros(4, device="cuda", dtype=torch.float32)
+    scan = torch.empty_like(u)
+    seed = torch.zeros(4, device="cuda", dtype=torch.int32)
+    index = torch.zeros(n_ops, device="cuda", dtype=torch.int32)
+    count = torch.zeros(4, device="cuda", dtype=torch.int32)
+    wrap = lambda t: dev.wrap(t.data_ptr(), t.numel() * t.element_size())
+    env = [wrap(t) for t in (x, y, f, s_out, u, scan, mask, index, count)]
+    b_seed = wrap(seed)
 
-    # the graph Graph::launch hands to BackendDevice::execute_graph for this trace: one Kernel pass
+    # the pass list Graph::launch hands to BackendDevice::execute_graph for this program
     ir = irm.c2_chain_ir()
-    passes = [{"kind": hj.PASS_KERNEL, "resources": [0, 1], "ir": ir, "size": n}]
-    descs = [(n, hj.F32, 4), (n, hj.F32, 4)]
+    passes = [{"kind": hj.PASS_KERNEL, "resources": [0, 1], "ir": ir, "size": n_map_g},
+              {"kind": hj.PASS_REDUCE, "arg": hj.SUM, "resources": [3, 2]},
+              {"kind": hj.PASS_PREFIX_SUM, "arg": 1, "resources": [5, 4]},
+              {"kind": hj.PASS_COMPRESS, "resources": [7, 8, 6]}]
+    descs = [(n_map_g, hj.F32, 4), (n_map_g, hj.F32, 4), (n_ops_g, hj.F32, 4), (1, hj.F32, 4), (n_ops_g, hj.U32, 4),
+             (n_ops_g, hj.U32, 4), (n_ops_g, hj.BOOL, 1), (n_ops_g, hj.U32, 4), (1, hj.U32, 4)]
+    S, R = L.RES_SHARDED, L.RES_REPLICATED
+    placement = [S, S, S, R, S, S, S, S, R]
+    seeds = [None, None, None, None, None, b_seed, None, None, None]
+    graph = hj.PreparedGraph(dev, passes, env, descs, comm, placement if comm else None, seeds if comm else None)
     kernel = dev.kernel(ir)  # compile outside the timed region (cached by IR hash afterwards)
-    index_base = (rank * n) & 0xFFFFFFFF
-
-    def step():
-        if world > 1:
-            dev.launch(kernel, n, [bx, by], index_base=index_base)  # global Index on a shard
-        else:
-            dev.execute_graph(passes, [bx, by], descs)
+    step = graph.run
 
     for _ in range(max(args.warmup, 3)):
         step()
@@ -417,12 +524,9 @@ def run_own(args):
     sampler = ClockSampler(local_rank)
     sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    per = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     e0.record()
-    for a, b in per:
-        a.record()
+    for _ in range(args.steps):
         step()
-        b.record()
     e1.record()
     torch.cuda.synchronize()
     if world > 1:
@@ -430,141 +534,249 @@ def run_own(args):
     total_ms = e0.elapsed_time(e1)
     launches = dev.launch_count() - launches0
     # keep the sampler alive long enough to have seen the load even for very short runs
-    if total_ms < 50:
+    if total_ms < 300:
         t_end = time.perf_counter() + 0.3
         while time.perf_counter() < t_end:
             step()
         torch.cuda.synchronize()
     clocks = sampler.stop()
-    kernel_ms = float(np.mean([a.elapsed_time(b) for a, b in per]))
-
     if world > 1:
-        t = torch.tensor([total_ms], device="cuda", dtype=torch.float64)
+        t = torch.tensor([total_ms], device=COLL_DEVICE, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         total_ms = float(t.item())
     ms_per_step = total_ms / args.steps
-    value = world * nbytes_step / (ms_per_step * 1e-3) / 1e9
 
-    # ---- correctness spot check (outside the timed region): samples for the oracle, which only the
-    # cpu_baseline leg below executes
+    # ---- every result of the step, verified on every rank with independent torch computations
+    checks = {}
+    count_g = int(count[0].item())
+    local_cnt = mask.sum(dtype=torch.int64).reshape(1).to(COLL_DEVICE)
+    cnts = [torch.zeros_like(local_cnt) for _ in range(world)]
+    if world > 1:
+        dist.all_gather(cnts, local_cnt)
+    else:
+        cnts = [local_cnt]
+    lc = int(local_cnt.item())
+    checks["compress_count"] = count_g == sum(int(c.item()) for c in cnts)
+    pos = torch.nonzero(mask[: 1 << 22]).flatten()[:4096].to(torch.int64) + o0   # first selected elements of the block
+    tailpos = torch.nonzero(mask[-(1 << 22):]).flatten()[-4096:].to(torch.int64) + (o1 - (1 << 22))
+    checks["compress_indices"] = bool(torch.equal(index[: pos.numel()].to(torch.int64) & 0xFFFFFFFF, pos)) and bool(
+        torch.equal(index[lc - tailpos.numel(): lc].to(torch.int64) & 0xFFFFFFFF, tailpos)) and bool(
+        (index[1:lc] > index[: lc - 1]).all().item() if o1 <= (1 << 31) else True)
+    exact = f.sum(dtype=torch.float64).reshape(1).to(COLL_DEVICE)
+    if world > 1:
+        dist.all_reduce(exact)
+    checks["reduce_sum_rel_1e-5"] = abs(float(s_out[0].item()) - float(exact.item())) <= 1e-5 * float(exact.item())
+    tot = u.sum(dtype=torch.int64).reshape(1).to(COLL_DEVICE)
+    tots = [torch.zeros_like(tot) for _ in range(world)]
+    if world > 1:
+        dist.all_gather(tots, tot)
+    else:
+        tots = [tot]
+    before = sum(int(t.item()) for t in tots[:rank]) & 0xFFFFFFFF
+    deferred = graph.deferred()[5]
+    seed_v = int(seed[0].item()) & 0xFFFFFFFF if deferred else 0
+    checks["scan_seed"] = (seed_v == before) if deferred else True
+    off = before if deferred else 0   # a materialised scan already carries the offset
+    sl = slice(n_ops - (1 << 22), n_ops)
+    want_tail = (torch.cumsum(u[sl].to(torch.int64), 0) + (int(tot.item()) - int(u[sl].sum(dtype=torch.int64).item())) + before) & 0xFFFFFFFF
+    got_tail = ((scan[sl].to(torch.int64) & 0xFFFFFFFF) + off) & 0xFFFFFFFF
+    want_head = (torch.cumsum(u[: 1 << 22].to(torch.int64), 0) + before) & 0xFFFFFFFF
+    got_head = ((scan[: 1 << 22].to(torch.int64) & 0xFFFFFFFF) + off) & 0xFFFFFFFF
+    checks["scan_bit_exact_head_and_tail"] = bool(torch.equal(got_tail, want_tail)) and bool(torch.equal(got_head, want_head))
+    t_ = torch.addcmul(torch.full_like(x[: 1 << 20], 0.25), x[: 1 << 20], torch.full_like(x[: 1 << 20], 1.5))
+    want_y = torch.where(x[: 1 << 20] > 0, torch.sin(t_), torch.exp2(t_))
+    checks["map_vs_torch_rtol_2e-6"] = bool(torch.allclose(y[: 1 << 20], want_y, rtol=2e-6, atol=1e-6))
+    checks = {k: all_true(v) for k, v in checks.items()}
+    sharded_check = all(checks.values())
+
+    by = step_bytes(n_map_g, n_ops_g, count_g)
+    bytes_step = sum(by.values())
+    value = bytes_step / (ms_per_step * 1e-3) / 1e9
+
+    # ---- per-pass durations: K further steps with per-pass CUDA events (hj_report)
+    acc = [0.0] * 4
+    names = [""] * 4
+    reps_timed = max(3, min(args.steps, 20))
+    for _ in range(reps_timed):
+        for i, (nm, _s, dur) in enumerate(graph.run(timed=True)):
+            acc[i] += dur
+            names[i] = nm
+    pass_us = [a / reps_timed for a in acc]
+    if world > 1:
+        t = torch.tensor(pass_us, device=COLL_DEVICE, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        pass_us = [float(v) for v in t.tolist()]
+    traffic = ncu_traffic()
+    kernel_names = ["hj_kernel_vec (NVRTC, C2 IR)", "reduce_kernel", "scan_ring_kernel", "compress_ring_kernel"]
+    keys_ = ["map", "reduce", "scan", "compress"]
+    rooflines = []
+    for i, k in enumerate(keys_):
+        per_gpu = by[k] / world
+        ach = per_gpu / (pass_us[i] * 1e-6) / 1e9
+        rooflines.append({"kernel": kernel_names[i], "pass": names[i], "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s",
+                          "frac": ach / peak, "frac_of_8TBps_nominal": ach / 8000.0, "kernel_ms": pass_us[i] / 1e3,
+                          "algorithmic_bytes_per_launch": per_gpu, "share_of_step": pass_us[i] / sum(pass_us),
+                          "traffic": traffic.get(k + "_dram_bytes_per_launch") if world == 1 else None,
+                          "includes_exchange": world > 1 and k != "map"})
+    dominant = max(rooflines, key=lambda r: r["kernel_ms"])
+
+    # correctness sample for the oracle (executed in the cpu_baseline leg below, rank 0)
     check_in, check_got = {}, {}
     if rank == 0:
         m = 1 << 16
         check_in["resident"], check_got["resident"] = x[:m].cpu().numpy(), y[:m].cpu().numpy()
 
-    # ---- end-to-end through the C ABI with HOST buffers (pinned), rank-local.  Two public paths:
-    #  (a) pipelined: hj_kernel_map_host streams chunks through upload / kernel / download streams
-    #      (the headline e2e: every input byte crosses PCIe in, every output byte out, per step);
-    #  (b) blocking, the reference's own call sequence: upload -> execute_graph -> to_host.
-    import ctypes
-    L = importlib.import_module("hephaestus-jit_b200._lib")
-    hx, hy = ctypes.c_void_p(), ctypes.c_void_p()
-    L.check(L.lib.hj_host_alloc(4 * n, ctypes.byref(hx)))
-    L.check(L.lib.hj_host_alloc(4 * n, ctypes.byref(hy)))
-    host_x = np.ctypeslib.as_array(ctypes.cast(hx, ctypes.POINTER(ctypes.c_float)), shape=(n,))
-    host_y = np.ctypeslib.as_array(ctypes.cast(hy, ctypes.POINTER(ctypes.c_float)), shape=(n,))
-    host_x[:] = np.random.Generator(np.random.PCG64(rank)).random(n, dtype=np.float32) * 8 - 4
-    e2e_steps = max(3, min(args.steps, 10))
-
-    def e2e_pipelined():
-        dev.map_host(kernel, n, [hx.value, hy.value], 1 << 23)
-
-    dx, dy = dev.create_buffer(4 * n), dev.create_buffer(4 * n)
-
-    def e2e_blocking():
-        L.check(L.lib.hj_buffer_upload(dx.handle, 0, hx, 4 * n))            # H2D, pinned source
-        dev.execute_graph(passes, [dx, dy], descs)
-        L.check(L.lib.hj_buffer_to_host(dy.handle, 0, 4 * n, hy))           # D2H, blocks until visible
-
-    def time_e2e(fn):
-        fn()
-        if world > 1:
-            dist.barrier()
-        t0 = time.perf_counter()
-        for _ in range(e2e_steps):
-            fn()
-        dev.sync()
-        dt = (time.perf_counter() - t0) / e2e_steps
-        if world > 1:
-            t = torch.tensor([dt], device="cuda", dtype=torch.float64)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            dt = float(t.item())
-        return dt
-
-    launches_e2e0 = dev.launch_count()
-    pipe_s = time_e2e(e2e_pipelined)
-    launches_e2e = (dev.launch_count() - launches_e2e0) // (e2e_steps + 1)
-    if rank == 0:
-        m = 1 << 16
-        check_in["e2e"], check_got["e2e"] = host_x[-m:].copy(), host_y[-m:].copy()
-    block_s = time_e2e(e2e_blocking)
-    e2e = {"value": world * nbytes_step / pipe_s / 1e9, "unit": "GB/s", "h2d_bytes_per_step": 4 * n,
-           "d2h_bytes_per_step": 4 * n, "ms_per_step": pipe_s * 1e3, "steps": e2e_steps,
-           "path": "pinned host arrays -> hj_kernel_map_host (8 Mi-element chunks, ramped at both ends: upload | kernel | download streams)",
-           "kernel_launches_per_step": int(launches_e2e), "oracle_check": None,
-           "blocking_path": {"value": world * nbytes_step / block_s / 1e9, "ms_per_step": block_s * 1e3,
-                             "path": "hj_buffer_upload (pinned) -> hj_execute_graph -> hj_buffer_to_host"}}
-    L.lib.hj_host_free(hx)
-    L.lib.hj_host_free(hy)
-    del dx, dy
+    # ---- end to end with HOST buffers (pinned), through the C ABI's host-streaming entry points
+    e2e = run_e2e(torch, dist, hj, L, dev, comm, kernel, world, rank, x, f, u, mask, count_g, args, all_true)
 
     suite = None
-    shard_suite = None
+    extras = None
     if not args.no_suite:
-        del x, y
+        del x, y, f, u, mask, scan, index, env, graph
         torch.cuda.empty_cache()
-        suite = run_suite(torch, hj, dev, peak, world, rank, None)
+        suite = run_suite(torch, hj, dev, peak, world, rank)
+        for name, key, kern in (("C5 histogram 2^28 keys -> 2^16 bins", "histogram", None),
+                                ("C5 gather f32 2^28 indices, table 2^28", "gather_dram", None),
+                                ("C5 gather f32 2^28 indices, table 2^20", "gather_l2", None)):
+            e = suite.get(name)
+            if e and "GB/s" in e:
+                rooflines.append({"kernel": e.get("kernel"), "pass": name, "bound": "hbm" if key != "histogram" else "smem-atomics/hbm",
+                                  "achieved": e["GB/s"], "peak": peak, "unit": "GB/s", "frac": e["GB/s"] / peak,
+                                  "kernel_ms": e["ms"], "algorithmic_bytes_per_launch": e["algorithmic_bytes"],
+                                  "traffic": traffic.get(key + "_dram_bytes_per_launch") if world == 1 else None,
+                                  "sector_GB/s": e.get("sector_GB/s")})
         if world > 1:
             torch.cuda.empty_cache()
-            shard_suite = run_sharded(torch, dist, hj, dev, peak, world, rank)
+            extras = run_sharded_extras(torch, dist, hj, dev, comm, peak, world, rank)
+            sharded_check = sharded_check and all(v.get("check", True) for v in extras.values())
 
     if rank == 0:
-        cpu_report, wants = cpu_baseline(check_in)
+        cpu_report, wants = (cpu_baseline(check_in) if world == 1 else (None, {}))
         ok = {k: bool(np.allclose(check_got[k], wants[k], rtol=4e-7, atol=1e-7)) for k in wants}
-        check, e2e["oracle_check"] = ok.get("resident"), ok.get("e2e")
-        achieved = nbytes_step / (kernel_ms * 1e-3) / 1e9
-        traffic = ncu_traffic().get("fused_c2_kernel_dram_bytes_per_launch")
         line = {
             "metric": METRIC, "value": value, "unit": "GB/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {
-                "workload": "C2: fused elementwise chain fma -> sin/exp2 -> select over 2^28 f32 per GPU, one NVRTC kernel",
-                "elements_per_gpu": n, "bytes_per_element": BYTES_PER_ELEM,
-                "l2_policy": "inputs (1 GiB in + 1 GiB out per step) are larger than the 126 MB L2; no flush needed",
-                "boundary": "hj_execute_graph (N=1) / hj_kernel_launch with index_base = rank*2^28 (N>1)",
-                "parallelism": f"{world} independent shards, no data-path collective",
-            },
-            "elements_per_s": world * n / (ms_per_step * 1e-3),
+            "scaling": "strong", "vs_baseline": None, "dtype": "f32/u32/u8", "data": "synthetic",
+            "config": config_dict(world),
+            "algorithmic_bytes_per_step": by,
             "frac_of_measured_peak": value / (world * peak),
             "frac_of_8TBps_nominal": value / (world * 8000.0),
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                         "kernel": "hj_kernel_vec (NVRTC, C2 IR)", "kernel_ms": kernel_ms,
-                         "algorithmic_bytes_per_launch": nbytes_step},
+            "roofline": dict(dominant, peak_source=peak_src),
+            "rooflines": rooflines,
             "cpu_baseline": cpu_report,
             "e2e": e2e,
             "gpu_launches": int(launches),
             "clocks": clocks,
-            "oracle_check": check,
+            "sharded_check": sharded_check,
+            "checks": checks,
+            "oracle_check": ok.get("resident"),
+            "comm": comm_info,
             "kernel_cache": dev.kernel_cache_stats(),
         }
         if suite is not None:
             line["suite"] = suite
-        if shard_suite is not None:
-            line["sharded"] = shard_suite
+        if extras is not None:
+            line["sharded"] = extras
         sys.stdout.flush()
         os.write(json_fd, (json.dumps(line) + "\n").encode())
     if world > 1:
         dist.barrier()
+        comm.destroy()
         dist.destroy_process_group()
-    return 0
+    return 0 if sharded_check else 1
+
+
+def run_e2e(torch, dist, hj, L, dev, comm, kernel, world, rank, x, f, u, mask, count_g, args, all_true):
+    """The step with HOST buffers: every rank streams its blocks from pinned host memory through the
+    GPU and the results back (map: y; reduce: the sum; scan: the scanned block; compress: the indices
+    + count), then the ranks exchange the three scalars.  Timed with the host clock around the calls
+    (they return when the results are in host memory), max over ranks."""
+    n_map, n_ops = x.numel(), f.numel()
+    sizes = {"hx": 4 * n_map, "hy": 4 * n_map, "hf": 4 * n_ops, "hu": 4 * n_ops, "hscan": 4 * n_ops, "hmask": n_ops,
+             "hidx": 4 * n_ops}
+    host = {}
+    try:
+        for k, nb in sizes.items():
+            p = ctypes.c_void_p()
+            L.check(L.lib.hj_host_alloc(nb, ctypes.byref(p)))
+            host[k] = p
+        # fill the pinned inputs from the resident synthetic tensors
+        for k, t in (("hx", x), ("hf", f), ("hu", u), ("hmask", mask)):
+            bw = dev.wrap(t.data_ptr(), t.numel() * t.element_size())
+            L.check(L.lib.hj_buffer_to_host(bw.handle, 0, t.numel() * t.element_size(), host[k]))
+        one = dev.create_buffer(16)
+        seed_b, dummy = dev.create_buffer(16), dev.create_buffer(16)
+        scalars = {}
+
+        def step():
+            dev.map_host(kernel, n_map, [host["hx"].value, host["hy"].value], 1 << 23)
+            s = dev.reduce_host(hj.SUM, hj.F32, n_ops, host["hf"].value)
+            dev.prefix_sum_host(hj.U32, n_ops, True, host["hu"].value, host["hscan"].value)
+            c = dev.compress_host(n_ops, host["hmask"].value, host["hidx"].value, (rank * n_ops) & 0xFFFFFFFF)
+            if comm is not None:   # the three scalars that cross the fabric
+                one.upload(np.array([s], np.float32))
+                comm.reduce(hj.SUM, hj.F32, 1, one, one)
+                s = one.to_host(np.float32, 0, 1)[0]
+                last = np.ctypeslib.as_array(ctypes.cast(host["hscan"], ctypes.POINTER(ctypes.c_uint32)), shape=(n_ops,))[-1]
+                dummy.upload(np.array([last], np.uint32))
+                comm.prefix_sum_deferred(hj.U32, 1, True, dummy, one, seed_b)
+                scalars["seed"] = int(seed_b.to_host(np.uint32, 0, 1)[0])
+                one.upload(np.array([c], np.uint32))
+                comm.reduce(hj.SUM, hj.U32, 1, one, one)
+                c = int(one.to_host(np.uint32, 0, 1)[0])
+            scalars["sum"], scalars["count"] = float(s), int(c)
+
+        e2e_steps = max(2, min(args.steps, 4))
+        step()
+        if world > 1:
+            dist.barrier()
+        launches0 = dev.launch_count()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            step()
+        dev.sync()
+        dt = (time.perf_counter() - t0) / e2e_steps
+        launches = (dev.launch_count() - launches0) // e2e_steps
+        if world > 1:
+            t = torch.tensor([dt], device=COLL_DEVICE, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        # verify what arrived in host memory
+        hy = np.ctypeslib.as_array(ctypes.cast(host["hy"], ctypes.POINTER(ctypes.c_float)), shape=(n_map,))
+        hscan = np.ctypeslib.as_array(ctypes.cast(host["hscan"], ctypes.POINTER(ctypes.c_uint32)), shape=(n_ops,))
+        hidx = np.ctypeslib.as_array(ctypes.cast(host["hidx"], ctypes.POINTER(ctypes.c_uint32)), shape=(n_ops,))
+        m = 1 << 20
+        xs = x[-m:]
+        t_ = torch.addcmul(torch.full_like(xs, 0.25), xs, torch.full_like(xs, 1.5))
+        want_y = torch.where(xs > 0, torch.sin(t_), torch.exp2(t_)).cpu().numpy()
+        ok = bool(np.allclose(hy[-m:], want_y, rtol=2e-6, atol=1e-6))
+        ok = ok and bool(np.array_equal(hscan[-m:], (torch.cumsum(u.to(torch.int64), 0)[-m:] & 0xFFFFFFFF).cpu().numpy().astype(np.uint32)))
+        lc = int(mask.sum().item())
+        want_idx = (torch.nonzero(mask[-m:]).flatten().to(torch.int64) + (rank * n_ops + n_ops - m)).cpu().numpy().astype(np.uint32)
+        ok = ok and bool(np.array_equal(hidx[lc - want_idx.size: lc], want_idx)) and scalars["count"] == count_g
+        exact = f.sum(dtype=torch.float64).reshape(1).to(COLL_DEVICE)
+        if world > 1:
+            dist.all_reduce(exact)
+        ok = ok and abs(scalars["sum"] - float(exact.item())) <= 1e-5 * float(exact.item())
+        ok = all_true(ok)
+        by = step_bytes(n_map * world, n_ops * world, count_g)
+        h2d = world * (4 * n_map + 4 * n_ops + 4 * n_ops + n_ops)
+        d2h = world * (4 * n_map + 4 * n_ops) + 4 * count_g + 8 * world
+        return {"value": sum(by.values()) / dt / 1e9, "unit": "GB/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                "ms_per_step": dt * 1e3, "steps": e2e_steps, "kernel_launches_per_step": int(launches), "check": ok,
+                "pcie_GB/s_each_way": {"h2d": h2d / world / dt / 1e9, "d2h": d2h / world / dt / 1e9},
+                "path": "pinned host arrays -> hj_kernel_map_host + hj_reduce_host + hj_prefix_sum_host + hj_compress_host "
+                        "(chunks of 2^23-2^24 elements: upload | kernel | download streams)" +
+                        (" + hj_sharded_reduce / prefix_sum_deferred of the three per-rank scalars" if comm is not None else "")}
+    finally:
+        for p in host.values():
+            L.lib.hj_host_free(p)
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="own", choices=["own", "reference"])
     ap.add_argument("--no-suite", action="store_true")

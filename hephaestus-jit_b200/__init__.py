@@ -214,6 +214,28 @@ class Device:
         arr = (ctypes.c_void_p * max(len(ptrs), 1))(*ptrs)
         check(lib.hj_kernel_map_host(self._h, kernel.handle, n, arr, len(ptrs), chunk_elems))
 
+    # -- device ops over HOST arrays (chunked, upload | kernel | download overlapped) -------------
+    @staticmethod
+    def _host_ptr(a):
+        return a.ctypes.data if hasattr(a, "ctypes") else int(a)
+
+    def reduce_host(self, op: int, ty: int, n: int, host_src, chunk_elems: int = 0):
+        """``hj_reduce_host``: fold of a host array (numpy array or raw address); returns the scalar."""
+        out = np.zeros(1, dtype=_NP[ty])
+        check(lib.hj_reduce_host(self._h, op, ty, n, self._host_ptr(host_src), out.ctypes.data, chunk_elems))
+        return out[0]
+
+    def prefix_sum_host(self, ty: int, n: int, inclusive: bool, host_src, host_dst, chunk_elems: int = 0) -> None:
+        check(lib.hj_prefix_sum_host(self._h, ty, n, int(inclusive), self._host_ptr(host_src), self._host_ptr(host_dst),
+                                     chunk_elems))
+
+    def compress_host(self, n: int, host_mask, host_index_out, index_base: int = 0, chunk_elems: int = 0) -> int:
+        """``hj_compress_host``: returns the count; ``host_index_out[:count]`` holds the indices."""
+        cnt = ctypes.c_uint32()
+        check(lib.hj_compress_host(self._h, n, self._host_ptr(host_mask), self._host_ptr(host_index_out),
+                                   ctypes.byref(cnt), index_base, chunk_elems))
+        return cnt.value
+
     def kernel_cache_stats(self) -> dict:
         v = [ctypes.c_uint64() for _ in range(3)]
         check(lib.hj_device_kernel_cache_stats(self._h, *[ctypes.byref(x) for x in v]))
@@ -273,6 +295,52 @@ def marshal_graph(passes, env, descs):
     c_env = (ctypes.c_void_p * max(len(env), 1))(*[(b.handle if b is not None else None) for b in env])
     c_desc = (_lib.BufferDesc * max(len(descs), 1))(*[_lib.BufferDesc(*d) for d in descs])
     return c_passes, n, c_env, c_desc, keep
+
+
+class PreparedGraph:
+    """A pass list marshalled ONCE for repeated launches (what Graph::launch_with rebuilds per call is a
+    few hundred bytes; through ctypes that costs more than a 2^27-element kernel runs).  ``comm``
+    (``sharded.Comm``) selects ``hj_execute_graph_sharded``; ``placement`` / ``seeds`` as in
+    ``Comm.execute_graph``."""
+
+    def __init__(self, device: "Device", passes, env, descs, comm=None, placement=None, seeds=None):
+        self.device, self.comm = device, comm
+        self._keep_env = list(env)
+        self.c_passes, self.n, self.c_env, self.c_desc, self._keep = marshal_graph(passes, env, descs)
+        self.n_res = len(env)
+        self.report = _lib.Report()
+        self.reps = (_lib.PassReport * max(self.n, 1))()
+        self.shards = None
+        if comm is not None:
+            self.shards = (_lib.ShardDesc * max(self.n_res, 1))()
+            self._seeds = list(seeds) if seeds else [None] * self.n_res
+            for i in range(self.n_res):
+                self.shards[i].placement = placement[i] if placement else _lib.RES_AUTO
+                self.shards[i].seed = self._seeds[i].handle if self._seeds[i] is not None else None
+            check(lib.hj_shard_plan(self.c_passes, self.n, self.c_desc, self.n_res, self.shards))
+            self._deferred_in = [0] * self.n_res
+
+    def run(self, timed: bool = False):
+        """One launch; with ``timed`` blocks and returns [(pass name, start_us, duration_us)]."""
+        self.report.passes = self.reps if timed else None
+        self.report.passes_capacity = self.n if timed else 0
+        if self.comm is None:
+            check(lib.hj_execute_graph(self.device.handle, self.c_passes, self.n, self.c_env, self.c_desc, self.n_res,
+                                       ctypes.byref(self.report) if timed else None))
+        else:
+            for i in range(self.n_res):
+                self.shards[i].deferred = self._deferred_in[i]   # the inputs' state; outputs are rewritten by the call
+            check(lib.hj_execute_graph_sharded(self.comm.handle, self.c_passes, self.n, self.c_env, self.c_desc,
+                                               self.n_res, self.shards, ctypes.byref(self.report) if timed else None))
+        if timed:
+            return [(self.reps[i].name.decode(), self.reps[i].start_us, self.reps[i].duration_us) for i in range(self.n)]
+        return None
+
+    def deferred(self):
+        return [bool(self.shards[i].deferred) for i in range(self.n_res)] if self.shards is not None else [False] * self.n_res
+
+    def placement(self):
+        return [self.shards[i].placement for i in range(self.n_res)] if self.shards is not None else [0] * self.n_res
 
 
 class Kernel:

@@ -139,6 +139,9 @@ _SIGS = {
     "hj_compress": (_i32, [_vp, _sz, _vp, _vp, _vp, _vp, _u32]),
     "hj_scatter_reduce": (_i32, [_vp, _i32, _i32, _sz, _vp, _vp, _u64, _vp, _sz]),
     "hj_gather": (_i32, [_vp, _sz, _sz, _vp, _vp, _vp]),
+    "hj_reduce_host": (_i32, [_vp, _i32, _i32, _sz, _vp, _vp, _sz]),
+    "hj_prefix_sum_host": (_i32, [_vp, _i32, _sz, _i32, _vp, _vp, _sz]),
+    "hj_compress_host": (_i32, [_vp, _sz, _vp, _vp, _pu32, _u32, _sz]),
     "hj_ir_hash": (_u64, [ctypes.POINTER(Ir)]),
     "hj_ir_codegen": (_i32, [ctypes.POINTER(Ir), ctypes.POINTER(ctypes.c_void_p)]),
     "hj_free_string": (None, [_vp]),

@@ -146,6 +146,20 @@ hj_status hj_scatter_reduce(hj_device* dev, hj_reduce_op op, hj_type_kind ty, si
 hj_status hj_gather(hj_device* dev, size_t elem_bytes, size_t n, hj_buffer* src,
                     hj_buffer* idx, hj_buffer* dst);
 
+/* The same three device ops over HOST arrays (pinned memory for full PCIe speed): the array is
+ * streamed through the GPU in chunks of `chunk_elems` elements (0 = default), upload, kernel and
+ * download overlapped on three streams; what crosses a chunk boundary (partials, the running total,
+ * the index base) stays on the device.  The pipelined form of the reference's blocking
+ * tr::array -> launch -> to_vec sequence (trace.rs:647-663, 1404-1438) for a single device op;
+ * results are complete on return.  hj_compress_host: host_index_out[0..*host_count) receives the
+ * indices (+ index_base), entries beyond are not touched. */
+hj_status hj_reduce_host(hj_device* dev, hj_reduce_op op, hj_type_kind ty, size_t n,
+                         const void* host_src, void* host_dst /* one element */, size_t chunk_elems);
+hj_status hj_prefix_sum_host(hj_device* dev, hj_type_kind ty, size_t n, int32_t inclusive,
+                             const void* host_src, void* host_dst, size_t chunk_elems);
+hj_status hj_compress_host(hj_device* dev, size_t n, const uint8_t* host_mask, uint32_t* host_index_out,
+                           uint32_t* host_count, uint32_t index_base, size_t chunk_elems);
+
 /* ---- fused-kernel IR (NVRTC path) ----------------------------------------------------
  * Flat mirror of `IR` / `ir::Var` (hephaestus-jit/src/ir.rs:12-46) and of the interned
  * `VarType` tree (vartype.rs:89-122). */

@@ -425,3 +425,58 @@ def test_baseline_config_c1(dev, seed):
     fi = rng.integers(0, 100, size=n).astype(np.float32)   # sum < 2^27 is not exactly representable step by step ...
     got_i = gpu_reduce(dev, hj.SUM, hj.F32, fi[:1000])       # ... so the exact case keeps the reference's 1000 elements
     assert float(got_i) == float(fi[:1000].astype(np.float64).sum())
+
+
+# ---- the device ops over HOST arrays (hj_reduce_host / hj_prefix_sum_host / hj_compress_host) ---------------
+@pytest.mark.parametrize("n,chunk", [(1, 0), (1000, 64), ((1 << 20) + 7, 1 << 16), ((1 << 22) + 3, 0), (5_000_001, 1 << 19)])
+def test_host_streamed_ops_match_oracle(dev, n, chunk):
+    rng = np.random.Generator(np.random.PCG64(n))
+    u = rng.integers(0, 2**32, size=n, dtype=np.uint64).astype(np.uint32)
+    f = rng.random(n, dtype=np.float32)
+    # reduce: chunk partials folded on the device
+    for op in (hj.SUM, hj.MAX, hj.XOR):
+        assert dev.reduce_host(op, hj.U32, n, u, chunk) == oracle.reduce(op, oracle.U32, u)[0]
+    exact = float(f.astype(np.float64).sum())
+    assert abs(float(dev.reduce_host(hj.SUM, hj.F32, n, f, chunk)) - exact) <= 1e-5 * max(exact, 1.0)
+    assert dev.reduce_host(hj.MIN, hj.F32, n, f, chunk) == f.min()
+    # scan: the running total is the seed of the next chunk
+    out = np.empty(n, np.uint32)
+    for inclusive in (True, False):
+        dev.prefix_sum_host(hj.U32, n, inclusive, u, out, chunk)
+        assert np.array_equal(out, oracle.prefix_sum(oracle.U32, u, inclusive))
+    u64 = rng.integers(0, 2**63, size=n, dtype=np.uint64)
+    out64 = np.empty(n, np.uint64)
+    dev.prefix_sum_host(hj.U64, n, True, u64, out64, chunk)
+    assert np.array_equal(out64, np.cumsum(u64, dtype=np.uint64))
+    # compress: indices of every chunk behind those of the chunks before it; the tail is not touched
+    for p in (0.5, 0.02, 1.0, 0.0):
+        mask = (rng.random(n) < p).astype(np.uint8)
+        idx = np.full(n, 0xDEADBEEF, np.uint32)
+        cnt = dev.compress_host(n, mask, idx, 0, chunk)
+        want_cnt, want = oracle.compress(mask)
+        assert cnt == want_cnt
+        assert np.array_equal(idx[:cnt], want[:cnt]) and (idx[cnt:] == 0xDEADBEEF).all()
+    idx = np.zeros(n, np.uint32)
+    mask = (rng.random(n) < 0.3).astype(np.uint8)
+    cnt = dev.compress_host(n, mask, idx, 1000, chunk)
+    assert np.array_equal(idx[:cnt], np.flatnonzero(mask).astype(np.uint32) + 1000)
+
+
+def test_host_streamed_ops_from_pinned_memory(dev):
+    """The same through pinned staging memory (hj_host_alloc), the configuration bench.py times."""
+    import ctypes
+    L = importlib.import_module("hephaestus-jit_b200._lib")
+    n = (1 << 23) + 11
+    src, dst = ctypes.c_void_p(), ctypes.c_void_p()
+    L.check(L.lib.hj_host_alloc(4 * n, ctypes.byref(src)))
+    L.check(L.lib.hj_host_alloc(4 * n, ctypes.byref(dst)))
+    try:
+        a = np.ctypeslib.as_array(ctypes.cast(src, ctypes.POINTER(ctypes.c_uint32)), shape=(n,))
+        b = np.ctypeslib.as_array(ctypes.cast(dst, ctypes.POINTER(ctypes.c_uint32)), shape=(n,))
+        a[:] = np.random.Generator(np.random.PCG64(1)).integers(0, 4, size=n).astype(np.uint32)
+        dev.prefix_sum_host(hj.U32, n, True, src.value, dst.value)
+        assert np.array_equal(b, np.cumsum(a, dtype=np.uint32))
+        assert dev.reduce_host(hj.SUM, hj.U32, n, src.value) == np.uint32(a.sum(dtype=np.uint64) & 0xFFFFFFFF)
+    finally:
+        L.lib.hj_host_free(src)
+        L.lib.hj_host_free(dst)
