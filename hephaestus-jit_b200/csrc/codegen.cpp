@@ -714,7 +714,11 @@ bool codegen_cuda(const hj_ir* ir, CodegenResult* out, std::string* err) {
     for (uint32_t b = 0; b < ir->n_buffers; b++) s << ", void* __restrict__ b" << b;
     s << ") {\n" << scalar_body.str() << "}\n\n";
 
-    s << "#define HJ_SIZE() u32 size = size_static; if (size_ptr) { u32 dyn = *size_ptr; size = dyn < size ? dyn : size; }\n\n";
+    // PDL (jit.cpp launches with programmatic stream serialization): let the next kernel be scheduled
+    // early, and touch no global memory before the kernel in front has completed
+    s << "#define HJ_SIZE() asm volatile(\"griddepcontrol.launch_dependents;\" ::: \"memory\"); "
+         "asm volatile(\"griddepcontrol.wait;\" ::: \"memory\"); "
+         "u32 size = size_static; if (size_ptr) { u32 dyn = *size_ptr; size = dyn < size ? dyn : size; }\n\n";
     // one invocation per element; `if (index >= size) return;` (glsl/mod.rs:129-133)
     s << "extern \"C\" __global__ void __launch_bounds__(" << threads << ") hj_kernel_scalar(" << params << ") {\n"
       << "    HJ_SIZE();\n"

@@ -367,11 +367,15 @@ compress_ring_kernel(const uint8_t* __restrict__ mask, size_t n, const uint32_t*
     extern __shared__ __align__(128) char smem[];
     size_t n_eff = n;
     if (size_buf) {  // DynSize: device-resident element count (graph.rs:503-508)
+        pdl_wait();  // written by a kernel in front
         const size_t dyn = size_buf[0];
         n_eff = dyn < n ? dyn : n;
     }
     const uint32_t n_tiles = (uint32_t)((n_eff + CR_TILE - 1) / CR_TILE);
-    if (n_tiles == 0 && blockIdx.x == 0 && threadIdx.x == 0) out_count[0] = 0;
+    if (n_tiles == 0 && blockIdx.x == 0 && threadIdx.x == 0) {
+        pdl_wait();
+        out_count[0] = 0;
+    }
     using Op = CompressOp<CR_TILE / CR_WARPS, CR_TILE, CR_TSLOTS, ZT>;
     typename Op::Args args{index_out, out_count, index_base, n_eff, counts_out, pv, xepoch};
     ring_pipeline<Op, CR_TILE, CR_STAGES, CR_WARPS, CR_AHEAD, CR_TSLOTS, true, 8, TRACE>(
@@ -450,10 +454,9 @@ hj_status launch_compress(hj_device* dev, size_t n, const uint32_t* size_buf, ui
         const unsigned grid = (unsigned)(tiles < (size_t)dev->sm_count ? tiles : (size_t)dev->sm_count);
         auto launch = [&](auto kernel, size_t smem) -> hj_status {
             HJ_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            kernel<<<grid, (CR_WARPS + 3) * 32, smem, dev->stream>>>(mask, n, size_buf, out_count, index_out,
-                                                                                index_base, view, (grid + 31u) & ~31u,
-                                                                                g_compress_trace, counts_out,
-                                                                                peers ? *peers : PeerView(), peers ? xepoch : 0u);
+            HJ_CUDA(launch_pdl(kernel, dim3(grid), dim3((CR_WARPS + 3) * 32), smem, dev->stream, mask, n, size_buf, out_count,
+                               index_out, index_base, view, (grid + 31u) & ~31u, g_compress_trace, counts_out,
+                               peers ? *peers : PeerView(), peers ? xepoch : 0u));
             return HJ_OK;
         };
         const size_t smem_small = ring_smem_bytes<uint32_t, 28672, 5, CR_WARPS, 8>(8 * (28672 / 8) + CR_WARPS * 1024);

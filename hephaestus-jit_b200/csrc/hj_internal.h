@@ -7,11 +7,13 @@
 #include <cstdarg>
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <mutex>
 #include <string>
 #include <unordered_map>
+#include <utility>
 #include <vector>
 
 #include "../../include/hj.h"
@@ -147,6 +149,28 @@ hj_status launch_fill(hj_device* dev, void* dst, size_t n, size_t elem_bytes, ui
 hj_device* comm_device(hj_comm* c);
 hj_status sharded_compress_pass(hj_comm* c, size_t n_local, uint32_t index_base, hj_buffer* mask, hj_buffer* index_out,
                                 hj_buffer* out_count, bool zero_tail);
+
+// Launch with programmatic stream serialization (PDL): the kernel may be scheduled while the kernel in
+// front of it on the stream is still draining — its CTAs run their prologue (shared-memory carve-out,
+// mbarrier init, bin zeroing) and then block in pdl_wait() (common.cuh) until that kernel has completed
+// and its memory is visible.  ONLY for kernels that call pdl_wait() before their first global access.
+// HJ_NO_PDL=1 launches them fully serialised.
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                              Args&&... args) {
+    static const bool no_pdl = getenv("HJ_NO_PDL") != nullptr;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = no_pdl ? 0 : 1;
+    return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
 
 inline hj_status check_launch(hj_device* dev, const char* what) {
     cudaError_t e = cudaGetLastError();

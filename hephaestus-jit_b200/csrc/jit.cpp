@@ -287,8 +287,19 @@ hj_status hj_kernel_launch(hj_device* dev, hj_kernel* k, size_t size, hj_buffer*
     const bool use_vec = k->vec && aligned && !getenv("HJ_JIT_SCALAR");
     const size_t per_block = use_vec ? (size_t)k->threads * k->vec_width * k->unroll : k->threads;
     const unsigned grid = (unsigned)((size + per_block - 1) / per_block);
-    cudaError_t e = cudaLaunchKernel((const void*)(use_vec ? k->vec : k->scalar), dim3(grid), dim3(k->threads),
-                                     args.data(), 0, dev->stream);
+    // programmatic stream serialization: the generated kernels wait (griddepcontrol.wait) before their
+    // first global access, so their launch may overlap the tail of the kernel in front
+    static const bool no_pdl = getenv("HJ_NO_PDL") != nullptr;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(k->threads);
+    cfg.stream = dev->stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = no_pdl ? 0 : 1;
+    cudaError_t e = cudaLaunchKernelExC(&cfg, (const void*)(use_vec ? k->vec : k->scalar), args.data());
     if (e != cudaSuccess) {
         cudaGetLastError();
         return fail(HJ_ERR_CUDA, "launch of fused kernel failed: %s", cudaGetErrorString(e));

@@ -241,6 +241,8 @@ reduce_kernel(const T* __restrict__ src, size_t n, size_t head, typename Scalar<
     constexpr int VEC = 16 / sizeof(T);
     __shared__ S smem[THREADS / 32];
     __shared__ bool is_last;
+    pdl_launch_dependents();  // PDL: the next kernel's prologue may overlap this kernel's tail ...
+    pdl_wait();               // ... and this one reads nothing before the kernel in front has completed
 
     // [0, head) scalar prologue so that the vector body is 16-byte aligned, then nvec
     // vectors, then a scalar tail.
@@ -304,9 +306,9 @@ hj_status run(hj_device* dev, size_t n, const void* src, void* dst, const PeerVi
     HJ_TRY(ensure_reduce_scratch(dev, 64 + cap * sizeof(uint64_t)));
     unsigned* ticket = reinterpret_cast<unsigned*>(dev->reduce_scratch);
     S* partials = reinterpret_cast<S*>(reinterpret_cast<char*>(dev->reduce_scratch) + 64);
-    reduce_kernel<T, OP, RED_THREADS, RED_UNROLL><<<grid, RED_THREADS, 0, dev->stream>>>(
-        reinterpret_cast<const T*>(src), n, head, partials, ticket, reinterpret_cast<T*>(dst), peers ? *peers : PeerView(),
-        peers ? epoch : 0u);
+    HJ_CUDA(launch_pdl(reduce_kernel<T, OP, RED_THREADS, RED_UNROLL>, dim3(grid), dim3(RED_THREADS), 0, dev->stream,
+                       reinterpret_cast<const T*>(src), n, head, partials, ticket, reinterpret_cast<T*>(dst),
+                       peers ? *peers : PeerView(), peers ? epoch : 0u));
     return check_launch(dev, "reduce_kernel");
 }
 

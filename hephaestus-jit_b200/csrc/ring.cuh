@@ -162,8 +162,12 @@ __device__ __forceinline__ void ring_pipeline(const char* __restrict__ src, size
             mbar_init(&ctl->pub[q], 1);
             mbar_init(&ctl->pref[q], 1);
         }
+        // everything above is local to the CTA: it overlaps the tail of the kernel in front (PDL)
+        pdl_launch_dependents();
+        pdl_wait();
         ctl->epoch = epoch_begin(lb);
     }
+    pdl_wait();  // every thread: no global access before the kernel in front has completed
     __syncthreads();
     lb.epoch = ctl->epoch;
 

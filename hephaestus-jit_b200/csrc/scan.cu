@@ -294,8 +294,13 @@ scan_ring_kernel(const T* __restrict__ src, T* __restrict__ dst, size_t n, const
     extern __shared__ __align__(128) char smem[];
     using Op = ScanOp<T, P, INCLUSIVE, TILE / CWARPS>;
     typename Op::Args args{dst, seed_out, pv, xepoch};
+    P seed_v = (P)0;
+    if (seed) {
+        pdl_wait();  // the seed is the output of the kernel in front (sharded scan: the totals pass)
+        seed_v = (P)seed[0];
+    }
     ring_pipeline<Op, TILE, STAGES, CWARPS, AHEAD, STAGES, false, 10>(reinterpret_cast<const char*>(src), n * sizeof(T), n_tiles,
-                                                   seed ? (P)seed[0] : (P)0, lb, G, args, smem);
+                                                   seed_v, lb, G, args, smem);
 }
 
 template <typename T, typename P, int TILE, int STAGES, int CWARPS, int AHEAD>
@@ -311,9 +316,9 @@ hj_status run_ring(hj_device* dev, size_t n, bool inclusive, const void* src, vo
     const uint32_t G = (grid + 31u) & ~31u;  // tiles per round: about one per CTA
     auto launch = [&](auto kernel) -> hj_status {
         HJ_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kernel<<<grid, (CWARPS + 3) * 32, smem, dev->stream>>>((const T*)src, (T*)dst, n, (const T*)seed, lb,
-                                                              (uint32_t)n_tiles, G, (T*)seed_out,
-                                                              peers ? *peers : PeerView(), peers ? xepoch : 0u);
+        HJ_CUDA(launch_pdl(kernel, dim3(grid), dim3((CWARPS + 3) * 32), smem, dev->stream, (const T*)src, (T*)dst, n,
+                           (const T*)seed, lb, (uint32_t)n_tiles, G, (T*)seed_out, peers ? *peers : PeerView(),
+                           peers ? xepoch : 0u));
         return check_launch(dev, "scan_ring_kernel");
     };
     return inclusive ? launch(scan_ring_kernel<T, P, true, TILE, STAGES, CWARPS, AHEAD>)

@@ -177,6 +177,7 @@ hist_ring_kernel(const uint32_t* __restrict__ keys, size_t n, uint32_t literal, 
         // for this grid's completion and memory flush before it reads the private histograms)
         pdl_launch_dependents();
     }
+    pdl_wait();  // zeroing the bins and the barrier init overlap the tail of the kernel in front (PDL)
     __syncthreads();
 
     if (warp == HR_WARPS) {  // the producer takes the highest warp id (issue arbiter favours it)
@@ -342,6 +343,7 @@ hist_fold_exchange_kernel(const uint32_t* __restrict__ scratch, uint32_t n_group
     const uint32_t wl = threadIdx.x % HFX_WORDS, slice = threadIdx.x / HFX_WORDS;
     const uint32_t w = blockIdx.x * HFX_WORDS + wl;
     const uint32_t n_words = (n_dst + 1) / 2;
+    pdl_launch_dependents();
     pdl_wait();  // the private histograms of hist_ring_kernel are complete and visible from here on
     uint32_t even = 0, odd = 0;
     if (w < n_words) {
@@ -465,8 +467,8 @@ hj_status launch_scatter_reduce(hj_device* dev, hj_reduce_op op, hj_type_kind ty
                 const size_t smem = ring + ((((size_t)n_words + 3) & ~(size_t)3) + 32) * 4;  // + 32 dummy words
                 auto kern = hist_ring_kernel<true>;
                 HJ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                kern<<<n_groups, (HR_WARPS + 1) * 32, smem, dev->stream>>>(
-                    idx, n, 1u, dev->hist_scratch, (uint32_t*)dst, (uint32_t)n_dst, (uint32_t)n_dst, 1u, 0u);
+                HJ_CUDA(launch_pdl(kern, dim3(n_groups), dim3((HR_WARPS + 1) * 32), smem, dev->stream, idx, n, 1u, dev->hist_scratch,
+                                   (uint32_t*)dst, (uint32_t)n_dst, (uint32_t)n_dst, 1u, 0u));
                 HJ_TRY(check_launch(dev, "hist_ring_kernel"));
                 static const bool old_fold = getenv("HJ_HIST_OLD_FOLD") != nullptr;
                 if (!old_fold && ((uintptr_t)dst & 7u) == 0) {
@@ -475,17 +477,9 @@ hj_status launch_scatter_reduce(hj_device* dev, hj_reduce_op op, hj_type_kind ty
                     const bool with_peers = ax && ax->world > 1 && n_words <= ax->slot_vecs;
                     ArrayPeerView view = with_peers ? *ax : ArrayPeerView();
                     if (!with_peers) { view.world = 1; view.rank = 0; }
-                    cudaLaunchConfig_t cfg = {};
-                    cfg.gridDim = dim3((n_words + HFX_WORDS - 1) / HFX_WORDS);
-                    cfg.blockDim = dim3(HFX_WORDS * HFX_SLICES);
-                    cfg.stream = dev->stream;
-                    cudaLaunchAttribute attr[1];
-                    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-                    attr[0].val.programmaticStreamSerializationAllowed = 1;
-                    cfg.attrs = attr;
-                    cfg.numAttrs = 1;
-                    HJ_CUDA(cudaLaunchKernelEx(&cfg, hist_fold_exchange_kernel, (const uint32_t*)dev->hist_scratch, n_groups,
-                                               (uint32_t*)dst, (uint32_t)n_dst, view));
+                    HJ_CUDA(launch_pdl(hist_fold_exchange_kernel, dim3((n_words + HFX_WORDS - 1) / HFX_WORDS),
+                                       dim3(HFX_WORDS * HFX_SLICES), 0, dev->stream, (const uint32_t*)dev->hist_scratch, n_groups,
+                                       (uint32_t*)dst, (uint32_t)n_dst, view));
                     if (exchanged) *exchanged = with_peers;
                     return check_launch(dev, "hist_fold_exchange_kernel");
                 }
@@ -505,8 +499,8 @@ hj_status launch_scatter_reduce(hj_device* dev, hj_reduce_op op, hj_type_kind ty
             const size_t smem = ring + (rs ? ((size_t)(bins_per_part + 1) << rs) + 32 : (size_t)bins_per_part + 32) * 4;  // + dummy words
             auto kern = hist_ring_kernel<false>;
             HJ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            kern<<<n_groups * parts, (HR_WARPS + 1) * 32, smem, dev->stream>>>(
-                idx, n, (uint32_t)literal, dev->hist_scratch, (uint32_t*)dst, (uint32_t)n_dst, bins_per_part, parts, rs);
+            HJ_CUDA(launch_pdl(kern, dim3(n_groups * parts), dim3((HR_WARPS + 1) * 32), smem, dev->stream, idx, n, (uint32_t)literal,
+                               dev->hist_scratch, (uint32_t*)dst, (uint32_t)n_dst, bins_per_part, parts, rs));
             HJ_TRY(check_launch(dev, "hist_ring_kernel"));
             hist_fold_kernel<false><<<dim3((unsigned)((n_dst + 255) / 256), HF_SLICES), 256, 0, dev->stream>>>(
                 (const uint32_t*)dev->hist_scratch, n_groups, (uint32_t*)dst, (uint32_t)n_dst);
