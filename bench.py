@@ -698,7 +698,7 @@ def run_e2e(torch, dist, hj, L, dev, comm, kernel, world, rank, x, f, u, mask, c
     try:
         for k, nb in sizes.items():
             p = ctypes.c_void_p()
-            L.check(L.lib.hj_host_alloc(nb, ctypes.byref(p)))
+            L.check(L.lib.hj_host_alloc_near(dev.handle, nb, ctypes.byref(p)))   # pinned, on the GPU's NUMA node
             host[k] = p
         # fill the pinned inputs from the resident synthetic tensors
         for k, t in (("hx", x), ("hf", f), ("hu", u), ("hmask", mask)):

@@ -133,6 +133,7 @@ _SIGS = {
     "hj_buffer_size": (_i32, [_vp, ctypes.POINTER(_sz)]),
     "hj_buffer_device": (_i32, [_vp, _pvp]),
     "hj_host_alloc": (_i32, [_sz, _pvp]),
+    "hj_host_alloc_near": (_i32, [_vp, _sz, _pvp]),
     "hj_host_free": (_i32, [_vp]),
     "hj_reduce": (_i32, [_vp, _i32, _i32, _sz, _vp, _vp]),
     "hj_prefix_sum": (_i32, [_vp, _i32, _sz, _i32, _vp, _vp, _vp]),

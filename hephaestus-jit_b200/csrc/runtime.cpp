@@ -9,6 +9,11 @@
 #include <cstdlib>
 #include <map>
 
+#include <sched.h>
+
+#include <cctype>
+#include <string>
+
 #include "hj_internal.h"
 
 namespace hj {
@@ -151,6 +156,11 @@ hj_status hj_device_create(int32_t ordinal, hj_device** out) {
     dev->total_mem = prop.totalGlobalMem;
     dev->l2_bytes = (size_t)prop.l2CacheSize;
     dev->max_smem_optin = (int)prop.sharedMemPerBlockOptin;
+    if (const char* e = getenv("HJ_L2_FETCH")) {  // experiment: L2 fetch granularity in bytes (32 / 64 / 128)
+        const int gran = atoi(e);
+        if (gran == 32 || gran == 64 || gran == 128) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)gran);
+        cudaGetLastError();
+    }
     HJ_CUDA(cudaStreamCreateWithFlags(&dev->own_stream, cudaStreamNonBlocking));
     dev->stream = dev->own_stream;
     HJ_CUDA(cudaDeviceGetDefaultMemPool(&dev->pool, ordinal));
@@ -347,6 +357,58 @@ hj_status hj_buffer_device(hj_buffer* buf, hj_device** out) {
 hj_status hj_host_alloc(size_t bytes, void** out) {
     HJ_REQUIRE(out, "null argument");
     HJ_CUDA(cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocDefault));
+    return HJ_OK;
+}
+// Pinned memory on the NUMA node the GPU hangs off: cudaHostAlloc places the pages where the calling
+// thread runs (first touch), so the thread is moved onto the CPUs of the device's node for the
+// duration of the allocation.  With 8 ranks streaming at once, buffers that all sit on node 0 send
+// half of the PCIe traffic across the socket interconnect.  Best effort: without sysfs topology or
+// with a cpuset that excludes those CPUs this is plain hj_host_alloc.
+hj_status hj_host_alloc_near(hj_device* dev, size_t bytes, void** out) {
+    HJ_REQUIRE(dev && out, "null argument");
+    cpu_set_t old_set, want;
+    bool moved = false;
+    if (!getenv("HJ_NO_NUMA") && sched_getaffinity(0, sizeof(old_set), &old_set) == 0) {
+        char bus[32] = {0};
+        int node = -1;
+        if (cudaDeviceGetPCIBusId(bus, sizeof(bus), dev->ordinal) == cudaSuccess) {
+            for (char* c = bus; *c; c++) *c = (char)tolower(*c);
+            std::string path = std::string("/sys/bus/pci/devices/") + bus + "/numa_node";
+            if (FILE* f = fopen(path.c_str(), "r")) {
+                if (fscanf(f, "%d", &node) != 1) node = -1;
+                fclose(f);
+            }
+        } else {
+            cudaGetLastError();
+        }
+        if (node >= 0) {
+            std::string path = "/sys/devices/system/node/node" + std::to_string(node) + "/cpulist";
+            CPU_ZERO(&want);
+            int n_cpus = 0;
+            if (FILE* f = fopen(path.c_str(), "r")) {
+                int a, b;
+                char sep;
+                while (fscanf(f, "%d", &a) == 1) {  // "0-23,48-71"
+                    b = a;
+                    if (fscanf(f, "%c", &sep) == 1 && sep == '-') {
+                        if (fscanf(f, "%d", &b) != 1) b = a;
+                        if (fscanf(f, "%c", &sep) != 1) sep = 0;
+                    }
+                    for (int c = a; c <= b && c < CPU_SETSIZE; c++)
+                        if (CPU_ISSET(c, &old_set)) { CPU_SET(c, &want); n_cpus++; }  // stay inside the cpuset
+                    if (sep != ',') break;
+                }
+                fclose(f);
+            }
+            if (n_cpus > 0 && sched_setaffinity(0, sizeof(want), &want) == 0) moved = true;
+        }
+    }
+    cudaError_t e = cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocDefault);
+    if (moved) sched_setaffinity(0, sizeof(old_set), &old_set);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return fail(HJ_ERR_OOM, "cudaHostAlloc(%zu) failed: %s", bytes, cudaGetErrorString(e));
+    }
     return HJ_OK;
 }
 hj_status hj_host_free(void* ptr) {

@@ -379,25 +379,40 @@ gather_kernel(const T* __restrict__ src, const uint32_t* __restrict__ idx, T* __
     for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < n; i += stride) dst[i] = __ldg(src + idx[i]);
 }
 
-// 4-byte elements, 16-byte aligned idx / dst: indices arrive as 128-bit streaming loads, eight
-// independent gathers per thread are in flight, results leave as 128-bit streaming stores.  The
-// table goes through the read-only path (L1 + L2); what bounds the kernel is the L2 sector rate
-// (L2-resident table) or the DRAM sector rate (32 bytes fetched per 4 bytes used).
+// 4-byte elements, 16-byte aligned idx / dst: indices arrive as 128-bit streaming loads, NV vectors
+// (4 * NV independent gathers) per thread are in flight, results leave as 128-bit streaming stores.
+// The table goes through the read-only path; what bounds the kernel is the L2 sector rate
+// (L2-resident table) or the DRAM random-access rate (one 32-byte sector — 64 bytes with the default
+// L2 fetch granularity — fetched per 4 bytes used).  NOALLOC: bypass L1 for the table (a table far
+// larger than L1 + L2 never hits there; the lines only evict the index stream's).
+__device__ __forceinline__ uint32_t ld_table(const uint32_t* p, bool noalloc) {
+    uint32_t v;
+    if (noalloc) asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(v) : "l"(p));
+    else v = __ldg(p);
+    return v;
+}
+template <int NV, bool NOALLOC>
 __global__ void __launch_bounds__(256)
 gather4_vec_kernel(const uint32_t* __restrict__ src, const uint32_t* __restrict__ idx, uint32_t* __restrict__ dst,
                    size_t n) {
+    pdl_launch_dependents();
+    pdl_wait();
     const size_t nvec = n / 4;
     const uint4* vidx = reinterpret_cast<const uint4*>(idx);
     uint4* vdst = reinterpret_cast<uint4*>(dst);
     const size_t stride = (size_t)gridDim.x * 256;
     size_t v = (size_t)blockIdx.x * 256 + threadIdx.x;
-    for (; v + stride < nvec; v += 2 * stride) {
-        const uint4 a = ld_stream_v4(vidx + v), b = ld_stream_v4(vidx + v + stride);
-        uint4 x, y;
-        x.x = __ldg(src + a.x); x.y = __ldg(src + a.y); x.z = __ldg(src + a.z); x.w = __ldg(src + a.w);
-        y.x = __ldg(src + b.x); y.y = __ldg(src + b.y); y.z = __ldg(src + b.z); y.w = __ldg(src + b.w);
-        st_stream_v4(vdst + v, x);
-        st_stream_v4(vdst + v + stride, y);
+    for (; v + (NV - 1) * stride < nvec; v += NV * stride) {
+        uint4 a[NV], x[NV];
+#pragma unroll
+        for (int k = 0; k < NV; k++) a[k] = ld_stream_v4(vidx + v + k * stride);
+#pragma unroll
+        for (int k = 0; k < NV; k++) {
+            x[k].x = ld_table(src + a[k].x, NOALLOC); x[k].y = ld_table(src + a[k].y, NOALLOC);
+            x[k].z = ld_table(src + a[k].z, NOALLOC); x[k].w = ld_table(src + a[k].w, NOALLOC);
+        }
+#pragma unroll
+        for (int k = 0; k < NV; k++) st_stream_v4(vdst + v + k * stride, x[k]);
     }
     for (; v < nvec; v += stride) {
         const uint4 a = ld_stream_v4(vidx + v);
@@ -544,9 +559,26 @@ hj_status launch_gather(hj_device* dev, size_t elem_bytes, size_t n, const void*
     case 1: gather_kernel<uint8_t><<<grid, 256, 0, dev->stream>>>((const uint8_t*)src, idx, (uint8_t*)dst, n); break;
     case 2: gather_kernel<uint16_t><<<grid, 256, 0, dev->stream>>>((const uint16_t*)src, idx, (uint16_t*)dst, n); break;
     case 4:
-        if ((((uintptr_t)idx | (uintptr_t)dst) & 15u) == 0 && n >= 4096)
-            gather4_vec_kernel<<<std::min<size_t>((n / 8 + 255) / 256, cap), 256, 0, dev->stream>>>((const uint32_t*)src, idx, (uint32_t*)dst, n);
-        else
+        if ((((uintptr_t)idx | (uintptr_t)dst) & 15u) == 0 && n >= 4096) {
+            // HJ_GATHER_CFG = 10 * (vectors per thread) + (1: table loads bypass L1); default 2 vectors, L1 allocate
+            static const int cfg = getenv("HJ_GATHER_CFG") ? atoi(getenv("HJ_GATHER_CFG")) : 20;
+            static const int ctas = getenv("HJ_GATHER_CTAS") ? atoi(getenv("HJ_GATHER_CTAS")) : 16;
+            const int nv = cfg / 10;
+            const size_t g4 = std::min<size_t>((n / (4 * (size_t)nv) + 255) / 256, (size_t)dev->sm_count * (size_t)ctas);
+            const uint32_t *s32 = (const uint32_t*)src;
+            uint32_t* d32 = (uint32_t*)dst;
+            cudaError_t e;
+            switch (cfg) {
+            case 11: e = launch_pdl(gather4_vec_kernel<1, true>, dim3((unsigned)g4), dim3(256), 0, dev->stream, s32, idx, d32, n); break;
+            case 21: e = launch_pdl(gather4_vec_kernel<2, true>, dim3((unsigned)g4), dim3(256), 0, dev->stream, s32, idx, d32, n); break;
+            case 40: e = launch_pdl(gather4_vec_kernel<4, false>, dim3((unsigned)g4), dim3(256), 0, dev->stream, s32, idx, d32, n); break;
+            case 41: e = launch_pdl(gather4_vec_kernel<4, true>, dim3((unsigned)g4), dim3(256), 0, dev->stream, s32, idx, d32, n); break;
+            case 80: e = launch_pdl(gather4_vec_kernel<8, false>, dim3((unsigned)g4), dim3(256), 0, dev->stream, s32, idx, d32, n); break;
+            case 81: e = launch_pdl(gather4_vec_kernel<8, true>, dim3((unsigned)g4), dim3(256), 0, dev->stream, s32, idx, d32, n); break;
+            default: e = launch_pdl(gather4_vec_kernel<2, false>, dim3((unsigned)g4), dim3(256), 0, dev->stream, s32, idx, d32, n); break;
+            }
+            HJ_CUDA(e);
+        } else
             gather_kernel<uint32_t><<<grid, 256, 0, dev->stream>>>((const uint32_t*)src, idx, (uint32_t*)dst, n);
         break;
     case 8: gather_kernel<uint2><<<grid, 256, 0, dev->stream>>>((const uint2*)src, idx, (uint2*)dst, n); break;

@@ -110,6 +110,8 @@ hj_status hj_buffer_size(hj_buffer* buf, size_t* out_bytes);
 hj_status hj_buffer_device(hj_buffer* buf, hj_device** out); /* borrowed, not retained */
 /* Pinned host staging memory for the end-to-end path. */
 hj_status hj_host_alloc(size_t bytes, void** out);
+/* The same on the NUMA node `dev` is attached to (best effort; see runtime.cpp). */
+hj_status hj_host_alloc_near(hj_device* dev, size_t bytes, void** out);
 hj_status hj_host_free(void* ptr);
 
 /* ---- device ops (hand-written sm_100a kernels) ---------------------------------------
