@@ -182,7 +182,8 @@ def config_dict(world: int) -> dict:
         "elements_global": {"map": n_map, "reduce": n_ops, "scan": n_ops, "compress": n_ops},
         "bytes_per_element": {"map": 8, "reduce": 4, "scan": 8, "compress": "1 + 4p"},
         "l2_policy": "every array of the step (>= 1 GiB / N per rank) is larger than the 126 MB L2; no flush needed",
-        "boundary": "hj_execute_graph (N=1) / hj_execute_graph_sharded (N>1), one call per step",
+        "boundary": "hj_execute_graph_cached (N=1) / hj_execute_graph_sharded_cached (N>1), one call per step: the relaunch "
+                    "path of a recorded function — the pass list is captured once and replayed as one CUDA graph",
         "parallelism": (f"strong scaling: every array split into {world} contiguous blocks; reduce = partials folded in rank "
                         "order, scan = shard totals -> deferred seed, compress = per-rank counts -> global count, each "
                         "exchanged inside the op's own kernel over NVLink peer memory (no NCCL call on the data path)")
@@ -510,7 +511,10 @@ def run_own(args):
     S, R = L.RES_SHARDED, L.RES_REPLICATED
     placement = [S, S, S, R, S, S, S, S, R]
     seeds = [None, None, None, None, None, b_seed, None, None, None]
-    graph = hj.PreparedGraph(dev, passes, env, descs, comm, placement if comm else None, seeds if comm else None)
+    # graph_key: the relaunch path of a recorded function (FCache::call, record.rs:120-210) — from the third
+    # launch on the whole pass list is ONE cudaGraphLaunch (hj_execute_graph_cached / _sharded_cached)
+    graph = hj.PreparedGraph(dev, passes, env, descs, comm, placement if comm else None, seeds if comm else None,
+                             graph_key=0 if os.environ.get("HJ_BENCH_NO_GRAPH") else 0xB200)
     kernel = dev.kernel(ir)  # compile outside the timed region (cached by IR hash afterwards)
     step = graph.run
 
@@ -524,15 +528,18 @@ def run_own(args):
     sampler = ClockSampler(local_rank)
     sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_host0 = time.perf_counter()
     e0.record()
     for _ in range(args.steps):
         step()
     e1.record()
+    host_us_per_step = (time.perf_counter() - t_host0) / args.steps * 1e6   # enqueue cost, before the GPU has drained
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
     total_ms = e0.elapsed_time(e1)
     launches = dev.launch_count() - launches0
+    launch_how = graph.how.value
     # keep the sampler alive long enough to have seen the load even for very short runs
     if total_ms < 300:
         t_end = time.perf_counter() + 0.3
@@ -545,6 +552,16 @@ def run_own(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         total_ms = float(t.item())
     ms_per_step = total_ms / args.steps
+
+    # ---- per-step distribution (diagnostic, outside the timed region): one event pair per step
+    evs = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    evs[0].record()
+    for i in range(args.steps):
+        step()
+        evs[i + 1].record()
+    torch.cuda.synchronize()
+    per_step = sorted(evs[i].elapsed_time(evs[i + 1]) for i in range(args.steps))
+    step_ms = {"min": per_step[0], "median": per_step[len(per_step) // 2], "max": per_step[-1]}
 
     # ---- every result of the step, verified on every rank with independent torch computations
     checks = {}
@@ -666,6 +683,9 @@ def run_own(args):
             "cpu_baseline": cpu_report,
             "e2e": e2e,
             "gpu_launches": int(launches),
+            "host_enqueue_us_per_step": host_us_per_step,
+            "step_ms_distribution_rank0": step_ms,
+            "launch_mode": {0: "pass by pass", 1: "captured", 2: "replay of one captured CUDA graph"}.get(launch_how, launch_how),
             "clocks": clocks,
             "sharded_check": sharded_check,
             "checks": checks,

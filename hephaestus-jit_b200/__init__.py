@@ -303,8 +303,9 @@ class PreparedGraph:
     (``sharded.Comm``) selects ``hj_execute_graph_sharded``; ``placement`` / ``seeds`` as in
     ``Comm.execute_graph``."""
 
-    def __init__(self, device: "Device", passes, env, descs, comm=None, placement=None, seeds=None):
-        self.device, self.comm = device, comm
+    def __init__(self, device: "Device", passes, env, descs, comm=None, placement=None, seeds=None, graph_key: int = 0):
+        self.device, self.comm, self.graph_key = device, comm, graph_key
+        self.how = ctypes.c_uint32()
         self._keep_env = list(env)
         self.c_passes, self.n, self.c_env, self.c_desc, self._keep = marshal_graph(passes, env, descs)
         self.n_res = len(env)
@@ -324,14 +325,23 @@ class PreparedGraph:
         """One launch; with ``timed`` blocks and returns [(pass name, start_us, duration_us)]."""
         self.report.passes = self.reps if timed else None
         self.report.passes_capacity = self.n if timed else 0
+        cached = self.graph_key and not timed   # relaunch path: replay of one captured CUDA graph
         if self.comm is None:
-            check(lib.hj_execute_graph(self.device.handle, self.c_passes, self.n, self.c_env, self.c_desc, self.n_res,
-                                       ctypes.byref(self.report) if timed else None))
+            if cached:
+                check(lib.hj_execute_graph_cached(self.device.handle, self.graph_key, self.c_passes, self.n, self.c_env,
+                                                  self.c_desc, self.n_res, ctypes.byref(self.how)))
+            else:
+                check(lib.hj_execute_graph(self.device.handle, self.c_passes, self.n, self.c_env, self.c_desc, self.n_res,
+                                           ctypes.byref(self.report) if timed else None))
         else:
             for i in range(self.n_res):
                 self.shards[i].deferred = self._deferred_in[i]   # the inputs' state; outputs are rewritten by the call
-            check(lib.hj_execute_graph_sharded(self.comm.handle, self.c_passes, self.n, self.c_env, self.c_desc,
-                                               self.n_res, self.shards, ctypes.byref(self.report) if timed else None))
+            if cached:
+                check(lib.hj_execute_graph_sharded_cached(self.comm.handle, self.graph_key, self.c_passes, self.n, self.c_env,
+                                                          self.c_desc, self.n_res, self.shards, ctypes.byref(self.how)))
+            else:
+                check(lib.hj_execute_graph_sharded(self.comm.handle, self.c_passes, self.n, self.c_env, self.c_desc,
+                                                   self.n_res, self.shards, ctypes.byref(self.report) if timed else None))
         if timed:
             return [(self.reps[i].name.decode(), self.reps[i].start_us, self.reps[i].duration_us) for i in range(self.n)]
         return None

@@ -171,6 +171,8 @@ _SIGS = {
     "hj_shard_plan": (_i32, [ctypes.POINTER(Pass), _u32, ctypes.POINTER(BufferDesc), _u32, ctypes.POINTER(ShardDesc)]),
     "hj_execute_graph_sharded": (_i32, [_vp, ctypes.POINTER(Pass), _u32, _pvp, ctypes.POINTER(BufferDesc), _u32,
                                         ctypes.POINTER(ShardDesc), ctypes.POINTER(Report)]),
+    "hj_execute_graph_sharded_cached": (_i32, [_vp, _u64, ctypes.POINTER(Pass), _u32, _pvp, ctypes.POINTER(BufferDesc), _u32,
+                                               ctypes.POINTER(ShardDesc), ctypes.POINTER(_u32)]),
     "hj_tr_array_sharded": (_i32, [_vp, _u32, _vp, _u64, _pu64]),
     "hj_tr_from_buffer_sharded": (_i32, [_vp, _vp, _u32, _u64, _pu64]),
     "hj_tr_var_shard": (_i32, [_u64, _pi32, _pu64, _pu64, _pi32]),

@@ -41,7 +41,6 @@ struct hj_comm {
     void* peer_arraybox[HJ_MAX_PEERS] = {};
     bool p2p = false;
     bool connected = true;    // false between hj_comm_create_local and hj_comm_connect
-    uint32_t xepoch = 0;
 };
 
 namespace hj {
@@ -153,6 +152,11 @@ hj_status need_comm_nccl(hj_comm* c, const char* what) {
     return need_nccl();
 }
 
+// scratch layout: [0,64) local scalar | [64, 64+8*world) gathered | 64 bytes seed / sum | 64 bytes:
+// the device-resident exchange epoch (u32) and the ticket of the multi-CTA exchange kernels (u32)
+size_t scratch_bytes(int world) { return 64 + 8 * (size_t)world + 64 + 64; }
+uint32_t* xepoch_slot(hj_comm* c) { return reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(c->scratch) + 64 + 8 * (size_t)c->world + 64); }
+
 char* local_slot(hj_comm* c) { return reinterpret_cast<char*>(c->scratch); }
 char* gathered_slot(hj_comm* c) { return reinterpret_cast<char*>(c->scratch) + 64; }
 char* extra_slot(hj_comm* c) { return reinterpret_cast<char*>(c->scratch) + 64 + 8 * (size_t)c->world; }
@@ -168,13 +172,12 @@ char* extra_slot(hj_comm* c) { return reinterpret_cast<char*>(c->scratch) + 64 +
 // alternate: a rank can only be one exchange ahead of a peer (it needs the peer's value of the
 // current exchange to finish it), so the slot it overwrites next is never one still being read.
 __global__ void __launch_bounds__(32)
-peer_allgather_kernel(PeerView pv, uint32_t epoch, const void* __restrict__ local, int es, void* __restrict__ gathered) {
+peer_allgather_kernel(PeerView pv, const void* __restrict__ local, int es, void* __restrict__ gathered) {
     const int lane = threadIdx.x;
-    if (lane >= pv.world) return;
     unsigned long long bits = 0;
     memcpy(&bits, local, es);  // es in {1, 2, 4, 8}
-    const unsigned long long v = peer_exchange(pv, epoch, bits, lane);
-    memcpy(reinterpret_cast<char*>(gathered) + (size_t)lane * es, &v, es);
+    const unsigned long long v = peer_allgather_warp(pv, bits, lane);
+    if (lane < pv.world) memcpy(reinterpret_cast<char*>(gathered) + (size_t)lane * es, &v, es);
 }
 
 // ---- all-reduce of one small array per rank over peer memory (privatised histograms) -----------
@@ -192,10 +195,6 @@ peer_allgather_kernel(PeerView pv, uint32_t epoch, const void* __restrict__ loca
 constexpr size_t HJ_ARRAYBOX_OFFSET = 4096, HJ_ARRAYBOX_BYTES = 256 * 1024;
 constexpr size_t HJ_ARRAYSLOT_BYTES = 2 * HJ_ARRAYBOX_BYTES;  // (element, epoch) pairs
 
-struct ArrayBoxes {
-    uint4* box[HJ_MAX_PEERS];  // inbox of every rank, at the current parity
-};
-
 template <typename T, int OP>
 __device__ __forceinline__ T fold2(T a, T b) {
     if (OP == HJ_REDUCE_SUM) return (T)(a + b);
@@ -210,11 +209,9 @@ __device__ __forceinline__ T fold2(T a, T b) {
 }
 
 template <typename T, int OP>
-__global__ void __launch_bounds__(256)
-array_allreduce_kernel(int rank, int world, uint32_t epoch, ArrayBoxes ab, uint32_t* __restrict__ dst32, uint32_t n) {
-    static_assert(sizeof(T) == 4, "4-byte elements");
-    const uint32_t i = blockIdx.x * 256 + threadIdx.x;
-    if (4 * i >= n) return;
+__device__ __forceinline__ void array_allreduce_element(const ArrayPeerView& ax, uint32_t epoch, uint32_t i,
+                                                        uint32_t* __restrict__ dst32, uint32_t n) {
+    const int rank = ax.rank, world = ax.world;
     // a thread owns four elements; the last vector of an array whose length is not a multiple of four
     // (or whose base is not 16-byte aligned) is moved element by element, the padding travels as zeros
     const bool whole = 4 * i + 4 <= n && ((uintptr_t)dst32 & 15u) == 0;
@@ -226,16 +223,18 @@ array_allreduce_kernel(int rank, int world, uint32_t epoch, ArrayBoxes ab, uint3
         for (uint32_t k = 0; k < 4 && 4 * i + k < n; k++) e[k] = dst32[4 * i + k];
         mine = make_uint4(e[0], e[1], e[2], e[3]);
     }
-    const size_t slot_vecs = HJ_ARRAYSLOT_BYTES / 16;
+    const size_t slot_vecs = ax.slot_vecs;
+    const size_t par = (size_t)(epoch & 1u) * ax.parity_vecs;
     const uint4 w0 = make_uint4(mine.x, epoch, mine.y, epoch), w1 = make_uint4(mine.z, epoch, mine.w, epoch);
-    const uint4* own = ab.box[0];  // ab.box[rank] without indexing the parameter struct dynamically
+    const uint4* own = ax.box[0];  // ax.box[rank] without indexing the parameter struct dynamically
 #pragma unroll
     for (int q = 1; q < HJ_MAX_PEERS; q++)
-        if (q == rank) own = ab.box[q];
+        if (q == rank) own = ax.box[q];
+    own += par;
 #pragma unroll
     for (int q = 0; q < HJ_MAX_PEERS; q++)
         if (q < world && q != rank) {
-            uint4* to = ab.box[q] + (size_t)rank * slot_vecs + 2 * (size_t)i;
+            uint4* to = ax.box[q] + par + (size_t)rank * slot_vecs + 2 * (size_t)i;
             st_sys_v4(to, w0);
             st_sys_v4(to + 1, w1);
         }
@@ -274,10 +273,17 @@ array_allreduce_kernel(int rank, int world, uint32_t epoch, ArrayBoxes ab, uint3
     }
 }
 
-// exchange epochs are 31-bit and never 0 (0 is what a cleared mailbox holds; bit 31 is a mode flag)
-void next_xepoch(hj_comm* c) {
-    c->xepoch = (c->xepoch + 1) & 0x7fffffffu;
-    if (c->xepoch == 0) c->xepoch = 1;
+template <typename T, int OP>
+__global__ void __launch_bounds__(256)
+array_allreduce_kernel(ArrayPeerView ax, uint32_t* __restrict__ dst32, uint32_t n) {
+    static_assert(sizeof(T) == 4, "4-byte elements");
+    __shared__ uint32_t s_epoch;
+    if (threadIdx.x == 0) s_epoch = xepoch_begin(ax.xepoch);
+    __syncthreads();
+    const uint32_t epoch = s_epoch;
+    const uint32_t i = blockIdx.x * 256 + threadIdx.x;
+    if (4 * i < n) array_allreduce_element<T, OP>(ax, epoch, i, dst32, n);
+    array_exchange_commit(ax, epoch);  // the CTA that finishes last commits the epoch
 }
 
 PeerView peer_view(hj_comm* c) {
@@ -285,33 +291,29 @@ PeerView peer_view(hj_comm* c) {
     for (int i = 0; i < HJ_MAX_PEERS; i++) pv.box[i] = reinterpret_cast<unsigned long long*>(c->peer_mailbox[i]);
     pv.rank = c->rank;
     pv.world = c->world;
+    pv.xepoch = xepoch_slot(c);
     return pv;
 }
 
-ArrayPeerView array_view(hj_comm* c) {  // consumes one exchange epoch
+ArrayPeerView array_view(hj_comm* c) {
     ArrayPeerView ax;
-    next_xepoch(c);
-    const size_t parity_off = (size_t)(c->xepoch & 1u) * (size_t)c->world * HJ_ARRAYSLOT_BYTES;
-    for (int r = 0; r < HJ_MAX_PEERS; r++)
-        ax.box[r] = r < c->world ? (uint4*)(reinterpret_cast<char*>(c->peer_arraybox[r]) + parity_off) : nullptr;
+    for (int r = 0; r < HJ_MAX_PEERS; r++) ax.box[r] = r < c->world ? reinterpret_cast<uint4*>(c->peer_arraybox[r]) : nullptr;
     ax.rank = c->rank;
     ax.world = c->world;
-    ax.epoch = c->xepoch;
     ax.slot_vecs = (uint32_t)(HJ_ARRAYSLOT_BYTES / 16);
+    ax.parity_vecs = (uint32_t)((size_t)c->world * HJ_ARRAYSLOT_BYTES / 16);
+    ax.xepoch = xepoch_slot(c);
+    ax.done = xepoch_slot(c) + 1;
     return ax;
 }
 
 // dst (n elements of a 4-byte type) = fold over ranks of their dst, through the peer inboxes
-// `view`: an epoch the caller has already drawn (array_view), else a new one is drawn here
 template <typename T>
-hj_status peer_array_allreduce(hj_comm* c, hj_reduce_op op, void* dst, size_t n, const ArrayPeerView* view) {
+hj_status peer_array_allreduce(hj_comm* c, hj_reduce_op op, void* dst, size_t n) {
     const uint32_t n_vec = (uint32_t)((n + 3) / 4);
-    const ArrayPeerView ax = view ? *view : array_view(c);
+    const ArrayPeerView ax = array_view(c);
     const unsigned grid = (n_vec + 255) / 256;
-    ArrayBoxes ab;
-    for (int r = 0; r < HJ_MAX_PEERS; r++) ab.box[r] = ax.box[r];
-#define HJ_COMBINE(OP) \
-    array_allreduce_kernel<T, OP><<<grid, 256, 0, c->dev->stream>>>(c->rank, c->world, ax.epoch, ab, (uint32_t*)dst, (uint32_t)n)
+#define HJ_COMBINE(OP) array_allreduce_kernel<T, OP><<<grid, 256, 0, c->dev->stream>>>(ax, (uint32_t*)dst, (uint32_t)n)
     switch (op) {
     case HJ_REDUCE_SUM: HJ_COMBINE(HJ_REDUCE_SUM); break;
     case HJ_REDUCE_MAX: HJ_COMBINE(HJ_REDUCE_MAX); break;
@@ -328,8 +330,7 @@ hj_status peer_array_allreduce(hj_comm* c, hj_reduce_op op, void* dst, size_t n,
 hj_status gather_scalars(hj_comm* c, size_t es) {
     if (c->p2p) {
         PeerView pv = peer_view(c);
-        next_xepoch(c);
-        peer_allgather_kernel<<<1, 32, 0, c->dev->stream>>>(pv, c->xepoch, local_slot(c), (int)es, gathered_slot(c));
+        peer_allgather_kernel<<<1, 32, 0, c->dev->stream>>>(pv, local_slot(c), (int)es, gathered_slot(c));
         return check_launch(c->dev, "peer_allgather_kernel");
     }
     HJ_TRY(need_comm_nccl(c, "the all-gather fallback"));
@@ -451,10 +452,9 @@ hj_status sharded_compress(hj_comm* c, size_t n_local, uint32_t index_base, cons
     }
     if (c->p2p && compress_can_fuse_exchange(n_local, mask)) {
         PeerView pv = peer_view(c);
-        next_xepoch(c);
-        const bool zt_in_kernel = zero_tail && ((uintptr_t)index_out & 15u) == 0 && !getenv("HJ_ZERO_TAIL_KERNEL");
-        HJ_TRY(launch_compress(c->dev, n_local, nullptr, out_count, mask, index_out, index_base, zt_in_kernel, counts, &pv,
-                               c->xepoch));
+        static const bool zt_kernel = getenv("HJ_ZERO_TAIL_KERNEL") != nullptr;
+        const bool zt_in_kernel = zero_tail && ((uintptr_t)index_out & 15u) == 0 && !zt_kernel;
+        HJ_TRY(launch_compress(c->dev, n_local, nullptr, out_count, mask, index_out, index_base, zt_in_kernel, counts, &pv));
         if (zero_tail && !zt_in_kernel) return launch_compress_zero_tail(c->dev, index_out, counts + c->rank, n_local);
         return HJ_OK;
     }
@@ -477,8 +477,7 @@ hj_status exclusive_offset_of_totals(hj_comm* c, hj_type_kind ty, size_t n_local
     const size_t es = type_size(ty);
     if (c->p2p) {
         PeerView pv = peer_view(c);
-        next_xepoch(c);
-        return launch_reduce(c->dev, HJ_REDUCE_SUM, ty, n_local, src, seed, &pv, c->xepoch | 0x80000000u);
+        return launch_reduce(c->dev, HJ_REDUCE_SUM, ty, n_local, src, seed, &pv, 2u);
     }
     HJ_TRY(launch_reduce(c->dev, HJ_REDUCE_SUM, ty, n_local, src, local_slot(c)));
     HJ_TRY(gather_scalars(c, es));
@@ -545,13 +544,13 @@ hj_status hj_comm_create(hj_device* dev, const uint8_t id[HJ_UNIQUE_ID_BYTES], i
         delete c;
         return fail(HJ_ERR_NCCL, "ncclCommInitRank failed: %s", nccl().GetErrorString(r));
     }
-    cudaError_t e = cudaMalloc(&c->scratch, 64 + 8 * (size_t)world + 64 + 64);
+    cudaError_t e = cudaMalloc(&c->scratch, scratch_bytes(world));
     if (e != cudaSuccess) {
         nccl().CommDestroy(c->comm);
         delete c;
         return fail(HJ_ERR_CUDA, "cudaMalloc failed: %s", cudaGetErrorString(e));
     }
-    cudaMemsetAsync(c->scratch, 0, 64 + 8 * (size_t)world + 64 + 64, dev->stream);
+    cudaMemsetAsync(c->scratch, 0, scratch_bytes(world), dev->stream);
     setup_peer_mailboxes(c);
     dev->rc.fetch_add(1);
     *out = c;
@@ -569,12 +568,12 @@ hj_status hj_comm_create_local(hj_device* dev, int32_t rank, int32_t world, hj_c
     c->rank = rank;
     c->world = world;
     c->connected = world == 1;
-    cudaError_t e = cudaMalloc(&c->scratch, 64 + 8 * (size_t)world + 64 + 64);
+    cudaError_t e = cudaMalloc(&c->scratch, scratch_bytes(world));
     if (e != cudaSuccess) {
         delete c;
         return fail(HJ_ERR_CUDA, "cudaMalloc failed: %s", cudaGetErrorString(e));
     }
-    cudaMemsetAsync(c->scratch, 0, 64 + 8 * (size_t)world + 64 + 64, dev->stream);
+    cudaMemsetAsync(c->scratch, 0, scratch_bytes(world), dev->stream);
     cudaIpcMemHandle_t mine;
     memset(&mine, 0, sizeof(mine));
     if (world > 1 && !alloc_mailbox(c, &mine)) {
@@ -646,8 +645,7 @@ hj_status hj_sharded_reduce(hj_comm* c, hj_reduce_op op, hj_type_kind ty, size_t
         // ONE kernel: the CTA that finishes the local reduction sends the partial to every peer's
         // mailbox over NVLink, collects theirs and folds them in rank order (reduce.cu)
         PeerView pv = peer_view(c);
-        next_xepoch(c);
-        return launch_reduce(c->dev, op, ty, n_local, src->ptr, dst->ptr, &pv, c->xepoch);
+        return launch_reduce(c->dev, op, ty, n_local, src->ptr, dst->ptr, &pv, 1u);
     }
     // local partial -> all-gather -> fold in rank order with the same reduction kernel
     HJ_TRY(launch_reduce(c->dev, op, ty, n_local, src->ptr, local_slot(c)));
@@ -691,9 +689,7 @@ hj_status hj_sharded_prefix_sum_deferred(hj_comm* c, hj_type_kind ty, size_t n_l
         // ONE kernel, 2 * sizeof(T) bytes/element: the local scan; the CTA that owns the last tile sends
         // the shard total to every peer's mailbox and leaves the sum of the lower ranks' totals in seed_out
         PeerView pv = peer_view(c);
-        next_xepoch(c);
-        return launch_prefix_sum(c->dev, ty, n_local, inclusive != 0, src->ptr, dst->ptr, nullptr, seed_out->ptr, &pv,
-                                 c->xepoch);
+        return launch_prefix_sum(c->dev, ty, n_local, inclusive != 0, src->ptr, dst->ptr, nullptr, seed_out->ptr, &pv);
     }
     // small / misaligned shards, or no peer memory: totals pass + exchange, then the unseeded scan
     HJ_TRY(exclusive_offset_of_totals(c, ty, n_local, src->ptr, seed_out->ptr));
@@ -742,16 +738,16 @@ hj_status hj_sharded_scatter_reduce(hj_comm* c, hj_reduce_op op, hj_type_kind ty
     // packed-16 histogram (BASELINE: 2^16 u32 bins) folds its private counters AND runs the
     // exchange over peer memory in one kernel (scatter.cu: hist_fold_exchange_kernel).
     bool exchanged = false;
-    const bool small_array = c->p2p && c->world > 1 && es == 4 && n_dst * 4 <= HJ_ARRAYBOX_BYTES && !getenv("HJ_NO_PEER_ARRAY");
+    static const bool no_peer_array = getenv("HJ_NO_PEER_ARRAY") != nullptr;
+    const bool small_array = c->p2p && c->world > 1 && es == 4 && n_dst * 4 <= HJ_ARRAYBOX_BYTES && !no_peer_array;
     if (small_array && op == HJ_REDUCE_SUM && (ty == HJ_U32 || ty == HJ_I32) && !src && n_local >= 1) {
         ArrayPeerView ax = array_view(c);
-        // every rank must consume this epoch whether or not its own launch takes the fused path; the
-        // choice below only depends on (n_dst, literal, alignment, n_local >= 2^20) — ranks whose
-        // shard is too small for the ring kernel run the plain exchange with the SAME epoch
+        // a rank whose shard is too small for the ring kernel runs the plain exchange kernel instead of
+        // the fused one: same wire format, same (device-resident) epoch, so the ranks may differ
         HJ_TRY(launch_scatter_reduce(c->dev, op, ty, n_local, (const uint32_t*)idx->ptr, nullptr, literal, dst->ptr, n_dst, &ax,
                                      &exchanged));
         if (exchanged) return HJ_OK;
-        return peer_array_allreduce<uint32_t>(c, op, dst->ptr, n_dst, &ax);
+        return peer_array_allreduce<uint32_t>(c, op, dst->ptr, n_dst);
     } else {
         HJ_TRY(launch_scatter_reduce(c->dev, op, ty, n_local, (const uint32_t*)idx->ptr, src ? src->ptr : nullptr, literal,
                                      dst->ptr, n_dst));
@@ -760,9 +756,9 @@ hj_status hj_sharded_scatter_reduce(hj_comm* c, hj_reduce_op op, hj_type_kind ty
     // small 4-byte arrays: exchange over peer memory
     const bool float_bits = ty == HJ_F32 && (op == HJ_REDUCE_OR || op == HJ_REDUCE_AND || op == HJ_REDUCE_XOR);
     if (small_array && ((uintptr_t)dst->ptr & 3u) == 0 && !float_bits) {
-        if (ty == HJ_F32) return peer_array_allreduce<float>(c, op, dst->ptr, n_dst, nullptr);
-        if (ty == HJ_I32) return peer_array_allreduce<int32_t>(c, op, dst->ptr, n_dst, nullptr);
-        if (ty == HJ_U32) return peer_array_allreduce<uint32_t>(c, op, dst->ptr, n_dst, nullptr);
+        if (ty == HJ_F32) return peer_array_allreduce<float>(c, op, dst->ptr, n_dst);
+        if (ty == HJ_I32) return peer_array_allreduce<int32_t>(c, op, dst->ptr, n_dst);
+        if (ty == HJ_U32) return peer_array_allreduce<uint32_t>(c, op, dst->ptr, n_dst);
     }
     HJ_TRY(need_comm_nccl(c, "hj_sharded_scatter_reduce of an array too large for the peer inbox"));
     ncclDataType_t dt;

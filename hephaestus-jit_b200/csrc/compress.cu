@@ -196,11 +196,11 @@ struct CompressOp {
         uint32_t* out_count;
         uint32_t index_base;
         size_t n;  // ZT: number of mask elements = length of index_out
-        // sharded compaction (comm.cu): xepoch != 0 makes the CTA that owns the last tile exchange the
+        // sharded compaction (comm.cu): `exchange` makes the CTA that owns the last tile exchange the
         // per-rank counts over peer memory — out_count[0] = global count, counts_out[q] = count of rank q
         uint32_t* counts_out;
         PeerView pv;
-        uint32_t xepoch;
+        uint32_t exchange;
     };
     // aux layout (shared memory behind the ring): TSLOTS mask planes of TILE/8 bytes (one u16 per
     // 16 mask bytes), then one 1 KiB index stage per consumer warp.  Phase 1 leaves only the masks
@@ -347,11 +347,11 @@ struct CompressOp {
     }
     // compress_large.glsl:214-216: the last partition publishes the count
     static __device__ __forceinline__ void finish(P total, const Args& a, int lane) {
-        if (a.xepoch == 0) {
+        if (a.exchange == 0) {
             if (lane == 0) a.out_count[0] = total;
             return;
         }
-        const uint32_t c = (uint32_t)peer_allgather_warp(a.pv, a.xepoch, total, lane);  // lane q: count of rank q
+        const uint32_t c = (uint32_t)peer_allgather_warp(a.pv, total, lane);  // lane q: count of rank q
         if (a.counts_out && lane < a.pv.world) a.counts_out[lane] = c;
         const uint32_t all = __reduce_add_sync(0xffffffffu, c);
         if (lane == 0) a.out_count[0] = all;
@@ -363,7 +363,7 @@ __global__ void __launch_bounds__((CR_WARPS + 3) * 32, 1)
 compress_ring_kernel(const uint8_t* __restrict__ mask, size_t n, const uint32_t* __restrict__ size_buf,
                      uint32_t* __restrict__ out_count, uint32_t* __restrict__ index_out, uint32_t index_base,
                      LookbackView lb, uint32_t G, unsigned long long* trace, uint32_t* __restrict__ counts_out,
-                     PeerView pv, uint32_t xepoch) {
+                     PeerView pv, uint32_t exchange) {
     extern __shared__ __align__(128) char smem[];
     size_t n_eff = n;
     if (size_buf) {  // DynSize: device-resident element count (graph.rs:503-508)
@@ -377,7 +377,7 @@ compress_ring_kernel(const uint8_t* __restrict__ mask, size_t n, const uint32_t*
         out_count[0] = 0;
     }
     using Op = CompressOp<CR_TILE / CR_WARPS, CR_TILE, CR_TSLOTS, ZT>;
-    typename Op::Args args{index_out, out_count, index_base, n_eff, counts_out, pv, xepoch};
+    typename Op::Args args{index_out, out_count, index_base, n_eff, counts_out, pv, exchange};
     ring_pipeline<Op, CR_TILE, CR_STAGES, CR_WARPS, CR_AHEAD, CR_TSLOTS, true, 8, TRACE>(
         reinterpret_cast<const char*>(mask), n_eff, n_tiles, 0u, lb, G, args, smem, trace);
 }
@@ -427,7 +427,7 @@ bool compress_can_fuse_exchange(size_t n, const uint8_t* mask) {
 
 hj_status launch_compress(hj_device* dev, size_t n, const uint32_t* size_buf, uint32_t* out_count,
                           const uint8_t* mask, uint32_t* index_out, uint32_t index_base, bool zero_tail,
-                          uint32_t* counts_out, const PeerView* peers, uint32_t xepoch) {
+                          uint32_t* counts_out, const PeerView* peers) {
     HJ_REQUIRE(n <= 0xffffffffull, "compress: n does not fit the u32 index type");
     HJ_REQUIRE(!peers || (compress_can_fuse_exchange(n, mask) && !size_buf),
                "compress: the fused exchange needs the ring kernel and a static size");
@@ -453,10 +453,10 @@ hj_status launch_compress(hj_device* dev, size_t n, const uint32_t* size_buf, ui
         LookbackView view = lookback_view(dev->lookback.base, dev->lookback.capacity_tiles, 0);
         const unsigned grid = (unsigned)(tiles < (size_t)dev->sm_count ? tiles : (size_t)dev->sm_count);
         auto launch = [&](auto kernel, size_t smem) -> hj_status {
-            HJ_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            HJ_TRY(ensure_dynamic_smem(dev, (const void*)kernel, smem));
             HJ_CUDA(launch_pdl(kernel, dim3(grid), dim3((CR_WARPS + 3) * 32), smem, dev->stream, mask, n, size_buf, out_count,
                                index_out, index_base, view, (grid + 31u) & ~31u, g_compress_trace, counts_out,
-                               peers ? *peers : PeerView(), peers ? xepoch : 0u));
+                               peers ? *peers : PeerView(), peers ? 1u : 0u));
             return HJ_OK;
         };
         const size_t smem_small = ring_smem_bytes<uint32_t, 28672, 5, CR_WARPS, 8>(8 * (28672 / 8) + CR_WARPS * 1024);

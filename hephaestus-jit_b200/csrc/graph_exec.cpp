@@ -32,6 +32,7 @@ struct GraphInstance {
     uint32_t n_epochs = 0;     // look-back epochs one replay consumes (host-side wrap accounting)
     uint64_t n_launches = 0;   // kernel launches one replay stands for
     bool uncapturable = false;
+    std::vector<uint32_t> deferred_out;  // sharded launches: the `deferred` flags the pass list leaves behind
 };
 struct GraphCache {
     std::unordered_map<uint64_t, std::vector<GraphInstance>> by_key;
@@ -667,9 +668,7 @@ extern "C" hj_status hj_execute_graph_sharded(hj_comm* comm, const hj_pass* pass
         HJ_REQUIRE(shards[r].placement == HJ_RES_REPLICATED || shards[r].placement == HJ_RES_SHARDED,
                    "resource %u has no placement (run hj_shard_plan first)", r);
     hj_device* dev = comm_device(comm);
-    // the exchange epochs of the sharded kernels are launch parameters: not replayable from a captured
-    // CUDA graph, so a sharded launch always runs pass by pass, with the device lock held throughout
-    DeviceGuard g(dev);
+    DeviceGuard g(dev);  // held throughout: the exchanges of one launch must not interleave with another thread's
     return execute_passes(dev, &sc, passes, n_passes, env, descs, n_resources, report);
 }
 
@@ -682,11 +681,14 @@ void destroy_instance(GraphInstance& g) {
 }
 }  // namespace
 
-extern "C" hj_status hj_execute_graph_cached(hj_device* dev, uint64_t graph_key, const hj_pass* passes,
-                                             uint32_t n_passes, hj_buffer* const* env, const hj_buffer_desc* descs,
-                                             uint32_t n_resources, uint32_t* how) {
-    HJ_REQUIRE(dev && (passes || n_passes == 0), "hj_execute_graph_cached: null argument");
-    HJ_REQUIRE((env && descs) || n_resources == 0, "hj_execute_graph_cached: null environment");
+namespace {
+// The relaunch path shared by hj_execute_graph_cached and hj_execute_graph_sharded_cached.  For a
+// sharded pass list (`sc`) an instance also belongs to the communicator, the placement, the seed
+// buffers and the `deferred` state the inputs arrive in; the state the list leaves behind is recorded
+// at capture and restored on every replay.  The sharded kernels read their exchange epoch from device
+// memory (peer.cuh), so a replay needs no new launch parameters.
+hj_status execute_cached(hj_device* dev, const ShardCtx* sc, uint64_t graph_key, const hj_pass* passes, uint32_t n_passes,
+                         hj_buffer* const* env, const hj_buffer_desc* descs, uint32_t n_resources, uint32_t* how) {
     static const bool disabled = getenv("HJ_NO_CUDA_GRAPHS") != nullptr;
     if (how) *how = 0;
     DeviceGuard g(dev);  // held across the whole capture: nobody else may enqueue on the capturing stream
@@ -694,14 +696,25 @@ extern "C" hj_status hj_execute_graph_cached(hj_device* dev, uint64_t graph_key,
     GraphCache& gc = *dev->gcache;
     if (disabled || n_passes == 0) {
         gc.plain++;
-        return hj_execute_graph(dev, passes, n_passes, env, descs, n_resources, nullptr);
+        return execute_passes(dev, sc, passes, n_passes, env, descs, n_resources, nullptr);
     }
     std::vector<void*> sig(n_resources);
     for (uint32_t i = 0; i < n_resources; i++) sig[i] = env[i] ? env[i]->ptr : nullptr;
+    if (sc) {
+        sig.push_back((void*)sc->comm);
+        for (uint32_t i = 0; i < n_resources; i++) {
+            sig.push_back(sc->shards[i].seed ? sc->shards[i].seed->ptr : nullptr);
+            sig.push_back((void*)(uintptr_t)(sc->shards[i].placement * 2u + (sc->shards[i].deferred ? 1u : 0u)));
+        }
+    }
     std::vector<GraphInstance>& insts = gc.by_key[graph_key];
     GraphInstance* inst = nullptr;
     for (GraphInstance& c : insts)
         if (c.ptrs == sig) inst = &c;
+    auto run_plain = [&]() {
+        gc.plain++;
+        return execute_passes(dev, sc, passes, n_passes, env, descs, n_resources, nullptr);
+    };
 
     if (!inst) {
         // first sight of these addresses: execute normally (compiles kernels, sizes every scratch)
@@ -716,8 +729,7 @@ extern "C" hj_status hj_execute_graph_cached(hj_device* dev, uint64_t graph_key,
         fresh.ptrs = std::move(sig);
         fresh.last_use = ++gc.clock;
         insts.push_back(std::move(fresh));
-        gc.plain++;
-        return hj_execute_graph(dev, passes, n_passes, env, descs, n_resources, nullptr);
+        return run_plain();
     }
     inst->last_use = ++gc.clock;
     if (inst->exec && inst->generation != dev->lookback.generation) destroy_instance(*inst);  // stale scratch pointers
@@ -725,23 +737,25 @@ extern "C" hj_status hj_execute_graph_cached(hj_device* dev, uint64_t graph_key,
         HJ_TRY(count_epoch(dev, inst->n_epochs));
         HJ_CUDA(cudaGraphLaunch(inst->exec, dev->stream));
         dev->launches.fetch_add(inst->n_launches, std::memory_order_relaxed);
+        if (sc)
+            for (uint32_t i = 0; i < n_resources; i++) sc->shards[i].deferred = inst->deferred_out[i];
         gc.replayed++;
         if (how) *how = 2;
         return HJ_OK;
     }
-    if (inst->uncapturable) {
-        gc.plain++;
-        return hj_execute_graph(dev, passes, n_passes, env, descs, n_resources, nullptr);
-    }
+    if (inst->uncapturable) return run_plain();
     // second launch with these addresses: capture the pass list
     const uint32_t epochs0 = dev->lookback.epoch;
     const uint64_t launches0 = dev->launches.load(std::memory_order_relaxed);
     const uint64_t gen0 = dev->lookback.generation;
+    std::vector<uint32_t> deferred_in;
+    if (sc)
+        for (uint32_t i = 0; i < n_resources; i++) deferred_in.push_back(sc->shards[i].deferred);
     cudaGraph_t graph = nullptr;
     cudaError_t e = cudaStreamBeginCapture(dev->stream, cudaStreamCaptureModeThreadLocal);
     hj_status st = HJ_ERR_CUDA;
     if (e == cudaSuccess) {
-        st = hj_execute_graph(dev, passes, n_passes, env, descs, n_resources, nullptr);
+        st = execute_passes(dev, sc, passes, n_passes, env, descs, n_resources, nullptr);
         e = cudaStreamEndCapture(dev->stream, &graph);
     }
     const uint32_t n_epochs = dev->lookback.epoch - epochs0;
@@ -756,16 +770,52 @@ extern "C" hj_status hj_execute_graph_cached(hj_device* dev, uint64_t graph_key,
         inst->uncapturable = true;
         dev->lookback.epoch = epochs0;
         dev->launches.store(launches0, std::memory_order_relaxed);
-        gc.plain++;
-        return hj_execute_graph(dev, passes, n_passes, env, descs, n_resources, nullptr);
+        if (sc)
+            for (uint32_t i = 0; i < n_resources; i++) sc->shards[i].deferred = deferred_in[i];
+        return run_plain();
     }
     inst->generation = gen0;
     inst->n_epochs = n_epochs;
     inst->n_launches = dev->launches.load(std::memory_order_relaxed) - launches0;
+    inst->deferred_out.clear();
+    if (sc)
+        for (uint32_t i = 0; i < n_resources; i++) inst->deferred_out.push_back(sc->shards[i].deferred);
     HJ_CUDA(cudaGraphLaunch(inst->exec, dev->stream));
     gc.captured++;
     if (how) *how = 1;
     return HJ_OK;
+}
+}  // namespace
+
+extern "C" hj_status hj_execute_graph_cached(hj_device* dev, uint64_t graph_key, const hj_pass* passes,
+                                             uint32_t n_passes, hj_buffer* const* env, const hj_buffer_desc* descs,
+                                             uint32_t n_resources, uint32_t* how) {
+    HJ_REQUIRE(dev && (passes || n_passes == 0), "hj_execute_graph_cached: null argument");
+    HJ_REQUIRE((env && descs) || n_resources == 0, "hj_execute_graph_cached: null environment");
+    return execute_cached(dev, nullptr, graph_key, passes, n_passes, env, descs, n_resources, how);
+}
+
+extern "C" hj_status hj_execute_graph_sharded_cached(hj_comm* comm, uint64_t graph_key, const hj_pass* passes, uint32_t n_passes,
+                                                     hj_buffer* const* env, const hj_buffer_desc* descs, uint32_t n_resources,
+                                                     hj_shard_desc* shards, uint32_t* how) {
+    HJ_REQUIRE(comm && (passes || n_passes == 0), "hj_execute_graph_sharded_cached: null argument");
+    HJ_REQUIRE((env && descs && shards) || n_resources == 0, "hj_execute_graph_sharded_cached: null environment");
+    ShardCtx sc;
+    sc.comm = comm;
+    sc.shards = shards;
+    int32_t rank = 0, world = 1, peer_memory = 0;
+    HJ_TRY(hj_comm_info(comm, &rank, &world, &peer_memory, nullptr));
+    sc.rank = rank;
+    sc.world = world;
+    for (uint32_t r = 0; r < n_resources; r++)
+        HJ_REQUIRE(shards[r].placement == HJ_RES_REPLICATED || shards[r].placement == HJ_RES_SHARDED,
+                   "resource %u has no placement (run hj_shard_plan first)", r);
+    hj_device* dev = comm_device(comm);
+    DeviceGuard g(dev);
+    if (how) *how = 0;
+    // without peer memory the exchanges are NCCL calls: those run pass by pass
+    if (world > 1 && !peer_memory) return execute_passes(dev, &sc, passes, n_passes, env, descs, n_resources, nullptr);
+    return execute_cached(dev, &sc, graph_key, passes, n_passes, env, descs, n_resources, how);
 }
 
 extern "C" hj_status hj_graph_cache_drop(hj_device* dev, uint64_t graph_key) {

@@ -114,26 +114,27 @@ hj_status count_epoch(hj_device* dev, uint32_t n = 1);
 
 // ---- kernel launchers (defined in the .cu files; device lock held by the caller) ---------
 struct PeerView;  // peer.cuh
-// `peers` / `epoch` (optional): fold the result with the partials of the other ranks over peer
-// memory inside the same kernel (sharded reduce, comm.cu)
+// `peers` / `mode` (optional): fold the result with the partials of the other ranks over peer memory
+// inside the same kernel (comm.cu) — mode 1: all ranks (sharded reduce), mode 2: the ranks before
+// this one (the seed of a sharded scan)
 hj_status launch_reduce(hj_device* dev, hj_reduce_op op, hj_type_kind ty, size_t n,
-                        const void* src, void* dst, const PeerView* peers = nullptr, uint32_t epoch = 0);
-// `seed_out` / `peers` / `xepoch` (optional, ring kernel only — see prefix_sum_can_fuse_exchange):
+                        const void* src, void* dst, const PeerView* peers = nullptr, uint32_t mode = 0);
+// `seed_out` / `peers` (optional, ring kernel only — see prefix_sum_can_fuse_exchange):
 // the kernel also exchanges the shard totals over peer memory and writes this rank's exclusive
 // offset to seed_out[0] (the DEFERRED seed of a sharded scan, comm.cu)
 hj_status launch_prefix_sum(hj_device* dev, hj_type_kind ty, size_t n, bool inclusive,
                             const void* src, void* dst, const void* seed, void* seed_out = nullptr,
-                            const PeerView* peers = nullptr, uint32_t xepoch = 0);
+                            const PeerView* peers = nullptr);
 bool prefix_sum_can_fuse_exchange(hj_type_kind ty, size_t n, const void* src, const void* dst);
 hj_status launch_compress_zero_tail(hj_device* dev, uint32_t* index_out, const uint32_t* count, size_t n);
 // zero_tail: also leave index_out[count .. n) zeroed (in the ring kernel where it can, else by
 // launch_compress_zero_tail afterwards)
-// `counts_out` / `peers` / `xepoch` (optional, ring kernel only — see compress_can_fuse_exchange): the
+// `counts_out` / `peers` (optional, ring kernel only — see compress_can_fuse_exchange): the
 // kernel also exchanges the per-rank counts over peer memory; out_count[0] then holds the GLOBAL
 // count and counts_out[q] (may be NULL) the count of rank q
 hj_status launch_compress(hj_device* dev, size_t n, const uint32_t* size_buf, uint32_t* out_count,
                           const uint8_t* mask, uint32_t* index_out, uint32_t index_base, bool zero_tail = false,
-                          uint32_t* counts_out = nullptr, const PeerView* peers = nullptr, uint32_t xepoch = 0);
+                          uint32_t* counts_out = nullptr, const PeerView* peers = nullptr);
 bool compress_can_fuse_exchange(size_t n, const uint8_t* mask);
 struct ArrayPeerView;  // peer.cuh
 // `ax` (optional): on the packed-16 histogram path the fold kernel also all-reduces the bins over
@@ -149,6 +150,10 @@ hj_status launch_fill(hj_device* dev, void* dst, size_t n, size_t elem_bytes, ui
 hj_device* comm_device(hj_comm* c);
 hj_status sharded_compress_pass(hj_comm* c, size_t n_local, uint32_t index_base, hj_buffer* mask, hj_buffer* index_out,
                                 hj_buffer* out_count, bool zero_tail);
+
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) once per (device, kernel, size) instead of on every
+// launch (a driver call of a few microseconds on the relaunch path).  Device lock held by the caller.
+hj_status ensure_dynamic_smem(hj_device* dev, const void* kernel, size_t smem);
 
 // Launch with programmatic stream serialization (PDL): the kernel may be scheduled while the kernel in
 // front of it on the stream is still draining — its CTAs run their prologue (shared-memory carve-out,

@@ -17,7 +17,22 @@ constexpr int HJ_MAX_PEERS = 16;
 struct PeerView {
     unsigned long long* box[HJ_MAX_PEERS];
     int rank, world;
+    // The exchange epoch lives ON THE DEVICE (one counter per communicator, in its scratch): a kernel
+    // that runs an exchange reads it, uses the next value and commits it when the exchange is done.
+    // Every rank performs the same sequence of exchanges, so the counters advance in lock step — and
+    // no launch parameter changes from one launch to the next, which is what lets a whole sharded
+    // pass list be replayed from a captured CUDA graph (graph_exec.cpp).
+    uint32_t* xepoch;
 };
+
+// exchange epochs are 31-bit and never 0 (0 is what a cleared mailbox holds)
+__device__ __forceinline__ uint32_t xepoch_next(uint32_t v) {
+    v = (v + 1u) & 0x7fffffffu;
+    return v ? v : 1u;
+}
+__device__ __forceinline__ uint32_t xepoch_begin(const uint32_t* counter) {
+    return xepoch_next(*reinterpret_cast<const volatile uint32_t*>(counter));
+}
 
 // pv.box[peer] without indexing the kernel-parameter struct dynamically (which would make every
 // thread copy the whole struct to local memory in the kernel prologue): a select chain over
@@ -87,11 +102,26 @@ __device__ __forceinline__ unsigned long long peer_exchange(const PeerView& pv, 
 // slots; a rank PUSHES its elements as self-validating 8-byte words (element, epoch) into slot
 // [its rank] of every peer's inbox and polls its own inbox for the peers' words (comm.cu).
 struct ArrayPeerView {
-    uint4* box[HJ_MAX_PEERS];  // inbox of every rank at the current parity (box[rank] = own, local memory)
+    uint4* box[HJ_MAX_PEERS];  // inbox of every rank, parity 0 (box[rank] = own, local memory)
     int rank, world;
-    uint32_t epoch;
     uint32_t slot_vecs;        // uint4 per slot: one uint4 carries two (element, epoch) pairs
+    uint32_t parity_vecs;      // distance between the two parities of an inbox, in uint4
+    uint32_t* xepoch;          // device-resident exchange counter (see PeerView)
+    uint32_t* done;            // ticket of the multi-CTA exchange kernels: the last CTA commits the epoch
 };
+// Called by every thread of a CTA of a multi-CTA exchange kernel, after its own part of the exchange
+// (contains a __syncthreads): the CTA that finishes last commits the epoch — by then every CTA has read it.
+__device__ __forceinline__ void array_exchange_commit(const ArrayPeerView& ax, uint32_t epoch) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        const unsigned t = atomicAdd(ax.done, 1u);
+        if (t == gridDim.x * gridDim.y - 1) {
+            *ax.done = 0;
+            *ax.xepoch = epoch;
+        }
+    }
+}
 __device__ __forceinline__ void st_sys_v4(uint4* p, uint4 v) {
     asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
@@ -102,15 +132,17 @@ __device__ __forceinline__ uint4 ld_sys_v4(const uint4* p) {
 }
 // Pair `pair` of the array (elements 2*pair, 2*pair+1): send (a, b) to every peer, return in
 // (*out_a, *out_b) the sum over all ranks in rank order (u32, wrapping) — bit-identical on every rank.
-__device__ __forceinline__ void array_pair_allreduce_add(const ArrayPeerView& ax, uint32_t pair, uint32_t a, uint32_t b,
-                                                         uint32_t* out_a, uint32_t* out_b) {
-    const uint4 w = make_uint4(a, ax.epoch, b, ax.epoch);
+__device__ __forceinline__ void array_pair_allreduce_add(const ArrayPeerView& ax, uint32_t epoch, uint32_t pair, uint32_t a,
+                                                         uint32_t b, uint32_t* out_a, uint32_t* out_b) {
+    const uint4 w = make_uint4(a, epoch, b, epoch);
+    const size_t par = (size_t)(epoch & 1u) * ax.parity_vecs;
     const uint4* own = ax.box[0];
 #pragma unroll
     for (int q = 0; q < HJ_MAX_PEERS; q++) {
         if (q == ax.rank) own = ax.box[q];
-        if (q < ax.world && q != ax.rank) st_sys_v4(ax.box[q] + (size_t)ax.rank * ax.slot_vecs + pair, w);
+        if (q < ax.world && q != ax.rank) st_sys_v4(ax.box[q] + par + (size_t)ax.rank * ax.slot_vecs + pair, w);
     }
+    own += par;
     uint32_t sa = 0, sb = 0;
 #pragma unroll
     for (int q = 0; q < HJ_MAX_PEERS; q++)
@@ -121,7 +153,7 @@ __device__ __forceinline__ void array_pair_allreduce_add(const ArrayPeerView& ax
                 unsigned ns = 20;
                 while (true) {
                     v = ld_sys_v4(from);
-                    if (v.y == ax.epoch && v.w == ax.epoch) break;
+                    if (v.y == epoch && v.w == epoch) break;
                     __nanosleep(ns);
                     if (ns < 500) ns *= 2;
                 }
@@ -135,10 +167,14 @@ __device__ __forceinline__ void array_pair_allreduce_add(const ArrayPeerView& ax
 
 // Executed by one full warp (e.g. the prefix warp of the ring kernels, in their `finish`): all-gather
 // of one value per rank — lane q (< world) returns the bits rank q contributed, other lanes 0.
-__device__ __forceinline__ unsigned long long peer_allgather_warp(const PeerView& pv, uint32_t epoch,
-                                                                  unsigned long long bits, int lane) {
+// Draws the next exchange epoch from the device-resident counter and commits it afterwards.
+__device__ __forceinline__ unsigned long long peer_allgather_warp(const PeerView& pv, unsigned long long bits, int lane) {
+    uint32_t epoch = lane == 0 ? xepoch_begin(pv.xepoch) : 0u;
+    epoch = __shfl_sync(0xffffffffu, epoch, 0);
     unsigned long long v = 0;
     if (lane < pv.world) v = peer_exchange(pv, epoch, bits, lane);
+    __syncwarp();
+    if (lane == 0) *pv.xepoch = epoch;
     return v;
 }
 

@@ -199,30 +199,34 @@ __device__ __forceinline__ S block_reduce(S v, S* smem) {
 }
 
 // Called by every thread of the CTA that holds the final local value (valid in thread 0).
-// epoch == 0: write it.  Otherwise (sharded reduce) this CTA also runs the exchange: the local
+// mode == 0: write it.  Otherwise (sharded reduce) this CTA also runs the exchange: the local
 // partial goes to every peer's mailbox over NVLink, theirs are collected from the own mailbox, and
 // thread 0 folds them IN RANK ORDER — compute and collective in one kernel, deterministic for floats.
+// mode == 1: the fold over ALL ranks (sharded reduce); mode == 2: the fold over the ranks BEFORE this
+// one (the seed of a sharded scan / compaction).
 template <typename T, typename S, int OP>
-__device__ __forceinline__ void finish(S v, T* __restrict__ dst, const PeerView& pv, uint32_t epoch) {
-    if (epoch == 0) {
+__device__ __forceinline__ void finish(S v, T* __restrict__ dst, const PeerView& pv, uint32_t mode) {
+    if (mode == 0) {
         if (threadIdx.x == 0) dst[0] = (T)v;
         return;
     }
     __shared__ unsigned long long s_mine;
     __shared__ unsigned long long s_all[HJ_MAX_PEERS];
+    __shared__ uint32_t s_epoch;
     if (threadIdx.x == 0) {
         T t = (T)v;
         unsigned long long bits = 0;
         memcpy(&bits, &t, sizeof(T));
         s_mine = bits;
+        s_epoch = xepoch_begin(pv.xepoch);
     }
     __syncthreads();
-    if ((int)threadIdx.x < pv.world) s_all[threadIdx.x] = peer_exchange(pv, epoch & 0x7fffffffu, s_mine, (int)threadIdx.x);
+    const uint32_t epoch = s_epoch;
+    if ((int)threadIdx.x < pv.world) s_all[threadIdx.x] = peer_exchange(pv, epoch, s_mine, (int)threadIdx.x);
     __syncthreads();
     if (threadIdx.x == 0) {
-        // epoch bit 31 selects what is written: the fold over ALL ranks (sharded reduce) or the
-        // fold over the ranks BEFORE this one (the seed of a sharded scan / compaction)
-        const int upto = (epoch >> 31) ? pv.rank : pv.world;
+        *pv.xepoch = epoch;  // the exchange is complete on this rank
+        const int upto = mode == 2 ? pv.rank : pv.world;
         S acc = identity<T, S, OP>();
         for (int q = 0; q < upto; q++) {
             T t;
@@ -236,7 +240,7 @@ __device__ __forceinline__ void finish(S v, T* __restrict__ dst, const PeerView&
 template <typename T, int OP, int THREADS, int UNROLL>
 __global__ void __launch_bounds__(THREADS)
 reduce_kernel(const T* __restrict__ src, size_t n, size_t head, typename Scalar<T>::type* partials,
-              unsigned* ticket, T* __restrict__ dst, PeerView pv, uint32_t epoch) {
+              unsigned* ticket, T* __restrict__ dst, PeerView pv, uint32_t mode) {
     using S = typename Scalar<T>::type;
     constexpr int VEC = 16 / sizeof(T);
     __shared__ S smem[THREADS / 32];
@@ -272,7 +276,7 @@ reduce_kernel(const T* __restrict__ src, size_t n, size_t head, typename Scalar<
 
     s = block_reduce<T, S, OP, THREADS>(s, smem);
     if (gridDim.x == 1) {
-        finish<T, S, OP>(s, dst, pv, epoch);
+        finish<T, S, OP>(s, dst, pv, mode);
         return;
     }
     if (threadIdx.x == 0) {
@@ -289,11 +293,11 @@ reduce_kernel(const T* __restrict__ src, size_t n, size_t head, typename Scalar<
     __syncthreads();  // smem reuse
     v = block_reduce<T, S, OP, THREADS>(v, smem);
     if (threadIdx.x == 0) *ticket = 0;  // ready for the next launch on this stream
-    finish<T, S, OP>(v, dst, pv, epoch);
+    finish<T, S, OP>(v, dst, pv, mode);
 }
 
 template <typename T, int OP>
-hj_status run(hj_device* dev, size_t n, const void* src, void* dst, const PeerView* peers, uint32_t epoch) {
+hj_status run(hj_device* dev, size_t n, const void* src, void* dst, const PeerView* peers, uint32_t mode) {
     using S = typename Scalar<T>::type;
     constexpr int VEC = 16 / sizeof(T);
     size_t mis = (size_t)((uintptr_t)src & 15u);
@@ -308,7 +312,7 @@ hj_status run(hj_device* dev, size_t n, const void* src, void* dst, const PeerVi
     S* partials = reinterpret_cast<S*>(reinterpret_cast<char*>(dev->reduce_scratch) + 64);
     HJ_CUDA(launch_pdl(reduce_kernel<T, OP, RED_THREADS, RED_UNROLL>, dim3(grid), dim3(RED_THREADS), 0, dev->stream,
                        reinterpret_cast<const T*>(src), n, head, partials, ticket, reinterpret_cast<T*>(dst),
-                       peers ? *peers : PeerView(), peers ? epoch : 0u));
+                       peers ? *peers : PeerView(), peers ? mode : 0u));
     return check_launch(dev, "reduce_kernel");
 }
 
@@ -340,20 +344,20 @@ hj_status run_uint(hj_device* dev, hj_reduce_op op, size_t n, const void* src, v
 }  // namespace
 
 hj_status launch_reduce(hj_device* dev, hj_reduce_op op, hj_type_kind ty, size_t n, const void* src,
-                        void* dst, const PeerView* peers, uint32_t epoch) {
+                        void* dst, const PeerView* peers, uint32_t mode) {
     hj_status s = HJ_ERR_UNSUPPORTED;
     switch (ty) {
-    case HJ_BOOL: s = run_bitwise<uint8_t>(dev, op, n, src, dst, peers, epoch); break;  // reduce.rs:141,150,159
-    case HJ_I8: s = run_arith<int8_t>(dev, op, n, src, dst, peers, epoch); break;
-    case HJ_U8: s = run_uint<uint8_t>(dev, op, n, src, dst, peers, epoch); break;
-    case HJ_I16: s = run_arith<int16_t>(dev, op, n, src, dst, peers, epoch); break;
-    case HJ_U16: s = run_uint<uint16_t>(dev, op, n, src, dst, peers, epoch); break;
-    case HJ_I32: s = run_arith<int32_t>(dev, op, n, src, dst, peers, epoch); break;
-    case HJ_U32: s = run_uint<uint32_t>(dev, op, n, src, dst, peers, epoch); break;
-    case HJ_I64: s = run_arith<int64_t>(dev, op, n, src, dst, peers, epoch); break;
-    case HJ_U64: s = run_uint<uint64_t>(dev, op, n, src, dst, peers, epoch); break;
-    case HJ_F32: s = run_arith<float>(dev, op, n, src, dst, peers, epoch); break;
-    case HJ_F64: s = run_arith<double>(dev, op, n, src, dst, peers, epoch); break;
+    case HJ_BOOL: s = run_bitwise<uint8_t>(dev, op, n, src, dst, peers, mode); break;  // reduce.rs:141,150,159
+    case HJ_I8: s = run_arith<int8_t>(dev, op, n, src, dst, peers, mode); break;
+    case HJ_U8: s = run_uint<uint8_t>(dev, op, n, src, dst, peers, mode); break;
+    case HJ_I16: s = run_arith<int16_t>(dev, op, n, src, dst, peers, mode); break;
+    case HJ_U16: s = run_uint<uint16_t>(dev, op, n, src, dst, peers, mode); break;
+    case HJ_I32: s = run_arith<int32_t>(dev, op, n, src, dst, peers, mode); break;
+    case HJ_U32: s = run_uint<uint32_t>(dev, op, n, src, dst, peers, mode); break;
+    case HJ_I64: s = run_arith<int64_t>(dev, op, n, src, dst, peers, mode); break;
+    case HJ_U64: s = run_uint<uint64_t>(dev, op, n, src, dst, peers, mode); break;
+    case HJ_F32: s = run_arith<float>(dev, op, n, src, dst, peers, mode); break;
+    case HJ_F64: s = run_arith<double>(dev, op, n, src, dst, peers, mode); break;
     default: break;  // F16: todo!() in the reference
     }
     if (s == HJ_ERR_UNSUPPORTED)

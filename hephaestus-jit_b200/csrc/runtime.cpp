@@ -112,6 +112,18 @@ hj_status count_epoch(hj_device* dev, uint32_t n) {
     return HJ_OK;
 }
 
+hj_status ensure_dynamic_smem(hj_device* dev, const void* kernel, size_t smem) {
+    static std::mutex mu;
+    static std::map<std::pair<int, const void*>, size_t> done;
+    std::lock_guard<std::mutex> g(mu);
+    auto key = std::make_pair(dev->ordinal, kernel);
+    auto it = done.find(key);
+    if (it != done.end() && it->second >= smem) return HJ_OK;
+    HJ_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    done[key] = smem;
+    return HJ_OK;
+}
+
 static std::mutex g_devices_mu;
 static std::map<int, hj_device*> g_devices;
 

@@ -219,11 +219,11 @@ struct ScanOp {
     static constexpr int ROWS = SLICE / 512;
     struct Args {
         T* dst;
-        // sharded scan with a DEFERRED seed (comm.cu): xepoch != 0 makes the CTA that owns the last
+        // sharded scan with a DEFERRED seed (comm.cu): `exchange` makes the CTA that owns the last
         // tile publish the shard total to every peer and write this rank's exclusive offset
         T* seed_out;
         PeerView pv;
-        uint32_t xepoch;
+        uint32_t exchange;
     };
     // phase 1: total of this warp's slice (the stage tail of a ragged tile is zero-filled)
     static __device__ __forceinline__ P total(const char* slice, char*, int, int, int lane) {
@@ -275,10 +275,10 @@ struct ScanOp {
     // peer's mailbox over NVLink, the totals of the ranks before this one are summed in rank order
     // and left in seed_out[0] — the offset every consumer of `dst` adds.
     static __device__ __forceinline__ void finish(P total, const Args& a, int lane) {
-        if (a.xepoch == 0) return;
+        if (a.exchange == 0) return;
         unsigned long long bits = 0;
         memcpy(&bits, &total, sizeof(P));
-        const unsigned long long got = peer_allgather_warp(a.pv, a.xepoch, bits, lane);
+        const unsigned long long got = peer_allgather_warp(a.pv, bits, lane);
         P mine;
         memcpy(&mine, &got, sizeof(P));
         P before = (P)0;
@@ -290,10 +290,10 @@ struct ScanOp {
 template <typename T, typename P, bool INCLUSIVE, int TILE, int STAGES, int CWARPS, int AHEAD>
 __global__ void __launch_bounds__((CWARPS + 3) * 32, 1)
 scan_ring_kernel(const T* __restrict__ src, T* __restrict__ dst, size_t n, const T* __restrict__ seed,
-                 LookbackView lb, uint32_t n_tiles, uint32_t G, T* __restrict__ seed_out, PeerView pv, uint32_t xepoch) {
+                 LookbackView lb, uint32_t n_tiles, uint32_t G, T* __restrict__ seed_out, PeerView pv, uint32_t exchange) {
     extern __shared__ __align__(128) char smem[];
     using Op = ScanOp<T, P, INCLUSIVE, TILE / CWARPS>;
-    typename Op::Args args{dst, seed_out, pv, xepoch};
+    typename Op::Args args{dst, seed_out, pv, exchange};
     P seed_v = (P)0;
     if (seed) {
         pdl_wait();  // the seed is the output of the kernel in front (sharded scan: the totals pass)
@@ -305,7 +305,7 @@ scan_ring_kernel(const T* __restrict__ src, T* __restrict__ dst, size_t n, const
 
 template <typename T, typename P, int TILE, int STAGES, int CWARPS, int AHEAD>
 hj_status run_ring(hj_device* dev, size_t n, bool inclusive, const void* src, void* dst, const void* seed,
-                   void* seed_out, const PeerView* peers, uint32_t xepoch) {
+                   void* seed_out, const PeerView* peers) {
     const size_t n_tiles = (n * sizeof(T) + TILE - 1) / TILE;
     HJ_REQUIRE(n_tiles < (1ull << 31), "prefix_sum: too many tiles");
     HJ_TRY(ensure_lookback_scratch(dev, n_tiles));
@@ -315,10 +315,10 @@ hj_status run_ring(hj_device* dev, size_t n, bool inclusive, const void* src, vo
     const unsigned grid = (unsigned)std::min<size_t>(n_tiles, (size_t)dev->sm_count);
     const uint32_t G = (grid + 31u) & ~31u;  // tiles per round: about one per CTA
     auto launch = [&](auto kernel) -> hj_status {
-        HJ_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        HJ_TRY(ensure_dynamic_smem(dev, (const void*)kernel, smem));
         HJ_CUDA(launch_pdl(kernel, dim3(grid), dim3((CWARPS + 3) * 32), smem, dev->stream, (const T*)src, (T*)dst, n,
                            (const T*)seed, lb, (uint32_t)n_tiles, G, (T*)seed_out, peers ? *peers : PeerView(),
-                           peers ? xepoch : 0u));
+                           peers ? 1u : 0u));
         return check_launch(dev, "scan_ring_kernel");
     };
     return inclusive ? launch(scan_ring_kernel<T, P, true, TILE, STAGES, CWARPS, AHEAD>)
@@ -327,7 +327,7 @@ hj_status run_ring(hj_device* dev, size_t n, bool inclusive, const void* src, vo
 
 template <typename T, typename P>
 hj_status run(hj_device* dev, size_t n, bool inclusive, const void* src, void* dst, const void* seed,
-              void* seed_out = nullptr, const PeerView* peers = nullptr, uint32_t xepoch = 0) {
+              void* seed_out = nullptr, const PeerView* peers = nullptr) {
     // 16-byte aligned buffers (every buffer this library allocates) take the ring pipeline;
     // anything else, and tiny inputs, the look-back kernel below.
     const bool aligned = (((uintptr_t)src | (uintptr_t)dst) & 15u) == 0;
@@ -336,8 +336,8 @@ hj_status run(hj_device* dev, size_t n, bool inclusive, const void* src, void* d
         // measured on B200 (profiles/r01_scan_ring_sweep.txt): 32 KiB x 6 stages, phase 1 three
         // tiles ahead for <= 4-byte prefixes; 8-byte prefixes (twice the shuffle work per byte,
         // two status words per tile) do better with fewer, larger tiles
-        if (sizeof(P) == 8) return run_ring<T, P, 49152, 4, 16, 2>(dev, n, inclusive, src, dst, seed, seed_out, peers, xepoch);
-        return run_ring<T, P, 32768, 6, 16, 3>(dev, n, inclusive, src, dst, seed, seed_out, peers, xepoch);
+        if (sizeof(P) == 8) return run_ring<T, P, 49152, 4, 16, 2>(dev, n, inclusive, src, dst, seed, seed_out, peers);
+        return run_ring<T, P, 32768, 6, 16, 3>(dev, n, inclusive, src, dst, seed, seed_out, peers);
     }
     if (peers) return fail(HJ_ERR_UNSUPPORTED, "prefix_sum: the fused exchange needs the ring kernel");
     constexpr int VEC = 16 / sizeof(T);
@@ -366,15 +366,15 @@ bool prefix_sum_can_fuse_exchange(hj_type_kind ty, size_t n, const void* src, co
 }
 
 hj_status launch_prefix_sum(hj_device* dev, hj_type_kind ty, size_t n, bool inclusive, const void* src,
-                            void* dst, const void* seed, void* seed_out, const PeerView* peers, uint32_t xepoch) {
+                            void* dst, const void* seed, void* seed_out, const PeerView* peers) {
     // Integer sums wrap, so signed types run on the unsigned kernel of the same width.
     switch (ty) {
-    case HJ_I8: case HJ_U8: return run<uint8_t, uint32_t>(dev, n, inclusive, src, dst, seed, seed_out, peers, xepoch);
-    case HJ_I16: case HJ_U16: return run<uint16_t, uint32_t>(dev, n, inclusive, src, dst, seed, seed_out, peers, xepoch);
-    case HJ_I32: case HJ_U32: return run<uint32_t, uint32_t>(dev, n, inclusive, src, dst, seed, seed_out, peers, xepoch);
-    case HJ_I64: case HJ_U64: return run<uint64_t, uint64_t>(dev, n, inclusive, src, dst, seed, seed_out, peers, xepoch);
-    case HJ_F32: return run<float, float>(dev, n, inclusive, src, dst, seed, seed_out, peers, xepoch);
-    case HJ_F64: return run<double, double>(dev, n, inclusive, src, dst, seed, seed_out, peers, xepoch);
+    case HJ_I8: case HJ_U8: return run<uint8_t, uint32_t>(dev, n, inclusive, src, dst, seed, seed_out, peers);
+    case HJ_I16: case HJ_U16: return run<uint16_t, uint32_t>(dev, n, inclusive, src, dst, seed, seed_out, peers);
+    case HJ_I32: case HJ_U32: return run<uint32_t, uint32_t>(dev, n, inclusive, src, dst, seed, seed_out, peers);
+    case HJ_I64: case HJ_U64: return run<uint64_t, uint64_t>(dev, n, inclusive, src, dst, seed, seed_out, peers);
+    case HJ_F32: return run<float, float>(dev, n, inclusive, src, dst, seed, seed_out, peers);
+    case HJ_F64: return run<double, double>(dev, n, inclusive, src, dst, seed, seed_out, peers);
     default:
         return fail(HJ_ERR_UNSUPPORTED, "prefix_sum: unsupported element type %s", type_name(ty));
     }

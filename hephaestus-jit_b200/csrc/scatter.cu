@@ -340,6 +340,7 @@ __global__ void __launch_bounds__(HFX_WORDS * HFX_SLICES)
 hist_fold_exchange_kernel(const uint32_t* __restrict__ scratch, uint32_t n_groups, uint32_t* __restrict__ dst, uint32_t n_dst,
                           ArrayPeerView ax) {
     __shared__ uint32_t s_even[HFX_SLICES][HFX_WORDS], s_odd[HFX_SLICES][HFX_WORDS];
+    __shared__ uint32_t s_epoch;
     const uint32_t wl = threadIdx.x % HFX_WORDS, slice = threadIdx.x / HFX_WORDS;
     const uint32_t w = blockIdx.x * HFX_WORDS + wl;
     const uint32_t n_words = (n_dst + 1) / 2;
@@ -358,18 +359,23 @@ hist_fold_exchange_kernel(const uint32_t* __restrict__ scratch, uint32_t n_group
     }
     s_even[slice][wl] = even;
     s_odd[slice][wl] = odd;
+    if (threadIdx.x == 0 && ax.world > 1) s_epoch = xepoch_begin(ax.xepoch);
     __syncthreads();
-    if (slice != 0 || w >= n_words) return;
+    const uint32_t epoch = s_epoch;
+    if (slice == 0 && w < n_words) {
 #pragma unroll
-    for (int k = 1; k < HFX_SLICES; k++) {
-        even += s_even[k][wl];
-        odd += s_odd[k][wl];
+        for (int k = 1; k < HFX_SLICES; k++) {
+            even += s_even[k][wl];
+            odd += s_odd[k][wl];
+        }
+        const bool has_odd = 2 * w + 1 < n_dst;
+        uint32_t a = dst[2 * w] + even, b = has_odd ? dst[2 * w + 1] + odd : 0u;
+        if (ax.world > 1) array_pair_allreduce_add(ax, epoch, w, a, b, &a, &b);
+        dst[2 * w] = a;
+        if (has_odd) dst[2 * w + 1] = b;
     }
-    const bool has_odd = 2 * w + 1 < n_dst;
-    uint32_t a = dst[2 * w] + even, b = has_odd ? dst[2 * w + 1] + odd : 0u;
-    if (ax.world > 1) array_pair_allreduce_add(ax, w, a, b, &a, &b);
-    dst[2 * w] = a;
-    if (has_odd) dst[2 * w + 1] = b;
+    // the CTA that finishes last commits the exchange epoch (every CTA has read it by then)
+    if (ax.world > 1) array_exchange_commit(ax, epoch);
 }
 
 template <typename T>
@@ -481,7 +487,7 @@ hj_status launch_scatter_reduce(hj_device* dev, hj_reduce_op op, hj_type_kind ty
                 HJ_TRY(ensure_hist_scratch(dev, (size_t)n_groups * n_words * 4));
                 const size_t smem = ring + ((((size_t)n_words + 3) & ~(size_t)3) + 32) * 4;  // + 32 dummy words
                 auto kern = hist_ring_kernel<true>;
-                HJ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                HJ_TRY(ensure_dynamic_smem(dev, (const void*)kern, smem));
                 HJ_CUDA(launch_pdl(kern, dim3(n_groups), dim3((HR_WARPS + 1) * 32), smem, dev->stream, idx, n, 1u, dev->hist_scratch,
                                    (uint32_t*)dst, (uint32_t)n_dst, (uint32_t)n_dst, 1u, 0u));
                 HJ_TRY(check_launch(dev, "hist_ring_kernel"));
@@ -513,7 +519,7 @@ hj_status launch_scatter_reduce(hj_device* dev, hj_reduce_op op, hj_type_kind ty
                 while (rs < 5 && ((size_t)(bins_per_part + 1) << (rs + 1)) <= HR_MAX_BINS + 1024) rs++;  // 1024 bins x 32 copies + the dummy row
             const size_t smem = ring + (rs ? ((size_t)(bins_per_part + 1) << rs) + 32 : (size_t)bins_per_part + 32) * 4;  // + dummy words
             auto kern = hist_ring_kernel<false>;
-            HJ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            HJ_TRY(ensure_dynamic_smem(dev, (const void*)kern, smem));
             HJ_CUDA(launch_pdl(kern, dim3(n_groups * parts), dim3((HR_WARPS + 1) * 32), smem, dev->stream, idx, n, (uint32_t)literal,
                                dev->hist_scratch, (uint32_t*)dst, (uint32_t)n_dst, bins_per_part, parts, rs));
             HJ_TRY(check_launch(dev, "hist_ring_kernel"));

@@ -581,13 +581,17 @@ void launch_graph(const Graph& g, hj_device* dev, const std::vector<VarId>& inpu
         // ---- the backend boundary: BackendDevice::execute_graph (graph.rs:315-323)
         if (!g.passes.empty()) {
             // Relaunches of a recorded graph with the same buffers replay ONE captured CUDA graph
-            // instead of enqueueing pass by pass; a launch that wants per-pass timings cannot, nor
-            // can a sharded one (its exchange epochs are launch parameters).
+            // instead of enqueueing pass by pass (sharded launches too: their exchange epochs live in
+            // device memory); a launch that wants per-pass timings cannot.
             hj_status s;
             auto b0 = std::chrono::steady_clock::now();
-            if (comm) {
+            if (comm && backend_report) {
                 s = hj_execute_graph_sharded(comm, passes.data(), (uint32_t)passes.size(), res.data(), descs.data(),
                                              (uint32_t)nres, shards.data(), backend_report);
+            } else if (comm) {
+                g.launched_on = dev;
+                s = hj_execute_graph_sharded_cached(comm, g.uid, passes.data(), (uint32_t)passes.size(), res.data(),
+                                                    descs.data(), (uint32_t)nres, shards.data(), nullptr);
             } else if (backend_report) {
                 s = hj_execute_graph(dev, passes.data(), (uint32_t)passes.size(), res.data(), descs.data(),
                                      (uint32_t)nres, backend_report);

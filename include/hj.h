@@ -422,6 +422,15 @@ hj_status hj_execute_graph_sharded(hj_comm* comm, const hj_pass* passes, uint32_
                                    uint32_t n_resources, hj_shard_desc* shards,
                                    hj_report* report /* may be NULL */);
 
+/* hj_execute_graph_cached for sharded pass lists: the first launch of a (key, buffers, placement,
+ * seeds, incoming `deferred` state) combination executes pass by pass, the second is captured into
+ * ONE CUDA graph, later ones replay it (the exchange epochs of the sharded kernels live in device
+ * memory, so nothing changes between launches).  Every rank must make the same sequence of calls. */
+hj_status hj_execute_graph_sharded_cached(hj_comm* comm, uint64_t graph_key, const hj_pass* passes,
+                                          uint32_t n_passes, hj_buffer* const* env,
+                                          const hj_buffer_desc* descs, uint32_t n_resources,
+                                          hj_shard_desc* shards, uint32_t* how /* may be NULL */);
+
 /* ---- trace / schedule / graph (host side) ------------------------------------------------
  * C++ restatement of the layers ABOVE the backend traits, so that programs written against
  * the reference's op vocabulary produce the same Graph / IR and drive this backend end to end:

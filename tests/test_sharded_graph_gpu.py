@@ -243,6 +243,60 @@ def _unsupported_shapes(rank, world, dev, comm, n):
         tr.compile().launch(dev)
 
 
+def _cached_sharded_graph(rank, world, dev, comm, n):
+    """The relaunch path: the same sharded pass list launched again and again is captured into ONE CUDA
+    graph and replayed (hj_execute_graph_sharded_cached) — possible because the exchange epochs of the
+    sharded kernels live in device memory.  Inputs change between launches; every result is checked."""
+    import oracle
+    irm = importlib.import_module("hephaestus-jit_b200.ir")
+    L = importlib.import_module("hephaestus-jit_b200._lib")
+    sh = importlib.import_module("hephaestus-jit_b200.sharded")
+    s, e = sh.shard_bounds(n, world, rank)
+    nl = e - s
+    bx, by = dev.create_buffer(4 * nl), dev.create_buffer(4 * nl)
+    bf, bs = dev.create_buffer(4 * nl), dev.create_buffer(4)
+    bu, bscan, bseed = dev.create_buffer(4 * nl), dev.create_buffer(4 * nl), dev.create_buffer(16)
+    bm, bidx, bcnt = dev.create_buffer(nl), dev.create_buffer(4 * nl), dev.create_buffer(4)
+    passes = [{"kind": hj.PASS_KERNEL, "resources": [0, 1], "ir": irm.c2_chain_ir(), "size": n},
+              {"kind": hj.PASS_REDUCE, "arg": hj.MAX, "resources": [3, 2]},
+              {"kind": hj.PASS_PREFIX_SUM, "arg": 1, "resources": [5, 4]},
+              {"kind": hj.PASS_COMPRESS, "resources": [7, 8, 6]}]
+    descs = [(n, hj.F32, 4), (n, hj.F32, 4), (n, hj.U32, 4), (1, hj.U32, 4), (n, hj.U32, 4), (n, hj.U32, 4), (n, hj.BOOL, 1),
+             (n, hj.U32, 4), (1, hj.U32, 4)]
+    S, R = L.RES_SHARDED, L.RES_REPLICATED
+    g = hj.PreparedGraph(dev, passes, [bx, by, bf, bs, bu, bscan, bm, bidx, bcnt], descs, comm, [S, S, S, R, S, S, S, S, R],
+                         [None] * 5 + [bseed] + [None] * 3, graph_key=0xC0FFEE + n)
+    hows = []
+    for it in range(5):
+        rng = np.random.Generator(np.random.PCG64(100 + it))       # every rank generates the whole arrays
+        x = (rng.random(n, dtype=np.float32) * 8 - 4).astype(np.float32)
+        f = rng.integers(0, 2**32, size=n, dtype=np.uint64).astype(np.uint32)
+        u = rng.integers(0, 1 << 12, size=n).astype(np.uint32)
+        m = (rng.random(n) < 0.3 + 0.1 * it).astype(np.uint8)
+        for b, a in ((bx, x), (bf, f), (bu, u), (bm, m)):
+            b.upload(a[s:e])
+        bidx.fill_zero()
+        g.run()
+        hows.append(g.how.value)
+        assert np.allclose(by.to_host(np.float32), oracle.c2_chain(x)[s:e], rtol=4e-7, atol=1e-7), it
+        assert bs.to_host(np.uint32)[0] == f.max(), it
+        deferred = g.deferred()[5]
+        assert deferred == (world > 1)
+        off = bseed.to_host(np.uint32, 0, 1)[0] if deferred else np.uint32(0)
+        with np.errstate(over="ignore"):
+            assert np.array_equal(bscan.to_host(np.uint32) + off, np.cumsum(u, dtype=np.uint32)[s:e]), it
+        gcnt, gidx = oracle.compress(m)
+        lc, before = int(m[s:e].sum()), int(m[:s].sum())
+        assert int(bcnt.to_host(np.uint32)[0]) == gcnt, it
+        assert np.array_equal(bidx.to_host(np.uint32)[:lc], gidx[before: before + lc]), it
+    assert hows == [0, 1, 2, 2, 2], hows       # executed, captured, replayed ...
+
+
+@pytest.mark.parametrize("world", [1, 2])
+def test_sharded_pass_list_replays_as_one_cuda_graph(world):
+    _run(world, "_cached_sharded_graph", (1 << 20) + 4099)
+
+
 @pytest.mark.parametrize("world", [1, 2, 3])
 def test_sharded_device_ops_fused_exchange(world):
     _run(world, "_device_ops", (1 << 21) + 77)
