@@ -520,14 +520,17 @@ def run_own(args):
 
     for _ in range(max(args.warmup, 3)):
         step()
+    # everything slow and rank-dependent (NVML init of the clock sampler) happens BEFORE the barrier: the
+    # ranks must enter the timed region together, or the first exchange of the fast ranks waits for the
+    # slow ones inside their timed region
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    launches0 = dev.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
-    launches0 = dev.launch_count()
-    sampler = ClockSampler(local_rank)
-    sampler.start()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t_host0 = time.perf_counter()
     e0.record()
     for _ in range(args.steps):

@@ -14,7 +14,8 @@ torch.cuda.set_device(lr); dev = hj.Device.cuda(lr)
 n = 1 << 30
 d_in = torch.empty(n, dtype=torch.uint8, device="cuda"); d_out = torch.empty(n, dtype=torch.uint8, device="cuda")
 s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
-cudart = torch.cuda.cudart()
+cudart = ctypes.CDLL("libcudart.so.12")
+cudart.cudaMemcpyAsync.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int, ctypes.c_void_p]
 def numa_of(ptr):
     try:
         import ctypes.util
