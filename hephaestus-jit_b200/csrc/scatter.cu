@@ -391,18 +391,28 @@ gather_kernel(const T* __restrict__ src, const uint32_t* __restrict__ idx, T* __
 // (L2-resident table) or the DRAM random-access rate (one 32-byte sector — 64 bytes with the default
 // L2 fetch granularity — fetched per 4 bytes used).  NOALLOC: bypass L1 for the table (a table far
 // larger than L1 + L2 never hits there; the lines only evict the index stream's).
-__device__ __forceinline__ uint32_t ld_table(const uint32_t* p, bool noalloc) {
+// How the table is read (LOADK): 0 ld.global.nc (__ldg), 1 ld.global.nc.L1::no_allocate, 2 plain ld.global,
+// 3 ld.global.cg (L2 only), 4 ld.global.cv, 5 ld.relaxed.gpu, 6 ld.global.nc.L2::cache_hint evict_first
+template <int LOADK>
+__device__ __forceinline__ uint32_t ld_table(const uint32_t* p, uint64_t pol) {
     uint32_t v;
-    if (noalloc) asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(v) : "l"(p));
+    if constexpr (LOADK == 1) asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(v) : "l"(p));
+    else if constexpr (LOADK == 2) asm volatile("ld.global.u32 %0, [%1];" : "=r"(v) : "l"(p));
+    else if constexpr (LOADK == 3) asm volatile("ld.global.cg.u32 %0, [%1];" : "=r"(v) : "l"(p));
+    else if constexpr (LOADK == 4) asm volatile("ld.global.cv.u32 %0, [%1];" : "=r"(v) : "l"(p));
+    else if constexpr (LOADK == 5) asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p));
+    else if constexpr (LOADK == 6) asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(pol));
     else v = __ldg(p);
     return v;
 }
-template <int NV, bool NOALLOC>
+template <int NV, int LOADK>
 __global__ void __launch_bounds__(256)
 gather4_vec_kernel(const uint32_t* __restrict__ src, const uint32_t* __restrict__ idx, uint32_t* __restrict__ dst,
                    size_t n) {
     pdl_launch_dependents();
     pdl_wait();
+    uint64_t pol = 0;
+    if constexpr (LOADK == 6) asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
     const size_t nvec = n / 4;
     const uint4* vidx = reinterpret_cast<const uint4*>(idx);
     uint4* vdst = reinterpret_cast<uint4*>(dst);
@@ -414,8 +424,8 @@ gather4_vec_kernel(const uint32_t* __restrict__ src, const uint32_t* __restrict_
         for (int k = 0; k < NV; k++) a[k] = ld_stream_v4(vidx + v + k * stride);
 #pragma unroll
         for (int k = 0; k < NV; k++) {
-            x[k].x = ld_table(src + a[k].x, NOALLOC); x[k].y = ld_table(src + a[k].y, NOALLOC);
-            x[k].z = ld_table(src + a[k].z, NOALLOC); x[k].w = ld_table(src + a[k].w, NOALLOC);
+            x[k].x = ld_table<LOADK>(src + a[k].x, pol); x[k].y = ld_table<LOADK>(src + a[k].y, pol);
+            x[k].z = ld_table<LOADK>(src + a[k].z, pol); x[k].w = ld_table<LOADK>(src + a[k].w, pol);
         }
 #pragma unroll
         for (int k = 0; k < NV; k++) st_stream_v4(vdst + v + k * stride, x[k]);
@@ -566,7 +576,7 @@ hj_status launch_gather(hj_device* dev, size_t elem_bytes, size_t n, const void*
     case 2: gather_kernel<uint16_t><<<grid, 256, 0, dev->stream>>>((const uint16_t*)src, idx, (uint16_t*)dst, n); break;
     case 4:
         if ((((uintptr_t)idx | (uintptr_t)dst) & 15u) == 0 && n >= 4096) {
-            // HJ_GATHER_CFG = 10 * (vectors per thread) + (1: table loads bypass L1); default 2 vectors, L1 allocate
+            // HJ_GATHER_CFG = 10 * (vectors per thread) + LOADK (see ld_table); default 2 vectors, ld.global.nc
             static const int cfg = getenv("HJ_GATHER_CFG") ? atoi(getenv("HJ_GATHER_CFG")) : 20;
             static const int ctas = getenv("HJ_GATHER_CTAS") ? atoi(getenv("HJ_GATHER_CTAS")) : 16;
             const int nv = cfg / 10;
@@ -574,15 +584,21 @@ hj_status launch_gather(hj_device* dev, size_t elem_bytes, size_t n, const void*
             const uint32_t *s32 = (const uint32_t*)src;
             uint32_t* d32 = (uint32_t*)dst;
             cudaError_t e;
+#define HJ_G(NV, LK) e = launch_pdl(gather4_vec_kernel<NV, LK>, dim3((unsigned)g4), dim3(256), 0, dev->stream, s32, idx, d32, n)
             switch (cfg) {
-            case 11: e = launch_pdl(gather4_vec_kernel<1, true>, dim3((unsigned)g4), dim3(256), 0, dev->stream, s32, idx, d32, n); break;
-            case 21: e = launch_pdl(gather4_vec_kernel<2, true>, dim3((unsigned)g4), dim3(256), 0, dev->stream, s32, idx, d32, n); break;
-            case 40: e = launch_pdl(gather4_vec_kernel<4, false>, dim3((unsigned)g4), dim3(256), 0, dev->stream, s32, idx, d32, n); break;
-            case 41: e = launch_pdl(gather4_vec_kernel<4, true>, dim3((unsigned)g4), dim3(256), 0, dev->stream, s32, idx, d32, n); break;
-            case 80: e = launch_pdl(gather4_vec_kernel<8, false>, dim3((unsigned)g4), dim3(256), 0, dev->stream, s32, idx, d32, n); break;
-            case 81: e = launch_pdl(gather4_vec_kernel<8, true>, dim3((unsigned)g4), dim3(256), 0, dev->stream, s32, idx, d32, n); break;
-            default: e = launch_pdl(gather4_vec_kernel<2, false>, dim3((unsigned)g4), dim3(256), 0, dev->stream, s32, idx, d32, n); break;
+            case 21: HJ_G(2, 1); break;
+            case 22: HJ_G(2, 2); break;
+            case 23: HJ_G(2, 3); break;
+            case 24: HJ_G(2, 4); break;
+            case 25: HJ_G(2, 5); break;
+            case 26: HJ_G(2, 6); break;
+            case 40: HJ_G(4, 0); break;
+            case 42: HJ_G(4, 2); break;
+            case 43: HJ_G(4, 3); break;
+            case 82: HJ_G(8, 2); break;
+            default: HJ_G(2, 0); break;
             }
+#undef HJ_G
             HJ_CUDA(e);
         } else
             gather_kernel<uint32_t><<<grid, 256, 0, dev->stream>>>((const uint32_t*)src, idx, (uint32_t*)dst, n);

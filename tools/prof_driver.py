@@ -42,6 +42,18 @@ def main():
         k = torch.randint(0, nb, (n,), device="cuda", generator=g, dtype=torch.int32)
         h = torch.zeros(nb, device="cuda", dtype=torch.int32)
         fn = lambda: dev.scatter_reduce(hj.SUM, hj.U32, n, wrap(k), None, 1, wrap(h), nb)
+    elif which.startswith("gather"):
+        log_t = int(which.split(":")[1]) if ":" in which else 28
+        table = torch.rand(1 << log_t, device="cuda", generator=g)
+        idx = torch.randint(0, 1 << log_t, (n,), device="cuda", generator=g, dtype=torch.int32)
+        out = torch.empty(n, device="cuda")
+        fn = lambda: dev.gather(4, n, wrap(table), wrap(idx), wrap(out))
+    elif which == "map":
+        irm = importlib.import_module("hephaestus-jit_b200.ir")
+        x = torch.rand(n, device="cuda", generator=g) * 8 - 4
+        y = torch.empty_like(x)
+        k = dev.kernel(irm.c2_chain_ir())
+        fn = lambda: dev.launch(k, n, [wrap(x), wrap(y)])
     else:
         raise SystemExit(f"unknown kernel {which}")
     for _ in range(iters):
