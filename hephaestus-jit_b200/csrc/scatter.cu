@@ -166,8 +166,14 @@ hist_ring_kernel(const uint32_t* __restrict__ keys, size_t n, uint32_t literal, 
     const size_t n_bytes = n * 4;
     const uint32_t n_tiles = (uint32_t)((n_bytes + HR_TILE - 1) / HR_TILE);
 
-    // PACKED16: also the padding the 128-bit sweep reads and the 32 dummy words
-    for (uint32_t b = threadIdx.x; b < (PACKED16 ? ((n_words + 3u) & ~3u) : n_words) + 32u; b += blockDim.x) bins[b] = 0;
+    // PACKED16: also the padding the 128-bit sweep reads and the 32 dummy words; 128-bit stores (the bins
+    // start 16-byte aligned behind the ring and its control block)
+    {
+        const uint32_t n_zero = (PACKED16 ? ((n_words + 3u) & ~3u) : n_words) + 32u;
+        uint4* z = reinterpret_cast<uint4*>(bins);
+        for (uint32_t b = threadIdx.x; b < n_zero / 4; b += blockDim.x) z[b] = make_uint4(0, 0, 0, 0);
+        for (uint32_t b = (n_zero & ~3u) + threadIdx.x; b < n_zero; b += blockDim.x) bins[b] = 0;
+    }
     if (threadIdx.x == 0) {
         for (int s = 0; s < HR_STAGES; s++) {
             mbar_init(&ctl->full[s], 1);
@@ -280,8 +286,16 @@ hist_ring_kernel(const uint32_t* __restrict__ keys, size_t n, uint32_t literal, 
     __syncthreads();
     // private histogram of this group: coalesced plain stores, folded by hist_fold_kernel
     if (PACKED16) {
-        uint32_t* mine = reinterpret_cast<uint32_t*>(out) + (size_t)group * ((n_dst + 1) / 2);
-        for (uint32_t b = threadIdx.x; b < (nb + 1) / 2; b += blockDim.x) mine[b] = bins[b];
+        const uint32_t n_w = (n_dst + 1) / 2;
+        uint32_t* mine = reinterpret_cast<uint32_t*>(out) + (size_t)group * n_w;
+        if ((((size_t)group * n_w) & 3u) == 0) {  // 128-bit stores when this group's slice of the scratch is 16-byte aligned
+            uint4* m4 = reinterpret_cast<uint4*>(mine);
+            const uint4* b4 = reinterpret_cast<const uint4*>(bins);
+            for (uint32_t b = threadIdx.x; b < n_w / 4; b += blockDim.x) m4[b] = b4[b];
+            for (uint32_t b = (n_w & ~3u) + threadIdx.x; b < n_w; b += blockDim.x) mine[b] = bins[b];
+        } else {
+            for (uint32_t b = threadIdx.x; b < n_w; b += blockDim.x) mine[b] = bins[b];
+        }
     } else {
         uint32_t* mine = reinterpret_cast<uint32_t*>(out) + (size_t)group * n_dst + lo;
         if (rs) {  // sum the copies; thread b starts at copy b so that a warp's reads spread over the banks
@@ -331,11 +345,13 @@ hist_fold_kernel(const uint32_t* __restrict__ scratch, uint32_t n_groups, uint32
 // PACKED16 fold AND, on a sharded launch, the cross-GPU all-reduce of the bins in ONE kernel
 // (launched with programmatic stream serialization behind hist_ring_kernel).  A CTA owns 64 packed
 // words (128 bins) and splits the group list over 4 slices of 64 threads; slice 0 then holds the
-// rank's final counts, adds what dst held, pushes each pair of bins as one self-validating uint4
+// rank's final counts (round 2: 16 slices of 32 words instead of 4 of 64 — the first version was
+// latency-bound at 12.7 us for 19 MB, ncu profiles/r02_ncu_summary.txt), adds what dst held, pushes
+// each pair of bins as one self-validating uint4
 // (bin, epoch, bin, epoch) into every peer's inbox over NVLink, polls its own inbox for the peers'
 // pairs and stores the sum over all ranks (peer.cuh: array_pair_allreduce_add) — fold kernel,
 // 8 x 65536 global atomics and the separate exchange kernel of round 1 become one launch.
-constexpr int HFX_WORDS = 64, HFX_SLICES = 4;
+constexpr int HFX_WORDS = 32, HFX_SLICES = 16;  // 512 threads: one 128-byte line per slice warp and group, ~9 loads in flight per thread
 __global__ void __launch_bounds__(HFX_WORDS * HFX_SLICES)
 hist_fold_exchange_kernel(const uint32_t* __restrict__ scratch, uint32_t n_groups, uint32_t* __restrict__ dst, uint32_t n_dst,
                           ArrayPeerView ax) {
@@ -350,11 +366,23 @@ hist_fold_exchange_kernel(const uint32_t* __restrict__ scratch, uint32_t n_group
     if (w < n_words) {
         const uint32_t per = (n_groups + HFX_SLICES - 1) / HFX_SLICES;
         const uint32_t g0 = slice * per, g1 = min(n_groups, g0 + per);
+        constexpr int HFX_MAX = 10;  // groups per slice with <= 160 groups: all loads of a thread in flight at once
+        if (g1 - g0 <= HFX_MAX) {
+            uint32_t word[HFX_MAX];
+#pragma unroll
+            for (int k = 0; k < HFX_MAX; k++) word[k] = g0 + k < g1 ? __ldg(scratch + (size_t)(g0 + k) * n_words + w) : 0u;
+#pragma unroll
+            for (int k = 0; k < HFX_MAX; k++) {
+                even += word[k] & 0xffffu;
+                odd += word[k] >> 16;
+            }
+        } else {
 #pragma unroll 8
-        for (uint32_t g = g0; g < g1; g++) {
-            const uint32_t word = __ldg(scratch + (size_t)g * n_words + w);
-            even += word & 0xffffu;
-            odd += word >> 16;
+            for (uint32_t g = g0; g < g1; g++) {
+                const uint32_t word = __ldg(scratch + (size_t)g * n_words + w);
+                even += word & 0xffffu;
+                odd += word >> 16;
+            }
         }
     }
     s_even[slice][wl] = even;
