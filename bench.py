@@ -731,11 +731,49 @@ def run_e2e(torch, dist, hj, L, dev, comm, kernel, world, rank, x, f, u, mask, c
         seed_b, dummy = dev.create_buffer(16), dev.create_buffer(16)
         scalars = {}
 
+        # how the four host ops of a step are issued: "serial" (one after the other), "pair" (the upload-only
+        # reduce next to the download-heavy compress, the rest serial), "all" (four threads at once)
+        mode = os.environ.get("HJ_BENCH_E2E_MODE", "serial")   # measured: pair / all gain nothing on a link that is already busy both ways
+        serial = mode == "serial"
+
         def step():
-            dev.map_host(kernel, n_map, [host["hx"].value, host["hy"].value], 1 << 23)
-            s = dev.reduce_host(hj.SUM, hj.F32, n_ops, host["hf"].value)
-            dev.prefix_sum_host(hj.U32, n_ops, True, host["hu"].value, host["hscan"].value)
-            c = dev.compress_host(n_ops, host["hmask"].value, host["hidx"].value, (rank * n_ops) & 0xFFFFFFFF)
+            # the four ops of the step stream concurrently from four host threads (the library holds its device
+            # lock only while a chunk is being enqueued): their copies share the two PCIe directions, so the
+            # download-heavy ops (scan, compress) overlap the upload-only reduce
+            res, errs = {}, []
+
+            def guarded(fn):
+                def run():
+                    try:
+                        fn()
+                    except BaseException as exc:  # noqa: BLE001 - re-raised on the calling thread
+                        errs.append(exc)
+                return run
+
+            jobs = [lambda: dev.prefix_sum_host(hj.U32, n_ops, True, host["hu"].value, host["hscan"].value),
+                    lambda: res.__setitem__("c", dev.compress_host(n_ops, host["hmask"].value, host["hidx"].value,
+                                                                   (rank * n_ops) & 0xFFFFFFFF)),
+                    lambda: dev.map_host(kernel, n_map, [host["hx"].value, host["hy"].value], 1 << 23),
+                    lambda: res.__setitem__("s", dev.reduce_host(hj.SUM, hj.F32, n_ops, host["hf"].value))]
+            def together(group):
+                ts = [threading.Thread(target=guarded(j)) for j in group]
+                for t in ts:
+                    t.start()
+                for t in ts:
+                    t.join()
+                if errs:
+                    raise errs[0]
+
+            if serial:
+                for j in jobs:
+                    j()
+            elif mode == "pair":
+                jobs[0]()                       # scan: 4 GiB in, 4 GiB out, overlapped inside the op
+                together([jobs[1], jobs[3]])    # compress (1 GiB in, 2 GiB out) beside reduce (4 GiB in)
+                jobs[2]()                       # map: 1 GiB in, 1 GiB out
+            else:
+                together(jobs)
+            s, c = res["s"], res["c"]
             if comm is not None:   # the three scalars that cross the fabric
                 one.upload(np.array([s], np.float32))
                 comm.reduce(hj.SUM, hj.F32, 1, one, one)
@@ -789,7 +827,8 @@ def run_e2e(torch, dist, hj, L, dev, comm, kernel, world, rank, x, f, u, mask, c
                 "ms_per_step": dt * 1e3, "steps": e2e_steps, "kernel_launches_per_step": int(launches), "check": ok,
                 "pcie_GB/s_each_way": {"h2d": h2d / world / dt / 1e9, "d2h": d2h / world / dt / 1e9},
                 "path": "pinned host arrays -> hj_kernel_map_host + hj_reduce_host + hj_prefix_sum_host + hj_compress_host "
-                        "(chunks of 2^23-2^24 elements: upload | kernel | download streams)" +
+                        "(chunks of 2^23-2^24 elements: upload | kernel | download streams" +
+                        {"serial": "; the four ops one after the other)", "pair": "; reduce_host beside compress_host from two host threads, scan and map alone)"}.get(mode, "; the four ops concurrently from four host threads)") +
                         (" + hj_sharded_reduce / prefix_sum_deferred of the three per-rank scalars" if comm is not None else "")}
     finally:
         for p in host.values():

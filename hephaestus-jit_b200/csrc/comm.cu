@@ -102,6 +102,8 @@ hj_status need_nccl() {
     return HJ_OK;
 }
 
+__global__ void set_u32_kernel(uint32_t* p, uint32_t v) { *p = v; }
+
 // seed[0] = sum of gathered[0 .. rank)  (exclusive scan of the per-rank totals at `rank`);
 // total[0] = sum of gathered[0 .. world)
 template <typename T>
@@ -794,8 +796,8 @@ hj_status hj_sharded_scatter_reduce(hj_comm* c, hj_reduce_op op, hj_type_kind ty
 // multi-GPU wavefront loop).  Rank q holds counts[q] elements; the global sequence is their
 // concatenation in rank order.  Afterwards rank r holds the contiguous block
 // [r*T/W + min(r, T%W), ...) of it (sizes differ by at most one, order preserved) in `dst`.
-// The counts are read back to the host once (W x 4 bytes): the caller sizes its next launches
-// from *new_count_host anyway; the payload moves GPU to GPU over NVLink as grouped ncclSend /
+// The counts are read back to the host once (W x 4 bytes, the one synchronisation of this call: NCCL
+// needs the slice sizes on the host, and the caller sizes its next launches from *new_count_host anyway); the payload moves GPU to GPU over NVLink as grouped ncclSend /
 // ncclRecv of exactly the overlapping slices — every element crosses the fabric at most once
 // and elements that stay on their rank are one device-to-device copy.
 hj_status hj_sharded_rebalance(hj_comm* c, size_t elem_bytes, hj_buffer* src, hj_buffer* counts, hj_buffer* dst,
@@ -843,10 +845,9 @@ hj_status hj_sharded_rebalance(hj_comm* c, size_t elem_bytes, hj_buffer* src, hj
         HJ_NCCL(r);
         HJ_NCCL(e);
     }
-    if (out_count) {
-        const uint32_t m32 = (uint32_t)mine;
-        HJ_CUDA(cudaMemcpyAsync(out_count->ptr, &m32, 4, cudaMemcpyHostToDevice, c->dev->stream));
-        HJ_CUDA(cudaStreamSynchronize(c->dev->stream));  // m32 lives on this stack frame
+    if (out_count) {  // the value travels as a kernel argument: no second synchronisation for a stack variable
+        set_u32_kernel<<<1, 1, 0, c->dev->stream>>>((uint32_t*)out_count->ptr, (uint32_t)mine);
+        HJ_TRY(check_launch(c->dev, "set_u32_kernel"));
     }
     if (new_count_host) *new_count_host = mine;
     return HJ_OK;

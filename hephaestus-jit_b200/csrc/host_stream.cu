@@ -16,7 +16,10 @@
 //   compress    `index_base` = first element of the chunk; the compacted indices of a chunk are
 //               downloaded behind those of the chunks before it (the host reads each chunk's count
 //               while the next chunks are already in flight)
-// Results are complete on return, like BackendBuffer::to_host.
+// Results are complete on return, like BackendBuffer::to_host.  The device lock is only held while a
+// chunk's work is being enqueued, never while waiting: several host threads may stream different
+// arrays at once (bench.py's end-to-end step runs its four ops that way), their copies share the two
+// PCIe directions and their kernels take turns on the device stream.
 #include <algorithm>
 #include <vector>
 
@@ -47,7 +50,10 @@ struct Pipe {
         // (an error path may leave copies in flight on the side streams)
         if (up) cudaStreamSynchronize(up);
         if (down) cudaStreamSynchronize(down);
-        for (void* p : device_allocs) cudaFreeAsync(p, dev->stream);
+        {
+            DeviceGuard g(dev);
+            for (void* p : device_allocs) cudaFreeAsync(p, dev->stream);
+        }
         for (int d = 0; d < DEPTH; d++) {
             if (up_done[d]) cudaEventDestroy(up_done[d]);
             if (comp_done[d]) cudaEventDestroy(comp_done[d]);
@@ -82,12 +88,17 @@ struct Pipe {
         HJ_CUDA(cudaStreamWaitEvent(down, start, 0));
         return HJ_OK;
     }
-    // and the device stream continues after them
-    hj_status join() {
-        HJ_CUDA(cudaEventRecord(start, down));
-        HJ_CUDA(cudaStreamWaitEvent(dev->stream, start, 0));
-        HJ_CUDA(cudaEventRecord(start, up));
-        HJ_CUDA(cudaStreamWaitEvent(dev->stream, start, 0));
+    // Blocks until this op's own work is done: everything enqueued on the device stream so far (its
+    // last kernel; recorded under the lock) and both side streams.  Does not wait for work other
+    // threads enqueue afterwards.
+    hj_status finish() {
+        {
+            DeviceGuard g(dev);
+            HJ_CUDA(cudaEventRecord(start, dev->stream));
+        }
+        HJ_CUDA(cudaEventSynchronize(start));
+        HJ_CUDA(cudaStreamSynchronize(up));
+        HJ_CUDA(cudaStreamSynchronize(down));
         return HJ_OK;
     }
 };
@@ -137,16 +148,19 @@ hj_status hj_reduce_host(hj_device* dev, hj_reduce_op op, hj_type_kind ty, size_
     const auto chunks = make_chunks(n, default_chunk(chunk_elems), 16 / std::min<size_t>(es, 16), false);
     size_t max_chunk = 0;
     for (auto& c : chunks) max_chunk = std::max(max_chunk, c.second);
-    DeviceGuard g(dev);
     Pipe p(dev);
-    HJ_TRY(p.init(false));
     void *slot[DEPTH], *partials = nullptr, *result = nullptr;
-    for (int d = 0; d < DEPTH; d++) HJ_TRY(p.alloc(max_chunk * es, &slot[d]));
-    HJ_TRY(p.alloc(chunks.size() * es, &partials));
-    HJ_TRY(p.alloc(16, &result));
-    HJ_TRY(p.fork());
+    {
+        DeviceGuard g(dev);
+        HJ_TRY(p.init(false));
+        for (int d = 0; d < DEPTH; d++) HJ_TRY(p.alloc(max_chunk * es, &slot[d]));
+        HJ_TRY(p.alloc(chunks.size() * es, &partials));
+        HJ_TRY(p.alloc(16, &result));
+        HJ_TRY(p.fork());
+    }
     for (size_t c = 0; c < chunks.size(); c++) {
         const int d = (int)(c % DEPTH);
+        DeviceGuard g(dev);  // per chunk: other threads' ops interleave between chunks
         if (c >= DEPTH) HJ_CUDA(cudaStreamWaitEvent(p.up, p.comp_done[d], 0));  // the slot has been reduced
         HJ_CUDA(cudaMemcpyAsync(slot[d], (const char*)host_src + chunks[c].first * es, chunks[c].second * es,
                                 cudaMemcpyHostToDevice, p.up));
@@ -155,15 +169,19 @@ hj_status hj_reduce_host(hj_device* dev, hj_reduce_op op, hj_type_kind ty, size_
         HJ_TRY(launch_reduce(dev, op, ty, chunks[c].second, slot[d], (char*)partials + c * es));
         HJ_CUDA(cudaEventRecord(p.comp_done[d], dev->stream));
     }
-    const void* final_src = partials;
-    if (chunks.size() > 1) {
-        HJ_TRY(launch_reduce(dev, op, ty, chunks.size(), partials, result));
-        final_src = result;
+    {
+        DeviceGuard g(dev);
+        const void* final_src = partials;
+        if (chunks.size() > 1) {
+            HJ_TRY(launch_reduce(dev, op, ty, chunks.size(), partials, result));
+            final_src = result;
+        }
+        // the result leaves on the download stream, behind the last kernel
+        HJ_CUDA(cudaEventRecord(p.comp_done[0], dev->stream));
+        HJ_CUDA(cudaStreamWaitEvent(p.down, p.comp_done[0], 0));
+        HJ_CUDA(cudaMemcpyAsync(host_dst, final_src, es, cudaMemcpyDeviceToHost, p.down));
     }
-    HJ_CUDA(cudaMemcpyAsync(host_dst, final_src, es, cudaMemcpyDeviceToHost, dev->stream));
-    HJ_TRY(p.join());
-    HJ_CUDA(cudaStreamSynchronize(dev->stream));
-    return HJ_OK;
+    return p.finish();
 }
 
 hj_status hj_prefix_sum_host(hj_device* dev, hj_type_kind ty, size_t n, int32_t inclusive, const void* host_src,
@@ -175,20 +193,23 @@ hj_status hj_prefix_sum_host(hj_device* dev, hj_type_kind ty, size_t n, int32_t 
     const auto chunks = make_chunks(n, default_chunk(chunk_elems), 16 / std::min<size_t>(es, 16), true);
     size_t max_chunk = 0;
     for (auto& c : chunks) max_chunk = std::max(max_chunk, c.second);
-    DeviceGuard g(dev);
     Pipe p(dev);
-    HJ_TRY(p.init(false));
     void *in[DEPTH], *out[DEPTH], *carry = nullptr;
-    for (int d = 0; d < DEPTH; d++) {
-        HJ_TRY(p.alloc(max_chunk * es, &in[d]));
-        HJ_TRY(p.alloc(max_chunk * es, &out[d]));
+    {
+        DeviceGuard g(dev);
+        HJ_TRY(p.init(false));
+        for (int d = 0; d < DEPTH; d++) {
+            HJ_TRY(p.alloc(max_chunk * es, &in[d]));
+            HJ_TRY(p.alloc(max_chunk * es, &out[d]));
+        }
+        HJ_TRY(p.alloc(16, &carry));
+        HJ_CUDA(cudaMemsetAsync(carry, 0, 16, dev->stream));
+        HJ_TRY(p.fork());
     }
-    HJ_TRY(p.alloc(16, &carry));
-    HJ_CUDA(cudaMemsetAsync(carry, 0, 16, dev->stream));
-    HJ_TRY(p.fork());
     for (size_t c = 0; c < chunks.size(); c++) {
         const int d = (int)(c % DEPTH);
         const size_t first = chunks[c].first, count = chunks[c].second;
+        DeviceGuard g(dev);  // per chunk
         if (c >= DEPTH) HJ_CUDA(cudaStreamWaitEvent(p.up, p.down_done[d], 0));  // the slot's previous chunk has left
         HJ_CUDA(cudaMemcpyAsync(in[d], (const char*)host_src + first * es, count * es, cudaMemcpyHostToDevice, p.up));
         HJ_CUDA(cudaEventRecord(p.up_done[d], p.up));
@@ -215,9 +236,7 @@ hj_status hj_prefix_sum_host(hj_device* dev, hj_type_kind ty, size_t n, int32_t 
         HJ_CUDA(cudaMemcpyAsync((char*)host_dst + first * es, out[d], count * es, cudaMemcpyDeviceToHost, p.down));
         HJ_CUDA(cudaEventRecord(p.down_done[d], p.down));
     }
-    HJ_TRY(p.join());
-    HJ_CUDA(cudaStreamSynchronize(dev->stream));
-    return HJ_OK;
+    return p.finish();
 }
 
 hj_status hj_compress_host(hj_device* dev, size_t n, const uint8_t* host_mask, uint32_t* host_index_out,
@@ -227,16 +246,18 @@ hj_status hj_compress_host(hj_device* dev, size_t n, const uint8_t* host_mask, u
     const auto chunks = make_chunks(n, default_chunk(chunk_elems), 16, true);
     size_t max_chunk = 0;
     for (auto& c : chunks) max_chunk = std::max(max_chunk, c.second);
-    DeviceGuard g(dev);
     Pipe p(dev);
-    HJ_TRY(p.init(true));
-    uint32_t* h_cnt = reinterpret_cast<uint32_t*>(p.pinned);
     void *mask[DEPTH], *idx[DEPTH];
-    for (int d = 0; d < DEPTH; d++) {
-        HJ_TRY(p.alloc(max_chunk, &mask[d]));
-        HJ_TRY(p.alloc(max_chunk * 4, &idx[d]));
+    {
+        DeviceGuard g(dev);
+        HJ_TRY(p.init(true));
+        for (int d = 0; d < DEPTH; d++) {
+            HJ_TRY(p.alloc(max_chunk, &mask[d]));
+            HJ_TRY(p.alloc(max_chunk * 4, &idx[d]));
+        }
+        HJ_TRY(p.fork());
     }
-    HJ_TRY(p.fork());
+    uint32_t* h_cnt = reinterpret_cast<uint32_t*>(p.pinned);
     size_t total = 0, finalized = 0;
     // the host reads a chunk's count (it decides where the next chunk's indices go) and enqueues the
     // download; by then DEPTH - 1 later chunks are already in flight
@@ -253,10 +274,10 @@ hj_status hj_compress_host(hj_device* dev, size_t n, const uint8_t* host_mask, u
     for (size_t c = 0; c < chunks.size(); c++) {
         const int d = (int)(c % DEPTH);
         const size_t first = chunks[c].first, count = chunks[c].second;
-        if (c >= DEPTH) {
-            while (finalized + DEPTH <= c) HJ_TRY(finalize(finalized++));
-            HJ_CUDA(cudaStreamWaitEvent(p.up, p.down_done[d], 0));
-        }
+        if (c >= DEPTH)
+            while (finalized + DEPTH <= c) HJ_TRY(finalize(finalized++));  // waits on the host: no lock held
+        DeviceGuard g(dev);  // per chunk
+        if (c >= DEPTH) HJ_CUDA(cudaStreamWaitEvent(p.up, p.down_done[d], 0));
         HJ_CUDA(cudaMemcpyAsync(mask[d], host_mask + first, count, cudaMemcpyHostToDevice, p.up));
         HJ_CUDA(cudaEventRecord(p.up_done[d], p.up));
         HJ_CUDA(cudaStreamWaitEvent(dev->stream, p.up_done[d], 0));
@@ -268,8 +289,7 @@ hj_status hj_compress_host(hj_device* dev, size_t n, const uint8_t* host_mask, u
         HJ_CUDA(cudaEventRecord(p.comp_done[d], dev->stream));
     }
     while (finalized < chunks.size()) HJ_TRY(finalize(finalized++));
-    HJ_TRY(p.join());
-    HJ_CUDA(cudaStreamSynchronize(dev->stream));
+    HJ_TRY(p.finish());
     *host_count = (uint32_t)total;
     return HJ_OK;
 }

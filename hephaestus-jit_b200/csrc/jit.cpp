@@ -13,6 +13,7 @@
 #include <condition_variable>
 #include <cstdlib>
 #include <fstream>
+#include <memory>
 #include <unordered_set>
 
 #include "hj_internal.h"
@@ -331,7 +332,9 @@ hj_status hj_kernel_map_host(hj_device* dev, hj_kernel* k, size_t n, void* const
     if (chunk_elems == 0) chunk_elems = (size_t)1 << 24;
     chunk_elems = (chunk_elems + per_block - 1) / per_block * per_block;
     constexpr int DEPTH = 3;
-    DeviceGuard g(dev);
+    // the device lock is only needed for the stream-ordered allocations on the device stream: the chunks
+    // run on this call's own three streams, so several host threads may stream at once
+    std::unique_ptr<DeviceGuard> g(new DeviceGuard(dev));
     cudaStream_t s_up, s_k, s_down;
     HJ_CUDA(cudaStreamCreateWithFlags(&s_up, cudaStreamNonBlocking));
     HJ_CUDA(cudaStreamCreateWithFlags(&s_k, cudaStreamNonBlocking));
@@ -362,6 +365,7 @@ hj_status hj_kernel_map_host(hj_device* dev, hj_kernel* k, size_t n, void* const
         HJ_CUDA(cudaStreamWaitEvent(s_k, start, 0));
         HJ_CUDA(cudaStreamWaitEvent(s_down, start, 0));
     }
+    g.reset();
     // Chunk schedule: the pipeline's fill (first upload) and drain (last download) cannot overlap
     // with traffic in the other direction, so the first and last chunks are small (1/8, 1/4, 1/2 of
     // a full chunk on the way in, mirrored on the way out) and only the middle runs at full size.
@@ -421,8 +425,11 @@ hj_status hj_kernel_map_host(hj_device* dev, hj_kernel* k, size_t n, void* const
     cudaStreamSynchronize(s_up);
     cudaStreamSynchronize(s_k);
     cudaError_t fin = cudaStreamSynchronize(s_down);
-    for (char* p : dbuf)
-        if (p) cudaFreeAsync(p, dev->stream);
+    {
+        DeviceGuard g2(dev);
+        for (char* p : dbuf)
+            if (p) cudaFreeAsync(p, dev->stream);
+    }
     for (int d = 0; d < DEPTH; d++) { cudaEventDestroy(up_done[d]); cudaEventDestroy(k_done[d]); cudaEventDestroy(down_done[d]); }
     cudaEventDestroy(start);
     cudaStreamDestroy(s_up); cudaStreamDestroy(s_k); cudaStreamDestroy(s_down);

@@ -480,3 +480,45 @@ def test_host_streamed_ops_from_pinned_memory(dev):
     finally:
         L.lib.hj_host_free(src)
         L.lib.hj_host_free(dst)
+
+
+def test_host_streamed_ops_from_concurrent_threads(dev):
+    """Four host threads stream four different arrays at once (the library only holds its device lock
+    while a chunk is being enqueued): every result must be what the op gives alone."""
+    import threading
+    irm = importlib.import_module("hephaestus-jit_b200.ir")
+    n = (1 << 22) + 123
+    rng = np.random.Generator(np.random.PCG64(9))
+    u = rng.integers(0, 1 << 16, size=n).astype(np.uint32)
+    f = rng.random(n, dtype=np.float32)
+    x = (rng.random(n, dtype=np.float32) * 8 - 4).astype(np.float32)
+    mask = (rng.random(n) < 0.4).astype(np.uint8)
+    scan, idx, y = np.empty(n, np.uint32), np.zeros(n, np.uint32), np.empty(n, np.float32)
+    kern = dev.kernel(irm.c2_chain_ir())
+    res, errs = {}, []
+
+    def guarded(fn):
+        def run():
+            try:
+                for _ in range(3):
+                    fn()
+            except BaseException as exc:  # noqa: BLE001
+                errs.append(repr(exc))
+        return run
+
+    jobs = [lambda: dev.prefix_sum_host(hj.U32, n, True, u, scan, 1 << 18),
+            lambda: res.__setitem__("cnt", dev.compress_host(n, mask, idx, 0, 1 << 18)),
+            lambda: dev.map_host(kern, n, [x, y], 1 << 18),
+            lambda: res.__setitem__("sum", dev.reduce_host(hj.SUM, hj.F32, n, f, 1 << 18))]
+    ts = [threading.Thread(target=guarded(j)) for j in jobs]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join(timeout=300)
+    assert not errs, errs
+    assert np.array_equal(scan, np.cumsum(u, dtype=np.uint32))
+    want_cnt, want_idx = oracle.compress(mask)
+    assert res["cnt"] == want_cnt and np.array_equal(idx[:want_cnt], want_idx[:want_cnt])
+    assert np.allclose(y, oracle.c2_chain(x), rtol=4e-7, atol=1e-7)
+    exact = float(f.astype(np.float64).sum())
+    assert abs(float(res["sum"]) - exact) <= 1e-5 * exact
