@@ -353,6 +353,34 @@ def test_histogram_single_bin_worst_case(dev):
     assert np.array_equal(dst.to_host(np.uint32), want)
 
 
+@pytest.mark.parametrize("dist", ["uniform", "one_bin", "oob", "hot_tail"])
+def test_histogram_adaptive_sweeping(dev, dist):
+    """The packed-16 histogram decides after its first 64512 keys per CTA whether the 16-bit counters need
+    their overflow sweeps, and a CTA that ran without them proves afterwards that no counter wrapped
+    (sum of its counters == keys applied) or walks its tiles again with the sweeps on.
+    uniform: no sweeps, the proof holds; one_bin: the sweeps are switched on; hot_tail: the projection is
+    wrong (the keys turn hot late), counters wrap, the second walk must give the exact result; oob: most
+    keys are out of range and land on the lanes' dummy counters (which may wrap too: a false alarm)."""
+    n, n_bins = (1 << 26) + 4099, 1 << 16
+    rng = np.random.Generator(np.random.PCG64(len(dist)))
+    if dist == "uniform":
+        keys = rng.integers(0, n_bins, size=n, dtype=np.uint32)
+    elif dist == "one_bin":
+        keys = np.full(n, 40001, np.uint32)
+        keys[1::3] = 40000
+    elif dist == "oob":
+        keys = rng.integers(0, 16 * n_bins, size=n, dtype=np.uint32)
+    else:  # uniform, except the last third of the keys: > 65535 late keys per CTA in a single bin
+        keys = rng.integers(0, n_bins, size=n, dtype=np.uint32)
+        keys[-(n // 3):] = 7
+    init = rng.integers(0, 1000, size=n_bins).astype(np.uint32)
+    for rep in range(2):
+        dst = dev.create_buffer_from_slice(init)
+        dev.scatter_reduce(hj.SUM, hj.U32, n, dev.create_buffer_from_slice(keys), None, 1, dst, n_bins)
+        want = init + np.bincount(keys[keys < n_bins], minlength=n_bins).astype(np.uint32)
+        assert np.array_equal(dst.to_host(np.uint32), want), (dist, rep)
+
+
 @pytest.mark.parametrize("op", [hj.MAX, hj.MIN, hj.OR, hj.AND, hj.XOR, hj.SUM])
 def test_scatter_reduce_values_bit_exact(dev, op):
     n, n_bins = 200003, 1000
