@@ -292,6 +292,105 @@ def _cached_sharded_graph(rank, world, dev, comm, n):
     assert hows == [0, 1, 2, 2, 2], hows       # executed, captured, replayed ...
 
 
+def _random_sharded_programs(rank, world, dev, comm, n, n_programs, seed):
+    """Random traced programs over sharded arrays against their numpy statement on the WHOLE arrays: every
+    rank builds the same program (same seed) over its blocks; elementwise chains, comparisons and selects,
+    scans (whose deferred seed the next fused kernel must add), reductions broadcast back, gathers from a
+    replicated table, the global Index, casts, recorded loops, compress — in random order and nesting."""
+    import random
+    tr = importlib.import_module("hephaestus-jit_b200.tr")
+    sh = importlib.import_module("hephaestus-jit_b200.sharded")
+    U32, F32 = hj.U32, hj.F32
+    s, e = sh.shard_bounds(n, world, rank)
+    rnd = random.Random(seed)
+    data_rng = np.random.Generator(np.random.PCG64(seed))
+    k_ = np.arange(n, dtype=np.uint32)
+    table_np = data_rng.integers(0, 1 << 20, size=1024).astype(np.uint32)
+    for prog in range(n_programs):
+        table = tr.array(table_np, dev)
+        a0 = data_rng.integers(0, 1 << 12, size=n).astype(np.uint32)
+        b0 = data_rng.integers(0, 1 << 31, size=n).astype(np.uint32)
+        pool = [(tr.array_sharded(a0, comm), a0), (tr.array_sharded(b0, comm), b0), (tr.sized_index(n), k_.copy())]
+        bools = [(pool[0][0].lt(tr.literal(2048, U32)), a0 < 2048)]
+        terminal, trace_ops = [], []
+        with np.errstate(over="ignore"):
+            for _ in range(rnd.randrange(3, 12)):
+                op = rnd.randrange(11)
+                (va, a), (vb, b) = rnd.choice(pool), rnd.choice(pool)
+                trace_ops.append(op)
+                if op == 0:
+                    which = rnd.randrange(5)
+                    pool.append([(va.add(vb), a + b), (va.sub(vb), a - b), (va.min(vb), np.minimum(a, b)),
+                                 (va.or_(vb), a | b), (va.xor(vb), a ^ b)][which])
+                elif op == 1:
+                    c = rnd.randrange(1, 9)
+                    pool.append((va.mul(tr.literal(c, U32)), a * np.uint32(c)))
+                elif op == 2:
+                    bools.append((va.lt(vb), a < b))
+                elif op == 3:
+                    vm, m = rnd.choice(bools)
+                    pool.append((va.select(vm, vb), np.where(m, a, b)))
+                elif op == 4:   # scan: the result stays (local scan, offset) until somebody needs the values
+                    inc = rnd.random() < 0.5
+                    cs = np.cumsum(a, dtype=np.uint32)
+                    pool.append((va.prefix_sum(inc), cs if inc else cs - a))
+                elif op == 5:   # reduction broadcast back: a replica read at a computed (literal) index
+                    pool.append((vb.add(va.reduce_sum().gather(tr.literal(0, U32))), b + a.sum(dtype=np.uint32)))
+                elif op == 6:   # gather from the replicated table at a computed index
+                    pool.append((table.gather(va.and_(tr.literal(1023, U32))), table_np[a & np.uint32(1023)]))
+                elif op == 7:   # compress: per-rank segment + global count
+                    vm, m = rnd.choice(bools)
+                    cnt, idx = vm.compress()
+                    terminal.append(("compress", cnt, idx, m))
+                elif op == 8:   # recorded loop: x = 3x + 1, `reps` times
+                    reps = rnd.randrange(1, 4)
+
+                    def body(c, vs, reps=reps):
+                        x, it = vs
+                        it = it.add(tr.literal(1, U32))
+                        return it.lt(tr.literal(reps, U32)), [x.mul(tr.literal(3, U32)).add(tr.literal(1, U32)), it]
+
+                    _, (x1, _it) = tr.loop_record(tr.literal(True), [va, tr.sized_literal(0, n, U32)], body)
+                    w = a.copy()
+                    for _ in range(reps):
+                        w = w * np.uint32(3) + np.uint32(1)
+                    pool.append((x1, w))
+                elif op == 9:   # through f32 and back, exact for small integers
+                    small_v, small = va.and_(tr.literal(1023, U32)), a & np.uint32(1023)
+                    pool.append((small_v.cast(F32).fma(tr.literal(2.0, F32), tr.literal(1.0, F32)).cast(U32),
+                                 small * np.uint32(2) + np.uint32(1)))
+                else:           # min / max reductions of a (possibly deferred) value
+                    terminal.append(("reduce", va.reduce_max(), None, a.max()))
+        outs = [pool[-1], rnd.choice(pool[3:] or pool)]
+        for v, _ in outs:
+            v.schedule()
+        for t in terminal:
+            t[1].schedule()
+        g = tr.compile()
+        g.launch(dev)
+        ctx = f"program {prog} ops {trace_ops} world {world} rank {rank}"
+        for v, want in outs:
+            sh_info = v.shard()
+            got = v.to_vec(np.uint32)
+            assert np.array_equal(got, want[s:e] if sh_info is not None else want), ctx
+        for t in terminal:
+            if t[0] == "reduce":
+                assert int(t[1].item(np.uint32)) == int(t[3]), ctx
+            else:
+                _, cnt, idx, m = t
+                sel = np.flatnonzero(m).astype(np.uint32)
+                assert int(cnt.to_vec(np.uint32)[0]) == sel.size, ctx
+                lc, before = int(m[s:e].sum()), int(m[:s].sum())
+                got = idx.to_vec(np.uint32)
+                assert np.array_equal(got[:lc], sel[before: before + lc]) and (got[lc:] == 0).all(), ctx
+        del pool, bools, terminal, outs, g, table
+
+
+@pytest.mark.parametrize("world,n", [(1, (1 << 17) + 5), (2, (1 << 18) + 11), (3, 50_001)])
+def test_random_programs_over_sharded_arrays(world, n):
+    _run(world, "_random_sharded_programs", n, 16, 1234 + world)
+
+
 @pytest.mark.parametrize("world", [1, 2])
 def test_sharded_pass_list_replays_as_one_cuda_graph(world):
     _run(world, "_cached_sharded_graph", (1 << 20) + 4099)
