@@ -361,6 +361,12 @@ hist_ring_kernel(const uint32_t* __restrict__ keys, size_t n, uint32_t literal, 
     }
 }
 
+
+// (Round 2 measured and rejected a two-pass radix PARTITION of the keys by 32 Ki-bin window for histograms
+// with many bins — rank keys inside (tile, window) groups with warp match + shared atomics, one block of a
+// partition buffer per tile, then one window per CTA: 798 / 532 / 325 GB/s at 2^18 / 2^20 / 2^22 bins against
+// 1048 GB/s for the window groups below and 775 GB/s for plain L2 atomics at any bin count;
+// profiles/r02_histogram.txt.)
 // dst[b] += sum over groups of their private counter (u32, or u16 pairs packed in u32 words).
 // The groups are split over gridDim.y so that enough loads are in flight to stream the scratch
 // (148 x 128 KiB) at HBM speed; each slice adds its partial sum with one global atomic per bin.

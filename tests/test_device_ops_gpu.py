@@ -353,6 +353,34 @@ def test_histogram_single_bin_worst_case(dev):
     assert np.array_equal(dst.to_host(np.uint32), want)
 
 
+@pytest.mark.parametrize("n_bins,literal,dist", [
+    (1 << 18, 1, "uniform"),     # 8 windows of 32 Ki bins: groups of 8 CTAs walk the same key tiles
+    (300_001, 3, "oob"),         # beyond 8 windows: one L2 atomic per key; literal != 1, half the keys out of range
+    (1 << 20, 1, "hot"),         # 60 % of the keys in four bins: hot addresses in L2
+    (5_000_000, 1, "uniform"),
+    (200_000, 1, "edge"),        # every key is n_dst - 1 or n_dst
+])
+def test_histogram_many_bins(dev, n_bins, literal, dist):
+    n = (1 << 22) + 12345
+    rng = np.random.Generator(np.random.PCG64(n_bins + literal))
+    if dist == "hot":
+        keys = np.where(rng.random(n) < 0.6, rng.integers(0, 4, size=n), rng.integers(0, n_bins, size=n)).astype(np.uint32)
+    elif dist == "oob":
+        keys = rng.integers(0, 2 * n_bins, size=n).astype(np.uint32)
+        keys[::1001] = 0xFFFFFFFF
+    elif dist == "edge":
+        keys = np.where(rng.random(n) < 0.5, n_bins - 1, n_bins).astype(np.uint32)
+    else:
+        keys = rng.integers(0, n_bins, size=n).astype(np.uint32)
+    init = rng.integers(0, 1000, size=n_bins).astype(np.uint32)
+    for rep in range(2):
+        dst = dev.create_buffer_from_slice(init)
+        dev.scatter_reduce(hj.SUM, hj.U32, n, dev.create_buffer_from_slice(keys), None, literal, dst, n_bins)
+        inside = keys[keys < n_bins]
+        want = init + (np.bincount(inside, minlength=n_bins).astype(np.uint32) * np.uint32(literal))
+        assert np.array_equal(dst.to_host(np.uint32), want), rep
+
+
 @pytest.mark.parametrize("dist", ["uniform", "one_bin", "oob", "hot_tail"])
 def test_histogram_adaptive_sweeping(dev, dist):
     """The packed-16 histogram decides after its first 64512 keys per CTA whether the 16-bit counters need

@@ -20,7 +20,8 @@ def timeit(fn, iters=10):
     return sorted(a.elapsed_time(b) for a, b in ev)[iters // 2]
 for n, nb, dist in ((1 << 28, 1 << 16, "uniform"), ((1 << 28) - 777, 1 << 16, "uniform"), (1 << 28, 1 << 16, "zipf"), (1 << 28, 1 << 10, "uniform"),
                     (1 << 28, 100000, "uniform"), ((1 << 20) + 3, 1 << 16, "uniform"), (1 << 26, 1 << 18, "uniform"), (1 << 26, 40000, "oob"),
-                    (1 << 28, 1 << 10, "one"), (1 << 28, 256, "uniform"), (1 << 28, 4000, "uniform"), (1 << 28, 1 << 10, "zipf")):
+                    (1 << 28, 1 << 10, "one"), (1 << 28, 256, "uniform"), (1 << 28, 4000, "uniform"), (1 << 28, 1 << 10, "zipf"),
+                    (1 << 28, 1 << 18, "uniform"), (1 << 28, 1 << 20, "uniform"), (1 << 28, 1 << 22, "uniform"), (1 << 28, 1 << 18, "zipf")):
     if dist == "zipf":
         u = torch.rand(n, device="cuda", generator=g)
         keys = ((nb ** u - 1).clamp(0, nb - 1)).to(torch.int32)  # heavy head, log-uniform
