@@ -37,6 +37,8 @@ Graph::~Graph() {
     if (launched_on && uid) hj_graph_cache_drop(launched_on, uid);
     for (GraphResource& r : resources)
         if (r.kind == GraphResource::Captured && r.id != NO_VAR) ref_drop(r.id);
+    for (hj_buffer* b : seed_cache)
+        if (b) hj_buffer_release(b);
 }
 
 namespace {
@@ -369,6 +371,7 @@ void launch_graph(const Graph& g, hj_device* dev, const std::vector<VarId>& inpu
                   LaunchReport* report, hj_report* backend_report, hj_comm* comm) {
     const size_t nres = g.resources.size();
     std::vector<hj_buffer*> res(nres, nullptr);  // each non-null entry owns one reference
+    std::vector<bool> seed_from_cache(nres, false);
     std::vector<hj_shard_desc> shards(nres);     // sharded launches: placement / deferred seed per resource
     for (hj_shard_desc& sd : shards) {
         sd.placement = HJ_RES_AUTO;
@@ -469,10 +472,12 @@ void launch_graph(const Graph& g, hj_device* dev, const std::vector<VarId>& inpu
                     const uint32_t rid = p.resources[0];
                     const uint32_t k = descs[rid].ty;
                     if (shards[rid].placement == HJ_RES_SHARDED && !shards[rid].seed && k >= HJ_I8 && k <= HJ_U64) {
-                        hj_buffer* seed = nullptr;
-                        if (hj_buffer_create(dev, 16, &seed) != HJ_OK)
+                        if (g.seed_cache.size() < nres) g.seed_cache.resize(nres, nullptr);
+                        if (!g.seed_cache[rid] && hj_buffer_create(dev, 16, &g.seed_cache[rid]) != HJ_OK)
                             throw TraceError(std::string("create_buffer failed: ") + hj_last_error());
-                        shards[rid].seed = seed;
+                        hj_buffer_retain(g.seed_cache[rid]);
+                        shards[rid].seed = g.seed_cache[rid];
+                        seed_from_cache[rid] = true;
                     }
                 }
         }
@@ -615,6 +620,11 @@ void launch_graph(const Graph& g, hj_device* dev, const std::vector<VarId>& inpu
                 r.comm = comm;
                 r.deferred = shards[rid].deferred != 0;
                 r.seed = r.deferred ? shards[rid].seed : nullptr;
+                if (r.seed && seed_from_cache[rid] && rid < g.seed_cache.size() && g.seed_cache[rid] == r.seed) {
+                    // the value outlives this launch inside a variable: the next launch needs a seed of its own
+                    hj_buffer_release(g.seed_cache[rid]);
+                    g.seed_cache[rid] = nullptr;
+                }
             }
             return r;
         };

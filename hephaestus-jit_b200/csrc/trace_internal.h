@@ -162,6 +162,10 @@ struct Graph {
     std::vector<BufferDesc> resource_descs;
     std::vector<GraphResource> resources;
     std::vector<uint32_t> inputs, outputs;
+    // sharded launches: the seed buffer of every sharded integer PrefixSum destination, kept from launch to
+    // launch (stable addresses let the captured CUDA graph replay); handed over to the variable — and
+    // replaced here — when a launch leaves a live variable or an output in the deferred state
+    mutable std::vector<hj_buffer*> seed_cache;
     ~Graph();
 };
 struct LaunchReport {  // graph.rs:138-143

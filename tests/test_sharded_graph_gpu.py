@@ -391,6 +391,55 @@ def test_random_programs_over_sharded_arrays(world, n):
     _run(world, "_random_sharded_programs", n, 16, 1234 + world)
 
 
+def _recorded_sharded_function(rank, world, dev, comm, n):
+    """record(f) over sharded inputs (record.rs:93-210): traced once, then relaunched with new blocks; the
+    relaunches go through hj_execute_graph_sharded_cached.  The function scans, feeds the (deferred) scan
+    into a fused kernel, reduces and compresses."""
+    tr = importlib.import_module("hephaestus-jit_b200.tr")
+    rec = importlib.import_module("hephaestus-jit_b200.record")
+    sh = importlib.import_module("hephaestus-jit_b200.sharded")
+    U32 = hj.U32
+    s, e = sh.shard_bounds(n, world, rank)
+    calls = []
+
+    def fn(x):
+        calls.append(1)
+        y = x.mul(tr.literal(3, U32)).add(tr.literal(1, U32))
+        scan = y.prefix_sum(True)
+        z = scan.xor(tr.sized_index(n))
+        top = z.reduce_max()
+        cnt, idx = x.and_(tr.literal(7, U32)).eq(tr.literal(0, U32)).compress()
+        return [z, top, cnt, idx]
+
+    f = rec.record(fn)
+    c0, r0, _ = dev.graph_cache_stats()
+    for it in range(12):
+        x = np.random.Generator(np.random.PCG64(50 + it)).integers(0, 1 << 10, size=n).astype(np.uint32)
+        (z, top, cnt, idx), _ = f(dev, tr.array_sharded(x, comm))
+        with np.errstate(over="ignore"):
+            want_z = np.cumsum(x * np.uint32(3) + np.uint32(1), dtype=np.uint32) ^ np.arange(n, dtype=np.uint32)
+        assert np.array_equal(z.to_vec(np.uint32), want_z[s:e]), it
+        assert int(top.item(np.uint32)) == int(want_z.max()), it
+        m = (x & 7) == 0
+        sel = np.flatnonzero(m).astype(np.uint32)
+        assert int(cnt.to_vec(np.uint32)[0]) == sel.size, it
+        lc, before = int(m[s:e].sum()), int(m[:s].sum())
+        got = idx.to_vec(np.uint32)
+        assert np.array_equal(got[:lc], sel[before: before + lc]) and (got[lc:] == 0).all(), it
+        del z, top, cnt, idx
+    assert len(calls) == 1, "the function must be traced once"
+    c1, r1, p1 = dev.graph_cache_stats()
+    print(f"recorded sharded function: captured {c1 - c0}, replayed {r1 - r0} of 12 launches")
+    # the pool hands a relaunch the same addresses again (possibly after a cycle of a few launches): some
+    # launches must have been replays of a captured CUDA graph
+    assert c1 - c0 >= 1 and r1 - r0 >= 1, (c0, r0, c1, r1)
+
+
+@pytest.mark.parametrize("world", [1, 2])
+def test_recorded_function_over_sharded_inputs(world):
+    _run(world, "_recorded_sharded_function", (1 << 19) + 77)
+
+
 @pytest.mark.parametrize("world", [1, 2])
 def test_sharded_pass_list_replays_as_one_cuda_graph(world):
     _run(world, "_cached_sharded_graph", (1 << 20) + 4099)
