@@ -824,12 +824,42 @@ def run_e2e(torch, dist, hj, L, dev, comm, kernel, world, rank, x, f, u, mask, c
         if world > 1:
             dist.all_reduce(exact)
         ok = ok and abs(scalars["sum"] - float(exact.item())) <= 1e-5 * float(exact.item())
+        # The reference's own call sequence for the map — tr::array -> graph.launch -> to_vec (trace.rs:647-663,
+        # graph.rs:315-323, trace.rs:1404-1438) — on the same pinned arrays: with the blocking upload the three
+        # steps run one after the other; with tr.array_async (hj_tr_array_async) the launch and the to_vec go chunk
+        # by chunk behind the upload.  Tracing, scheduling and compiling the graph are inside the timed region.
+        traced = None
+        if rank == 0:
+            try:
+                tr = importlib.import_module("hephaestus-jit_b200.tr")
+                hx = np.ctypeslib.as_array(ctypes.cast(host["hx"], ctypes.POINTER(ctypes.c_float)), shape=(n_map,))
+                traced = {"unit": "GB/s", "bytes": "8 B/elem (f32 in, f32 out), 2^%d elements" % int(np.log2(n_map))}
+                for name, make in (("tr.array -> launch -> to_vec", tr.array), ("tr.array_async -> launch -> to_vec", tr.array_async)):
+                    ts = []
+                    for _ in range(4):
+                        hy[-m:] = 0
+                        t0 = time.perf_counter()
+                        xv = make(hx, dev)
+                        tv = xv.fma(tr.literal(1.5, hj.F32), tr.literal(0.25, hj.F32))
+                        yv = tv.sin().select(xv.gt(tr.literal(0.0, hj.F32)), tv.exp2())
+                        yv.schedule()
+                        tr.compile().launch(dev)
+                        yv.to_vec(out=hy.view(np.uint8))
+                        ts.append(time.perf_counter() - t0)
+                        del xv, tv, yv
+                    traced[name] = round(8 * n_map / float(np.median(ts[1:])) / 1e9, 2)
+                    traced[name + " check"] = bool(np.allclose(hy[-m:], want_y, rtol=2e-6, atol=1e-6))
+                    ok = ok and traced[name + " check"]
+                dev.sync()
+            except Exception as exc:  # noqa: BLE001
+                traced = {"error": str(exc)[:300]}
         ok = all_true(ok)
         by = step_bytes(n_map * world, n_ops * world, count_g)
         h2d = world * (4 * n_map + 4 * n_ops + 4 * n_ops + n_ops)
         d2h = world * (4 * n_map + 4 * n_ops) + 4 * count_g + 8 * world
         return {"value": sum(by.values()) / dt / 1e9, "unit": "GB/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                 "ms_per_step": dt * 1e3, "steps": e2e_steps, "kernel_launches_per_step": int(launches), "check": ok,
+                "traced_sequence": traced,
                 "pcie_GB/s_each_way": {"h2d": h2d / world / dt / 1e9, "d2h": d2h / world / dt / 1e9},
                 "path": "pinned host arrays -> hj_kernel_map_host + hj_reduce_host + hj_prefix_sum_host + hj_compress_host "
                         "(chunks of 2^23-2^24 elements: upload | kernel | download streams" +

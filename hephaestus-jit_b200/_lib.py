@@ -123,6 +123,7 @@ _SIGS = {
     "hj_device_launch_count": (_i32, [_vp, ctypes.POINTER(_u64)]),
     "hj_buffer_create": (_i32, [_vp, _sz, _pvp]),
     "hj_buffer_create_from_slice": (_i32, [_vp, _vp, _sz, _pvp]),
+    "hj_buffer_create_from_host_async": (_i32, [_vp, _vp, _sz, _sz, _pvp]),
     "hj_buffer_wrap": (_i32, [_vp, _vp, _sz, _pvp]),
     "hj_buffer_retain": (_i32, [_vp]),
     "hj_buffer_release": (_i32, [_vp]),
@@ -206,6 +207,7 @@ _SIGS = {
     "hj_tr_literal": (_i32, [_u32, _u64, _pu64]),
     "hj_tr_sized_literal": (_i32, [_u32, _u64, _u64, _pu64]),
     "hj_tr_array": (_i32, [_vp, _u32, _vp, _u64, _pu64]),
+    "hj_tr_array_async": (_i32, [_vp, _u32, _vp, _u64, _pu64]),
     "hj_tr_from_buffer": (_i32, [_vp, _u32, _u64, _pu64]),
     "hj_tr_bop": (_i32, [_u32, _u64, _u64, _pu64]),
     "hj_tr_uop": (_i32, [_u32, _u64, _pu64]),

@@ -643,6 +643,7 @@ hj_status hj_sharded_reduce(hj_comm* c, hj_reduce_op op, hj_type_kind ty, size_t
     size_t es = type_size(ty);
     HJ_REQUIRE(es && n_local >= 1 && n_local * es <= src->bytes && es <= dst->bytes, "hj_sharded_reduce: bad sizes");
     DeviceGuard g(c->dev);
+    settle_all(c->dev, {src, dst});
     if (c->p2p && c->world > 1) {
         // ONE kernel: the CTA that finishes the local reduction sends the partial to every peer's
         // mailbox over NVLink, collects theirs and folds them in rank order (reduce.cu)
@@ -667,6 +668,7 @@ hj_status hj_sharded_prefix_sum(hj_comm* c, hj_type_kind ty, size_t n_local, int
     HJ_REQUIRE(es && n_local >= 1 && n_local * es <= src->bytes && n_local * es <= dst->bytes,
                "hj_sharded_prefix_sum: bad sizes");
     DeviceGuard g(c->dev);
+    settle_all(c->dev, {src, dst});
     if (c->world == 1) return launch_prefix_sum(c->dev, ty, n_local, inclusive != 0, src->ptr, dst->ptr, nullptr);
     // MATERIALISED result: shard total (a read-only pass, sizeof(T) bytes/element, the exchange fused
     // into its last CTA) -> scan seeded with this rank's exclusive offset.  12 bytes/element for 4-byte
@@ -683,6 +685,7 @@ hj_status hj_sharded_prefix_sum_deferred(hj_comm* c, hj_type_kind ty, size_t n_l
     HJ_REQUIRE(es && n_local >= 1 && n_local * es <= src->bytes && n_local * es <= dst->bytes && seed_out->bytes >= es,
                "hj_sharded_prefix_sum_deferred: bad sizes");
     DeviceGuard g(c->dev);
+    settle_all(c->dev, {src, dst, seed_out});
     if (c->world == 1) {
         HJ_CUDA(cudaMemsetAsync(seed_out->ptr, 0, es, c->dev->stream));
         return launch_prefix_sum(c->dev, ty, n_local, inclusive != 0, src->ptr, dst->ptr, nullptr);
@@ -704,6 +707,7 @@ hj_status hj_apply_seed(hj_device* dev, hj_type_kind ty, size_t n, hj_buffer* bu
     HJ_REQUIRE(es && n * es <= buf->bytes && seed->bytes >= es, "hj_apply_seed: bad sizes");
     if (n == 0) return HJ_OK;
     DeviceGuard g(dev);
+    settle_all(dev, {buf, seed});
     switch (ty) {
     case HJ_I8: case HJ_U8: return run_apply_seed<uint8_t>(dev, n, buf->ptr, seed->ptr);
     case HJ_I16: case HJ_U16: return run_apply_seed<uint16_t>(dev, n, buf->ptr, seed->ptr);
@@ -723,6 +727,7 @@ hj_status hj_sharded_compress(hj_comm* c, size_t n_local, uint32_t index_base, h
                "hj_sharded_compress: bad sizes");
     HJ_REQUIRE(!counts_out || counts_out->bytes >= 4 * (size_t)c->world, "hj_sharded_compress: counts_out too small");
     DeviceGuard g(c->dev);
+    settle_all(c->dev, {src_mask, index_out, out_count, counts_out});
     return sharded_compress(c, n_local, index_base, (const uint8_t*)src_mask->ptr, (uint32_t*)index_out->ptr,
                             (uint32_t*)out_count->ptr, counts_out ? (uint32_t*)counts_out->ptr : nullptr, false);
 }
@@ -735,6 +740,7 @@ hj_status hj_sharded_scatter_reduce(hj_comm* c, hj_reduce_op op, hj_type_kind ty
     HJ_REQUIRE(es && n_local * 4 <= idx->bytes && n_dst * es <= dst->bytes && (!src || n_local * es <= src->bytes),
                "hj_sharded_scatter_reduce: bad sizes");
     DeviceGuard g(c->dev);
+    settle_all(c->dev, {idx, src, dst});
     // privatised per GPU: every rank reduces its keys into its own copy of dst (which the
     // caller initialised with the operator's identity), then the copies are combined.  The
     // packed-16 histogram (BASELINE: 2^16 u32 bins) folds its private counters AND runs the
@@ -807,6 +813,7 @@ hj_status hj_sharded_rebalance(hj_comm* c, size_t elem_bytes, hj_buffer* src, hj
     HJ_REQUIRE(counts->bytes >= 4 * (size_t)c->world, "hj_sharded_rebalance: counts too small");
     HJ_REQUIRE(!out_count || out_count->bytes >= 4, "hj_sharded_rebalance: out_count too small");
     DeviceGuard g(c->dev);
+    settle_all(c->dev, {src, counts, dst, out_count});
     const int W = c->world, me = c->rank;
     std::vector<uint32_t> cnt(W);
     HJ_CUDA(cudaMemcpyAsync(cnt.data(), counts->ptr, 4 * (size_t)W, cudaMemcpyDeviceToHost, c->dev->stream));

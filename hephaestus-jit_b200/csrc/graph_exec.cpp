@@ -261,6 +261,40 @@ hj_status execute_passes(hj_device* dev, const ShardCtx* sc, const hj_pass* pass
         HJ_TRY(events.create((size_t)n_passes + 1));
         HJ_CUDA(cudaEventRecord(ev[0], dev->stream));
     }
+    if (dev->async_live.load(std::memory_order_acquire) != 0) {
+        // Some buffer is still arriving chunk by chunk (hj_buffer_create_from_host_async).  A single kernel pass
+        // over the bare Index joins the pipeline: it is launched per chunk behind the upload events and its
+        // outputs inherit the schedule (jit.cpp: kernel_launch_streamed).  Everything else waits for the
+        // whole upload: the device stream is ordered behind it.
+        if (!sc && !timed && n_passes == 1 && passes[0].kind == HJ_PASS_KERNEL && passes[0].size_buffer < 0 && passes[0].ir &&
+            passes[0].resources && validate_ir(passes[0].ir).empty() && passes[0].ir->n_buffers == passes[0].n_resources) {
+            const hj_pass& p = passes[0];
+            std::vector<hj_buffer*> bufs(p.n_resources);
+            bool bound = true;
+            for (uint32_t b = 0; b < p.n_resources; b++) {
+                bound = bound && p.resources[b] < n_resources && env[p.resources[b]];
+                if (bound) bufs[b] = env[p.resources[b]];
+            }
+            if (bound) {
+                hj_kernel* k = nullptr;
+                HJ_TRY(hj_kernel_get(dev, p.ir, &k));
+                bool done = false;
+                hj_status s = kernel_launch_streamed(dev, k, p.size, bufs.data(), (uint32_t)bufs.size(), &done);
+                hj_kernel_release(k);
+                HJ_TRY(s);
+                if (done) {
+                    if (report) {
+                        report->n_passes = n_passes;
+                        report->cpu_duration_us =
+                            std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - cpu_start).count();
+                    }
+                    return HJ_OK;
+                }
+            }
+        }
+        DeviceGuard g(dev);
+        for (uint32_t i = 0; i < n_resources; i++) settle_locked(env[i]);
+    }
     auto res = [&](const hj_pass& p, uint32_t k, hj_buffer** out, const hj_buffer_desc** desc) -> hj_status {
         HJ_REQUIRE(k < p.n_resources, "pass references resource slot %u but has %u", k, p.n_resources);
         uint32_t id = p.resources[k];
@@ -694,7 +728,10 @@ hj_status execute_cached(hj_device* dev, const ShardCtx* sc, uint64_t graph_key,
     DeviceGuard g(dev);  // held across the whole capture: nobody else may enqueue on the capturing stream
     if (!dev->gcache) dev->gcache = new GraphCache();
     GraphCache& gc = *dev->gcache;
-    if (disabled || n_passes == 0) {
+    bool arriving = false;  // a buffer that is still being uploaded: its events cannot be waited for inside a capture
+    if (dev->async_live.load(std::memory_order_acquire) != 0)
+        for (uint32_t i = 0; i < n_resources; i++) arriving = arriving || (env[i] && env[i]->progress);
+    if (disabled || n_passes == 0 || arriving) {
         gc.plain++;
         return execute_passes(dev, sc, passes, n_passes, env, descs, n_resources, nullptr);
     }

@@ -9,6 +9,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <initializer_list>
 #include <memory>
 #include <mutex>
 #include <string>
@@ -63,6 +64,21 @@ struct LookbackScratch {
     uint64_t generation = 0;  // bumped whenever any per-device scratch is reallocated (captured graphs hold raw pointers)
 };
 
+// A buffer that is still being written (or read) chunk by chunk on one of the device's side streams:
+// an asynchronous upload (hj_buffer_create_from_host_async) or the output of a kernel pass that was
+// launched chunk-wise behind such an upload (jit.cpp: kernel_launch_streamed).  `done[c]` fires when
+// chunk c — elements [first[c], first[c] + count[c]) — is complete, `done.back()` when everything is.
+// A schedule-less progress (first.empty()) is a plain fence: the buffer is being READ on a side stream.
+// Everything that touches the buffer on the device stream calls settle() first.
+struct AsyncProgress {
+    std::vector<size_t> first, count;
+    std::vector<cudaEvent_t> done;
+    ~AsyncProgress() {
+        for (cudaEvent_t e : done)
+            if (e) cudaEventDestroy(e);
+    }
+};
+
 }  // namespace hj
 
 struct hj_device {
@@ -85,6 +101,9 @@ struct hj_device {
     std::atomic<uint64_t> n_alloc{0}, n_free{0};
     hj::KernelCache* kcache = nullptr;
     hj::GraphCache* gcache = nullptr;  // captured CUDA graphs of hj_execute_graph_cached
+    // side streams of the chunk-wise asynchronous path (upload | kernels | download), created on first use
+    cudaStream_t side_up = nullptr, side_kernel = nullptr, side_down = nullptr;
+    std::atomic<int> async_live{0};  // buffers that carry an AsyncProgress (settle() is free while this is 0)
 };
 
 struct hj_buffer {
@@ -93,6 +112,8 @@ struct hj_buffer {
     void* ptr = nullptr;
     size_t bytes = 0;
     bool owned = true;
+    std::shared_ptr<hj::AsyncProgress> progress;  // guarded by the device lock
+    uint32_t progress_elem_bytes = 0;
 };
 
 namespace hj {
@@ -103,6 +124,28 @@ struct DeviceGuard {
     std::unique_lock<std::recursive_mutex> lock;
     explicit DeviceGuard(hj_device* d) : dev(d), lock(d->mu) { cudaSetDevice(d->ordinal); }
 };
+
+// ---- chunk-wise asynchronous buffers (runtime.cpp) ------------------------------------------
+hj_status ensure_side_streams(hj_device* dev);  // device lock held
+void attach_progress(hj_buffer* b, std::shared_ptr<AsyncProgress> p, uint32_t elem_bytes);  // device lock held
+// Orders the device stream behind whatever a side stream still does with `b` and forgets the progress.
+void settle_locked(hj_buffer* b);
+inline void settle(hj_buffer* b) {
+    if (!b || b->dev->async_live.load(std::memory_order_acquire) == 0) return;
+    DeviceGuard g(b->dev);
+    settle_locked(b);
+}
+inline void settle_all(hj_device* dev, std::initializer_list<hj_buffer*> bs) {  // device lock held
+    if (dev->async_live.load(std::memory_order_acquire) == 0) return;
+    for (hj_buffer* b : bs) settle_locked(b);
+}
+// first / count (in elements) of the chunks `n` elements are moved in: small chunks at both ends (the fill
+// and the drain of the pipeline overlap nothing), full ones in between
+void chunk_schedule(size_t n, size_t chunk_elems, size_t align_elems, std::vector<size_t>* first, std::vector<size_t>* count);
+
+// jit.cpp: launches a kernel pass chunk by chunk behind asynchronous uploads; *done = false when not applicable
+hj_status kernel_launch_streamed(hj_device* dev, hj_kernel* k, size_t size, hj_buffer* const* buffers, uint32_t n_buffers,
+                                 bool* done);
 
 // Grow-only scratch helpers (called with the device lock held).
 hj_status ensure_reduce_scratch(hj_device* dev, size_t bytes);

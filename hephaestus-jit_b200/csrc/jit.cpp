@@ -133,6 +133,95 @@ hj_status get_cubin(const hj_ir* ir, CodegenResult* cg, std::vector<char>* cubin
 
 using namespace hj;
 
+namespace hj {
+// A kernel pass behind asynchronous uploads: when at least one buffer is still arriving chunk by chunk
+// (AsyncProgress with a schedule) and the kernel touches every buffer through the bare Index only, the
+// pass is launched once per chunk on the kernel side stream, each launch behind the upload events of
+// its chunk, and the buffers it writes inherit the schedule with one event per chunk — hj_buffer_to_host
+// then drains them chunk by chunk.  `*done` = false: not applicable, the caller launches normally
+// (hj_kernel_launch settles the buffers first).
+hj_status kernel_launch_streamed(hj_device* dev, hj_kernel* k, size_t size, hj_buffer* const* buffers, uint32_t n_buffers,
+                                 bool* done) {
+    *done = false;
+    static const bool debug = getenv("HJ_DEBUG_STREAMED") != nullptr;
+    auto why = [&](int reason) {
+        if (debug) fprintf(stderr, "[hj] kernel pass not streamed: reason %d\n", reason);
+        return HJ_OK;
+    };
+    static const bool off = getenv("HJ_NO_STREAMED_LAUNCH") != nullptr;
+    if (off || !k->vec || n_buffers != k->n_buffers || size == 0 || size > 0xffffffffull) return why(1);
+    if (dev->async_live.load(std::memory_order_acquire) == 0) return why(2);
+    DeviceGuard g(dev);
+    std::shared_ptr<AsyncProgress> ref;
+    for (uint32_t i = 0; i < n_buffers; i++) {
+        hj_buffer* b = buffers[i];
+        if (!b || b->dev != dev) return why(3);
+        if (k->slot_flags[i] != 1 && k->slot_flags[i] != 2) return why(4);
+        if (((uintptr_t)b->ptr & 15u) != 0 || b->bytes < size * k->slot_elem_bytes[i]) return why(5);
+        for (uint32_t j = 0; j < i; j++)
+            if (buffers[j] == b || buffers[j]->ptr == b->ptr) return why(6);  // aliased slots: the ordinary launch checks them
+        if (!b->progress) continue;
+        if (k->slot_flags[i] == 2) return why(7);  // a destination that is itself still being written
+        if (b->progress->first.empty()) return why(8);  // being read elsewhere: settle and launch normally
+        if (b->progress_elem_bytes != k->slot_elem_bytes[i]) return why(9);
+        if (!ref) ref = b->progress;
+        else if (ref->first != b->progress->first || ref->count != b->progress->count) return why(10);
+    }
+    if (!ref || ref->first.back() + ref->count.back() != size) return why(11);
+    HJ_TRY(ensure_side_streams(dev));
+    cudaStream_t sk = dev->side_kernel;
+    // outputs were allocated on the device stream; whatever was enqueued there comes first
+    cudaEvent_t start = nullptr;
+    HJ_CUDA(cudaEventCreateWithFlags(&start, cudaEventDisableTiming));
+    cudaError_t e = cudaEventRecord(start, dev->stream);
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(sk, start, 0);
+    cudaEventDestroy(start);
+    if (e != cudaSuccess) { cudaGetLastError(); return fail(HJ_ERR_CUDA, "streamed launch: %s", cudaGetErrorString(e)); }
+    auto out = std::make_shared<AsyncProgress>();
+    out->first = ref->first;
+    out->count = ref->count;
+    const size_t per_block = (size_t)k->threads * k->vec_width * k->unroll;
+    std::vector<void*> ptrs(n_buffers);
+    for (size_t c = 0; c < ref->first.size(); c++) {
+        const size_t first = ref->first[c], count = ref->count[c];
+        for (uint32_t i = 0; i < n_buffers; i++) {
+            if (buffers[i]->progress) cudaStreamWaitEvent(sk, buffers[i]->progress->done[c], 0);
+            ptrs[i] = (char*)buffers[i]->ptr + first * k->slot_elem_bytes[i];
+        }
+        const uint32_t* size_ptr = nullptr;
+        uint32_t size_static = (uint32_t)count, index_base = (uint32_t)first;
+        std::vector<void*> args = {(void*)&size_ptr, (void*)&size_static, (void*)&index_base};
+        for (uint32_t i = 0; i < n_buffers; i++) args.push_back((void*)&ptrs[i]);
+        const unsigned grid = (unsigned)((count + per_block - 1) / per_block);
+        e = cudaLaunchKernel((const void*)k->vec, dim3(grid), dim3(k->threads), args.data(), 0, sk);
+        cudaEvent_t ev = nullptr;
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
+        if (ev) out->done.push_back(ev);
+        if (e == cudaSuccess) e = cudaEventRecord(ev, sk);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            cudaStreamSynchronize(sk);  // nothing of this pass may outlive the error return
+            return fail(HJ_ERR_CUDA, "streamed launch of fused kernel failed: %s", cudaGetErrorString(e));
+        }
+        dev->launches.fetch_add(1, std::memory_order_relaxed);
+    }
+    // the buffers this pass wrote arrive chunk by chunk; the ones it read are busy until its last chunk
+    auto fence = std::make_shared<AsyncProgress>();
+    {
+        cudaEvent_t ev = nullptr;
+        HJ_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        fence->done.push_back(ev);
+        HJ_CUDA(cudaEventRecord(ev, sk));
+    }
+    for (uint32_t i = 0; i < n_buffers; i++) {
+        if (k->slot_flags[i] == 2) attach_progress(buffers[i], out, k->slot_elem_bytes[i]);
+        else attach_progress(buffers[i], fence, k->slot_elem_bytes[i]);
+    }
+    *done = true;
+    return HJ_OK;
+}
+}  // namespace hj
+
 extern "C" {
 
 hj_status hj_ir_codegen(const hj_ir* ir, char** out_source) {
@@ -285,6 +374,7 @@ hj_status hj_kernel_launch(hj_device* dev, hj_kernel* k, size_t size, hj_buffer*
     for (uint32_t i = 0; i < n_buffers; i++) args.push_back((void*)&ptrs[i]);
 
     DeviceGuard g(dev);
+    for (uint32_t i = 0; i < n_buffers; i++) settle_locked(buffers[i]);
     const bool use_vec = k->vec && aligned && !getenv("HJ_JIT_SCALAR");
     const size_t per_block = use_vec ? (size_t)k->threads * k->vec_width * k->unroll : k->threads;
     const unsigned grid = (unsigned)((size + per_block - 1) / per_block);
@@ -371,22 +461,9 @@ hj_status hj_kernel_map_host(hj_device* dev, hj_kernel* k, size_t n, void* const
     // a full chunk on the way in, mirrored on the way out) and only the middle runs at full size.
     std::vector<std::pair<size_t, size_t>> chunks;  // (first element, count)
     {
-        static const bool ramp = !getenv("HJ_MAP_NO_RAMP");
-        size_t left = n;
-        auto take = [&](size_t c) {
-            c = std::min(c, left);
-            if (c) {
-                chunks.emplace_back(n - left, c);
-                left -= c;
-            }
-        };
-        if (ramp && n >= 4 * chunk_elems) {
-            const size_t tail_total = chunk_elems / 2 + chunk_elems / 4 + chunk_elems / 8;
-            for (size_t div = 8; div >= 2; div /= 2) take(chunk_elems / div);
-            while (left > tail_total) take(std::min(chunk_elems, left - tail_total));
-            for (size_t div = 2; div <= 8; div *= 2) take(chunk_elems / div);
-        }
-        while (left) take(chunk_elems);
+        std::vector<size_t> first, count;
+        chunk_schedule(n, chunk_elems, per_block, &first, &count);
+        for (size_t c = 0; c < first.size(); c++) chunks.emplace_back(first[c], count[c]);
     }
     const size_t n_chunks = chunks.size();
     for (size_t c = 0; c < n_chunks && st == HJ_OK; c++) {

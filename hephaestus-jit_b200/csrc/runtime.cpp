@@ -6,6 +6,7 @@
 // host<->device copies.  CUDA-native choices: one non-blocking stream per device (stream order
 // replaces the reference's render-graph barriers and its blocking fence per submit), the
 // stream-ordered allocator `cudaMallocAsync` with an unbounded release threshold as the pool.
+#include <algorithm>
 #include <cstdlib>
 #include <map>
 
@@ -198,6 +199,8 @@ hj_status hj_device_sync(hj_device* dev) {
     HJ_REQUIRE(dev, "null device");
     DeviceGuard g(dev);
     HJ_CUDA(cudaStreamSynchronize(dev->stream));
+    for (cudaStream_t s : {dev->side_up, dev->side_kernel, dev->side_down})
+        if (s) HJ_CUDA(cudaStreamSynchronize(s));
     return HJ_OK;
 }
 hj_status hj_device_stream(hj_device* dev, void** out_stream) {
@@ -248,6 +251,53 @@ hj_status hj_device_launch_count(hj_device* dev, uint64_t* out) {
     return HJ_OK;
 }
 
+// ---- chunk-wise asynchronous buffers ----------------------------------------------------------
+}  // extern "C"
+namespace hj {
+hj_status ensure_side_streams(hj_device* dev) {
+    if (dev->side_down) return HJ_OK;
+    HJ_CUDA(cudaStreamCreateWithFlags(&dev->side_up, cudaStreamNonBlocking));
+    HJ_CUDA(cudaStreamCreateWithFlags(&dev->side_kernel, cudaStreamNonBlocking));
+    HJ_CUDA(cudaStreamCreateWithFlags(&dev->side_down, cudaStreamNonBlocking));
+    return HJ_OK;
+}
+void attach_progress(hj_buffer* b, std::shared_ptr<AsyncProgress> p, uint32_t elem_bytes) {
+    if (!b->progress) b->dev->async_live.fetch_add(1, std::memory_order_release);
+    b->progress = std::move(p);
+    b->progress_elem_bytes = elem_bytes;
+}
+void settle_locked(hj_buffer* b) {
+    if (!b || !b->progress) return;
+    if (!b->progress->done.empty()) cudaStreamWaitEvent(b->dev->stream, b->progress->done.back(), 0);
+    b->progress.reset();
+    b->dev->async_live.fetch_sub(1, std::memory_order_release);
+}
+void chunk_schedule(size_t n, size_t chunk_elems, size_t align_elems, std::vector<size_t>* first, std::vector<size_t>* count) {
+    first->clear();
+    count->clear();
+    if (align_elems == 0) align_elems = 1;
+    chunk_elems = std::max(align_elems, (chunk_elems + align_elems - 1) / align_elems * align_elems);
+    static const bool ramp = !getenv("HJ_MAP_NO_RAMP");
+    size_t left = n;
+    auto take = [&](size_t c) {
+        c = std::min((c + align_elems - 1) / align_elems * align_elems, left);
+        if (c) {
+            first->push_back(n - left);
+            count->push_back(c);
+            left -= c;
+        }
+    };
+    if (ramp && n >= 4 * chunk_elems) {
+        const size_t tail_total = chunk_elems / 2 + chunk_elems / 4 + chunk_elems / 8 + 3 * align_elems;
+        for (size_t div = 8; div >= 2; div /= 2) take(chunk_elems / div);
+        while (left > tail_total) take(std::min(chunk_elems, left - tail_total));
+        for (size_t div = 2; div <= 8; div *= 2) take(chunk_elems / div);
+    }
+    while (left) take(chunk_elems);
+}
+}  // namespace hj
+extern "C" {
+
 // ---- buffers --------------------------------------------------------------------------------
 
 hj_status hj_buffer_create(hj_device* dev, size_t bytes, hj_buffer** out) {
@@ -286,6 +336,56 @@ hj_status hj_buffer_create_from_slice(hj_device* dev, const void* data, size_t b
     return HJ_OK;
 }
 
+// Asynchronous chunk-wise upload (`tr::array -> launch -> to_vec` without three blocking steps).
+// Returns at once; the copy runs on the upload side stream in the chunks of chunk_schedule(), one event
+// per chunk.  A kernel pass over the bare Index that reads such buffers is launched chunk by chunk behind
+// those events (jit.cpp: kernel_launch_streamed) and hj_buffer_to_host of its outputs drains chunk by
+// chunk too, so upload, kernels and download of one array -> launch -> to_vec sequence overlap like in
+// hj_kernel_map_host.  Contract: `src` stays valid and unchanged until the buffer has been consumed by
+// something that blocks (hj_buffer_to_host of a dependent result, hj_device_sync); pinned memory
+// (hj_host_alloc) is needed for the copy to be asynchronous at all.
+hj_status hj_buffer_create_from_host_async(hj_device* dev, const void* src, size_t bytes, size_t elem_bytes,
+                                           hj_buffer** out) {
+    HJ_REQUIRE(dev && out && (src || bytes == 0), "null argument");
+    HJ_REQUIRE(elem_bytes > 0 && bytes % elem_bytes == 0, "size %zu is not a multiple of the element size %zu", bytes, elem_bytes);
+    HJ_TRY(hj_buffer_create(dev, bytes, out));
+    if (!bytes) return HJ_OK;
+    DeviceGuard g(dev);
+    hj_status st = ensure_side_streams(dev);
+    auto pr = std::make_shared<AsyncProgress>();
+    if (st == HJ_OK) {
+        static const size_t chunk = getenv("HJ_ASYNC_CHUNK_ELEMS") ? (size_t)atoll(getenv("HJ_ASYNC_CHUNK_ELEMS")) : ((size_t)1 << 24);
+        chunk_schedule(bytes / elem_bytes, chunk, 4096, &pr->first, &pr->count);
+        cudaEvent_t alloc_done = nullptr;  // the allocation is ordered on the device stream
+        cudaError_t e = cudaEventCreateWithFlags(&alloc_done, cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventRecord(alloc_done, dev->stream);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(dev->side_up, alloc_done, 0);
+        for (size_t c = 0; c < pr->first.size() && e == cudaSuccess; c++) {
+            cudaEvent_t ev = nullptr;
+            e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
+            if (e != cudaSuccess) break;
+            pr->done.push_back(ev);
+            e = cudaMemcpyAsync((char*)(*out)->ptr + pr->first[c] * elem_bytes, (const char*)src + pr->first[c] * elem_bytes,
+                                pr->count[c] * elem_bytes, cudaMemcpyHostToDevice, dev->side_up);
+            if (e == cudaSuccess) e = cudaEventRecord(ev, dev->side_up);
+        }
+        if (alloc_done) cudaEventDestroy(alloc_done);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            cudaStreamSynchronize(dev->side_up);
+            st = fail(HJ_ERR_CUDA, "asynchronous upload failed: %s", cudaGetErrorString(e));
+        }
+    }
+    if (st != HJ_OK) {
+        g.lock.unlock();
+        hj_buffer_release(*out);
+        *out = nullptr;
+        return st;
+    }
+    attach_progress(*out, std::move(pr), (uint32_t)elem_bytes);
+    return HJ_OK;
+}
+
 hj_status hj_buffer_wrap(hj_device* dev, void* device_ptr, size_t bytes, hj_buffer** out) {
     HJ_REQUIRE(dev && out && device_ptr, "null argument");
     auto b = new hj_buffer();
@@ -308,6 +408,7 @@ hj_status hj_buffer_release(hj_buffer* buf) {
     HJ_REQUIRE(buf, "null buffer");
     if (buf->rc.fetch_sub(1) != 1) return HJ_OK;
     hj_device* dev = buf->dev;
+    settle(buf);  // a side stream may still be filling or reading it: the free below is ordered behind that
     if (buf->owned && buf->ptr) {
         DeviceGuard g(dev);
         // stream-ordered free: memory returns to the pool after all enqueued work that may
@@ -325,10 +426,31 @@ hj_status hj_buffer_to_host(hj_buffer* buf, size_t offset_bytes, size_t nbytes, 
     HJ_REQUIRE(offset_bytes + nbytes <= buf->bytes, "to_host range [%zu, %zu) exceeds buffer of %zu bytes",
                offset_bytes, offset_bytes + nbytes, buf->bytes);
     if (!nbytes) return HJ_OK;
-    DeviceGuard g(buf->dev);
+    hj_device* dev = buf->dev;
+    std::unique_lock<std::recursive_mutex> lock(dev->mu);
+    cudaSetDevice(dev->ordinal);
+    if (buf->progress && !buf->progress->first.empty() && dev->side_down) {
+        // The buffer is still being produced chunk by chunk on a side stream: every chunk goes down as soon as
+        // its event fires, on the download stream — the copy overlaps the uploads and kernels of later chunks.
+        std::shared_ptr<AsyncProgress> pr = buf->progress;
+        const size_t es = buf->progress_elem_bytes;
+        for (size_t c = 0; c < pr->first.size(); c++) {
+            const size_t c0 = pr->first[c] * es, c1 = c0 + pr->count[c] * es;
+            const size_t lo = std::max(c0, offset_bytes), hi = std::min(c1, offset_bytes + nbytes);
+            if (lo >= hi) continue;
+            HJ_CUDA(cudaStreamWaitEvent(dev->side_down, pr->done[c], 0));
+            HJ_CUDA(cudaMemcpyAsync((char*)dst + (lo - offset_bytes), (const char*)buf->ptr + lo, hi - lo,
+                                    cudaMemcpyDeviceToHost, dev->side_down));
+        }
+        cudaStream_t down = dev->side_down;
+        lock.unlock();  // other threads may enqueue while this one waits for its data
+        HJ_CUDA(cudaStreamSynchronize(down));
+        return HJ_OK;
+    }
+    settle_locked(buf);
     HJ_CUDA(cudaMemcpyAsync(dst, (const char*)buf->ptr + offset_bytes, nbytes, cudaMemcpyDeviceToHost,
-                            buf->dev->stream));
-    HJ_CUDA(cudaStreamSynchronize(buf->dev->stream));
+                            dev->stream));
+    HJ_CUDA(cudaStreamSynchronize(dev->stream));
     return HJ_OK;
 }
 
@@ -337,6 +459,7 @@ hj_status hj_buffer_upload(hj_buffer* buf, size_t offset_bytes, const void* src,
     HJ_REQUIRE(offset_bytes + nbytes <= buf->bytes, "upload range exceeds buffer");
     if (!nbytes) return HJ_OK;
     DeviceGuard g(buf->dev);
+    settle_locked(buf);
     HJ_CUDA(cudaMemcpyAsync((char*)buf->ptr + offset_bytes, src, nbytes, cudaMemcpyHostToDevice,
                             buf->dev->stream));
     return HJ_OK;
@@ -346,12 +469,14 @@ hj_status hj_buffer_fill_zero(hj_buffer* buf) {
     HJ_REQUIRE(buf, "null buffer");
     if (!buf->bytes) return HJ_OK;
     DeviceGuard g(buf->dev);
+    settle_locked(buf);
     HJ_CUDA(cudaMemsetAsync(buf->ptr, 0, buf->bytes, buf->dev->stream));
     return HJ_OK;
 }
 
 hj_status hj_buffer_device_ptr(hj_buffer* buf, void** out) {
     HJ_REQUIRE(buf && out, "null argument");
+    settle(buf);  // the pointer leaves the library: whatever uses it is ordered on the device stream
     *out = buf->ptr;
     return HJ_OK;
 }
@@ -440,6 +565,7 @@ hj_status hj_reduce(hj_device* dev, hj_reduce_op op, hj_type_kind ty, size_t n, 
     HJ_REQUIRE(n * es <= src->bytes, "hj_reduce: src holds %zu bytes, need %zu", src->bytes, n * es);
     HJ_REQUIRE(es <= dst->bytes, "hj_reduce: dst too small");
     DeviceGuard g(dev);
+    settle_all(dev, {src, dst});
     return launch_reduce(dev, op, ty, n, src->ptr, dst->ptr);
 }
 
@@ -453,6 +579,7 @@ hj_status hj_prefix_sum(hj_device* dev, hj_type_kind ty, size_t n, int32_t inclu
     HJ_REQUIRE(!seed || seed->bytes >= es, "hj_prefix_sum: seed too small");
     if (getenv("HJ_REF_COMPAT")) inclusive = 1;  // reference defect D10: always inclusive
     DeviceGuard g(dev);
+    settle_all(dev, {src, dst, seed});
     return launch_prefix_sum(dev, ty, n, inclusive != 0, src->ptr, dst->ptr, seed ? seed->ptr : nullptr);
 }
 
@@ -464,6 +591,7 @@ hj_status hj_compress(hj_device* dev, size_t n, hj_buffer* size_buf, hj_buffer* 
     HJ_REQUIRE(n * 4 <= index_out->bytes, "hj_compress: index_out too small");
     HJ_REQUIRE(out_count->bytes >= 4 && (!size_buf || size_buf->bytes >= 4), "hj_compress: count buffer too small");
     DeviceGuard g(dev);
+    settle_all(dev, {size_buf, out_count, src_mask, index_out});
     return launch_compress(dev, n, size_buf ? (const uint32_t*)size_buf->ptr : nullptr,
                            (uint32_t*)out_count->ptr, (const uint8_t*)src_mask->ptr,
                            (uint32_t*)index_out->ptr, index_base);
@@ -478,6 +606,7 @@ hj_status hj_scatter_reduce(hj_device* dev, hj_reduce_op op, hj_type_kind ty, si
     HJ_REQUIRE(!src || n * es <= src->bytes, "hj_scatter_reduce: src too small");
     HJ_REQUIRE(n_dst * es <= dst->bytes, "hj_scatter_reduce: dst too small");
     DeviceGuard g(dev);
+    settle_all(dev, {idx, src, dst});
     return launch_scatter_reduce(dev, op, ty, n, (const uint32_t*)idx->ptr, src ? src->ptr : nullptr,
                                  literal, dst->ptr, n_dst);
 }
@@ -487,6 +616,7 @@ hj_status hj_gather(hj_device* dev, size_t elem_bytes, size_t n, hj_buffer* src,
     HJ_REQUIRE(dev && src && idx && dst, "hj_gather: null argument");
     HJ_REQUIRE(n * 4 <= idx->bytes && n * elem_bytes <= dst->bytes, "hj_gather: buffer too small");
     DeviceGuard g(dev);
+    settle_all(dev, {src, idx, dst});
     return launch_gather(dev, elem_bytes, n, src->ptr, (const uint32_t*)idx->ptr, dst->ptr);
 }
 

@@ -353,6 +353,16 @@ VarId array(hj_device* dev, TypeId ty, const void* data, size_t n) {  // trace.r
     v.data.buf = buf;  // ownership of the creation reference moves into the trace
     return new_var(std::move(v), {});
 }
+VarId array_async(hj_device* dev, TypeId ty, const void* pinned, size_t n) {  // runtime.cpp: chunk-wise upload on a side stream
+    hj_buffer* buf = nullptr;
+    if (hj_buffer_create_from_host_async(dev, pinned, n * type_size(ty), type_size(ty), &buf) != HJ_OK)
+        throw TraceError(std::string("create_buffer_from_host_async failed: ") + hj_last_error());
+    Extent e; e.n = n;
+    Var v = make(OpKind::Buffer, 0, 0, ty, e);
+    v.data.kind = Resource::Buffer;
+    v.data.buf = buf;
+    return new_var(std::move(v), {});
+}
 VarId from_buffer(hj_buffer* buf, TypeId ty, size_t n) {
     hj_buffer_retain(buf);
     Extent e; e.n = n;

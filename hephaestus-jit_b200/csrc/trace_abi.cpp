@@ -104,6 +104,7 @@ hj_status hj_tr_literal(uint32_t ty, uint64_t bits, uint64_t* out) { OUT(literal
 hj_status hj_tr_sized_literal(uint32_t ty, uint64_t bits, uint64_t n, uint64_t* out) { OUT(literal(ty, bits, n)); }
 hj_status hj_tr_array(hj_device* dev, uint32_t ty, const void* data, uint64_t n, uint64_t* out) { OUT(array(dev, ty, data, n)); }
 hj_status hj_tr_from_buffer(hj_buffer* buf, uint32_t ty, uint64_t n, uint64_t* out) { OUT(from_buffer(buf, ty, n)); }
+hj_status hj_tr_array_async(hj_device* dev, uint32_t ty, const void* data, uint64_t n, uint64_t* out) { OUT(array_async(dev, ty, data, n)); }
 hj_status hj_tr_array_sharded(hj_comm* comm, uint32_t ty, const void* local_data, uint64_t n_global, uint64_t* out) {
     OUT(array_sharded(comm, ty, local_data, n_global));
 }

@@ -97,6 +97,7 @@ VarId sized_index(size_t n);
 VarId dynamic_index(size_t capacity, VarId size);
 VarId literal(TypeId ty, uint64_t bits, size_t size);
 VarId array(hj_device* dev, TypeId ty, const void* data, size_t n);
+VarId array_async(hj_device* dev, TypeId ty, const void* pinned, size_t n);
 VarId from_buffer(hj_buffer* buf, TypeId ty, size_t n);
 // this rank's block of an n_global-element array: from host memory / from an existing device buffer
 VarId array_sharded(hj_comm* comm, TypeId ty, const void* local_data, size_t n_global);

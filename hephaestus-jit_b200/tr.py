@@ -86,7 +86,7 @@ def type_offset(ty: int, elem: int) -> int:
 class VarRef:
     """Mirror of ``tr::VarRef`` (trace.rs:244-291): an owned reference to a trace variable."""
 
-    __slots__ = ("_id", "__weakref__")
+    __slots__ = ("_id", "_keepalive", "__weakref__")
 
     def __init__(self, handle: int):
         self._id = int(handle)
@@ -294,9 +294,10 @@ class VarRef:
     def reduce_xor(self): return self.reduce(XOR)
 
     # -- read back (trace.rs:1400-1438) --------------------------------------------------------------
-    def to_vec(self, dtype=None, start: int = 0, end: int | None = None) -> np.ndarray:
+    def to_vec(self, dtype=None, start: int = 0, end: int | None = None, out: np.ndarray | None = None) -> np.ndarray:
         """``to_vec::<T>(range)``: the evaluated values as ``dtype`` (default: the variable's own
-        scalar type); a DynSize variable reads its device-resident count first."""
+        scalar type); a DynSize variable reads its device-resident count first.  ``out``: a contiguous
+        destination of the right size (pinned memory makes the download asynchronous per chunk)."""
         ty = self.ty()
         n = _u64()
         check(lib.hj_tr_var_size(self._id, ctypes.byref(n)))
@@ -312,10 +313,14 @@ class VarRef:
         dt = np.dtype(dtype)
         nbytes = (end - start) * es
         assert nbytes % dt.itemsize == 0 and (start * es) % dt.itemsize == 0
-        raw = np.empty(nbytes, dtype=np.uint8)
+        if out is not None:
+            assert out.flags["C_CONTIGUOUS"] and out.nbytes == nbytes, "to_vec: `out` does not match the range"
+            raw = out
+        else:
+            raw = np.empty(nbytes, dtype=np.uint8)
         if nbytes:
             check(lib.hj_tr_to_host(self._id, start, end - start, raw.ctypes.data_as(ctypes.c_void_p)))
-        return raw.view(dt)
+        return raw if out is not None else raw.view(dt)
 
     def item(self, dtype=None):
         assert self.size() == 1
@@ -391,6 +396,22 @@ def array(data, device: Device, ty: int | None = None) -> VarRef:
     out = _u64()
     check(lib.hj_tr_array(device.handle, ty, a.ctypes.data_as(ctypes.c_void_p), a.size, ctypes.byref(out)))
     return VarRef(out.value)
+
+
+def array_async(data: np.ndarray, device: Device, ty: int | None = None) -> VarRef:
+    """``tr::array`` that returns at once (``hj_tr_array_async``): ``data`` — a contiguous numpy array over
+    PINNED memory — is uploaded chunk by chunk on a side stream; a launch of one fused kernel over it and the
+    ``to_vec`` of its results then run chunk-wise behind the upload, so the three steps overlap.  The array is
+    kept alive by the variable and must not be modified until a dependent ``to_vec`` / ``device.sync()`` returned."""
+    assert isinstance(data, np.ndarray) and data.flags["C_CONTIGUOUS"], "array_async takes a contiguous numpy array"
+    if ty is None:
+        ty = _FROM_NP[data.dtype]
+    assert np.dtype(_NP[ty]).itemsize == data.dtype.itemsize
+    out = _u64()
+    check(lib.hj_tr_array_async(device.handle, ty, data.ctypes.data_as(ctypes.c_void_p), data.size, ctypes.byref(out)))
+    v = VarRef(out.value)
+    v._keepalive = data
+    return v
 
 
 def array_sharded(data, comm, ty: int | None = None, is_global: bool = True) -> VarRef:

@@ -97,6 +97,16 @@ hj_status hj_device_launch_count(hj_device* dev, uint64_t* out);
 hj_status hj_buffer_create(hj_device* dev, size_t bytes, hj_buffer** out);
 hj_status hj_buffer_create_from_slice(hj_device* dev, const void* data, size_t bytes,
                                       hj_buffer** out);
+/* create_buffer_from_slice that returns at once: `src` (pinned: hj_host_alloc) is copied chunk by chunk on a
+ * side stream.  A single kernel pass over the bare Index that reads such buffers (hj_execute_graph with one
+ * Kernel pass — what `x.fma(..).sin()..` of a traced program compiles to) is launched per chunk behind the
+ * upload, and hj_buffer_to_host of its outputs drains per chunk: the reference's three blocking steps
+ * `tr::array -> graph.launch -> to_vec` (trace.rs:647-663, graph.rs:315-323, trace.rs:1404-1438) overlap.
+ * Every other use of the buffer first waits (on the device, not the host) for the whole upload.
+ * `src` must stay valid and unchanged until a blocking call on a dependent result (hj_buffer_to_host,
+ * hj_device_sync) has returned.  `elem_bytes`: element size of the array (chunks end on element boundaries). */
+hj_status hj_buffer_create_from_host_async(hj_device* dev, const void* src, size_t bytes, size_t elem_bytes,
+                                           hj_buffer** out);
 /* Non-owning view over device memory someone else allocated (e.g. a torch tensor). */
 hj_status hj_buffer_wrap(hj_device* dev, void* device_ptr, size_t bytes, hj_buffer** out);
 hj_status hj_buffer_retain(hj_buffer* buf);
@@ -478,6 +488,8 @@ hj_status hj_tr_from_buffer(hj_buffer* buf, uint32_t ty, uint64_t n, uint64_t* o
  * (hj_shard_bounds).  Everything traced from it is scheduled exactly like the reference schedules the
  * unsharded program; Graph launches that meet a sharded variable run through hj_execute_graph_sharded.
  * The communicator is borrowed and must outlive the variables. */
+/* tr::array over pinned host memory with the asynchronous upload of hj_buffer_create_from_host_async */
+hj_status hj_tr_array_async(hj_device* dev, uint32_t ty, const void* pinned_data, uint64_t n, uint64_t* out);
 hj_status hj_tr_array_sharded(hj_comm* comm, uint32_t ty, const void* local_data, uint64_t n_global, uint64_t* out);
 hj_status hj_tr_from_buffer_sharded(hj_comm* comm, hj_buffer* local_buf, uint32_t ty, uint64_t n_global, uint64_t* out);
 /* *sharded = 1: the variable's buffer is the block [start, start + count) of its global extent;
