@@ -292,6 +292,23 @@ hj_status execute_passes(hj_device* dev, const ShardCtx* sc, const hj_pass* pass
                 }
             }
         }
+        if (!sc && !timed && n_passes == 1 && passes[0].kind == HJ_PASS_PREFIX_SUM && passes[0].n_resources >= 2 &&
+            passes[0].resources && passes[0].resources[0] < n_resources && passes[0].resources[1] < n_resources &&
+            env[passes[0].resources[0]] && env[passes[0].resources[1]]) {
+            const hj_pass& p = passes[0];
+            const uint32_t rd = p.resources[0], rs = p.resources[1];
+            bool done = false;
+            HJ_TRY(prefix_sum_arriving(dev, (hj_type_kind)descs[rd].ty, descs[rs].size, p.arg != 0 || getenv("HJ_REF_COMPAT"),
+                                       env[rs], env[rd], &done));
+            if (done) {
+                if (report) {
+                    report->n_passes = n_passes;
+                    report->cpu_duration_us =
+                        std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - cpu_start).count();
+                }
+                return HJ_OK;
+            }
+        }
         DeviceGuard g(dev);
         for (uint32_t i = 0; i < n_resources; i++) settle_locked(env[i]);
     }

@@ -147,6 +147,10 @@ void chunk_schedule(size_t n, size_t chunk_elems, size_t align_elems, std::vecto
 hj_status kernel_launch_streamed(hj_device* dev, hj_kernel* k, size_t size, hj_buffer* const* buffers, uint32_t n_buffers,
                                  bool* done);
 
+// host_stream.cu: a PrefixSum pass over a source that is still arriving; *done = false when not applicable
+hj_status prefix_sum_arriving(hj_device* dev, hj_type_kind ty, size_t n, bool inclusive, hj_buffer* src, hj_buffer* dst,
+                              bool* done);
+
 // Grow-only scratch helpers (called with the device lock held).
 hj_status ensure_reduce_scratch(hj_device* dev, size_t bytes);
 hj_status ensure_hist_scratch(hj_device* dev, size_t bytes);

@@ -131,9 +131,79 @@ std::vector<std::pair<size_t, size_t>> make_chunks(size_t n, size_t chunk, size_
     return out;
 }
 
+// carry[0] = running total after the chunk `in` -> `out` of `count` elements (on the device stream)
+void launch_carry(hj_device* dev, hj_type_kind ty, size_t es, void* carry, const void* out, const void* in, size_t count,
+                  int inclusive) {
+    switch (es) {
+    case 1: carry_kernel<uint8_t><<<1, 32, 0, dev->stream>>>((uint8_t*)carry, (const uint8_t*)out, (const uint8_t*)in, count, inclusive); break;
+    case 2: carry_kernel<uint16_t><<<1, 32, 0, dev->stream>>>((uint16_t*)carry, (const uint16_t*)out, (const uint16_t*)in, count, inclusive); break;
+    case 4:
+        if (ty == HJ_F32) carry_kernel<float><<<1, 32, 0, dev->stream>>>((float*)carry, (const float*)out, (const float*)in, count, inclusive);
+        else carry_kernel<uint32_t><<<1, 32, 0, dev->stream>>>((uint32_t*)carry, (const uint32_t*)out, (const uint32_t*)in, count, inclusive);
+        break;
+    default:
+        if (ty == HJ_F64) carry_kernel<double><<<1, 32, 0, dev->stream>>>((double*)carry, (const double*)out, (const double*)in, count, inclusive);
+        else carry_kernel<unsigned long long><<<1, 32, 0, dev->stream>>>((unsigned long long*)carry, (const unsigned long long*)out, (const unsigned long long*)in, count, inclusive);
+        break;
+    }
+}
+
 size_t default_chunk(size_t chunk_elems) { return chunk_elems ? chunk_elems : ((size_t)1 << 24); }
 
 }  // namespace
+
+// A PrefixSum pass whose source is still arriving chunk by chunk (hj_buffer_create_from_host_async): every chunk
+// is scanned on the device stream as soon as its upload event fires, with the running total of the chunks in front
+// as its seed, and `dst` inherits the schedule so that hj_buffer_to_host drains it chunk by chunk — the download of
+// chunk c overlaps the upload of chunk c + 2.  Integer types only: a float scan cut at other places rounds
+// differently, and the result must not depend on how the source got to the device.
+hj_status prefix_sum_arriving(hj_device* dev, hj_type_kind ty, size_t n, bool inclusive, hj_buffer* src, hj_buffer* dst,
+                              bool* done) {
+    *done = false;
+    const size_t es = type_size(ty);
+    const bool integer = ty != HJ_F16 && ty != HJ_F32 && ty != HJ_F64 && ty != HJ_BOOL;
+    static const bool off = getenv("HJ_NO_STREAMED_LAUNCH") != nullptr;
+    if (off || !es || !integer || !src || !dst || src == dst || n == 0) return HJ_OK;
+    DeviceGuard g(dev);
+    std::shared_ptr<AsyncProgress> pr = src->progress;
+    if (!pr || pr->first.empty() || src->progress_elem_bytes != es || pr->first.back() + pr->count.back() != n) return HJ_OK;
+    if (src->dev != dev || dst->dev != dev || n * es > src->bytes || n * es > dst->bytes || src->ptr == dst->ptr) return HJ_OK;
+    settle_locked(dst);
+    auto out = std::make_shared<AsyncProgress>();
+    out->first = pr->first;
+    out->count = pr->count;
+    for (size_t c = 0; c < pr->first.size(); c++) {
+        cudaEvent_t ev = nullptr;
+        HJ_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        out->done.push_back(ev);
+    }
+    void* carry = nullptr;
+    HJ_CUDA(cudaMallocAsync(&carry, 16, dev->stream));
+    hj_status st = HJ_OK;
+    for (size_t c = 0; c < pr->first.size() && st == HJ_OK; c++) {
+        const size_t first = pr->first[c], count = pr->count[c];
+        const char* in = (const char*)src->ptr + first * es;
+        char* o = (char*)dst->ptr + first * es;
+        cudaError_t e = cudaStreamWaitEvent(dev->stream, pr->done[c], 0);
+        if (e != cudaSuccess) { cudaGetLastError(); st = fail(HJ_ERR_CUDA, "streamed scan: %s", cudaGetErrorString(e)); break; }
+        st = launch_prefix_sum(dev, ty, count, inclusive, in, o, c ? carry : nullptr);
+        if (st != HJ_OK) break;
+        if (c + 1 < pr->first.size()) {
+            launch_carry(dev, ty, es, carry, o, in, count, inclusive ? 1 : 0);
+            st = check_launch(dev, "carry_kernel");
+            if (st != HJ_OK) break;
+        }
+        e = cudaEventRecord(out->done[c], dev->stream);
+        if (e != cudaSuccess) { cudaGetLastError(); st = fail(HJ_ERR_CUDA, "streamed scan: %s", cudaGetErrorString(e)); }
+    }
+    cudaFreeAsync(carry, dev->stream);
+    // the device stream has waited for every upload event (or the error path below waits for the last one)
+    settle_locked(src);
+    HJ_TRY(st);
+    attach_progress(dst, std::move(out), (uint32_t)es);
+    *done = true;
+    return HJ_OK;
+}
 }  // namespace hj
 
 using namespace hj;
@@ -217,18 +287,7 @@ hj_status hj_prefix_sum_host(hj_device* dev, hj_type_kind ty, size_t n, int32_t 
         if (c >= DEPTH) HJ_CUDA(cudaStreamWaitEvent(dev->stream, p.down_done[d], 0));
         HJ_TRY(launch_prefix_sum(dev, ty, count, inclusive != 0, in[d], out[d], carry));
         if (c + 1 < chunks.size()) {
-            switch (es) {
-            case 1: carry_kernel<uint8_t><<<1, 32, 0, dev->stream>>>((uint8_t*)carry, (const uint8_t*)out[d], (const uint8_t*)in[d], count, inclusive); break;
-            case 2: carry_kernel<uint16_t><<<1, 32, 0, dev->stream>>>((uint16_t*)carry, (const uint16_t*)out[d], (const uint16_t*)in[d], count, inclusive); break;
-            case 4:
-                if (ty == HJ_F32) carry_kernel<float><<<1, 32, 0, dev->stream>>>((float*)carry, (const float*)out[d], (const float*)in[d], count, inclusive);
-                else carry_kernel<uint32_t><<<1, 32, 0, dev->stream>>>((uint32_t*)carry, (const uint32_t*)out[d], (const uint32_t*)in[d], count, inclusive);
-                break;
-            default:
-                if (ty == HJ_F64) carry_kernel<double><<<1, 32, 0, dev->stream>>>((double*)carry, (const double*)out[d], (const double*)in[d], count, inclusive);
-                else carry_kernel<unsigned long long><<<1, 32, 0, dev->stream>>>((unsigned long long*)carry, (const unsigned long long*)out[d], (const unsigned long long*)in[d], count, inclusive);
-                break;
-            }
+            launch_carry(dev, ty, es, carry, out[d], in[d], count, inclusive);
             HJ_TRY(check_launch(dev, "carry_kernel"));
         }
         HJ_CUDA(cudaEventRecord(p.comp_done[d], dev->stream));

@@ -177,9 +177,17 @@ hj_status kernel_launch_streamed(hj_device* dev, hj_kernel* k, size_t size, hj_b
     if (e == cudaSuccess) e = cudaStreamWaitEvent(sk, start, 0);
     cudaEventDestroy(start);
     if (e != cudaSuccess) { cudaGetLastError(); return fail(HJ_ERR_CUDA, "streamed launch: %s", cudaGetErrorString(e)); }
+    // every event this pass needs exists before its first launch: an error below never leaves work in flight
+    // that nothing waits for
     auto out = std::make_shared<AsyncProgress>();
+    auto fence = std::make_shared<AsyncProgress>();
     out->first = ref->first;
     out->count = ref->count;
+    for (size_t c = 0; c <= ref->first.size(); c++) {
+        cudaEvent_t ev = nullptr;
+        HJ_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        (c < ref->first.size() ? out : fence)->done.push_back(ev);
+    }
     const size_t per_block = (size_t)k->threads * k->vec_width * k->unroll;
     std::vector<void*> ptrs(n_buffers);
     for (size_t c = 0; c < ref->first.size(); c++) {
@@ -194,10 +202,7 @@ hj_status kernel_launch_streamed(hj_device* dev, hj_kernel* k, size_t size, hj_b
         for (uint32_t i = 0; i < n_buffers; i++) args.push_back((void*)&ptrs[i]);
         const unsigned grid = (unsigned)((count + per_block - 1) / per_block);
         e = cudaLaunchKernel((const void*)k->vec, dim3(grid), dim3(k->threads), args.data(), 0, sk);
-        cudaEvent_t ev = nullptr;
-        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
-        if (ev) out->done.push_back(ev);
-        if (e == cudaSuccess) e = cudaEventRecord(ev, sk);
+        if (e == cudaSuccess) e = cudaEventRecord(out->done[c], sk);
         if (e != cudaSuccess) {
             cudaGetLastError();
             cudaStreamSynchronize(sk);  // nothing of this pass may outlive the error return
@@ -206,12 +211,11 @@ hj_status kernel_launch_streamed(hj_device* dev, hj_kernel* k, size_t size, hj_b
         dev->launches.fetch_add(1, std::memory_order_relaxed);
     }
     // the buffers this pass wrote arrive chunk by chunk; the ones it read are busy until its last chunk
-    auto fence = std::make_shared<AsyncProgress>();
-    {
-        cudaEvent_t ev = nullptr;
-        HJ_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
-        fence->done.push_back(ev);
-        HJ_CUDA(cudaEventRecord(ev, sk));
+    e = cudaEventRecord(fence->done[0], sk);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        cudaStreamSynchronize(sk);
+        return fail(HJ_ERR_CUDA, "streamed launch: %s", cudaGetErrorString(e));
     }
     for (uint32_t i = 0; i < n_buffers; i++) {
         if (k->slot_flags[i] == 2) attach_progress(buffers[i], out, k->slot_elem_bytes[i]);

@@ -148,6 +148,28 @@ def test_consumers_that_cannot_stream_wait_for_the_upload(device):
     assert np.array_equal(p.to_vec(), np.cumsum(a + 1, dtype=np.uint32))
 
 
+@pytest.mark.parametrize("inclusive", [True, False])
+def test_scan_of_an_arriving_array_is_streamed_and_bit_identical(device, inclusive):
+    rng = np.random.default_rng(7)
+    a = pinned(rng.integers(0, 1 << 32, N, dtype=np.uint32))  # wraps many times
+    ref, n_ref = run(lambda: [tr.array(a, device)], lambda x: x.prefix_sum(inclusive), device)
+    got, n_got = run(lambda: [tr.array_async(a, device)], lambda x: x.prefix_sum(inclusive), device)
+    assert n_got > 2 * n_ref + 8, "the scan did not go chunk by chunk"
+    want = np.cumsum(a, dtype=np.uint32)
+    if not inclusive:
+        want = np.concatenate([[0], want[:-1]]).astype(np.uint32)
+    assert np.array_equal(got[0], want) and np.array_equal(ref[0], got[0])
+
+
+def test_float_scan_of_an_arriving_array_is_not_cut_differently(device):
+    rng = np.random.default_rng(8)
+    a = pinned(rng.random(N, dtype=np.float32))
+    ref, n_ref = run(lambda: [tr.array(a, device)], lambda x: x.prefix_sum(True), device)
+    got, n_got = run(lambda: [tr.array_async(a, device)], lambda x: x.prefix_sum(True), device)
+    assert n_got == n_ref  # waits for the whole upload: same kernel, same rounding
+    assert np.array_equal(ref[0].view(np.uint32), got[0].view(np.uint32))
+
+
 def test_streamed_result_feeds_later_launches_and_inputs_are_reusable(device):
     rng = np.random.default_rng(5)
     a = pinned(rng.integers(0, 1 << 20, N, dtype=np.uint32))

@@ -42,6 +42,27 @@ def bench(fn, reps=5):
     return 8 * n / float(np.median(ts)) / 1e9
 
 
+hu = torch.randint(0, 4, (n,), dtype=torch.int32).pin_memory().numpy().view(np.uint32)
+hs = torch.empty(n, dtype=torch.int32).pin_memory().numpy().view(np.uint32)
+
+
+def traced_scan(make):
+    sv = make(hu, dev).prefix_sum(True)
+    sv.schedule()
+    tr.compile().launch(dev)
+    sv.to_vec(out=hs.view(np.uint8))
+
+
+want = None
+for name, fn in (("scan: tr.array       -> launch -> to_vec", lambda: traced_scan(tr.array)),
+                 ("scan: tr.array_async -> launch -> to_vec", lambda: traced_scan(tr.array_async)),
+                 ("scan: hj_prefix_sum_host", lambda: dev.prefix_sum_host(hj.U32, n, True, hu.ctypes.data, hs.ctypes.data))):
+    hs[:] = 0
+    gbs = bench(fn)
+    if want is None:
+        want = hs.copy()
+    print(f"{name:40s} {gbs:7.1f} GB/s (8 B/elem, n = 2^{int(np.log2(n))})  identical to the blocking result: {bool(np.array_equal(hs, want))}")
+
 want = None
 for name, fn in (("tr.array       -> launch -> to_vec", lambda: traced(tr.array)),
                  ("tr.array_async -> launch -> to_vec", lambda: traced(tr.array_async)),
