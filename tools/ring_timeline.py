@@ -68,4 +68,21 @@ for p in (0.5, 0.01, 0.99):
     tiles_per_cta = np.bincount(cta.astype(np.int64))
     print(f"  tiles per CTA: min {tiles_per_cta.min()} max {tiles_per_cta.max()};  sum of consumer waits per CTA: "
           f"{waits.sum() / len(np.unique(cta)) / 1e3:.1f} us of {s[7].max() / 1e3:.1f} us")
+    # fill and drain: the k-th tile of every CTA from the start, and from the end (times relative to the kernel's
+    # first draw / to the last phase-2-done of the whole kernel; means over CTAs)
+    end = s[7].max()
+    seqs = []
+    for c in np.unique(cta):
+        ids = np.nonzero(cta == c)[0]
+        seqs.append(ids[np.argsort(s[0][ids])])
+    names = ("draw", "ph1 start", "ph1 done", "published", "sweep start", "prefix", "ph2 start", "ph2 done")
+    for label, pick, ref in (("first tiles of a CTA, us after the kernel's first draw", lambda q, k: q[k], 0),
+                             ("last tiles of a CTA, us before the kernel's last phase-2-done", lambda q, k: q[-1 - k], end)):
+        print(f"  -- {label}")
+        for k in range(5):
+            ids = np.array([pick(q, k) for q in seqs if len(q) > k])
+            cells = "  ".join(f"{nm} {abs(s[j][ids] - ref).mean() / 1e3:6.2f}" for j, nm in enumerate(names))
+            print(f"     tile {'+' if ref == 0 else '-'}{k}: {cells}")
+    last_done = np.array([s[7][q].max() for q in seqs])
+    print(f"  CTA finish times before the kernel end: mean {(end - last_done).mean() / 1e3:.2f} us, max {(end - last_done).max() / 1e3:.2f} us")
     del m, idx, tr
