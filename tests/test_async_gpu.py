@@ -203,6 +203,51 @@ def test_dropping_an_arriving_array_and_many_in_flight(device):
     device.sync()
 
 
+def test_two_host_threads_stream_their_own_arrays(device):
+    """Device: Send + Sync.  The side streams are per device: two threads' chunks interleave on them,
+    ordered by their own events only.  Through the buffer-level API (the trace and its schedule are per thread)."""
+    import ctypes
+    import threading
+    irm = importlib.import_module("hephaestus-jit_b200.ir")
+
+    def ir_add(c):  # dst[i] = src[i] + c
+        b = irm.IRBuilder()
+        t = b.scalar(U32)
+        src = b.buffer_ref(t)
+        idx = b.index()
+        v = b.bop(irm.BOP_ADD, t, b.gather(t, src, idx), b.literal(U32, c))
+        dst = b.buffer_ref(t)
+        b.scatter(dst, v, idx)
+        return b
+
+    errors = []
+
+    def worker(seed):
+        try:
+            rng = np.random.default_rng(seed)
+            for it in range(3):
+                a = pinned(rng.integers(0, 1 << 30, N, dtype=np.uint32))
+                out = ctypes.c_void_p()
+                hj.check(hj.lib.hj_buffer_create_from_host_async(device.handle, a.ctypes.data_as(ctypes.c_void_p), a.nbytes, 4,
+                                                                 ctypes.byref(out)))
+                bx = hj.Buffer(out.value, device)
+                by = device.create_buffer(4 * N)
+                device.execute_graph([{"kind": hj.PASS_KERNEL, "resources": [0, 1], "ir": ir_add(seed + it), "size": N}],
+                                     [bx, by], [(N, U32, 4), (N, U32, 4)])
+                got = by.to_host(np.uint32)
+                if not np.array_equal(got, a + np.uint32(seed + it)):
+                    errors.append(f"thread {seed} iteration {it}: wrong result")
+        except BaseException as exc:  # noqa: BLE001
+            errors.append(repr(exc))
+
+    ts = [threading.Thread(target=worker, args=(s,)) for s in (11, 23)]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    assert not errors, errors
+
+
 def test_buffer_level_api_through_execute_graph(device):
     """The same without the trace layer: hj_buffer_create_from_host_async + one Kernel pass + to_host."""
     irm = importlib.import_module("hephaestus-jit_b200.ir")

@@ -83,6 +83,9 @@ for p in (0.5, 0.01, 0.99):
             ids = np.array([pick(q, k) for q in seqs if len(q) > k])
             cells = "  ".join(f"{nm} {abs(s[j][ids] - ref).mean() / 1e3:6.2f}" for j, nm in enumerate(names))
             print(f"     tile {'+' if ref == 0 else '-'}{k}: {cells}")
+            if k == 0:
+                cells = "  ".join(f"{nm} {abs(s[j][ids] - ref).max() / 1e3:6.2f}" for j, nm in enumerate(names))
+                print(f"       (max): {cells}")
     last_done = np.array([s[7][q].max() for q in seqs])
     print(f"  CTA finish times before the kernel end: mean {(end - last_done).mean() / 1e3:.2f} us, max {(end - last_done).max() / 1e3:.2f} us")
     del m, idx, tr
