@@ -48,4 +48,16 @@ seed = dev.create_buffer_from_slice(np.array([5], np.uint32)); bu = dev.create_b
 L.check(L.lib.hj_apply_seed(dev.handle, hj.U32, n, bu.handle, seed.handle)); assert np.array_equal(bu.to_host(np.uint32), u + 5)
 del vu, vx, scan, z, t, yv, tot, cnt, ind, g
 comm.destroy(); dev.sync()
+# asynchronous arrays: chunk-wise upload | kernels | download (map, integer scan, a consumer that has to wait)
+os.environ.setdefault("HJ_ASYNC_CHUNK_ELEMS", "65536")
+na = 1_000_003
+ha = np.random.default_rng(5).integers(0, 1 << 20, na, dtype=np.uint32)
+va = tr.array_async(ha, dev); ya = va.mul(tr.literal(3, hj.U32)); ya.schedule(); tr.compile().launch(dev)
+assert np.array_equal(ya.to_vec(), ha * 3)
+vs = tr.array_async(ha, dev).prefix_sum(True); vs.schedule(); tr.compile().launch(dev)
+assert np.array_equal(vs.to_vec(), np.cumsum(ha, dtype=np.uint32))
+vm = tr.array_async(ha, dev).reduce_max(); vm.schedule(); tr.compile().launch(dev)
+assert int(vm.item()) == int(ha.max())
+del va, ya, vs, vm
+dev.sync()
 print("sanitize r02 workload ok")
