@@ -124,6 +124,7 @@ _SIGS = {
     "hj_buffer_create": (_i32, [_vp, _sz, _pvp]),
     "hj_buffer_create_from_slice": (_i32, [_vp, _vp, _sz, _pvp]),
     "hj_buffer_create_from_host_async": (_i32, [_vp, _vp, _sz, _sz, _pvp]),
+    "hj_async_chunk_schedule": (_i32, [_u64, _u64, _pu64, _pu64, _u32, ctypes.POINTER(_u32)]),
     "hj_buffer_wrap": (_i32, [_vp, _vp, _sz, _pvp]),
     "hj_buffer_retain": (_i32, [_vp]),
     "hj_buffer_release": (_i32, [_vp]),

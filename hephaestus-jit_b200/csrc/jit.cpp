@@ -426,6 +426,19 @@ hj_status hj_kernel_map_host(hj_device* dev, hj_kernel* k, size_t n, void* const
     if (chunk_elems == 0) chunk_elems = (size_t)1 << 24;
     chunk_elems = (chunk_elems + per_block - 1) / per_block * per_block;
     constexpr int DEPTH = 3;
+    // Chunk schedule: the pipeline's fill (first upload) and drain (last download) cannot overlap
+    // with traffic in the other direction, so the first and last chunks are small (1/8, 1/4, 1/2 of
+    // a full chunk on the way in, mirrored on the way out) and only the middle runs at full size.
+    std::vector<std::pair<size_t, size_t>> chunks;  // (first element, count)
+    size_t max_chunk = 0;
+    {
+        std::vector<size_t> first, count;
+        chunk_schedule(n, chunk_elems, per_block, &first, &count);
+        for (size_t c = 0; c < first.size(); c++) {
+            chunks.emplace_back(first[c], count[c]);
+            max_chunk = std::max(max_chunk, count[c]);
+        }
+    }
     // the device lock is only needed for the stream-ordered allocations on the device stream: the chunks
     // run on this call's own three streams, so several host threads may stream at once
     std::unique_ptr<DeviceGuard> g(new DeviceGuard(dev));
@@ -449,7 +462,7 @@ hj_status hj_kernel_map_host(hj_device* dev, hj_kernel* k, size_t n, void* const
     hj_status st = HJ_OK;
     for (size_t i = 0; i < dbuf.size() && st == HJ_OK; i++) {
         void* p = nullptr;
-        cudaError_t e = cudaMallocAsync(&p, chunk_elems * k->slot_elem_bytes[i % n_arrays], dev->stream);
+        cudaError_t e = cudaMallocAsync(&p, max_chunk * k->slot_elem_bytes[i % n_arrays], dev->stream);
         if (e != cudaSuccess) { cudaGetLastError(); st = fail(HJ_ERR_OOM, "chunk buffer allocation failed: %s", cudaGetErrorString(e)); }
         dbuf[i] = (char*)p;
     }
@@ -460,15 +473,6 @@ hj_status hj_kernel_map_host(hj_device* dev, hj_kernel* k, size_t n, void* const
         HJ_CUDA(cudaStreamWaitEvent(s_down, start, 0));
     }
     g.reset();
-    // Chunk schedule: the pipeline's fill (first upload) and drain (last download) cannot overlap
-    // with traffic in the other direction, so the first and last chunks are small (1/8, 1/4, 1/2 of
-    // a full chunk on the way in, mirrored on the way out) and only the middle runs at full size.
-    std::vector<std::pair<size_t, size_t>> chunks;  // (first element, count)
-    {
-        std::vector<size_t> first, count;
-        chunk_schedule(n, chunk_elems, per_block, &first, &count);
-        for (size_t c = 0; c < first.size(); c++) chunks.emplace_back(first[c], count[c]);
-    }
     const size_t n_chunks = chunks.size();
     for (size_t c = 0; c < n_chunks && st == HJ_OK; c++) {
         const int d = (int)(c % DEPTH);

@@ -276,24 +276,40 @@ void chunk_schedule(size_t n, size_t chunk_elems, size_t align_elems, std::vecto
     first->clear();
     count->clear();
     if (align_elems == 0) align_elems = 1;
-    chunk_elems = std::max(align_elems, (chunk_elems + align_elems - 1) / align_elems * align_elems);
-    static const bool ramp = !getenv("HJ_MAP_NO_RAMP");
-    size_t left = n;
-    auto take = [&](size_t c) {
-        c = std::min((c + align_elems - 1) / align_elems * align_elems, left);
+    auto up = [&](size_t v) { return std::max(align_elems, (v + align_elems - 1) / align_elems * align_elems); };
+    const size_t chunk = up(chunk_elems);
+    size_t pos = 0;
+    auto push = [&](size_t c) {
         if (c) {
-            first->push_back(n - left);
+            first->push_back(pos);
             count->push_back(c);
-            left -= c;
+            pos += c;
         }
     };
-    if (ramp && n >= 4 * chunk_elems) {
-        const size_t tail_total = chunk_elems / 2 + chunk_elems / 4 + chunk_elems / 8 + 3 * align_elems;
-        for (size_t div = 8; div >= 2; div /= 2) take(chunk_elems / div);
-        while (left > tail_total) take(std::min(chunk_elems, left - tail_total));
-        for (size_t div = 2; div <= 8; div *= 2) take(chunk_elems / div);
+    // every boundary is a multiple of `align_elems`; what is left of a ragged n joins the last chunk
+    const size_t n_al = n / align_elems * align_elems;
+    static const bool ramp = !getenv("HJ_MAP_NO_RAMP");
+    const size_t r[3] = {up(chunk / 8), up(chunk / 4), up(chunk / 2)};
+    const size_t ramp_total = r[0] + r[1] + r[2];
+    if (ramp && n_al >= 4 * chunk && n_al >= 2 * ramp_total + chunk) {
+        for (int i = 0; i < 3; i++) push(r[i]);
+        for (size_t mid = n_al - 2 * ramp_total; mid;) {
+            const size_t c = std::min(chunk, mid);
+            push(c);
+            mid -= c;
+        }
+        for (int i = 2; i >= 0; i--) push(r[i]);
+    } else {
+        for (size_t left = n_al; left;) {
+            const size_t c = std::min(chunk, left);
+            push(c);
+            left -= c;
+        }
     }
-    while (left) take(chunk_elems);
+    if (n > n_al) {
+        if (count->empty()) push(n - n_al);
+        else count->back() += n - n_al;
+    }
 }
 }  // namespace hj
 extern "C" {
@@ -344,6 +360,22 @@ hj_status hj_buffer_create_from_slice(hj_device* dev, const void* data, size_t b
 // hj_kernel_map_host.  Contract: `src` stays valid and unchanged until the buffer has been consumed by
 // something that blocks (hj_buffer_to_host of a dependent result, hj_device_sync); pinned memory
 // (hj_host_alloc) is needed for the copy to be asynchronous at all.
+static size_t default_async_chunk() {
+    static const size_t chunk = getenv("HJ_ASYNC_CHUNK_ELEMS") ? (size_t)atoll(getenv("HJ_ASYNC_CHUNK_ELEMS")) : ((size_t)1 << 24);
+    return chunk ? chunk : ((size_t)1 << 24);
+}
+hj_status hj_async_chunk_schedule(uint64_t n, uint64_t chunk_elems, uint64_t* first, uint64_t* count, uint32_t capacity,
+                                  uint32_t* n_chunks) {
+    HJ_REQUIRE(n_chunks && ((first && count) || capacity == 0), "hj_async_chunk_schedule: null argument");
+    std::vector<size_t> f, c;
+    chunk_schedule((size_t)n, chunk_elems ? (size_t)chunk_elems : default_async_chunk(), 4096, &f, &c);
+    for (size_t i = 0; i < f.size() && i < capacity; i++) {
+        first[i] = f[i];
+        count[i] = c[i];
+    }
+    *n_chunks = (uint32_t)f.size();
+    return HJ_OK;
+}
 hj_status hj_buffer_create_from_host_async(hj_device* dev, const void* src, size_t bytes, size_t elem_bytes,
                                            hj_buffer** out) {
     HJ_REQUIRE(dev && out && (src || bytes == 0), "null argument");
@@ -354,8 +386,7 @@ hj_status hj_buffer_create_from_host_async(hj_device* dev, const void* src, size
     hj_status st = ensure_side_streams(dev);
     auto pr = std::make_shared<AsyncProgress>();
     if (st == HJ_OK) {
-        static const size_t chunk = getenv("HJ_ASYNC_CHUNK_ELEMS") ? (size_t)atoll(getenv("HJ_ASYNC_CHUNK_ELEMS")) : ((size_t)1 << 24);
-        chunk_schedule(bytes / elem_bytes, chunk, 4096, &pr->first, &pr->count);
+        chunk_schedule(bytes / elem_bytes, default_async_chunk(), 4096, &pr->first, &pr->count);
         cudaEvent_t alloc_done = nullptr;  // the allocation is ordered on the device stream
         cudaError_t e = cudaEventCreateWithFlags(&alloc_done, cudaEventDisableTiming);
         if (e == cudaSuccess) e = cudaEventRecord(alloc_done, dev->stream);

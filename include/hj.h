@@ -107,6 +107,13 @@ hj_status hj_buffer_create_from_slice(hj_device* dev, const void* data, size_t b
  * hj_device_sync) has returned.  `elem_bytes`: element size of the array (chunks end on element boundaries). */
 hj_status hj_buffer_create_from_host_async(hj_device* dev, const void* src, size_t bytes, size_t elem_bytes,
                                            hj_buffer** out);
+/* The chunk schedule of the asynchronous upload for an array of `n` elements (host logic only, no device needed):
+ * writes up to `capacity` (first, count) pairs and returns the number of chunks in *n_chunks (which may exceed
+ * `capacity`).  Chunks are contiguous, cover [0, n), every boundary but the last is a multiple of 4096 elements;
+ * a long array ramps 1/8, 1/4, 1/2 of a full chunk up at the front and down at the back (the fill and the drain of
+ * the pipeline overlap nothing).  `chunk_elems` = 0: the default (2^24, or HJ_ASYNC_CHUNK_ELEMS). */
+hj_status hj_async_chunk_schedule(uint64_t n, uint64_t chunk_elems, uint64_t* first, uint64_t* count, uint32_t capacity,
+                                  uint32_t* n_chunks);
 /* Non-owning view over device memory someone else allocated (e.g. a torch tensor). */
 hj_status hj_buffer_wrap(hj_device* dev, void* device_ptr, size_t bytes, hj_buffer** out);
 hj_status hj_buffer_retain(hj_buffer* buf);
