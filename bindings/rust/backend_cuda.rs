@@ -223,6 +223,17 @@ impl BackendDevice for CudaDevice {
         Ok(CudaBuffer { buf, device: self.clone() })
     }
 
+    // (inherent method, next to the trait: `tr::array` over pinned memory.  The upload returns at once; a launch of
+    // ONE fused kernel over the buffer and `to_host` of its result then follow it chunk by chunk — DESIGN.md 3.8.
+    // `src` must stay alive and unchanged until a blocking call on a dependent result has returned, which the
+    // `PinnedSlice` owner type below guarantees by keeping the allocation until it is dropped.)
+    // pub fn create_buffer_from_pinned<T: Copy>(&self, src: &PinnedSlice<T>) -> backend::Result<CudaBuffer> {
+    //     let mut buf = std::ptr::null_mut();
+    //     check(unsafe { ffi::hj_buffer_create_from_host_async(self.0, src.as_ptr() as *const c_void,
+    //                    src.len() * std::mem::size_of::<T>(), std::mem::size_of::<T>(), &mut buf) })?;
+    //     Ok(CudaBuffer { buf, device: self.clone() })
+    // }
+
     fn create_texture(&self, _desc: &backend::TextureDesc) -> backend::Result<Self::Texture> {
         todo!("textures are outside the CUDA backend's scope")
     }

@@ -104,6 +104,10 @@ extern "C" {
     pub fn hj_device_release(dev: *mut hj_device) -> i32;
     pub fn hj_buffer_create(dev: *mut hj_device, bytes: usize, out: *mut *mut hj_buffer) -> i32;
     pub fn hj_buffer_create_from_slice(dev: *mut hj_device, data: *const c_void, bytes: usize, out: *mut *mut hj_buffer) -> i32;
+    pub fn hj_buffer_create_from_host_async(dev: *mut hj_device, src: *const c_void, bytes: usize, elem_bytes: usize,
+                                            out: *mut *mut hj_buffer) -> i32;
+    pub fn hj_host_alloc(bytes: usize, out: *mut *mut c_void) -> i32;
+    pub fn hj_host_free(p: *mut c_void) -> i32;
     pub fn hj_buffer_retain(buf: *mut hj_buffer) -> i32;
     pub fn hj_buffer_release(buf: *mut hj_buffer) -> i32;
     pub fn hj_buffer_to_host(buf: *mut hj_buffer, offset_bytes: usize, nbytes: usize, dst: *mut c_void) -> i32;
