@@ -203,6 +203,70 @@ def test_dropping_an_arriving_array_and_many_in_flight(device):
     device.sync()
 
 
+@pytest.mark.parametrize("seed", range(24))
+def test_random_programs_do_not_depend_on_how_the_inputs_arrive(device, seed):
+    """A random traced program — elementwise chains over up to three inputs of mixed width, comparisons and
+    selects, the global Index, optionally ended by a scan, a reduction or a gather through a computed index,
+    one to three scheduled results — run with blocking uploads and with any subset of the inputs arriving
+    asynchronously: every result bit-identical.  Streamed or not is the library's choice; the values are not."""
+    import random
+    rnd = random.Random(9000 + seed)
+    rng = np.random.default_rng(9000 + seed)
+    n = rnd.choice([N, 300_001, 65_536 * 3, 70_000])
+    host = [pinned(rng.integers(0, 1 << 16, n, dtype=np.uint32)), pinned(rng.random(n, dtype=np.float32)),
+            pinned((rng.random(n) < 0.4).astype(np.uint8))]
+    arriving = [rnd.random() < 0.7 for _ in host]
+    if not any(arriving):
+        arriving[rnd.randrange(3)] = True
+    script = [(rnd.randrange(8), rnd.randrange(100), rnd.randrange(100), rnd.randrange(1, 9)) for _ in range(rnd.randrange(2, 9))]
+    ending = rnd.randrange(5)
+    n_out = rnd.randrange(1, 4)
+
+    def program(asynchronous):
+        make = lambda a, late: (tr.array_async if (asynchronous and late) else tr.array)(a, device)
+        vu, vf, vm = (make(a, late) for a, late in zip(host, arriving))
+        ints, floats = [vu, tr.sized_index(n)], [vf]
+        keep = vm.neq(tr.literal(0, U8))
+        for op, i, j, c in script:
+            a, b = ints[i % len(ints)], ints[j % len(ints)]
+            x, y = floats[i % len(floats)], floats[j % len(floats)]
+            if op == 0:
+                ints.append(a.add(b))
+            elif op == 1:
+                ints.append(a.mul(tr.literal(c, U32)).xor(b))
+            elif op == 2:
+                ints.append(a.select(keep, b))
+            elif op == 3:
+                ints.append(a.min(b).or_(tr.literal(c, U32)))
+            elif op == 4:
+                floats.append(x.fma(tr.literal(1.25, F32), y))
+            elif op == 5:
+                floats.append(x.sin().select(x.gt(y), y.exp2()))
+            elif op == 6:
+                ints.append(x.mul(tr.literal(1000.0, F32)).cast(U32).add(a))
+            else:
+                floats.append(a.and_(tr.literal(1023, U32)).cast(F32).add(x))
+        outs = [ints[-1], floats[-1], ints[len(ints) // 2]][:n_out]
+        if ending == 0:
+            outs.append(ints[-1].prefix_sum(True))
+        elif ending == 1:
+            outs.append(ints[-1].reduce_sum())
+        elif ending == 2:
+            outs.append(ints[-1].gather(tr.literal(n - 1, U32).sub(tr.sized_index(n))))
+        elif ending == 3:
+            outs.append(vu.prefix_sum(False))  # a scan straight on an (arriving) input
+        for o in outs:
+            o.schedule()
+        tr.compile().launch(device)
+        return [o.to_vec() for o in outs]
+
+    want = program(False)
+    got = program(True)
+    assert len(want) == len(got)
+    for w, g in zip(want, got):
+        assert w.dtype == g.dtype and np.array_equal(w.view(np.uint8), g.view(np.uint8))
+
+
 def test_two_host_threads_stream_their_own_arrays(device):
     """Device: Send + Sync.  The side streams are per device: two threads' chunks interleave on them,
     ordered by their own events only.  Through the buffer-level API (the trace and its schedule are per thread)."""
