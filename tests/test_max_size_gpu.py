@@ -19,8 +19,9 @@ NBIG = (1 << 31) + 12345
 @pytest.fixture(scope="module")
 def dev():
     torch.cuda.set_device(0)
-    if torch.cuda.get_device_properties(0).total_memory < 60 * (1 << 30):
-        pytest.skip("needs 40 GiB of device memory")
+    free, _total = torch.cuda.mem_get_info()
+    if free < 64 * (1 << 30):
+        pytest.skip("needs 64 GiB of free device memory")
     d = hj.Device.cuda(0)
     s = torch.cuda.Stream()
     torch.cuda.set_stream(s)
@@ -147,22 +148,21 @@ def test_histogram_of_every_key_at_the_largest_extent(dev):
     assert bool((u32(hist) == want).all())
 
 
-def test_gather_reverses_the_largest_extent(dev):
-    n = NMAX
-    src = torch.empty(n, device="cuda", dtype=torch.int32)
+def test_gather_over_the_largest_extent(dev):
+    """dst[i] = table[idx[i]] for 2^32 - 1 indices into a 2^20-entry table: idx[i] = (n - 1 - i) mod 2^20."""
+    n, tn = NMAX, 1 << 20
+    table = torch.arange(tn, device="cuda", dtype=torch.int32) * 7 + 3
     idx = torch.empty(n, device="cuda", dtype=torch.int32)
-    for lo in range(0, n, 1 << 28):  # src[i] = 7 i (mod 2^32), idx[i] = n - 1 - i
+    for lo in range(0, n, 1 << 28):
         hi = min(n, lo + (1 << 28))
-        a = torch.arange(lo, hi, device="cuda", dtype=torch.int64)
-        src[lo:hi] = as_i32((7 * a) & 0xFFFFFFFF)
-        idx[lo:hi] = as_i32(n - 1 - a)
-    dst = torch.empty_like(src)
-    dev.gather(4, n, wrap(dev, src), wrap(dev, idx), wrap(dev, dst))
+        idx[lo:hi] = ((n - 1 - torch.arange(lo, hi, device="cuda", dtype=torch.int64)) & (tn - 1)).to(torch.int32)
+    dst = torch.empty(n, device="cuda", dtype=torch.int32)
+    dev.gather(4, n, wrap(dev, table), wrap(dev, idx), wrap(dev, dst))
     torch.cuda.synchronize()
     for lo in range(0, n, 1 << 28):
         hi = min(n, lo + (1 << 28))
-        a = torch.arange(lo, hi, device="cuda", dtype=torch.int64)
-        assert bool((u32(dst[lo:hi]) == (7 * (n - 1 - a)) & 0xFFFFFFFF).all()), f"mismatch in [{lo}, {hi})"
+        want = ((n - 1 - torch.arange(lo, hi, device="cuda", dtype=torch.int64)) & (tn - 1)) * 7 + 3
+        assert bool((dst[lo:hi].to(torch.int64) == want).all()), f"mismatch in [{lo}, {hi})"
 
 
 def test_2p32_elements_are_rejected_not_truncated(dev):
