@@ -1,6 +1,6 @@
 """Sharded execution on the GPU, parity against the oracle on the WHOLE array.
 
-Two layers are covered at world 1, 2 and 3:
+Two layers are covered at world 1, 2, 3 and 4 (the device ops also at 8):
   * the sharded device ops of include/hj.h with their exchange FUSED into the kernel (reduce, scan
     with a deferred seed, compress with the counts exchange, the packed-16 histogram fold+exchange);
   * whole traced programs over arrays partitioned with ``tr.array_sharded`` — Graph.launch ->
@@ -9,7 +9,7 @@ Two layers are covered at world 1, 2 and 3:
 The communicator is bootstrapped WITHOUT NCCL (hj_comm_create_local / hj_comm_connect: the CUDA-IPC
 handles of the peer mailboxes travel over a torch.distributed gloo group), so the ranks of a world
 may share one GPU: on the one-GPU box the driver tests on, the kernels of the two or three
-processes are time-sliced and the exchange code is exactly the multi-GPU one.  With enough GPUs
+processes (up to eight) are time-sliced and the exchange code is exactly the multi-GPU one.  With enough GPUs
 every rank takes its own (tests/test_sharded_gpu.py covers the NCCL bootstrap there).
 """
 import importlib
@@ -445,12 +445,12 @@ def test_sharded_pass_list_replays_as_one_cuda_graph(world):
     _run(world, "_cached_sharded_graph", (1 << 20) + 4099)
 
 
-@pytest.mark.parametrize("world", [1, 2, 3])
+@pytest.mark.parametrize("world", [1, 2, 3, 4, 8])
 def test_sharded_device_ops_fused_exchange(world):
     _run(world, "_device_ops", (1 << 21) + 77)
 
 
-@pytest.mark.parametrize("world", [1, 2, 3])
+@pytest.mark.parametrize("world", [1, 2, 3, 4])
 def test_traced_program_over_sharded_arrays(world):
     _run(world, "_traced_program", (1 << 21) + 13)
 
