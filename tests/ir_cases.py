@@ -497,7 +497,9 @@ def scatter_reduce_ops(kind=I.U32, rop=I.R_SUM, n=50021, n_bins=257, seed=4, con
         bufs.append(_rand(rng, I.BOOL, n))
     b.scatter_reduce(rop, dst, v, k, c)
     is_f = kind in (I.F32, I.F64)
-    return Case(f"scatter_reduce_{kind}_{rop}", b, n, bufs, exact=not (is_f and rop == I.R_SUM), rtol=1e-4)
+    # float sums: the atomics add in an arbitrary order, ~200 values of magnitude <= 4 and mixed sign per bin — a
+    # bin that sums to almost zero still carries an absolute error of ~200 * 4 * 2^-24, hence the absolute term
+    return Case(f"scatter_reduce_{kind}_{rop}", b, n, bufs, exact=not (is_f and rop == I.R_SUM), rtol=1e-4, atol=1e-3)
 
 
 def dyn_size(n=1000, live=137):
