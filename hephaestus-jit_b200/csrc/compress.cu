@@ -11,9 +11,10 @@
 //     ring of ring.cuh with 56 KiB tiles x 3 TMA stages, 28 consumer warps and EARLY release.
 //     Phase 1 turns every 16-byte vector into a 16-bit lane mask (IDP.4A: for 0/1 bytes the byte dot
 //     product with (1,2,4,8) IS the mask nibble), counts it and parks the mask in a side plane, so
-//     the data stage returns to the producer at once; phase 2 ranks rows in pairs with one packed
-//     warp scan and picks a store path per density (sparse: direct; medium: u16 stage + 128-byte
-//     warp stores; dense: word-broadcast, contiguous runs).  DESIGN.md 3.3 has the measurements.
+//     the data stage returns to the producer at once; phase 2 picks an emission path per slice by its
+//     density: sparse slices store straight from the lanes' bit walks, everything else is staged as u16
+//     offsets in output order (lane-major ownership below p ~ 0.5, "quads" above) and leaves as
+//     aligned 128-bit stores (CompressOp::SliceOut).  DESIGN.md 3.3 has the measurements.
 //     On a sharded launch `finish` also exchanges the per-rank counts over peer memory (comm.cu).
 //   * compress_kernel — the fallback for small or misaligned inputs: two sweeps per 32 KiB tile
 //     with decoupled look-back (sweep 1 counts, sweep 2 re-reads the L2-resident rows and emits).
@@ -21,7 +22,10 @@
 // in the kernel (D4), `index_base` is added to every index (the shard's global offset), indices
 // leave as coalesced warp stores instead of one 32-byte sector per 4-byte index
 // (compress_large.glsl:224-228).  Algorithmic bytes: n (mask) + 4 * count (indices).
+#include <array>
+#include <cstdio>
 #include <cstdlib>
+#include <cstring>
 
 #include "hj_internal.h"
 #include "lookback.cuh"
@@ -159,6 +163,7 @@ compress_kernel(const uint8_t* __restrict__ mask, size_t n, const uint32_t* __re
 // coalesced store of base + offset.  The kernel is instruction-issue bound, not HBM bound, at
 // low selectivity, hence the 28 warps and the lean inner loops.
 constexpr int CR_WARPS = 28;
+constexpr int CR_STAGE_BYTES = 1040;  // per consumer warp: 512 u16 offsets of one row + 3 carried over, 16-byte multiple
 
 // 16 mask bytes -> 16-bit lane mask (bit i = byte i is non-zero).
 // Fast path: `bool` buffers only ever hold 0 or 1 (codegen stores bool as u8 0/1,
@@ -201,12 +206,15 @@ struct CompressOp {
         uint32_t* counts_out;
         PeerView pv;
         uint32_t exchange;
+        // how a slice is emitted, by its number of selected elements: below staged_lo the sparse path (direct
+        // stores), [staged_lo, staged_mid) staged with lane-major ownership, from staged_mid on with quads
+        uint32_t staged_lo, staged_mid;
     };
     // aux layout (shared memory behind the ring): TSLOTS mask planes of TILE/8 bytes (one u16 per
     // 16 mask bytes), then one 1 KiB index stage per consumer warp.  Phase 1 leaves only the masks
     // behind, so the data stage goes straight back to the producer (EARLY release).
     static __device__ __forceinline__ uint16_t* stage_of(char* aux, int cw) {
-        return reinterpret_cast<uint16_t*>(aux + TSLOTS * MASK_PLANE + cw * 1024);
+        return reinterpret_cast<uint16_t*>(aux + TSLOTS * MASK_PLANE + cw * CR_STAGE_BYTES);
     }
     static constexpr int MASK_PLANE = TILE / 8;
     static __device__ __forceinline__ uint16_t* masks_of(char* aux, int slot, int cw) {
@@ -224,64 +232,119 @@ struct CompressOp {
         }
         return __reduce_add_sync(0xffffffffu, cnt);
     }
-    // One 512-element row: lane `lane` owns bits `b` (elements lane*16 ..), its first selected
-    // element has rank `k` in the row.  Selected positions are staged as u16 row offsets, then
-    // written as base + offset with 128-bit stores once the output address is 16-byte aligned.
-    // One 512-element row whose 32 lane masks sit in shared memory as 16 consecutive 32-bit words:
-    // word j holds elements 32j .. 32j+31 in order (lane L owns elements 16L .. 16L+15, so two
-    // adjacent u16 lane masks ARE one such word).
-    //   sparse row (<= 64 selected): every lane walks its own bits and stores straight to HBM —
-    //     most lanes hold 0 or 1 selected elements, so the k-th stores are nearly contiguous;
-    //   medium row (< 416 selected): compacted through a per-warp u16 stage, see below;
-    //   dense row: 16 steps, one word each.  All lanes read the same word (a broadcast, no bank
-    //     conflicts), lane l owns element 32j + l, its rank inside the word is popc(word & lt_mask)
-    //     and the word's offset in the row comes from one 16-lane scan of the word popcounts.  The
-    //     selected lanes of a step store one CONTIGUOUS run of indices: no staging buffer, no
-    //     divergence, no copy-out pass.  Its cost does not depend on the density, so it only wins
-    //     when most lanes store (measured at 2^28: p = 0.99 297 -> 250 us, but p = 0.5 164 -> 224 us).
-    static __device__ __forceinline__ void emit_row(const uint32_t* words, uint16_t* stage, uint32_t b, uint32_t k,
-                                                    uint32_t row_total, uint32_t base, uint32_t* out, int lane) {
-        if (row_total <= 64) {
-            const uint32_t mine = base + lane * 16;
-            while (b) {
-                const int j = __ffs(b) - 1;
-                b &= b - 1;
-                out[k++] = mine + j;
-            }
-            return;
+    // Staged slices (round 2, variant E of profiles/r02_compress_medium_variants.md).  The selected positions of a
+    // slice are staged as u16 offsets relative to the SLICE, in output order, in a per-warp stage that is shifted
+    // by the position of the slice's first output inside its 16-byte line: four consecutive entries always are
+    // one aligned uint4 of the output.  After every row the complete vectors leave as LDS.64 + STG.128 and the up
+    // to three entries behind them move to the front of the stage as the head of the next row; only the first
+    // vector of a slice (entries in front of the slice's first output) and its last entries go out as scalar
+    // stores.  (Round 1 copied every row out with LDS.U16 + STG.32 and a 64-bit address per index: 94 of the 233
+    // warp instructions of a row.)
+    struct SliceOut {
+        uint16_t* stage;
+        uint4* line;     // output line of stage vector 0
+        uint32_t base;   // index of the slice's first element
+        uint32_t hg;     // stage entries [0, hg) are not ours (only before the first flush)
+        uint32_t pos;    // stage entries [hg, pos) are pending
+        int lane;
+        __device__ __forceinline__ SliceOut(uint16_t* st, uint32_t b, uint32_t* out, int l) : stage(st), base(b), lane(l) {
+            hg = (uint32_t)((uintptr_t)out >> 2) & 3u;
+            line = reinterpret_cast<uint4*>(out - hg);
+            pos = hg;
         }
-        if (row_total < 416) {
-            // medium density: the word path below would issue 16 half-empty stores per row.
-            // Compact the row through a u16 stage instead (16 predicated steps, no divergence,
-            // no bit scans), then copy out with full 128-byte warp stores.
-            const uint32_t mine = lane * 16;
-            uint16_t* p = stage + k;
-#pragma unroll
-            for (int j = 0; j < 16; j++) {
-                if (b & (1u << j)) *p++ = (uint16_t)(mine + j);
+        // entries [pos, S) have just been staged by the whole warp
+        __device__ __forceinline__ void flush(uint32_t S) {
+            const uint32_t nv = S >> 2;  // vectors [0, nv) are complete
+            __syncwarp();
+            if (nv) {
+                uint32_t v = lane;
+                if (hg) {
+                    if ((uint32_t)lane >= hg && lane < 4) reinterpret_cast<uint32_t*>(line)[lane] = base + stage[lane];
+                    hg = 0;
+                    if (lane == 0) v = 32;
+                }
+#pragma unroll 1
+                for (; v < nv; v += 32) {
+                    const uint2 w = *reinterpret_cast<const uint2*>(stage + 4 * v);
+                    line[v] = make_uint4(base + (w.x & 0xffffu), base + (w.x >> 16), base + (w.y & 0xffffu), base + (w.y >> 16));
+                }
+                const uint32_t rem = S & 3u;
+                const uint16_t x = (uint32_t)lane < rem ? stage[4 * nv + lane] : (uint16_t)0;
+                __syncwarp();
+                if ((uint32_t)lane < rem) stage[lane] = x;
+                line += nv;
+                pos = rem;
+            } else {
+                pos = S;
             }
             __syncwarp();
-            for (uint32_t q = lane; q < row_total; q += 32) out[q] = base + stage[q];
+        }
+        __device__ __forceinline__ void finish() {  // fewer than four entries are left (or no vector was ever complete)
+            if ((uint32_t)lane >= hg && (uint32_t)lane < pos) reinterpret_cast<uint32_t*>(line)[lane] = base + stage[lane];
             __syncwarp();
-            return;
         }
-        const uint32_t wl = lane < 16 ? words[lane] : 0u;
-        const uint32_t pc = __popc(wl);
-        uint32_t inc = pc;
+    };
+    // "Quad" ownership, for the denser slices: a row is four groups of 128 elements and lane j owns elements
+    // 4j .. 4j+3 of EVERY group, so the staging stores of a step ascend by at most 4 entries per lane — 1.2
+    // wavefronts per store where lane-major ownership (16 consecutive elements per lane) has 2.9 at p = 0.5.  The
+    // four group ranks come from ONE warp scan of the nibble popcounts packed into bytes (inclusive sums <= 128).
+    static __device__ __forceinline__ void emit_slice_quads(const uint32_t* words, uint16_t* stage, uint32_t base,
+                                                            uint32_t* out, int lane) {
+        const uint32_t sh = (lane & 7) * 4, wi = lane >> 3;
+        SliceOut so(stage, base, out, lane);
 #pragma unroll
-        for (int d = 1; d < 16; d <<= 1) {
-            const uint32_t o = __shfl_up_sync(0xffffffffu, inc, d);
-            if (lane >= d) inc += o;
-        }
-        const uint32_t ex = inc - pc;  // lanes 0..15: selected elements before word `lane`
-        const uint32_t lt = (1u << lane) - 1u, me = 1u << lane;
-        const uint32_t v0 = base + lane;
+        for (int r = 0; r < ROWS; r++) {
+            uint32_t q[4];
 #pragma unroll
-        for (int j = 0; j < 16; j++) {
-            const uint32_t w = words[j];
-            const uint32_t off = __shfl_sync(0xffffffffu, ex, j);
-            if (w & me) out[off + __popc(w & lt)] = v0 + 32 * j;
+            for (int g = 0; g < 4; g++) q[g] = (words[r * 16 + 4 * g + wi] >> sh) & 0xFu;
+            uint32_t c = q[0] | (q[1] << 8) | (q[2] << 16) | (q[3] << 24);
+            c = c - ((c >> 1) & 0x05050505u);
+            c = (c & 0x03030303u) + ((c >> 2) & 0x03030303u);  // byte g = popc(q[g])
+            const uint32_t inc = warp_inclusive_sum(c);
+            const uint32_t tot = __shfl_sync(0xffffffffu, inc, 31);
+            const uint32_t ex = inc - c;
+            uint32_t gb = so.pos;
+#pragma unroll
+            for (int g = 0; g < 4; g++) {
+                uint16_t* p = stage + gb + ((ex >> (8 * g)) & 0xffu);
+                const uint32_t val = r * 512 + g * 128 + lane * 4;
+#pragma unroll
+                for (int k = 0; k < 4; k++)
+                    if (q[g] & (1u << k)) *p++ = (uint16_t)(val + k);
+                gb += (tot >> (8 * g)) & 0xffu;
+            }
+            so.flush(gb);
         }
+        so.finish();
+    }
+    // Lane-major ownership (lane L owns elements 16L .. 16L+15 of a row), for the sparser slices: no nibble
+    // extraction, one packed scan per pair of rows; the bank conflicts of its staging stores grow with the
+    // density, which is why the quads take over above ~0.4.
+    static __device__ __forceinline__ void emit_slice_lanes(const uint16_t* m, uint16_t* stage, uint32_t base, uint32_t* out,
+                                                            int lane) {
+        SliceOut so(stage, base, out, lane);
+#pragma unroll
+        for (int r = 0; r < ROWS; r += 2) {
+            const uint32_t b0 = m[r * 32 + lane], b1 = m[(r + 1) * 32 + lane];
+            const uint32_t c = __popc(b0) | (__popc(b1) << 16);
+            const uint32_t inc = warp_inclusive_sum(c);
+            const uint32_t tot = __shfl_sync(0xffffffffu, inc, 31);
+            const uint32_t ex = inc - c;
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                const uint32_t b = h ? b1 : b0;
+                const uint32_t t = h ? tot >> 16 : tot & 0xffffu;
+                if (t) {
+                    uint16_t* p = stage + so.pos + (h ? ex >> 16 : ex & 0xffffu);
+                    const uint32_t val = (r + h) * 512 + lane * 16;
+#pragma unroll
+                    for (int j = 0; j < 16; j++)
+                        if (b & (1u << j)) *p++ = (uint16_t)(val + j);
+                    so.flush(so.pos + t);
+                }
+            }
+        }
+        so.finish();
     }
     static __device__ __forceinline__ void emit(const char*, char* aux, int slot, size_t byte_off, uint32_t valid, P carry,
                                                 P slice_total, int lane, int cw, const Args& a) {
@@ -297,52 +360,42 @@ struct CompressOp {
             const uint32_t done = head + 4 * n_vec;
             if ((uint32_t)lane < nz - done) z[done + lane] = 0;
         }
+        if (slice_total == 0) return;
         const uint16_t* m = masks_of(aux, slot, cw);
-        if (slice_total <= 64u * ROWS) {
-            // Sparse slice (p <~ 0.12; the total is the one phase 1 counted).  The mask plane of
-            // the slice IS its bitmap in element order (ROWS * 16 words), so a lane may just as
-            // well own WPL consecutive words: ONE warp scan ranks the whole slice and every lane
-            // walks its own bits straight to HBM — no per-row scans, no staging.  At p = 0.01 this
-            // is 31 M instead of 49 M warp instructions for 2^28 elements.
-            if (slice_total == 0) return;
-            constexpr int WPL = ROWS / 2;
-            uint32_t w[WPL];
-            uint32_t c = 0;
-#pragma unroll
-            for (int i = 0; i < WPL; i++) {
-                w[i] = reinterpret_cast<const uint32_t*>(m)[lane * WPL + i];
-                c += __popc(w[i]);
-            }
-            uint32_t* out = a.index_out + carry + (warp_inclusive_sum(c) - c);
-            const uint32_t e = a.index_base + (uint32_t)byte_off + lane * (32 * WPL);
-#pragma unroll
-            for (int i = 0; i < WPL; i++) {
-                uint32_t b = w[i];
-                while (b) {
-                    const int j = __ffs(b) - 1;
-                    b &= b - 1;
-                    *out++ = e + 32 * i + j;
-                }
-            }
+        if (slice_total >= a.staged_lo) {
+            // measured over p = 0.01 .. 0.99 (profiles/r02_compress_medium_variants.md): lane-major staging wins
+            // below p ~ 0.5, the quads above — all the way to p = 0.99, where they beat the word-broadcast
+            // path of round 1 (direct STG.32 runs, no stage) by 9 %
+            if (slice_total >= a.staged_mid)
+                emit_slice_quads(reinterpret_cast<const uint32_t*>(m), stage_of(aux, cw), a.index_base + (uint32_t)byte_off,
+                                 a.index_out + carry, lane);
+            else
+                emit_slice_lanes(m, stage_of(aux, cw), a.index_base + (uint32_t)byte_off, a.index_out + carry, lane);
             return;
         }
-        uint32_t bits[ROWS];
+        // Sparse slice (p <~ 0.09; the total is the one phase 1 counted).  The mask plane of the slice IS its
+        // bitmap in element order (ROWS * 16 words), so a lane may just as well own WPL consecutive words: ONE
+        // warp scan ranks the whole slice and every lane walks its own bits straight to HBM — no per-row scans,
+        // no staging.  At p = 0.01 this is 31 M instead of 49 M warp instructions for 2^28 elements; from p ~ 0.09
+        // on the scattered 4-byte stores (every lane its own run) cost more than staging does.
+        constexpr int WPL = ROWS / 2;
+        uint32_t w[WPL];
+        uint32_t c = 0;
 #pragma unroll
-        for (int r = 0; r < ROWS; r++) bits[r] = m[r * 32 + lane];
-        const uint32_t* words = reinterpret_cast<const uint32_t*>(m);  // 16 words per row
-        uint16_t* stage = stage_of(aux, cw);
-        const uint32_t base = a.index_base + (uint32_t)byte_off;
+        for (int i = 0; i < WPL; i++) {
+            w[i] = reinterpret_cast<const uint32_t*>(m)[lane * WPL + i];
+            c += __popc(w[i]);
+        }
+        uint32_t* out = a.index_out + carry + (warp_inclusive_sum(c) - c);
+        const uint32_t e = a.index_base + (uint32_t)byte_off + lane * (32 * WPL);
 #pragma unroll
-        for (int r = 0; r < ROWS; r += 2) {
-            // one scan per pair of rows: counts packed as (odd row << 16) | even row, each <= 512
-            const uint32_t c = __popc(bits[r]) | (__popc(bits[r + 1]) << 16);
-            const uint32_t inc = warp_inclusive_sum(c);
-            const uint32_t tot = __shfl_sync(0xffffffffu, inc, 31);
-            const uint32_t ex = inc - c;
-            const uint32_t t0 = tot & 0xffffu, t1 = tot >> 16;
-            if (t0) emit_row(words + r * 16, stage, bits[r], ex & 0xffffu, t0, base + r * 512, a.index_out + carry, lane);
-            if (t1) emit_row(words + (r + 1) * 16, stage, bits[r + 1], ex >> 16, t1, base + (r + 1) * 512, a.index_out + carry + t0, lane);
-            carry += t0 + t1;
+        for (int i = 0; i < WPL; i++) {
+            uint32_t b = w[i];
+            while (b) {
+                const int j = __ffs(b) - 1;
+                b &= b - 1;
+                *out++ = e + 32 * i + j;
+            }
         }
     }
     // compress_large.glsl:214-216: the last partition publishes the count
@@ -363,7 +416,7 @@ __global__ void __launch_bounds__((CR_WARPS + 3) * 32, 1)
 compress_ring_kernel(const uint8_t* __restrict__ mask, size_t n, const uint32_t* __restrict__ size_buf,
                      uint32_t* __restrict__ out_count, uint32_t* __restrict__ index_out, uint32_t index_base,
                      LookbackView lb, uint32_t G, unsigned long long* trace, uint32_t* __restrict__ counts_out,
-                     PeerView pv, uint32_t exchange) {
+                     PeerView pv, uint32_t exchange, uint32_t staged_lo, uint32_t staged_mid) {
     extern __shared__ __align__(128) char smem[];
     size_t n_eff = n;
     if (size_buf) {  // DynSize: device-resident element count (graph.rs:503-508)
@@ -377,7 +430,7 @@ compress_ring_kernel(const uint8_t* __restrict__ mask, size_t n, const uint32_t*
         out_count[0] = 0;
     }
     using Op = CompressOp<CR_TILE / CR_WARPS, CR_TILE, CR_TSLOTS, ZT>;
-    typename Op::Args args{index_out, out_count, index_base, n_eff, counts_out, pv, exchange};
+    typename Op::Args args{index_out, out_count, index_base, n_eff, counts_out, pv, exchange, staged_lo, staged_mid};
     ring_pipeline<Op, CR_TILE, CR_STAGES, CR_WARPS, CR_AHEAD, CR_TSLOTS, true, 8, TRACE>(
         reinterpret_cast<const char*>(mask), n_eff, n_tiles, 0u, lb, G, args, smem, trace);
 }
@@ -452,15 +505,27 @@ hj_status launch_compress(hj_device* dev, size_t n, const uint32_t* size_buf, ui
         HJ_TRY(count_epoch(dev));
         LookbackView view = lookback_view(dev->lookback.base, dev->lookback.capacity_tiles, 0);
         const unsigned grid = (unsigned)(tiles < (size_t)dev->sm_count ? tiles : (size_t)dev->sm_count);
+        // emission path by the number of selected elements of a 2048-element slice (halved for the 1024-element
+        // slices of the 28 KiB geometry): sparse | lane-major staged | quads staged.  HJ_COMPRESS_STAGED=lo,mid moves them.
+        static const std::array<uint32_t, 2> staged = [] {
+            std::array<uint32_t, 2> t = {176u, 1100u};
+            if (const char* e = getenv("HJ_COMPRESS_STAGED")) {
+                unsigned a = 0, b = 0;
+                if (sscanf(e, "%u,%u", &a, &b) == 2) t = {a, b};
+            }
+            return t;
+        }();
         auto launch = [&](auto kernel, size_t smem) -> hj_status {
             HJ_TRY(ensure_dynamic_smem(dev, (const void*)kernel, smem));
             HJ_CUDA(launch_pdl(kernel, dim3(grid), dim3((CR_WARPS + 3) * 32), smem, dev->stream, mask, n, size_buf, out_count,
                                index_out, index_base, view, (grid + 31u) & ~31u, g_compress_trace, counts_out,
-                               peers ? *peers : PeerView(), peers ? 1u : 0u));
+                               peers ? *peers : PeerView(), peers ? 1u : 0u, staged[0] / (big ? 1u : 2u), staged[1] / (big ? 1u : 2u)));
             return HJ_OK;
         };
-        const size_t smem_small = ring_smem_bytes<uint32_t, 28672, 5, CR_WARPS, 8>(8 * (28672 / 8) + CR_WARPS * 1024);
-        const size_t smem_big = ring_smem_bytes<uint32_t, 57344, 3, CR_WARPS, 4>(4 * (57344 / 8) + CR_WARPS * 1024);
+        const size_t smem_small = ring_smem_bytes<uint32_t, 28672, 5, CR_WARPS, 8>(8 * (28672 / 8) + CR_WARPS * CR_STAGE_BYTES);
+        const size_t smem_big = ring_smem_bytes<uint32_t, 57344, 3, CR_WARPS, 4>(4 * (57344 / 8) + CR_WARPS * CR_STAGE_BYTES);
+        static_assert(ring_smem_bytes<uint32_t, 57344, 3, CR_WARPS, 4>(4 * (57344 / 8) + CR_WARPS * CR_STAGE_BYTES) <= 232448,
+                      "compress ring: over the 227 KiB of shared memory a CTA may opt in to");
         // measured on B200 (profiles/r01_ring_sweeps.txt): the 56 KiB geometry wins at low
         // selectivity (fewer status-word sweeps per byte) and ties elsewhere
         if (g_compress_trace) HJ_TRY(launch(compress_ring_kernel<57344, 3, 4, 3, true>, smem_big));  // tools/ring_timeline.py
