@@ -208,6 +208,9 @@ struct CompressOp {
         uint32_t exchange;
         // how a slice is emitted, by its number of selected elements: below staged_lo the sparse path (direct
         // stores), [staged_lo, staged_mid) staged with lane-major ownership, from staged_mid on with quads
+        // (letting half of the warps of a CTA switch earlier than the other half — lane-major is bound by the
+        // shared-memory pipe, the quads by the issue slots — was measured and is slower: a tile is done when its
+        // slowest warp is)
         uint32_t staged_lo, staged_mid;
     };
     // aux layout (shared memory behind the ring): TSLOTS mask planes of TILE/8 bytes (one u16 per
@@ -508,7 +511,7 @@ hj_status launch_compress(hj_device* dev, size_t n, const uint32_t* size_buf, ui
         // emission path by the number of selected elements of a 2048-element slice (halved for the 1024-element
         // slices of the 28 KiB geometry): sparse | lane-major staged | quads staged.  HJ_COMPRESS_STAGED=lo,mid moves them.
         static const std::array<uint32_t, 2> staged = [] {
-            std::array<uint32_t, 2> t = {176u, 1100u};
+            std::array<uint32_t, 2> t = {176u, 960u};
             if (const char* e = getenv("HJ_COMPRESS_STAGED")) {
                 unsigned a = 0, b = 0;
                 if (sscanf(e, "%u,%u", &a, &b) == 2) t = {a, b};

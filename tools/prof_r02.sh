@@ -16,6 +16,7 @@ cap reduce reduce_kernel reduce 30 4
 cap scan scan_ring scan 30 4
 cap compress_p50 compress_ring compress:0.5 30 4
 cap compress_p01 compress_ring compress:0.01 30 4
+cap compress_p99 compress_ring compress:0.99 30 4
 cap hist hist_ring hist:65536 28 4
 cap hist_fold hist_fold hist:65536 28 4
 cap gather_dram gather4 gather:28 28 4

@@ -10,12 +10,14 @@ KEYS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "sm__throughput.avg.pct_of_peak_sustained_elapsed", "sm__warps_active.avg.pct_of_peak_sustained_active", "launch__registers_per_thread",
         "launch__grid_size", "launch__block_size", "launch__shared_mem_per_block_dynamic", "smsp__inst_executed.sum",
         "smsp__issue_active.avg.pct_of_peak_sustained_active", "l1tex__data_bank_conflicts_pipe_lsu.sum",
+        "l1tex__data_pipe_lsu_wavefronts_mem_shared_op_st.sum", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared_op_st.sum",
+        "l1tex__data_pipe_lsu_wavefronts_mem_shared_op_ld.sum",
         "smsp__average_warp_latency_issue_stalled_long_scoreboard.ratio", "smsp__average_warp_latency_issue_stalled_short_scoreboard.ratio",
         "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio", "smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio",
         "smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio", "smsp__average_warps_issue_stalled_membar_per_issue_active.ratio",
         "dram__sectors_read.sum", "lts__t_sectors_srcunit_tex_op_read.sum", "lts__t_sectors_srcunit_tex_lookup_miss.sum"]
 MULT = {"byte": 1, "kbyte": 1e3, "mbyte": 1e6, "gbyte": 1e9, "tbyte": 1e12}
-NAMES = [("map", "map"), ("reduce", "reduce"), ("scan", "scan"), ("compress_p50", "compress"), ("compress_p01", "compress_p01"),
+NAMES = [("map", "map"), ("reduce", "reduce"), ("scan", "scan"), ("compress_p50", "compress"), ("compress_p01", "compress_p01"), ("compress_p99", "compress_p99"),
          ("hist", "histogram"), ("hist_fold", "histogram_fold"), ("gather_dram", "gather_dram"), ("gather_l2", "gather_l2")]
 traffic = {"_source": "profiles/r02_ncu_summary.txt (tools/prof_r02.sh: ncu --set full --clock-control none; dram__bytes_read.sum + dram__bytes_write.sum of one launch at the size bench.py runs)"}
 lines = []
