@@ -1,6 +1,7 @@
 #!/usr/bin/env python3
 """compress over a sweep of mask densities (2^28 bytes by default): time and GB/s of algorithmic bytes (n + 4 count).
-Run twice, with and without HJ_COMPRESS_QUADS=1, for the A/B of the medium-density path.  Usage: [log2 n]"""
+HJ_COMPRESS_STAGED=lo,mid moves the thresholds between the sparse / lane-major staged / quad staged paths
+(1,3000 = lane-major everywhere, 1,1 = quads everywhere).  Usage: [log2 n]"""
 import importlib, os, sys
 import numpy as np, torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -13,7 +14,7 @@ st = torch.cuda.Stream(); torch.cuda.set_stream(st); dev.set_stream(st.cuda_stre
 wrap = lambda t: dev.wrap(t.data_ptr(), t.numel() * t.element_size())
 g = torch.Generator(device="cuda").manual_seed(0)
 idx = torch.zeros(n, device="cuda", dtype=torch.int32); cnt = torch.zeros(4, device="cuda", dtype=torch.int32)
-print(f"HJ_COMPRESS_QUADS={os.environ.get('HJ_COMPRESS_QUADS', '')} n=2^{int(np.log2(n))}")
+print(f"HJ_COMPRESS_STAGED={os.environ.get('HJ_COMPRESS_STAGED', '(default 176,960)')} n=2^{int(np.log2(n))}")
 for p in (0.01, 0.05, 0.1, 0.15, 0.2, 0.3, 0.4, 0.5, 0.6, 0.7, 0.78, 0.85, 0.99):
     m = (torch.rand(n, device="cuda", generator=g) < p).to(torch.uint8)
     want = torch.nonzero(m).flatten().to(torch.int32)
