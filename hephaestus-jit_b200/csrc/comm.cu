@@ -503,11 +503,17 @@ hj_status exclusive_offset_of_totals(hj_comm* c, hj_type_kind ty, size_t n_local
 
 namespace hj {
 hj_status sharded_compress_pass(hj_comm* c, size_t n_local, uint32_t index_base, hj_buffer* mask, hj_buffer* index_out,
-                                hj_buffer* out_count, bool zero_tail) {
+                                hj_buffer* out_count, bool zero_tail, hj_buffer* local_count) {
     HJ_REQUIRE(c->connected, "communicator is not connected yet (hj_comm_connect)");
+    HJ_REQUIRE(!local_count || local_count->bytes >= 4, "sharded compress: the local-count buffer is smaller than 4 bytes");
     DeviceGuard g(c->dev);
-    return sharded_compress(c, n_local, index_base, (const uint8_t*)mask->ptr, (uint32_t*)index_out->ptr,
-                            (uint32_t*)out_count->ptr, nullptr, zero_tail);
+    HJ_TRY(sharded_compress(c, n_local, index_base, (const uint8_t*)mask->ptr, (uint32_t*)index_out->ptr,
+                            (uint32_t*)out_count->ptr, nullptr, zero_tail));
+    // every path of sharded_compress leaves the per-rank counts in the communicator's scratch
+    if (local_count)
+        HJ_CUDA(cudaMemcpyAsync(local_count->ptr, (const uint32_t*)gathered_slot(c) + c->rank, 4, cudaMemcpyDeviceToDevice,
+                                c->dev->stream));
+    return HJ_OK;
 }
 }  // namespace hj
 

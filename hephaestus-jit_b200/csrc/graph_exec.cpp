@@ -241,12 +241,15 @@ bool integer_kind(uint32_t k) { return k >= HJ_I8 && k <= HJ_U64; }
 // buf[0 .. n_local) += seed: a deferred scan result becomes an ordinary shard
 hj_status materialise(hj_device* dev, const ShardCtx* sc, uint32_t rid, hj_buffer* buf, const hj_buffer_desc& d) {
     hj_shard_desc& sd = sc->shards[rid];
-    if (!sd.deferred) return HJ_OK;
+    if (sd.deferred == HJ_SHARD_SEGMENT)
+        return fail(HJ_ERR_UNSUPPORTED, "resource %u is a per-rank compacted segment: only DynSize kernels sized by its count "
+                    "run over it (SURVEY 8e; re-balance it into a block-sharded array first: hj_sharded_rebalance)", rid);
+    if (sd.deferred != HJ_SHARD_DEFERRED) return HJ_OK;
     HJ_REQUIRE(sd.seed, "resource %u is marked deferred but carries no seed buffer", rid);
     uint64_t s0, s1;
     shard_bounds(d.size, sc->world, sc->rank, &s0, &s1);
     HJ_TRY(hj_apply_seed(dev, (hj_type_kind)d.ty, (size_t)(s1 - s0), buf, sd.seed));
-    sd.deferred = 0;
+    sd.deferred = HJ_SHARD_PLAIN;
     return HJ_OK;
 }
 
@@ -334,6 +337,86 @@ hj_status execute_passes(hj_device* dev, const ShardCtx* sc, const hj_pass* pass
         return HJ_OK;
     };
 
+    // A DynSize kernel over sharded resources: the wavefront step behind a sharded Compress
+    // (jit/test.rs:1020-1062: indices = mask.compress_dyn(); a.gather(indices) ... scatter(a, indices)).
+    // Every rank runs it over ITS segment of the compacted indices, sized by its own count (the segment's
+    // seed).  The indices are global and fall into the rank's block of every array of the mask's extent,
+    // so such arrays are bound with their base moved back by the block's start and addressed in place.
+    auto segment_kernel = [&](const hj_pass& p, uint32_t i) -> hj_status {
+        std::vector<hj_buffer*> bufs(p.n_resources);
+        for (uint32_t b = 0; b < p.n_resources; b++) HJ_TRY(res(p, b, &bufs[b], nullptr));
+        std::vector<SlotAccess> slot;
+        analyse_slot_access(p.ir, &slot);
+        std::vector<SegmentAccess> acc;
+        std::string why = "none of its resources is the index segment of a sharded Compress that carries a seed buffer";
+        uint32_t seg_slot = p.n_resources;
+        std::vector<uint64_t> shift(p.n_resources, 0);
+        std::vector<uint32_t> born;  // slots written at Index for the first time: aligned with the segment from now on
+        for (uint32_t c = 0; c < p.n_resources && seg_slot == p.n_resources; c++) {
+            const uint32_t crid = p.resources[c];
+            if (!sharded(crid) || sc->shards[crid].deferred != HJ_SHARD_SEGMENT || !sc->shards[crid].seed ||
+                descs[crid].ty != HJ_U32 || descs[crid].size != p.size)
+                continue;
+            if (!analyse_segment_access(p.ir, c, &acc, &why)) continue;
+            bool ok = true;
+            std::fill(shift.begin(), shift.end(), 0);
+            born.clear();
+            for (uint32_t b = 0; b < p.n_resources && ok; b++) {
+                const uint32_t rid = p.resources[b];
+                const SegmentAccess& a = acc[b];
+                if (!a.read && !a.written) continue;
+                char msg[160] = "";
+                if (!sharded(rid)) {
+                    if (a.written) snprintf(msg, sizeof(msg), "resource %u, a replica, is written", rid);
+                    else if (slot[b].any_index) snprintf(msg, sizeof(msg), "replica %u is read at Index, the position in the rank's segment", rid);
+                } else if (sc->shards[rid].deferred == HJ_SHARD_SEGMENT) {
+                    if (!a.index_only) snprintf(msg, sizeof(msg), "segment %u is addressed through a computed index", rid);
+                } else if (a.through_segment) {
+                    if (descs[rid].size != descs[crid].size)
+                        snprintf(msg, sizeof(msg), "sharded resource %u has another extent than the compacted mask", rid);
+                } else if (a.index_only && !a.read) {
+                    if (descs[rid].size != p.size) snprintf(msg, sizeof(msg), "resource %u written at Index has another extent", rid);
+                    else if (!sc->shards[rid].seed) snprintf(msg, sizeof(msg), "resource %u written at Index carries no seed buffer for its count", rid);
+                    else born.push_back(b);
+                } else {
+                    snprintf(msg, sizeof(msg), "sharded resource %u is addressed neither through the index segment nor as a segment", rid);
+                }
+                if (msg[0]) {
+                    why = msg;
+                    ok = false;
+                }
+            }
+            if (ok) seg_slot = c;
+        }
+        if (seg_slot == p.n_resources)
+            return fail(HJ_ERR_UNSUPPORTED, "kernel pass %u: a DynSize kernel over sharded resources runs per compacted segment, but %s "
+                        "(SURVEY 8e; otherwise re-balance the compacted sequence first: hj_sharded_rebalance)", i, why.c_str());
+        const uint32_t seg_rid = p.resources[seg_slot];
+        uint64_t s0 = 0, cnt = 0;
+        HJ_TRY(local_of(seg_rid, &s0, &cnt));
+        for (uint32_t b = 0; b < p.n_resources; b++) {
+            const uint32_t rid = p.resources[b];
+            if (!sharded(rid) || sc->shards[rid].deferred == HJ_SHARD_SEGMENT || !(acc[b].read || acc[b].written)) continue;
+            if (acc[b].through_segment) {
+                HJ_TRY(materialise(dev, sc, rid, bufs[b], descs[rid]));  // a deferred scan result is written / gathered in place
+                HJ_REQUIRE(cnt * descs[rid].elem_bytes <= bufs[b]->bytes, "kernel pass %u: resource %u is smaller than the rank's block", i, rid);
+                shift[b] = s0 * descs[rid].elem_bytes;
+            }
+        }
+        hj_kernel* k = nullptr;
+        HJ_TRY(hj_kernel_get(dev, p.ir, &k));
+        hj_status s = kernel_launch_shifted(dev, k, (size_t)cnt, sc->shards[seg_rid].seed, bufs.data(), (uint32_t)bufs.size(), 0, shift.data());
+        hj_kernel_release(k);
+        HJ_TRY(s);
+        for (uint32_t b : born) {
+            hj_shard_desc& sd = sc->shards[p.resources[b]];
+            HJ_REQUIRE(sd.seed->bytes >= 4, "kernel pass %u: the seed buffer of resource %u is smaller than 4 bytes", i, p.resources[b]);
+            HJ_CUDA(cudaMemcpyAsync(sd.seed->ptr, sc->shards[seg_rid].seed->ptr, 4, cudaMemcpyDeviceToDevice, dev->stream));
+            sd.deferred = HJ_SHARD_SEGMENT;
+        }
+        return HJ_OK;
+    };
+
     int64_t zero_tail_for = -1;  // index of the Compress pass that has to zero index[count..n) itself
     for (uint32_t i = 0; i < n_passes; i++) {
         const hj_pass& p = passes[i];
@@ -356,8 +439,11 @@ hj_status execute_passes(hj_device* dev, const ShardCtx* sc, const hj_pass* pass
             }
             bool pass_sharded = false;
             for (uint32_t b = 0; b < p.n_resources; b++) pass_sharded = pass_sharded || sharded(p.resources[b]);
-            HJ_REQUIRE(!(pass_sharded && size_buf), "kernel pass %u: a DynSize kernel over sharded resources is not supported "
-                       "(re-balance the compacted sequence first: hj_sharded_rebalance)", i);
+            if (pass_sharded && size_buf) {
+                snprintf(name, sizeof(name), "JIT Kernel %u [segment of %llu]", i, (unsigned long long)p.size);
+                HJ_TRY(segment_kernel(p, i));
+                break;
+            }
             HistMatch hm;
             if (!size_buf && p.n_resources == 2 && p.size >= (1u << 20) && match_histogram(p.ir, &hm) &&
                 (!pass_sharded || (sharded(p.resources[hm.key_slot]) && !sharded(p.resources[hm.dst_slot])))) {
@@ -476,6 +562,11 @@ hj_status execute_passes(hj_device* dev, const ShardCtx* sc, const hj_pass* pass
                         return fail(HJ_ERR_UNSUPPORTED, "kernel pass %u addresses sharded resource %u through a computed index "
                                     "or with another extent: only Index-addressed access shards (SURVEY 8e)", i, rid);
                     HJ_TRY(local_of(rid, &s0, &cnt));
+                    if (sc->shards[rid].deferred == HJ_SHARD_SEGMENT) {
+                        // overwriting a segment (the index zero-fill in front of the next Compress) makes it a block again
+                        if (access[b].read) HJ_TRY(materialise(dev, sc, rid, bufs[b], descs[rid]));  // fails, naming the resource
+                        sc->shards[rid].deferred = HJ_SHARD_PLAIN;
+                    }
                     if (sc->shards[rid].deferred) {
                         if (access[b].written || access[b].cond_gather) HJ_TRY(materialise(dev, sc, rid, bufs[b], descs[rid]));
                         else add_seed[b] = any_seed = true;
@@ -565,7 +656,12 @@ hj_status execute_passes(hj_device* dev, const ShardCtx* sc, const hj_pass* pass
                 HJ_TRY(local_of(p.resources[2], &s0, &cnt));
                 HJ_REQUIRE(cnt <= src->bytes && cnt * 4 <= index_out->bytes && out_count->bytes >= 4,
                            "compress pass %u: buffer sizes do not match the %llu-element shard", i, (unsigned long long)cnt);
-                HJ_TRY(sharded_compress_pass(sc->comm, (size_t)cnt, (uint32_t)s0, src, index_out, out_count, zt));
+                HJ_REQUIRE(sc->shards[p.resources[2]].deferred != HJ_SHARD_SEGMENT,
+                           "compress pass %u: the mask is a per-rank segment, not a block of a sharded array", i);
+                // the rank's own count stays beside the segment: it sizes the DynSize kernels that run over it
+                hj_shard_desc& seg = sc->shards[p.resources[0]];
+                HJ_TRY(sharded_compress_pass(sc->comm, (size_t)cnt, (uint32_t)s0, src, index_out, out_count, zt, seg.seed));
+                seg.deferred = seg.seed ? HJ_SHARD_SEGMENT : HJ_SHARD_PLAIN;
             } else if (zt) {
                 const size_t n = dsrc->size;
                 HJ_REQUIRE(n >= 1 && n <= src->bytes && n * 4 <= index_out->bytes && out_count->bytes >= 4 &&
@@ -660,6 +756,10 @@ extern "C" hj_status hj_shard_plan(const hj_pass* passes, uint32_t n_passes, con
             return fail(HJ_ERR_UNSUPPORTED, "pass %u: device op %u is out of scope for the B200 backend", i, p.kind);
         }
     }
+    // index segment -> the count its Compress pass writes (the size buffer of the DynSize kernels behind it)
+    std::vector<int64_t> count_of_index(n_resources, -1);
+    for (uint32_t i = 0; i < n_passes; i++)
+        if (passes[i].kind == HJ_PASS_COMPRESS) count_of_index[passes[i].resources[0]] = (int64_t)passes[i].resources[1];
     bool changed = true;
     auto place = [&](uint32_t rid, uint32_t pl) {
         if (shards[rid].placement == HJ_RES_AUTO) {
@@ -676,7 +776,30 @@ extern "C" hj_status hj_shard_plan(const hj_pass* passes, uint32_t n_passes, con
             case HJ_PASS_KERNEL: {
                 bool any = false;
                 for (uint32_t b = 0; b < p.n_resources; b++) any = any || is(p.resources[b], HJ_RES_SHARDED);
-                if (!any || p.size_buffer >= 0) break;  // undecided for now (or DynSize: never sharded)
+                if (!any) break;  // undecided for now
+                if (p.size_buffer >= 0) {
+                    // DynSize: shards only as a SEGMENT kernel — one of its resources is the index segment of a
+                    // sharded Compress whose count sizes the pass (or arrives as a segment); then what it reaches
+                    // through the segment, or writes at Index, lives per rank as well
+                    for (uint32_t c = 0; c < p.n_resources; c++) {
+                        const uint32_t crid = p.resources[c];
+                        const bool from_compress = count_of_index[crid] == (int64_t)p.size_buffer;
+                        if (!is(crid, HJ_RES_SHARDED) || !(from_compress || shards[crid].deferred == HJ_SHARD_SEGMENT) ||
+                            descs[crid].ty != HJ_U32 || descs[crid].size != p.size)
+                            continue;
+                        std::vector<SegmentAccess> acc;
+                        if (!analyse_segment_access(p.ir, c, &acc, nullptr)) continue;
+                        for (uint32_t b = 0; b < p.n_resources; b++) {
+                            const uint32_t rid = p.resources[b];
+                            const SegmentAccess& a = acc[b];
+                            const bool per_rank = (a.read || a.written) && descs[rid].size == p.size &&
+                                                  (a.through_segment || (a.index_only && !a.read));
+                            place(rid, per_rank ? HJ_RES_SHARDED : HJ_RES_REPLICATED);
+                        }
+                        break;
+                    }
+                    break;
+                }
                 for (uint32_t b = 0; b < p.n_resources; b++) {
                     const uint32_t rid = p.resources[b];
                     const SlotAccess& a = access[i][b];

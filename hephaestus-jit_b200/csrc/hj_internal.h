@@ -147,6 +147,10 @@ void chunk_schedule(size_t n, size_t chunk_elems, size_t align_elems, std::vecto
 hj_status kernel_launch_streamed(hj_device* dev, hj_kernel* k, size_t size, hj_buffer* const* buffers, uint32_t n_buffers,
                                  bool* done);
 
+// jit.cpp: hj_kernel_launch with slot i bound to buffers[i]->ptr - shift_bytes[i] (shift_bytes may be NULL)
+hj_status kernel_launch_shifted(hj_device* dev, hj_kernel* k, size_t size, hj_buffer* size_buf, hj_buffer* const* buffers,
+                                uint32_t n_buffers, uint32_t index_base, const uint64_t* shift_bytes);
+
 // host_stream.cu: a PrefixSum pass over a source that is still arriving; *done = false when not applicable
 hj_status prefix_sum_arriving(hj_device* dev, hj_type_kind ty, size_t n, bool inclusive, hj_buffer* src, hj_buffer* dst,
                               bool* done);
@@ -195,8 +199,10 @@ hj_status launch_fill(hj_device* dev, void* dst, size_t n, size_t elem_bytes, ui
 
 // comm.cu internals used by the sharded pass interpreter (graph_exec.cpp)
 hj_device* comm_device(hj_comm* c);
+// `local_count` (optional, >= 4 bytes): receives this rank's own count (what sizes the DynSize kernels that
+// run over the rank's segment)
 hj_status sharded_compress_pass(hj_comm* c, size_t n_local, uint32_t index_base, hj_buffer* mask, hj_buffer* index_out,
-                                hj_buffer* out_count, bool zero_tail);
+                                hj_buffer* out_count, bool zero_tail, hj_buffer* local_count = nullptr);
 
 // cudaFuncSetAttribute(MaxDynamicSharedMemorySize) once per (device, kernel, size) instead of on every
 // launch (a driver call of a few microseconds on the relaunch path).  Device lock held by the caller.

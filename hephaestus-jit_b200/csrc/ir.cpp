@@ -56,6 +56,55 @@ void analyse_slot_access(const hj_ir* ir, std::vector<SlotAccess>* out) {
     }
 }
 
+bool analyse_segment_access(const hj_ir* ir, uint32_t seg_slot, std::vector<SegmentAccess>* out, std::string* why) {
+    IRView v(ir);
+    out->assign(ir->n_buffers, SegmentAccess());
+    auto is_index = [&](uint32_t id) { return v.var(id).op == HJ_OP_INDEX; };
+    auto is_segment_gather = [&](uint32_t id) {
+        const hj_ir_var& g = v.var(id);
+        if (g.op != HJ_OP_GATHER) return false;
+        const hj_ir_var& buf = v.var(v.dep(id, 0));
+        if (buf.op != HJ_OP_BUFFER_REF || buf.data != seg_slot || !is_index(v.dep(id, 1))) return false;
+        if (v.n_deps(id) == 2) return true;
+        const hj_ir_var& c = v.var(v.dep(id, 2));  // an inactive lane would read index 0: only `true` is safe
+        return c.op == HJ_OP_LITERAL && c.data != 0;
+    };
+    for (uint32_t i = 0; i < ir->n_vars; i++) {
+        const hj_ir_var& var = v.var(i);
+        int idx_pos = -1;  // which dependency is the access index
+        switch (var.op) {
+        case HJ_OP_GATHER: case HJ_OP_ATOMIC_INC: idx_pos = 1; break;
+        case HJ_OP_SCATTER: case HJ_OP_SCATTER_REDUCE: case HJ_OP_SCATTER_ATOMIC: idx_pos = 2; break;
+        default: break;
+        }
+        for (uint32_t k = 0; k < v.n_deps(i); k++)
+            if (is_index(v.dep(i, k)) && (int)k != idx_pos) {
+                if (why) *why = "KernelOp::Index is used as a value (var " + std::to_string(i) + ")";
+                return false;
+            }
+        if (idx_pos < 0) continue;
+        const hj_ir_var& buf = v.var(v.dep(i, 0));
+        if (buf.op != HJ_OP_BUFFER_REF || buf.data >= ir->n_buffers) continue;
+        SegmentAccess& s = (*out)[buf.data];
+        if (var.op == HJ_OP_GATHER) s.read = true;
+        else s.written = true;
+        if (var.op != HJ_OP_GATHER && var.op != HJ_OP_SCATTER) s.read = true;  // atomics read-modify-write
+        const uint32_t idx = v.dep(i, (uint32_t)idx_pos);
+        if (!is_index(idx)) s.index_only = false;
+        if (!is_segment_gather(idx)) s.through_segment = false;
+    }
+    if (seg_slot >= ir->n_buffers) {
+        if (why) *why = "segment slot out of range";
+        return false;
+    }
+    const SegmentAccess& seg = (*out)[seg_slot];
+    if (seg.written || !seg.read || !seg.index_only) {
+        if (why) *why = "the index segment must only be read, at the bare Index";
+        return false;
+    }
+    return true;
+}
+
 static bool dep_count_ok(uint32_t op, uint32_t n, const char** want) {
     switch (op) {
     case HJ_OP_NOP: *want = "1"; return n == 1;

@@ -51,6 +51,19 @@ inline bool slots_may_share(const SlotAccess& r, const SlotAccess& w) {
     return r.identity && w.identity && !r.written && !w.read && r.last_read < w.first_write;
 }
 
+// A DynSize kernel that runs over a per-rank compacted SEGMENT (the index output of a sharded Compress,
+// bound to `seg_slot`): how it reaches each of its slots.  The segment holds GLOBAL indices that fall into
+// the rank's own block, so a slot addressed only through `Gather(segment, Index)` can be that block.
+struct SegmentAccess {
+    bool read = false, written = false;
+    bool index_only = true;       // every access at the bare Index: the slot is aligned with the segment
+    bool through_segment = true;  // every access index is Gather(BufferRef(seg_slot), Index [, literal true])
+};
+// false (+ why) when the kernel cannot run per segment: the segment is written or not read at the bare
+// Index, or KernelOp::Index is used as a value (it is the position in the RANK's segment there, not the
+// position in the global compacted sequence).  `ir` must have passed validate_ir.
+bool analyse_segment_access(const hj_ir* ir, uint32_t seg_slot, std::vector<SegmentAccess>* out, std::string* why);
+
 // vartype.rs:125-189
 size_t type_size(const IRView& v, uint32_t t);
 size_t type_align(const IRView& v, uint32_t t);

@@ -343,6 +343,16 @@ hj_status hj_device_kernel_cache_stats(hj_device* dev, uint64_t* n_compiled, uin
 
 hj_status hj_kernel_launch(hj_device* dev, hj_kernel* k, size_t size, hj_buffer* size_buf,
                            hj_buffer* const* buffers, uint32_t n_buffers, uint32_t index_base) {
+    return hj::kernel_launch_shifted(dev, k, size, size_buf, buffers, n_buffers, index_base, nullptr);
+}
+
+}  // extern "C"
+
+// `shift_bytes[i]` (optional): slot i is bound to buffers[i]->ptr - shift_bytes[i].  A segment kernel of
+// the sharded pass interpreter addresses the rank's BLOCK of a sharded array with GLOBAL indices that all
+// fall into that block: the base moves back by the block's start, every access lands inside the buffer.
+hj_status hj::kernel_launch_shifted(hj_device* dev, hj_kernel* k, size_t size, hj_buffer* size_buf, hj_buffer* const* buffers,
+                                    uint32_t n_buffers, uint32_t index_base, const uint64_t* shift_bytes) {
     HJ_REQUIRE(dev && k, "null argument");
     HJ_REQUIRE(n_buffers == k->n_buffers, "kernel expects %u buffers, got %u", k->n_buffers, n_buffers);
     HJ_REQUIRE(size <= 0xffffffffull, "kernel size does not fit the u32 index type (trace.rs:552-562)");
@@ -351,8 +361,10 @@ hj_status hj_kernel_launch(hj_device* dev, hj_kernel* k, size_t size, hj_buffer*
     bool aligned = true;
     for (uint32_t i = 0; i < n_buffers; i++) {
         HJ_REQUIRE(buffers && buffers[i], "buffer %u is null", i);
-        ptrs[i] = buffers[i]->ptr;
-        if ((uintptr_t)ptrs[i] & 15u) aligned = false;
+        const uint64_t shift = shift_bytes ? shift_bytes[i] : 0;
+        ptrs[i] = (char*)buffers[i]->ptr - shift;
+        // a shifted slot is only ever addressed through computed indices: no vector access touches it
+        if (!shift && ((uintptr_t)ptrs[i] & 15u)) aligned = false;
     }
     // One buffer under two slots: every slot is declared __restrict__ and read-only slots are loaded
     // through the non-coherent path, so a duplicate is only legal when no thread can observe another
@@ -361,7 +373,7 @@ hj_status hj_kernel_launch(hj_device* dev, hj_kernel* k, size_t size, hj_buffer*
     // lifetime aliasing produces, graph.rs:237-296).
     for (uint32_t i = 0; i < n_buffers; i++)
         for (uint32_t j = i + 1; j < n_buffers; j++) {
-            const char *a0 = (const char*)ptrs[i], *b0 = (const char*)ptrs[j];
+            const char *a0 = (const char*)buffers[i]->ptr, *b0 = (const char*)buffers[j]->ptr;
             if (a0 + buffers[i]->bytes <= b0 || b0 + buffers[j]->bytes <= a0) continue;
             const SlotAccess &a = k->slot_access[i], &b = k->slot_access[j];
             if (!a.written && !b.written) continue;
@@ -402,6 +414,8 @@ hj_status hj_kernel_launch(hj_device* dev, hj_kernel* k, size_t size, hj_buffer*
     dev->launches.fetch_add(1, std::memory_order_relaxed);
     return HJ_OK;
 }
+
+extern "C" {
 
 // Out-of-core elementwise map: every buffer of the kernel lives in HOST memory (pinned for full
 // speed) and is addressed by the bare Index only.  The array is cut into chunks that flow

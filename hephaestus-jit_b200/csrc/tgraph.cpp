@@ -360,6 +360,9 @@ hj_buffer* create_buffer(hj_device* dev, const BufferDesc& d) {  // Resource::cr
         throw TraceError(std::string("create_buffer failed: ") + hj_last_error());
     return b;
 }
+uint32_t shard_state(const Var& v) {  // hj_shard_desc.deferred of the variable's buffer
+    return v.data.segment ? HJ_SHARD_SEGMENT : v.data.deferred ? HJ_SHARD_DEFERRED : HJ_SHARD_PLAIN;
+}
 uint32_t scalar_kind(TypeId t) {
     TypeNode n = type_node(t);
     return n.kind;
@@ -426,7 +429,7 @@ void launch_graph(const Graph& g, hj_device* dev, const std::vector<VarId>& inpu
                 if (comm && comm != var.data.comm) throw TraceError("variables sharded over different communicators in one launch");
                 comm = var.data.comm;
                 shards[rid].placement = HJ_RES_SHARDED;
-                shards[rid].deferred = var.data.deferred ? 1 : 0;
+                shards[rid].deferred = shard_state(var);
                 if (var.data.seed) {
                     hj_buffer_retain(var.data.seed);
                     shards[rid].seed = var.data.seed;
@@ -467,19 +470,27 @@ void launch_graph(const Graph& g, hj_device* dev, const std::vector<VarId>& inpu
                 throw TraceError(std::string("hj_shard_plan failed: ") + hj_last_error());
             // a sharded integer scan result keeps its cross-GPU offset beside it (8 instead of 12 bytes
             // per element; the consumers add it): give every such destination a seed slot
-            for (const hj_pass& p : passes)
+            auto give_seed = [&](uint32_t rid) {
+                if (shards[rid].placement != HJ_RES_SHARDED || shards[rid].seed) return;
+                if (g.seed_cache.size() < nres) g.seed_cache.resize(nres, nullptr);
+                if (!g.seed_cache[rid] && hj_buffer_create(dev, 16, &g.seed_cache[rid]) != HJ_OK)
+                    throw TraceError(std::string("create_buffer failed: ") + hj_last_error());
+                hj_buffer_retain(g.seed_cache[rid]);
+                shards[rid].seed = g.seed_cache[rid];
+                seed_from_cache[rid] = true;
+            };
+            for (const hj_pass& p : passes) {
                 if (p.kind == HJ_PASS_PREFIX_SUM && p.n_resources >= 2) {
-                    const uint32_t rid = p.resources[0];
-                    const uint32_t k = descs[rid].ty;
-                    if (shards[rid].placement == HJ_RES_SHARDED && !shards[rid].seed && k >= HJ_I8 && k <= HJ_U64) {
-                        if (g.seed_cache.size() < nres) g.seed_cache.resize(nres, nullptr);
-                        if (!g.seed_cache[rid] && hj_buffer_create(dev, 16, &g.seed_cache[rid]) != HJ_OK)
-                            throw TraceError(std::string("create_buffer failed: ") + hj_last_error());
-                        hj_buffer_retain(g.seed_cache[rid]);
-                        shards[rid].seed = g.seed_cache[rid];
-                        seed_from_cache[rid] = true;
-                    }
+                    const uint32_t k = descs[p.resources[0]].ty;
+                    if (k >= HJ_I8 && k <= HJ_U64) give_seed(p.resources[0]);
                 }
+                // the index segment of a sharded Compress keeps the rank's own count beside it, and so does
+                // everything a DynSize kernel writes over such a segment (hj.h: HJ_SHARD_SEGMENT)
+                if (p.kind == HJ_PASS_COMPRESS && p.n_resources >= 3) give_seed(p.resources[0]);
+                if (p.kind == HJ_PASS_KERNEL && p.size_buffer >= 0)
+                    for (uint32_t b = 0; b < p.n_resources; b++)
+                        if (descs[p.resources[b]].size == p.size) give_seed(p.resources[b]);
+            }
         }
         auto local_desc = [&](size_t rid, BufferDesc d) {  // what this rank allocates for the resource
             if (comm && shards[rid].placement == HJ_RES_SHARDED) {
@@ -618,8 +629,9 @@ void launch_graph(const Graph& g, hj_device* dev, const std::vector<VarId>& inpu
             r.buf = res[rid];
             if (comm && shards[rid].placement == HJ_RES_SHARDED) {
                 r.comm = comm;
-                r.deferred = shards[rid].deferred != 0;
-                r.seed = r.deferred ? shards[rid].seed : nullptr;
+                r.deferred = shards[rid].deferred == HJ_SHARD_DEFERRED;
+                r.segment = shards[rid].deferred == HJ_SHARD_SEGMENT;
+                r.seed = r.deferred || r.segment ? shards[rid].seed : nullptr;
                 if (r.seed && seed_from_cache[rid] && rid < g.seed_cache.size() && g.seed_cache[rid] == r.seed) {
                     // the value outlives this launch inside a variable: the next launch needs a seed of its own
                     hj_buffer_release(g.seed_cache[rid]);
@@ -653,7 +665,7 @@ void launch_graph(const Graph& g, hj_device* dev, const std::vector<VarId>& inpu
             } else if (comm && shards[i].placement == HJ_RES_SHARDED && gr.kind == GraphResource::Captured) {
                 // a captured deferred scan result a device op of this launch had to materialise
                 if (Var* var = g_trace.get(gr.id))
-                    if (var->data.kind == Resource::Buffer && var->data.buf == res[i] && var->data.deferred && !shards[i].deferred)
+                    if (var->data.kind == Resource::Buffer && var->data.buf == res[i] && shard_state(*var) != shards[i].deferred)
                         set_resource(*var, resource_of(i));
             }
         }
@@ -661,7 +673,7 @@ void launch_graph(const Graph& g, hj_device* dev, const std::vector<VarId>& inpu
         for (size_t i = 0; comm && i < inputs.size() && i < g.inputs.size(); i++) {
             const uint32_t rid = g.inputs[i];
             if (Var* var = g_trace.get(inputs[i]))
-                if (var->data.kind == Resource::Buffer && var->data.buf == res[rid] && var->data.deferred && !shards[rid].deferred)
+                if (var->data.kind == Resource::Buffer && var->data.buf == res[rid] && shard_state(*var) != shards[rid].deferred)
                     set_resource(*var, resource_of(rid));
         }
     } catch (...) {

@@ -421,6 +421,7 @@ VarId from_buffer_sharded(hj_comm* comm, hj_buffer* local_buf, TypeId ty, size_t
 }
 ShardInfo shard_info(VarId id) {
     hj_comm* comm = nullptr;
+    hj_buffer* seed = nullptr;
     ShardInfo si;
     size_t n = 0;
     {
@@ -428,11 +429,24 @@ ShardInfo shard_info(VarId id) {
         const Var& v = g_trace.var(id);
         comm = v.data.kind == Resource::Buffer ? v.data.comm : nullptr;
         si.deferred = v.data.deferred;
+        si.segment = v.data.segment;
         n = v.extent.n;
+        if (comm && si.segment && v.extent.dynamic) {  // a static `compress` index keeps its capacity and zero tail
+            seed = v.data.seed;
+            if (!seed) throw TraceError("a sharded segment without its count buffer");
+            hj_buffer_retain(seed);
+        }
     }
     if (!comm) return ShardInfo();
     si.sharded = true;
     local_block(comm, n, &si.start, &si.count);
+    if (seed) {
+        uint32_t valid = 0;
+        const hj_status s = hj_buffer_to_host(seed, 0, 4, &valid);
+        hj_buffer_release(seed);
+        if (s != HJ_OK) throw TraceError(std::string("to_host failed: ") + hj_last_error());
+        si.count = std::min<uint64_t>(si.count, valid);
+    }
     return si;
 }
 void materialise(VarId id) {

@@ -26,8 +26,11 @@ struct Resource {
     // the variable's global extent (hj_shard_bounds).  `deferred`: the block is a LOCAL scan whose
     // global value is buf[i] + seed[0] (hj_sharded_prefix_sum_deferred); the Var owns a reference to
     // `seed`.  The communicator is borrowed: it must outlive the variables sharded over it.
+    // `segment`: the block is a per-rank compacted SEGMENT (the index output of a sharded Compress, or what
+    // a DynSize kernel wrote over it): only the first seed[0] (u32) entries are defined.
     hj_comm* comm = nullptr;
     bool deferred = false;
+    bool segment = false;
     hj_buffer* seed = nullptr;
 };
 
@@ -102,7 +105,8 @@ VarId from_buffer(hj_buffer* buf, TypeId ty, size_t n);
 // this rank's block of an n_global-element array: from host memory / from an existing device buffer
 VarId array_sharded(hj_comm* comm, TypeId ty, const void* local_data, size_t n_global);
 VarId from_buffer_sharded(hj_comm* comm, hj_buffer* local_buf, TypeId ty, size_t n_global);
-struct ShardInfo { bool sharded = false, deferred = false; uint64_t start = 0, count = 0; };
+// `count`: elements of the rank's block — for a DynSize segment the rank's own count (read from the device)
+struct ShardInfo { bool sharded = false, deferred = false, segment = false; uint64_t start = 0, count = 0; };
 ShardInfo shard_info(VarId id);
 void materialise(VarId id);  // a deferred scan result becomes an ordinary shard (buf[i] += seed)
 VarId bop(uint32_t op, VarId a, VarId b);

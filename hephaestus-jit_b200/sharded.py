@@ -126,7 +126,8 @@ class Comm:
     def execute_graph(self, passes, env, descs, placement, seeds=None, timed: bool = False):
         """``hj_execute_graph_sharded``: ``placement[i]`` in {RES_REPLICATED, RES_SHARDED, RES_AUTO} per
         resource (AUTO ones are planned with ``hj_shard_plan`` first), ``seeds[i]`` an optional
-        one-element Buffer that lets a sharded integer scan into resource i stay deferred.  Returns
+        one-element Buffer that lets a sharded integer scan into resource i stay deferred (and that receives
+        the rank's own count when resource i is the index segment of a sharded Compress).  Returns
         ``(placement, deferred, report)`` after the call."""
         c_passes, n, c_env, c_desc, _keep = marshal_graph(passes, env, descs)
         nres = len(env)
@@ -143,7 +144,7 @@ class Comm:
             report.passes_capacity = n
         check(lib.hj_execute_graph_sharded(self._h, c_passes, n, c_env, c_desc, nres, sh, ctypes.byref(report)))
         rep = [(reps[i].name.decode(), reps[i].start_us, reps[i].duration_us) for i in range(n)] if timed else None
-        return [sh[i].placement for i in range(nres)], [bool(sh[i].deferred) for i in range(nres)], rep
+        return [sh[i].placement for i in range(nres)], [sh[i].deferred == 1 for i in range(nres)], rep
 
     def compress(self, n_local: int, index_base: int, src_mask: Buffer, index_out: Buffer, out_count: Buffer,
                  counts_out: Buffer | None = None) -> None:

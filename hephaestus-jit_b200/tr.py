@@ -329,11 +329,19 @@ class VarRef:
     def shard(self):
         """None for an ordinary variable; ``(start, count, deferred)`` when the variable's buffer is the
         block ``[start, start + count)`` of its global extent on this rank (``hj_tr_var_shard``).
-        ``deferred``: a scan result kept as (local scan, offset); ``to_vec`` adds the offset."""
+        ``deferred``: a scan result kept as (local scan, offset); ``to_vec`` adds the offset.  For a per-rank
+        compacted segment (``is_segment``: the indices of a sharded ``compress``) ``count`` is the rank's own
+        count, so ``to_vec`` returns the rank's part of the compacted sequence."""
         sharded, deferred, start, count = ctypes.c_int32(), ctypes.c_int32(), _u64(), _u64()
         check(lib.hj_tr_var_shard(self._id, ctypes.byref(sharded), ctypes.byref(start), ctypes.byref(count),
                                   ctypes.byref(deferred)))
-        return (start.value, count.value, bool(deferred.value)) if sharded.value else None
+        return (start.value, count.value, deferred.value == 1) if sharded.value else None
+
+    def is_segment(self) -> bool:
+        """True when the buffer is this rank's segment of a compacted sequence (``HJ_SHARD_SEGMENT``)."""
+        sharded, deferred = ctypes.c_int32(), ctypes.c_int32()
+        check(lib.hj_tr_var_shard(self._id, ctypes.byref(sharded), None, None, ctypes.byref(deferred)))
+        return bool(sharded.value) and deferred.value == 2
 
     def materialise(self) -> None:
         """Adds the offset of a deferred scan result on the device (``hj_tr_materialise``)."""

@@ -418,16 +418,29 @@ hj_status hj_sharded_rebalance(hj_comm* comm, size_t elem_bytes, hj_buffer* src,
  *                                  the offset; else hj_sharded_prefix_sum;
  *   Compress                       local compaction with global indices, counts exchanged in the kernel;
  *                                  index_out stays a per-rank segment, out_count is the global count.
- * Not sharded (SURVEY 8e "replicas only"): access to a sharded resource through a computed index,
- * writes to a replica from a sharded kernel, DynSize kernels over sharded data -> HJ_ERR_UNSUPPORTED. */
+ *   DynSize kernel behind a        the wavefront step (jit/test.rs:1020-1062: compress_dyn -> gather /
+ *   sharded Compress               scatter through the compacted indices): every rank runs the kernel over
+ *                                  ITS segment, sized by its own count on the device; the segment's indices
+ *                                  are global and fall into the rank's block by construction, so sharded
+ *                                  arrays of the mask's extent are addressed through them in place.  Needs
+ *                                  a seed buffer on the index segment (it receives the rank's count).
+ * Not sharded (SURVEY 8e "replicas only"): access to a sharded resource through any other computed
+ * index, writes to a replica from a sharded kernel, KernelOp::Index used as a VALUE inside a segment
+ * kernel (it is the position in the rank's segment there), device ops over a segment
+ * -> HJ_ERR_UNSUPPORTED. */
 typedef enum { HJ_RES_REPLICATED = 0, HJ_RES_SHARDED = 1, HJ_RES_AUTO = 2 } hj_placement;
+/* values of hj_shard_desc.deferred */
+#define HJ_SHARD_PLAIN 0u    /* the buffer holds the rank's block as it is */
+#define HJ_SHARD_DEFERRED 1u /* a LOCAL scan: the global value of element i is buffer[i] + seed[0] */
+#define HJ_SHARD_SEGMENT 2u  /* a per-rank compacted SEGMENT (Compress index output, or what a DynSize
+                                kernel wrote at Index): only the first seed[0] (u32) entries are defined */
 typedef struct {
     uint32_t placement; /* hj_placement.  SHARDED: the buffer holds this rank's block
                            [start, end) = hj_shard_bounds(descs[i].size, world, rank) of the global array */
-    uint32_t deferred;  /* in / out, SHARDED scan results: 1 = the buffer holds the LOCAL scan; the
-                           global value of element i is buffer[i] + seed[0] */
-    hj_buffer* seed;    /* one element of the resource's type on the device, or NULL (then PrefixSum
-                           results are always materialised) */
+    uint32_t deferred;  /* in / out, SHARDED resources: HJ_SHARD_PLAIN / _DEFERRED / _SEGMENT */
+    hj_buffer* seed;    /* >= 4 bytes (one element of the resource's type for a scan) on the device, or
+                           NULL (then PrefixSum results are always materialised and a Compress index
+                           segment cannot size dependent DynSize kernels) */
 } hj_shard_desc;
 /* Block of rank `rank`: sizes differ by at most one, order preserved. */
 void hj_shard_bounds(uint64_t n, int32_t world, int32_t rank, uint64_t* start, uint64_t* end);
@@ -500,8 +513,10 @@ hj_status hj_tr_array_async(hj_device* dev, uint32_t ty, const void* pinned_data
 hj_status hj_tr_array_sharded(hj_comm* comm, uint32_t ty, const void* local_data, uint64_t n_global, uint64_t* out);
 hj_status hj_tr_from_buffer_sharded(hj_comm* comm, hj_buffer* local_buf, uint32_t ty, uint64_t n_global, uint64_t* out);
 /* *sharded = 1: the variable's buffer is the block [start, start + count) of its global extent;
- * *deferred = 1: it is a scan result kept as (local scan, offset) — hj_tr_to_host adds the offset,
- * hj_tr_materialise adds it on the device.  hj_tr_to_host of a sharded variable addresses the BLOCK. */
+ * *deferred = HJ_SHARD_DEFERRED: it is a scan result kept as (local scan, offset) — hj_tr_to_host adds
+ * the offset, hj_tr_materialise adds it on the device; HJ_SHARD_SEGMENT: it is the rank's segment of a
+ * compacted sequence (for a DynSize variable *count is then the rank's own count, read from the device).
+ * hj_tr_to_host of a sharded variable addresses the BLOCK. */
 hj_status hj_tr_var_shard(uint64_t v, int32_t* sharded, uint64_t* start, uint64_t* count, int32_t* deferred);
 hj_status hj_tr_materialise(uint64_t v);
 hj_status hj_tr_bop(uint32_t op /* hj_bop */, uint64_t a, uint64_t b, uint64_t* out);  /* :968-1046 */

@@ -435,6 +435,131 @@ def _recorded_sharded_function(rank, world, dev, comm, n):
     assert c1 - c0 >= 1 and r1 - r0 >= 1, (c0, r0, c1, r1)
 
 
+def _wavefront_reference(a0, steps):
+    """The wavefront loop on the whole array: lanes alive in `mask` are scaled and stay alive while > 0.1."""
+    a, alive = a0.copy(), np.ones(a0.size, bool)
+    history = []
+    for _ in range(steps):
+        idx = np.flatnonzero(alive).astype(np.uint32)
+        v = a[idx] * np.float32(0.9)
+        alive[idx] = v > np.float32(0.1)
+        a[idx] = v
+        history.append((idx, a.copy(), alive.copy()))
+    return history
+
+
+def _wavefront_pass_list(rank, world, dev, comm, n):
+    """Compress + the two DynSize kernels behind it (tests/test_sharded_cpu.py: _wavefront_passes) through
+    hj_execute_graph_sharded(_cached): every rank runs the kernels over its own segment, sized by its own
+    count; the relaunches replay one captured CUDA graph.  Checked against the loop on the whole array."""
+    from test_sharded_cpu import _wavefront_passes
+    sh = importlib.import_module("hephaestus-jit_b200.sharded")
+    S, R = sh.RES_SHARDED, sh.RES_REPLICATED
+    s, e = sh.shard_bounds(n, world, rank)
+    nl = e - s
+    a0 = np.random.Generator(np.random.PCG64(5)).random(n, dtype=np.float32)
+    steps = 14
+    history = _wavefront_reference(a0, steps)
+    passes, descs = _wavefront_passes(n)
+    ba, bm = dev.create_buffer_from_slice(a0[s:e]), dev.create_buffer_from_slice(np.ones(nl, np.uint8))
+    bidx, bcnt, bseed = dev.create_buffer_from_slice(np.zeros(nl, np.uint32)), dev.create_buffer(4), dev.create_buffer(16)
+    g = hj.PreparedGraph(dev, passes, [ba, bm, bidx, bcnt], descs, comm=comm, placement=[S, S, S, R],
+                         seeds=[None, None, bseed, None], graph_key=0x77AF0)
+    c0, r0, _ = dev.graph_cache_stats()
+    for it, (idx, a, alive) in enumerate(history):
+        g.run()
+        lo, hi = np.searchsorted(idx, s), np.searchsorted(idx, e)
+        assert int(bcnt.to_host(np.uint32, 0, 1)[0]) == idx.size, it
+        assert int(bseed.to_host(np.uint32, 0, 1)[0]) == hi - lo, it
+        assert np.array_equal(bidx.to_host(np.uint32)[: hi - lo], idx[lo:hi]), it
+        assert np.array_equal(ba.to_host(np.float32), a[s:e]), it
+        assert np.array_equal(bm.to_host(np.uint8).astype(bool), alive[s:e]), it
+        assert g.segments() == [False, False, True, False]
+    assert history[-1][0].size < history[0][0].size // 2, "the wavefront must have shrunk"
+    c1, r1, _ = dev.graph_cache_stats()
+    assert c1 - c0 == 1 and r1 - r0 == steps - 2, (c1 - c0, r1 - r0)
+    # without a seed on the index segment there is nothing to size the kernels with: refused, not mis-sized
+    g2 = hj.PreparedGraph(dev, passes, [ba, bm, bidx, bcnt], descs, comm=comm, placement=[S, S, S, R])
+    with pytest.raises(hj.HjError, match="segment"):
+        g2.run()
+    # KernelOp::Index as a value is the position in the RANK's segment there: refused
+    bad, _ = _wavefront_passes(n, index_as_value=True)
+    g3 = hj.PreparedGraph(dev, bad, [ba, bm, bidx, bcnt], descs, comm=comm, placement=[S, S, S, R], seeds=[None, None, bseed, None])
+    with pytest.raises(hj.HjError, match="Index is used as a value"):
+        g3.run()
+    # a device op over a segment: refused
+    red = [{"kind": hj.PASS_COMPRESS, "resources": [2, 3, 1]}, {"kind": hj.PASS_REDUCE, "arg": hj.MAX, "resources": [3, 2]}]
+    g4 = hj.PreparedGraph(dev, red, [ba, bm, bidx, bcnt], descs, comm=comm, placement=[S, S, S, R], seeds=[None, None, bseed, None])
+    with pytest.raises(hj.HjError, match="compacted segment"):
+        g4.run()
+
+
+def _traced_wavefront(rank, world, dev, comm, n):
+    """jit/test.rs:1020-1062 (`example`) over sharded arrays, traced: indices = mask.compress_dyn();
+    b = a.gather(indices) * 0.9; (b > 0.1).scatter(mask, indices); b.scatter(a, indices) — recorded once,
+    launched again and again; the compacted indices stay per-rank segments."""
+    tr = importlib.import_module("hephaestus-jit_b200.tr")
+    rec = importlib.import_module("hephaestus-jit_b200.record")
+    sh = importlib.import_module("hephaestus-jit_b200.sharded")
+    F32 = hj.F32
+    s, e = sh.shard_bounds(n, world, rank)
+    a0 = np.random.Generator(np.random.PCG64(6)).random(n, dtype=np.float32)
+    steps = 10
+    history = _wavefront_reference(a0, steps)
+    a = tr.array_sharded(a0, comm)
+    mask = tr.array_sharded(np.ones(n, np.bool_), comm)
+    # traced and launched step by step: `indices` is a live DynSize variable, to_vec reads the rank's own count
+    for it, (idx, want_a, alive) in enumerate(history[:5]):
+        indices = mask.compress_dyn()
+        b = a.gather(indices).mul(tr.literal(0.9, F32))
+        b.gt(tr.literal(0.1, F32)).scatter(mask, indices)
+        b.scatter(a, indices)
+        a.schedule()
+        indices.schedule()
+        tr.compile().launch(dev)
+        lo, hi = np.searchsorted(idx, s), np.searchsorted(idx, e)
+        assert indices.is_segment() and indices.shard() == (s, hi - lo, False), (it, indices.shard())
+        assert np.array_equal(indices.to_vec(np.uint32), idx[lo:hi]), it   # the rank's part of the compacted sequence
+        assert np.array_equal(a.to_vec(np.float32), want_a[s:e]), it
+        assert np.array_equal(mask.to_vec(np.uint8).astype(bool), alive[s:e]), it
+        del indices, b
+    # recorded once, relaunched (record.rs:93-210); outputs of a recorded function have a static extent
+    # (graph.rs:345: Extent::Size(desc.size)): the index output is the block with its zero tail
+    calls = []
+
+    def step():
+        calls.append(1)
+        indices = mask.compress_dyn()
+        b = a.gather(indices).mul(tr.literal(0.9, F32))
+        b.gt(tr.literal(0.1, F32)).scatter(mask, indices)
+        b.scatter(a, indices)
+        a.schedule()
+        return [indices]
+
+    f = rec.record(step)
+    for it, (idx, want_a, alive) in enumerate(history[5:]):
+        (indices,), _ = f(dev)
+        lo, hi = np.searchsorted(idx, s), np.searchsorted(idx, e)
+        got = indices.to_vec(np.uint32)
+        assert indices.is_segment() and len(got) == e - s, it
+        assert np.array_equal(got[: hi - lo], idx[lo:hi]) and (got[hi - lo:] == 0).all(), it
+        assert np.array_equal(a.to_vec(np.float32), want_a[s:e]), it
+        assert np.array_equal(mask.to_vec(np.uint8).astype(bool), alive[s:e]), it
+        del indices
+    assert len(calls) == 1, "traced once"
+    assert not a.is_segment() and a.shard() == (s, e - s, False)
+
+
+@pytest.mark.parametrize("world", [1, 2, 3])
+def test_wavefront_pass_list_runs_per_segment(world):
+    _run(world, "_wavefront_pass_list", (1 << 18) + 33)
+
+
+@pytest.mark.parametrize("world", [1, 2, 3])
+def test_traced_wavefront_over_sharded_arrays(world):
+    _run(world, "_traced_wavefront", (1 << 18) + 5)
+
+
 @pytest.mark.parametrize("world", [1, 2])
 def test_recorded_function_over_sharded_inputs(world):
     _run(world, "_recorded_sharded_function", (1 << 19) + 77)
