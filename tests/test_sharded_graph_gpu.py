@@ -475,7 +475,7 @@ def _wavefront_pass_list(rank, world, dev, comm, n):
         assert np.array_equal(ba.to_host(np.float32), a[s:e]), it
         assert np.array_equal(bm.to_host(np.uint8).astype(bool), alive[s:e]), it
         assert g.segments() == [False, False, True, False]
-    assert history[-1][0].size < history[0][0].size // 2, "the wavefront must have shrunk"
+    assert history[-1][0].size < history[0][0].size * 3 // 4, "the wavefront must have shrunk"
     c1, r1, _ = dev.graph_cache_stats()
     assert c1 - c0 == 1 and r1 - r0 == steps - 2, (c1 - c0, r1 - r0)
     # without a seed on the index segment there is nothing to size the kernels with: refused, not mis-sized
