@@ -15,6 +15,7 @@ execute on the GPU through hj_execute_graph.
 from __future__ import annotations
 
 import ctypes
+import struct as _struct
 
 import numpy as np
 
@@ -29,10 +30,19 @@ from ._lib import check, lib
 U_CAST, U_BITCAST, U_NEG, U_SQRT, U_ABS, U_SIN, U_COS, U_EXP2, U_LOG2 = range(9)
 
 _u64 = ctypes.c_uint64
+_PACK = {BOOL: _struct.Struct("<?"), I8: _struct.Struct("<b"), U8: _struct.Struct("<B"), I16: _struct.Struct("<h"),
+         U16: _struct.Struct("<H"), I32: _struct.Struct("<i"), U32: _struct.Struct("<I"), I64: _struct.Struct("<q"),
+         U64: _struct.Struct("<Q"), F16: _struct.Struct("<e"), F32: _struct.Struct("<f"), F64: _struct.Struct("<d")}
 
 
 def _bits(value, ty: int) -> int:
     """The u64 the reference stores for a literal (trace.rs:604-606: the value's bytes, zero padded)."""
+    fmt = _PACK.get(ty)
+    if fmt is not None and type(value) in (int, float, bool):  # plain Python scalars: no numpy round trip
+        try:
+            return int.from_bytes(fmt.pack(value), "little")
+        except (_struct.error, OverflowError, TypeError):
+            pass  # out of range / float into an integer type: numpy's conversion rules decide
     a = np.array([value], dtype=_NP[ty])
     return int.from_bytes(a.tobytes().ljust(8, b"\0"), "little")
 
@@ -154,7 +164,8 @@ class VarRef:
 
     # -- elementwise (trace.rs:968-1082) ------------------------------------------------------
     def _bop(self, op: int, rhs) -> "VarRef":
-        rhs = _into(rhs, self.ty())
+        if not isinstance(rhs, VarRef):  # the type is only needed to turn a plain value into a literal
+            rhs = _into(rhs, self.ty())
         out = _u64()
         check(lib.hj_tr_bop(op, self._id, rhs._id, ctypes.byref(out)))
         return VarRef(out.value)
@@ -202,14 +213,18 @@ class VarRef:
         return VarRef(out.value)
 
     def fma(self, b, c) -> "VarRef":
-        b, c = _into(b, self.ty()), _into(c, self.ty())
+        if not (isinstance(b, VarRef) and isinstance(c, VarRef)):
+            ty = self.ty()
+            b, c = _into(b, ty), _into(c, ty)
         out = _u64()
         check(lib.hj_tr_fma(self._id, b._id, c._id, ctypes.byref(out)))
         return VarRef(out.value)
 
     def select(self, condition, false_val) -> "VarRef":
         """``true_val.select(&cond, &false_val)`` (trace.rs:1483-1504)."""
-        condition, false_val = _into(condition, BOOL), _into(false_val, self.ty())
+        condition = _into(condition, BOOL)
+        if not isinstance(false_val, VarRef):
+            false_val = _into(false_val, self.ty())
         out = _u64()
         check(lib.hj_tr_select(self._id, condition._id, false_val._id, ctypes.byref(out)))
         return VarRef(out.value)
