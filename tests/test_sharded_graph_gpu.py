@@ -361,6 +361,32 @@ def _random_sharded_programs(rank, world, dev, comm, n, n_programs, seed):
                                  small * np.uint32(2) + np.uint32(1)))
                 else:           # min / max reductions of a (possibly deferred) value
                     terminal.append(("reduce", va.reduce_max(), None, a.max()))
+        # every other program also takes a wavefront step: compact one of its masks, update the selected
+        # elements of a sharded array in place through the compacted indices (a DynSize kernel per segment)
+        wave = random.Random(seed * 7919 + prog)
+        if wave.random() < 0.6:
+            vm, m = wave.choice(bools)
+            sel = np.flatnonzero(m).astype(np.uint32)
+            d0 = data_rng.integers(0, 1 << 16, size=n).astype(np.uint32)
+            dst = tr.array_sharded(d0, comm)
+            idx = vm.compress_dyn()
+            with np.errstate(over="ignore"):
+                variant = wave.randrange(3)
+                if variant == 0:    # dst[i] = 3 dst[i] + table[i & 1023]
+                    val = dst.gather(idx).mul(tr.literal(3, U32)).add(table.gather(idx.and_(tr.literal(1023, U32))))
+                    want_d = d0.copy()
+                    want_d[sel] = d0[sel] * np.uint32(3) + table_np[sel & np.uint32(1023)]
+                elif variant == 1:  # dst[i] = a0[i] ^ b0[i] + i: two other sharded arrays and the index value itself
+                    val = pool[0][0].gather(idx).xor(pool[1][0].gather(idx)).add(idx)
+                    want_d = d0.copy()
+                    want_d[sel] = (a0[sel] ^ b0[sel]) + sel
+                else:               # dst[i] = min(dst[i], a0[i])
+                    val = dst.gather(idx).min(pool[0][0].gather(idx))
+                    want_d = d0.copy()
+                    want_d[sel] = np.minimum(d0[sel], a0[sel])
+            val.scatter(dst, idx)
+            terminal.append(("scatter", dst, None, want_d))
+            del idx, val
         outs = [pool[-1], rnd.choice(pool[3:] or pool)]
         for v, _ in outs:
             v.schedule()
@@ -376,6 +402,8 @@ def _random_sharded_programs(rank, world, dev, comm, n, n_programs, seed):
         for t in terminal:
             if t[0] == "reduce":
                 assert int(t[1].item(np.uint32)) == int(t[3]), ctx
+            elif t[0] == "scatter":
+                assert np.array_equal(t[1].to_vec(np.uint32), t[3][s:e]), ctx + " (wavefront step)"
             else:
                 _, cnt, idx, m = t
                 sel = np.flatnonzero(m).astype(np.uint32)
