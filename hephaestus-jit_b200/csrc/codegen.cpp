@@ -718,7 +718,10 @@ bool codegen_cuda(const hj_ir* ir, CodegenResult* out, std::string* err) {
     // early, and touch no global memory before the kernel in front has completed
     s << "#define HJ_SIZE() asm volatile(\"griddepcontrol.launch_dependents;\" ::: \"memory\"); "
          "asm volatile(\"griddepcontrol.wait;\" ::: \"memory\"); "
-         "u32 size = size_static; if (size_ptr) { u32 dyn = *size_ptr; size = dyn < size ? dyn : size; }\n\n";
+         "u32 size = size_static; if (size_ptr) { u32 dyn = *size_ptr; size = dyn < size ? dyn : size; "
+         // a segment kernel of the sharded pass interpreter: the position of the rank's segment in the global
+         // compacted sequence is only known on the device (it sits behind the count)
+         "if (index_base == 0xffffffffu) index_base = size_ptr[1]; }\n\n";
     // one invocation per element; `if (index >= size) return;` (glsl/mod.rs:129-133)
     s << "extern \"C\" __global__ void __launch_bounds__(" << threads << ") hj_kernel_scalar(" << params << ") {\n"
       << "    HJ_SIZE();\n"

@@ -119,6 +119,18 @@ __global__ void offsets_kernel(const T* gathered, int rank, int world, T* seed, 
     }
 }
 
+// What sizes and places the DynSize kernels that run over this rank's segment of a sharded compaction:
+// seg[0] = the rank's own count, seg[1] = the counts of the ranks before it (where the segment starts in
+// the global compacted sequence — KernelOp::Index of those kernels, codegen.cpp: HJ_SIZE)
+__global__ void segment_seed_kernel(const uint32_t* counts, int rank, uint32_t* seg) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        uint32_t before = 0;
+        for (int q = 0; q < rank; q++) before += counts[q];
+        seg[0] = counts[rank];
+        seg[1] = before;
+    }
+}
+
 // dst[i] = fold over ranks (in rank order) of all[q * n + i]
 template <typename T, int OP>
 __global__ void fold_ranks_kernel(const T* all, size_t n, int world, T* dst) {
@@ -505,14 +517,15 @@ namespace hj {
 hj_status sharded_compress_pass(hj_comm* c, size_t n_local, uint32_t index_base, hj_buffer* mask, hj_buffer* index_out,
                                 hj_buffer* out_count, bool zero_tail, hj_buffer* local_count) {
     HJ_REQUIRE(c->connected, "communicator is not connected yet (hj_comm_connect)");
-    HJ_REQUIRE(!local_count || local_count->bytes >= 4, "sharded compress: the local-count buffer is smaller than 4 bytes");
+    HJ_REQUIRE(!local_count || local_count->bytes >= 8, "sharded compress: the segment's seed buffer is smaller than 8 bytes");
     DeviceGuard g(c->dev);
     HJ_TRY(sharded_compress(c, n_local, index_base, (const uint8_t*)mask->ptr, (uint32_t*)index_out->ptr,
                             (uint32_t*)out_count->ptr, nullptr, zero_tail));
     // every path of sharded_compress leaves the per-rank counts in the communicator's scratch
-    if (local_count)
-        HJ_CUDA(cudaMemcpyAsync(local_count->ptr, (const uint32_t*)gathered_slot(c) + c->rank, 4, cudaMemcpyDeviceToDevice,
-                                c->dev->stream));
+    if (local_count) {
+        segment_seed_kernel<<<1, 32, 0, c->dev->stream>>>((const uint32_t*)gathered_slot(c), c->rank, (uint32_t*)local_count->ptr);
+        HJ_TRY(check_launch(c->dev, "segment_seed_kernel"));
+    }
     return HJ_OK;
 }
 }  // namespace hj

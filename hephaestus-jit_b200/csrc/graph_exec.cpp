@@ -355,7 +355,7 @@ hj_status execute_passes(hj_device* dev, const ShardCtx* sc, const hj_pass* pass
         for (uint32_t c = 0; c < p.n_resources && seg_slot == p.n_resources; c++) {
             const uint32_t crid = p.resources[c];
             if (!sharded(crid) || sc->shards[crid].deferred != HJ_SHARD_SEGMENT || !sc->shards[crid].seed ||
-                descs[crid].ty != HJ_U32 || descs[crid].size != p.size)
+                sc->shards[crid].seed->bytes < 8 || descs[crid].ty != HJ_U32 || descs[crid].size != p.size)
                 continue;
             if (!analyse_segment_access(p.ir, c, &acc, &why)) continue;
             bool ok = true;
@@ -405,13 +405,16 @@ hj_status execute_passes(hj_device* dev, const ShardCtx* sc, const hj_pass* pass
         }
         hj_kernel* k = nullptr;
         HJ_TRY(hj_kernel_get(dev, p.ir, &k));
-        hj_status s = kernel_launch_shifted(dev, k, (size_t)cnt, sc->shards[seg_rid].seed, bufs.data(), (uint32_t)bufs.size(), 0, shift.data());
+        // index_base = 0xffffffff: KernelOp::Index = seed[1] + local position, the position in the GLOBAL compacted
+        // sequence (codegen.cpp: HJ_SIZE reads it behind the count)
+        hj_status s = kernel_launch_shifted(dev, k, (size_t)cnt, sc->shards[seg_rid].seed, bufs.data(), (uint32_t)bufs.size(),
+                                            0xffffffffu, shift.data());
         hj_kernel_release(k);
         HJ_TRY(s);
         for (uint32_t b : born) {
             hj_shard_desc& sd = sc->shards[p.resources[b]];
-            HJ_REQUIRE(sd.seed->bytes >= 4, "kernel pass %u: the seed buffer of resource %u is smaller than 4 bytes", i, p.resources[b]);
-            HJ_CUDA(cudaMemcpyAsync(sd.seed->ptr, sc->shards[seg_rid].seed->ptr, 4, cudaMemcpyDeviceToDevice, dev->stream));
+            HJ_REQUIRE(sd.seed->bytes >= 8, "kernel pass %u: the seed buffer of resource %u is smaller than 8 bytes", i, p.resources[b]);
+            HJ_CUDA(cudaMemcpyAsync(sd.seed->ptr, sc->shards[seg_rid].seed->ptr, 8, cudaMemcpyDeviceToDevice, dev->stream));
             sd.deferred = HJ_SHARD_SEGMENT;
         }
         return HJ_OK;
@@ -660,8 +663,9 @@ hj_status execute_passes(hj_device* dev, const ShardCtx* sc, const hj_pass* pass
                            "compress pass %u: the mask is a per-rank segment, not a block of a sharded array", i);
                 // the rank's own count stays beside the segment: it sizes the DynSize kernels that run over it
                 hj_shard_desc& seg = sc->shards[p.resources[0]];
-                HJ_TRY(sharded_compress_pass(sc->comm, (size_t)cnt, (uint32_t)s0, src, index_out, out_count, zt, seg.seed));
-                seg.deferred = seg.seed ? HJ_SHARD_SEGMENT : HJ_SHARD_PLAIN;
+                hj_buffer* seg_seed = seg.seed && seg.seed->bytes >= 8 ? seg.seed : nullptr;
+                HJ_TRY(sharded_compress_pass(sc->comm, (size_t)cnt, (uint32_t)s0, src, index_out, out_count, zt, seg_seed));
+                seg.deferred = seg_seed ? HJ_SHARD_SEGMENT : HJ_SHARD_PLAIN;
             } else if (zt) {
                 const size_t n = dsrc->size;
                 HJ_REQUIRE(n >= 1 && n <= src->bytes && n * 4 <= index_out->bytes && out_count->bytes >= 4 &&

@@ -199,8 +199,8 @@ hj_status launch_fill(hj_device* dev, void* dst, size_t n, size_t elem_bytes, ui
 
 // comm.cu internals used by the sharded pass interpreter (graph_exec.cpp)
 hj_device* comm_device(hj_comm* c);
-// `local_count` (optional, >= 4 bytes): receives this rank's own count (what sizes the DynSize kernels that
-// run over the rank's segment)
+// `local_count` (optional, >= 8 bytes): receives this rank's own count and the counts of the ranks before it
+// (what sizes the DynSize kernels that run over the rank's segment, and their KernelOp::Index)
 hj_status sharded_compress_pass(hj_comm* c, size_t n_local, uint32_t index_base, hj_buffer* mask, hj_buffer* index_out,
                                 hj_buffer* out_count, bool zero_tail, hj_buffer* local_count = nullptr);
 

@@ -77,11 +77,6 @@ bool analyse_segment_access(const hj_ir* ir, uint32_t seg_slot, std::vector<Segm
         case HJ_OP_SCATTER: case HJ_OP_SCATTER_REDUCE: case HJ_OP_SCATTER_ATOMIC: idx_pos = 2; break;
         default: break;
         }
-        for (uint32_t k = 0; k < v.n_deps(i); k++)
-            if (is_index(v.dep(i, k)) && (int)k != idx_pos) {
-                if (why) *why = "KernelOp::Index is used as a value (var " + std::to_string(i) + ")";
-                return false;
-            }
         if (idx_pos < 0) continue;
         const hj_ir_var& buf = v.var(v.dep(i, 0));
         if (buf.op != HJ_OP_BUFFER_REF || buf.data >= ir->n_buffers) continue;

@@ -60,8 +60,8 @@ struct SegmentAccess {
     bool through_segment = true;  // every access index is Gather(BufferRef(seg_slot), Index [, literal true])
 };
 // false (+ why) when the kernel cannot run per segment: the segment is written or not read at the bare
-// Index, or KernelOp::Index is used as a value (it is the position in the RANK's segment there, not the
-// position in the global compacted sequence).  `ir` must have passed validate_ir.
+// Index.  (KernelOp::Index as a VALUE is the position in the global compacted sequence: the launcher hands
+// the kernel the rank's offset through the count buffer, codegen.cpp: HJ_SIZE.)  `ir` must have passed validate_ir.
 bool analyse_segment_access(const hj_ir* ir, uint32_t seg_slot, std::vector<SegmentAccess>* out, std::string* why);
 
 // vartype.rs:125-189

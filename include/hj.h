@@ -425,20 +425,22 @@ hj_status hj_sharded_rebalance(hj_comm* comm, size_t elem_bytes, hj_buffer* src,
  *                                  arrays of the mask's extent are addressed through them in place.  Needs
  *                                  a seed buffer on the index segment (it receives the rank's count).
  * Not sharded (SURVEY 8e "replicas only"): access to a sharded resource through any other computed
- * index, writes to a replica from a sharded kernel, KernelOp::Index used as a VALUE inside a segment
- * kernel (it is the position in the rank's segment there), device ops over a segment
- * -> HJ_ERR_UNSUPPORTED. */
+ * index, writes to a replica from a sharded kernel, a replica read at the bare Index inside a segment
+ * kernel, device ops over a segment -> HJ_ERR_UNSUPPORTED.  (KernelOp::Index as a VALUE inside a segment
+ * kernel is the position in the GLOBAL compacted sequence, as on one GPU: the rank's offset sits behind
+ * its count in the seed buffer.) */
 typedef enum { HJ_RES_REPLICATED = 0, HJ_RES_SHARDED = 1, HJ_RES_AUTO = 2 } hj_placement;
 /* values of hj_shard_desc.deferred */
 #define HJ_SHARD_PLAIN 0u    /* the buffer holds the rank's block as it is */
 #define HJ_SHARD_DEFERRED 1u /* a LOCAL scan: the global value of element i is buffer[i] + seed[0] */
 #define HJ_SHARD_SEGMENT 2u  /* a per-rank compacted SEGMENT (Compress index output, or what a DynSize
-                                kernel wrote at Index): only the first seed[0] (u32) entries are defined */
+                                kernel wrote at Index): only the first seed[0] (u32) entries are defined;
+                                seed[1] (u32) = entries of the ranks before this one */
 typedef struct {
     uint32_t placement; /* hj_placement.  SHARDED: the buffer holds this rank's block
                            [start, end) = hj_shard_bounds(descs[i].size, world, rank) of the global array */
     uint32_t deferred;  /* in / out, SHARDED resources: HJ_SHARD_PLAIN / _DEFERRED / _SEGMENT */
-    hj_buffer* seed;    /* >= 4 bytes (one element of the resource's type for a scan) on the device, or
+    hj_buffer* seed;    /* >= 8 bytes (one element of the resource's type for a scan; two u32 for a segment) on the device, or
                            NULL (then PrefixSum results are always materialised and a Compress index
                            segment cannot size dependent DynSize kernels) */
 } hj_shard_desc;

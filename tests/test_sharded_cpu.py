@@ -174,8 +174,8 @@ def _wavefront_passes(n, index_as_value=False, conditional=False):
         active = b.bop(irm.BOP_LT, bl, i, b.literal(hj.U32, 7)) if conditional else b.literal(hj.BOOL, 1)
         idx = b.gather(u32, rindex, i, active)
         v = b.bop(irm.BOP_MUL, f32, b.gather(f32, ra, idx), b.literal(hj.F32, 0.9))
-        if index_as_value:
-            v = b.bop(irm.BOP_ADD, f32, v, b.uop(irm.UOP_CAST, f32, i))
+        if index_as_value:   # the value is the position in the compacted sequence
+            v = b.uop(irm.UOP_CAST, f32, i)
         if write_mask:
             b.scatter(b.buffer_ref(bl), b.bop(irm.BOP_GT, bl, v, b.literal(hj.F32, 0.1)), idx)
         else:
@@ -200,11 +200,13 @@ def test_shard_plan_places_the_wavefront_step():
     assert sharded.shard_plan(passes, descs, [A, S, A, A]) == [S, S, S, R]
     assert sharded.shard_plan(passes, descs, [S, S, A, A]) == [S, S, S, R]
     assert sharded.shard_plan(passes, descs, [A, A, A, A]) == [R, R, R, R]
-    # Index used as a value, or a conditional read of the segment: not a segment kernel, `a` stays undecided
-    # (a replica), and the launch then refuses the pass instead of computing something else
-    for kw in ({"index_as_value": True}, {"conditional": True}):
-        passes, descs = _wavefront_passes(1 << 16, **kw)
-        assert sharded.shard_plan(passes, descs, [A, S, A, A]) == [R, S, S, R]
+    # KernelOp::Index as a value (the position in the global compacted sequence) is fine
+    passes, descs = _wavefront_passes(1 << 16, index_as_value=True)
+    assert sharded.shard_plan(passes, descs, [A, S, A, A]) == [S, S, S, R]
+    # a conditional read of the segment: not a segment kernel, `a` stays undecided (a replica), and the
+    # launch then refuses the pass instead of computing something else
+    passes, descs = _wavefront_passes(1 << 16, conditional=True)
+    assert sharded.shard_plan(passes, descs, [A, S, A, A]) == [R, S, S, R]
 
 
 def test_shard_plan_rejects_malformed_pass_lists():

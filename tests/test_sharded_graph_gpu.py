@@ -463,13 +463,14 @@ def _recorded_sharded_function(rank, world, dev, comm, n):
     assert c1 - c0 >= 1 and r1 - r0 >= 1, (c0, r0, c1, r1)
 
 
-def _wavefront_reference(a0, steps):
-    """The wavefront loop on the whole array: lanes alive in `mask` are scaled and stay alive while > 0.1."""
+def _wavefront_reference(a0, steps, index_as_value=False):
+    """The wavefront loop on the whole array: lanes alive in `mask` are scaled and stay alive while > 0.1
+    (index_as_value: they take their position in the compacted sequence instead)."""
     a, alive = a0.copy(), np.ones(a0.size, bool)
     history = []
     for _ in range(steps):
         idx = np.flatnonzero(alive).astype(np.uint32)
-        v = a[idx] * np.float32(0.9)
+        v = np.arange(idx.size, dtype=np.float32) if index_as_value else a[idx] * np.float32(0.9)
         alive[idx] = v > np.float32(0.1)
         a[idx] = v
         history.append((idx, a.copy(), alive.copy()))
@@ -510,11 +511,22 @@ def _wavefront_pass_list(rank, world, dev, comm, n):
     g2 = hj.PreparedGraph(dev, passes, [ba, bm, bidx, bcnt], descs, comm=comm, placement=[S, S, S, R])
     with pytest.raises(hj.HjError, match="segment"):
         g2.run()
-    # KernelOp::Index as a value is the position in the RANK's segment there: refused
-    bad, _ = _wavefront_passes(n, index_as_value=True)
+    # a conditional read of the segment (an inactive lane would address element 0 of another rank's block): refused
+    bad, _ = _wavefront_passes(n, conditional=True)
     g3 = hj.PreparedGraph(dev, bad, [ba, bm, bidx, bcnt], descs, comm=comm, placement=[S, S, S, R], seeds=[None, None, bseed, None])
-    with pytest.raises(hj.HjError, match="Index is used as a value"):
+    with pytest.raises(hj.HjError, match="segment"):
         g3.run()
+    # KernelOp::Index as a VALUE is the position in the global compacted sequence, as on one GPU
+    ba2, bm2 = dev.create_buffer_from_slice(a0[s:e]), dev.create_buffer_from_slice(np.ones(nl, np.uint8))
+    byidx, _ = _wavefront_passes(n, index_as_value=True)
+    g5 = hj.PreparedGraph(dev, byidx, [ba2, bm2, bidx, bcnt], descs, comm=comm, placement=[S, S, S, R],
+                          seeds=[None, None, bseed, None])
+    for it, (idx, a, alive) in enumerate(_wavefront_reference(a0, 3, index_as_value=True)):
+        g5.run()
+        lo, hi = np.searchsorted(idx, s), np.searchsorted(idx, e)
+        assert list(bseed.to_host(np.uint32, 0, 2)) == [hi - lo, lo], it
+        assert np.array_equal(ba2.to_host(np.float32), a[s:e]), it
+        assert np.array_equal(bm2.to_host(np.uint8).astype(bool), alive[s:e]), it
     # a device op over a segment: refused
     red = [{"kind": hj.PASS_COMPRESS, "resources": [2, 3, 1]}, {"kind": hj.PASS_REDUCE, "arg": hj.MAX, "resources": [3, 2]}]
     g4 = hj.PreparedGraph(dev, red, [ba, bm, bidx, bcnt], descs, comm=comm, placement=[S, S, S, R], seeds=[None, None, bseed, None])
@@ -576,6 +588,19 @@ def _traced_wavefront(rank, world, dev, comm, n):
         del indices
     assert len(calls) == 1, "traced once"
     assert not a.is_segment() and a.shard() == (s, e - s, False)
+    # KernelOp::Index as a value inside the DynSize kernel: the position in the GLOBAL compacted sequence,
+    # as on one GPU (trace.rs:578-597 dynamic_index) — every surviving lane takes its rank in the wavefront
+    alive = history[-1][2]
+    sel = np.flatnonzero(alive).astype(np.uint32)
+    count, index = mask.compress()
+    j = tr.dynamic_index(n, count)
+    j.cast(F32).scatter(a, index.gather(j))
+    a.schedule()
+    tr.compile().launch(dev)
+    want = history[-1][1].copy()
+    want[sel] = np.arange(sel.size, dtype=np.float32)
+    assert int(count.to_vec(np.uint32)[0]) == sel.size
+    assert np.array_equal(a.to_vec(np.float32), want[s:e])
 
 
 @pytest.mark.parametrize("world", [1, 2, 3])
