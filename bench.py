@@ -62,6 +62,10 @@ WORKLOAD = ("C2+C3+C4 as one pass list: fused chain fma -> sin/exp2 -> select ov
             "f32 sum over 2^30, inclusive u32 scan over 2^30, compress of a 2^30-byte mask (p=0.5)")
 
 
+WAVEFRONT_NAME = ("C5 wavefront step 2^28 lanes, half alive: Compress + 2 DynSize kernels through the compacted indices "
+                  "(n + 25 count bytes)")
+
+
 def step_bytes(n_map: int, n_ops: int, count: int) -> dict:
     """Algorithmic bytes of one step per kernel."""
     return {"map": 8 * n_map, "reduce": 4 * n_ops, "scan": 8 * n_ops, "compress": n_ops + 4 * count}
@@ -362,9 +366,59 @@ def run_suite(torch, hj, dev, peak, world, rank):
             del count, index, cgraph, mvar, mask_t
         except Exception as exc:  # an extra line of the suite must never take the bench down
             out["C4 traced mask.compress() p=0.5 2^28 (zero-fill + Compress passes)"] = {"error": str(exc)[:200]}
+        try:
+            ms, nbytes, ok = wavefront_step(torch, hj, dev, None, 1, 0, lambda fn: timed_events(torch, fn, iters, 3),
+                                            lambda flag: bool(flag), lambda v: int(v))
+            out[WAVEFRONT_NAME] = entry(nbytes, ms, {"check": ok, "bytes_per_lane": round(nbytes / (1 << 28), 2)})
+        except Exception as exc:
+            out[WAVEFRONT_NAME] = {"error": str(exc)[:300]}
     if world > 1:
         out["_note"] = f"per-GPU share (1/{world}) of each array, local kernels only; the exchanges are in the headline step and under 'sharded'"
     return out
+
+
+def wavefront_step(torch, hj, dev, comm, world, rank, timed, all_true, all_sum):
+    """The wavefront step of the reference's `example` (jit/test.rs:1020-1062) at 2^28 lanes, half of them alive:
+    Compress of the mask + the two DynSize kernels sized by its count (gather / scatter through the compacted
+    indices).  With a communicator every rank runs the kernels over its own segment; the pass list
+    replays as one CUDA graph.  Returns (ms, algorithmic bytes of the whole job, verified?)."""
+    irm = importlib.import_module("hephaestus-jit_b200.ir")
+    sh = importlib.import_module("hephaestus-jit_b200.sharded")
+    n = 1 << 28
+    s, e = sh.shard_bounds(n, world, rank)
+    nl = e - s
+    g = torch.Generator(device="cuda").manual_seed(99 + rank)
+    wrap = lambda t: dev.wrap(t.data_ptr(), t.numel() * t.element_size())
+    a = torch.rand(nl, device="cuda", generator=g, dtype=torch.float32)
+    mask = (torch.rand(nl, device="cuda", generator=g) < 0.5).to(torch.uint8)
+    a0, m0 = a.clone(), mask.clone()
+    index = torch.zeros(nl, device="cuda", dtype=torch.int32)
+    count = torch.zeros(1, device="cuda", dtype=torch.int32)
+    seed = torch.zeros(4, device="cuda", dtype=torch.int32)
+    passes, descs = irm.wavefront_step_passes(n, threshold=-1.0)   # every alive lane stays alive: the same work each step
+    S, R = sh.RES_SHARDED, sh.RES_REPLICATED
+    graph = hj.PreparedGraph(dev, passes, [wrap(a), wrap(mask), wrap(index), wrap(count)], descs, comm=comm,
+                             placement=[S, S, S, R] if comm is not None else None,
+                             seeds=[None, None, wrap(seed), None] if comm is not None else None, graph_key=0x3A7EF207)
+    runs = [0]
+
+    def step():
+        graph.run()
+        runs[0] += 1
+
+    ms = timed(step)
+    torch.cuda.synchronize()
+    alive = m0.bool()
+    want = a0.clone()
+    for _ in range(runs[0]):
+        want[alive] = want[alive] * 0.9
+    c_local = int(alive.sum().item())
+    c_global = all_sum(c_local)
+    ok = bool(torch.equal(a, want)) and bool(torch.equal(mask, m0)) and (int(count.item()) & 0xFFFFFFFF) == c_global
+    ok = ok and bool(torch.equal(index[:c_local].long(), torch.nonzero(alive).flatten() + s))
+    if comm is not None:
+        ok = ok and (int(seed[0].item()), graph.segments()[2]) == (c_local, True)
+    return ms, n + 25 * c_global, all_true(ok)
 
 
 def run_sharded_extras(torch, dist, hj, dev, comm, peak, world, rank):
@@ -428,6 +482,16 @@ def run_sharded_extras(torch, dist, hj, dev, comm, peak, world, rank):
     out["C4 sharded inclusive scan u32 2^30, MATERIALISED (totals pass + seeded scan: 12 B/elem moved, 8 credited)"] = entry(
         8 * n30 * world, ms, all_true(ok))
     del xu, on
+    try:
+        def all_sum(v: int) -> int:
+            t = torch.tensor([v], device=COLL_DEVICE, dtype=torch.int64)
+            dist.all_reduce(t)
+            return int(t.item())
+
+        ms, nbytes, ok = wavefront_step(torch, hj, dev, comm, world, rank, timed, all_true, all_sum)
+        out[WAVEFRONT_NAME] = entry(nbytes, ms, ok)
+    except Exception as exc:  # an extra line must never take the bench down
+        out[WAVEFRONT_NAME] = {"error": str(exc)[:300]}
     return out
 
 

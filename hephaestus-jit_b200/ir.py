@@ -175,3 +175,37 @@ def c2_chain_ir() -> IRBuilder:
     y_ref = b.buffer_ref(f32)
     b.scatter(y_ref, y, idx)
     return b
+
+
+def wavefront_step_passes(n: int, index_as_value: bool = False, conditional: bool = False, threshold: float = 0.1):
+    """The wavefront step of the reference's `example` (jit/test.rs:1020-1062) as the pass list Graph::compile
+    produces for it: Compress(index, count, mask), then two DynSize kernels sized by `count` —
+    ``mask[idx] = a[idx] * 0.9 > threshold`` and ``a[idx] = a[idx] * 0.9`` with ``idx = index[Index]``.
+    Resources: 0 a (f32), 1 mask (bool), 2 index (u32), 3 count (u32, one element).  ``index_as_value``: the
+    lanes take their position in the compacted sequence instead; ``conditional``: the index is read under a
+    condition (what a sharded launch must refuse).  Returns ``(passes, descs)``."""
+    from . import PASS_COMPRESS, PASS_KERNEL
+
+    def step(write_mask: bool) -> IRBuilder:
+        b = IRBuilder()
+        f32, u32, bl = b.scalar(F32), b.scalar(U32), b.scalar(BOOL)
+        ra, rindex = b.buffer_ref(f32), b.buffer_ref(u32)
+        i = b.index()
+        active = b.bop(BOP_LT, bl, i, b.literal(U32, 7)) if conditional else b.literal(BOOL, 1)
+        idx = b.gather(u32, rindex, i, active)
+        v = b.bop(BOP_MUL, f32, b.gather(f32, ra, idx), b.literal(F32, 0.9))
+        if index_as_value:
+            v = b.uop(UOP_CAST, f32, i)
+        if write_mask:
+            b.scatter(b.buffer_ref(bl), b.bop(BOP_GT, bl, v, b.literal(F32, threshold)), idx)
+        else:
+            b.scatter(ra, v, idx)
+        return b
+
+    passes = [
+        {"kind": PASS_COMPRESS, "resources": [2, 3, 1]},
+        {"kind": PASS_KERNEL, "resources": [0, 2, 1], "ir": step(True), "size": n, "size_buffer": 3},
+        {"kind": PASS_KERNEL, "resources": [0, 2], "ir": step(False), "size": n, "size_buffer": 3},
+    ]
+    descs = [(n, F32, 4), (n, BOOL, 1), (n, U32, 4), (1, U32, 4)]
+    return passes, descs

@@ -161,35 +161,9 @@ def test_shard_plan_propagates_placement():
 
 
 def _wavefront_passes(n, index_as_value=False, conditional=False):
-    """The wavefront step of jit/test.rs:1020-1062 as a pass list: Compress, then two DynSize kernels sized by
-    its count — new_mask[idx] = a[idx] * 0.9 > 0.1 and a[idx] *= 0.9 with idx = index[Index]."""
-    hj = importlib.import_module("hephaestus-jit_b200")
+    """Compress + the two DynSize kernels of the wavefront step (hephaestus-jit_b200/ir.py)."""
     irm = importlib.import_module("hephaestus-jit_b200.ir")
-
-    def step(write_mask):
-        b = irm.IRBuilder()
-        f32, u32, bl = b.scalar(hj.F32), b.scalar(hj.U32), b.scalar(hj.BOOL)
-        ra, rindex = b.buffer_ref(f32), b.buffer_ref(u32)
-        i = b.index()
-        active = b.bop(irm.BOP_LT, bl, i, b.literal(hj.U32, 7)) if conditional else b.literal(hj.BOOL, 1)
-        idx = b.gather(u32, rindex, i, active)
-        v = b.bop(irm.BOP_MUL, f32, b.gather(f32, ra, idx), b.literal(hj.F32, 0.9))
-        if index_as_value:   # the value is the position in the compacted sequence
-            v = b.uop(irm.UOP_CAST, f32, i)
-        if write_mask:
-            b.scatter(b.buffer_ref(bl), b.bop(irm.BOP_GT, bl, v, b.literal(hj.F32, 0.1)), idx)
-        else:
-            b.scatter(ra, v, idx)
-        return b
-
-    # resources: 0 a, 1 mask, 2 index, 3 count
-    passes = [
-        {"kind": hj.PASS_COMPRESS, "resources": [2, 3, 1]},
-        {"kind": hj.PASS_KERNEL, "resources": [0, 2, 1], "ir": step(True), "size": n, "size_buffer": 3},
-        {"kind": hj.PASS_KERNEL, "resources": [0, 2], "ir": step(False), "size": n, "size_buffer": 3},
-    ]
-    descs = [(n, hj.F32, 4), (n, hj.BOOL, 1), (n, hj.U32, 4), (1, hj.U32, 4)]
-    return passes, descs
+    return irm.wavefront_step_passes(n, index_as_value=index_as_value, conditional=conditional)
 
 
 def test_shard_plan_places_the_wavefront_step():
