@@ -54,6 +54,15 @@ def main():
         y = torch.empty_like(x)
         k = dev.kernel(irm.c2_chain_ir())
         fn = lambda: dev.launch(k, n, [wrap(x), wrap(y)])
+    elif which == "wavefront":   # Compress + the two DynSize kernels of the wavefront step, pass by pass
+        irm = importlib.import_module("hephaestus-jit_b200.ir")
+        a = torch.rand(n, device="cuda", generator=g)
+        m = (torch.rand(n, device="cuda", generator=g) < 0.5).to(torch.uint8)
+        idx = torch.zeros(n, device="cuda", dtype=torch.int32)
+        cnt = torch.zeros(1, device="cuda", dtype=torch.int32)
+        passes, descs = irm.wavefront_step_passes(n, threshold=-1.0)
+        graph = hj.PreparedGraph(dev, passes, [wrap(a), wrap(m), wrap(idx), wrap(cnt)], descs)
+        fn = graph.run
     else:
         raise SystemExit(f"unknown kernel {which}")
     for _ in range(iters):
