@@ -309,7 +309,44 @@ struct Gen {
     }
 
     // ---- body emission ------------------------------------------------------------------------
-    std::string reg(uint32_t id) { return "r" + std::to_string(id); }
+    // two-phase emission of the vector entry keeps every variable per element: `rN[e_]`
+    std::string suffix;
+    std::string reg(uint32_t id) { return "r" + std::to_string(id) + suffix; }
+
+    // Where the vector entry may cut the element body in two: the first side effect, when it sits at nesting
+    // depth 0 and a Gather in front of it reads a slot the kernel also writes.  Such a load cannot be moved
+    // across the stores of the element before it by the compiler (same buffer), so a thread that handles
+    // several elements would run load -> store -> load -> store, one memory round trip after the other.  The
+    // reference's model has one invocation per element and no order between invocations: running the part
+    // in front of the first side effect for ALL elements of the thread first, then the rest, is the same
+    // program with every gather in flight at once.  -1: no cut.
+    int split_point() {
+        int depth = 0;
+        bool rmw_gather = false;
+        for (uint32_t i = 0; i < v.n_vars(); i++) {
+            const hj_ir_var& var = v.var(i);
+            switch (var.op) {
+            case HJ_OP_LOOP_START: case HJ_OP_IF_START: depth++; break;
+            case HJ_OP_LOOP_END: case HJ_OP_IF_END: depth--; break;
+            case HJ_OP_GATHER: rmw_gather = rmw_gather || slots[v.var(v.dep(i, 0)).data].written; break;
+            case HJ_OP_SCATTER: case HJ_OP_SCATTER_REDUCE: case HJ_OP_SCATTER_ATOMIC: case HJ_OP_ATOMIC_INC:
+                return depth == 0 && rmw_gather ? (int)i : -1;
+            default: break;
+            }
+        }
+        return -1;
+    }
+
+    void emit_decls(std::ostream& o, uint32_t array_len) {
+        for (uint32_t i = 0; i < v.n_vars(); i++) {
+            const hj_ir_var& var = v.var(i);
+            uint32_t k = v.type(var.ty).kind;
+            if (k == HJ_VOID || var.op == HJ_OP_BUFFER_REF) continue;
+            o << "    " << tname(var.ty) << " r" << i;
+            if (array_len) o << "[" << array_len << "]";
+            o << ";\n";
+        }
+    }
 
     // address expression of a Gather/Scatter index: the bare Index var addresses LOCAL memory
     // (shard-local element), any computed value is used as is.
@@ -322,15 +359,13 @@ struct Gen {
 
     // staged: element (u,k) of the vector path, gathers/scatters of staged slots go through
     // the in_/out_ register arrays.
-    bool emit_body(std::ostream& o, bool staged) {
+    // [lo, hi): the variables whose statements are emitted (two-phase emission calls it twice, with the
+    // declarations made by the caller)
+    bool emit_body(std::ostream& o, bool staged, uint32_t lo = 0, uint32_t hi = UINT32_MAX, bool decls = true) {
         // declarations first: GLSL-style block scoping would hide loop-carried values
-        for (uint32_t i = 0; i < v.n_vars(); i++) {
-            const hj_ir_var& var = v.var(i);
-            uint32_t k = v.type(var.ty).kind;
-            if (k == HJ_VOID || var.op == HJ_OP_BUFFER_REF) continue;
-            o << "    " << tname(var.ty) << " " << reg(i) << ";\n";
-        }
-        for (uint32_t i = 0; i < v.n_vars(); i++) {
+        if (decls) emit_decls(o, 0);
+        hi = std::min(hi, v.n_vars());
+        for (uint32_t i = lo; i < hi; i++) {
             const hj_ir_var& var = v.var(i);
             const uint32_t ty = var.ty;
             const uint32_t kind = v.type(ty).kind;
@@ -693,9 +728,18 @@ bool codegen_cuda(const hj_ir* ir, CodegenResult* out, std::string* err) {
     if (const char* e = getenv("HJ_JIT_UNROLL")) { int u = atoi(e); if (u >= 1 && u <= 8) unroll = (uint32_t)u; }
     const uint32_t threads = 256;
 
-    std::ostringstream scalar_body, staged_body;
+    std::ostringstream scalar_body, staged_body, staged_decls, staged_tail;
     if (!g.emit_body(scalar_body, false)) { *err = g.err; return false; }
-    if (any_staged && !g.emit_body(staged_body, true)) { *err = g.err; return false; }
+    static const bool no_two_phase = getenv("HJ_NO_TWO_PHASE") != nullptr;
+    const int split = any_staged && !no_two_phase ? g.split_point() : -1;
+    if (split >= 0) {
+        g.suffix = "[e_]";
+        g.emit_decls(staged_decls, vec * unroll);
+        const bool ok = g.emit_body(staged_body, true, 0, (uint32_t)split, false) &&
+                        g.emit_body(staged_tail, true, (uint32_t)split, UINT32_MAX, false);
+        g.suffix.clear();
+        if (!ok) { *err = g.err; return false; }
+    } else if (any_staged && !g.emit_body(staged_body, true)) { *err = g.err; return false; }
 
     std::ostringstream s;
     if (g.uses_f16) s << "#define HJ_USES_F16 1\n";
@@ -749,13 +793,18 @@ bool codegen_cuda(const hj_ir* ir, CodegenResult* out, std::string* err) {
             const char* et = sl.elem_kind == HJ_BOOL ? "u8" : kScalarNames[sl.elem_kind];
             if (sl.stage_load) s << "            in_" << b << "[u] = hj_load_vec<" << et << ", " << vec << ">(b" << b << ", first);\n";
         }
-        s << "        }\n"
-          << "        _Pragma(\"unroll\") for (int u = 0; u < " << unroll << "; u++) {\n"
-          << "            _Pragma(\"unroll\") for (int k = 0; k < " << vec << "; k++) {\n"
-          << "                const u32 index = tile + (u * " << threads << "u + threadIdx.x) * " << vec << "u + k;\n"
-          << "                const u32 gindex = index_base + index;\n"
-          << staged_body.str()
-          << "            }\n        }\n"
+        s << "        }\n" << staged_decls.str();
+        for (const std::ostringstream* part : {&staged_body, &staged_tail}) {
+            if (part == &staged_tail && split < 0) break;
+            s << "        _Pragma(\"unroll\") for (int u = 0; u < " << unroll << "; u++) {\n"
+              << "            _Pragma(\"unroll\") for (int k = 0; k < " << vec << "; k++) {\n"
+              << "                const int e_ = u * " << vec << " + k; (void)e_;\n"
+              << "                const u32 index = tile + (u * " << threads << "u + threadIdx.x) * " << vec << "u + k;\n"
+              << "                const u32 gindex = index_base + index; (void)gindex;\n"
+              << part->str()
+              << "            }\n        }\n";
+        }
+        s
           << "        _Pragma(\"unroll\") for (int u = 0; u < " << unroll << "; u++) {\n"
           << "            const u32 first = tile + (u * " << threads << "u + threadIdx.x) * " << vec << "u;\n";
         for (uint32_t b = 0; b < ir->n_buffers; b++) {

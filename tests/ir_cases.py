@@ -611,6 +611,59 @@ def matrix_product(n=257):
     return Case("matrix_product", b, n, [np.zeros((n, 4), np.float32)], expect={0: want})
 
 
+def rmw_through_index_list(n=3 * 4096 + 517, seed=11):
+    """a[p[i]] = a[p[i]] * 3 + 1 and flags[p[i]] = a[p[i]] > t, p a permutation: the wavefront update
+    (test.rs:1020-1062).  The slot is gathered AND scattered through a computed index: the vector entry
+    runs the gathers of all its elements first (codegen.cpp: split_point); full tiles and a ragged tail."""
+    b = irm.IRBuilder()
+    u32, boolt = b.scalar(I.U32), b.scalar(I.BOOL)
+    ra, rp = b.buffer_ref(u32), b.buffer_ref(u32)
+    idx = b.index()
+    p = b.gather(u32, rp, idx)
+    v = b.bop(I.BOP_ADD, u32, b.bop(I.BOP_MUL, u32, b.gather(u32, ra, p), b.literal(I.U32, 3)), b.literal(I.U32, 1))
+    b.scatter(ra, v, p)
+    b.scatter(b.buffer_ref(boolt), b.bop(I.BOP_GT, boolt, v, b.literal(I.U32, 1 << 31)), p)
+    rng = np.random.Generator(np.random.PCG64(seed))
+    a = rng.integers(0, 2**32, size=n, dtype=np.uint64).astype(np.uint32)
+    perm = rng.permutation(n).astype(np.uint32)
+    want = a * np.uint32(3) + np.uint32(1)
+    return Case("rmw_through_index_list", b, n, [a.copy(), perm, np.zeros(n, np.uint8)],
+                expect={0: want, 2: (want > np.uint32(1 << 31)).astype(np.uint8)})
+
+
+def rmw_then_loop(n=2 * 4096 + 33, seed=12):
+    """A vec3 value and a conditional scatter behind the cut, a recorded loop after it:
+    w = (a[p[i]], a[p[i]] + 1, 2); if a[p[i]] is even: a[p[i]] = w.x + w.y; then k = 0; while k < 3: k += 1;
+    out[i] = k + w.z.  Everything up to the first scatter runs for all elements of a thread first."""
+    b = irm.IRBuilder()
+    i32, boolt = b.scalar(I.I32), b.scalar(I.BOOL)
+    u32 = b.scalar(I.U32)
+    v3 = b.vec(i32, 3)
+    st = b.struct([boolt, i32])
+    ra, rp = b.buffer_ref(i32), b.buffer_ref(u32)
+    idx = b.index()
+    p = b.gather(u32, rp, idx)
+    x = b.gather(i32, ra, p)
+    w = b.push(I.OP_CONSTRUCT, v3, [x, b.bop(I.BOP_ADD, i32, x, b.literal(I.I32, 1)), b.literal(I.I32, 2)])
+    even = b.bop(I.BOP_EQ, boolt, b.bop(I.BOP_AND, i32, x, b.literal(I.I32, 1)), b.literal(I.I32, 0))
+    wx, wy = b.push(I.OP_EXTRACT, i32, [w], arg=0), b.push(I.OP_EXTRACT, i32, [w], arg=1)
+    b.scatter(ra, b.bop(I.BOP_ADD, i32, wx, wy), p, even)
+    s0 = b.push(I.OP_CONSTRUCT, st, [b.literal(I.BOOL, True), b.literal(I.I32, 0)])
+    ls = b.push(I.OP_LOOP_START, st, [s0])
+    k1 = b.push(I.OP_EXTRACT, i32, [ls], arg=1)
+    k2 = b.bop(I.BOP_ADD, i32, k1, b.literal(I.I32, 1))
+    s1 = b.push(I.OP_CONSTRUCT, st, [b.bop(I.BOP_LT, boolt, k2, b.literal(I.I32, 3)), k2])
+    le = b.push(I.OP_LOOP_END, st, [ls, s1])
+    k_out = b.push(I.OP_EXTRACT, i32, [le], arg=1)
+    _out(b, I.I32, b.bop(I.BOP_ADD, i32, k_out, b.push(I.OP_EXTRACT, i32, [w], arg=2)), idx)
+    rng = np.random.Generator(np.random.PCG64(seed))
+    a = rng.integers(-1000, 1000, size=n).astype(np.int32)
+    perm = rng.permutation(n).astype(np.uint32)
+    want = np.where(a % 2 == 0, 2 * a + 1, a).astype(np.int32)
+    return Case("rmw_then_loop", b, n, [a.copy(), perm, np.zeros(n, np.int32)],
+                expect={0: want, 2: np.full(n, 5, np.int32)})
+
+
 SYNTHETIC_CASES = (
     [lambda k=k: binary_ops(k) for k in INT_KINDS + FLOAT_KINDS]
     + [bool_ops]
@@ -622,6 +675,7 @@ SYNTHETIC_CASES = (
        lambda: scatter_reduce_ops(I.I64, I.R_MAX), lambda: scatter_reduce_ops(I.F32, I.R_SUM),
        lambda: scatter_reduce_ops(I.F32, I.R_MAX), lambda: scatter_reduce_ops(I.U32, I.R_SUM, cond=True)]
     + [dyn_size, index_base, c2_chain, mixed_width, in_place_update, vector_ops, matrix_product]
+    + [rmw_through_index_list, rmw_then_loop]
 )
 
 ALL_CASES = REFERENCE_CASES + SYNTHETIC_CASES
