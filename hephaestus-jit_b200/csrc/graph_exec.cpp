@@ -371,6 +371,7 @@ hj_status execute_passes(hj_device* dev, const ShardCtx* sc, const hj_pass* pass
                     else if (slot[b].any_index) snprintf(msg, sizeof(msg), "replica %u is read at Index, the position in the rank's segment", rid);
                 } else if (sc->shards[rid].deferred == HJ_SHARD_SEGMENT) {
                     if (!a.index_only) snprintf(msg, sizeof(msg), "segment %u is addressed through a computed index", rid);
+                    else if (a.written && b != c) born.push_back(b);  // rewritten over THIS segment: its count is this one's now
                 } else if (a.through_segment) {
                     if (descs[rid].size != descs[crid].size)
                         snprintf(msg, sizeof(msg), "sharded resource %u has another extent than the compacted mask", rid);

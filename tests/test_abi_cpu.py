@@ -46,3 +46,21 @@ def test_ir_codegen_and_cubin_work_without_a_gpu():
     cubin = irm.compile_cubin(ir)
     assert cubin[:4] == b"\x7fELF"
     assert irm.ir_hash(ir) == irm.ir_hash(irm.c2_chain_ir().build())  # stable content hash
+
+
+def test_vector_entry_is_cut_in_two_only_for_read_modify_write_through_computed_indices():
+    """codegen.cpp: split_point — a slot that is gathered AND scattered through computed indices makes the vector
+    entry run the part of the element body in front of the first side effect for all elements of a thread first
+    (every variable becomes `rN[e_]`); every other kernel keeps the single loop."""
+    import ir_cases   # tests/ is on sys.path (pytest rootdir conftest)
+    irm = importlib.import_module("hephaestus-jit_b200.ir")
+    cut = {fn().name for fn in ir_cases.ALL_CASES if "[e_]" in irm.codegen(fn().builder.build())}
+    assert cut == {"rmw_through_index_list", "rmw_then_loop"}
+    passes, _ = irm.wavefront_step_passes(1 << 16)
+    mask_update, a_update = (irm.codegen(p["ir"].build()) for p in passes[1:])
+    assert "[e_]" not in mask_update      # `a` is only read there: __ldg loads move freely already
+    assert "[e_]" in a_update
+    body = a_update[a_update.index("hj_kernel_vec"):]
+    assert body.index("((const f32*)b0)[") < body.index("((f32*)b0)[")   # all gathers, then all stores
+    assert body.count("_Pragma(\"unroll\") for (int k = 0;") == 2
+

@@ -601,6 +601,28 @@ def _traced_wavefront(rank, world, dev, comm, n):
     want[sel] = np.arange(sel.size, dtype=np.float32)
     assert int(count.to_vec(np.uint32)[0]) == sel.size
     assert np.array_equal(a.to_vec(np.float32), want[s:e])
+    del count, index, j
+    # a DynSize array written by one launch (aligned with the segment: the rank holds its own part of it) and
+    # consumed, together with the indices, by a later launch
+    lo, hi = np.searchsorted(sel, s), np.searchsorted(sel, e)
+    indices = mask.compress_dyn()
+    vals = a.gather(indices).add(tr.literal(1.0, F32))
+    vals.schedule()
+    indices.schedule()
+    tr.compile().launch(dev)
+    assert vals.is_segment() and indices.is_segment() and vals.shard() == (s, hi - lo, False)
+    assert np.array_equal(vals.to_vec(np.float32), (want[sel] + np.float32(1.0))[lo:hi])
+    vals.mul(tr.literal(2.0, F32)).scatter(a, indices)
+    a.schedule()
+    tr.compile().launch(dev)
+    want[sel] = (want[sel] + np.float32(1.0)) * np.float32(2.0)
+    assert np.array_equal(a.to_vec(np.float32), want[s:e])
+    # device ops do not run over a segment: refused, not computed over the undefined tail
+    bad = vals.reduce_max()
+    bad.schedule()
+    with pytest.raises(hj.HjError, match="compacted segment"):
+        tr.compile().launch(dev)
+    del bad, vals, indices
 
 
 @pytest.mark.parametrize("world", [1, 2, 3])
