@@ -356,6 +356,8 @@ hj_status hj::kernel_launch_shifted(hj_device* dev, hj_kernel* k, size_t size, h
     HJ_REQUIRE(dev && k, "null argument");
     HJ_REQUIRE(n_buffers == k->n_buffers, "kernel expects %u buffers, got %u", k->n_buffers, n_buffers);
     HJ_REQUIRE(size <= 0xffffffffull, "kernel size does not fit the u32 index type (trace.rs:552-562)");
+    HJ_REQUIRE(index_base != 0xffffffffu || (size_buf && size_buf->bytes >= 8),
+               "index_base 0xffffffff reads the base from size_buf[1]: a size buffer of two u32 is needed");
     if (size == 0) return HJ_OK;
     std::vector<void*> ptrs(n_buffers);
     bool aligned = true;

@@ -259,7 +259,9 @@ hj_status hj_kernel_release(hj_kernel* k);
 hj_status hj_ir_compile_cubin(const hj_ir* ir, void** out_cubin, size_t* out_size);
 /* Launch over `size` elements (or the device-resident u32 in `size_buf` if non-NULL,
  * capped by `size`), buffers in IR slot order; replaces the Kernel arm of execute_graph
- * (backend/vulkan/mod.rs:194-257).  `index_base` offsets KernelOp::Index (sharding). */
+ * (backend/vulkan/mod.rs:194-257).  `index_base` offsets KernelOp::Index (sharding); the value
+ * 0xffffffff (never a block start: sizes fit u32) means "read it from size_buf[1]" — `size_buf` must then
+ * hold two u32 (count, base), which is how the sharded pass interpreter runs DynSize kernels per segment. */
 hj_status hj_kernel_launch(hj_device* dev, hj_kernel* k, size_t size, hj_buffer* size_buf,
                            hj_buffer* const* buffers, uint32_t n_buffers, uint32_t index_base);
 /* Out-of-core elementwise map over HOST arrays (pinned memory for full PCIe speed): array i is
