@@ -21,4 +21,6 @@ cap hist hist_ring hist:65536 28 4
 cap hist_fold hist_fold hist:65536 28 4
 cap gather_dram gather4 gather:28 28 4
 cap gather_l2 gather4 gather:20 28 4
+# the two DynSize kernels of the wavefront step (profiles/r02_wavefront.md): launches 2 and 3 of the NVRTC entry
+timeout 300 $NCU --set full --import-source on -k regex:hj_kernel -s 2 -c 2 -o gpurun_out/r02_wavefront python tools/prof_driver.py wavefront 28 3 > gpurun_out/ncu_wavefront.log 2>&1
 ls -la gpurun_out
