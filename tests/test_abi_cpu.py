@@ -2,6 +2,7 @@
 include/hj.h declares, every symbol has a ctypes signature in the host mirror, and the compute entry
 points fail loudly (no CPU fallback) when no CUDA device is present."""
 import ctypes
+import os
 import importlib
 
 import numpy as np
@@ -64,3 +65,23 @@ def test_vector_entry_is_cut_in_two_only_for_read_modify_write_through_computed_
     assert body.index("((const f32*)b0)[") < body.index("((f32*)b0)[")   # all gathers, then all stores
     assert body.count("_Pragma(\"unroll\") for (int k = 0;") == 2
 
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (the CPU arm the driver times beside the GPU arm): one JSON line on stdout, the
+    own arm's metric / unit / config, `cpu_baseline` describing the run and an `e2e` that moved no bytes."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    proc = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1"],
+                          capture_output=True, text=True, timeout=300, cwd=root)
+    assert proc.returncode == 0, proc.stderr[-2000:]
+    lines = [ln for ln in proc.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1, "stdout must carry the JSON line only"
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["unit"] == "GB/s" and d["higher_is_better"] is True and d["n_gpus"] == 1
+    assert d["value"] > 0 and d["cpu_baseline"]["value"] == d["value"] == d["e2e"]["value"]
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["sample"]
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
+    assert "workload" in d["config"] and d["gpu_launches"] == 0
