@@ -352,7 +352,7 @@ class PreparedGraph:
     def segments(self):
         """Per resource: True when it is a per-rank compacted segment after the last launch (``HJ_SHARD_SEGMENT``:
         the index output of a sharded Compress, its seed buffer holds the rank's own count)."""
-        return [self.shards[i].deferred == 2 for i in range(self.n_res)] if self.shards is not None else [False] * self.n_res
+        return [self.shards[i].deferred in (2, 3) for i in range(self.n_res)] if self.shards is not None else [False] * self.n_res
 
     def placement(self):
         return [self.shards[i].placement for i in range(self.n_res)] if self.shards is not None else [0] * self.n_res

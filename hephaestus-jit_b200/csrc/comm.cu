@@ -457,14 +457,15 @@ namespace {
 // count, counts[q] = count of rank q (counts_out, else the communicator's scratch).  With peer memory the
 // exchange of the counts runs inside the compaction kernel (compress.cu: CompressOp::finish).
 hj_status sharded_compress(hj_comm* c, size_t n_local, uint32_t index_base, const uint8_t* mask, uint32_t* index_out,
-                           uint32_t* out_count, uint32_t* counts_out, bool zero_tail) {
+                           uint32_t* out_count, uint32_t* counts_out, bool zero_tail, const uint32_t* size_buf = nullptr) {
+    // size_buf (DynSize: only the first size_buf[0] mask elements of this rank count) takes the unfused path
     uint32_t* counts = counts_out ? counts_out : (uint32_t*)gathered_slot(c);
     if (c->world == 1) {
-        HJ_TRY(launch_compress(c->dev, n_local, nullptr, out_count, mask, index_out, index_base, zero_tail));
+        HJ_TRY(launch_compress(c->dev, n_local, size_buf, out_count, mask, index_out, index_base, zero_tail));
         HJ_CUDA(cudaMemcpyAsync(counts, out_count, 4, cudaMemcpyDeviceToDevice, c->dev->stream));
         return HJ_OK;
     }
-    if (c->p2p && compress_can_fuse_exchange(n_local, mask)) {
+    if (!size_buf && c->p2p && compress_can_fuse_exchange(n_local, mask)) {
         PeerView pv = peer_view(c);
         static const bool zt_kernel = getenv("HJ_ZERO_TAIL_KERNEL") != nullptr;
         const bool zt_in_kernel = zero_tail && ((uintptr_t)index_out & 15u) == 0 && !zt_kernel;
@@ -473,7 +474,7 @@ hj_status sharded_compress(hj_comm* c, size_t n_local, uint32_t index_base, cons
         return HJ_OK;
     }
     // small / misaligned shards, or no peer memory: compaction, then the exchange as its own step
-    HJ_TRY(launch_compress(c->dev, n_local, nullptr, (uint32_t*)local_slot(c), mask, index_out, index_base, zero_tail));
+    HJ_TRY(launch_compress(c->dev, n_local, size_buf, (uint32_t*)local_slot(c), mask, index_out, index_base, zero_tail));
     HJ_TRY(gather_scalars(c, 4));
     offsets_kernel<uint32_t><<<1, 32, 0, c->dev->stream>>>((const uint32_t*)gathered_slot(c), c->rank, c->world, nullptr,
                                                           out_count);
@@ -515,12 +516,13 @@ hj_status exclusive_offset_of_totals(hj_comm* c, hj_type_kind ty, size_t n_local
 
 namespace hj {
 hj_status sharded_compress_pass(hj_comm* c, size_t n_local, uint32_t index_base, hj_buffer* mask, hj_buffer* index_out,
-                                hj_buffer* out_count, bool zero_tail, hj_buffer* local_count) {
+                                hj_buffer* out_count, bool zero_tail, hj_buffer* local_count, hj_buffer* local_size) {
     HJ_REQUIRE(c->connected, "communicator is not connected yet (hj_comm_connect)");
+    HJ_REQUIRE(!local_size || local_size->bytes >= 4, "sharded compress: the local size buffer is smaller than 4 bytes");
     HJ_REQUIRE(!local_count || local_count->bytes >= 8, "sharded compress: the segment's seed buffer is smaller than 8 bytes");
     DeviceGuard g(c->dev);
     HJ_TRY(sharded_compress(c, n_local, index_base, (const uint8_t*)mask->ptr, (uint32_t*)index_out->ptr,
-                            (uint32_t*)out_count->ptr, nullptr, zero_tail));
+                            (uint32_t*)out_count->ptr, nullptr, zero_tail, local_size ? (const uint32_t*)local_size->ptr : nullptr));
     // every path of sharded_compress leaves the per-rank counts in the communicator's scratch
     if (local_count) {
         segment_seed_kernel<<<1, 32, 0, c->dev->stream>>>((const uint32_t*)gathered_slot(c), c->rank, (uint32_t*)local_count->ptr);

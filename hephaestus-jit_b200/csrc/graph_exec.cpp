@@ -237,11 +237,12 @@ void build_seeded_ir(const hj_ir* ir, const std::vector<bool>& deferred, SeededI
 }
 
 bool integer_kind(uint32_t k) { return k >= HJ_I8 && k <= HJ_U64; }
+bool is_segment_state(uint32_t st) { return st == HJ_SHARD_SEGMENT || st == HJ_SHARD_SEGMENT_LOCAL; }
 
 // buf[0 .. n_local) += seed: a deferred scan result becomes an ordinary shard
 hj_status materialise(hj_device* dev, const ShardCtx* sc, uint32_t rid, hj_buffer* buf, const hj_buffer_desc& d) {
     hj_shard_desc& sd = sc->shards[rid];
-    if (sd.deferred == HJ_SHARD_SEGMENT)
+    if (is_segment_state(sd.deferred))
         return fail(HJ_ERR_UNSUPPORTED, "resource %u is a per-rank compacted segment: only DynSize kernels sized by its count "
                     "run over it (SURVEY 8e; re-balance it into a block-sharded array first: hj_sharded_rebalance)", rid);
     if (sd.deferred != HJ_SHARD_DEFERRED) return HJ_OK;
@@ -354,9 +355,12 @@ hj_status execute_passes(hj_device* dev, const ShardCtx* sc, const hj_pass* pass
         std::vector<uint32_t> born;  // slots written at Index for the first time: aligned with the segment from now on
         for (uint32_t c = 0; c < p.n_resources && seg_slot == p.n_resources; c++) {
             const uint32_t crid = p.resources[c];
-            if (!sharded(crid) || sc->shards[crid].deferred != HJ_SHARD_SEGMENT || !sc->shards[crid].seed ||
+            if (!sharded(crid) || !is_segment_state(sc->shards[crid].deferred) || !sc->shards[crid].seed ||
                 sc->shards[crid].seed->bytes < 8 || descs[crid].ty != HJ_U32 || descs[crid].size != p.size)
                 continue;
+            // entries of a LOCAL segment are positions in the rank's part of its parent sequence: what is reached
+            // through them must itself be a segment (bound as it is), not a block of a sharded array
+            const bool local_positions = sc->shards[crid].deferred == HJ_SHARD_SEGMENT_LOCAL;
             if (!analyse_segment_access(p.ir, c, &acc, &why)) continue;
             bool ok = true;
             std::fill(shift.begin(), shift.end(), 0);
@@ -369,11 +373,16 @@ hj_status execute_passes(hj_device* dev, const ShardCtx* sc, const hj_pass* pass
                 if (!sharded(rid)) {
                     if (a.written) snprintf(msg, sizeof(msg), "resource %u, a replica, is written", rid);
                     else if (slot[b].any_index) snprintf(msg, sizeof(msg), "replica %u is read at Index, the position in the rank's segment", rid);
-                } else if (sc->shards[rid].deferred == HJ_SHARD_SEGMENT) {
-                    if (!a.index_only) snprintf(msg, sizeof(msg), "segment %u is addressed through a computed index", rid);
-                    else if (a.written && b != c) born.push_back(b);  // rewritten over THIS segment: its count is this one's now
+                } else if (is_segment_state(sc->shards[rid].deferred)) {
+                    if (a.index_only) {
+                        if (a.written && b != c) born.push_back(b);  // rewritten over THIS segment: its count is this one's now
+                    } else if (!(local_positions && a.through_segment && descs[rid].size == descs[crid].size)) {
+                        snprintf(msg, sizeof(msg), "segment %u is addressed through a computed index", rid);
+                    }
                 } else if (a.through_segment) {
-                    if (descs[rid].size != descs[crid].size)
+                    if (local_positions)
+                        snprintf(msg, sizeof(msg), "resource %u, a block of a sharded array, is addressed through positions in a segment", rid);
+                    else if (descs[rid].size != descs[crid].size)
                         snprintf(msg, sizeof(msg), "sharded resource %u has another extent than the compacted mask", rid);
                 } else if (a.index_only && !a.read) {
                     if (descs[rid].size != p.size) snprintf(msg, sizeof(msg), "resource %u written at Index has another extent", rid);
@@ -397,7 +406,7 @@ hj_status execute_passes(hj_device* dev, const ShardCtx* sc, const hj_pass* pass
         HJ_TRY(local_of(seg_rid, &s0, &cnt));
         for (uint32_t b = 0; b < p.n_resources; b++) {
             const uint32_t rid = p.resources[b];
-            if (!sharded(rid) || sc->shards[rid].deferred == HJ_SHARD_SEGMENT || !(acc[b].read || acc[b].written)) continue;
+            if (!sharded(rid) || is_segment_state(sc->shards[rid].deferred) || !(acc[b].read || acc[b].written)) continue;
             if (acc[b].through_segment) {
                 HJ_TRY(materialise(dev, sc, rid, bufs[b], descs[rid]));  // a deferred scan result is written / gathered in place
                 HJ_REQUIRE(cnt * descs[rid].elem_bytes <= bufs[b]->bytes, "kernel pass %u: resource %u is smaller than the rank's block", i, rid);
@@ -566,7 +575,7 @@ hj_status execute_passes(hj_device* dev, const ShardCtx* sc, const hj_pass* pass
                         return fail(HJ_ERR_UNSUPPORTED, "kernel pass %u addresses sharded resource %u through a computed index "
                                     "or with another extent: only Index-addressed access shards (SURVEY 8e)", i, rid);
                     HJ_TRY(local_of(rid, &s0, &cnt));
-                    if (sc->shards[rid].deferred == HJ_SHARD_SEGMENT) {
+                    if (is_segment_state(sc->shards[rid].deferred)) {
                         // overwriting a segment (the index zero-fill in front of the next Compress) makes it a block again
                         if (access[b].read) HJ_TRY(materialise(dev, sc, rid, bufs[b], descs[rid]));  // fails, naming the resource
                         sc->shards[rid].deferred = HJ_SHARD_PLAIN;
@@ -655,18 +664,30 @@ hj_status execute_passes(hj_device* dev, const ShardCtx* sc, const hj_pass* pass
             if (sharded(p.resources[2])) {
                 HJ_REQUIRE(sharded(p.resources[0]) && !sharded(p.resources[1]),
                            "compress pass %u: the index segment of a sharded mask is sharded, the count a replica", i);
-                HJ_REQUIRE(!size_buf, "compress pass %u: DynSize over a sharded mask is not supported", i);
                 uint64_t s0, cnt;
                 HJ_TRY(local_of(p.resources[2], &s0, &cnt));
                 HJ_REQUIRE(cnt <= src->bytes && cnt * 4 <= index_out->bytes && out_count->bytes >= 4,
                            "compress pass %u: buffer sizes do not match the %llu-element shard", i, (unsigned long long)cnt);
-                HJ_REQUIRE(sc->shards[p.resources[2]].deferred != HJ_SHARD_SEGMENT,
-                           "compress pass %u: the mask is a per-rank segment, not a block of a sharded array", i);
                 // the rank's own count stays beside the segment: it sizes the DynSize kernels that run over it
                 hj_shard_desc& seg = sc->shards[p.resources[0]];
+                const hj_shard_desc& msk = sc->shards[p.resources[2]];
                 hj_buffer* seg_seed = seg.seed && seg.seed->bytes >= 8 ? seg.seed : nullptr;
-                HJ_TRY(sharded_compress_pass(sc->comm, (size_t)cnt, (uint32_t)s0, src, index_out, out_count, zt, seg_seed));
-                seg.deferred = seg_seed ? HJ_SHARD_SEGMENT : HJ_SHARD_PLAIN;
+                if (size_buf) {
+                    // nested compaction (jit/test.rs:976-1019): the mask is aligned with a segment and only its first
+                    // seed[0] elements on this rank count.  The result holds positions in the RANK's part of the
+                    // parent sequence (index_base 0): they address the rank's segments in place.
+                    HJ_REQUIRE(msk.deferred == HJ_SHARD_SEGMENT && msk.seed && msk.seed->bytes >= 8,
+                               "compress pass %u: a DynSize Compress over sharded data needs a mask that is aligned with a "
+                               "compacted segment and carries its count", i);
+                    snprintf(name, sizeof(name), "Compress Large (segment)");
+                    HJ_TRY(sharded_compress_pass(sc->comm, (size_t)cnt, 0u, src, index_out, out_count, zt, seg_seed, msk.seed));
+                    seg.deferred = seg_seed ? HJ_SHARD_SEGMENT_LOCAL : HJ_SHARD_PLAIN;
+                } else {
+                    HJ_REQUIRE(!is_segment_state(msk.deferred),
+                               "compress pass %u: the mask is a per-rank segment, not a block of a sharded array", i);
+                    HJ_TRY(sharded_compress_pass(sc->comm, (size_t)cnt, (uint32_t)s0, src, index_out, out_count, zt, seg_seed));
+                    seg.deferred = seg_seed ? HJ_SHARD_SEGMENT : HJ_SHARD_PLAIN;
+                }
             } else if (zt) {
                 const size_t n = dsrc->size;
                 HJ_REQUIRE(n >= 1 && n <= src->bytes && n * 4 <= index_out->bytes && out_count->bytes >= 4 &&
@@ -789,7 +810,7 @@ extern "C" hj_status hj_shard_plan(const hj_pass* passes, uint32_t n_passes, con
                     for (uint32_t c = 0; c < p.n_resources; c++) {
                         const uint32_t crid = p.resources[c];
                         const bool from_compress = count_of_index[crid] == (int64_t)p.size_buffer;
-                        if (!is(crid, HJ_RES_SHARDED) || !(from_compress || shards[crid].deferred == HJ_SHARD_SEGMENT) ||
+                        if (!is(crid, HJ_RES_SHARDED) || !(from_compress || is_segment_state(shards[crid].deferred)) ||
                             descs[crid].ty != HJ_U32 || descs[crid].size != p.size)
                             continue;
                         std::vector<SegmentAccess> acc;

@@ -201,8 +201,10 @@ hj_status launch_fill(hj_device* dev, void* dst, size_t n, size_t elem_bytes, ui
 hj_device* comm_device(hj_comm* c);
 // `local_count` (optional, >= 8 bytes): receives this rank's own count and the counts of the ranks before it
 // (what sizes the DynSize kernels that run over the rank's segment, and their KernelOp::Index)
+// `local_size` (optional): DynSize — only the first local_size[0] mask elements of this rank are compacted
 hj_status sharded_compress_pass(hj_comm* c, size_t n_local, uint32_t index_base, hj_buffer* mask, hj_buffer* index_out,
-                                hj_buffer* out_count, bool zero_tail, hj_buffer* local_count = nullptr);
+                                hj_buffer* out_count, bool zero_tail, hj_buffer* local_count = nullptr,
+                                hj_buffer* local_size = nullptr);
 
 // cudaFuncSetAttribute(MaxDynamicSharedMemorySize) once per (device, kernel, size) instead of on every
 // launch (a driver call of a few microseconds on the relaunch path).  Device lock held by the caller.

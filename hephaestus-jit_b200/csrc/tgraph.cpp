@@ -361,7 +361,8 @@ hj_buffer* create_buffer(hj_device* dev, const BufferDesc& d) {  // Resource::cr
     return b;
 }
 uint32_t shard_state(const Var& v) {  // hj_shard_desc.deferred of the variable's buffer
-    return v.data.segment ? HJ_SHARD_SEGMENT : v.data.deferred ? HJ_SHARD_DEFERRED : HJ_SHARD_PLAIN;
+    if (v.data.segment) return v.data.segment_local ? HJ_SHARD_SEGMENT_LOCAL : HJ_SHARD_SEGMENT;
+    return v.data.deferred ? HJ_SHARD_DEFERRED : HJ_SHARD_PLAIN;
 }
 uint32_t scalar_kind(TypeId t) {
     TypeNode n = type_node(t);
@@ -630,7 +631,8 @@ void launch_graph(const Graph& g, hj_device* dev, const std::vector<VarId>& inpu
             if (comm && shards[rid].placement == HJ_RES_SHARDED) {
                 r.comm = comm;
                 r.deferred = shards[rid].deferred == HJ_SHARD_DEFERRED;
-                r.segment = shards[rid].deferred == HJ_SHARD_SEGMENT;
+                r.segment = shards[rid].deferred == HJ_SHARD_SEGMENT || shards[rid].deferred == HJ_SHARD_SEGMENT_LOCAL;
+                r.segment_local = shards[rid].deferred == HJ_SHARD_SEGMENT_LOCAL;
                 r.seed = r.deferred || r.segment ? shards[rid].seed : nullptr;
                 if (r.seed && seed_from_cache[rid] && rid < g.seed_cache.size() && g.seed_cache[rid] == r.seed) {
                     // the value outlives this launch inside a variable: the next launch needs a seed of its own

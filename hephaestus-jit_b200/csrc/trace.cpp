@@ -430,6 +430,7 @@ ShardInfo shard_info(VarId id) {
         comm = v.data.kind == Resource::Buffer ? v.data.comm : nullptr;
         si.deferred = v.data.deferred;
         si.segment = v.data.segment;
+        si.segment_local = v.data.segment_local;
         n = v.extent.n;
         if (comm && si.segment && v.extent.dynamic) {  // a static `compress` index keeps its capacity and zero tail
             seed = v.data.seed;

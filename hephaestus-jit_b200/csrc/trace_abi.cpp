@@ -117,7 +117,8 @@ hj_status hj_tr_var_shard(uint64_t v, int32_t* sharded, uint64_t* start, uint64_
         if (sharded) *sharded = si.sharded;
         if (start) *start = si.start;
         if (count) *count = si.count;
-        if (deferred) *deferred = si.segment ? (int32_t)HJ_SHARD_SEGMENT : si.deferred ? (int32_t)HJ_SHARD_DEFERRED : 0;
+        if (deferred)
+            *deferred = si.segment ? (int32_t)(si.segment_local ? HJ_SHARD_SEGMENT_LOCAL : HJ_SHARD_SEGMENT) : si.deferred ? (int32_t)HJ_SHARD_DEFERRED : 0;
     });
 }
 hj_status hj_tr_materialise(uint64_t v) {

@@ -31,6 +31,7 @@ struct Resource {
     hj_comm* comm = nullptr;
     bool deferred = false;
     bool segment = false;
+    bool segment_local = false;  // ... whose entries are positions in the rank's part of the parent sequence (HJ_SHARD_SEGMENT_LOCAL)
     hj_buffer* seed = nullptr;
 };
 
@@ -106,7 +107,7 @@ VarId from_buffer(hj_buffer* buf, TypeId ty, size_t n);
 VarId array_sharded(hj_comm* comm, TypeId ty, const void* local_data, size_t n_global);
 VarId from_buffer_sharded(hj_comm* comm, hj_buffer* local_buf, TypeId ty, size_t n_global);
 // `count`: elements of the rank's block — for a DynSize segment the rank's own count (read from the device)
-struct ShardInfo { bool sharded = false, deferred = false, segment = false; uint64_t start = 0, count = 0; };
+struct ShardInfo { bool sharded = false, deferred = false, segment = false, segment_local = false; uint64_t start = 0, count = 0; };
 ShardInfo shard_info(VarId id);
 void materialise(VarId id);  // a deferred scan result becomes an ordinary shard (buf[i] += seed)
 VarId bop(uint32_t op, VarId a, VarId b);

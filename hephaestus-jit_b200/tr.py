@@ -356,7 +356,7 @@ class VarRef:
         """True when the buffer is this rank's segment of a compacted sequence (``HJ_SHARD_SEGMENT``)."""
         sharded, deferred = ctypes.c_int32(), ctypes.c_int32()
         check(lib.hj_tr_var_shard(self._id, ctypes.byref(sharded), None, None, ctypes.byref(deferred)))
-        return bool(sharded.value) and deferred.value == 2
+        return bool(sharded.value) and deferred.value in (2, 3)
 
     def materialise(self) -> None:
         """Adds the offset of a deferred scan result on the device (``hj_tr_materialise``)."""

@@ -438,10 +438,15 @@ typedef enum { HJ_RES_REPLICATED = 0, HJ_RES_SHARDED = 1, HJ_RES_AUTO = 2 } hj_p
 #define HJ_SHARD_SEGMENT 2u  /* a per-rank compacted SEGMENT (Compress index output, or what a DynSize
                                 kernel wrote at Index): only the first seed[0] (u32) entries are defined;
                                 seed[1] (u32) = entries of the ranks before this one */
+#define HJ_SHARD_SEGMENT_LOCAL 3u /* the index output of a DynSize Compress over a segment-aligned mask (nested
+                                     compaction, jit/test.rs:976-1019): a segment whose entries are positions in
+                                     the RANK's part of the parent sequence — they address the rank's segments in
+                                     place; on one GPU the same entries are positions in the whole parent sequence
+                                     (= these + the parent's seed[1]) */
 typedef struct {
     uint32_t placement; /* hj_placement.  SHARDED: the buffer holds this rank's block
                            [start, end) = hj_shard_bounds(descs[i].size, world, rank) of the global array */
-    uint32_t deferred;  /* in / out, SHARDED resources: HJ_SHARD_PLAIN / _DEFERRED / _SEGMENT */
+    uint32_t deferred;  /* in / out, SHARDED resources: HJ_SHARD_PLAIN / _DEFERRED / _SEGMENT / _SEGMENT_LOCAL */
     hj_buffer* seed;    /* >= 8 bytes (one element of the resource's type for a scan; two u32 for a segment) on the device, or
                            NULL (then PrefixSum results are always materialised and a Compress index
                            segment cannot size dependent DynSize kernels) */

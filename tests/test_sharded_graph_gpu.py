@@ -625,6 +625,41 @@ def _traced_wavefront(rank, world, dev, comm, n):
     del bad, vals, indices
 
 
+def _traced_nested_compaction(rank, world, dev, comm, n):
+    """jit/test.rs:976-1019 (`dynamic_index`) over a sharded array: compact, gather, compact the gathered values
+    again, gather through the second indices.  The second Compress is DynSize (its mask is aligned with the first
+    segment); its indices are positions in the rank's part of the first sequence and address the rank's segments
+    in place.  Every rank ends up with its part of the result, in order."""
+    tr = importlib.import_module("hephaestus-jit_b200.tr")
+    sh = importlib.import_module("hephaestus-jit_b200.sharded")
+    I32 = hj.I32
+    s, e = sh.shard_bounds(n, world, rank)
+    lo, hi = 3, 7
+    for seed in (13, 14):
+        src = np.random.Generator(np.random.PCG64(seed)).integers(0, 10, size=n).astype(np.int32)
+        src_var = tr.array_sharded(src, comm)
+        indices = src_var.lt(tr.literal(hi, I32)).compress_dyn()
+        values = src_var.gather(indices)
+        indices2 = values.gt(tr.literal(lo, I32)).compress_dyn()
+        values2 = values.gather(indices2)
+        values2.schedule()
+        indices2.schedule()
+        tr.compile().launch(dev)
+        mine = src[s:e]
+        first = mine[mine < hi]                      # the rank's part of the first compacted sequence
+        want = first[first > lo]
+        assert values2.is_segment() and values2.shard() == (s, want.size, False)
+        assert np.array_equal(values2.to_vec(np.int32), want)
+        assert indices2.is_segment()
+        assert np.array_equal(indices2.to_vec(np.uint32), np.flatnonzero(first > lo).astype(np.uint32))   # rank-local positions
+        del src_var, indices, values, indices2, values2
+
+
+@pytest.mark.parametrize("world", [1, 2, 3])
+def test_nested_compaction_over_sharded_arrays(world):
+    _run(world, "_traced_nested_compaction", (1 << 17) + 9)
+
+
 @pytest.mark.parametrize("world", [1, 2, 3])
 def test_wavefront_pass_list_runs_per_segment(world):
     _run(world, "_wavefront_pass_list", (1 << 18) + 33)
