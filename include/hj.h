@@ -425,7 +425,9 @@ hj_status hj_sharded_rebalance(hj_comm* comm, size_t elem_bytes, hj_buffer* src,
  *                                  ITS segment, sized by its own count on the device; the segment's indices
  *                                  are global and fall into the rank's block by construction, so sharded
  *                                  arrays of the mask's extent are addressed through them in place.  Needs
- *                                  a seed buffer on the index segment (it receives the rank's count).
+ *                                  a seed buffer on the index segment (it receives the rank's count).  A
+ *                                  DynSize Compress whose mask is aligned with a segment (nested compaction)
+ *                                  compacts the rank's part: HJ_SHARD_SEGMENT_LOCAL.
  * Not sharded (SURVEY 8e "replicas only"): access to a sharded resource through any other computed
  * index, writes to a replica from a sharded kernel, a replica read at the bare Index inside a segment
  * kernel, device ops over a segment -> HJ_ERR_UNSUPPORTED.  (KernelOp::Index as a VALUE inside a segment
