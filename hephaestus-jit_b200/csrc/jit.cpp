@@ -364,7 +364,7 @@ hj_status hj::kernel_launch_shifted(hj_device* dev, hj_kernel* k, size_t size, h
     for (uint32_t i = 0; i < n_buffers; i++) {
         HJ_REQUIRE(buffers && buffers[i], "buffer %u is null", i);
         const uint64_t shift = shift_bytes ? shift_bytes[i] : 0;
-        ptrs[i] = (char*)buffers[i]->ptr - shift;
+        ptrs[i] = (void*)((uintptr_t)buffers[i]->ptr - (uintptr_t)shift);  // an address, not a pointer into the allocation
         // a shifted slot is only ever addressed through computed indices: no vector access touches it
         if (!shift && ((uintptr_t)ptrs[i] & 15u)) aligned = false;
     }
