@@ -330,11 +330,25 @@ struct Gen {
             case HJ_OP_LOOP_END: case HJ_OP_IF_END: depth--; break;
             case HJ_OP_GATHER: rmw_gather = rmw_gather || slots[v.var(v.dep(i, 0)).data].written; break;
             case HJ_OP_SCATTER: case HJ_OP_SCATTER_REDUCE: case HJ_OP_SCATTER_ATOMIC: case HJ_OP_ATOMIC_INC:
-                return depth == 0 && rmw_gather ? (int)i : -1;
+                return depth == 0 && rmw_gather && live_across(i) <= 12 ? (int)i : -1;
             default: break;
             }
         }
         return -1;
+    }
+    // 32-bit words per element that are computed in front of `cut` and used behind it: the two-phase entry
+    // keeps them for every element of the thread (16), so a wide cut would spill
+    uint32_t live_across(uint32_t cut) {
+        std::set<uint32_t> live;
+        for (uint32_t i = cut; i < v.n_vars(); i++)
+            for (uint32_t k = 0; k < v.n_deps(i); k++) {
+                const uint32_t d = v.dep(i, k);
+                const uint32_t op = v.var(d).op;
+                if (d < cut && op != HJ_OP_LITERAL && op != HJ_OP_BUFFER_REF && op != HJ_OP_INDEX) live.insert(d);
+            }
+        uint32_t words = 0;
+        for (uint32_t d : live) words += (uint32_t)((type_size(v, v.var_type(d)) + 3) / 4);
+        return words;
     }
 
     void emit_decls(std::ostream& o, uint32_t array_len) {
