@@ -183,6 +183,43 @@ def test_shard_plan_places_the_wavefront_step():
     assert sharded.shard_plan(passes, descs, [A, S, A, A]) == [R, S, S, R]
 
 
+def test_shard_plan_places_a_nested_compaction():
+    """jit/test.rs:976-1019 (`dynamic_index`) as a pass list: compact, gather, compact the gathered values again
+    (a DynSize Compress whose mask is aligned with the first segment), gather through the second indices.
+    Everything that lives per compacted sequence is per rank; the two counts are replicas."""
+    hj = importlib.import_module("hephaestus-jit_b200")
+    irm = importlib.import_module("hephaestus-jit_b200.ir")
+    S, R, A = sharded.RES_SHARDED, sharded.RES_REPLICATED, sharded.RES_AUTO
+    n = 1 << 14
+
+    def through(write_mask):   # out[i] = src[idx[i]]  (or out[i] = src[idx[i]] > 3)
+        b = irm.IRBuilder()
+        i32, u32, bl = b.scalar(hj.I32), b.scalar(hj.U32), b.scalar(hj.BOOL)
+        rsrc, ridx = b.buffer_ref(i32), b.buffer_ref(u32)
+        i = b.index()
+        t = b.literal(hj.BOOL, 1)
+        v = b.gather(i32, rsrc, b.gather(u32, ridx, i, t), t)
+        if write_mask:
+            b.scatter(b.buffer_ref(bl), b.bop(irm.BOP_GT, bl, v, b.literal(hj.I32, 3)), i)
+        else:
+            b.scatter(b.buffer_ref(i32), v, i)
+        return b
+
+    # resources: 0 count1, 1 src, 2 idx1, 3 mask1, 4 mask2, 5 count2, 6 idx2, 7 values1, 8 values2
+    passes = [
+        {"kind": hj.PASS_COMPRESS, "resources": [2, 0, 3]},
+        {"kind": hj.PASS_KERNEL, "resources": [1, 2, 4], "ir": through(True), "size": n, "size_buffer": 0},
+        {"kind": hj.PASS_COMPRESS, "resources": [6, 5, 4], "size_buffer": 0},
+        {"kind": hj.PASS_KERNEL, "resources": [1, 2, 7], "ir": through(False), "size": n, "size_buffer": 0},
+        {"kind": hj.PASS_KERNEL, "resources": [7, 6, 8], "ir": through(False), "size": n, "size_buffer": 5},
+    ]
+    descs = [(1, hj.U32, 4), (n, hj.I32, 4), (n, hj.U32, 4), (n, hj.BOOL, 1), (n, hj.BOOL, 1), (1, hj.U32, 4),
+             (n, hj.U32, 4), (n, hj.I32, 4), (n, hj.I32, 4)]
+    got = sharded.shard_plan(passes, descs, [A, S, A, S, A, A, A, A, A])
+    assert got == [R, S, S, S, S, R, S, S, S]
+    assert sharded.shard_plan(passes, descs, [A] * 9) == [R] * 9
+
+
 def test_shard_plan_rejects_malformed_pass_lists():
     hj = importlib.import_module("hephaestus-jit_b200")
     passes, descs = _c2_like_passes(1 << 12)
